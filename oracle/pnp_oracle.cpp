@@ -1,0 +1,519 @@
+// ============================================================================
+// oracle/pnp_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU fp64 restatement of MonoRUn's native uncertainty-PnP op, used only as the
+// parity checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs.  Nothing under monorun_b200/ may import, link or call it.
+//
+// PARITY UNPINNED for the solver control flow: the reference links ceres-solver
+// 1.14.0 (INSTALL.md:13,29-30; monorun/ops/least_squares/setup.py:20-22), which is
+// neither vendored in /root/reference nor installable here (no Ceres/Eigen/glog, no
+// network), and the reference ships no tests or golden vectors for this path.  The
+// trust-region Levenberg-Marquardt loop below restates the published algorithm of
+// Ceres 1.14 (TrustRegionMinimizer + LevenbergMarquardtStrategy + DenseQRSolver with
+// default Solver::Options) from knowledge of the upstream source.  What IS pinned:
+//   * the residual / clip semantics follow the reference functor line by line
+//     (monorun/ops/least_squares/src/pnp_uncert_cpu.cpp:24-51 diag weights,
+//      :189-217 full 2x2 weights restricted to the 4 pose parameters);
+//   * the pipeline covariance H = J^T J is checked against the reference's own
+//     pure-torch approx_hessian (monorun/ops/least_squares/hessian.py:67-87,
+//     jacobian.py:4-98), imported from /root/reference by tests/golden/make_golden.py;
+//   * the minimiser itself is cross-checked against scipy.optimize.least_squares.
+//
+// C ABI: `pnp_uncert` has exactly the signature of
+// monorun/ops/least_squares/src/ext.h:1-13 so the restated Python driver
+// (oracle/pnp_driver.py) binds it the way pnp_uncert_cpu.py:102-106 does.
+// ============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// Default ceres::Solver::Options of 1.14 that the reference leaves untouched
+// (pnp_uncert_cpu.cpp:270-271 only sets linear_solver_type = DENSE_QR).
+struct LMOptions {
+    int max_num_iterations = 50;
+    double function_tolerance = 1e-6;
+    double gradient_tolerance = 1e-10;
+    double parameter_tolerance = 1e-8;
+    double initial_trust_region_radius = 1e4;
+    double max_trust_region_radius = 1e16;
+    double min_trust_region_radius = 1e-32;
+    double min_relative_decrease = 1e-3;
+    double min_lm_diagonal = 1e-6;
+    double max_lm_diagonal = 1e32;
+    int max_num_consecutive_invalid_steps = 5;
+    // 0: Ceres 1.14 behaviour -- on the function-tolerance exit the candidate point is
+    //    NOT adopted (TrustRegionMinimizer::Minimize returns before HandleSuccessfulStep).
+    // 1: adopt the candidate on that exit when it lowers the cost (documented switch,
+    //    SURVEY.md section 7 "hard parts").
+    int adopt_candidate_on_ftol = 0;
+};
+
+enum Termination { CONVERGENCE = 0, NO_CONVERGENCE = 1, FAILURE = 2 };
+
+struct Problem {
+    const double* pts2d;  // n,2
+    const double* pts3d;  // n,3
+    const double* wgt2d;  // n,2 (diag) or n,3 (full: wxx,wxy,wyy)
+    int pn;
+    bool full_w;
+    double fx, fy, cx, cy;
+    double z_min, u_min, u_max, v_min, v_max;
+};
+
+// One reprojection block, Ceres-Jet semantics (pnp_uncert_cpu.cpp:24-51 / :189-217):
+// value and derivative follow the *selected branch* of max() / the ternary clamps, so a
+// clipped depth keeps d(u)/d(x') but drops d(u)/d(z'), and a clamped u/v has zero derivative.
+// jac: 2x4 row-major, columns [yaw, tx, ty, tz]; may be NULL.
+inline void eval_point(const Problem& P, int i, double yaw_s, double yaw_c, const double* t,
+                       double* r, double* jac) {
+    const double X = P.pts3d[i * 3], Y = P.pts3d[i * 3 + 1], Z = P.pts3d[i * 3 + 2];
+    // ceres::AngleAxisRotatePoint((0,yaw,0), X) == R_y(yaw) X   (pnp_uncert_cpu.cpp:28-31)
+    const double qx = yaw_c * X + yaw_s * Z;
+    const double qz = -yaw_s * X + yaw_c * Z;
+    const double xc = qx + t[0], yc = Y + t[1], zc = qz + t[2];  // :32-34
+    const bool z_free = !(zc < P.z_min);                          // :36  max(z, z_min)
+    const double z = z_free ? zc : P.z_min;
+    const double iz = 1.0 / z;
+    double pu = P.fx * xc * iz + P.cx;                            // :38
+    double pv = P.fy * yc * iz + P.cy;                            // :39
+    bool u_free = true, v_free = true;
+    if (pu < P.u_min) { pu = P.u_min; u_free = false; }           // :41
+    else if (pu > P.u_max) { pu = P.u_max; u_free = false; }
+    if (pv < P.v_min) { pv = P.v_min; v_free = false; }           // :42
+    else if (pv > P.v_max) { pv = P.v_max; v_free = false; }
+    const double du = pu - P.pts2d[i * 2], dv = pv - P.pts2d[i * 2 + 1];  // :44-45
+    double w00, w01, w11;
+    if (P.full_w) {                                               // :214-215
+        w00 = P.wgt2d[i * 3]; w01 = P.wgt2d[i * 3 + 1]; w11 = P.wgt2d[i * 3 + 2];
+    } else {                                                      // :47-48
+        w00 = P.wgt2d[i * 2]; w01 = 0.0; w11 = P.wgt2d[i * 2 + 1];
+    }
+    r[0] = w00 * du + w01 * dv;
+    r[1] = w01 * du + w11 * dv;
+    if (jac) {
+        // d(x',y',z')/d(yaw) = (qz, 0, -qx); d/dt = I
+        const double mz = z_free ? 1.0 : 0.0;
+        double ju[4] = {0, 0, 0, 0}, jv[4] = {0, 0, 0, 0};
+        if (u_free) {
+            const double a = P.fx * iz, b = -P.fx * xc * iz * iz * mz;  // d/dx', d/dz'
+            ju[0] = a * qz + b * (-qx); ju[1] = a; ju[2] = 0.0; ju[3] = b;
+        }
+        if (v_free) {
+            const double a = P.fy * iz, b = -P.fy * yc * iz * iz * mz;
+            jv[0] = b * (-qx); jv[1] = 0.0; jv[2] = a; jv[3] = b;
+        }
+        for (int k = 0; k < 4; ++k) {
+            jac[k] = w00 * ju[k] + w01 * jv[k];
+            jac[4 + k] = w01 * ju[k] + w11 * jv[k];
+        }
+    }
+}
+
+// Evaluator::Evaluate: cost = 1/2 |r|^2, residuals (2n), jacobian (2n x 4 row-major),
+// gradient = J^T r.  Returns false when anything is non-finite (Ceres rejects such
+// evaluations: ResidualBlock::Evaluate -> IsEvaluationValid).
+bool evaluate(const Problem& P, const double* x, double* cost, double* res, double* jac,
+              double* grad) {
+    const double s = std::sin(x[0]), c = std::cos(x[0]);
+    double acc = 0.0;
+    double g[4] = {0, 0, 0, 0};
+    double rr[2], jj[8];
+    bool ok = true;
+    for (int i = 0; i < P.pn; ++i) {
+        eval_point(P, i, s, c, x + 1, rr, jac ? jj : nullptr);
+        acc += rr[0] * rr[0] + rr[1] * rr[1];
+        if (res) { res[2 * i] = rr[0]; res[2 * i + 1] = rr[1]; }
+        if (jac) {
+            std::memcpy(jac + 8 * i, jj, sizeof(jj));
+            for (int k = 0; k < 4; ++k) {
+                g[k] += jj[k] * rr[0] + jj[4 + k] * rr[1];
+                ok = ok && std::isfinite(jj[k]) && std::isfinite(jj[4 + k]);
+            }
+        }
+    }
+    *cost = 0.5 * acc;
+    if (grad) std::memcpy(grad, g, sizeof(g));
+    return ok && std::isfinite(acc);
+}
+
+// DenseQRSolver::SolveImpl (Ceres 1.14): least squares  min |[A; diag(D)] y - [b; 0]|
+// by unpivoted Householder QR (Eigen householderQr().solve()).  A is m x 4 row-major,
+// already column-scaled.  Returns false if y is not finite.
+bool dense_qr_solve(const double* A, const double* b, const double* D, int m, double* y,
+                    std::vector<double>& work) {
+    const int n = 4, M = m + n;
+    work.resize(static_cast<size_t>(M) * (n + 1));
+    double* W = work.data();  // M x (n+1): augmented [A | b ; D | 0]
+    for (int i = 0; i < m; ++i) {
+        for (int k = 0; k < n; ++k) W[i * (n + 1) + k] = A[i * n + k];
+        W[i * (n + 1) + n] = b[i];
+    }
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k <= n; ++k) W[(m + i) * (n + 1) + k] = 0.0;
+        W[(m + i) * (n + 1) + i] = D[i];
+    }
+    for (int k = 0; k < n; ++k) {
+        double tail = 0.0;
+        for (int i = k + 1; i < M; ++i) tail += W[i * (n + 1) + k] * W[i * (n + 1) + k];
+        const double c0 = W[k * (n + 1) + k];
+        if (tail <= std::numeric_limits<double>::min()) continue;  // column already triangular
+        double beta = std::sqrt(c0 * c0 + tail);
+        if (c0 >= 0) beta = -beta;
+        // v = [1; essential], essential = x_tail / (c0 - beta), tau = (beta - c0) / beta
+        const double inv = 1.0 / (c0 - beta), tau = (beta - c0) / beta;
+        for (int i = k + 1; i < M; ++i) W[i * (n + 1) + k] *= inv;
+        W[k * (n + 1) + k] = beta;
+        for (int col = k + 1; col <= n; ++col) {
+            double dot = W[k * (n + 1) + col];
+            for (int i = k + 1; i < M; ++i) dot += W[i * (n + 1) + k] * W[i * (n + 1) + col];
+            dot *= tau;
+            W[k * (n + 1) + col] -= dot;
+            for (int i = k + 1; i < M; ++i) W[i * (n + 1) + col] -= dot * W[i * (n + 1) + k];
+        }
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        double v = W[k * (n + 1) + n];
+        for (int j = k + 1; j < n; ++j) v -= W[k * (n + 1) + j] * y[j];
+        y[k] = v / W[k * (n + 1) + k];
+    }
+    for (int k = 0; k < n; ++k)
+        if (!std::isfinite(y[k])) return false;
+    return true;
+}
+
+struct LMResult {
+    Termination term;
+    int iterations;        // index of the last iteration summary pushed (Ceres numbering)
+    int num_cost_evals;    // residual-only + full evaluations
+    int num_jac_evals;
+    double final_cost;
+    double tr_radius;      // summary.iterations.back().trust_region_radius (cpp:277)
+};
+
+// TrustRegionMinimizer::Minimize of Ceres 1.14 specialised to: one 4-vector parameter
+// block, no bounds, no inner iterations, monotonic steps, Jacobi scaling on, LM strategy,
+// DENSE_QR.  x holds init on entry and the returned parameters on exit.
+LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
+    const int m = 2 * P.pn;
+    std::vector<double> res(m), jac(static_cast<size_t>(m) * 4), model_res(m), work;
+    double x[4], grad[4], scale[4], diag[4], lm_diag[4], step[4], delta[4], cand[4];
+    std::memcpy(x, x_io, sizeof(x));
+    LMResult out{FAILURE, 0, 0, 0, 0.0, opt.initial_trust_region_radius};
+
+    double x_cost, cand_cost;
+    double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
+    bool reuse_diagonal = false;
+    int num_invalid = 0;
+    double minimum_cost = std::numeric_limits<double>::max();
+
+    // ---- IterationZero -> EvaluateGradientAndJacobian(new_point) ----
+    bool ok = evaluate(P, x, &x_cost, res.data(), jac.data(), grad);
+    out.num_cost_evals++; out.num_jac_evals++;
+    if (!ok) { out.final_cost = x_cost; return out; }  // FAILURE, parameters untouched
+    {   // jacobi_scaling: 1 / (1 + sqrt(squared column norm)), from the initial Jacobian only
+        double cn[4] = {0, 0, 0, 0};
+        for (int i = 0; i < m; ++i) for (int k = 0; k < 4; ++k) cn[k] += jac[i * 4 + k] * jac[i * 4 + k];
+        for (int k = 0; k < 4; ++k) scale[k] = 1.0 / (1.0 + std::sqrt(cn[k]));
+    }
+    auto scale_columns = [&]() {
+        for (int i = 0; i < m; ++i) for (int k = 0; k < 4; ++k) jac[i * 4 + k] *= scale[k];
+    };
+    scale_columns();
+    auto max_norm = [](const double* g) {
+        double v = 0; for (int k = 0; k < 4; ++k) v = std::max(v, std::fabs(g[k])); return v; };
+    auto norm4 = [](const double* v) {
+        double s = 0; for (int k = 0; k < 4; ++k) s += v[k] * v[k]; return std::sqrt(s); };
+    double x_norm = norm4(x);
+    double gradient_max_norm = max_norm(grad);
+
+    int iteration = 0;
+    bool step_is_successful = true;  // iteration 0 counts as successful
+    out.term = NO_CONVERGENCE;
+    while (true) {
+        // ---- FinalizeIterationAndCheckIfMinimizerCanContinue ----
+        if (step_is_successful && x_cost < minimum_cost) {
+            minimum_cost = x_cost;
+            std::memcpy(x_io, x, sizeof(x));
+        }
+        out.tr_radius = radius;
+        out.iterations = iteration;
+        if (iteration >= opt.max_num_iterations) { out.term = NO_CONVERGENCE; break; }
+        if (step_is_successful && gradient_max_norm <= opt.gradient_tolerance) { out.term = CONVERGENCE; break; }
+        if (radius <= opt.min_trust_region_radius) { out.term = CONVERGENCE; break; }
+        ++iteration;
+        step_is_successful = false;
+
+        // ---- ComputeTrustRegionStep -> LevenbergMarquardtStrategy::ComputeStep ----
+        if (!reuse_diagonal) {
+            for (int k = 0; k < 4; ++k) diag[k] = 0.0;
+            for (int i = 0; i < m; ++i) for (int k = 0; k < 4; ++k) diag[k] += jac[i * 4 + k] * jac[i * 4 + k];
+            for (int k = 0; k < 4; ++k)
+                diag[k] = std::min(std::max(diag[k], opt.min_lm_diagonal), opt.max_lm_diagonal);
+        }
+        for (int k = 0; k < 4; ++k) lm_diag[k] = std::sqrt(diag[k] / radius);
+        bool solved = dense_qr_solve(jac.data(), res.data(), lm_diag, m, step, work);
+        reuse_diagonal = true;
+        bool step_is_valid = false;
+        double model_cost_change = 0.0;
+        if (solved) {
+            for (int k = 0; k < 4; ++k) step[k] = -step[k];
+            double dot = 0.0;  // -(J step)^T (f + J step / 2)
+            for (int i = 0; i < m; ++i) {
+                double mr = 0.0;
+                for (int k = 0; k < 4; ++k) mr += jac[i * 4 + k] * step[k];
+                dot += mr * (res[i] + mr / 2.0);
+            }
+            model_cost_change = -dot;
+            step_is_valid = model_cost_change > 0.0;
+        }
+        if (!step_is_valid) {
+            // ---- HandleInvalidStep ----
+            if (++num_invalid >= opt.max_num_consecutive_invalid_steps) { out.term = FAILURE; break; }
+            radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;  // StepIsInvalid
+            continue;
+        }
+        num_invalid = 0;
+        for (int k = 0; k < 4; ++k) delta[k] = step[k] * scale[k];  // undo column scaling
+
+        // ---- ComputeCandidatePointAndEvaluateCost ----
+        for (int k = 0; k < 4; ++k) cand[k] = x[k] + delta[k];
+        if (!evaluate(P, cand, &cand_cost, nullptr, nullptr, nullptr))
+            cand_cost = std::numeric_limits<double>::max();
+        out.num_cost_evals++;
+
+        // ---- ParameterToleranceReached ----
+        {
+            const double step_norm = norm4(delta);
+            if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+                out.term = CONVERGENCE; break;
+            }
+        }
+        // ---- FunctionToleranceReached ----
+        const double cost_change = x_cost - cand_cost;
+        if (std::fabs(cost_change) <= opt.function_tolerance * x_cost) {
+            if (opt.adopt_candidate_on_ftol && cand_cost < minimum_cost) {
+                minimum_cost = cand_cost; x_cost = cand_cost;
+                std::memcpy(x_io, cand, sizeof(cand));
+            }
+            out.term = CONVERGENCE; break;
+        }
+        // ---- IsStepSuccessful (monotonic TrustRegionStepEvaluator) ----
+        const double relative_decrease = cost_change / model_cost_change;
+        if (relative_decrease > opt.min_relative_decrease) {
+            // ---- HandleSuccessfulStep ----
+            std::memcpy(x, cand, sizeof(x));
+            x_norm = norm4(x);
+            ok = evaluate(P, x, &x_cost, res.data(), jac.data(), grad);
+            out.num_cost_evals++; out.num_jac_evals++;
+            if (!ok) { out.term = FAILURE; break; }
+            scale_columns();
+            gradient_max_norm = max_norm(grad);
+            step_is_successful = true;
+            // LevenbergMarquardtStrategy::StepAccepted
+            radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3));
+            radius = std::min(opt.max_trust_region_radius, radius);
+            decrease_factor = 2.0;
+            reuse_diagonal = false;
+        } else {
+            // ---- HandleUnsuccessfulStep -> StepRejected ----
+            radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        }
+    }
+    out.final_cost = minimum_cost;
+    return out;
+}
+
+// (J^T J)^-1 for a symmetric positive definite 4x4 via Cholesky; false if not SPD.
+bool spd_inverse4(const double* H, double* inv) {
+    double L[16] = {0};
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = H[i * 4 + j];
+            for (int k = 0; k < j; ++k) s -= L[i * 4 + k] * L[j * 4 + k];
+            if (i == j) {
+                if (!(s > 0.0) || !std::isfinite(s)) return false;
+                L[i * 4 + i] = std::sqrt(s);
+            } else {
+                L[i * 4 + j] = s / L[j * 4 + j];
+            }
+        }
+    double Li[16] = {0};  // inverse of L (lower)
+    for (int i = 0; i < 4; ++i) {
+        Li[i * 4 + i] = 1.0 / L[i * 4 + i];
+        for (int j = 0; j < i; ++j) {
+            double s = 0.0;
+            for (int k = j; k < i; ++k) s -= L[i * 4 + k] * Li[k * 4 + j];
+            Li[i * 4 + j] = s / L[i * 4 + i];
+        }
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = std::max(i, j); k < 4; ++k) s += Li[k * 4 + i] * Li[k * 4 + j];
+            inv[i * 4 + j] = s;
+        }
+    return true;
+}
+
+Problem make_problem(const double* pts2d, const double* pts3d, const double* wgt2d, const double* K,
+                     int pn, const double* clips, bool full_w) {
+    Problem P;
+    P.pts2d = pts2d; P.pts3d = pts3d; P.wgt2d = wgt2d; P.pn = pn; P.full_w = full_w;
+    P.fx = K[0]; P.fy = K[4]; P.cx = K[2]; P.cy = K[5];  // pnp_uncert_cpu.cpp:265
+    P.z_min = clips[0]; P.u_min = clips[1]; P.u_max = clips[2]; P.v_min = clips[3]; P.v_max = clips[4];
+    return P;
+}
+
+LMOptions g_options;  // process-wide; only the ftol switch is ever changed (tests)
+
+void solve_one(const double* pts2d, const double* pts3d, const double* wgt2d, const double* K,
+               const double* init_pose, int* result_val, double* result_pose, double* result_cov,
+               double* result_tr, int pn, const double* clips, bool full_w, int* stats /*4 or NULL*/,
+               double* final_cost /*or NULL*/) {
+    Problem P = make_problem(pts2d, pts3d, wgt2d, K, pn, clips, full_w);
+    std::memcpy(result_pose, init_pose, 4 * sizeof(double));           // cpp:259
+    LMResult r = trust_region_lm(P, result_pose, g_options);           // cpp:270-274
+    *result_val = (r.term == CONVERGENCE || r.term == NO_CONVERGENCE); // IsSolutionUsable, cpp:276
+    if (result_tr) *result_tr = r.tr_radius;                           // cpp:277
+    if (stats) { stats[0] = r.iterations; stats[1] = r.num_cost_evals; stats[2] = r.num_jac_evals; stats[3] = r.term; }
+    if (final_cost) *final_cost = r.final_cost;
+    if (*result_val && result_cov) {                                    // cpp:279-291, Ceres Covariance = (J^T J)^-1
+        std::vector<double> jac(static_cast<size_t>(2 * pn) * 4);
+        double cost, H[16] = {0};
+        evaluate(P, result_pose, &cost, nullptr, jac.data(), nullptr);
+        for (int i = 0; i < 2 * pn; ++i)
+            for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) H[a * 4 + b] += jac[i * 4 + a] * jac[i * 4 + b];
+        *result_val = spd_inverse4(H, result_cov) ? 1 : 0;              // rank-deficient -> Compute() fails
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Exact ABI of monorun/ops/least_squares/src/ext.h:1-13.
+void pnp_uncert(double* pts2d, double* pts3d, double* wgt2d, double* K, double* init_pose,
+                int* result_val, double* result_pose, double* result_cov, double* result_tr,
+                int pn, double* clips) {
+    solve_one(pts2d, pts3d, wgt2d, K, init_pose, result_val, result_pose, result_cov, result_tr, pn, clips,
+              false, nullptr, nullptr);
+}
+
+// 4-DoF solve with full symmetric 2x2 whitening W = [wxx wxy; wxy wyy]: the residual form of
+// NocCovReprojectionErrorArray (pnp_uncert_cpu.cpp:214-215, ext.h:33) with the log-dimension
+// unknowns held fixed at 0 -- BASELINE.json config 3.  wgt2d is [pn,3].
+void pnp_uncert_fullw(double* pts2d, double* pts3d, double* wgt2d, double* K, double* init_pose,
+                      int* result_val, double* result_pose, double* result_cov, double* result_tr,
+                      int pn, double* clips) {
+    solve_one(pts2d, pts3d, wgt2d, K, init_pose, result_val, result_pose, result_cov, result_tr, pn, clips,
+              true, nullptr, nullptr);
+}
+
+// Batched driver used by the CPU-baseline timing and the parity tests.  Object b reads
+// pn[b] points starting at point offset off[b] in the packed (sum pn, C) arrays (so inlier-
+// compacted objects of different sizes can be stacked).  K is [nb,9], clips [nb,5].
+// stats: [nb,4] = iterations, cost evals, jacobian evals, termination;  cost: [nb].
+// threads <= 0 -> all OpenMP threads (the reference is single-threaded: pass 1).
+void pnp_uncert_batch(const double* pts2d, const double* pts3d, const double* wgt2d, const double* K,
+                      const double* init_pose, int* result_val, double* result_pose, double* result_cov,
+                      double* result_tr, const int* pn, const long long* off, const double* clips,
+                      int nb, int full_w, int* stats, double* cost, int threads) {
+    const int wc = full_w ? 3 : 2;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 8) num_threads(threads)
+#endif
+    for (int b = 0; b < nb; ++b) {
+        const long long o = off[b];
+        solve_one(pts2d + o * 2, pts3d + o * 3, wgt2d + o * wc, K + b * 9, init_pose + b * 4,
+                  result_val + b, result_pose + b * 4, result_cov ? result_cov + b * 16 : nullptr,
+                  result_tr ? result_tr + b : nullptr, pn[b], clips + b * 5, full_w != 0,
+                  stats ? stats + b * 4 : nullptr, cost ? cost + b : nullptr);
+    }
+}
+
+// cost = 1/2 |r|^2, gradient J^T r (4) and Gauss-Newton matrix J^T J (4x4) at `pose`
+// with Ceres-Jet clip semantics (what the LM loop sees).  For tests.
+void pnp_eval(const double* pts2d, const double* pts3d, const double* wgt2d, const double* K,
+              const double* pose, int pn, const double* clips, int full_w, double* cost, double* grad,
+              double* JtJ) {
+    Problem P = make_problem(pts2d, pts3d, wgt2d, K, pn, clips, full_w != 0);
+    std::vector<double> jac(static_cast<size_t>(2 * pn) * 4);
+    evaluate(P, pose, cost, nullptr, jac.data(), grad);
+    for (int k = 0; k < 16; ++k) JtJ[k] = 0.0;
+    for (int i = 0; i < 2 * pn; ++i)
+        for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) JtJ[a * 4 + b] += jac[i * 4 + a] * jac[i * 4 + b];
+}
+
+// Pipeline covariance Hessian H = J^T J restating hessian.py:67-87 (approx_hessian) on top of
+// jacobian.py:4-98: projection through the full K (jacobian.py:20-33), z clip kills BOTH rows of a
+// point (:52-59), uv clip kills its own row, outliers are zeroed, weights are per-axis istd.
+// inlier: [pn] bytes or NULL.  K row-major 3x3.  H: 4x4 row-major, order [yaw,tx,ty,tz].
+void pnp_approx_hessian(const double* pts2d, const double* pts3d, const double* istd, const double* K,
+                        const double* pose, const unsigned char* inlier, int pn, const double* clips,
+                        double* H) {
+    (void)pts2d;
+    const double s = std::sin(pose[0]), c = std::cos(pose[0]);
+    const double R[9] = {c, 0, s, 0, 1, 0, -s, 0, c};
+    double KR[9], Kt[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            KR[i * 3 + j] = 0;
+            for (int k = 0; k < 3; ++k) KR[i * 3 + j] += K[i * 3 + k] * R[k * 3 + j];
+        }
+        Kt[i] = K[i * 3] * pose[1] + K[i * 3 + 1] * pose[2] + K[i * 3 + 2] * pose[3];
+    }
+    // jac_yaw_m1 = K[0:2,[0,2]] @ [[-s, c], [-c, -s]]     (jacobian.py:74-80)
+    const double m1[4] = {K[0] * -s + K[2] * -c, K[0] * c + K[2] * -s,
+                          K[3] * -s + K[5] * -c, K[3] * c + K[5] * -s};
+    for (int k = 0; k < 16; ++k) H[k] = 0.0;
+    for (int i = 0; i < pn; ++i) {
+        if (inlier && !inlier[i]) continue;
+        const double X = pts3d[i * 3], Y = pts3d[i * 3 + 1], Z = pts3d[i * 3 + 2];
+        double uvz[3];
+        for (int a = 0; a < 3; ++a) uvz[a] = KR[a * 3] * X + KR[a * 3 + 1] * Y + KR[a * 3 + 2] * Z + Kt[a];
+        double z = uvz[2];
+        const bool zclip = z < clips[0];
+        if (zclip) z = clips[0];
+        double uv[2] = {uvz[0] / z, uvz[1] / z};
+        const double lb[2] = {clips[1], clips[3]}, ub[2] = {clips[2], clips[4]};
+        bool zero[2];
+        for (int a = 0; a < 2; ++a) {
+            const bool clip = uv[a] < lb[a] || uv[a] > ub[a];
+            uv[a] = std::max(lb[a], std::min(ub[a], uv[a]));
+            zero[a] = zclip || clip;
+        }
+        for (int a = 0; a < 2; ++a) {
+            if (zero[a]) continue;
+            const double w = istd[i * 2 + a];
+            double j[4];
+            j[0] = ((m1[a * 2] + uv[a] * c) * X + (m1[a * 2 + 1] + uv[a] * s) * Z) / z * w;
+            j[1] = K[a * 3] / z * w;
+            j[2] = K[a * 3 + 1] / z * w;
+            j[3] = (K[a * 3 + 2] - uv[a]) / z * w;
+            for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q) H[p * 4 + q] += j[p] * j[q];
+        }
+    }
+}
+
+// inverse of an SPD 4x4 (torch.inverse(h) in pnp_uncert.py:77-78); returns 0 if not SPD.
+int pnp_spd_inverse4(const double* H, double* inv) { return spd_inverse4(H, inv) ? 1 : 0; }
+
+void pnp_oracle_set_adopt_candidate_on_ftol(int v) { g_options.adopt_candidate_on_ftol = v; }
+int pnp_oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"
