@@ -1,0 +1,136 @@
+/* monorun_pnp.h -- C ABI of libmonorun_pnp.so: batched uncertainty-weighted PnP on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for MonoRUn's native least-squares op.  The reference binds ONE
+ * per-object host function through cffi,
+ *
+ *     void pnp_uncert(double* pts2d, double* pts3d, double* wgt2d, double* K, double* init_pose,
+ *                     int* result_val, double* result_pose, double* result_cov, double* result_tr,
+ *                     int pn, double* clips);
+ *         -- monorun/ops/least_squares/src/ext.h:1-13, called per object from
+ *            monorun/ops/least_squares/pnp_uncert_cpu.py:102-106 inside the serial loop :180-191,
+ *
+ * after a device->host copy of every input (monorun/ops/least_squares/pnp_uncert.py:34-43).  The entry
+ * points below replace that call *and* the loop around it with one batched launch on device-resident
+ * tensors; mrpnp_solve_host keeps the reference's host-buffer calling convention for callers that have
+ * not moved their data to the GPU.  Plain pointers and sizes only; no torch types.  All functions are
+ * thread-safe; a context owns one device's scratch memory and may be used by one thread at a time.
+ *
+ * Per-object semantics (identical to the reference):
+ *   residual / clip rules   pnp_uncert_cpu.cpp:24-51 (diag weights), :189-217 (full 2x2 weights)
+ *   solver                  Ceres 1.14 trust-region Levenberg-Marquardt, default options, DENSE_QR
+ *   istd inlier test        pnp_uncert_cpu.py:164-168, "<=4 inliers -> use all" :23-32
+ *   weights from log-std    uncert_prop_pnp_optimizer.py:73
+ *   pose covariance         inverse of approx_hessian, hessian.py:67-87 / pnp_uncert.py:71-85
+ */
+#ifndef MONORUN_PNP_H_
+#define MONORUN_PNP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRPNP_VERSION 1
+#define MRPNP_MAX_POINTS 1024   /* points per object (H*W); 28x28 = 784 in every reference config */
+#define MRPNP_RESULT_STRIDE 24  /* floats per result row */
+
+/* tensor layout of the correspondence arrays */
+#define MRPNP_LAYOUT_PLANAR 0      /* [N, C, P]  == [N, C, H, W] head-level tensors (monorun_roi_head.py:513-529) */
+#define MRPNP_LAYOUT_INTERLEAVED 1 /* [N, P, C]  op-level tensors of PnPUncert.forward (pnp_uncert.py:125-142)    */
+
+/* meaning of the `weights` array */
+#define MRPNP_W_LOGSTD 0 /* C=2 log-std; istd = exp(-logstd)/std_scale (uncert_prop_pnp_optimizer.py:73) */
+#define MRPNP_W_ISTD 1   /* C=2 inverse std per axis (coords_2d_istd of pnp_uncert.py:7)                   */
+#define MRPNP_W_FULL 2   /* C=3 symmetric whitening matrix [wxx, wxy, wyy] (ext.h:33, .cpp:214-215)         */
+
+/* arithmetic of the solver */
+#define MRPNP_PREC_FP64 0 /* residual/Jacobian/normal equations in fp64: reproduces the fp64 reference decisions */
+#define MRPNP_PREC_FP32 1 /* fp32 Jacobian + fp32 cost-difference formulation, fp64 4x4 solve: fast path          */
+
+/* pose covariance written to the result row */
+#define MRPNP_COV_NONE 0
+#define MRPNP_COV_PIPELINE 1 /* inverse(J^T J) with jacobian.py:48-98 masks -- what pnp_uncert.py:71-85 returns */
+#define MRPNP_COV_CERES 2    /* inverse(J^T J) with Ceres-Jet masks -- what pnp_uncert_cpu.cpp:279-291 returns  */
+
+/* where LM starts */
+#define MRPNP_INIT_GIVEN 0  /* init_pose[N,4] supplied by the caller (e.g. an EPnP result)                     */
+#define MRPNP_INIT_LINEAR 1 /* on-device weighted linear 4-DoF initialiser (replaces cv2.solvePnP, .py:34-58) */
+
+/* status codes */
+#define MRPNP_OK 0
+#define MRPNP_ERR_ARG (-1)
+#define MRPNP_ERR_CUDA (-2)
+#define MRPNP_ERR_ALIGN (-3)
+
+typedef struct mrpnp_params {
+    int32_t n_obj;          /* N objects                                                              */
+    int32_t n_pts;          /* P points per object, 4 <= P <= MRPNP_MAX_POINTS                         */
+    int32_t layout;         /* MRPNP_LAYOUT_*                                                          */
+    int32_t weight_mode;    /* MRPNP_W_*                                                               */
+    int32_t cam_stride;     /* 0: one 3x3 K for all objects, 9: K per object (cam_mats (N|1,3,3))      */
+    int32_t range_stride;   /* 0: one [u_min,u_max,v_min,v_max] for all, 4: per object                 */
+    int32_t precision;      /* MRPNP_PREC_*                                                            */
+    int32_t cov_mode;       /* MRPNP_COV_*                                                             */
+    int32_t init_mode;      /* MRPNP_INIT_*                                                            */
+    int32_t inlier_opt_only;/* 1: LM sees inliers only (all reference configs), 0: all points          */
+    int32_t max_iterations; /* <=0: Ceres default 50                                                   */
+    int32_t adopt_candidate_on_ftol; /* 0: Ceres 1.14 (candidate dropped on the function-tolerance exit) */
+    float z_min;            /* PnPUncert(z_min=0.5)                                                    */
+    float std_scale;        /* UncertPropPnPOptimizer(std_scale=10); only for MRPNP_W_LOGSTD           */
+    float istd_thres;       /* epnp_istd_thres (0.6); <= 0 disables the istd inlier test               */
+    float reserved;
+} mrpnp_params;
+
+typedef struct mrpnp_ctx mrpnp_ctx;
+
+/* Fills `p` with the reference defaults (configs/kitti_multiclass.py:122-132) for n_obj x n_pts. */
+void mrpnp_default_params(mrpnp_params* p, int32_t n_obj, int32_t n_pts);
+
+/* Creates a context on CUDA device `device` (scratch buffers, work counter, streams for the host path). */
+int mrpnp_create(mrpnp_ctx** ctx, int device);
+void mrpnp_destroy(mrpnp_ctx* ctx);
+
+/* Batched solve on DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL).
+ *   coords_3d   [N,3,P] or [N,P,3] float   object-frame points
+ *   coords_2d   [N,2,P] or [N,P,2] float   pixel observations
+ *   weights     [N,2|3,P] or [N,P,2|3] float, meaning per weight_mode
+ *   cam_mats    [N|1,3,3] float row-major (only fx,fy,cx,cy are used, as in pnp_uncert_cpu.cpp:265)
+ *   uv_range    [N|1,4] float  u_min,u_max,v_min,v_max  (clips[1..4] of ext.h:12)
+ *   init_pose   [N,4] float  yaw,tx,ty,tz (ignored for MRPNP_INIT_LINEAR, may be NULL then)
+ *   inlier_in   [N,P] uint8 or NULL: externally supplied inlier mask (skips the istd test)
+ *   result      [N,24] float: yaw,tx,ty,tz | cov 4x4 row-major | valid, lm_iterations, final_cost, tr_radius
+ *   inlier_out  [N,P] uint8 or NULL: inlier mask actually used
+ *   result64    [N,8] double or NULL: yaw,tx,ty,tz,final_cost,tr_radius,cost_evals,termination (for parity tests)
+ * Planar inputs must be 16-byte aligned with P % 4 == 0 to take the TMA path; otherwise a plain
+ * coalesced-load path is used (same results). Returns MRPNP_OK or a negative status. */
+int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p,
+                const float* coords_3d, const float* coords_2d, const float* weights,
+                const float* cam_mats, const float* uv_range, const float* init_pose,
+                const uint8_t* inlier_in,
+                float* result, uint8_t* inlier_out, double* result64, void* stream);
+
+/* Same contract on HOST pointers: copies inputs to the device in chunks overlapped with the solve,
+ * copies `result` (and inlier_out) back, and returns when they are valid -- the calling convention of
+ * the reference's CPU op (numpy buffers in, numpy buffers out; pnp_uncert_cpu.py:128-209). */
+int mrpnp_solve_host(mrpnp_ctx* ctx, const mrpnp_params* p,
+                     const float* coords_3d, const float* coords_2d, const float* weights,
+                     const float* cam_mats, const float* uv_range, const float* init_pose,
+                     const uint8_t* inlier_in,
+                     float* result, uint8_t* inlier_out);
+
+/* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);
+
+/* Static facts about the solver kernel for the given problem: writes warps per CTA, CTAs, dynamic
+ * shared memory bytes and whether the TMA path is taken into info[0..3]. */
+int mrpnp_kernel_info(mrpnp_ctx* ctx, const mrpnp_params* p, int32_t info[4]);
+
+int mrpnp_version(void);
+/* Message of the last error on the calling thread ("" if none). */
+const char* mrpnp_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONORUN_PNP_H_ */

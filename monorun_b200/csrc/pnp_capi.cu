@@ -1,0 +1,305 @@
+// pnp_capi.cu -- C ABI (include/monorun_pnp.h) over the sm_100a solver kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+#include "monorun_pnp.h"
+#include "pnp_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+#define MR_CUDA(call)                                                                    \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) return fail(MRPNP_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int kHostStreams = 2;
+constexpr int kCounterSets = 8;
+
+}  // namespace
+
+struct mrpnp_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int max_smem_optin = 0;
+    int* counters = nullptr;  // kCounterSets x 2 ints, all zero between launches
+    int next_counter = 0;
+    int64_t launches = 0;
+    // host-path staging
+    cudaStream_t streams[kHostStreams] = {nullptr, nullptr};
+    void* chunk_buf[kHostStreams] = {nullptr, nullptr};
+    size_t chunk_bytes = 0;
+    float* small_buf = nullptr;  // cam / range
+    size_t small_bytes = 0;
+};
+
+namespace {
+
+using mrpnp::KParams;
+
+struct LaunchPlan {
+    int warps, ctas, smem, use_tma;
+};
+
+int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, const void* c3d, const void* c2d, const void* wgt,
+                LaunchPlan* plan) {
+    const int wc = p->weight_mode == MRPNP_W_FULL ? 3 : 2;
+    const size_t slot_floats = (size_t)(5 + wc) * p->n_pts;
+    size_t slot_bytes = slot_floats * sizeof(float);
+    slot_bytes = (slot_bytes + 15) & ~size_t(15);
+    const size_t avail = (size_t)ctx->max_smem_optin - mrpnp::kBarrierBytes;
+    int warps = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, avail / slot_bytes);
+    if (warps < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
+    // keep every SM busy before stacking warps: at small N spread objects over CTAs
+    const int per_sm = (p->n_obj + ctx->num_sms - 1) / ctx->num_sms;
+    warps = std::max(1, std::min(warps, per_sm));
+    plan->warps = warps;
+    plan->ctas = std::min(ctx->num_sms, (p->n_obj + warps - 1) / warps);
+    plan->smem = (int)(mrpnp::kBarrierBytes + warps * slot_bytes);
+    const bool aligned = (p->n_pts % 4 == 0) && (((uintptr_t)c3d | (uintptr_t)c2d | (uintptr_t)wgt) % 16 == 0);
+    plan->use_tma = aligned ? 1 : 0;
+    return MRPNP_OK;
+}
+
+int check_params(const mrpnp_params* p) {
+    if (!p) return fail(MRPNP_ERR_ARG, "params is NULL%s");
+    if (p->n_obj < 0) return fail(MRPNP_ERR_ARG, "n_obj < 0%s");
+    if (p->n_pts < 4 || p->n_pts > MRPNP_MAX_POINTS) return fail(MRPNP_ERR_ARG, "n_pts outside [4, 1024]%s");
+    if (p->layout != MRPNP_LAYOUT_PLANAR && p->layout != MRPNP_LAYOUT_INTERLEAVED)
+        return fail(MRPNP_ERR_ARG, "bad layout%s");
+    if (p->weight_mode < 0 || p->weight_mode > 2) return fail(MRPNP_ERR_ARG, "bad weight_mode%s");
+    if (p->precision != MRPNP_PREC_FP64 && p->precision != MRPNP_PREC_FP32) return fail(MRPNP_ERR_ARG, "bad precision%s");
+    if (p->cov_mode < 0 || p->cov_mode > 2) return fail(MRPNP_ERR_ARG, "bad cov_mode%s");
+    if (p->init_mode != MRPNP_INIT_GIVEN && p->init_mode != MRPNP_INIT_LINEAR) return fail(MRPNP_ERR_ARG, "bad init_mode%s");
+    if (p->cam_stride != 0 && p->cam_stride != 9) return fail(MRPNP_ERR_ARG, "cam_stride must be 0 or 9%s");
+    if (p->range_stride != 0 && p->range_stride != 4) return fail(MRPNP_ERR_ARG, "range_stride must be 0 or 4%s");
+    if (p->weight_mode == MRPNP_W_LOGSTD && !(p->std_scale > 0.f)) return fail(MRPNP_ERR_ARG, "std_scale must be > 0%s");
+    return MRPNP_OK;
+}
+
+template <int WMODE, int LAYOUT>
+cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan, cudaStream_t stream) {
+    cudaError_t e;
+    if (precision == MRPNP_PREC_FP64) {
+        auto k = mrpnp::pnp_lm_kernel<double, WMODE, LAYOUT>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
+        if (e != cudaSuccess) return e;
+        k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
+    } else {
+        auto k = mrpnp::pnp_lm_kernel<float, WMODE, LAYOUT>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
+        if (e != cudaSuccess) return e;
+        k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch(const mrpnp_params* p, const KParams& kp, const LaunchPlan& plan, cudaStream_t stream) {
+#define MR_CASE(W, L) \
+    if (p->weight_mode == W && p->layout == L) return launch_one<W, L>(p->precision, kp, plan, stream);
+    MR_CASE(MRPNP_W_LOGSTD, MRPNP_LAYOUT_PLANAR)
+    MR_CASE(MRPNP_W_ISTD, MRPNP_LAYOUT_PLANAR)
+    MR_CASE(MRPNP_W_FULL, MRPNP_LAYOUT_PLANAR)
+    MR_CASE(MRPNP_W_LOGSTD, MRPNP_LAYOUT_INTERLEAVED)
+    MR_CASE(MRPNP_W_ISTD, MRPNP_LAYOUT_INTERLEAVED)
+    MR_CASE(MRPNP_W_FULL, MRPNP_LAYOUT_INTERLEAVED)
+#undef MR_CASE
+    return cudaErrorInvalidValue;
+}
+
+int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const float* c2d, const float* wgt,
+                 const float* cam, const float* range, const float* init, const uint8_t* inl_in, float* result,
+                 uint8_t* inl_out, double* result64, cudaStream_t stream) {
+    if (p->n_obj == 0) return MRPNP_OK;
+    if (!c3d || !c2d || !wgt || !cam || !range || !result) return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    if (p->init_mode == MRPNP_INIT_GIVEN && !init) return fail(MRPNP_ERR_ARG, "init_pose is NULL with MRPNP_INIT_GIVEN%s");
+    LaunchPlan plan;
+    int rc = plan_launch(ctx, p, c3d, c2d, wgt, &plan);
+    if (rc != MRPNP_OK) return rc;
+    KParams kp;
+    kp.c3d = c3d; kp.c2d = c2d; kp.wgt = wgt; kp.cam = cam; kp.range = range; kp.init = init;
+    kp.inl_in = inl_in; kp.result = result; kp.inl_out = inl_out; kp.result64 = result64;
+    kp.counters = ctx->counters + 2 * ctx->next_counter;
+    ctx->next_counter = (ctx->next_counter + 1) % kCounterSets;
+    kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride;
+    kp.cov_mode = p->cov_mode; kp.init_mode = p->init_mode; kp.inlier_opt_only = p->inlier_opt_only;
+    kp.max_iter = p->max_iterations; kp.adopt_ftol = p->adopt_candidate_on_ftol;
+    kp.use_tma = plan.use_tma;
+    kp.slot_floats = (int)((plan.smem - mrpnp::kBarrierBytes) / plan.warps / sizeof(float));
+    kp.z_min = p->z_min; kp.std_scale = p->std_scale; kp.istd_thres = p->istd_thres;
+    cudaError_t e = dispatch(p, kp, plan, stream);
+    if (e != cudaSuccess) return fail(MRPNP_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    ctx->launches += 1;
+    return MRPNP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrpnp_version(void) { return MRPNP_VERSION; }
+const char* mrpnp_last_error(void) { return g_err; }
+
+void mrpnp_default_params(mrpnp_params* p, int32_t n_obj, int32_t n_pts) {
+    memset(p, 0, sizeof(*p));
+    p->n_obj = n_obj;
+    p->n_pts = n_pts;
+    p->layout = MRPNP_LAYOUT_PLANAR;
+    p->weight_mode = MRPNP_W_LOGSTD;
+    p->cam_stride = 0;
+    p->range_stride = 0;
+    p->precision = MRPNP_PREC_FP64;
+    p->cov_mode = MRPNP_COV_PIPELINE;
+    p->init_mode = MRPNP_INIT_GIVEN;
+    p->inlier_opt_only = 1;      // configs/kitti_multiclass.py:127
+    p->max_iterations = 50;      // ceres::Solver::Options default
+    p->adopt_candidate_on_ftol = 0;
+    p->z_min = 0.5f;             // configs/kitti_multiclass.py:125
+    p->std_scale = 10.f;         // uncert_prop_pnp_optimizer.py:28
+    p->istd_thres = 0.6f;        // configs/kitti_multiclass.py:126
+}
+
+int mrpnp_create(mrpnp_ctx** out, int device) {
+    if (!out) return fail(MRPNP_ERR_ARG, "ctx out pointer is NULL%s");
+    *out = nullptr;
+    MR_CUDA(cudaSetDevice(device));
+    mrpnp_ctx* c = new (std::nothrow) mrpnp_ctx();
+    if (!c) return fail(MRPNP_ERR_ARG, "out of host memory%s");
+    c->device = device;
+    cudaDeviceProp prop;
+    MR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete c;
+        return fail(MRPNP_ERR_CUDA, "libmonorun_pnp is built for sm_100a only; device is %s", prop.name);
+    }
+    c->num_sms = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    MR_CUDA(cudaMalloc(&c->counters, sizeof(int) * 2 * kCounterSets));
+    MR_CUDA(cudaMemset(c->counters, 0, sizeof(int) * 2 * kCounterSets));
+    *out = c;
+    return MRPNP_OK;
+}
+
+void mrpnp_destroy(mrpnp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < kHostStreams; ++i) {
+        if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+        if (c->chunk_buf[i]) cudaFree(c->chunk_buf[i]);
+    }
+    if (c->small_buf) cudaFree(c->small_buf);
+    if (c->counters) cudaFree(c->counters);
+    delete c;
+}
+
+int64_t mrpnp_launch_count(const mrpnp_ctx* c) { return c ? c->launches : 0; }
+
+int mrpnp_kernel_info(mrpnp_ctx* ctx, const mrpnp_params* p, int32_t info[4]) {
+    if (!ctx || !info) return fail(MRPNP_ERR_ARG, "NULL argument%s");
+    int rc = check_params(p);
+    if (rc != MRPNP_OK) return rc;
+    LaunchPlan plan;
+    rc = plan_launch(ctx, p, nullptr, nullptr, nullptr, &plan);
+    if (rc != MRPNP_OK) return rc;
+    info[0] = plan.warps; info[1] = plan.ctas; info[2] = plan.smem; info[3] = plan.use_tma;
+    return MRPNP_OK;
+}
+
+int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_3d, const float* coords_2d,
+                const float* weights, const float* cam_mats, const float* uv_range, const float* init_pose,
+                const uint8_t* inlier_in, float* result, uint8_t* inlier_out, double* result64, void* stream) {
+    if (!ctx) return fail(MRPNP_ERR_ARG, "ctx is NULL%s");
+    int rc = check_params(p);
+    if (rc != MRPNP_OK) return rc;
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    return solve_device(ctx, p, coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose, inlier_in, result,
+                        inlier_out, result64, static_cast<cudaStream_t>(stream));
+}
+
+// Host-buffer entry: objects are cut into chunks; chunk i+1's host->device copies run on the other
+// stream while chunk i is being solved, and each chunk's result rows are copied back as soon as its
+// kernel finishes.  Pinned host memory makes the copies truly asynchronous; pageable memory also works.
+int mrpnp_solve_host(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_3d, const float* coords_2d,
+                     const float* weights, const float* cam_mats, const float* uv_range, const float* init_pose,
+                     const uint8_t* inlier_in, float* result, uint8_t* inlier_out) {
+    if (!ctx) return fail(MRPNP_ERR_ARG, "ctx is NULL%s");
+    int rc = check_params(p);
+    if (rc != MRPNP_OK) return rc;
+    if (p->n_obj == 0) return MRPNP_OK;
+    if (!coords_3d || !coords_2d || !weights || !cam_mats || !uv_range || !result)
+        return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    if (p->init_mode == MRPNP_INIT_GIVEN && !init_pose) return fail(MRPNP_ERR_ARG, "init_pose is NULL with MRPNP_INIT_GIVEN%s");
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    const int wc = p->weight_mode == MRPNP_W_FULL ? 3 : 2;
+    const size_t P = (size_t)p->n_pts;
+    const int chunk = std::min(p->n_obj, 2048);
+    // per-chunk device layout: c3d | c2d | wgt | init | result | inl_in | inl_out (each 256-B aligned)
+    auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t o3 = 0, o2 = o3 + al(chunk * 3 * P * 4), ow = o2 + al(chunk * 2 * P * 4);
+    const size_t oi = ow + al(chunk * wc * P * 4), orr = oi + al((size_t)chunk * 16);
+    const size_t omi = orr + al((size_t)chunk * MRPNP_RESULT_STRIDE * 4), omo = omi + al(chunk * P);
+    const size_t total = omo + al(chunk * P);
+    if (total > ctx->chunk_bytes) {
+        for (int i = 0; i < kHostStreams; ++i) {
+            if (ctx->chunk_buf[i]) MR_CUDA(cudaFree(ctx->chunk_buf[i]));
+            ctx->chunk_buf[i] = nullptr;
+            MR_CUDA(cudaMalloc(&ctx->chunk_buf[i], total));
+        }
+        ctx->chunk_bytes = total;
+    }
+    for (int i = 0; i < kHostStreams; ++i)
+        if (!ctx->streams[i]) MR_CUDA(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
+    const size_t cam_n = p->cam_stride ? (size_t)p->n_obj * 9 : 9, rng_n = p->range_stride ? (size_t)p->n_obj * 4 : 4;
+    const size_t small = (cam_n + rng_n) * 4;
+    if (small > ctx->small_bytes) {
+        if (ctx->small_buf) MR_CUDA(cudaFree(ctx->small_buf));
+        ctx->small_buf = nullptr;
+        MR_CUDA(cudaMalloc(&ctx->small_buf, small));
+        ctx->small_bytes = small;
+    }
+    float* d_cam = ctx->small_buf;
+    float* d_rng = ctx->small_buf + cam_n;
+    MR_CUDA(cudaMemcpyAsync(d_cam, cam_mats, cam_n * 4, cudaMemcpyHostToDevice, ctx->streams[0]));
+    MR_CUDA(cudaMemcpyAsync(d_rng, uv_range, rng_n * 4, cudaMemcpyHostToDevice, ctx->streams[0]));
+    MR_CUDA(cudaStreamSynchronize(ctx->streams[0]));
+
+    int ci = 0;
+    for (int start = 0; start < p->n_obj; start += chunk, ++ci) {
+        const int n = std::min(chunk, p->n_obj - start);
+        cudaStream_t st = ctx->streams[ci % kHostStreams];
+        char* base = static_cast<char*>(ctx->chunk_buf[ci % kHostStreams]);
+        float* d3 = (float*)(base + o3); float* d2 = (float*)(base + o2); float* dw = (float*)(base + ow);
+        float* di = (float*)(base + oi); float* dr = (float*)(base + orr);
+        uint8_t* dmi = (uint8_t*)(base + omi); uint8_t* dmo = (uint8_t*)(base + omo);
+        MR_CUDA(cudaMemcpyAsync(d3, coords_3d + (size_t)start * 3 * P, (size_t)n * 3 * P * 4, cudaMemcpyHostToDevice, st));
+        MR_CUDA(cudaMemcpyAsync(d2, coords_2d + (size_t)start * 2 * P, (size_t)n * 2 * P * 4, cudaMemcpyHostToDevice, st));
+        MR_CUDA(cudaMemcpyAsync(dw, weights + (size_t)start * wc * P, (size_t)n * wc * P * 4, cudaMemcpyHostToDevice, st));
+        if (init_pose) MR_CUDA(cudaMemcpyAsync(di, init_pose + (size_t)start * 4, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+        if (inlier_in) MR_CUDA(cudaMemcpyAsync(dmi, inlier_in + (size_t)start * P, (size_t)n * P, cudaMemcpyHostToDevice, st));
+        mrpnp_params q = *p;
+        q.n_obj = n;
+        rc = solve_device(ctx, &q, d3, d2, dw, d_cam + (p->cam_stride ? (size_t)start * 9 : 0),
+                          d_rng + (p->range_stride ? (size_t)start * 4 : 0), init_pose ? di : nullptr,
+                          inlier_in ? dmi : nullptr, dr, inlier_out ? dmo : nullptr, nullptr, st);
+        if (rc != MRPNP_OK) return rc;
+        MR_CUDA(cudaMemcpyAsync(result + (size_t)start * MRPNP_RESULT_STRIDE, dr, (size_t)n * MRPNP_RESULT_STRIDE * 4,
+                                cudaMemcpyDeviceToHost, st));
+        if (inlier_out) MR_CUDA(cudaMemcpyAsync(inlier_out + (size_t)start * P, dmo, (size_t)n * P, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kHostStreams; ++i) MR_CUDA(cudaStreamSynchronize(ctx->streams[i]));
+    return MRPNP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's PnP op interface over the CUDA C ABI.
+
+Same names, argument meaning and return tuples as ``monorun/ops/least_squares``:
+
+* :func:`pnp_uncert`   <- monorun/ops/least_squares/pnp_uncert.py:7-87
+* :class:`PnPUncert`   <- monorun/ops/least_squares/pnp_uncert.py:90-142 (registered as ``'PnPUncert'`` in ``PNP``)
+* :func:`build_pnp`    <- monorun/ops/least_squares/builder.py:6-7
+
+What changes underneath: no device->host copy (pnp_uncert.py:34-43), no per-object Python loop
+(pnp_uncert_cpu.py:180-191), no OpenCV / Ceres; one batched sm_100a kernel launch solves every object and also
+produces the pose covariance that the reference computes with ~40 torch launches (pnp_uncert.py:71-85).
+PyTorch is used for device memory and streams only.  There is no CPU fallback: tensors must live on a CUDA
+device and ``libmonorun_pnp.so`` must be built, otherwise these calls raise.
+"""
+import torch
+
+from . import _native
+from .registry import PNP, build_pnp  # noqa: F401  (re-exported like monorun.ops)
+
+C = _native.CONST
+RESULT_STRIDE = C['MRPNP_RESULT_STRIDE']
+
+_ctx_cache = {}
+
+
+class _Ctx:
+    """One ``mrpnp_ctx`` per CUDA device, created on first use."""
+
+    def __init__(self, device_index):
+        lib = _native.lib()
+        out = _native.ffi.new('mrpnp_ctx**')
+        _native.check(lib.mrpnp_create(out, device_index))
+        self.ptr = out[0]
+        self.device_index = device_index
+
+    @property
+    def launches(self):
+        return int(_native.lib().mrpnp_launch_count(self.ptr))
+
+
+def get_ctx(device):
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('monorun_b200 PnP runs on CUDA tensors only (no CPU fallback); got device '
+                           f'{device}')
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _ctx_cache:
+        _ctx_cache[idx] = _Ctx(idx)
+    return _ctx_cache[idx]
+
+
+def launch_count(device='cuda'):
+    return get_ctx(device).launches
+
+
+def make_params(n_obj, n_pts, **kw):
+    p = _native.ffi.new('mrpnp_params*')
+    _native.lib().mrpnp_default_params(p, n_obj, n_pts)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t, ctype='float*'):
+    return _native.ffi.cast(ctype, t.data_ptr()) if t is not None else _native.ffi.NULL
+
+
+def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None, inlier_mask=None, *,
+                  layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, istd_thres=0.6,
+                  inlier_opt_only=True, cov_mode='pipeline', precision='fp64', max_iterations=50,
+                  adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False):
+    """Batched uncertainty-PnP on device tensors -- direct wrapper of ``mrpnp_solve``.
+
+    layout 'planar':      coords_3d [N,3,*], coords_2d [N,2,*], weights [N,2|3,*]   (head level)
+    layout 'interleaved': coords_3d [N,P,3], coords_2d [N,P,2], weights [N,P,2|3]   (op level)
+    weight_mode 'logstd' | 'istd' | 'full';  cam_mats [N|1,3,3];  uv_range [N|1,4] = u_min,u_max,v_min,v_max;
+    init_pose [N,4] or None (on-device linear initialiser);  inlier_mask [N,P] bool/uint8 or None.
+
+    Returns (result [N,24] float32, inlier_mask [N,P] bool | None, result64 [N,8] float64 | None); the result
+    row is ``yaw,tx,ty,tz | cov(16) | valid, lm_iterations, final_cost, trust_region_radius``.
+    """
+    dev = coords_3d.device
+    ctx = get_ctx(dev)
+    n = coords_3d.shape[0]
+    planar = layout == 'planar'
+    n_pts = coords_3d[0].numel() // 3 if n else (coords_3d.shape[2:].numel() if planar else coords_3d.shape[1])
+    wmode = {'logstd': C['MRPNP_W_LOGSTD'], 'istd': C['MRPNP_W_ISTD'], 'full': C['MRPNP_W_FULL']}[weight_mode]
+    result = torch.empty((n, RESULT_STRIDE), dtype=torch.float32, device=dev)
+    inl_out = torch.empty((n, n_pts), dtype=torch.uint8, device=dev) if return_inlier_mask else None
+    res64 = torch.empty((n, 8), dtype=torch.float64, device=dev) if return_fp64 else None
+    if n == 0:
+        return result, (inl_out.bool() if inl_out is not None else None), res64
+    c3, c2, w = _f32c(coords_3d), _f32c(coords_2d), _f32c(weights)
+    cam, rng = _f32c(cam_mats).reshape(-1, 9), _f32c(uv_range).reshape(-1, 4)
+    if cam.shape[0] not in (1, n) or rng.shape[0] not in (1, n):
+        raise ValueError('cam_mats / uv_range must have batch size 1 or N')
+    init = _f32c(init_pose) if init_pose is not None else None
+    inl_in = inlier_mask.to(torch.uint8).contiguous() if inlier_mask is not None else None
+    p = make_params(
+        n, n_pts,
+        layout=C['MRPNP_LAYOUT_PLANAR'] if planar else C['MRPNP_LAYOUT_INTERLEAVED'],
+        weight_mode=wmode,
+        cam_stride=9 if cam.shape[0] == n and n > 1 else 0,
+        range_stride=4 if rng.shape[0] == n and n > 1 else 0,
+        precision=C['MRPNP_PREC_FP64'] if precision == 'fp64' else C['MRPNP_PREC_FP32'],
+        cov_mode={'none': 0, 'pipeline': 1, 'ceres': 2}[cov_mode],
+        init_mode=C['MRPNP_INIT_GIVEN'] if init is not None else C['MRPNP_INIT_LINEAR'],
+        inlier_opt_only=int(bool(inlier_opt_only)), max_iterations=int(max_iterations),
+        adopt_candidate_on_ftol=int(bool(adopt_candidate_on_ftol)),
+        z_min=float(z_min), std_scale=float(std_scale), istd_thres=float(istd_thres))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_solve(
+            ctx.ptr, p, _ptr(c3), _ptr(c2), _ptr(w), _ptr(cam), _ptr(rng), _ptr(init),
+            _ptr(inl_in, 'uint8_t*'), _ptr(result), _ptr(inl_out, 'uint8_t*'), _ptr(res64, 'double*'),
+            _native.ffi.cast('void*', stream)))
+    return result, (inl_out.bool() if inl_out is not None else None), res64
+
+
+def solve_host(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None, *, device=0, layout='planar',
+               weight_mode='logstd', result=None, **kw):
+    """``mrpnp_solve_host`` on CPU tensors / numpy-backed memory (pinned for full speed): the reference op's
+    host-buffer calling convention (pnp_uncert_cpu.py:128-209).  Returns result [N,24] (CPU tensor)."""
+    ctx = get_ctx(torch.device('cuda', device))
+    n = coords_3d.shape[0]
+    n_pts = coords_3d[0].numel() // 3
+    if result is None:
+        result = torch.empty((n, RESULT_STRIDE), dtype=torch.float32)
+    cam, rng = _f32c(cam_mats).reshape(-1, 9), _f32c(uv_range).reshape(-1, 4)
+    wmode = {'logstd': C['MRPNP_W_LOGSTD'], 'istd': C['MRPNP_W_ISTD'], 'full': C['MRPNP_W_FULL']}[weight_mode]
+    p = make_params(
+        n, n_pts, layout=C['MRPNP_LAYOUT_PLANAR'] if layout == 'planar' else C['MRPNP_LAYOUT_INTERLEAVED'],
+        weight_mode=wmode, cam_stride=9 if cam.shape[0] == n and n > 1 else 0,
+        range_stride=4 if rng.shape[0] == n and n > 1 else 0,
+        precision=C['MRPNP_PREC_FP64'] if kw.get('precision', 'fp64') == 'fp64' else C['MRPNP_PREC_FP32'],
+        cov_mode={'none': 0, 'pipeline': 1, 'ceres': 2}[kw.get('cov_mode', 'pipeline')],
+        init_mode=C['MRPNP_INIT_GIVEN'] if init_pose is not None else C['MRPNP_INIT_LINEAR'],
+        z_min=float(kw.get('z_min', 0.5)), std_scale=float(kw.get('std_scale', 10.0)),
+        istd_thres=float(kw.get('istd_thres', 0.6)))
+    for t in (coords_3d, coords_2d, weights):
+        assert t.device.type == 'cpu' and t.dtype == torch.float32 and t.is_contiguous()
+    _native.check(_native.lib().mrpnp_solve_host(
+        ctx.ptr, p, _ptr(coords_3d), _ptr(coords_2d), _ptr(weights), _ptr(cam), _ptr(rng),
+        _ptr(_f32c(init_pose) if init_pose is not None else None), _native.ffi.NULL, _ptr(result),
+        _native.ffi.NULL))
+    return result
+
+
+def _unpack(result, inlier_mask):
+    ret_val = result[:, 20] > 0.5
+    r_vec = result[:, 0:1].clone()
+    t_vec = result[:, 1:4].clone()
+    pose_cov = result[:, 4:20].reshape(-1, 4, 4).clone()
+    return ret_val, r_vec, t_vec, pose_cov, inlier_mask
+
+
+def pnp_uncert(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range, z_min=0.5, epnp_istd_thres=1.0,
+               epnp_ransac_thres=None, inlier_opt_only=False, forward_exact_hessian=False, use_6dof=False,
+               init_pose=None, precision='fp64'):
+    """Drop-in for monorun/ops/least_squares/pnp_uncert.py:7-87.
+
+    Args (as in the reference):
+        coords_2d (Tensor): (Nbatch, Npoint, 2);  coords_2d_istd (Tensor): (Nbatch, Npoint, 2)
+        coords_3d (Tensor): (Nbatch, Npoint, 3);  cam_mats (Tensor): (Nbatch, 3, 3) or (1, 3, 3)
+        u_range, v_range (Tensor): (Nbatch, 2) or (1, 2);  z_min, epnp_istd_thres (float)
+        epnp_ransac_thres (None | Tensor): accepted for signature compatibility.  OpenCV's RANSAC-EPnP
+            (pnp_uncert_cpu.py:34-51) is not reproduced on the GPU; the on-device linear initialiser uses the
+            istd inliers (documented deviation).
+        forward_exact_hessian: only False is supported (all shipped configs; the reference's exact_hessian
+            does not run on torch >= 2).  use_6dof: accepted and unused, exactly as in the reference.
+        init_pose (Tensor | None): extension -- (Nbatch, 4) [yaw, t] to start LM from (e.g. an EPnP result).
+    Returns:
+        ret_val (Nbatch,) bool, r_vec (Nbatch, 1), t_vec (Nbatch, 3), pose_cov (Nbatch, 4, 4),
+        inlier_mask (Nbatch, Npoint) bool -- all on the input device.
+    """
+    if forward_exact_hessian:
+        raise NotImplementedError('forward_exact_hessian=True is not supported (unused by every reference config)')
+    with torch.no_grad():
+        n = coords_2d.shape[0]
+        if n == 0:  # pnp_uncert.py:60-61, pnp_uncert_cpu.py:201-207
+            return (coords_2d.new_zeros((0,), dtype=torch.bool), coords_2d.new_zeros((0, 1)),
+                    coords_2d.new_zeros((0, 3)), coords_2d.new_zeros((0, 4, 4)),
+                    coords_2d.new_zeros((0, coords_2d.shape[1]), dtype=torch.bool))
+        uv_range = torch.cat([u_range.expand(max(u_range.shape[0], v_range.shape[0]), 2),
+                              v_range.expand(max(u_range.shape[0], v_range.shape[0]), 2)], dim=1)
+        result, inlier_mask, _ = solve_batched(
+            coords_3d, coords_2d, coords_2d_istd, cam_mats, uv_range, init_pose=init_pose, layout='interleaved',
+            weight_mode='istd', z_min=z_min, istd_thres=epnp_istd_thres, inlier_opt_only=inlier_opt_only,
+            cov_mode='pipeline', precision=precision)
+        return _unpack(result, inlier_mask)
+
+
+@PNP.register_module()
+class PnPUncert(torch.nn.Module):
+    """Drop-in for monorun/ops/least_squares/pnp_uncert.py:90-142 (same constructor kwargs and forward)."""
+
+    def __init__(self, z_min=0.5, epnp_istd_thres=0.6, inlier_opt_only=True, coord_istd_normalize=False,
+                 forward_exact_hessian=False, use_6dof=False, eps=1e-6, precision='fp64'):
+        super(PnPUncert, self).__init__()
+        self.z_min = z_min
+        self.epnp_istd_thres = epnp_istd_thres
+        self.inlier_opt_only = inlier_opt_only
+        self.coord_istd_normalize = coord_istd_normalize
+        self.forward_exact_hessian = forward_exact_hessian
+        self.use_6dof = use_6dof
+        self.eps = eps
+        self.precision = precision
+
+    def forward(self, coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range, epnp_ransac_thres=None,
+                init_pose=None):
+        if self.coord_istd_normalize:  # pnp_uncert.py:130-132
+            mean = torch.mean(coords_2d_istd, dim=(1, 2), keepdim=True)
+            coords_2d_istd = coords_2d_istd / mean.clamp(min=self.eps)
+        return pnp_uncert(
+            coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range, z_min=self.z_min,
+            epnp_istd_thres=self.epnp_istd_thres, epnp_ransac_thres=epnp_ransac_thres,
+            inlier_opt_only=self.inlier_opt_only, forward_exact_hessian=self.forward_exact_hessian,
+            use_6dof=self.use_6dof, init_pose=init_pose, precision=self.precision)
+
+    def forward_dense(self, coords_2d, coords_2d_logstd, coords_3d, cam_mats, uv_range, std_scale, init_pose=None):
+        """Head-level entry used by UncertPropPnPOptimizer: NCHW tensors and log-std straight into the kernel
+        (fuses uncert_prop_pnp_optimizer.py:73 and the three permute copies of :82-84)."""
+        with torch.no_grad():
+            if self.coord_istd_normalize:
+                raise NotImplementedError('coord_istd_normalize with the dense entry')
+            result, inlier_mask, _ = solve_batched(
+                coords_3d, coords_2d, coords_2d_logstd, cam_mats, uv_range, init_pose=init_pose, layout='planar',
+                weight_mode='logstd', z_min=self.z_min, std_scale=std_scale, istd_thres=self.epnp_istd_thres,
+                inlier_opt_only=self.inlier_opt_only, cov_mode='pipeline', precision=self.precision)
+            return _unpack(result, inlier_mask)

@@ -192,7 +192,7 @@ bool dense_qr_solve(const double* A, const double* b, const double* D, int m, do
 struct LMResult {
     Termination term;
     int iterations;        // index of the last iteration summary pushed (Ceres numbering)
-    int num_cost_evals;    // residual-only + full evaluations
+    int num_cost_evals;    // 1 (initial point) + candidate points evaluated
     int num_jac_evals;
     double final_cost;
     double tr_radius;      // summary.iterations.back().trust_region_radius (cpp:277)
@@ -312,7 +312,7 @@ LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
             std::memcpy(x, cand, sizeof(x));
             x_norm = norm4(x);
             ok = evaluate(P, x, &x_cost, res.data(), jac.data(), grad);
-            out.num_cost_evals++; out.num_jac_evals++;
+            out.num_jac_evals++;
             if (!ok) { out.term = FAILURE; break; }
             scale_columns();
             gradient_max_norm = max_norm(grad);
