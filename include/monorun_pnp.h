@@ -45,8 +45,8 @@ extern "C" {
 #define MRPNP_W_FULL 2   /* C=3 symmetric whitening matrix [wxx, wxy, wyy] (ext.h:33, .cpp:214-215)         */
 
 /* arithmetic of the solver */
-#define MRPNP_PREC_FP64 0 /* residual/Jacobian/normal equations in fp64: reproduces the fp64 reference decisions */
-#define MRPNP_PREC_FP32 1 /* fp32 Jacobian + fp32 cost-difference formulation, fp64 4x4 solve: fast path          */
+#define MRPNP_PREC_FP64 0  /* residual, Jacobian and normal equations in fp64: reproduces the fp64 reference decisions */
+#define MRPNP_PREC_MIXED 1 /* fp64 residual/cost chain + fp32 Jacobian sums, fp64 4x4 solve: the fast path            */
 
 /* pose covariance written to the result row */
 #define MRPNP_COV_NONE 0
@@ -98,17 +98,18 @@ void mrpnp_destroy(mrpnp_ctx* ctx);
  *   cam_mats    [N|1,3,3] float row-major (only fx,fy,cx,cy are used, as in pnp_uncert_cpu.cpp:265)
  *   uv_range    [N|1,4] float  u_min,u_max,v_min,v_max  (clips[1..4] of ext.h:12)
  *   init_pose   [N,4] float  yaw,tx,ty,tz (ignored for MRPNP_INIT_LINEAR, may be NULL then)
- *   inlier_in   [N,P] uint8 or NULL: externally supplied inlier mask (skips the istd test)
+ *   inlier_in   [N,ceil(P/32)] uint32 or NULL: externally supplied inlier mask, packed (bit j of word k of an
+ *               object = point 32k+j); skips the istd test
  *   result      [N,24] float: yaw,tx,ty,tz | cov 4x4 row-major | valid, lm_iterations, final_cost, tr_radius
- *   inlier_out  [N,P] uint8 or NULL: inlier mask actually used
+ *   inlier_out  [N,ceil(P/32)] uint32 or NULL: inlier mask actually used, packed the same way
  *   result64    [N,8] double or NULL: yaw,tx,ty,tz,final_cost,tr_radius,cost_evals,termination (for parity tests)
  * Planar inputs must be 16-byte aligned with P % 4 == 0 to take the TMA path; otherwise a plain
  * coalesced-load path is used (same results). Returns MRPNP_OK or a negative status. */
 int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p,
                 const float* coords_3d, const float* coords_2d, const float* weights,
                 const float* cam_mats, const float* uv_range, const float* init_pose,
-                const uint8_t* inlier_in,
-                float* result, uint8_t* inlier_out, double* result64, void* stream);
+                const uint32_t* inlier_in,
+                float* result, uint32_t* inlier_out, double* result64, void* stream);
 
 /* Same contract on HOST pointers: copies inputs to the device in chunks overlapped with the solve,
  * copies `result` (and inlier_out) back, and returns when they are valid -- the calling convention of
@@ -116,8 +117,8 @@ int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p,
 int mrpnp_solve_host(mrpnp_ctx* ctx, const mrpnp_params* p,
                      const float* coords_3d, const float* coords_2d, const float* weights,
                      const float* cam_mats, const float* uv_range, const float* init_pose,
-                     const uint8_t* inlier_in,
-                     float* result, uint8_t* inlier_out);
+                     const uint32_t* inlier_in,
+                     float* result, uint32_t* inlier_out);
 
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);

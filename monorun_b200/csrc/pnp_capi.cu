@@ -57,15 +57,15 @@ int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, const void* c3d, co
     const size_t slot_floats = (size_t)(5 + wc) * p->n_pts;
     size_t slot_bytes = slot_floats * sizeof(float);
     slot_bytes = (slot_bytes + 15) & ~size_t(15);
-    const size_t avail = (size_t)ctx->max_smem_optin - mrpnp::kBarrierBytes;
-    int warps = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, avail / slot_bytes);
+    const size_t avail = (size_t)ctx->max_smem_optin;
+    int warps = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, avail / (slot_bytes + mrpnp::kWarpHeaderBytes));
     if (warps < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
     // keep every SM busy before stacking warps: at small N spread objects over CTAs
     const int per_sm = (p->n_obj + ctx->num_sms - 1) / ctx->num_sms;
     warps = std::max(1, std::min(warps, per_sm));
     plan->warps = warps;
     plan->ctas = std::min(ctx->num_sms, (p->n_obj + warps - 1) / warps);
-    plan->smem = (int)(mrpnp::kBarrierBytes + warps * slot_bytes);
+    plan->smem = (int)(warps * (slot_bytes + mrpnp::kWarpHeaderBytes));
     const bool aligned = (p->n_pts % 4 == 0) && (((uintptr_t)c3d | (uintptr_t)c2d | (uintptr_t)wgt) % 16 == 0);
     plan->use_tma = aligned ? 1 : 0;
     return MRPNP_OK;
@@ -78,7 +78,7 @@ int check_params(const mrpnp_params* p) {
     if (p->layout != MRPNP_LAYOUT_PLANAR && p->layout != MRPNP_LAYOUT_INTERLEAVED)
         return fail(MRPNP_ERR_ARG, "bad layout%s");
     if (p->weight_mode < 0 || p->weight_mode > 2) return fail(MRPNP_ERR_ARG, "bad weight_mode%s");
-    if (p->precision != MRPNP_PREC_FP64 && p->precision != MRPNP_PREC_FP32) return fail(MRPNP_ERR_ARG, "bad precision%s");
+    if (p->precision != MRPNP_PREC_FP64 && p->precision != MRPNP_PREC_MIXED) return fail(MRPNP_ERR_ARG, "bad precision%s");
     if (p->cov_mode < 0 || p->cov_mode > 2) return fail(MRPNP_ERR_ARG, "bad cov_mode%s");
     if (p->init_mode != MRPNP_INIT_GIVEN && p->init_mode != MRPNP_INIT_LINEAR) return fail(MRPNP_ERR_ARG, "bad init_mode%s");
     if (p->cam_stride != 0 && p->cam_stride != 9) return fail(MRPNP_ERR_ARG, "cam_stride must be 0 or 9%s");
@@ -91,12 +91,12 @@ template <int WMODE, int LAYOUT>
 cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan, cudaStream_t stream) {
     cudaError_t e;
     if (precision == MRPNP_PREC_FP64) {
-        auto k = mrpnp::pnp_lm_kernel<double, WMODE, LAYOUT>;
+        auto k = mrpnp::pnp_lm_kernel<false, WMODE, LAYOUT>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
     } else {
-        auto k = mrpnp::pnp_lm_kernel<float, WMODE, LAYOUT>;
+        auto k = mrpnp::pnp_lm_kernel<true, WMODE, LAYOUT>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
@@ -118,8 +118,8 @@ cudaError_t dispatch(const mrpnp_params* p, const KParams& kp, const LaunchPlan&
 }
 
 int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const float* c2d, const float* wgt,
-                 const float* cam, const float* range, const float* init, const uint8_t* inl_in, float* result,
-                 uint8_t* inl_out, double* result64, cudaStream_t stream) {
+                 const float* cam, const float* range, const float* init, const uint32_t* inl_in, float* result,
+                 uint32_t* inl_out, double* result64, cudaStream_t stream) {
     if (p->n_obj == 0) return MRPNP_OK;
     if (!c3d || !c2d || !wgt || !cam || !range || !result) return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
     if (p->init_mode == MRPNP_INIT_GIVEN && !init) return fail(MRPNP_ERR_ARG, "init_pose is NULL with MRPNP_INIT_GIVEN%s");
@@ -135,7 +135,7 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     kp.cov_mode = p->cov_mode; kp.init_mode = p->init_mode; kp.inlier_opt_only = p->inlier_opt_only;
     kp.max_iter = p->max_iterations; kp.adopt_ftol = p->adopt_candidate_on_ftol;
     kp.use_tma = plan.use_tma;
-    kp.slot_floats = (int)((plan.smem - mrpnp::kBarrierBytes) / plan.warps / sizeof(float));
+    kp.slot_floats = (int)((plan.smem / plan.warps - mrpnp::kWarpHeaderBytes) / sizeof(float));
     kp.z_min = p->z_min; kp.std_scale = p->std_scale; kp.istd_thres = p->istd_thres;
     cudaError_t e = dispatch(p, kp, plan, stream);
     if (e != cudaSuccess) return fail(MRPNP_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
@@ -217,7 +217,7 @@ int mrpnp_kernel_info(mrpnp_ctx* ctx, const mrpnp_params* p, int32_t info[4]) {
 
 int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_3d, const float* coords_2d,
                 const float* weights, const float* cam_mats, const float* uv_range, const float* init_pose,
-                const uint8_t* inlier_in, float* result, uint8_t* inlier_out, double* result64, void* stream) {
+                const uint32_t* inlier_in, float* result, uint32_t* inlier_out, double* result64, void* stream) {
     if (!ctx) return fail(MRPNP_ERR_ARG, "ctx is NULL%s");
     int rc = check_params(p);
     if (rc != MRPNP_OK) return rc;
@@ -232,7 +232,7 @@ int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_3d, c
 // kernel finishes.  Pinned host memory makes the copies truly asynchronous; pageable memory also works.
 int mrpnp_solve_host(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_3d, const float* coords_2d,
                      const float* weights, const float* cam_mats, const float* uv_range, const float* init_pose,
-                     const uint8_t* inlier_in, float* result, uint8_t* inlier_out) {
+                     const uint32_t* inlier_in, float* result, uint32_t* inlier_out) {
     if (!ctx) return fail(MRPNP_ERR_ARG, "ctx is NULL%s");
     int rc = check_params(p);
     if (rc != MRPNP_OK) return rc;
@@ -249,8 +249,9 @@ int mrpnp_solve_host(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_
     auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
     const size_t o3 = 0, o2 = o3 + al(chunk * 3 * P * 4), ow = o2 + al(chunk * 2 * P * 4);
     const size_t oi = ow + al(chunk * wc * P * 4), orr = oi + al((size_t)chunk * 16);
-    const size_t omi = orr + al((size_t)chunk * MRPNP_RESULT_STRIDE * 4), omo = omi + al(chunk * P);
-    const size_t total = omo + al(chunk * P);
+    const size_t W = (P + 31) / 32;  // packed mask words per object
+    const size_t omi = orr + al((size_t)chunk * MRPNP_RESULT_STRIDE * 4), omo = omi + al(chunk * W * 4);
+    const size_t total = omo + al(chunk * W * 4);
     if (total > ctx->chunk_bytes) {
         for (int i = 0; i < kHostStreams; ++i) {
             if (ctx->chunk_buf[i]) MR_CUDA(cudaFree(ctx->chunk_buf[i]));
@@ -282,12 +283,12 @@ int mrpnp_solve_host(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_
         char* base = static_cast<char*>(ctx->chunk_buf[ci % kHostStreams]);
         float* d3 = (float*)(base + o3); float* d2 = (float*)(base + o2); float* dw = (float*)(base + ow);
         float* di = (float*)(base + oi); float* dr = (float*)(base + orr);
-        uint8_t* dmi = (uint8_t*)(base + omi); uint8_t* dmo = (uint8_t*)(base + omo);
+        uint32_t* dmi = (uint32_t*)(base + omi); uint32_t* dmo = (uint32_t*)(base + omo);
         MR_CUDA(cudaMemcpyAsync(d3, coords_3d + (size_t)start * 3 * P, (size_t)n * 3 * P * 4, cudaMemcpyHostToDevice, st));
         MR_CUDA(cudaMemcpyAsync(d2, coords_2d + (size_t)start * 2 * P, (size_t)n * 2 * P * 4, cudaMemcpyHostToDevice, st));
         MR_CUDA(cudaMemcpyAsync(dw, weights + (size_t)start * wc * P, (size_t)n * wc * P * 4, cudaMemcpyHostToDevice, st));
         if (init_pose) MR_CUDA(cudaMemcpyAsync(di, init_pose + (size_t)start * 4, (size_t)n * 16, cudaMemcpyHostToDevice, st));
-        if (inlier_in) MR_CUDA(cudaMemcpyAsync(dmi, inlier_in + (size_t)start * P, (size_t)n * P, cudaMemcpyHostToDevice, st));
+        if (inlier_in) MR_CUDA(cudaMemcpyAsync(dmi, inlier_in + (size_t)start * W, (size_t)n * W * 4, cudaMemcpyHostToDevice, st));
         mrpnp_params q = *p;
         q.n_obj = n;
         rc = solve_device(ctx, &q, d3, d2, dw, d_cam + (p->cam_stride ? (size_t)start * 9 : 0),
@@ -296,7 +297,7 @@ int mrpnp_solve_host(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_
         if (rc != MRPNP_OK) return rc;
         MR_CUDA(cudaMemcpyAsync(result + (size_t)start * MRPNP_RESULT_STRIDE, dr, (size_t)n * MRPNP_RESULT_STRIDE * 4,
                                 cudaMemcpyDeviceToHost, st));
-        if (inlier_out) MR_CUDA(cudaMemcpyAsync(inlier_out + (size_t)start * P, dmo, (size_t)n * P, cudaMemcpyDeviceToHost, st));
+        if (inlier_out) MR_CUDA(cudaMemcpyAsync(inlier_out + (size_t)start * W, dmo, (size_t)n * W * 4, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < kHostStreams; ++i) MR_CUDA(cudaStreamSynchronize(ctx->streams[i]));
     return MRPNP_OK;

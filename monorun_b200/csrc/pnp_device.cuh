@@ -4,8 +4,8 @@
 // into the warp's shared-memory slot with 1-D bulk TMA copies (cp.async.bulk + mbarrier), the istd
 // inlier test compacts it in place, and every Levenberg-Marquardt pass streams the compacted points
 // from shared memory, accumulating cost, J^T r and the upper triangle of J^T J in registers, followed by
-// a warp-shuffle butterfly.  The 4x4 damped solve and the trust-region bookkeeping run redundantly on all
-// lanes in fp64 (no divergence, no broadcast).
+// a transposed warp-shuffle reduction.  The 4x4 damped solve and the trust-region bookkeeping run
+// redundantly on all lanes in fp64 (no divergence, no broadcast).
 //
 // Reference semantics being reproduced (see DESIGN.md section 2 for the full table):
 //   residual + clips   monorun/ops/least_squares/src/pnp_uncert_cpu.cpp:24-51, :189-217
@@ -22,9 +22,9 @@ namespace mrpnp {
 
 constexpr int kMaxWarpsPerCta = 10;        // 10 x 21,952 B slots fill the 227 KB of one SM at P = 784
 constexpr int kMaxThreads = kMaxWarpsPerCta * 32;
-constexpr int kBarrierBytes = 128;          // one 8-byte mbarrier per warp, padded
+constexpr int kWarpHeaderBytes = 256;      // per warp: mbarrier (8 B) + 16-double reduction scratch at +128
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kNumAcc = 15;                 // |r|^2, g[4], upper-tri(J^T J)[10]
+constexpr int kMaxRows = MRPNP_MAX_POINTS / 32;
 
 struct KParams {
     const float* c3d;
@@ -33,11 +33,11 @@ struct KParams {
     const float* cam;
     const float* range;
     const float* init;
-    const uint8_t* inl_in;
+    const uint32_t* inl_in;   // packed: word k of object n = inlier bits of points 32k..32k+31
     float* result;
-    uint8_t* inl_out;
+    uint32_t* inl_out;        // packed, same layout
     double* result64;
-    int* counters;  // [0] next object, [1] finished CTAs (self-resetting)
+    int* counters;            // [0] next object, [1] finished CTAs (self-resetting)
     int n_obj, n_pts, cam_stride, range_stride;
     int cov_mode, init_mode, inlier_opt_only, max_iter, adopt_ftol;
     int use_tma, slot_floats;
@@ -97,7 +97,31 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// fp64 reciprocal: MUFU.RCP64H seed (2^-23) + two Newton steps on the fp64 pipe (no slow-path branch).
+// Transposed all-reduce of 16 per-lane partial sums: 8+4+2+1+1 = 16 shuffles instead of 16 x 5.
+// After the exchange lane L holds the total of value L>>1; the totals go through the warp's shared
+// scratch so that every lane ends with all 16 (bitwise identical on all lanes, fixed summation tree).
+template <typename T>
+__device__ __forceinline__ void warp_allreduce16(T v[16], T* scratch, int lane) {
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const T send = up ? v[i] : v[i + half];
+            const T keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, bit);
+        }
+    }
+    v[0] += __shfl_xor_sync(kFull, v[0], 1);
+    __syncwarp();
+    scratch[lane >> 1] = v[0];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = scratch[i];
+}
+
+// fp64 reciprocal / square root: MUFU seed (2^-23) + two Newton steps on the fp64 pipe.
+// No slow-path branch; relative error ~1e-16 (not correctly rounded).
 __device__ __forceinline__ double fast_rcp(double z) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(z));
@@ -107,6 +131,24 @@ __device__ __forceinline__ double fast_rcp(double z) {
     x = fma(x, e, x);
     return x;
 }
+__device__ __forceinline__ float fast_rcp(float z) {
+    float x;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(z));
+    return x;
+}
+__device__ __forceinline__ double fast_sqrt(double a) {  // a >= 0; returns 0 for a == 0
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double h = 0.5 * y;
+    double e = fma(-a * y, h, 0.5);  // 0.5 - 0.5 a y^2
+    y = fma(y, e, y);
+    h = 0.5 * y;
+    e = fma(-a * y, h, 0.5);
+    y = fma(y, e, y);
+    double s = a * y;
+    s = fma(0.5 * y, fma(-s, s, a), s);  // one correction of sqrt itself
+    return a > 0.0 ? s : 0.0;
+}
 
 template <typename T>
 struct Camera {
@@ -114,78 +156,65 @@ struct Camera {
     T z_min, u_min, u_max, v_min, v_max;
 };
 
-__device__ __forceinline__ float fast_rcp(float z) {
-    float x;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(z));
-    return x;
-}
-__device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
-__device__ __forceinline__ void sincos_t(double a, float* s, float* c) {
-    double sd, cd;  // once per pass: keep the rotation exact, round once
-    sincos(a, &sd, &cd);
-    *s = (float)sd;
-    *c = (float)cd;
-}
-
-// ------------------------------------------------------------------ fused residual / Jacobian / normal-equation pass
-// Accumulates, over this lane's share of the n active points,
+// ------------------------------------------------------------------ fused pass, fp64 arithmetic (MRPNP_PREC_FP64)
+// Accumulates over this lane's share of the n active points and all-reduces over the warp:
 //   acc[0]     sum |r|^2
 //   acc[1..4]  J^T r        (order yaw, tx, ty, tz)
 //   acc[5..14] J^T J upper triangle  (00 01 02 03 11 12 13 22 23 33)
-// and butterfly-reduces them over the warp (every lane ends with the full sums).
-// T = double reproduces the fp64 reference arithmetic; T = float is the fast path.
+// Every operation is fp64 in the reference's own order of evaluation, so decisions of the LM loop are
+// reproduced exactly.
 // CLIPSEM 0: Ceres-Jet semantics (pnp_uncert_cpu.cpp:36-42): z clip drops only d/dz', u/v clamp drops that row.
 // CLIPSEM 1: jacobian.py:52-59 semantics: a z-clipped point loses both rows (used for the pipeline covariance).
 // USE_BITS : skip points whose bit in `bits` (bit k <-> point 32k+lane) is 0 (outliers when not compacted).
-// Returns in `clip` whether any point processed by this lane hit a clip.
-template <typename T, int WMODE, int LAYOUT, int CLIPSEM, bool USE_BITS>
-__device__ __forceinline__ void eval_pass(const float* __restrict__ s3, const float* __restrict__ s2,
-                                          const float* __restrict__ sw, int P, int n, int lane, uint32_t bits,
-                                          const double x[4], const Camera<T>& cam, T acc[kNumAcc], bool& clip) {
+// `clip` returns whether any point of the warp hit a clip.
+template <int WMODE, int LAYOUT, int CLIPSEM, bool USE_BITS>
+__device__ __forceinline__ void eval_pass_fp64(const float* __restrict__ s3, const float* __restrict__ s2,
+                                               const float* __restrict__ sw, int P, int n, int lane, uint32_t bits,
+                                               const double x[4], const Camera<double>& cam, double acc[16],
+                                               double* scratch, bool& clip) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
-    T sn, cs;
-    sincos_t(x[0], &sn, &cs);
-    const T tx = (T)x[1], ty = (T)x[2], tz = (T)x[3];
-    const T zero = (T)0, one = (T)1;
+    double sn, cs;
+    sincos(x[0], &sn, &cs);
+    const double tx = x[1], ty = x[2], tz = x[3];
 #pragma unroll
-    for (int i = 0; i < kNumAcc; ++i) acc[i] = zero;
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
     bool any = false;
 #pragma unroll 2
     for (int p = lane, k = 0; p < n; p += 32, ++k) {
         if (USE_BITS && !((bits >> k) & 1u)) continue;
-        const T X = (T)s3[sidx<LAYOUT, 3>(p, 0, P)];
-        const T Y = (T)s3[sidx<LAYOUT, 3>(p, 1, P)];
-        const T Z = (T)s3[sidx<LAYOUT, 3>(p, 2, P)];
-        const T uo = (T)s2[sidx<LAYOUT, 2>(p, 0, P)];
-        const T vo = (T)s2[sidx<LAYOUT, 2>(p, 1, P)];
-        const T qx = fma(cs, X, sn * Z);
-        const T qz = fma(cs, Z, -sn * X);
-        const T xc = qx + tx, yc = Y + ty, zc = qz + tz;
+        const double X = (double)s3[sidx<LAYOUT, 3>(p, 0, P)];
+        const double Y = (double)s3[sidx<LAYOUT, 3>(p, 1, P)];
+        const double Z = (double)s3[sidx<LAYOUT, 3>(p, 2, P)];
+        const double uo = (double)s2[sidx<LAYOUT, 2>(p, 0, P)];
+        const double vo = (double)s2[sidx<LAYOUT, 2>(p, 1, P)];
+        const double qx = fma(cs, X, sn * Z);
+        const double qz = fma(cs, Z, -sn * X);
+        const double xc = qx + tx, yc = Y + ty, zc = qz + tz;
         const bool zfree = !(zc < cam.z_min);
-        const T z = zfree ? zc : cam.z_min;
-        const T iz = fast_rcp(z);
-        const T xn = xc * iz, yn = yc * iz;
-        T pu = fma(cam.fx, xn, cam.cx);
-        T pv = fma(cam.fy, yn, cam.cy);
+        const double z = zfree ? zc : cam.z_min;
+        const double iz = fast_rcp(z);
+        const double xn = xc * iz, yn = yc * iz;
+        double pu = fma(cam.fx, xn, cam.cx);
+        double pv = fma(cam.fy, yn, cam.cy);
         bool ufree = true, vfree = true;
         if (pu < cam.u_min) { pu = cam.u_min; ufree = false; } else if (pu > cam.u_max) { pu = cam.u_max; ufree = false; }
         if (pv < cam.v_min) { pv = cam.v_min; vfree = false; } else if (pv > cam.v_max) { pv = cam.v_max; vfree = false; }
         any = any || !zfree || !ufree || !vfree;
-        const T du = pu - uo, dv = pv - vo;
-        const T mz = zfree ? one : zero;
+        const double du = pu - uo, dv = pv - vo;
+        const double mz = zfree ? 1.0 : 0.0;
         if (CLIPSEM == 1 && !zfree) { ufree = false; vfree = false; }
         // unweighted projection Jacobian rows: Ju = (ju0, a_u, 0, b_u), Jv = (jv0, 0, a_v, b_v)
-        const T au = ufree ? cam.fx * iz : zero;
-        const T av = vfree ? cam.fy * iz : zero;
-        const T bu = -au * xn * mz, bv = -av * yn * mz;
-        const T ju0 = fma(au, qz, -bu * qx);
-        const T jv0 = -bv * qx;
+        const double au = ufree ? cam.fx * iz : 0.0;
+        const double av = vfree ? cam.fy * iz : 0.0;
+        const double bu = -au * xn * mz, bv = -av * yn * mz;
+        const double ju0 = fma(au, qz, -bu * qx);
+        const double jv0 = -bv * qx;
         if (WMODE != MRPNP_W_FULL) {
-            const T wu = (T)sw[sidx<LAYOUT, WC>(p, 0, P)];
-            const T wv = (T)sw[sidx<LAYOUT, WC>(p, 1, P)];
-            const T ru = wu * du, rv = wv * dv;
-            const T a0 = wu * ju0, a1 = wu * au, a3 = wu * bu;   // row u: (a0, a1, 0, a3)
-            const T b0 = wv * jv0, b2 = wv * av, b3 = wv * bv;   // row v: (b0, 0, b2, b3)
+            const double wu = (double)sw[sidx<LAYOUT, WC>(p, 0, P)];
+            const double wv = (double)sw[sidx<LAYOUT, WC>(p, 1, P)];
+            const double ru = wu * du, rv = wv * dv;
+            const double a0 = wu * ju0, a1 = wu * au, a3 = wu * bu;   // row u: (a0, a1, 0, a3)
+            const double b0 = wv * jv0, b2 = wv * av, b3 = wv * bv;   // row v: (b0, 0, b2, b3)
             acc[0] = fma(ru, ru, fma(rv, rv, acc[0]));
             acc[1] = fma(a0, ru, fma(b0, rv, acc[1]));
             acc[2] = fma(a1, ru, acc[2]);
@@ -202,13 +231,13 @@ __device__ __forceinline__ void eval_pass(const float* __restrict__ s3, const fl
             acc[13] = fma(b2, b3, acc[13]);
             acc[14] = fma(a3, a3, fma(b3, b3, acc[14]));
         } else {
-            const T wxx = (T)sw[sidx<LAYOUT, WC>(p, 0, P)];
-            const T wxy = (T)sw[sidx<LAYOUT, WC>(p, 1, P)];
-            const T wyy = (T)sw[sidx<LAYOUT, WC>(p, 2, P)];
-            const T r0 = fma(wxx, du, wxy * dv), r1 = fma(wxy, du, wyy * dv);
+            const double wxx = (double)sw[sidx<LAYOUT, WC>(p, 0, P)];
+            const double wxy = (double)sw[sidx<LAYOUT, WC>(p, 1, P)];
+            const double wyy = (double)sw[sidx<LAYOUT, WC>(p, 2, P)];
+            const double r0 = fma(wxx, du, wxy * dv), r1 = fma(wxy, du, wyy * dv);
             // whitened rows: r0-row = wxx*Ju + wxy*Jv, r1-row = wxy*Ju + wyy*Jv
-            const T a0 = fma(wxx, ju0, wxy * jv0), a1 = wxx * au, a2 = wxy * av, a3 = fma(wxx, bu, wxy * bv);
-            const T b0 = fma(wxy, ju0, wyy * jv0), b1 = wxy * au, b2 = wyy * av, b3 = fma(wxy, bu, wyy * bv);
+            const double a0 = fma(wxx, ju0, wxy * jv0), a1 = wxx * au, a2 = wxy * av, a3 = fma(wxx, bu, wxy * bv);
+            const double b0 = fma(wxy, ju0, wyy * jv0), b1 = wxy * au, b2 = wyy * av, b3 = fma(wxy, bu, wyy * bv);
             acc[0] = fma(r0, r0, fma(r1, r1, acc[0]));
             acc[1] = fma(a0, r0, fma(b0, r1, acc[1]));
             acc[2] = fma(a1, r0, fma(b1, r1, acc[2]));
@@ -226,9 +255,145 @@ __device__ __forceinline__ void eval_pass(const float* __restrict__ s3, const fl
             acc[14] = fma(a3, a3, fma(b3, b3, acc[14]));
         }
     }
-    clip = any;
+    clip = __any_sync(kFull, any);
+    warp_allreduce16<double>(acc, scratch, lane);
+}
+
+// ------------------------------------------------------------------ fused pass, mixed precision (MRPNP_PREC_MIXED)
+// The residual chain (rotation, projection, pixel difference, weighting) and the cost sum run in fp64 on
+// the fp64 pipe, so cost and cost differences -- what the trust-region accept / function-tolerance tests
+// read -- agree with the fp64 reference to ~1e-15.  The Jacobian, J^T r and J^T J are built from an
+// independent fp32 projection on the FMA pipe (errors ~1e-7 relative, which only perturb the step).
+// Rows in which any lane is clipped (never on in-range data) take the exact fp64 routine instead.
+// Output layout as eval_pass_fp64.
+template <int WMODE, int LAYOUT, int CLIPSEM, bool USE_BITS>
+__device__ __forceinline__ void eval_pass_mixed(const float* __restrict__ s3, const float* __restrict__ s2,
+                                                const float* __restrict__ sw, int P, int n, int lane, uint32_t bits,
+                                                const double x[4], const Camera<double>& cam,
+                                                const Camera<float>& camf, double acc[16], double* scratch,
+                                                bool& clip) {
+    constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
+    double sn, cs;
+    sincos(x[0], &sn, &cs);
+    const double tx = x[1], ty = x[2], tz = x[3];
+    const float snf = (float)sn, csf = (float)cs, txf = (float)tx, tyf = (float)ty, tzf = (float)tz;
+    double cost2 = 0.0;
+    float a[16];
 #pragma unroll
-    for (int i = 0; i < kNumAcc; ++i) acc[i] = warp_sum(acc[i]);
+    for (int i = 0; i < 16; ++i) a[i] = 0.f;
+    bool any = false;
+    const int rows = (n + 31) >> 5;
+#pragma unroll 2
+    for (int k = 0; k < rows; ++k) {
+        const int pr = k * 32 + lane;
+        bool valid = pr < n;
+        if (USE_BITS) valid = valid && ((bits >> k) & 1u);
+        const int p = pr < n ? pr : n - 1;
+        const float Xf = s3[sidx<LAYOUT, 3>(p, 0, P)], Yf = s3[sidx<LAYOUT, 3>(p, 1, P)], Zf = s3[sidx<LAYOUT, 3>(p, 2, P)];
+        const float uf = s2[sidx<LAYOUT, 2>(p, 0, P)], vf = s2[sidx<LAYOUT, 2>(p, 1, P)];
+        float w0 = sw[sidx<LAYOUT, WC>(p, 0, P)], w1 = sw[sidx<LAYOUT, WC>(p, 1, P)];
+        float w2 = (WMODE == MRPNP_W_FULL) ? sw[sidx<LAYOUT, WC>(p, WC - 1, P)] : 0.f;
+        if (!valid) { w0 = 0.f; w1 = 0.f; w2 = 0.f; }  // padding lanes / outliers contribute nothing
+        // ---- fp64 residual chain ----
+        const double X = (double)Xf, Y = (double)Yf, Z = (double)Zf;
+        const double qx = fma(cs, X, sn * Z);
+        const double qz = fma(cs, Z, -sn * X);
+        const double xc = qx + tx, yc = Y + ty, zc = qz + tz;
+        const double iz = fast_rcp(zc);
+        const double pu = fma(cam.fx, xc * iz, cam.cx);
+        const double pv = fma(cam.fy, yc * iz, cam.cy);
+        const bool flagged = (zc < cam.z_min) || (pu < cam.u_min) || (pu > cam.u_max) || (pv < cam.v_min) || (pv > cam.v_max);
+        if (__any_sync(kFull, flagged && valid)) {
+            // ---- exact slow row: full clip semantics in fp64 ----
+            any = true;
+            const bool zfree = !(zc < cam.z_min);
+            const double z = zfree ? zc : cam.z_min;
+            const double izc = fast_rcp(z);
+            const double xn = xc * izc, yn = yc * izc;
+            double pu2 = fma(cam.fx, xn, cam.cx), pv2 = fma(cam.fy, yn, cam.cy);
+            bool ufree = true, vfree = true;
+            if (pu2 < cam.u_min) { pu2 = cam.u_min; ufree = false; } else if (pu2 > cam.u_max) { pu2 = cam.u_max; ufree = false; }
+            if (pv2 < cam.v_min) { pv2 = cam.v_min; vfree = false; } else if (pv2 > cam.v_max) { pv2 = cam.v_max; vfree = false; }
+            const double du = pu2 - (double)uf, dv = pv2 - (double)vf;
+            const double mz = zfree ? 1.0 : 0.0;
+            if (CLIPSEM == 1 && !zfree) { ufree = false; vfree = false; }
+            const double au = ufree ? cam.fx * izc : 0.0, av = vfree ? cam.fy * izc : 0.0;
+            const double bu = -au * xn * mz, bv = -av * yn * mz;
+            const double ju0 = fma(au, qz, -bu * qx), jv0 = -bv * qx;
+            const double wxx = (double)w0, wxy = (WMODE == MRPNP_W_FULL) ? (double)w1 : 0.0;
+            const double wyy = (WMODE == MRPNP_W_FULL) ? (double)w2 : (double)w1;
+            const double r0 = fma(wxx, du, wxy * dv), r1 = fma(wxy, du, wyy * dv);
+            const double ja[4] = {fma(wxx, ju0, wxy * jv0), wxx * au, wxy * av, fma(wxx, bu, wxy * bv)};
+            const double jb[4] = {fma(wxy, ju0, wyy * jv0), wxy * au, wyy * av, fma(wxy, bu, wyy * bv)};
+            cost2 = fma(r0, r0, fma(r1, r1, cost2));
+            int q = 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] += (float)fma(ja[i], r0, jb[i] * r1);
+#pragma unroll
+                for (int j = i; j < 4; ++j, ++q) a[q] += (float)fma(ja[i], ja[j], jb[i] * jb[j]);
+            }
+            continue;
+        }
+        const double du = pu - (double)uf, dv = pv - (double)vf;
+        // ---- fp32 Jacobian branch (independent projection; no clip on this row) ----
+        const float qxf = fmaf(csf, Xf, snf * Zf), qzf = fmaf(csf, Zf, -snf * Xf);
+        const float xcf = qxf + txf, ycf = Yf + tyf, zcf = qzf + tzf;
+        const float izf = fast_rcp(zcf);
+        const float xnf = xcf * izf, ynf = ycf * izf;
+        const float au = camf.fx * izf, av = camf.fy * izf;
+        const float bu = -au * xnf, bv = -av * ynf;
+        const float ju0 = fmaf(au, qzf, -bu * qxf), jv0 = -bv * qxf;
+        if (WMODE != MRPNP_W_FULL) {
+            const double ru = (double)w0 * du, rv = (double)w1 * dv;
+            cost2 = fma(ru, ru, fma(rv, rv, cost2));
+            const float ruf = w0 * (fmaf(camf.fx, xnf, camf.cx) - uf), rvf = w1 * (fmaf(camf.fy, ynf, camf.cy) - vf);
+            const float a0 = w0 * ju0, a1 = w0 * au, a3 = w0 * bu;
+            const float b0 = w1 * jv0, b2 = w1 * av, b3 = w1 * bv;
+            a[0] = fmaf(a0, ruf, fmaf(b0, rvf, a[0]));
+            a[1] = fmaf(a1, ruf, a[1]);
+            a[2] = fmaf(b2, rvf, a[2]);
+            a[3] = fmaf(a3, ruf, fmaf(b3, rvf, a[3]));
+            a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
+            a[5] = fmaf(a0, a1, a[5]);
+            a[6] = fmaf(b0, b2, a[6]);
+            a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
+            a[8] = fmaf(a1, a1, a[8]);
+            a[10] = fmaf(a1, a3, a[10]);
+            a[11] = fmaf(b2, b2, a[11]);
+            a[12] = fmaf(b2, b3, a[12]);
+            a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
+        } else {
+            const double r0 = fma((double)w0, du, (double)w1 * dv), r1 = fma((double)w1, du, (double)w2 * dv);
+            cost2 = fma(r0, r0, fma(r1, r1, cost2));
+            const float duf = fmaf(camf.fx, xnf, camf.cx) - uf, dvf = fmaf(camf.fy, ynf, camf.cy) - vf;
+            const float r0f = fmaf(w0, duf, w1 * dvf), r1f = fmaf(w1, duf, w2 * dvf);
+            const float a0 = fmaf(w0, ju0, w1 * jv0), a1 = w0 * au, a2 = w1 * av, a3 = fmaf(w0, bu, w1 * bv);
+            const float b0 = fmaf(w1, ju0, w2 * jv0), b1 = w1 * au, b2 = w2 * av, b3 = fmaf(w1, bu, w2 * bv);
+            a[0] = fmaf(a0, r0f, fmaf(b0, r1f, a[0]));
+            a[1] = fmaf(a1, r0f, fmaf(b1, r1f, a[1]));
+            a[2] = fmaf(a2, r0f, fmaf(b2, r1f, a[2]));
+            a[3] = fmaf(a3, r0f, fmaf(b3, r1f, a[3]));
+            a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
+            a[5] = fmaf(a0, a1, fmaf(b0, b1, a[5]));
+            a[6] = fmaf(a0, a2, fmaf(b0, b2, a[6]));
+            a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
+            a[8] = fmaf(a1, a1, fmaf(b1, b1, a[8]));
+            a[9] = fmaf(a1, a2, fmaf(b1, b2, a[9]));
+            a[10] = fmaf(a1, a3, fmaf(b1, b3, a[10]));
+            a[11] = fmaf(a2, a2, fmaf(b2, b2, a[11]));
+            a[12] = fmaf(a2, a3, fmaf(b2, b3, a[12]));
+            a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
+        }
+    }
+    clip = any;
+    // cost: 5-step fp64 butterfly; the 14 fp32 sums: transposed reduction through the scratch
+    cost2 = warp_sum(cost2);
+    warp_allreduce16<float>(a, reinterpret_cast<float*>(scratch), lane);
+    acc[0] = cost2;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[1 + i] = (double)a[i];
+    acc[15] = 0.0;
 }
 
 // ------------------------------------------------------------------ 4x4 SPD helpers (fp64, fully unrolled)
@@ -237,63 +402,57 @@ __device__ __forceinline__ constexpr int tri(int i, int j) {
     return i <= j ? (i * 4 - (i * (i - 1)) / 2 + (j - i)) : (j * 4 - (j * (j - 1)) / 2 + (i - j));
 }
 
-// Cholesky A = L L^T of the packed symmetric A; L packed by tri(j,i) (i >= j).  false if not SPD.
-__device__ __forceinline__ bool chol4(const double A[10], double L[10]) {
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        double d = A[tri(j, j)];
-#pragma unroll
-        for (int k = 0; k < j; ++k) d = fma(-L[tri(k, j)], L[tri(k, j)], d);
-        ok = ok && (d > 0.0) && (d < 1.7e308);
-        const double ld = sqrt(d);
-        const double inv = 1.0 / ld;
-        L[tri(j, j)] = ld;
-#pragma unroll
-        for (int i = j + 1; i < 4; ++i) {
-            double s = A[tri(j, i)];
-#pragma unroll
-            for (int k = 0; k < j; ++k) s = fma(-L[tri(k, i)], L[tri(k, j)], s);
-            L[tri(j, i)] = s * inv;  // element L[i][j] stored at tri(j,i)
-        }
-    }
-    return ok;
+// A = L D L^T of the packed symmetric A (unit lower L, reciprocal pivots), without square roots and
+// with fast reciprocals.  ok == false if a pivot is not positive/finite (A not SPD).
+struct Ldl4 {
+    double l10, l20, l30, l21, l31, l32;
+    double i0, i1, i2, i3;
+    bool ok;
+};
+__device__ __forceinline__ Ldl4 ldl4_factor(const double A[10]) {
+    Ldl4 f;
+    const double d0 = A[0];
+    f.i0 = fast_rcp(d0);
+    f.l10 = A[1] * f.i0; f.l20 = A[2] * f.i0; f.l30 = A[3] * f.i0;
+    const double d1 = fma(-f.l10, A[1], A[4]);
+    f.i1 = fast_rcp(d1);
+    const double t21 = fma(-f.l20, A[1], A[5]), t31 = fma(-f.l30, A[1], A[6]);
+    f.l21 = t21 * f.i1; f.l31 = t31 * f.i1;
+    const double d2 = fma(-f.l21, t21, fma(-f.l20, A[2], A[7]));
+    f.i2 = fast_rcp(d2);
+    const double t32 = fma(-f.l31, t21, fma(-f.l30, A[2], A[8]));
+    f.l32 = t32 * f.i2;
+    const double d3 = fma(-f.l32, t32, fma(-f.l31, t31, fma(-f.l30, A[3], A[9])));
+    f.i3 = fast_rcp(d3);
+    f.ok = (d0 > 0.0) && (d1 > 0.0) && (d2 > 0.0) && (d3 > 0.0) && (d0 < 1.7e308) && (d1 < 1.7e308) &&
+           (d2 < 1.7e308) && (d3 < 1.7e308);
+    return f;
 }
-
-// Solve L L^T y = b.
-__device__ __forceinline__ void chol4_solve(const double L[10], const double b[4], double y[4]) {
-    double w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double s = b[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) s = fma(-L[tri(k, i)], w[k], s);
-        w[i] = s / L[tri(i, i)];
-    }
-#pragma unroll
-    for (int i = 3; i >= 0; --i) {
-        double s = w[i];
-#pragma unroll
-        for (int k = i + 1; k < 4; ++k) s = fma(-L[tri(i, k)], y[k], s);
-        y[i] = s / L[tri(i, i)];
-    }
+__device__ __forceinline__ void ldl4_solve(const Ldl4& f, const double b[4], double y[4]) {
+    const double z0 = b[0];
+    const double z1 = fma(-f.l10, z0, b[1]);
+    const double z2 = fma(-f.l21, z1, fma(-f.l20, z0, b[2]));
+    const double z3 = fma(-f.l32, z2, fma(-f.l31, z1, fma(-f.l30, z0, b[3])));
+    y[3] = z3 * f.i3;
+    y[2] = fma(-f.l32, y[3], z2 * f.i2);
+    y[1] = fma(-f.l31, y[3], fma(-f.l21, y[2], z1 * f.i1));
+    y[0] = fma(-f.l30, y[3], fma(-f.l20, y[2], fma(-f.l10, y[1], z0 * f.i0)));
 }
 
 // Full inverse of the packed SPD matrix H into row-major inv[16]; false if not SPD.
 __device__ __forceinline__ bool spd_inverse4(const double H[10], double inv[16]) {
-    double L[10];
-    if (!chol4(H, L)) return false;
+    const Ldl4 f = ldl4_factor(H);
+    if (!f.ok) return false;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         double e[4] = {0.0, 0.0, 0.0, 0.0}, y[4];
         e[c] = 1.0;
-        chol4_solve(L, e, y);
+        ldl4_solve(f, e, y);
 #pragma unroll
         for (int r = 0; r < 4; ++r) inv[r * 4 + c] = y[r];
     }
     return true;
 }
-
 
 // ------------------------------------------------------------------ on-device linear initialiser
 // Replaces cv2.solvePnP(EPNP) of pnp_uncert_cpu.py:53-58 as the LM starting point.  With the rotation
@@ -305,20 +464,22 @@ __device__ __forceinline__ bool spd_inverse4(const double H[10], double inv[16])
 template <int N>
 __device__ __forceinline__ bool chol_solve_dense(double A[N][N], const double b[N], double x[N]) {
     bool ok = true;
+    double inv[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         double d = A[j][j];
 #pragma unroll
         for (int k = 0; k < j; ++k) d = fma(-A[j][k], A[j][k], d);
         ok = ok && (d > 0.0) && (d < 1.7e308);
-        const double ld = sqrt(d), inv = 1.0 / ld;
+        const double ld = fast_sqrt(d);
+        inv[j] = fast_rcp(ld);
         A[j][j] = ld;
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
             double v = A[i][j];
 #pragma unroll
             for (int k = 0; k < j; ++k) v = fma(-A[i][k], A[j][k], v);
-            A[i][j] = v * inv;
+            A[i][j] = v * inv[j];
         }
     }
     double w[N];
@@ -327,46 +488,47 @@ __device__ __forceinline__ bool chol_solve_dense(double A[N][N], const double b[
         double v = b[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) v = fma(-A[i][k], w[k], v);
-        w[i] = v / A[i][i];
+        w[i] = v * inv[i];
     }
 #pragma unroll
     for (int i = N - 1; i >= 0; --i) {
         double v = w[i];
 #pragma unroll
         for (int k = i + 1; k < N; ++k) v = fma(-A[k][i], x[k], v);
-        x[i] = v / A[i][i];
+        x[i] = v * inv[i];
     }
     return ok;
 }
 
-template <typename T, int WMODE, int LAYOUT>
+// fp32 accumulation of the (well-scaled, normalised-coordinate) normal equations, fp64 solves.
+template <int WMODE, int LAYOUT>
 __device__ __forceinline__ bool linear_init(const float* __restrict__ s3, const float* __restrict__ s2,
                                             const float* __restrict__ sw, int P, int n, int lane,
-                                            const Camera<T>& cam, double x[4]) {
+                                            const Camera<float>& cam, float* scratch, double x[4]) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
-    const T ifx = (T)1 / cam.fx, ify = (T)1 / cam.fy;
-    // ---- stage A: 5 unknowns ----
-    T m[15], r[5];
+    const float ifx = 1.f / cam.fx, ify = 1.f / cam.fy;
+    // ---- stage A: 5 unknowns: 15 matrix entries + 5 rhs = 20 sums -> two transposed reductions ----
+    float m[16], r[16];
 #pragma unroll
-    for (int i = 0; i < 15; ++i) m[i] = (T)0;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) r[i] = (T)0;
+    for (int i = 0; i < 16; ++i) { m[i] = 0.f; r[i] = 0.f; }
     for (int p = lane; p < n; p += 32) {
-        const T X = (T)s3[sidx<LAYOUT, 3>(p, 0, P)], Y = (T)s3[sidx<LAYOUT, 3>(p, 1, P)], Z = (T)s3[sidx<LAYOUT, 3>(p, 2, P)];
-        const T un = ((T)s2[sidx<LAYOUT, 2>(p, 0, P)] - cam.cx) * ifx;
-        const T vn = ((T)s2[sidx<LAYOUT, 2>(p, 1, P)] - cam.cy) * ify;
-        const T wu = (T)sw[sidx<LAYOUT, WC>(p, 0, P)] * cam.fx, wv = (T)sw[sidx<LAYOUT, WC>(p, WC - 1, P)] * cam.fy;
-        const T a[5] = {wu * (X - un * Z), wu * (Z + un * X), wu, (T)0, -wu * un};
-        const T b[5] = {-wv * vn * Z, wv * vn * X, (T)0, wv, -wv * vn};
-        const T rb = -wv * Y;
+        const float X = s3[sidx<LAYOUT, 3>(p, 0, P)], Y = s3[sidx<LAYOUT, 3>(p, 1, P)], Z = s3[sidx<LAYOUT, 3>(p, 2, P)];
+        const float un = (s2[sidx<LAYOUT, 2>(p, 0, P)] - cam.cx) * ifx;
+        const float vn = (s2[sidx<LAYOUT, 2>(p, 1, P)] - cam.cy) * ify;
+        const float wu = sw[sidx<LAYOUT, WC>(p, 0, P)] * cam.fx, wv = sw[sidx<LAYOUT, WC>(p, WC - 1, P)] * cam.fy;
+        const float a[5] = {wu * (X - un * Z), wu * (Z + un * X), wu, 0.f, -wu * un};
+        const float b[5] = {-wv * vn * Z, wv * vn * X, 0.f, wv, -wv * vn};
+        const float rb = -wv * Y;
         int q = 0;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
 #pragma unroll
-            for (int j = i; j < 5; ++j, ++q) m[q] = fma(a[i], a[j], fma(b[i], b[j], m[q]));
-            r[i] = fma(b[i], rb, r[i]);
+            for (int j = i; j < 5; ++j, ++q) m[q] = fmaf(a[i], a[j], fmaf(b[i], b[j], m[q]));
+            r[i] = fmaf(b[i], rb, r[i]);
         }
     }
+    warp_allreduce16<float>(m, scratch, lane);
+    warp_allreduce16<float>(r, scratch, lane);
     double A[5][5], rhs[5], sol[5];
     {
         int q = 0;
@@ -374,50 +536,48 @@ __device__ __forceinline__ bool linear_init(const float* __restrict__ s3, const 
         for (int i = 0; i < 5; ++i) {
 #pragma unroll
             for (int j = i; j < 5; ++j, ++q) {
-                const double v = (double)warp_sum(m[q]);
-                A[i][j] = v;
-                A[j][i] = v;
+                A[i][j] = (double)m[q];
+                A[j][i] = (double)m[q];
             }
-            rhs[i] = (double)warp_sum(r[i]);
+            rhs[i] = (double)r[i];
         }
     }
     if (!chol_solve_dense<5>(A, rhs, sol)) return false;
     const double yaw = atan2(sol[1], sol[0]);
     // ---- stage B: translation with yaw fixed ----
-    T sn, cs;
-    sincos_t(yaw, &sn, &cs);
-    T m3[6], r3[3];
+    double snd, csd;
+    sincos(yaw, &snd, &csd);
+    const float sn = (float)snd, cs = (float)csd;
+    float m3[16];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) m3[i] = (T)0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) r3[i] = (T)0;
+    for (int i = 0; i < 16; ++i) m3[i] = 0.f;
     for (int p = lane; p < n; p += 32) {
-        const T X = (T)s3[sidx<LAYOUT, 3>(p, 0, P)], Y = (T)s3[sidx<LAYOUT, 3>(p, 1, P)], Z = (T)s3[sidx<LAYOUT, 3>(p, 2, P)];
-        const T un = ((T)s2[sidx<LAYOUT, 2>(p, 0, P)] - cam.cx) * ifx;
-        const T vn = ((T)s2[sidx<LAYOUT, 2>(p, 1, P)] - cam.cy) * ify;
-        const T wu = (T)sw[sidx<LAYOUT, WC>(p, 0, P)] * cam.fx, wv = (T)sw[sidx<LAYOUT, WC>(p, WC - 1, P)] * cam.fy;
-        const T qx = fma(cs, X, sn * Z), qz = fma(cs, Z, -sn * X);
+        const float X = s3[sidx<LAYOUT, 3>(p, 0, P)], Y = s3[sidx<LAYOUT, 3>(p, 1, P)], Z = s3[sidx<LAYOUT, 3>(p, 2, P)];
+        const float un = (s2[sidx<LAYOUT, 2>(p, 0, P)] - cam.cx) * ifx;
+        const float vn = (s2[sidx<LAYOUT, 2>(p, 1, P)] - cam.cy) * ify;
+        const float wu = sw[sidx<LAYOUT, WC>(p, 0, P)] * cam.fx, wv = sw[sidx<LAYOUT, WC>(p, WC - 1, P)] * cam.fy;
+        const float qx = fmaf(cs, X, sn * Z), qz = fmaf(cs, Z, -sn * X);
         // rows: wu [1 0 -un] t = -wu (qx - un qz);  wv [0 1 -vn] t = -wv (Y - vn qz)
-        const T ra = -wu * (qx - un * qz), rb = -wv * (Y - vn * qz);
-        const T a2 = -wu * un, b2 = -wv * vn;
-        m3[0] = fma(wu, wu, m3[0]);                 // (0,0)
-        m3[1] = fma(wu, a2, m3[1]);                 // (0,2)
-        m3[2] = fma(wv, wv, m3[2]);                 // (1,1)
-        m3[3] = fma(wv, b2, m3[3]);                 // (1,2)
-        m3[4] = fma(a2, a2, fma(b2, b2, m3[4]));    // (2,2)
-        r3[0] = fma(wu, ra, r3[0]);
-        r3[1] = fma(wv, rb, r3[1]);
-        r3[2] = fma(a2, ra, fma(b2, rb, r3[2]));
+        const float ra = -wu * (qx - un * qz), rb = -wv * (Y - vn * qz);
+        const float a2 = -wu * un, b2 = -wv * vn;
+        m3[0] = fmaf(wu, wu, m3[0]);                  // (0,0)
+        m3[1] = fmaf(wu, a2, m3[1]);                  // (0,2)
+        m3[2] = fmaf(wv, wv, m3[2]);                  // (1,1)
+        m3[3] = fmaf(wv, b2, m3[3]);                  // (1,2)
+        m3[4] = fmaf(a2, a2, fmaf(b2, b2, m3[4]));    // (2,2)
+        m3[5] = fmaf(wu, ra, m3[5]);
+        m3[6] = fmaf(wv, rb, m3[6]);
+        m3[7] = fmaf(a2, ra, fmaf(b2, rb, m3[7]));
     }
+    warp_allreduce16<float>(m3, scratch, lane);
     double B[3][3], rh3[3], t[3];
-    B[0][0] = (double)warp_sum(m3[0]);
+    B[0][0] = (double)m3[0];
     B[0][1] = B[1][0] = 0.0;
-    B[0][2] = B[2][0] = (double)warp_sum(m3[1]);
-    B[1][1] = (double)warp_sum(m3[2]);
-    B[1][2] = B[2][1] = (double)warp_sum(m3[3]);
-    B[2][2] = (double)warp_sum(m3[4]);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) rh3[i] = (double)warp_sum(r3[i]);
+    B[0][2] = B[2][0] = (double)m3[1];
+    B[1][1] = (double)m3[2];
+    B[1][2] = B[2][1] = (double)m3[3];
+    B[2][2] = (double)m3[4];
+    rh3[0] = (double)m3[5]; rh3[1] = (double)m3[6]; rh3[2] = (double)m3[7];
     if (!chol_solve_dense<3>(B, rh3, t)) return false;
     x[0] = yaw; x[1] = t[0]; x[2] = t[1]; x[3] = t[2];
     return (fabs(t[0]) + fabs(t[1]) + fabs(t[2])) < 1.7e308;

@@ -1,4 +1,6 @@
-// pnp_kernel.cuh -- persistent warp-per-object LM kernel; T = double (MRPNP_PREC_FP64) or float (MRPNP_PREC_FP32).
+// pnp_kernel.cuh -- persistent warp-per-object LM kernel.
+// MIXED = false: MRPNP_PREC_FP64 (all fp64, reproduces the fp64 reference decisions exactly)
+// MIXED = true : MRPNP_PREC_MIXED (fp64 residual/cost chain + fp32 Jacobian sums; fast path)
 #pragma once
 #include "pnp_device.cuh"
 
@@ -20,7 +22,6 @@ constexpr double kDblMax = 1.7976931348623157e308;
 enum Termination { kConvergence = 0, kNoConvergence = 1, kFailure = 2 };
 
 __device__ __forceinline__ bool finite_value(double v) { return fabs(v) < kDblMax; }  // false for NaN too
-__device__ __forceinline__ bool finite_value(float v) { return fabsf(v) < 3.0e38f; }
 
 // Stage one object's slab into the warp's slot.  TMA path: three 1-D bulk copies completing on the
 // warp's mbarrier; fallback: coalesced loads through registers.
@@ -53,23 +54,22 @@ __device__ __forceinline__ void load_object(const KParams& kp, int obj, float* s
     }
 }
 
-// istd from log-std in place, per-axis mean, inlier decision, inlier_out, in-place compaction.
-// Returns the number of active points (compacted inliers, or P) and the per-lane inlier bits.
-template <int WMODE, int LAYOUT>
-__device__ __forceinline__ int prepare_object(const KParams& kp, int obj, float* slot, int lane, uint32_t& bits,
-                                              bool& compacted, int& n_inliers) {
+// Sweep A: weights -> inverse std in place (uncert_prop_pnp_optimizer.py:73) and the per-axis thresholds
+// thres * mean (pnp_uncert_cpu.py:164-165; fp32 like numpy).
+template <int WMODE, int LAYOUT, bool FASTEXP>
+__device__ __forceinline__ void weights_and_thresholds(const KParams& kp, float* sw, int lane, float& thr_u,
+                                                       float& thr_v) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     constexpr int CV = WC - 1;  // channel of the v-axis weight (wyy for full W)
     const int P = kp.n_pts;
-    float* s3 = slot;
-    float* s2 = slot + 3 * P;
-    float* sw = slot + 5 * P;
+    const float inv_scale = 1.f / kp.std_scale;
     float su = 0.f, sv = 0.f;
+#pragma unroll 4
     for (int p = lane; p < P; p += 32) {
         float wu = sw[sidx<LAYOUT, WC>(p, 0, P)], wv = sw[sidx<LAYOUT, WC>(p, CV, P)];
-        if (WMODE == MRPNP_W_LOGSTD) {  // uncert_prop_pnp_optimizer.py:73
-            wu = __fdiv_rn(expf(-wu), kp.std_scale);
-            wv = __fdiv_rn(expf(-wv), kp.std_scale);
+        if (WMODE == MRPNP_W_LOGSTD) {
+            wu = (FASTEXP ? __expf(-wu) : expf(-wu)) * inv_scale;
+            wv = (FASTEXP ? __expf(-wv) : expf(-wv)) * inv_scale;
             sw[sidx<LAYOUT, WC>(p, 0, P)] = wu;
             sw[sidx<LAYOUT, WC>(p, CV, P)] = wv;
         }
@@ -78,53 +78,60 @@ __device__ __forceinline__ int prepare_object(const KParams& kp, int obj, float*
     }
     su = warp_sum(su);
     sv = warp_sum(sv);
-    // pnp_uncert_cpu.py:164-168: istd >= thres * mean on both axes (fp32 like numpy)
-    const float thr_u = kp.istd_thres * __fdiv_rn(su, (float)P);
-    const float thr_v = kp.istd_thres * __fdiv_rn(sv, (float)P);
-    const uint8_t* gin = kp.inl_in ? kp.inl_in + (size_t)obj * P : nullptr;
-    const bool test = kp.istd_thres > 0.f;
-    bits = 0u;
-    int cnt = 0;
+    const float invP = 1.f / (float)P;
+    thr_u = kp.istd_thres * (su * invP);
+    thr_v = kp.istd_thres * (sv * invP);
+    __syncwarp();
+}
+
+// Sweep B: inlier decision (pnp_uncert_cpu.py:166-168 or the caller's packed mask), packed inlier_out,
+// and in-place order-preserving compaction (boolean-mask indexing of pnp_uncert_cpu.py:24-27,62-66).
+// Returns the inlier count; `bits` = this lane's inlier flags (bit k <-> point 32k+lane).
+// With COMPACT the slot is rewritten; the caller must re-load it if the count turns out to be <= 4.
+template <int WMODE, int LAYOUT, bool COMPACT>
+__device__ __forceinline__ int mask_and_compact(const KParams& kp, int obj, float* slot, int lane, float thr_u,
+                                                float thr_v, bool all_inliers, uint32_t& bits) {
+    constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
+    constexpr int CV = WC - 1;
+    const int P = kp.n_pts;
+    float* s3 = slot;
+    float* s2 = slot + 3 * P;
+    float* sw = slot + 5 * P;
     const int rows = (P + 31) >> 5;
+    const bool test = kp.istd_thres > 0.f;
+    uint32_t in_word = 0u;
+    if (kp.inl_in && lane < rows) in_word = __ldg(kp.inl_in + (size_t)obj * rows + lane);
+    uint32_t out_word = 0u;
+    bits = 0u;
+    int base = 0;
     for (int k = 0; k < rows; ++k) {
         const int p = k * 32 + lane;
         bool inl = p < P;
+        float wu = 0.f, wv = 0.f;
         if (inl) {
-            if (gin) inl = gin[p] != 0;
-            else if (test) inl = sw[sidx<LAYOUT, WC>(p, 0, P)] >= thr_u && sw[sidx<LAYOUT, WC>(p, CV, P)] >= thr_v;
+            wu = sw[sidx<LAYOUT, WC>(p, 0, P)];
+            wv = sw[sidx<LAYOUT, WC>(p, CV, P)];
         }
+        if (!all_inliers) {
+            if (kp.inl_in) {
+                const uint32_t row_word = __shfl_sync(kFull, in_word, k);  // every lane takes part
+                inl = inl && ((row_word >> lane) & 1u);
+            } else if (test) {
+                inl = inl && (wu >= thr_u) && (wv >= thr_v);
+            }
+        }
+        const unsigned m = __ballot_sync(kFull, inl);
         bits |= (inl ? 1u : 0u) << k;
-        cnt += __popc(__ballot_sync(kFull, inl));
-    }
-    if (cnt <= 4) {  // pnp_uncert_cpu.py:23-32: too few inliers -> every point is an inlier
-        cnt = P;
-        bits = 0u;
-        for (int k = 0; k < rows; ++k) bits |= ((k * 32 + lane) < P ? 1u : 0u) << k;
-    }
-    if (kp.inl_out) {
-        uint8_t* gout = kp.inl_out + (size_t)obj * P;
-        for (int k = 0; k < rows; ++k) {
-            const int p = k * 32 + lane;
-            if (p < P) gout[p] = (uint8_t)((bits >> k) & 1u);
-        }
-    }
-    compacted = false;
-    n_inliers = cnt;
-    if (kp.inlier_opt_only && cnt < P) {  // pnp_uncert_cpu.py:62-66: LM sees the inliers only, order kept
-        int base = 0;
-        for (int k = 0; k < rows; ++k) {
-            const int p = k * 32 + lane;
-            const bool inl = (bits >> k) & 1u;
-            float v3[3], v2[2], vw[WC];
+        if (lane == k) out_word = m;
+        if (COMPACT) {
+            float v3[3], v2[2], w1 = 0.f;
             if (inl) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) v3[c] = s3[sidx<LAYOUT, 3>(p, c, P)];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) v2[c] = s2[sidx<LAYOUT, 2>(p, c, P)];
-#pragma unroll
-                for (int c = 0; c < WC; ++c) vw[c] = sw[sidx<LAYOUT, WC>(p, c, P)];
+                if (WMODE == MRPNP_W_FULL) w1 = sw[sidx<LAYOUT, WC>(p, 1, P)];
             }
-            const unsigned m = __ballot_sync(kFull, inl);
             __syncwarp();  // this row's reads (all lanes) happen before any lane's compacted writes
             if (inl) {
                 const int d = base + __popc(m & ((1u << lane) - 1u));
@@ -132,26 +139,28 @@ __device__ __forceinline__ int prepare_object(const KParams& kp, int obj, float*
                 for (int c = 0; c < 3; ++c) s3[sidx<LAYOUT, 3>(d, c, P)] = v3[c];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) s2[sidx<LAYOUT, 2>(d, c, P)] = v2[c];
-#pragma unroll
-                for (int c = 0; c < WC; ++c) sw[sidx<LAYOUT, WC>(d, c, P)] = vw[c];
+                sw[sidx<LAYOUT, WC>(d, 0, P)] = wu;
+                if (WMODE == MRPNP_W_FULL) sw[sidx<LAYOUT, WC>(d, 1, P)] = w1;
+                sw[sidx<LAYOUT, WC>(d, CV, P)] = wv;
             }
-            base += __popc(m);
         }
-        __syncwarp();
-        compacted = true;
-        return cnt;
+        base += __popc(m);
     }
     __syncwarp();
-    return P;
+    if (kp.inl_out && lane < rows) kp.inl_out[(size_t)obj * rows + lane] = out_word;
+    return base;
 }
 
-template <typename T, int WMODE, int LAYOUT>
+template <bool MIXED, int WMODE, int LAYOUT>
 __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
-    float* slot = reinterpret_cast<float*>(smem_raw + kBarrierBytes) + (size_t)warp * kp.slot_floats;
+    const int nwarps = blockDim.x >> 5;
+    unsigned char* header = smem_raw + (size_t)warp * kWarpHeaderBytes;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(header);
+    double* scratch = reinterpret_cast<double*>(header + 128);
+    float* slot = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * kWarpHeaderBytes) + (size_t)warp * kp.slot_floats;
     const int P = kp.n_pts;
     const float* s3 = slot;
     const float* s2 = slot + 3 * P;
@@ -172,23 +181,44 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
         obj = __shfl_sync(kFull, obj, 0);
         if (obj >= kp.n_obj) break;
 
-        load_object<WC>(kp, obj, slot, bar, parity, lane);
-
-        Camera<T> cam;
+        Camera<double> cam;
+        Camera<float> camf;
         {
             const float* K = kp.cam + (size_t)obj * kp.cam_stride;
             const float* R = kp.range + (size_t)obj * kp.range_stride;
-            cam.fx = (T)__ldg(K + 0); cam.fy = (T)__ldg(K + 4);  // pnp_uncert_cpu.cpp:265
-            cam.cx = (T)__ldg(K + 2); cam.cy = (T)__ldg(K + 5);
-            cam.z_min = (T)kp.z_min;
-            cam.u_min = (T)__ldg(R + 0); cam.u_max = (T)__ldg(R + 1);
-            cam.v_min = (T)__ldg(R + 2); cam.v_max = (T)__ldg(R + 3);
+            camf.fx = __ldg(K + 0); camf.fy = __ldg(K + 4);  // pnp_uncert_cpu.cpp:265
+            camf.cx = __ldg(K + 2); camf.cy = __ldg(K + 5);
+            camf.z_min = kp.z_min;
+            camf.u_min = __ldg(R + 0); camf.u_max = __ldg(R + 1);
+            camf.v_min = __ldg(R + 2); camf.v_max = __ldg(R + 3);
+            cam.fx = (double)camf.fx; cam.fy = (double)camf.fy; cam.cx = (double)camf.cx; cam.cy = (double)camf.cy;
+            cam.z_min = (double)camf.z_min; cam.u_min = (double)camf.u_min; cam.u_max = (double)camf.u_max;
+            cam.v_min = (double)camf.v_min; cam.v_max = (double)camf.v_max;
         }
 
-        uint32_t bits;
-        bool compacted;
-        int n_inliers;
-        const int n = prepare_object<WMODE, LAYOUT>(kp, obj, slot, lane, bits, compacted, n_inliers);
+        // ---------------- stage + istd + inlier mask + compaction ----------------
+        uint32_t bits = 0u;
+        int n_inliers = P, n = P;
+        bool compacted = false;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            load_object<WC>(kp, obj, slot, bar, parity, lane);
+            float thr_u, thr_v;
+            weights_and_thresholds<WMODE, LAYOUT, MIXED>(kp, slot + 5 * P, lane, thr_u, thr_v);
+            if (attempt == 1) {  // pnp_uncert_cpu.py:28-32: <= 4 inliers -> every point is an inlier
+                n_inliers = mask_and_compact<WMODE, LAYOUT, false>(kp, obj, slot, lane, thr_u, thr_v, true, bits);
+                break;
+            }
+            if (kp.inlier_opt_only) {
+                n_inliers = mask_and_compact<WMODE, LAYOUT, true>(kp, obj, slot, lane, thr_u, thr_v, false, bits);
+                if (n_inliers > 4) { compacted = true; n = n_inliers; break; }
+            } else {
+                n_inliers = mask_and_compact<WMODE, LAYOUT, false>(kp, obj, slot, lane, thr_u, thr_v, false, bits);
+                if (n_inliers > 4) break;
+            }
+        }
+        if (!compacted) n = P;
+        const bool lm_bits = !compacted && !kp.inlier_opt_only && n_inliers < P;  // never: LM then sees all points
+        (void)lm_bits;
 
         // ---------------- Levenberg-Marquardt, Ceres 1.14 TrustRegionMinimizer control flow ----------------
         double x[4];
@@ -198,23 +228,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
 #pragma unroll
             for (int i = 0; i < 4; ++i) x[i] = (double)__ldg(ip + i);
         } else {
-            init_ok = linear_init<T, WMODE, LAYOUT>(s3, s2, sw, P, n, lane, cam, x);
+            init_ok = linear_init<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, camf, reinterpret_cast<float*>(scratch), x);
             if (!init_ok) { x[0] = x[1] = x[2] = x[3] = 0.0; }  // pnp_uncert_cpu.py:119-125
 #pragma unroll
             for (int i = 0; i < 4; ++i) x[i] = (double)(float)x[i];  // fp32 hand-over, like the EPnP result
         }
-        T acc[kNumAcc];
+        double acc[16];
         bool clip_x;
-        eval_pass<T, WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, x, cam, acc, clip_x);
-        double cost = 0.5 * (double)acc[0];
+        if (MIXED) eval_pass_mixed<WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, x, cam, camf, acc, scratch, clip_x);
+        else eval_pass_fp64<WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, x, cam, acc, scratch, clip_x);
+        double cost = 0.5 * acc[0];
         double g[4], H[10];  // unscaled gradient / Gauss-Newton matrix at x
 #pragma unroll
-        for (int i = 0; i < 4; ++i) g[i] = (double)acc[1 + i];
+        for (int i = 0; i < 4; ++i) g[i] = acc[1 + i];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) H[i] = (double)acc[5 + i];
+        for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
         bool finite = finite_value(acc[0]);
 #pragma unroll
-        for (int i = 1; i < kNumAcc; ++i) finite = finite && finite_value(acc[i]);
+        for (int i = 1; i < 15; ++i) finite = finite && finite_value(acc[i]);
 
         int term = kNoConvergence;
         int iteration = 0, cost_evals = 1;
@@ -224,12 +255,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
         } else {
             double scale[4];  // jacobi_scaling from the initial Jacobian only
 #pragma unroll
-            for (int i = 0; i < 4; ++i) scale[i] = 1.0 / (1.0 + sqrt(H[tri(i, i)]));
+            for (int i = 0; i < 4; ++i) scale[i] = fast_rcp(1.0 + fast_sqrt(H[tri(i, i)]));
             double diag[4];
             double decrease_factor = 2.0;
             bool reuse_diagonal = false;
             int num_invalid = 0;
-            double x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+            double x_norm = fast_sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
             bool step_ok = true;  // iteration 0 counts as a successful step
             while (true) {
                 // FinalizeIterationAndCheckIfMinimizerCanContinue
@@ -255,28 +286,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
                     for (int i = 0; i < 4; ++i) diag[i] = fmin(fmax(Hs[tri(i, i)], kMinLmDiag), kMaxLmDiag);
                 }
                 reuse_diagonal = true;
-                double A[10], L[10], y[4];
+                double A[10], y[4];
+                const double inv_radius = fast_rcp(radius);
 #pragma unroll
                 for (int i = 0; i < 10; ++i) A[i] = Hs[i];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) A[tri(i, i)] += diag[i] / radius;
-                bool valid = chol4(A, L);
+                for (int i = 0; i < 4; ++i) A[tri(i, i)] = fma(diag[i], inv_radius, A[tri(i, i)]);
+                const Ldl4 f = ldl4_factor(A);
+                bool valid = f.ok;
                 double model_change = 0.0;
                 if (valid) {
-                    chol4_solve(L, gs, y);  // step = -y
+                    ldl4_solve(f, gs, y);  // step = -y
                     // model_cost_change = -step^T gs - 1/2 step^T Hs step = y^T gs - 1/2 y^T Hs y
-                    double hy[4];
+                    double yg = 0.0, yhy = 0.0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         double s = 0.0;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) s = fma(Hs[tri(i, j)], y[j], s);
-                        hy[i] = s;
+                        yg = fma(y[i], gs[i], yg);
+                        yhy = fma(y[i], s, yhy);
                     }
-                    double yg = 0.0, yhy = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { yg = fma(y[i], gs[i], yg); yhy = fma(y[i], hy[i], yhy); }
-                    model_change = yg - 0.5 * yhy;
+                    model_change = fma(-0.5, yhy, yg);
                     valid = (model_change > 0.0) && (fabs(y[0]) + fabs(y[1]) + fabs(y[2]) + fabs(y[3]) < kDblMax);
                 }
                 if (!valid) {  // HandleInvalidStep
@@ -292,45 +323,46 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
 
                 // candidate cost, fused with its gradient / Gauss-Newton matrix (used only if accepted)
                 bool clip_c;
-                eval_pass<T, WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, cand, cam, acc, clip_c);
+                if (MIXED) eval_pass_mixed<WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, cand, cam, camf, acc, scratch, clip_c);
+                else eval_pass_fp64<WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, cand, cam, acc, scratch, clip_c);
                 ++cost_evals;
                 const bool cfinite = finite_value(acc[0]);
                 bool jfinite = cfinite;  // the fused pass also produced the candidate's Jacobian sums
 #pragma unroll
-                for (int i = 1; i < kNumAcc; ++i) jfinite = jfinite && finite_value(acc[i]);
-                const double cand_cost = cfinite ? 0.5 * (double)acc[0] : kDblMax;
+                for (int i = 1; i < 15; ++i) jfinite = jfinite && finite_value(acc[i]);
+                const double cand_cost = cfinite ? 0.5 * acc[0] : kDblMax;
 
                 // ParameterToleranceReached
-                const double step_norm =
-                    sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2] + delta[3] * delta[3]);
-                if (step_norm <= kParameterTol * (x_norm + kParameterTol)) { term = kConvergence; break; }
+                const double step_norm2 = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2] + delta[3] * delta[3];
+                const double ptol = kParameterTol * (x_norm + kParameterTol);
+                if (step_norm2 <= ptol * ptol) { term = kConvergence; break; }
                 // FunctionToleranceReached (Ceres 1.14: candidate is not adopted on this exit)
                 const double cost_change = cost - cand_cost;
                 if (fabs(cost_change) <= kFunctionTol * cost) {
                     if (kp.adopt_ftol && cand_cost < cost) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { x[i] = cand[i]; g[i] = (double)acc[1 + i]; }
+                        for (int i = 0; i < 4; ++i) { x[i] = cand[i]; g[i] = acc[1 + i]; }
 #pragma unroll
-                        for (int i = 0; i < 10; ++i) H[i] = (double)acc[5 + i];
+                        for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
                         cost = cand_cost;
                         clip_x = clip_c;
                     }
                     term = kConvergence;
                     break;
                 }
-                const double rho = cost_change / model_change;
+                const double rho = cost_change * fast_rcp(model_change);
                 if (rho > kMinRelDecrease) {  // HandleSuccessfulStep
                     if (!jfinite) { term = kFailure; break; }  // re-evaluation at the new point fails in Ceres
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { x[i] = cand[i]; g[i] = (double)acc[1 + i]; }
+                    for (int i = 0; i < 4; ++i) { x[i] = cand[i]; g[i] = acc[1 + i]; }
 #pragma unroll
-                    for (int i = 0; i < 10; ++i) H[i] = (double)acc[5 + i];
+                    for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
                     cost = cand_cost;
                     clip_x = clip_c;
-                    x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+                    x_norm = fast_sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
                     step_ok = true;
                     const double q = 2.0 * rho - 1.0;
-                    radius = radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+                    radius = radius * fast_rcp(fmax(1.0 / 3.0, 1.0 - q * q * q));
                     radius = fmin(kMaxRadius, radius);
                     decrease_factor = 2.0;
                     reuse_diagonal = false;
@@ -353,10 +385,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
             const bool need_pass = kp.cov_mode == MRPNP_COV_PIPELINE && (any_clip || (!compacted && n_inliers < P));
             if (need_pass) {
                 bool c2;
-                eval_pass<T, WMODE, LAYOUT, 1, true>(s3, s2, sw, P, n, lane, compacted ? 0xffffffffu : bits, x, cam,
-                                                       acc, c2);
+                eval_pass_fp64<WMODE, LAYOUT, 1, true>(s3, s2, sw, P, n, lane, compacted ? 0xffffffffu : bits, x, cam,
+                                                       acc, scratch, c2);
 #pragma unroll
-                for (int i = 0; i < 10; ++i) H[i] = (double)acc[5 + i];
+                for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
             }
             if (!spd_inverse4(H, cov)) {  // pnp_uncert.py:79-85 fallback: H := I, object invalid
 #pragma unroll

@@ -20,6 +20,8 @@ from .registry import PNP, build_pnp  # noqa: F401  (re-exported like monorun.op
 C = _native.CONST
 RESULT_STRIDE = C['MRPNP_RESULT_STRIDE']
 
+_PREC = {'fp64': C['MRPNP_PREC_FP64'], 'mixed': C['MRPNP_PREC_MIXED']}
+
 _ctx_cache = {}
 
 
@@ -61,6 +63,23 @@ def make_params(n_obj, n_pts, **kw):
     return p
 
 
+def pack_mask(mask):
+    """[N,P] bool -> [N,ceil(P/32)] int32 words (bit j of word k = point 32k+j): the C ABI's mask format."""
+    n, p = mask.shape
+    w = (p + 31) // 32
+    m = torch.zeros((n, w * 32), dtype=torch.int64, device=mask.device)
+    m[:, :p] = mask.to(torch.int64)
+    words = (m.view(n, w, 32) << torch.arange(32, device=mask.device, dtype=torch.int64)).sum(-1)
+    return words.view(torch.int32)[:, ::2].contiguous()  # low 32 bits (little endian)
+
+
+def unpack_mask(words, n_pts):
+    """Inverse of :func:`pack_mask`."""
+    n, w = words.shape
+    bits = (words.to(torch.int64).unsqueeze(-1) >> torch.arange(32, device=words.device, dtype=torch.int64)) & 1
+    return bits.view(n, w * 32)[:, :n_pts].bool()
+
+
 def _f32c(t):
     if t.dtype != torch.float32:
         t = t.float()
@@ -73,7 +92,7 @@ def _ptr(t, ctype='float*'):
 
 def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None, inlier_mask=None, *,
                   layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, istd_thres=0.6,
-                  inlier_opt_only=True, cov_mode='pipeline', precision='fp64', max_iterations=50,
+                  inlier_opt_only=True, cov_mode='pipeline', precision='mixed', max_iterations=50,
                   adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False):
     """Batched uncertainty-PnP on device tensors -- direct wrapper of ``mrpnp_solve``.
 
@@ -92,23 +111,24 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
     n_pts = coords_3d[0].numel() // 3 if n else (coords_3d.shape[2:].numel() if planar else coords_3d.shape[1])
     wmode = {'logstd': C['MRPNP_W_LOGSTD'], 'istd': C['MRPNP_W_ISTD'], 'full': C['MRPNP_W_FULL']}[weight_mode]
     result = torch.empty((n, RESULT_STRIDE), dtype=torch.float32, device=dev)
-    inl_out = torch.empty((n, n_pts), dtype=torch.uint8, device=dev) if return_inlier_mask else None
+    n_words = (n_pts + 31) // 32
+    inl_out = torch.empty((n, n_words), dtype=torch.int32, device=dev) if return_inlier_mask else None
     res64 = torch.empty((n, 8), dtype=torch.float64, device=dev) if return_fp64 else None
     if n == 0:
-        return result, (inl_out.bool() if inl_out is not None else None), res64
+        return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None), res64
     c3, c2, w = _f32c(coords_3d), _f32c(coords_2d), _f32c(weights)
     cam, rng = _f32c(cam_mats).reshape(-1, 9), _f32c(uv_range).reshape(-1, 4)
     if cam.shape[0] not in (1, n) or rng.shape[0] not in (1, n):
         raise ValueError('cam_mats / uv_range must have batch size 1 or N')
     init = _f32c(init_pose) if init_pose is not None else None
-    inl_in = inlier_mask.to(torch.uint8).contiguous() if inlier_mask is not None else None
+    inl_in = pack_mask(inlier_mask.reshape(n, n_pts).bool()) if inlier_mask is not None else None
     p = make_params(
         n, n_pts,
         layout=C['MRPNP_LAYOUT_PLANAR'] if planar else C['MRPNP_LAYOUT_INTERLEAVED'],
         weight_mode=wmode,
         cam_stride=9 if cam.shape[0] == n and n > 1 else 0,
         range_stride=4 if rng.shape[0] == n and n > 1 else 0,
-        precision=C['MRPNP_PREC_FP64'] if precision == 'fp64' else C['MRPNP_PREC_FP32'],
+        precision=_PREC[precision],
         cov_mode={'none': 0, 'pipeline': 1, 'ceres': 2}[cov_mode],
         init_mode=C['MRPNP_INIT_GIVEN'] if init is not None else C['MRPNP_INIT_LINEAR'],
         inlier_opt_only=int(bool(inlier_opt_only)), max_iterations=int(max_iterations),
@@ -118,9 +138,9 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
     with torch.cuda.device(dev):
         _native.check(_native.lib().mrpnp_solve(
             ctx.ptr, p, _ptr(c3), _ptr(c2), _ptr(w), _ptr(cam), _ptr(rng), _ptr(init),
-            _ptr(inl_in, 'uint8_t*'), _ptr(result), _ptr(inl_out, 'uint8_t*'), _ptr(res64, 'double*'),
+            _ptr(inl_in, 'uint32_t*'), _ptr(result), _ptr(inl_out, 'uint32_t*'), _ptr(res64, 'double*'),
             _native.ffi.cast('void*', stream)))
-    return result, (inl_out.bool() if inl_out is not None else None), res64
+    return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None), res64
 
 
 def solve_host(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None, *, device=0, layout='planar',
@@ -138,7 +158,7 @@ def solve_host(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None
         n, n_pts, layout=C['MRPNP_LAYOUT_PLANAR'] if layout == 'planar' else C['MRPNP_LAYOUT_INTERLEAVED'],
         weight_mode=wmode, cam_stride=9 if cam.shape[0] == n and n > 1 else 0,
         range_stride=4 if rng.shape[0] == n and n > 1 else 0,
-        precision=C['MRPNP_PREC_FP64'] if kw.get('precision', 'fp64') == 'fp64' else C['MRPNP_PREC_FP32'],
+        precision=_PREC[kw.get('precision', 'mixed')],
         cov_mode={'none': 0, 'pipeline': 1, 'ceres': 2}[kw.get('cov_mode', 'pipeline')],
         init_mode=C['MRPNP_INIT_GIVEN'] if init_pose is not None else C['MRPNP_INIT_LINEAR'],
         z_min=float(kw.get('z_min', 0.5)), std_scale=float(kw.get('std_scale', 10.0)),
@@ -162,7 +182,7 @@ def _unpack(result, inlier_mask):
 
 def pnp_uncert(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range, z_min=0.5, epnp_istd_thres=1.0,
                epnp_ransac_thres=None, inlier_opt_only=False, forward_exact_hessian=False, use_6dof=False,
-               init_pose=None, precision='fp64'):
+               init_pose=None, precision='mixed'):
     """Drop-in for monorun/ops/least_squares/pnp_uncert.py:7-87.
 
     Args (as in the reference):
@@ -201,7 +221,7 @@ class PnPUncert(torch.nn.Module):
     """Drop-in for monorun/ops/least_squares/pnp_uncert.py:90-142 (same constructor kwargs and forward)."""
 
     def __init__(self, z_min=0.5, epnp_istd_thres=0.6, inlier_opt_only=True, coord_istd_normalize=False,
-                 forward_exact_hessian=False, use_6dof=False, eps=1e-6, precision='fp64'):
+                 forward_exact_hessian=False, use_6dof=False, eps=1e-6, precision='mixed'):
         super(PnPUncert, self).__init__()
         self.z_min = z_min
         self.epnp_istd_thres = epnp_istd_thres

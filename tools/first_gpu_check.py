@@ -69,11 +69,11 @@ def timing(n, weights='diag', mode='S1', precision='fp64', config=2, reps=20):
 
 if __name__ == '__main__':
     print(torch.cuda.get_device_name(0))
-    for prec in ('fp64', 'fp32'):
+    for prec in ('fp64', 'mixed'):
         parity(512, 2, 'diag', 'S0', prec)
         parity(512, 2, 'diag', 'S1', prec)
         parity(512, 3, 'full', 'S0', prec)
-    for prec in ('fp64', 'fp32'):
+    for prec in ('fp64', 'mixed'):
         for n in (1024, 8192, 32768):
             timing(n, 'diag', 'S1', prec)
         timing(8192, 'diag', 'S0', prec)
