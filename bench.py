@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched uncertainty-PnP hot path (BASELINE.json metric: PnP objects/s at 28x28
+correspondences, % of the HBM roofline, next to the reference-equivalent CPU path on the same box).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload full|diag] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: 8192 objects per GPU (BASELINE.json configs[2]; configs[4]
+shards 65,536 objects over 8 GPUs = the same 8192 per GPU, so scaling is weak), each with 784 correspondences,
+full 2x2 per-pixel covariance and pose-covariance output.  One kernel launch per step; for N > 1 the step also
+contains the single NCCL all-gather of the [N_local, 24] result rows.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OBJ_PER_GPU = 8192
+ALG_BYTES = {'full': 8 * 784 * 4 + 96, 'diag': 7 * 784 * 4 + 96}  # reads + 96 B result row
+METRIC = 'pnp_objects_per_s'
+UNIT = 'objects/s'
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json, STREAM-style copy, burst)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read+write per launch from the committed ncu capture of this workload, if present."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))[workload]
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        load = [s for s in sm if mx and s > 0.5 * mx] or sm
+        return {'sm_mhz': float(np.median(load)) if load else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_inputs(workload, n, config, rank, nsets):
+    from monorun_b200 import synth
+    sets = []
+    for s in range(nsets):
+        b = synth.make_batch(n, config=config, rank=rank * 16 + s, weights=workload, mode='S1',
+                             classes=(0, 1, 2) if workload == 'full' else (0,))
+        sets.append(b)
+    return sets
+
+
+def cpu_args(od, b, workload, max_objects=None):
+    from monorun_b200 import synth
+    op = synth.to_op_level(b)
+    full = workload == 'full'
+    w = op['w_full'] if full else op['coords_2d_istd']
+    n = w.shape[0] if max_objects is None else min(max_objects, w.shape[0])
+    mask = od.istd_inlier_masks(w[:n][..., [0, 2]] if full else w[:n], 0.6)
+    mask[mask.sum(1) <= 4] = True
+    clips = np.array([[0.5, op['u_range'][0, 0], op['u_range'][0, 1], op['v_range'][0, 0], op['v_range'][0, 1]]])
+    return (op['coords_2d'][:n], op['coords_3d'][:n], w[:n], op['cam_mats'], b['init_pose'][:n], clips, mask), n, full
+
+
+def cpu_lm_rate(od, b, workload, threads, min_seconds, max_objects=None):
+    """Oracle (restated Ceres LM + covariance, fp64) on the same workload: objects/s with `threads` OpenMP threads."""
+    args, n, full = cpu_args(od, b, workload, max_objects)
+    od.lm_batch(*args, full_w=full, with_pose_cov=True, threads=threads)  # warm-up (page-in, thread pool)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        od.lm_batch(*args, full_w=full, with_pose_cov=True, threads=threads)
+        done += n
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return done / dt, done, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  Its native op needs ceres-solver 1.14
+    (absent, not installable), so this is the oracle port with every host thread; step = 2048 objects of the
+    same workload."""
+    if rank != 0:
+        return
+    from oracle import pnp_driver as od
+    od.build()
+    threads = od.lib().pnp_oracle_num_threads()
+    sample = 2048
+    b = make_inputs(args.workload, sample, 3 if args.workload == 'full' else 2, 0, 1)[0]
+    cargs, n, full = cpu_args(od, b, args.workload)
+    for _ in range(max(args.warmup, 1)):
+        od.lm_batch(*cargs, full_w=full, with_pose_cov=True, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        od.lm_batch(*cargs, full_w=full, with_pose_cov=True, threads=threads)
+    dt = time.perf_counter() - t0
+    value = args.steps * sample / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.workload), 'objects_per_step': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': f'{sample} objects/step of the same workload, oracle LM + covariance from the '
+                                   f'shared init, {threads} OpenMP threads (reference native op needs ceres 1.14: absent)'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(w):
+    return ('cfg3: 8192 mixed-class ROIs/GPU x 28x28 corr, full 2x2 per-pixel covariance, pose-cov out' if w == 'full'
+            else 'cfg2-style: 8192 car ROIs/GPU x 28x28 corr, diagonal covariance (log-std in), pose-cov out')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--workload', choices=['full', 'diag'], default='full')
+    ap.add_argument('--precision', choices=['mixed', 'fp64'], default='mixed')
+    ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from monorun_b200 import pnp
+    from monorun_b200 import dist as mdist
+    from monorun_b200 import _native
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device; there is no CPU fallback')
+    _native.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    full = args.workload == 'full'
+    n_local, n_total = OBJ_PER_GPU, OBJ_PER_GPU * world
+
+    # ---- synthetic inputs: two alternating sets per rank (2 x 206 MB > 126 MB L2) ----
+    sets = make_inputs(args.workload, n_local, 3 if full else 2, rank, 2)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dsets = []
+    for b in sets:
+        ih, iw = b['img_shape']
+        dsets.append(dict(c3=t(b['coords_3d']), c2=t(b['coords_2d']), w=t(b['w_full'] if full else b['logstd']),
+                          cam=t(b['cam_mat'][None]), rng=torch.tensor([[-200., iw + 200., -200., ih + 200.]], device=dev),
+                          init=t(b['init_pose'])))
+    kw = dict(layout='planar', weight_mode='full' if full else 'logstd', precision=args.precision,
+              cov_mode='pipeline', return_inlier_mask=False)
+
+    def step(i):
+        d = dsets[i % 2]
+        rows, _, _ = pnp.solve_batched(d['c3'], d['c2'], d['w'], d['cam'], d['rng'], init_pose=d['init'], **kw)
+        if world > 1:
+            rows = mdist.all_gather_rows(rows, n_total)
+        return rows
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity spot check against the oracle before any number counts (rank 0, 256 objects) ----
+    parity = None
+    if rank == 0:
+        from monorun_b200 import synth
+        from oracle import pnp_driver as od
+        od.build()
+        m = 256
+        b = sets[0]
+        op = synth.to_op_level({k: (v[:m] if isinstance(v, np.ndarray) and v.shape[:1] == (n_local,) else v) for k, v in b.items()})
+        wgt = op['w_full'] if full else op['coords_2d_istd']
+        d = dsets[0]
+        rows, inl, _ = pnp.solve_batched(d['c3'][:m], d['c2'][:m], d['w'][:m], d['cam'], d['rng'], init_pose=d['init'][:m],
+                                         **dict(kw, return_inlier_mask=True))
+        clips = np.array([[0.5, op['u_range'][0, 0], op['u_range'][0, 1], op['v_range'][0, 0], op['v_range'][0, 1]]])
+        ref = od.lm_batch(op['coords_2d'], op['coords_3d'], wgt, op['cam_mats'], b['init_pose'][:m], clips,
+                          inl.cpu().numpy(), full_w=full, threads=0)
+        r = rows.cpu().numpy().astype(np.float64)
+        t_err = np.linalg.norm(r[:, 1:4] - ref['pose'][:, 1:], axis=1) / np.linalg.norm(ref['pose'][:, 1:], axis=1)
+        parity = {'objects': m, 'max_rel_translation_err': float(t_err.max()),
+                  'max_yaw_err_rad': float(np.abs(r[:, 0] - ref['pose'][:, 0]).max()),
+                  'valid': float(r[:, 20].mean())}
+        if not (parity['max_rel_translation_err'] < 1e-4 and parity['max_yaw_err_rad'] < 1e-3):
+            raise SystemExit(f'parity check failed: {parity}')
+
+    # ---- device-resident throughput: W warm-ups, then exactly K steps between fences ----
+    for i in range(args.warmup):
+        step(i)
+    fence()
+    launches0 = pnp.launch_count(dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    fence()
+    ev[0].record()
+    for i in range(args.steps):
+        d = dsets[i % 2]
+        kev[i][0].record()
+        rows, _, _ = pnp.solve_batched(d['c3'], d['c2'], d['w'], d['cam'], d['rng'], init_pose=d['init'], **kw)
+        kev[i][1].record()
+        if world > 1:
+            rows = mdist.all_gather_rows(rows, n_total)
+    ev[1].record()
+    fence()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = pnp.launch_count(dev) - launches0
+    ms_total = ev[0].elapsed_time(ev[1])
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    iters = rows[:n_local, 21] if world == 1 else rows[rank * n_local:(rank + 1) * n_local, 21]
+    hist = torch.bincount(iters.to(torch.int64).clamp(0, 63)).cpu().tolist()
+    valid_frac = float(rows[:, 20].mean().item())
+
+    # ---- end to end through the host-buffer C ABI call: pinned host inputs, H2D + kernel + D2H every step ----
+    hsets = []
+    for b in sets:
+        ih, iw = b['img_shape']
+        hsets.append(dict(c3=torch.from_numpy(b['coords_3d']).pin_memory(), c2=torch.from_numpy(b['coords_2d']).pin_memory(),
+                          w=torch.from_numpy(b['w_full'] if full else b['logstd']).pin_memory(),
+                          cam=torch.from_numpy(b['cam_mat'][None].copy()),
+                          rng=torch.tensor([[-200., iw + 200., -200., ih + 200.]]),
+                          init=torch.from_numpy(b['init_pose']).pin_memory(),
+                          out=torch.empty((n_local, pnp.RESULT_STRIDE)).pin_memory()))
+    hkw = dict(device=local_rank, layout='planar', weight_mode='full' if full else 'logstd', precision=args.precision)
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        h = hsets[i % 2]
+        pnp.solve_host(h['c3'], h['c2'], h['w'], h['cam'], h['rng'], h['init'], result=h['out'], **hkw)
+    fence()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        h = hsets[i % 2]
+        pnp.solve_host(h['c3'], h['c2'], h['w'], h['cam'], h['rng'], h['init'], result=h['out'], **hkw)
+    fence()
+    e2e_s = time.perf_counter() - t0
+    h2d = int(sum(hsets[0][k].numel() * 4 for k in ('c3', 'c2', 'w', 'init', 'cam', 'rng')))
+    d2h = int(hsets[0]['out'].numel() * 4)
+
+    # ---- max over ranks ----
+    tv = torch.tensor([ms_total, kernel_ms, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+    ms_total, kernel_ms, e2e_s = tv.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg = ALG_BYTES[args.workload] * n_local
+        achieved = alg / (kernel_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': n_total * args.steps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 residual/cost + f32 Jacobian'
+            if args.precision == 'mixed' else 'f64', 'data': 'synthetic',
+            'config': {'workload': workload_name(args.workload), 'objects_per_gpu': n_local, 'points_per_object': 784,
+                       'precision': args.precision, 'init': 'ground truth perturbed (5e-2 rad, 2% depth), shared with the oracle',
+                       'l2': 'two alternating input sets of %.0f MB each (> 126 MB L2)' % (alg / 1e6),
+                       'parallelism': f'objects sharded contiguously over {world} GPU(s)' + (', 1 NCCL all-gather of [N,24] rows per step' if world > 1 else '')},
+            'clocks': clocks,
+            'e2e': {'value': n_total * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d * world,
+                    'd2h_bytes_per_step': d2h * world, 'steps': e2e_steps,
+                    'path': 'mrpnp_solve_host: pinned host tensors -> chunked H2D overlapped with the kernel -> D2H of result rows'},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': ncu_traffic(args.workload), 'peak_source': peak_src,
+                         'kernel': 'mrpnp::pnp_lm_kernel', 'kernel_ms': kernel_ms,
+                         'algorithmic_bytes_per_object': ALG_BYTES[args.workload], 'objects_per_launch': n_local},
+            'lm_iterations_histogram': hist, 'valid_fraction': valid_frac, 'parity_check': parity,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import pnp_driver as od
+            threads = od.lib().pnp_oracle_num_threads()
+            all_rate, done, dt = cpu_lm_rate(od, sets[0], args.workload, threads, 6.0)
+            one_rate, done1, dt1 = cpu_lm_rate(od, sets[0], args.workload, 1, 4.0, max_objects=2048)
+            line['cpu_baseline'] = {
+                'value': all_rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                'sample': f'{done} object solves of this workload in {dt:.1f} s: oracle (restated Ceres-1.14 LM + covariance, '
+                          f'fp64) from the shared init, OpenMP over objects on {threads} host threads of {os.cpu_count()}; '
+                          f'single thread (what the reference does, pnp_uncert_cpu.py:180-191): {one_rate:.0f} objects/s '
+                          f'({done1} solves in {dt1:.1f} s)',
+                'single_thread_value': one_rate}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

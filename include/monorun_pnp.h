@@ -74,7 +74,7 @@ typedef struct mrpnp_params {
     int32_t cov_mode;       /* MRPNP_COV_*                                                             */
     int32_t init_mode;      /* MRPNP_INIT_*                                                            */
     int32_t inlier_opt_only;/* 1: LM sees inliers only (all reference configs), 0: all points          */
-    int32_t max_iterations; /* <=0: Ceres default 50                                                   */
+    int32_t max_iterations; /* 0: Ceres default 50; <0: no LM step, evaluate cost/covariance at init_pose  */
     int32_t adopt_candidate_on_ftol; /* 0: Ceres 1.14 (candidate dropped on the function-tolerance exit) */
     float z_min;            /* PnPUncert(z_min=0.5)                                                    */
     float std_scale;        /* UncertPropPnPOptimizer(std_scale=10); only for MRPNP_W_LOGSTD           */

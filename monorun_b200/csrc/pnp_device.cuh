@@ -163,25 +163,28 @@ struct Camera {
 //   acc[5..14] J^T J upper triangle  (00 01 02 03 11 12 13 22 23 33)
 // Every operation is fp64 in the reference's own order of evaluation, so decisions of the LM loop are
 // reproduced exactly.
-// CLIPSEM 0: Ceres-Jet semantics (pnp_uncert_cpu.cpp:36-42): z clip drops only d/dz', u/v clamp drops that row.
-// CLIPSEM 1: jacobian.py:52-59 semantics: a z-clipped point loses both rows (used for the pipeline covariance).
-// USE_BITS : skip points whose bit in `bits` (bit k <-> point 32k+lane) is 0 (outliers when not compacted).
-// `clip` returns whether any point of the warp hit a clip.
-template <int WMODE, int LAYOUT, int CLIPSEM, bool USE_BITS>
-__device__ __forceinline__ void eval_pass_fp64(const float* __restrict__ s3, const float* __restrict__ s2,
-                                               const float* __restrict__ sw, int P, int n, int lane, uint32_t bits,
-                                               const double x[4], const Camera<double>& cam, double acc[16],
-                                               double* scratch, bool& clip) {
+// clipsem 0: Ceres-Jet semantics (pnp_uncert_cpu.cpp:36-42): z clip drops only d/dz', u/v clamp drops that row.
+// clipsem 1: jacobian.py:52-59 semantics: a z-clipped point loses both rows (used for the pipeline covariance).
+// use_bits : skip points whose bit in `bits` (bit k <-> point 32k+lane) is 0 (outliers when not compacted).
+// *clip_out returns whether any point of the warp hit a clip.  Deliberately not inlined: it is the main
+// pass only in MRPNP_PREC_FP64 mode and the cold fallback of the mixed pass, and keeping one copy keeps the
+// hot code of the kernel inside the instruction cache.
+template <int WMODE, int LAYOUT>
+__device__ __noinline__ void eval_pass_fp64(const float* __restrict__ s3, const float* __restrict__ s2,
+                                            const float* __restrict__ sw, int P, int n, int lane, uint32_t bits,
+                                            int clipsem, bool use_bits, const double* x, const Camera<double>& cam,
+                                            double* acc_out, double* scratch, bool* clip_out) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     double sn, cs;
     sincos(x[0], &sn, &cs);
     const double tx = x[1], ty = x[2], tz = x[3];
+    double acc[16];  // register accumulators; copied to acc_out after the reduction
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.0;
     bool any = false;
 #pragma unroll 2
     for (int p = lane, k = 0; p < n; p += 32, ++k) {
-        if (USE_BITS && !((bits >> k) & 1u)) continue;
+        if (use_bits && !((bits >> k) & 1u)) continue;
         const double X = (double)s3[sidx<LAYOUT, 3>(p, 0, P)];
         const double Y = (double)s3[sidx<LAYOUT, 3>(p, 1, P)];
         const double Z = (double)s3[sidx<LAYOUT, 3>(p, 2, P)];
@@ -202,7 +205,7 @@ __device__ __forceinline__ void eval_pass_fp64(const float* __restrict__ s3, con
         any = any || !zfree || !ufree || !vfree;
         const double du = pu - uo, dv = pv - vo;
         const double mz = zfree ? 1.0 : 0.0;
-        if (CLIPSEM == 1 && !zfree) { ufree = false; vfree = false; }
+        if (clipsem == 1 && !zfree) { ufree = false; vfree = false; }
         // unweighted projection Jacobian rows: Ju = (ju0, a_u, 0, b_u), Jv = (jv0, 0, a_v, b_v)
         const double au = ufree ? cam.fx * iz : 0.0;
         const double av = vfree ? cam.fy * iz : 0.0;
@@ -255,8 +258,10 @@ __device__ __forceinline__ void eval_pass_fp64(const float* __restrict__ s3, con
             acc[14] = fma(a3, a3, fma(b3, b3, acc[14]));
         }
     }
-    clip = __any_sync(kFull, any);
+    *clip_out = __any_sync(kFull, any);
     warp_allreduce16<double>(acc, scratch, lane);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc_out[i] = acc[i];
 }
 
 // ------------------------------------------------------------------ fused pass, mixed precision (MRPNP_PREC_MIXED)
@@ -264,90 +269,62 @@ __device__ __forceinline__ void eval_pass_fp64(const float* __restrict__ s3, con
 // the fp64 pipe, so cost and cost differences -- what the trust-region accept / function-tolerance tests
 // read -- agree with the fp64 reference to ~1e-15.  The Jacobian, J^T r and J^T J are built from an
 // independent fp32 projection on the FMA pipe (errors ~1e-7 relative, which only perturb the step).
-// Rows in which any lane is clipped (never on in-range data) take the exact fp64 routine instead.
-// Output layout as eval_pass_fp64.
-template <int WMODE, int LAYOUT, int CLIPSEM, bool USE_BITS>
+// If any point comes within a small margin of a clip bound (never on in-range data) `flagged_out` is set
+// and the caller redoes the whole pass with the exact fp64 routine.  Output layout as eval_pass_fp64.
+// (An invalid padding lane re-reads point n-1 with zero weights, so it can only raise the flag if that
+// point itself is near a clip.)
+template <int WMODE, int LAYOUT>
 __device__ __forceinline__ void eval_pass_mixed(const float* __restrict__ s3, const float* __restrict__ s2,
-                                                const float* __restrict__ sw, int P, int n, int lane, uint32_t bits,
+                                                const float* __restrict__ sw, int P, int n, int lane,
                                                 const double x[4], const Camera<double>& cam,
                                                 const Camera<float>& camf, double acc[16], double* scratch,
-                                                bool& clip) {
+                                                bool& flagged_out) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     double sn, cs;
     sincos(x[0], &sn, &cs);
     const double tx = x[1], ty = x[2], tz = x[3];
     const float snf = (float)sn, csf = (float)cs, txf = (float)tx, tyf = (float)ty, tzf = (float)tz;
+    // clip detection on the fp32 projection with a safety margin far above its rounding error (~1e-4 px)
+    const float zlo = camf.z_min * 1.001f + 1e-3f;
+    const float ulo = camf.u_min + 0.05f, uhi = camf.u_max - 0.05f, vlo = camf.v_min + 0.05f, vhi = camf.v_max - 0.05f;
     double cost2 = 0.0;
     float a[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = 0.f;
-    bool any = false;
+    bool flagged = false;
     const int rows = (n + 31) >> 5;
 #pragma unroll 2
     for (int k = 0; k < rows; ++k) {
         const int pr = k * 32 + lane;
-        bool valid = pr < n;
-        if (USE_BITS) valid = valid && ((bits >> k) & 1u);
-        const int p = pr < n ? pr : n - 1;
+        const bool valid = pr < n;
+        const int p = valid ? pr : n - 1;
         const float Xf = s3[sidx<LAYOUT, 3>(p, 0, P)], Yf = s3[sidx<LAYOUT, 3>(p, 1, P)], Zf = s3[sidx<LAYOUT, 3>(p, 2, P)];
         const float uf = s2[sidx<LAYOUT, 2>(p, 0, P)], vf = s2[sidx<LAYOUT, 2>(p, 1, P)];
         float w0 = sw[sidx<LAYOUT, WC>(p, 0, P)], w1 = sw[sidx<LAYOUT, WC>(p, 1, P)];
         float w2 = (WMODE == MRPNP_W_FULL) ? sw[sidx<LAYOUT, WC>(p, WC - 1, P)] : 0.f;
-        if (!valid) { w0 = 0.f; w1 = 0.f; w2 = 0.f; }  // padding lanes / outliers contribute nothing
-        // ---- fp64 residual chain ----
+        if (!valid) { w0 = 0.f; w1 = 0.f; w2 = 0.f; }  // padding lanes contribute nothing
+        // ---- fp32 projection: Jacobian + clip detection ----
+        const float qxf = fmaf(csf, Xf, snf * Zf), qzf = fmaf(csf, Zf, -snf * Xf);
+        const float xcf = qxf + txf, ycf = Yf + tyf, zcf = qzf + tzf;
+        const float izf = fast_rcp(zcf);
+        const float xnf = xcf * izf, ynf = ycf * izf;
+        const float puf = fmaf(camf.fx, xnf, camf.cx), pvf = fmaf(camf.fy, ynf, camf.cy);
+        flagged = flagged || !(zcf >= zlo) || !(puf >= ulo) || !(puf <= uhi) || !(pvf >= vlo) || !(pvf <= vhi);
+        const float au = camf.fx * izf, av = camf.fy * izf;
+        const float bu = -au * xnf, bv = -av * ynf;
+        const float ju0 = fmaf(au, qzf, -bu * qxf), jv0 = -bv * qxf;
+        // ---- fp64 residual chain (no clip assumed; the pass is redone exactly if any point was flagged) ----
         const double X = (double)Xf, Y = (double)Yf, Z = (double)Zf;
         const double qx = fma(cs, X, sn * Z);
         const double qz = fma(cs, Z, -sn * X);
         const double xc = qx + tx, yc = Y + ty, zc = qz + tz;
         const double iz = fast_rcp(zc);
-        const double pu = fma(cam.fx, xc * iz, cam.cx);
-        const double pv = fma(cam.fy, yc * iz, cam.cy);
-        const bool flagged = (zc < cam.z_min) || (pu < cam.u_min) || (pu > cam.u_max) || (pv < cam.v_min) || (pv > cam.v_max);
-        if (__any_sync(kFull, flagged && valid)) {
-            // ---- exact slow row: full clip semantics in fp64 ----
-            any = true;
-            const bool zfree = !(zc < cam.z_min);
-            const double z = zfree ? zc : cam.z_min;
-            const double izc = fast_rcp(z);
-            const double xn = xc * izc, yn = yc * izc;
-            double pu2 = fma(cam.fx, xn, cam.cx), pv2 = fma(cam.fy, yn, cam.cy);
-            bool ufree = true, vfree = true;
-            if (pu2 < cam.u_min) { pu2 = cam.u_min; ufree = false; } else if (pu2 > cam.u_max) { pu2 = cam.u_max; ufree = false; }
-            if (pv2 < cam.v_min) { pv2 = cam.v_min; vfree = false; } else if (pv2 > cam.v_max) { pv2 = cam.v_max; vfree = false; }
-            const double du = pu2 - (double)uf, dv = pv2 - (double)vf;
-            const double mz = zfree ? 1.0 : 0.0;
-            if (CLIPSEM == 1 && !zfree) { ufree = false; vfree = false; }
-            const double au = ufree ? cam.fx * izc : 0.0, av = vfree ? cam.fy * izc : 0.0;
-            const double bu = -au * xn * mz, bv = -av * yn * mz;
-            const double ju0 = fma(au, qz, -bu * qx), jv0 = -bv * qx;
-            const double wxx = (double)w0, wxy = (WMODE == MRPNP_W_FULL) ? (double)w1 : 0.0;
-            const double wyy = (WMODE == MRPNP_W_FULL) ? (double)w2 : (double)w1;
-            const double r0 = fma(wxx, du, wxy * dv), r1 = fma(wxy, du, wyy * dv);
-            const double ja[4] = {fma(wxx, ju0, wxy * jv0), wxx * au, wxy * av, fma(wxx, bu, wxy * bv)};
-            const double jb[4] = {fma(wxy, ju0, wyy * jv0), wxy * au, wyy * av, fma(wxy, bu, wyy * bv)};
-            cost2 = fma(r0, r0, fma(r1, r1, cost2));
-            int q = 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                a[i] += (float)fma(ja[i], r0, jb[i] * r1);
-#pragma unroll
-                for (int j = i; j < 4; ++j, ++q) a[q] += (float)fma(ja[i], ja[j], jb[i] * jb[j]);
-            }
-            continue;
-        }
-        const double du = pu - (double)uf, dv = pv - (double)vf;
-        // ---- fp32 Jacobian branch (independent projection; no clip on this row) ----
-        const float qxf = fmaf(csf, Xf, snf * Zf), qzf = fmaf(csf, Zf, -snf * Xf);
-        const float xcf = qxf + txf, ycf = Yf + tyf, zcf = qzf + tzf;
-        const float izf = fast_rcp(zcf);
-        const float xnf = xcf * izf, ynf = ycf * izf;
-        const float au = camf.fx * izf, av = camf.fy * izf;
-        const float bu = -au * xnf, bv = -av * ynf;
-        const float ju0 = fmaf(au, qzf, -bu * qxf), jv0 = -bv * qxf;
+        const double du = fma(cam.fx, xc * iz, cam.cx) - (double)uf;
+        const double dv = fma(cam.fy, yc * iz, cam.cy) - (double)vf;
         if (WMODE != MRPNP_W_FULL) {
             const double ru = (double)w0 * du, rv = (double)w1 * dv;
             cost2 = fma(ru, ru, fma(rv, rv, cost2));
-            const float ruf = w0 * (fmaf(camf.fx, xnf, camf.cx) - uf), rvf = w1 * (fmaf(camf.fy, ynf, camf.cy) - vf);
+            const float ruf = w0 * (puf - uf), rvf = w1 * (pvf - vf);
             const float a0 = w0 * ju0, a1 = w0 * au, a3 = w0 * bu;
             const float b0 = w1 * jv0, b2 = w1 * av, b3 = w1 * bv;
             a[0] = fmaf(a0, ruf, fmaf(b0, rvf, a[0]));
@@ -366,7 +343,7 @@ __device__ __forceinline__ void eval_pass_mixed(const float* __restrict__ s3, co
         } else {
             const double r0 = fma((double)w0, du, (double)w1 * dv), r1 = fma((double)w1, du, (double)w2 * dv);
             cost2 = fma(r0, r0, fma(r1, r1, cost2));
-            const float duf = fmaf(camf.fx, xnf, camf.cx) - uf, dvf = fmaf(camf.fy, ynf, camf.cy) - vf;
+            const float duf = puf - uf, dvf = pvf - vf;
             const float r0f = fmaf(w0, duf, w1 * dvf), r1f = fmaf(w1, duf, w2 * dvf);
             const float a0 = fmaf(w0, ju0, w1 * jv0), a1 = w0 * au, a2 = w1 * av, a3 = fmaf(w0, bu, w1 * bv);
             const float b0 = fmaf(w1, ju0, w2 * jv0), b1 = w1 * au, b2 = w2 * av, b3 = fmaf(w1, bu, w2 * bv);
@@ -386,7 +363,7 @@ __device__ __forceinline__ void eval_pass_mixed(const float* __restrict__ s3, co
             a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
         }
     }
-    clip = any;
+    flagged_out = __any_sync(kFull, flagged);
     // cost: 5-step fp64 butterfly; the 14 fp32 sums: transposed reduction through the scratch
     cost2 = warp_sum(cost2);
     warp_allreduce16<float>(a, reinterpret_cast<float*>(scratch), lane);
@@ -502,9 +479,9 @@ __device__ __forceinline__ bool chol_solve_dense(double A[N][N], const double b[
 
 // fp32 accumulation of the (well-scaled, normalised-coordinate) normal equations, fp64 solves.
 template <int WMODE, int LAYOUT>
-__device__ __forceinline__ bool linear_init(const float* __restrict__ s3, const float* __restrict__ s2,
+__device__ __noinline__ bool linear_init(const float* __restrict__ s3, const float* __restrict__ s2,
                                             const float* __restrict__ sw, int P, int n, int lane,
-                                            const Camera<float>& cam, float* scratch, double x[4]) {
+                                            const Camera<float>& cam, float* scratch, double* x) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     const float ifx = 1.f / cam.fx, ify = 1.f / cam.fy;
     // ---- stage A: 5 unknowns: 15 matrix entries + 5 rhs = 20 sums -> two transposed reductions ----

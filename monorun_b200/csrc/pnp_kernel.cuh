@@ -87,10 +87,10 @@ __device__ __forceinline__ void weights_and_thresholds(const KParams& kp, float*
 // Sweep B: inlier decision (pnp_uncert_cpu.py:166-168 or the caller's packed mask), packed inlier_out,
 // and in-place order-preserving compaction (boolean-mask indexing of pnp_uncert_cpu.py:24-27,62-66).
 // Returns the inlier count; `bits` = this lane's inlier flags (bit k <-> point 32k+lane).
-// With COMPACT the slot is rewritten; the caller must re-load it if the count turns out to be <= 4.
-template <int WMODE, int LAYOUT, bool COMPACT>
+// With `compact` the slot is rewritten; the caller must re-load it if the count turns out to be <= 4.
+template <int WMODE, int LAYOUT>
 __device__ __forceinline__ int mask_and_compact(const KParams& kp, int obj, float* slot, int lane, float thr_u,
-                                                float thr_v, bool all_inliers, uint32_t& bits) {
+                                                float thr_v, bool all_inliers, bool compact, uint32_t& bits) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     constexpr int CV = WC - 1;
     const int P = kp.n_pts;
@@ -123,7 +123,7 @@ __device__ __forceinline__ int mask_and_compact(const KParams& kp, int obj, floa
         const unsigned m = __ballot_sync(kFull, inl);
         bits |= (inl ? 1u : 0u) << k;
         if (lane == k) out_word = m;
-        if (COMPACT) {
+        if (compact) {
             float v3[3], v2[2], w1 = 0.f;
             if (inl) {
 #pragma unroll
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
     }
     __syncwarp();
     uint32_t parity = 0;
-    const int max_iter = kp.max_iter > 0 ? kp.max_iter : 50;
+    const int max_iter = kp.max_iter > 0 ? kp.max_iter : (kp.max_iter < 0 ? 0 : 50);
 
     while (true) {
         int obj = 0;
@@ -204,89 +204,139 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
             load_object<WC>(kp, obj, slot, bar, parity, lane);
             float thr_u, thr_v;
             weights_and_thresholds<WMODE, LAYOUT, MIXED>(kp, slot + 5 * P, lane, thr_u, thr_v);
-            if (attempt == 1) {  // pnp_uncert_cpu.py:28-32: <= 4 inliers -> every point is an inlier
-                n_inliers = mask_and_compact<WMODE, LAYOUT, false>(kp, obj, slot, lane, thr_u, thr_v, true, bits);
+            // second attempt == pnp_uncert_cpu.py:28-32: <= 4 inliers -> every point is an inlier (slot re-staged)
+            const bool all = attempt == 1;
+            const bool compact = !all && kp.inlier_opt_only != 0;
+            n_inliers = mask_and_compact<WMODE, LAYOUT>(kp, obj, slot, lane, thr_u, thr_v, all, compact, bits);
+            if (all || n_inliers > 4) {
+                compacted = compact;
                 break;
             }
-            if (kp.inlier_opt_only) {
-                n_inliers = mask_and_compact<WMODE, LAYOUT, true>(kp, obj, slot, lane, thr_u, thr_v, false, bits);
-                if (n_inliers > 4) { compacted = true; n = n_inliers; break; }
-            } else {
-                n_inliers = mask_and_compact<WMODE, LAYOUT, false>(kp, obj, slot, lane, thr_u, thr_v, false, bits);
-                if (n_inliers > 4) break;
-            }
         }
-        if (!compacted) n = P;
-        const bool lm_bits = !compacted && !kp.inlier_opt_only && n_inliers < P;  // never: LM then sees all points
-        (void)lm_bits;
+        n = compacted ? n_inliers : P;
 
         // ---------------- Levenberg-Marquardt, Ceres 1.14 TrustRegionMinimizer control flow ----------------
-        double x[4];
+        // One evaluation site: `pt` is the initial point in phase 0 and the candidate x + delta afterwards.
+        double x[4], pt[4];
         bool init_ok = true;
         if (kp.init_mode == MRPNP_INIT_GIVEN) {
             const float* ip = kp.init + (size_t)obj * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = (double)__ldg(ip + i);
+            for (int i = 0; i < 4; ++i) pt[i] = (double)__ldg(ip + i);
         } else {
-            init_ok = linear_init<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, camf, reinterpret_cast<float*>(scratch), x);
-            if (!init_ok) { x[0] = x[1] = x[2] = x[3] = 0.0; }  // pnp_uncert_cpu.py:119-125
+            init_ok = linear_init<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, camf, reinterpret_cast<float*>(scratch), pt);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = (double)(float)x[i];  // fp32 hand-over, like the EPnP result
+            for (int i = 0; i < 4; ++i) pt[i] = init_ok ? (double)(float)pt[i] : 0.0;  // fp32 hand-over; .py:119-125
         }
-        double acc[16];
-        bool clip_x;
-        if (MIXED) eval_pass_mixed<WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, x, cam, camf, acc, scratch, clip_x);
-        else eval_pass_fp64<WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, x, cam, acc, scratch, clip_x);
-        double cost = 0.5 * acc[0];
-        double g[4], H[10];  // unscaled gradient / Gauss-Newton matrix at x
 #pragma unroll
-        for (int i = 0; i < 4; ++i) g[i] = acc[1 + i];
-#pragma unroll
-        for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
-        bool finite = finite_value(acc[0]);
-#pragma unroll
-        for (int i = 1; i < 15; ++i) finite = finite && finite_value(acc[i]);
+        for (int i = 0; i < 4; ++i) x[i] = pt[i];
 
-        int term = kNoConvergence;
-        int iteration = 0, cost_evals = 1;
-        double radius = kInitialRadius;
-        if (!finite || !init_ok) {
-            term = kFailure;  // IterationZero failed: parameters stay at init
-        } else {
-            double scale[4];  // jacobi_scaling from the initial Jacobian only
+        double cost = 0.0, g[4], H[10], scale[4], diag[4], delta[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) scale[i] = fast_rcp(1.0 + fast_sqrt(H[tri(i, i)]));
-            double diag[4];
-            double decrease_factor = 2.0;
-            bool reuse_diagonal = false;
-            int num_invalid = 0;
-            double x_norm = fast_sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-            bool step_ok = true;  // iteration 0 counts as a successful step
+        for (int i = 0; i < 4; ++i) { g[i] = 0.0; scale[i] = 1.0; diag[i] = 1.0; delta[i] = 0.0; }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) H[i] = 0.0;
+        int term = kNoConvergence, iteration = 0, cost_evals = 0, num_invalid = 0;
+        double radius = kInitialRadius, decrease_factor = 2.0, x_norm = 0.0, model_change = 1.0;
+        bool reuse_diagonal = false, step_ok = true, clip_x = false, first = true;
+
+        while (true) {
+            // ---- the fused pass at pt ----
+            double acc[16];
+            bool clip_p = false;
+            if (MIXED) {
+                bool flagged;
+                eval_pass_mixed<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, pt, cam, camf, acc, scratch, flagged);
+                if (flagged)  // a point near a clip bound: redo the pass with exact fp64 clip semantics
+                    eval_pass_fp64<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, bits, 0, false, pt, cam, acc, scratch, &clip_p);
+            } else {
+                eval_pass_fp64<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, bits, 0, false, pt, cam, acc, scratch, &clip_p);
+            }
+            ++cost_evals;
+            const bool cfinite = finite_value(acc[0]);
+            double asum = 0.0;  // finite iff every Jacobian sum is finite
+#pragma unroll
+            for (int i = 1; i < 15; ++i) asum += fabs(acc[i]);
+            const bool jfinite = cfinite && finite_value(asum);
+            bool accept = false;
+            if (first) {  // IterationZero
+                first = false;
+                if (!jfinite || !init_ok) { term = kFailure; break; }  // parameters stay at init
+                accept = true;
+                cost = 0.5 * acc[0];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)  // jacobi_scaling from the initial Jacobian only
+                    scale[i] = fast_rcp(1.0 + fast_sqrt(acc[5 + tri(i, i)]));
+            } else {
+                const double cand_cost = cfinite ? 0.5 * acc[0] : kDblMax;
+                // ParameterToleranceReached
+                const double step_norm2 = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2] + delta[3] * delta[3];
+                const double ptol = kParameterTol * (x_norm + kParameterTol);
+                if (step_norm2 <= ptol * ptol) { term = kConvergence; break; }
+                // FunctionToleranceReached (Ceres 1.14: the candidate is not adopted on this exit)
+                const double cost_change = cost - cand_cost;
+                if (fabs(cost_change) <= kFunctionTol * cost) {
+                    term = kConvergence;
+                    if (!(kp.adopt_ftol && cand_cost < cost)) break;
+                    accept = true;  // documented switch: take the candidate, then stop
+                }
+                const double rho = cost_change * fast_rcp(model_change);
+                if (accept || rho > kMinRelDecrease) {  // HandleSuccessfulStep
+                    if (!jfinite) { term = kFailure; break; }  // re-evaluation at the new point fails in Ceres
+                    const bool stop = accept;
+                    accept = true;
+                    cost = cand_cost;
+                    const double q = 2.0 * rho - 1.0;
+                    radius = fmin(kMaxRadius, radius * fast_rcp(fmax(1.0 / 3.0, 1.0 - q * q * q)));
+                    decrease_factor = 2.0;
+                    reuse_diagonal = false;
+                    if (stop) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { x[i] = pt[i]; g[i] = acc[1 + i]; }
+#pragma unroll
+                        for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
+                        clip_x = clip_p;
+                        break;
+                    }
+                } else {  // HandleUnsuccessfulStep
+                    radius /= decrease_factor;
+                    decrease_factor *= 2.0;
+                }
+            }
+            if (accept) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { x[i] = pt[i]; g[i] = acc[1 + i]; }
+#pragma unroll
+                for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
+                clip_x = clip_p;
+                x_norm = fast_sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+                step_ok = true;
+            }
+            // ---- next trust-region step (invalid steps shrink the radius without a new evaluation) ----
+            bool stop = false;
             while (true) {
                 // FinalizeIterationAndCheckIfMinimizerCanContinue
-                if (iteration >= max_iter) { term = kNoConvergence; break; }
+                if (iteration >= max_iter) { term = kNoConvergence; stop = true; break; }
                 if (step_ok) {
                     const double gmax = fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3])));
-                    if (gmax <= kGradientTol) { term = kConvergence; break; }
+                    if (gmax <= kGradientTol) { term = kConvergence; stop = true; break; }
                 }
-                if (radius <= kMinRadius) { term = kConvergence; break; }
+                if (radius <= kMinRadius) { term = kConvergence; stop = true; break; }
                 ++iteration;
                 step_ok = false;
-
                 // LevenbergMarquardtStrategy::ComputeStep on the column-scaled system
-                double Hs[10], gs[4];
+                double Hs[10], gs[4], A[10], y[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     gs[i] = g[i] * scale[i];
 #pragma unroll
-                    for (int j = i; j < 4; ++j) Hs[tri(i, j)] = H[tri(i, j)] * scale[i] * scale[j];
+                    for (int j = i; j < 4; ++j) Hs[tri(i, j)] = H[tri(i, j)] * (scale[i] * scale[j]);
                 }
                 if (!reuse_diagonal) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) diag[i] = fmin(fmax(Hs[tri(i, i)], kMinLmDiag), kMaxLmDiag);
                 }
                 reuse_diagonal = true;
-                double A[10], y[4];
                 const double inv_radius = fast_rcp(radius);
 #pragma unroll
                 for (int i = 0; i < 10; ++i) A[i] = Hs[i];
@@ -294,83 +344,33 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
                 for (int i = 0; i < 4; ++i) A[tri(i, i)] = fma(diag[i], inv_radius, A[tri(i, i)]);
                 const Ldl4 f = ldl4_factor(A);
                 bool valid = f.ok;
-                double model_change = 0.0;
                 if (valid) {
                     ldl4_solve(f, gs, y);  // step = -y
                     // model_cost_change = -step^T gs - 1/2 step^T Hs step = y^T gs - 1/2 y^T Hs y
                     double yg = 0.0, yhy = 0.0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        double s = 0.0;
+                        double t = 0.0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) s = fma(Hs[tri(i, j)], y[j], s);
+                        for (int j = 0; j < 4; ++j) t = fma(Hs[tri(i, j)], y[j], t);
                         yg = fma(y[i], gs[i], yg);
-                        yhy = fma(y[i], s, yhy);
+                        yhy = fma(y[i], t, yhy);
                     }
                     model_change = fma(-0.5, yhy, yg);
-                    valid = (model_change > 0.0) && (fabs(y[0]) + fabs(y[1]) + fabs(y[2]) + fabs(y[3]) < kDblMax);
+                    valid = (model_change > 0.0) && finite_value(fabs(y[0]) + fabs(y[1]) + fabs(y[2]) + fabs(y[3]));
                 }
-                if (!valid) {  // HandleInvalidStep
-                    if (++num_invalid >= kMaxInvalidSteps) { term = kFailure; break; }
-                    radius /= decrease_factor;
-                    decrease_factor *= 2.0;
-                    continue;
-                }
-                num_invalid = 0;
-                double delta[4], cand[4];
+                if (valid) {
+                    num_invalid = 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { delta[i] = -y[i] * scale[i]; cand[i] = x[i] + delta[i]; }
-
-                // candidate cost, fused with its gradient / Gauss-Newton matrix (used only if accepted)
-                bool clip_c;
-                if (MIXED) eval_pass_mixed<WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, cand, cam, camf, acc, scratch, clip_c);
-                else eval_pass_fp64<WMODE, LAYOUT, 0, false>(s3, s2, sw, P, n, lane, bits, cand, cam, acc, scratch, clip_c);
-                ++cost_evals;
-                const bool cfinite = finite_value(acc[0]);
-                bool jfinite = cfinite;  // the fused pass also produced the candidate's Jacobian sums
-#pragma unroll
-                for (int i = 1; i < 15; ++i) jfinite = jfinite && finite_value(acc[i]);
-                const double cand_cost = cfinite ? 0.5 * acc[0] : kDblMax;
-
-                // ParameterToleranceReached
-                const double step_norm2 = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2] + delta[3] * delta[3];
-                const double ptol = kParameterTol * (x_norm + kParameterTol);
-                if (step_norm2 <= ptol * ptol) { term = kConvergence; break; }
-                // FunctionToleranceReached (Ceres 1.14: candidate is not adopted on this exit)
-                const double cost_change = cost - cand_cost;
-                if (fabs(cost_change) <= kFunctionTol * cost) {
-                    if (kp.adopt_ftol && cand_cost < cost) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { x[i] = cand[i]; g[i] = acc[1 + i]; }
-#pragma unroll
-                        for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
-                        cost = cand_cost;
-                        clip_x = clip_c;
-                    }
-                    term = kConvergence;
+                    for (int i = 0; i < 4; ++i) { delta[i] = -y[i] * scale[i]; pt[i] = x[i] + delta[i]; }
                     break;
                 }
-                const double rho = cost_change * fast_rcp(model_change);
-                if (rho > kMinRelDecrease) {  // HandleSuccessfulStep
-                    if (!jfinite) { term = kFailure; break; }  // re-evaluation at the new point fails in Ceres
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { x[i] = cand[i]; g[i] = acc[1 + i]; }
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
-                    cost = cand_cost;
-                    clip_x = clip_c;
-                    x_norm = fast_sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-                    step_ok = true;
-                    const double q = 2.0 * rho - 1.0;
-                    radius = radius * fast_rcp(fmax(1.0 / 3.0, 1.0 - q * q * q));
-                    radius = fmin(kMaxRadius, radius);
-                    decrease_factor = 2.0;
-                    reuse_diagonal = false;
-                } else {  // HandleUnsuccessfulStep
-                    radius /= decrease_factor;
-                    decrease_factor *= 2.0;
-                }
+                // HandleInvalidStep
+                if (++num_invalid >= kMaxInvalidSteps) { term = kFailure; stop = true; break; }
+                radius /= decrease_factor;
+                decrease_factor *= 2.0;
             }
+            if (stop) break;
         }
         bool usable = term != kFailure;  // Summary::IsSolutionUsable (pnp_uncert_cpu.cpp:276)
 
@@ -385,8 +385,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
             const bool need_pass = kp.cov_mode == MRPNP_COV_PIPELINE && (any_clip || (!compacted && n_inliers < P));
             if (need_pass) {
                 bool c2;
-                eval_pass_fp64<WMODE, LAYOUT, 1, true>(s3, s2, sw, P, n, lane, compacted ? 0xffffffffu : bits, x, cam,
-                                                       acc, scratch, c2);
+                double acc[16];
+                eval_pass_fp64<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, bits, 1, !compacted, x, cam, acc, scratch, &c2);
 #pragma unroll
                 for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
             }

@@ -1,0 +1,296 @@
+"""Drop-in heads of the hot path, registered under the reference's names in ``HEADS``.
+
+* UncertPropPnPOptimizer  <- monorun/models/roi_heads/bbox_3d_heads/optimizers/uncert_prop_pnp_optimizer.py:12-99
+* FCNNOCDecoder           <- monorun/models/roi_heads/bbox_3d_heads/dense_decoders/fcn_noc_decoder.py:15-267
+* UncertProjectionHead    <- .../reprojection_heads/uncert_projection_head.py (test-time parts: get_distance, coder)
+* MonoRUnRoIHead          <- monorun/models/roi_heads/monorun_roi_head.py:13-40, hot sequence :509-534
+
+Constructor kwargs, attribute names, state-dict keys and return tuples follow the reference so that the
+``roi_head`` blocks of configs/kitti_*.py build and pretrained weights would load.  Training-only members
+(losses, target builders) are accepted and ignored: the PnP forward is non-differentiable in the reference too
+(pnp_uncert.py:33) and training is out of this path's scope.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .coders import coords_2d_from_rois
+from .registry import (HEADS, build_coord_coder, build_head, build_pnp, build_proj_error_coder,
+                       build_rotation_coder)
+
+
+@HEADS.register_module()
+class UncertPropPnPOptimizer(nn.Module):
+    """Pose head: log-std -> weights, clip ranges, PnP, covariance calibration.
+
+    The reference permutes the three NCHW maps to (N, 784, C) and calls the op (:82-95); here the NCHW tensors and
+    the log-std go straight into the kernel (``PnPUncert.forward_dense``), which fuses :73 and :82-84.
+    """
+
+    def __init__(self, loss_rot=None, loss_trans=None, loss_calib=None,
+                 rotation_coder=dict(type='Vec2DRotationCoder'),
+                 pnp=dict(type='PnPUncert', z_min=0.5, epnp_istd_thres=0.6, inlier_opt_only=True,
+                          forward_exact_hessian=False),
+                 allowed_border=200, epnp_ransac_thres_ratio=0.2, std_scale=10):
+        super(UncertPropPnPOptimizer, self).__init__()
+        pnp = dict(pnp)
+        pnp.pop('backward_exact_hessian', None)  # present in the reference's default dict, rejected by PnPUncert
+        self.pnp = build_pnp(pnp)
+        self.epnp_ransac_thres_ratio = epnp_ransac_thres_ratio
+        self.allowed_border = allowed_border
+        self.std_scale = std_scale
+        self.rotation_coder = build_rotation_coder(rotation_coder)
+        self.fp16_enabled = False
+        self.loss_rot = self.loss_trans = self.loss_calib = None  # training only
+        self.cov_calib_logscale = nn.Parameter(torch.full((4, ), 0, dtype=torch.float))
+
+    def init_weights(self):
+        pass
+
+    def forward(self, coords_2d, coords_2d_logstd, coords_3d, cam_intrinsic, img_shapes, init_pose=None):
+        """uncert_prop_pnp_optimizer.py:50-99.
+
+        Args:
+            coords_2d (Tensor): (Nbatch, 2, h, w);  coords_2d_logstd (Tensor): (Nbatch, 2, h, w)
+            coords_3d (Tensor): (Nbatch, 3, h, w);  cam_intrinsic (Tensor): (Nbatch, 3, 3) or (1, 3, 3)
+            img_shapes (Tensor): (Nbatch, 2) or (1, 2), rows are (h, w)
+        Returns:
+            ret_val (Nbatch,) bool, yaw_pred (Nbatch, 1), t_vec_pred (Nbatch, 3),
+            pose_cov_pred (Nbatch, 4, 4), pose_cov_calib (Nbatch, 4, 4)
+        """
+        b = float(self.allowed_border)
+        uv_range = coords_2d.new_empty((img_shapes.size(0), 4))
+        uv_range[:, 0] = -b                      # :75-80
+        uv_range[:, 1] = img_shapes[:, 1] + b
+        uv_range[:, 2] = -b
+        uv_range[:, 3] = img_shapes[:, 0] + b
+        ret_val, yaw_pred, t_vec_pred, pose_cov_pred, _ = self.pnp.forward_dense(
+            coords_2d, coords_2d_logstd, coords_3d, cam_intrinsic, uv_range, self.std_scale, init_pose=init_pose)
+        cov_calib_scale = torch.exp(self.cov_calib_logscale)
+        pose_cov_calib = (cov_calib_scale * cov_calib_scale[:, None]) * pose_cov_pred  # :96-97
+        return ret_val, yaw_pred, t_vec_pred, pose_cov_pred, pose_cov_calib
+
+
+class ConvModule(nn.Module):
+    """mmcv.cnn.ConvModule with norm_cfg=None: Conv2d(bias=True) + ReLU (fcn_noc_decoder.py:98-105)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, padding=0):
+        super(ConvModule, self).__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, padding=padding)
+        self.activate = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.activate(self.conv(x))
+
+
+class CARAFEPack(nn.Module):
+    """Functional restatement of mmcv.ops.carafe.CARAFEPack (source not in this tree):
+    channel_compressor 1x1 -> content_encoder k_enc x k_enc -> pixel_shuffle -> softmax over the k_up^2 taps ->
+    per-pixel reassembly of the k_up x k_up neighbourhood of the low-resolution map."""
+
+    def __init__(self, channels, scale_factor, up_kernel=5, up_group=1, encoder_kernel=3, encoder_dilation=1,
+                 compressed_channels=64):
+        super(CARAFEPack, self).__init__()
+        self.channels, self.scale_factor, self.up_kernel, self.up_group = channels, scale_factor, up_kernel, up_group
+        self.channel_compressor = nn.Conv2d(channels, compressed_channels, 1)
+        self.content_encoder = nn.Conv2d(
+            compressed_channels, up_kernel * up_kernel * up_group * scale_factor * scale_factor, encoder_kernel,
+            padding=int((encoder_kernel - 1) * encoder_dilation / 2), dilation=encoder_dilation)
+
+    def init_weights(self):
+        nn.init.xavier_uniform_(self.channel_compressor.weight)
+        nn.init.constant_(self.channel_compressor.bias, 0)
+        nn.init.normal_(self.content_encoder.weight, std=0.001)
+        nn.init.constant_(self.content_encoder.bias, 0)
+
+    def forward(self, x):
+        n, c, h, w = x.shape
+        s, k, g = self.scale_factor, self.up_kernel, self.up_group
+        mask = self.content_encoder(self.channel_compressor(x))
+        mask = F.pixel_shuffle(mask, s)                                   # (n, g*k*k, h*s, w*s)
+        mask = F.softmax(mask.view(n, g, k * k, h * s, w * s), dim=2)
+        patches = F.unfold(x, k, padding=k // 2).view(n, g, c // g, k * k, h, w)
+        patches = patches.repeat_interleave(s, dim=4).repeat_interleave(s, dim=5)  # nearest source pixel
+        out = (patches * mask.unsqueeze(2)).sum(dim=3)
+        return out.view(n, c, h * s, w * s)
+
+
+@HEADS.register_module()
+class FCNNOCDecoder(nn.Module):
+    """Dense correspondence head, fcn_noc_decoder.py:15-267 (forward :189-240, slice_pred :242-267)."""
+
+    def __init__(self, num_convs=3, roi_feat_size=14, in_channels=256, conv_kernel_size=3, conv_out_channels=256,
+                 num_classes=3, class_agnostic=False,
+                 upsample_cfg=dict(type='carafe', scale_factor=2, up_kernel=5, up_group=1, encoder_kernel=3,
+                                   encoder_dilation=1, compressed_channels=64),
+                 num_convs_upsampled=1, conv_cfg=None, norm_cfg=None, loss_noc=None, noc_channels=3,
+                 uncert_channels=2, dropout2d_rate=0.2, num_dropout2d_layers=1, flip_correction=True, plugins=None,
+                 coord_coder=dict(type='NOCCoder', target_means=(-0.1, -0.5, 0.0), target_stds=(0.35, 0.23, 0.34),
+                                  eps=1e-5),
+                 use_latent_vec=True, latent_activation=None, latent_channels=16):
+        super(FCNNOCDecoder, self).__init__()
+        assert num_convs > 0 and conv_cfg is None and norm_cfg is None and plugins is None
+        up = dict(type='carafe', scale_factor=2, up_kernel=5, up_group=1, encoder_kernel=3, encoder_dilation=1,
+                  compressed_channels=64)  # mmcv CARAFEPack defaults, partially overridden by the config (:98)
+        up.update(upsample_cfg)
+        if up['type'] != 'carafe':
+            raise NotImplementedError('only the carafe upsampler used by every reference config is provided')
+        self.num_convs, self.num_convs_upsampled = num_convs, num_convs_upsampled
+        self.in_channels, self.conv_out_channels = in_channels, conv_out_channels
+        self.num_classes, self.class_agnostic = num_classes, class_agnostic
+        self.upsample_method, self.scale_factor = up.pop('type'), up.pop('scale_factor')
+        self.fp16_enabled = False
+        self.loss_noc = None  # training only
+        self.flip_correction = flip_correction
+        self.noc_channels, self.uncert_channels = noc_channels, uncert_channels
+        self.channel_per_class = noc_channels + uncert_channels
+        self.coord_coder = build_coord_coder(coord_coder)
+        self.use_latent_vec = use_latent_vec
+        self.latent_activation = (nn.ReLU() if latent_activation == 'ReLU'
+                                  else nn.LeakyReLU() if latent_activation == 'LeakyReLU' else None)
+        if use_latent_vec:
+            self.latent_decoder = nn.Linear(latent_channels, conv_out_channels)
+        pad = (conv_kernel_size - 1) // 2
+        self.convs = nn.ModuleList(
+            [ConvModule(in_channels if i == 0 else conv_out_channels, conv_out_channels, conv_kernel_size, pad)
+             for i in range(num_convs)])
+        self.upsample = CARAFEPack(channels=conv_out_channels, scale_factor=self.scale_factor, **up)
+        self.convs_upsampled = nn.ModuleList(
+            [ConvModule(conv_out_channels, conv_out_channels, conv_kernel_size, pad)
+             for _ in range(num_convs_upsampled)])
+        final_out = self.channel_per_class * (1 if class_agnostic else num_classes) * (2 if flip_correction else 1)
+        self.conv_final = nn.Conv2d(conv_out_channels, final_out, 1)
+        self.use_dropout2d = dropout2d_rate > 0
+        if self.use_dropout2d:
+            self.dropout2d = nn.Dropout2d(dropout2d_rate)
+        self.num_dropout2d_layers = num_dropout2d_layers
+
+    def init_weights(self):
+        self.upsample.init_weights()
+        nn.init.kaiming_normal_(self.conv_final.weight, mode='fan_out', nonlinearity='relu')
+        nn.init.constant_(self.conv_final.bias, 0)
+        if self.use_latent_vec:
+            nn.init.constant_(self.latent_decoder.weight, 0)
+            nn.init.constant_(self.latent_decoder.bias, 0)
+
+    def forward(self, x, latent_pred, latent_var, labels, flip=False):
+        if self.use_dropout2d and self.num_dropout2d_layers > 0:
+            x = self.dropout2d(x)
+        for i, conv in enumerate(self.convs):
+            x = conv(x)
+            if self.use_dropout2d and i + 1 < self.num_dropout2d_layers:
+                x = self.dropout2d(x)
+        if self.use_latent_vec:
+            if self.latent_activation is not None:
+                latent_pred = self.latent_activation(latent_pred)
+            x = x + self.latent_decoder(latent_pred)[..., None, None]
+        if x.size(0) == 0:
+            c = self.conv_final.out_channels // (2 if self.flip_correction else 1)
+            s = x.size(2) * self.scale_factor
+            all_pred = x.new_zeros((0, c, s, s))
+        else:
+            x = self.upsample(x)
+            for conv_upsampled in self.convs_upsampled:
+                x = conv_upsampled(x)
+            all_pred = self.conv_final(x)
+            if self.flip_correction:
+                all_pred = all_pred.view(all_pred.size(0), 2, all_pred.size(1) // 2, all_pred.size(2), all_pred.size(3))
+                if isinstance(flip, bool):
+                    all_pred = all_pred[:, 1 if flip else 0]
+                else:
+                    inds = torch.arange(0, all_pred.size(0), dtype=torch.long, device=all_pred.device)
+                    all_pred = all_pred[inds, inds.new_tensor(flip)]
+        noc_pred, noc_var, proj_logstd = self.slice_pred(all_pred, labels)
+        return noc_pred, noc_var, proj_logstd, None
+
+    def slice_pred(self, all_pred, labels):
+        k = 1 if self.class_agnostic else self.num_classes
+        all_noc_pred, all_proj_logstd = all_pred.split([self.noc_channels * k, self.uncert_channels * k], dim=1)
+        if self.class_agnostic:
+            return all_noc_pred, None, all_proj_logstd
+        n, _, h, w = all_noc_pred.size()
+        inds = torch.arange(0, n, dtype=torch.long, device=all_noc_pred.device)
+        noc_pred = all_noc_pred.view(n, self.num_classes, 3, h, w)[inds, labels]
+        proj_logstd = all_proj_logstd.view(n, self.num_classes, self.uncert_channels, h, w)[inds, labels]
+        return noc_pred, None, proj_logstd
+
+
+@HEADS.register_module()
+class UncertProjectionHead(nn.Module):
+    """Test-time members of uncert_projection_head.py: the projection-error coder and get_distance (:104-109)."""
+
+    def __init__(self, loss_proj=None, z_min=0.5, allowed_border=200,
+                 proj_error_coder=dict(type='DistanceInvarProjErrorCoder', ref_length=1.6, ref_focal_y=722,
+                                       target_std=0.15),
+                 distance_mode='range'):
+        super(UncertProjectionHead, self).__init__()
+        assert distance_mode in ['z-depth', 'range']
+        self.z_min, self.allowed_border, self.distance_mode = z_min, allowed_border, distance_mode
+        self.proj_error_coder = build_proj_error_coder(proj_error_coder)
+
+    def get_distance(self, t_vec):
+        return t_vec[:, 2] if self.distance_mode == 'z-depth' else torch.norm(t_vec, p=2, dim=1)
+
+
+_OUT_OF_SCOPE = ('bbox_roi_extractor', 'bbox_head', 'global_head', 'score_head', 'noc_roi_extractor',
+                 'shared_head', 'mask_roi_extractor', 'mask_head')
+
+
+@HEADS.register_module()
+class MonoRUnRoIHead(nn.Module):
+    """ROI head boundary class (monorun_roi_head.py:13-40).  Builds the on-path sub-heads (noc_head,
+    projection_head, pose_head); the mmdet-owned pieces that are outside this path's scope (2-D bbox head,
+    MC-dropout global extractor, score head, RoI extractors) are kept as their config dicts in ``self.deferred``
+    so that the whole ``roi_head`` block of configs/kitti_*.py is accepted.  ``forward_3d`` is the hot sequence
+    of ``simple_test`` (:509-534) on tensors the upstream detector stages provide."""
+
+    def __init__(self, noc_roi_extractor=None, noc_head=None, global_head=None, projection_head=None,
+                 pose_head=None, score_head=None, debug=False, train_cfg=None, test_cfg=None, **kwargs):
+        super(MonoRUnRoIHead, self).__init__()
+        self.deferred = {k: v for k, v in dict(kwargs, noc_roi_extractor=noc_roi_extractor, global_head=global_head,
+                                               score_head=score_head).items() if v is not None}
+        unknown = set(kwargs) - set(_OUT_OF_SCOPE)
+        if unknown:
+            raise TypeError(f'unexpected MonoRUnRoIHead arguments: {sorted(unknown)}')
+        self.train_cfg, self.test_cfg, self.debug = train_cfg, test_cfg, debug
+        if noc_head is not None:
+            self.noc_head = build_head(noc_head)
+        if projection_head is not None:
+            self.projection_head = build_head(projection_head)
+        if pose_head is not None:
+            self.pose_head = build_head(pose_head)
+
+    @property
+    def with_noc(self):
+        return hasattr(self, 'noc_head') and self.noc_head is not None
+
+    @property
+    def with_pose(self):
+        return hasattr(self, 'pose_head') and self.pose_head is not None
+
+    def init_weights(self):
+        if self.with_noc:
+            self.noc_head.init_weights()
+
+    def forward_3d(self, noc_feats, bbox_3d_rois, det_labels, latent_pred, dimensions_pred, dimensions_var,
+                   cam_intrinsic, img_shape, flip=False, distance_pred=None, cov_correction=True):
+        """monorun_roi_head.py:509-534: dense head -> decode -> analytic coords_2d -> PnP -> covariance correction.
+
+        noc_feats (N,256,14,14), bbox_3d_rois (N,5), det_labels (N,), latent_pred (N,16), dimensions_pred (N,3),
+        dimensions_var (N,3)|None, cam_intrinsic (1|N,3,3), img_shape (h, w).
+        Returns dict(ret_val, yaw_pred, t_vec_pred, pose_cov_pred, pose_cov_calib, coords_3d, proj_logstd).
+        """
+        noc_pred, noc_var, proj_logstd, _ = self.noc_head(noc_feats, latent_pred, None, det_labels, flip=flip)
+        coords_3d, coords_3d_var = self.noc_head.coord_coder.decode(           # :513-515
+            noc_pred, noc_var, dimensions_pred, dimensions_var, flip)
+        proj_logstd = self.projection_head.proj_error_coder.decode_logstd(     # :516-519
+            proj_logstd, coords_3d_var, distance_pred)
+        coords_2d_roi = coords_2d_from_rois(bbox_3d_rois, noc_pred.shape[-1])  # :521-523
+        img_shapes = cam_intrinsic.new_tensor(img_shape[:2])[None, ...]
+        ret_val, yaw, t_vec, cov, cov_calib = self.pose_head(                  # :525-529
+            coords_2d_roi, proj_logstd, coords_3d, cam_intrinsic, img_shapes)
+        if cov_correction:                                                     # :530-534
+            distance = self.projection_head.get_distance(t_vec)
+            cov_calib = self.projection_head.proj_error_coder.cov_correction(cov_calib, distance)
+        return dict(ret_val=ret_val, yaw_pred=yaw, t_vec_pred=t_vec, pose_cov_pred=cov, pose_cov_calib=cov_calib,
+                    coords_3d=coords_3d, proj_logstd=proj_logstd, coords_2d=coords_2d_roi)

@@ -1,0 +1,324 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on identical
+seeded inputs, against the committed golden vectors, and through size-independent properties at full size.
+
+Tolerances (BASELINE.json north_star): translation 1e-4 relative, rotation 1e-3 rad.  MRPNP_PREC_FP64 is held to
+1e-9 (it reproduces the fp64 oracle's decisions exactly); MRPNP_PREC_MIXED to the north_star tolerances.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from monorun_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+T_TOL, R_TOL = 1e-4, 1e-3
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def uvr(op):
+    return torch.tensor([[op['u_range'][0, 0], op['u_range'][0, 1], op['v_range'][0, 0], op['v_range'][0, 1]]],
+                        device='cuda')
+
+
+def clips(op):
+    return np.array([[0.5, op['u_range'][0, 0], op['u_range'][0, 1], op['v_range'][0, 0], op['v_range'][0, 1]]])
+
+
+def host_mask(od, w, full):
+    m = od.istd_inlier_masks(w[..., [0, 2]] if full else w, 0.6)
+    m[m.sum(1) <= 4] = True
+    return m
+
+
+def pose_errors(pose, ref):
+    t_err = np.linalg.norm(pose[:, 1:4] - ref[:, 1:4], axis=1) / np.linalg.norm(ref[:, 1:4], axis=1)
+    d = pose[:, 0] - ref[:, 0]
+    return t_err, np.abs((d + np.pi) % (2 * np.pi) - np.pi)
+
+
+def case(n, cfg, weights, mode):
+    b = synth.make_batch(n, config=cfg, weights=weights, mode=mode)
+    op = synth.to_op_level(b)
+    full = weights == 'full'
+    return b, op, full, (op['w_full'] if full else op['coords_2d_istd'])
+
+
+CASES = [(256, 1, 'identity', 'S0'), (1024, 2, 'diag', 'S0'), (1024, 2, 'diag', 'S1'), (1024, 3, 'full', 'S0'),
+         (512, 3, 'full', 'S1')]
+
+
+@pytest.mark.parametrize('n,cfg,weights,mode', CASES)
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+def test_lm_parity_with_oracle(cuda_lib, oracle, n, cfg, weights, mode, precision):
+    """Same inputs, same init, same inlier mask -> same pose, cost and number of evaluations."""
+    from monorun_b200 import pnp
+    b, op, full, w = case(n, cfg, weights, mode)
+    mask = host_mask(oracle, w, full)
+    ref = oracle.lm_batch(op['coords_2d'], op['coords_3d'], w, op['cam_mats'], b['init_pose'], clips(op), mask,
+                          full_w=full, threads=0)
+    res, inl, r64 = pnp.solve_batched(
+        dev(op['coords_3d']), dev(op['coords_2d']), dev(w), dev(op['cam_mats']), uvr(op), init_pose=dev(b['init_pose']),
+        inlier_mask=dev(mask), layout='interleaved', weight_mode='full' if full else 'istd', precision=precision,
+        return_fp64=True)
+    r64, res = r64.cpu().numpy(), res.cpu().numpy()
+    assert ref['val'].all() and (res[:, 20] == 1).all()
+    assert np.array_equal(inl.cpu().numpy(), mask)
+    t_err, r_err = pose_errors(r64, ref['pose'])
+    same_evals = (r64[:, 6].astype(int) == ref['stats'][:, 1]).mean()
+    if precision == 'fp64':
+        assert t_err.max() < 1e-9 and r_err.max() < 1e-9 and same_evals == 1.0
+        np.testing.assert_allclose(r64[:, 4], ref['cost'], rtol=1e-11)
+    else:
+        assert t_err.max() < T_TOL and r_err.max() < R_TOL, (t_err.max(), r_err.max())
+        assert same_evals > 0.99
+        np.testing.assert_allclose(r64[:, 4], ref['cost'], rtol=1e-6)
+    # fp32 result row agrees with the fp64 side channel
+    np.testing.assert_allclose(res[:, :4], r64[:, :4].astype(np.float32), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('cfg', [1, 2, 3])
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+def test_golden_vectors(cuda_lib, cfg, precision):
+    """Committed inputs + oracle outputs (tests/golden/make_golden.py); head-level planar tensors, log-std in."""
+    from monorun_b200 import pnp
+    g = np.load(os.path.join(GOLD, f'lm_cfg{cfg}.npz'))
+    full = 'w_full' in g.files
+    ih, iw = g['img_shape']
+    rng = torch.tensor([[-200., iw + 200., -200., ih + 200.]], device='cuda')
+    res, inl, r64 = pnp.solve_batched(
+        dev(g['coords_3d']), dev(g['coords_2d']), dev(g['w_full'] if full else g['logstd']), dev(g['cam_mat'][None]),
+        rng, init_pose=dev(g['init_pose']), inlier_mask=dev(g['inlier_mask']), layout='planar',
+        weight_mode='full' if full else 'logstd', precision=precision, return_fp64=True,
+        cov_mode='ceres' if full else 'pipeline')
+    r64, res = r64.cpu().numpy(), res.cpu().numpy()
+    t_err, r_err = pose_errors(r64, g['oracle_pose'])
+    # log-std -> istd happens on the device here (expf vs numpy exp differ by an ulp), hence not 1e-9
+    assert t_err.max() < (1e-6 if precision == 'fp64' else T_TOL) and r_err.max() < (1e-6 if precision == 'fp64' else R_TOL)
+    assert (r64[:, 6].astype(int) == g['oracle_stats'][:, 1]).all()
+    cov = res[:, 4:20].reshape(-1, 4, 4)
+    ref_cov = g['oracle_cov_ceres'] if full else g['oracle_cov_pipeline']
+    rel = np.linalg.norm(cov - ref_cov, axis=(1, 2)) / np.linalg.norm(ref_cov, axis=(1, 2))
+    assert rel.max() < 1e-3, rel.max()
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+def test_covariance_masks_against_reference_torch_outputs(cuda_lib, precision):
+    """hessian_ref.npz: H from the reference's own hessian.py at fixed poses with z-/uv-clipped points and
+    outliers.  The kernel evaluates at init_pose without stepping (max_iterations < 0)."""
+    from monorun_b200 import pnp
+    g = np.load(os.path.join(GOLD, 'hessian_ref.npz'))
+    rng = torch.from_numpy(np.concatenate([g['u_range'], g['v_range']], 1)).cuda()
+    res, _, _ = pnp.solve_batched(
+        dev(g['coords_3d']), dev(g['coords_2d']), dev(g['coords_2d_istd']), dev(g['cam_mats']), rng,
+        init_pose=dev(g['pose']), inlier_mask=dev(g['inlier_mask']), layout='interleaved', weight_mode='istd',
+        precision=precision, max_iterations=-1, cov_mode='pipeline')
+    res = res.cpu().numpy()
+    cov = res[:, 4:20].reshape(-1, 4, 4).astype(np.float64)
+    ref = np.linalg.inv(g['H_ref64'])
+    rel = np.linalg.norm(cov - ref, axis=(1, 2)) / np.linalg.norm(ref, axis=(1, 2))
+    assert (res[:, 20] == 1).all() and (res[:, 21] == 0).all()
+    assert rel.max() < (1e-5 if precision == 'fp64' else 1e-3), rel
+
+
+def test_device_inlier_test_matches_numpy(cuda_lib, oracle):
+    """pnp_uncert_cpu.py:164-168 on the device.  numpy's mean is a sequential fp32 sum, the kernel's a tree sum:
+    points whose istd sits within rounding of 0.6*mean may flip; nothing else may."""
+    from monorun_b200 import pnp
+    b, op, full, w = case(2048, 2, 'diag', 'S0')
+    mask = host_mask(oracle, w, full)
+    _, inl, _ = pnp.solve_batched(dev(op['coords_3d']), dev(op['coords_2d']), dev(w), dev(op['cam_mats']), uvr(op),
+                                  init_pose=dev(b['init_pose']), layout='interleaved', weight_mode='istd')
+    diff = inl.cpu().numpy() != mask
+    assert diff.sum() <= 8, diff.sum()
+    if diff.any():
+        thr = 0.6 * w.mean(1, keepdims=True)
+        margin = np.abs(w - thr).min(2) / thr.max(2)
+        assert margin[diff].max() < 1e-5
+
+
+def test_too_few_inliers_falls_back_to_all_points(cuda_lib, oracle):
+    from monorun_b200 import pnp
+    b, op, full, w = case(8, 2, 'diag', 'S0')
+    w = w.copy()
+    w[:4] = 1e-3
+    w[:4, :3] = 10.0  # 3 strong points: <= 4 inliers -> every point is an inlier (pnp_uncert_cpu.py:23-32)
+    mask = host_mask(oracle, w, False)
+    assert mask[:4].all() and not mask[4:].all()
+    ref = oracle.lm_batch(op['coords_2d'], op['coords_3d'], w, op['cam_mats'], b['init_pose'], clips(op), mask)
+    _, inl, r64 = pnp.solve_batched(dev(op['coords_3d']), dev(op['coords_2d']), dev(w), dev(op['cam_mats']), uvr(op),
+                                    init_pose=dev(b['init_pose']), layout='interleaved', weight_mode='istd',
+                                    precision='fp64', return_fp64=True)
+    assert np.array_equal(inl.cpu().numpy(), mask)
+    t_err, r_err = pose_errors(r64.cpu().numpy(), ref['pose'])
+    assert t_err.max() < 1e-9 and r_err.max() < 1e-9
+
+
+@pytest.mark.parametrize('roi,n', [(14, 37), (7, 5), (28, 1), (32, 3)])
+def test_ragged_sizes_and_unaligned_shapes(cuda_lib, oracle, roi, n):
+    """P = 196 / 49 (not a multiple of 4 -> plain-load path) / 784 / 1024 (maximum), odd batch sizes."""
+    from monorun_b200 import pnp, _native
+    b = synth.make_batch(n, config=2, roi=roi)
+    op = synth.to_op_level(b)
+    w = op['coords_2d_istd']
+    mask = host_mask(oracle, w, False)
+    ref = oracle.lm_batch(op['coords_2d'], op['coords_3d'], w, op['cam_mats'], b['init_pose'], clips(op), mask)
+    for layout in ('interleaved', 'planar'):
+        if layout == 'planar':
+            args = (dev(b['coords_3d']), dev(b['coords_2d']),
+                    dev(np.ascontiguousarray(w.transpose(0, 2, 1).reshape(n, 2, roi, roi))))
+        else:
+            args = (dev(op['coords_3d']), dev(op['coords_2d']), dev(w))
+        _, inl, r64 = pnp.solve_batched(*args, dev(op['cam_mats']), uvr(op), init_pose=dev(b['init_pose']),
+                                        inlier_mask=dev(mask), layout=layout, weight_mode='istd', precision='fp64',
+                                        return_fp64=True)
+        t_err, r_err = pose_errors(r64.cpu().numpy(), ref['pose'])
+        assert t_err.max() < 1e-9 and r_err.max() < 1e-9
+    info = _native.ffi.new('int32_t[4]')
+    p = pnp.make_params(n, roi * roi)
+    _native.check(_native.lib().mrpnp_kernel_info(pnp.get_ctx('cuda').ptr, p, info))
+    assert info[0] >= 1 and info[2] <= 232448
+
+
+def test_empty_batch_and_bad_arguments(cuda_lib):
+    from monorun_b200 import pnp, _native
+    e = torch.zeros((0, 3, 28, 28), device='cuda')
+    res, inl, _ = pnp.solve_batched(e, e[:, :2], e[:, :2], torch.eye(3, device='cuda')[None],
+                                    torch.zeros(1, 4, device='cuda'), init_pose=torch.zeros(0, 4, device='cuda'))
+    assert res.shape == (0, 24) and inl.shape == (0, 784)
+    p = pnp.make_params(4, 2000)
+    rc = _native.lib().mrpnp_solve(pnp.get_ctx('cuda').ptr, p, *([_native.ffi.NULL] * 10), _native.ffi.NULL)
+    assert rc == _native.CONST['MRPNP_ERR_ARG'] and 'n_pts' in _native.last_error()
+
+
+def test_non_finite_object_is_flagged_and_isolated(cuda_lib, oracle):
+    from monorun_b200 import pnp
+    b, op, full, w = case(16, 2, 'diag', 'S0')
+    c3 = op['coords_3d'].copy()
+    c3[3, 10, 0] = np.nan
+    mask = host_mask(oracle, w, False)
+    ref = oracle.lm_batch(op['coords_2d'], c3, w, op['cam_mats'], b['init_pose'], clips(op), mask)
+    res, _, r64 = pnp.solve_batched(dev(c3), dev(op['coords_2d']), dev(w), dev(op['cam_mats']), uvr(op),
+                                    init_pose=dev(b['init_pose']), inlier_mask=dev(mask), layout='interleaved',
+                                    weight_mode='istd', precision='fp64', return_fp64=True)
+    res, r64 = res.cpu().numpy(), r64.cpu().numpy()
+    assert not ref['val'][3] and res[3, 20] == 0          # Summary::IsSolutionUsable() == false
+    np.testing.assert_array_equal(res[3, :4], b['init_pose'][3])  # parameters stay at the initial pose
+    ok = np.arange(16) != 3
+    t_err, r_err = pose_errors(r64[ok], ref['pose'][ok])
+    assert (res[ok, 20] == 1).all() and t_err.max() < 1e-9
+
+
+def test_op_level_dropin_signature(cuda_lib, oracle):
+    """PnPUncert.forward: argument order, shapes, dtypes and device of the 5-tuple (pnp_uncert.py:125-142)."""
+    import monorun_b200
+    b, op, full, w = case(64, 2, 'diag', 'S1')
+    m = monorun_b200.build_pnp(dict(type='PnPUncert', z_min=0.5, epnp_istd_thres=0.6, inlier_opt_only=True,
+                                    forward_exact_hessian=False)).cuda()
+    ret_val, r_vec, t_vec, pose_cov, inlier_mask = m(
+        dev(op['coords_2d']), dev(w), dev(op['coords_3d']), dev(op['cam_mats']), dev(op['u_range']), dev(op['v_range']),
+        None)
+    assert ret_val.dtype == torch.bool and ret_val.shape == (64,) and r_vec.shape == (64, 1) and t_vec.shape == (64, 3)
+    assert pose_cov.shape == (64, 4, 4) and inlier_mask.shape == (64, 784) and inlier_mask.dtype == torch.bool
+    assert all(t.is_cuda for t in (ret_val, r_vec, t_vec, pose_cov, inlier_mask)) and ret_val.all()
+    # the on-device linear initialiser lands in the same basin as the reference's OpenCV EPnP initialisation
+    ref = oracle.pnp_uncert_ref(op['coords_2d'], w, op['coords_3d'], op['cam_mats'], op['u_range'], op['v_range'],
+                                0.5, 0.6, None, True)
+    pose = torch.cat([r_vec, t_vec], 1).cpu().numpy()
+    t_err, r_err = pose_errors(pose, np.concatenate([ref[1], ref[2]], 1))
+    assert np.median(t_err) < 2e-5 and t_err.max() < 5e-4 and r_err.max() < 2e-3  # both within Ceres' own exit slack
+    rel = (np.linalg.norm(pose_cov.cpu().numpy() - ref[3], axis=(1, 2)) / np.linalg.norm(ref[3], axis=(1, 2)))
+    assert np.median(rel) < 1e-3
+
+
+def test_head_level_matches_op_level(cuda_lib):
+    """UncertPropPnPOptimizer.forward (NCHW + log-std, fused in-kernel) == the reference's permute + exp + op call."""
+    import monorun_b200
+    b = synth.make_batch(128, config=2, mode='S1')
+    head = monorun_b200.build_head(dict(type='UncertPropPnPOptimizer', pnp=dict(type='PnPUncert', precision='fp64'))).cuda()
+    with torch.no_grad():
+        head.cov_calib_logscale.copy_(torch.tensor([0.1, -0.2, 0.3, 0.0]))
+    c2, ls, c3 = dev(b['coords_2d']), dev(b['logstd']), dev(b['coords_3d'])
+    cam, shp, init = dev(b['cam_mat'][None]), dev(b['img_shape'][None]), dev(b['init_pose'])
+    ret, yaw, t, cov, cov_cal = head(c2, ls, c3, cam, shp, init_pose=init)
+    assert ret.all() and cov_cal.shape == (128, 4, 4)
+    s = torch.exp(head.cov_calib_logscale)
+    assert torch.allclose(cov_cal, (s * s[:, None]) * cov)
+    # reference formulation (uncert_prop_pnp_optimizer.py:71-95) through the op-level entry
+    istd = torch.exp(-ls) / 10
+    n = 128
+    u_range = torch.tensor([[-200., b['img_shape'][1] + 200.]], device='cuda')
+    v_range = torch.tensor([[-200., b['img_shape'][0] + 200.]], device='cuda')
+    ret2, yaw2, t2, cov2, _ = monorun_b200.pnp_uncert(
+        c2.permute(0, 2, 3, 1).reshape(n, 784, 2), istd.permute(0, 2, 3, 1).reshape(n, 784, 2),
+        c3.permute(0, 2, 3, 1).reshape(n, 784, 3), cam, u_range, v_range, z_min=0.5, epnp_istd_thres=0.6,
+        inlier_opt_only=True, init_pose=init, precision='fp64')
+    assert torch.allclose(t, t2, rtol=2e-6) and torch.allclose(yaw, yaw2, atol=2e-6) and torch.allclose(cov, cov2, rtol=1e-3)
+
+
+def test_roi_head_hot_sequence_runs(cuda_lib):
+    """MonoRUnRoIHead.forward_3d (monorun_roi_head.py:509-534) end to end on random-init weights: shapes,
+    finiteness, and PnP-stage parity on the tensors captured at the head->PnP boundary."""
+    import monorun_b200
+    from tests.test_host import _roi_head_cfg
+    torch.manual_seed(0)
+    head = monorun_b200.build_head(_roi_head_cfg()).cuda().eval()
+    head.init_weights()
+    n = 12
+    b = synth.make_batch(n, config=3, mode='S1')
+    rois = torch.cat([torch.zeros(n, 1), torch.from_numpy(b['boxes'])], 1).cuda()
+    out = head.forward_3d(torch.randn(n, 256, 14, 14, device='cuda'), rois, dev(b['labels']),
+                          torch.randn(n, 16, device='cuda'), dev(b['dims']), torch.full((n, 3), 1e-3, device='cuda'),
+                          dev(b['cam_mat'][None]), (375, 1242))
+    assert out['coords_3d'].shape == (n, 3, 28, 28) and out['coords_2d'].shape == (n, 2, 28, 28)
+    assert out['yaw_pred'].shape == (n, 1) and out['t_vec_pred'].shape == (n, 3) and out['pose_cov_calib'].shape == (n, 4, 4)
+    assert torch.isfinite(out['t_vec_pred']).all()
+
+
+def test_full_size_properties(cuda_lib):
+    """BASELINE.json size (8192 x 784), properties that need no oracle: noise-free ground-truth recovery,
+    permutation equivariance (bitwise), idempotence at the solution, host-buffer path == device path."""
+    from monorun_b200 import pnp
+    n = 8192
+    rng = np.random.default_rng(99)
+    labels, dims, yaw, t = synth.sample_objects(rng, n, classes=(0, 1, 2))
+    pts = synth._points_in_box(rng, dims, 784)
+    uv, _ = synth.project(synth.KITTI_K, yaw, t, pts)
+    chw = lambda a: np.ascontiguousarray(a.transpose(0, 2, 1).reshape(n, a.shape[2], 28, 28), np.float32)
+    c3, c2 = dev(chw(pts)), dev(chw(uv))
+    logstd = torch.full((n, 2, 28, 28), float(-np.log(10.0)), device='cuda')
+    cam = dev(synth.KITTI_K.astype(np.float32)[None])
+    rng_t = torch.tensor([[-200., 1442., -200., 575.]], device='cuda')
+    init = np.concatenate([(yaw + rng.normal(0, 0.05, n))[:, None], t * (1 + rng.normal(0, 0.02, (n, 3)))], 1).astype(np.float32)
+    res, _, _ = pnp.solve_batched(c3, c2, logstd, cam, rng_t, init_pose=dev(init), precision='mixed')
+    r = res.cpu().numpy()
+    assert (r[:, 20] == 1).all()
+    gt = np.concatenate([yaw[:, None], t], 1)
+    t_err, r_err = pose_errors(r.astype(np.float64), gt)
+    assert t_err.max() < 2e-5 and r_err.max() < 2e-4, (t_err.max(), r_err.max())   # fp32 inputs limit exactness
+    # permutation equivariance, bitwise (objects are independent; dynamic scheduling must not matter)
+    perm = torch.randperm(n, device='cuda')
+    res_p, _, _ = pnp.solve_batched(c3[perm], c2[perm], logstd[perm], cam, rng_t, init_pose=dev(init)[perm], precision='mixed')
+    assert torch.equal(res_p, res[perm])
+    # idempotence: restarting at the solution terminates after one candidate, pose essentially unchanged
+    res2, _, r64 = pnp.solve_batched(c3, c2, logstd, cam, rng_t, init_pose=res[:, :4].contiguous(), precision='mixed',
+                                     return_fp64=True)
+    t2, _ = pose_errors(res2.cpu().numpy().astype(np.float64), r.astype(np.float64))
+    assert t2.max() < 1e-5 and (r64[:, 6] <= 3).all()
+    # host-buffer entry (mrpnp_solve_host) returns the same rows as the device entry
+    host = pnp.solve_host(c3.cpu().pin_memory(), c2.cpu().pin_memory(), logstd.cpu().pin_memory(), cam.cpu(),
+                          rng_t.cpu(), torch.from_numpy(init), precision='mixed')
+    assert torch.equal(host, res.cpu())
+    before = pnp.launch_count()
+    pnp.solve_batched(c3[:64], c2[:64], logstd[:64], cam, rng_t, init_pose=dev(init)[:64])
+    assert pnp.launch_count() == before + 1
+
+
+def test_smoke_entry(cuda_lib):
+    import __graft_entry__ as g
+    g.smoke()
