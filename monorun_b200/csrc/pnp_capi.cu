@@ -7,6 +7,7 @@
 
 #include "monorun_pnp.h"
 #include "pnp_kernel.cuh"
+#include "pnp_kernel_pair.cuh"
 
 namespace {
 
@@ -48,7 +49,7 @@ namespace {
 using mrpnp::KParams;
 
 struct LaunchPlan {
-    int warps, ctas, smem, use_tma;
+    int warps, groups, ctas, smem, use_tma, slot_floats;
 };
 
 int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, const void* c3d, const void* c2d, const void* wgt,
@@ -57,15 +58,19 @@ int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, const void* c3d, co
     const size_t slot_floats = (size_t)(5 + wc) * p->n_pts;
     size_t slot_bytes = slot_floats * sizeof(float);
     slot_bytes = (slot_bytes + 15) & ~size_t(15);
-    const size_t avail = (size_t)ctx->max_smem_optin;
-    int warps = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, avail / (slot_bytes + mrpnp::kWarpHeaderBytes));
-    if (warps < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
-    // keep every SM busy before stacking warps: at small N spread objects over CTAs
+    const bool pair = p->precision == MRPNP_PREC_MIXED;  // two specialised warps per object
+    const size_t header = pair ? mrpnp::kPairHeaderBytes : mrpnp::kWarpHeaderBytes;
+    const int max_groups = pair ? mrpnp::kMaxPairsPerCta : mrpnp::kMaxWarpsPerCta;
+    int groups = (int)std::min<size_t>(max_groups, (size_t)ctx->max_smem_optin / (slot_bytes + header));
+    if (groups < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
+    // keep every SM busy before stacking objects on one SM: at small N spread objects over CTAs
     const int per_sm = (p->n_obj + ctx->num_sms - 1) / ctx->num_sms;
-    warps = std::max(1, std::min(warps, per_sm));
-    plan->warps = warps;
-    plan->ctas = std::min(ctx->num_sms, (p->n_obj + warps - 1) / warps);
-    plan->smem = (int)(warps * (slot_bytes + mrpnp::kWarpHeaderBytes));
+    groups = std::max(1, std::min(groups, per_sm));
+    plan->warps = groups * (pair ? 2 : 1);
+    plan->groups = groups;
+    plan->ctas = std::min(ctx->num_sms, (p->n_obj + groups - 1) / groups);
+    plan->smem = (int)(groups * (slot_bytes + header));
+    plan->slot_floats = (int)(slot_bytes / sizeof(float));
     const bool aligned = (p->n_pts % 4 == 0) && (((uintptr_t)c3d | (uintptr_t)c2d | (uintptr_t)wgt) % 16 == 0);
     plan->use_tma = aligned ? 1 : 0;
     return MRPNP_OK;
@@ -96,7 +101,7 @@ cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan,
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
     } else {
-        auto k = mrpnp::pnp_lm_kernel<true, WMODE, LAYOUT>;
+        auto k = mrpnp::pnp_lm_pair_kernel<WMODE, LAYOUT>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
@@ -135,7 +140,7 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     kp.cov_mode = p->cov_mode; kp.init_mode = p->init_mode; kp.inlier_opt_only = p->inlier_opt_only;
     kp.max_iter = p->max_iterations; kp.adopt_ftol = p->adopt_candidate_on_ftol;
     kp.use_tma = plan.use_tma;
-    kp.slot_floats = (int)((plan.smem / plan.warps - mrpnp::kWarpHeaderBytes) / sizeof(float));
+    kp.slot_floats = plan.slot_floats;
     kp.z_min = p->z_min; kp.std_scale = p->std_scale; kp.istd_thres = p->istd_thres;
     cudaError_t e = dispatch(p, kp, plan, stream);
     if (e != cudaSuccess) return fail(MRPNP_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));

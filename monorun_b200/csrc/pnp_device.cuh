@@ -479,7 +479,7 @@ __device__ __forceinline__ bool chol_solve_dense(double A[N][N], const double b[
 
 // fp32 accumulation of the (well-scaled, normalised-coordinate) normal equations, fp64 solves.
 template <int WMODE, int LAYOUT>
-__device__ __noinline__ bool linear_init(const float* __restrict__ s3, const float* __restrict__ s2,
+__device__ __forceinline__ bool linear_init_impl(const float* __restrict__ s3, const float* __restrict__ s2,
                                             const float* __restrict__ sw, int P, int n, int lane,
                                             const Camera<float>& cam, float* scratch, double* x) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
@@ -558,6 +558,14 @@ __device__ __noinline__ bool linear_init(const float* __restrict__ s3, const flo
     if (!chol_solve_dense<3>(B, rh3, t)) return false;
     x[0] = yaw; x[1] = t[0]; x[2] = t[1]; x[3] = t[2];
     return (fabs(t[0]) + fabs(t[1]) + fabs(t[2])) < 1.7e308;
+}
+
+// Out-of-line wrapper used by the warp-per-object kernel (keeps its hot code small).
+template <int WMODE, int LAYOUT>
+__device__ __noinline__ bool linear_init(const float* __restrict__ s3, const float* __restrict__ s2,
+                                         const float* __restrict__ sw, int P, int n, int lane,
+                                         const Camera<float>& cam, float* scratch, double* x) {
+    return linear_init_impl<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, cam, scratch, x);
 }
 
 }  // namespace mrpnp
