@@ -58,7 +58,7 @@ int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, const void* c3d, co
     const size_t slot_floats = (size_t)(5 + wc) * p->n_pts;
     size_t slot_bytes = slot_floats * sizeof(float);
     slot_bytes = (slot_bytes + 15) & ~size_t(15);
-    const bool pair = p->precision == MRPNP_PREC_MIXED;  // two specialised warps per object
+    const bool pair = false;  // (the two-warps-per-object kernel of pnp_kernel_pair.cuh measured no faster)
     const size_t header = pair ? mrpnp::kPairHeaderBytes : mrpnp::kWarpHeaderBytes;
     const int max_groups = pair ? mrpnp::kMaxPairsPerCta : mrpnp::kMaxWarpsPerCta;
     int groups = (int)std::min<size_t>(max_groups, (size_t)ctx->max_smem_optin / (slot_bytes + header));
@@ -101,7 +101,7 @@ cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan,
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
     } else {
-        auto k = mrpnp::pnp_lm_pair_kernel<WMODE, LAYOUT>;
+        auto k = mrpnp::pnp_lm_kernel<true, WMODE, LAYOUT>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);

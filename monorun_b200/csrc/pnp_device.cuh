@@ -22,9 +22,15 @@ namespace mrpnp {
 
 constexpr int kMaxWarpsPerCta = 10;        // 10 x 21,952 B slots fill the 227 KB of one SM at P = 784
 constexpr int kMaxThreads = kMaxWarpsPerCta * 32;
-constexpr int kWarpHeaderBytes = 256;      // per warp: mbarrier (8 B) + 16-double reduction scratch at +128
+constexpr int kWarpHeaderBytes = 512;      // per warp: mbarrier (8 B) + 40-double scratch at +128 (reductions, cold-path I/O)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxRows = MRPNP_MAX_POINTS / 32;
+
+// Scratch layout used by the out-of-line (cold) routines: no pointer-to-local crosses a call, because with
+// the maximum shared-memory carve-out L1 is ~3 KB and local-memory traffic would go to L2.
+constexpr int kScrSums = 0;    // [0..15] reduction scratch / the 16 sums returned by eval_pass_fp64
+constexpr int kScrPt = 16;     // [16..19] evaluation point handed to eval_pass_fp64 / returned by linear_init
+constexpr int kScrClip = 20;   // [20] clip flag returned by eval_pass_fp64
 
 struct KParams {
     const float* c3d;
@@ -166,14 +172,32 @@ struct Camera {
 // clipsem 0: Ceres-Jet semantics (pnp_uncert_cpu.cpp:36-42): z clip drops only d/dz', u/v clamp drops that row.
 // clipsem 1: jacobian.py:52-59 semantics: a z-clipped point loses both rows (used for the pipeline covariance).
 // use_bits : skip points whose bit in `bits` (bit k <-> point 32k+lane) is 0 (outliers when not compacted).
-// *clip_out returns whether any point of the warp hit a clip.  Deliberately not inlined: it is the main
+// Evaluation point in: scratch[kScrPt..]; out: 16 sums in scratch[kScrSums..], clip flag in scratch[kScrClip].
+// Deliberately not inlined: it is the main
 // pass only in MRPNP_PREC_FP64 mode and the cold fallback of the mixed pass, and keeping one copy keeps the
 // hot code of the kernel inside the instruction cache.
+template <typename T>
+__device__ __forceinline__ Camera<T> load_camera(const KParams& kp, int obj) {
+    Camera<T> c;
+    const float* K = kp.cam + (size_t)obj * kp.cam_stride;
+    const float* R = kp.range + (size_t)obj * kp.range_stride;
+    c.fx = (T)__ldg(K + 0); c.fy = (T)__ldg(K + 4);  // pnp_uncert_cpu.cpp:265
+    c.cx = (T)__ldg(K + 2); c.cy = (T)__ldg(K + 5);
+    c.z_min = (T)kp.z_min;
+    c.u_min = (T)__ldg(R + 0); c.u_max = (T)__ldg(R + 1);
+    c.v_min = (T)__ldg(R + 2); c.v_max = (T)__ldg(R + 3);
+    return c;
+}
+
 template <int WMODE, int LAYOUT>
-__device__ __noinline__ void eval_pass_fp64(const float* __restrict__ s3, const float* __restrict__ s2,
-                                            const float* __restrict__ sw, int P, int n, int lane, uint32_t bits,
-                                            int clipsem, bool use_bits, const double* x, const Camera<double>& cam,
-                                            double* acc_out, double* scratch, bool* clip_out) {
+__device__ __noinline__ void eval_pass_fp64(const KParams& kp, int obj, const float* __restrict__ slot, int n, int lane,
+                                            uint32_t bits, int clipsem, bool use_bits, double* scratch) {
+    const int P = kp.n_pts;
+    const float* __restrict__ s3 = slot;
+    const float* __restrict__ s2 = slot + 3 * P;
+    const float* __restrict__ sw = slot + 5 * P;
+    const Camera<double> cam = load_camera<double>(kp, obj);
+    const double x[4] = {scratch[kScrPt], scratch[kScrPt + 1], scratch[kScrPt + 2], scratch[kScrPt + 3]};
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     double sn, cs;
     sincos(x[0], &sn, &cs);
@@ -258,10 +282,10 @@ __device__ __noinline__ void eval_pass_fp64(const float* __restrict__ s3, const 
             acc[14] = fma(a3, a3, fma(b3, b3, acc[14]));
         }
     }
-    *clip_out = __any_sync(kFull, any);
-    warp_allreduce16<double>(acc, scratch, lane);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc_out[i] = acc[i];
+    any = __any_sync(kFull, any);
+    warp_allreduce16<double>(acc, scratch + kScrSums, lane);  // leaves the 16 totals in scratch[0..15]
+    if (lane == 0) scratch[kScrClip] = any ? 1.0 : 0.0;
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------ fused pass, mixed precision (MRPNP_PREC_MIXED)
@@ -280,6 +304,7 @@ __device__ __forceinline__ void eval_pass_mixed(const float* __restrict__ s3, co
                                                 const Camera<float>& camf, double acc[16], double* scratch,
                                                 bool& flagged_out) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
+    constexpr int R = 2;  // rows carried through the dependent chains together (ILP; one row alone issues ~1/8 cycles)
     double sn, cs;
     sincos(x[0], &sn, &cs);
     const double tx = x[1], ty = x[2], tz = x[3];
@@ -287,83 +312,114 @@ __device__ __forceinline__ void eval_pass_mixed(const float* __restrict__ s3, co
     // clip detection on the fp32 projection with a safety margin far above its rounding error (~1e-4 px)
     const float zlo = camf.z_min * 1.001f + 1e-3f;
     const float ulo = camf.u_min + 0.05f, uhi = camf.u_max - 0.05f, vlo = camf.v_min + 0.05f, vhi = camf.v_max - 0.05f;
-    double cost2 = 0.0;
+    double cost[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) cost[r] = 0.0;
     float a[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = 0.f;
-    bool flagged = false;
+    float margin = 1e30f;  // min over points of the distance to the nearest clip bound (negative = flagged)
     const int rows = (n + 31) >> 5;
-#pragma unroll 2
-    for (int k = 0; k < rows; ++k) {
-        const int pr = k * 32 + lane;
-        const bool valid = pr < n;
-        const int p = valid ? pr : n - 1;
-        const float Xf = s3[sidx<LAYOUT, 3>(p, 0, P)], Yf = s3[sidx<LAYOUT, 3>(p, 1, P)], Zf = s3[sidx<LAYOUT, 3>(p, 2, P)];
-        const float uf = s2[sidx<LAYOUT, 2>(p, 0, P)], vf = s2[sidx<LAYOUT, 2>(p, 1, P)];
-        float w0 = sw[sidx<LAYOUT, WC>(p, 0, P)], w1 = sw[sidx<LAYOUT, WC>(p, 1, P)];
-        float w2 = (WMODE == MRPNP_W_FULL) ? sw[sidx<LAYOUT, WC>(p, WC - 1, P)] : 0.f;
-        if (!valid) { w0 = 0.f; w1 = 0.f; w2 = 0.f; }  // padding lanes contribute nothing
+    for (int k0 = 0; k0 < rows; k0 += R) {
+        float Xf[R], Yf[R], Zf[R], uf[R], vf[R], w0[R], w1[R], w2[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int pr = (k0 + r) * 32 + lane;
+            const bool valid = pr < n;
+            const int p = valid ? pr : n - 1;
+            Xf[r] = s3[sidx<LAYOUT, 3>(p, 0, P)]; Yf[r] = s3[sidx<LAYOUT, 3>(p, 1, P)]; Zf[r] = s3[sidx<LAYOUT, 3>(p, 2, P)];
+            uf[r] = s2[sidx<LAYOUT, 2>(p, 0, P)]; vf[r] = s2[sidx<LAYOUT, 2>(p, 1, P)];
+            w0[r] = sw[sidx<LAYOUT, WC>(p, 0, P)]; w1[r] = sw[sidx<LAYOUT, WC>(p, 1, P)];
+            w2[r] = (WMODE == MRPNP_W_FULL) ? sw[sidx<LAYOUT, WC>(p, WC - 1, P)] : 0.f;
+            if (!valid) { w0[r] = 0.f; w1[r] = 0.f; w2[r] = 0.f; }  // padding lanes / rows contribute nothing
+        }
+        // ---- fp64 residual chain ----
+        double xc[R], yc[R], zc[R], iz[R], du[R], dv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double X = (double)Xf[r], Y = (double)Yf[r], Z = (double)Zf[r];
+            xc[r] = fma(cs, X, fma(sn, Z, tx));
+            zc[r] = fma(cs, Z, fma(-sn, X, tz));
+            yc[r] = Y + ty;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) iz[r] = fast_rcp(zc[r]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            du[r] = fma(cam.fx, xc[r] * iz[r], cam.cx) - (double)uf[r];
+            dv[r] = fma(cam.fy, yc[r] * iz[r], cam.cy) - (double)vf[r];
+        }
         // ---- fp32 projection: Jacobian + clip detection ----
-        const float qxf = fmaf(csf, Xf, snf * Zf), qzf = fmaf(csf, Zf, -snf * Xf);
-        const float xcf = qxf + txf, ycf = Yf + tyf, zcf = qzf + tzf;
-        const float izf = fast_rcp(zcf);
-        const float xnf = xcf * izf, ynf = ycf * izf;
-        const float puf = fmaf(camf.fx, xnf, camf.cx), pvf = fmaf(camf.fy, ynf, camf.cy);
-        flagged = flagged || !(zcf >= zlo) || !(puf >= ulo) || !(puf <= uhi) || !(pvf >= vlo) || !(pvf <= vhi);
-        const float au = camf.fx * izf, av = camf.fy * izf;
-        const float bu = -au * xnf, bv = -av * ynf;
-        const float ju0 = fmaf(au, qzf, -bu * qxf), jv0 = -bv * qxf;
-        // ---- fp64 residual chain (no clip assumed; the pass is redone exactly if any point was flagged) ----
-        const double X = (double)Xf, Y = (double)Yf, Z = (double)Zf;
-        const double qx = fma(cs, X, sn * Z);
-        const double qz = fma(cs, Z, -sn * X);
-        const double xc = qx + tx, yc = Y + ty, zc = qz + tz;
-        const double iz = fast_rcp(zc);
-        const double du = fma(cam.fx, xc * iz, cam.cx) - (double)uf;
-        const double dv = fma(cam.fy, yc * iz, cam.cy) - (double)vf;
-        if (WMODE != MRPNP_W_FULL) {
-            const double ru = (double)w0 * du, rv = (double)w1 * dv;
-            cost2 = fma(ru, ru, fma(rv, rv, cost2));
-            const float ruf = w0 * (puf - uf), rvf = w1 * (pvf - vf);
-            const float a0 = w0 * ju0, a1 = w0 * au, a3 = w0 * bu;
-            const float b0 = w1 * jv0, b2 = w1 * av, b3 = w1 * bv;
-            a[0] = fmaf(a0, ruf, fmaf(b0, rvf, a[0]));
-            a[1] = fmaf(a1, ruf, a[1]);
-            a[2] = fmaf(b2, rvf, a[2]);
-            a[3] = fmaf(a3, ruf, fmaf(b3, rvf, a[3]));
-            a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
-            a[5] = fmaf(a0, a1, a[5]);
-            a[6] = fmaf(b0, b2, a[6]);
-            a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
-            a[8] = fmaf(a1, a1, a[8]);
-            a[10] = fmaf(a1, a3, a[10]);
-            a[11] = fmaf(b2, b2, a[11]);
-            a[12] = fmaf(b2, b3, a[12]);
-            a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
-        } else {
-            const double r0 = fma((double)w0, du, (double)w1 * dv), r1 = fma((double)w1, du, (double)w2 * dv);
-            cost2 = fma(r0, r0, fma(r1, r1, cost2));
-            const float duf = puf - uf, dvf = pvf - vf;
-            const float r0f = fmaf(w0, duf, w1 * dvf), r1f = fmaf(w1, duf, w2 * dvf);
-            const float a0 = fmaf(w0, ju0, w1 * jv0), a1 = w0 * au, a2 = w1 * av, a3 = fmaf(w0, bu, w1 * bv);
-            const float b0 = fmaf(w1, ju0, w2 * jv0), b1 = w1 * au, b2 = w2 * av, b3 = fmaf(w1, bu, w2 * bv);
-            a[0] = fmaf(a0, r0f, fmaf(b0, r1f, a[0]));
-            a[1] = fmaf(a1, r0f, fmaf(b1, r1f, a[1]));
-            a[2] = fmaf(a2, r0f, fmaf(b2, r1f, a[2]));
-            a[3] = fmaf(a3, r0f, fmaf(b3, r1f, a[3]));
-            a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
-            a[5] = fmaf(a0, a1, fmaf(b0, b1, a[5]));
-            a[6] = fmaf(a0, a2, fmaf(b0, b2, a[6]));
-            a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
-            a[8] = fmaf(a1, a1, fmaf(b1, b1, a[8]));
-            a[9] = fmaf(a1, a2, fmaf(b1, b2, a[9]));
-            a[10] = fmaf(a1, a3, fmaf(b1, b3, a[10]));
-            a[11] = fmaf(a2, a2, fmaf(b2, b2, a[11]));
-            a[12] = fmaf(a2, a3, fmaf(b2, b3, a[12]));
-            a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
+        float qxf[R], qzf[R], izf[R], xnf[R], ynf[R], puf[R], pvf[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            qxf[r] = fmaf(csf, Xf[r], snf * Zf[r]);
+            qzf[r] = fmaf(csf, Zf[r], -snf * Xf[r]);
+            const float zcf = qzf[r] + tzf;
+            margin = fminf(margin, zcf - zlo);
+            izf[r] = fast_rcp(zcf);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            xnf[r] = (qxf[r] + txf) * izf[r];
+            ynf[r] = (Yf[r] + tyf) * izf[r];
+            puf[r] = fmaf(camf.fx, xnf[r], camf.cx);
+            pvf[r] = fmaf(camf.fy, ynf[r], camf.cy);
+            margin = fminf(margin, fminf(fminf(puf[r] - ulo, uhi - puf[r]), fminf(pvf[r] - vlo, vhi - pvf[r])));
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float au = camf.fx * izf[r], av = camf.fy * izf[r];
+            const float bu = -au * xnf[r], bv = -av * ynf[r];
+            const float ju0 = fmaf(au, qzf[r], -bu * qxf[r]), jv0 = -bv * qxf[r];
+            const float duf = puf[r] - uf[r], dvf = pvf[r] - vf[r];
+            if (WMODE != MRPNP_W_FULL) {
+                const double ru = (double)w0[r] * du[r], rv = (double)w1[r] * dv[r];
+                cost[r] = fma(ru, ru, fma(rv, rv, cost[r]));
+                const float ruf = w0[r] * duf, rvf = w1[r] * dvf;
+                const float a0 = w0[r] * ju0, a1 = w0[r] * au, a3 = w0[r] * bu;
+                const float b0 = w1[r] * jv0, b2 = w1[r] * av, b3 = w1[r] * bv;
+                a[0] = fmaf(a0, ruf, fmaf(b0, rvf, a[0]));
+                a[1] = fmaf(a1, ruf, a[1]);
+                a[2] = fmaf(b2, rvf, a[2]);
+                a[3] = fmaf(a3, ruf, fmaf(b3, rvf, a[3]));
+                a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
+                a[5] = fmaf(a0, a1, a[5]);
+                a[6] = fmaf(b0, b2, a[6]);
+                a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
+                a[8] = fmaf(a1, a1, a[8]);
+                a[10] = fmaf(a1, a3, a[10]);
+                a[11] = fmaf(b2, b2, a[11]);
+                a[12] = fmaf(b2, b3, a[12]);
+                a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
+            } else {
+                const double r0 = fma((double)w0[r], du[r], (double)w1[r] * dv[r]);
+                const double r1 = fma((double)w1[r], du[r], (double)w2[r] * dv[r]);
+                cost[r] = fma(r0, r0, fma(r1, r1, cost[r]));
+                const float r0f = fmaf(w0[r], duf, w1[r] * dvf), r1f = fmaf(w1[r], duf, w2[r] * dvf);
+                const float a0 = fmaf(w0[r], ju0, w1[r] * jv0), a1 = w0[r] * au, a2 = w1[r] * av, a3 = fmaf(w0[r], bu, w1[r] * bv);
+                const float b0 = fmaf(w1[r], ju0, w2[r] * jv0), b1 = w1[r] * au, b2 = w2[r] * av, b3 = fmaf(w1[r], bu, w2[r] * bv);
+                a[0] = fmaf(a0, r0f, fmaf(b0, r1f, a[0]));
+                a[1] = fmaf(a1, r0f, fmaf(b1, r1f, a[1]));
+                a[2] = fmaf(a2, r0f, fmaf(b2, r1f, a[2]));
+                a[3] = fmaf(a3, r0f, fmaf(b3, r1f, a[3]));
+                a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
+                a[5] = fmaf(a0, a1, fmaf(b0, b1, a[5]));
+                a[6] = fmaf(a0, a2, fmaf(b0, b2, a[6]));
+                a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
+                a[8] = fmaf(a1, a1, fmaf(b1, b1, a[8]));
+                a[9] = fmaf(a1, a2, fmaf(b1, b2, a[9]));
+                a[10] = fmaf(a1, a3, fmaf(b1, b3, a[10]));
+                a[11] = fmaf(a2, a2, fmaf(b2, b2, a[11]));
+                a[12] = fmaf(a2, a3, fmaf(b2, b3, a[12]));
+                a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
+            }
         }
     }
-    flagged_out = __any_sync(kFull, flagged);
+    flagged_out = __any_sync(kFull, !(margin >= 0.f));
+    double cost2 = cost[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) cost2 += cost[r];
     // cost: 5-step fp64 butterfly; the 14 fp32 sums: transposed reduction through the scratch
     cost2 = warp_sum(cost2);
     warp_allreduce16<float>(a, reinterpret_cast<float*>(scratch), lane);
@@ -560,12 +616,22 @@ __device__ __forceinline__ bool linear_init_impl(const float* __restrict__ s3, c
     return (fabs(t[0]) + fabs(t[1]) + fabs(t[2])) < 1.7e308;
 }
 
-// Out-of-line wrapper used by the warp-per-object kernel (keeps its hot code small).
+// Out-of-line wrapper used by the warp-per-object kernel (keeps its hot code small); pose -> scratch[kScrPt..].
 template <int WMODE, int LAYOUT>
-__device__ __noinline__ bool linear_init(const float* __restrict__ s3, const float* __restrict__ s2,
-                                         const float* __restrict__ sw, int P, int n, int lane,
-                                         const Camera<float>& cam, float* scratch, double* x) {
-    return linear_init_impl<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, cam, scratch, x);
+__device__ __noinline__ bool linear_init(const KParams& kp, int obj, const float* __restrict__ slot, int n, int lane,
+                                         double* scratch) {
+    const int P = kp.n_pts;
+    const Camera<float> cam = load_camera<float>(kp, obj);
+    double x[4];
+    const bool ok = linear_init_impl<WMODE, LAYOUT>(slot, slot + 3 * P, slot + 5 * P, P, n, lane, cam,
+                                                    reinterpret_cast<float*>(scratch), x);
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) scratch[kScrPt + i] = ok ? (double)(float)x[i] : 0.0;  // fp32 hand-over; .py:119-125
+    }
+    __syncwarp();
+    return ok;
 }
 
 }  // namespace mrpnp

@@ -152,7 +152,7 @@ __device__ __forceinline__ int mask_and_compact(const KParams& kp, int obj, floa
 }
 
 template <bool MIXED, int WMODE, int LAYOUT>
-__global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp) {
+__global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_constant__ KParams kp) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,20 +181,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
         obj = __shfl_sync(kFull, obj, 0);
         if (obj >= kp.n_obj) break;
 
+        const Camera<float> camf = load_camera<float>(kp, obj);
         Camera<double> cam;
-        Camera<float> camf;
-        {
-            const float* K = kp.cam + (size_t)obj * kp.cam_stride;
-            const float* R = kp.range + (size_t)obj * kp.range_stride;
-            camf.fx = __ldg(K + 0); camf.fy = __ldg(K + 4);  // pnp_uncert_cpu.cpp:265
-            camf.cx = __ldg(K + 2); camf.cy = __ldg(K + 5);
-            camf.z_min = kp.z_min;
-            camf.u_min = __ldg(R + 0); camf.u_max = __ldg(R + 1);
-            camf.v_min = __ldg(R + 2); camf.v_max = __ldg(R + 3);
-            cam.fx = (double)camf.fx; cam.fy = (double)camf.fy; cam.cx = (double)camf.cx; cam.cy = (double)camf.cy;
-            cam.z_min = (double)camf.z_min; cam.u_min = (double)camf.u_min; cam.u_max = (double)camf.u_max;
-            cam.v_min = (double)camf.v_min; cam.v_max = (double)camf.v_max;
-        }
+        cam.fx = camf.fx; cam.fy = camf.fy; cam.cx = camf.cx; cam.cy = camf.cy;  // only these four are used inline
 
         // ---------------- stage + istd + inlier mask + compaction ----------------
         uint32_t bits = 0u;
@@ -224,9 +213,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
 #pragma unroll
             for (int i = 0; i < 4; ++i) pt[i] = (double)__ldg(ip + i);
         } else {
-            init_ok = linear_init<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, camf, reinterpret_cast<float*>(scratch), pt);
+            init_ok = linear_init<WMODE, LAYOUT>(kp, obj, slot, n, lane, scratch);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pt[i] = init_ok ? (double)(float)pt[i] : 0.0;  // fp32 hand-over; .py:119-125
+            for (int i = 0; i < 4; ++i) pt[i] = scratch[kScrPt + i];
+            __syncwarp();
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[i] = pt[i];
@@ -244,13 +234,22 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
             // ---- the fused pass at pt ----
             double acc[16];
             bool clip_p = false;
-            if (MIXED) {
-                bool flagged;
-                eval_pass_mixed<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, pt, cam, camf, acc, scratch, flagged);
-                if (flagged)  // a point near a clip bound: redo the pass with exact fp64 clip semantics
-                    eval_pass_fp64<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, bits, 0, false, pt, cam, acc, scratch, &clip_p);
-            } else {
-                eval_pass_fp64<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, bits, 0, false, pt, cam, acc, scratch, &clip_p);
+            bool exact = !MIXED;
+            if (MIXED) eval_pass_mixed<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, pt, cam, camf, acc, scratch, exact);
+            if (exact) {  // MRPNP_PREC_FP64, or a point near a clip bound in the mixed pass: exact fp64 clip semantics
+                __syncwarp();
+                if (lane < 4) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v = (lane == i) ? pt[i] : v;
+                    scratch[kScrPt + lane] = v;
+                }
+                __syncwarp();
+                eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 0, false, scratch);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = scratch[kScrSums + i];
+                clip_p = scratch[kScrClip] != 0.0;
+                __syncwarp();
             }
             ++cost_evals;
             const bool cfinite = finite_value(acc[0]);
@@ -384,11 +383,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const KParams kp
             const bool any_clip = __any_sync(kFull, clip_x);
             const bool need_pass = kp.cov_mode == MRPNP_COV_PIPELINE && (any_clip || (!compacted && n_inliers < P));
             if (need_pass) {
-                bool c2;
-                double acc[16];
-                eval_pass_fp64<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, bits, 1, !compacted, x, cam, acc, scratch, &c2);
+                __syncwarp();
+                if (lane < 4) {
+                    double v = 0.0;
 #pragma unroll
-                for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
+                    for (int i = 0; i < 4; ++i) v = (lane == i) ? x[i] : v;
+                    scratch[kScrPt + lane] = v;
+                }
+                __syncwarp();
+                eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 1, !compacted, scratch);
+#pragma unroll
+                for (int i = 0; i < 10; ++i) H[i] = scratch[kScrSums + 5 + i];
+                __syncwarp();
             }
             if (!spd_inverse4(H, cov)) {  // pnp_uncert.py:79-85 fallback: H := I, object invalid
 #pragma unroll

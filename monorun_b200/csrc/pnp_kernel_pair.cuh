@@ -53,18 +53,6 @@ __device__ __forceinline__ void pair_sync(int barid) {
     asm volatile("bar.sync %0, 64;" ::"r"(barid) : "memory");
 }
 
-__device__ __forceinline__ Camera<float> load_camera(const KParams& kp, int obj) {
-    Camera<float> c;
-    const float* K = kp.cam + (size_t)obj * kp.cam_stride;
-    const float* R = kp.range + (size_t)obj * kp.range_stride;
-    c.fx = __ldg(K + 0); c.fy = __ldg(K + 4);  // pnp_uncert_cpu.cpp:265
-    c.cx = __ldg(K + 2); c.cy = __ldg(K + 5);
-    c.z_min = kp.z_min;
-    c.u_min = __ldg(R + 0); c.u_max = __ldg(R + 1);
-    c.v_min = __ldg(R + 2); c.v_max = __ldg(R + 3);
-    return c;
-}
-
 // ------------------------------------------------------------------ cold paths of warp A (not inlined)
 // Exact fp64 pass with full clip semantics at hdr->pt; results: 16 sums -> hdr->xres[0..15], clip -> xres[16].
 template <int WMODE, int LAYOUT>
@@ -75,7 +63,7 @@ __device__ __noinline__ void pair_exact_pass(const KParams& kp, PairHeader* hdr,
     const float* s3 = slot;
     const float* s2 = slot + 3 * P;
     const float* sw = slot + 5 * P;
-    const Camera<float> cf = load_camera(kp, hdr->obj);
+    const Camera<float> cf = load_camera<float>(kp, hdr->obj);
     const double fx = cf.fx, fy = cf.fy, cx = cf.cx, cy = cf.cy, zmin = cf.z_min;
     const double umin = cf.u_min, umax = cf.u_max, vmin = cf.v_min, vmax = cf.v_max;
     double sn, cs;
@@ -132,7 +120,7 @@ __device__ __noinline__ void pair_exact_pass(const KParams& kp, PairHeader* hdr,
 template <int WMODE, int LAYOUT>
 __device__ __noinline__ bool pair_linear_init(const KParams& kp, PairHeader* hdr, const float* slot, int n, int lane) {
     const int P = kp.n_pts;
-    const Camera<float> cf = load_camera(kp, hdr->obj);
+    const Camera<float> cf = load_camera<float>(kp, hdr->obj);
     double x[4];
     const bool ok = linear_init_impl<WMODE, LAYOUT>(slot, slot + 3 * P, slot + 5 * P, P, n, lane, cf, reinterpret_cast<float*>(hdr->xres), x);
     if (lane == 0) {
@@ -366,7 +354,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) pnp_lm_pair_kernel(const __gr
             for (int i = t; i < WC * P; i += 64) sw[i] = __ldg(gw + i);
             pair_sync(barid);
         }
-        const Camera<float> camf = load_camera(kp, obj);
+        const Camera<float> camf = load_camera<float>(kp, obj);
         MR_TRACE(1);
 
         // ---- sweep A: weights -> istd in place + per-axis sums; A takes even rows, B odd rows ----
