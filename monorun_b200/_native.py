@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, 'libmonorun_pnp.so')
 HEADER = os.path.join(_ROOT, 'include', 'monorun_pnp.h')
-SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('pnp_capi.cu', 'pnp_kernel.cuh', 'pnp_device.cuh')]
+SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('pnp_capi.cu', 'pnp_kernel.cuh', 'pnp_device.cuh', 'pnp_kernel_pair.cuh')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']

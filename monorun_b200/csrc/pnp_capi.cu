@@ -7,7 +7,9 @@
 
 #include "monorun_pnp.h"
 #include "pnp_kernel.cuh"
+#ifdef MRPNP_WITH_PAIR_KERNEL  // experiment kept for reference, see DESIGN.md section 5
 #include "pnp_kernel_pair.cuh"
+#endif
 
 namespace {
 
@@ -58,9 +60,18 @@ int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, const void* c3d, co
     const size_t slot_floats = (size_t)(5 + wc) * p->n_pts;
     size_t slot_bytes = slot_floats * sizeof(float);
     slot_bytes = (slot_bytes + 15) & ~size_t(15);
-    const bool pair = false;  // (the two-warps-per-object kernel of pnp_kernel_pair.cuh measured no faster)
+#ifdef MRPNP_WITH_PAIR_KERNEL
+    const bool pair = p->precision == MRPNP_PREC_MIXED;
+#else
+    const bool pair = false;  // the two-warps-per-object kernel (pnp_kernel_pair.cuh) measured no faster: off by default
+#endif
+#ifdef MRPNP_WITH_PAIR_KERNEL
     const size_t header = pair ? mrpnp::kPairHeaderBytes : mrpnp::kWarpHeaderBytes;
     const int max_groups = pair ? mrpnp::kMaxPairsPerCta : mrpnp::kMaxWarpsPerCta;
+#else
+    const size_t header = mrpnp::kWarpHeaderBytes;
+    const int max_groups = mrpnp::kMaxWarpsPerCta;
+#endif
     int groups = (int)std::min<size_t>(max_groups, (size_t)ctx->max_smem_optin / (slot_bytes + header));
     if (groups < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
     // keep every SM busy before stacking objects on one SM: at small N spread objects over CTAs
@@ -101,7 +112,11 @@ cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan,
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
     } else {
+#ifdef MRPNP_WITH_PAIR_KERNEL
+        auto k = mrpnp::pnp_lm_pair_kernel<WMODE, LAYOUT>;
+#else
         auto k = mrpnp::pnp_lm_kernel<true, WMODE, LAYOUT>;
+#endif
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);

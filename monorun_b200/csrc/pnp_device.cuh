@@ -137,6 +137,13 @@ __device__ __forceinline__ double fast_rcp(double z) {
     x = fma(x, e, x);
     return x;
 }
+// One Newton step: relative error (2^-23)^2 ~ 1.4e-14 -- used on the serial 4x4 solve where latency matters.
+__device__ __forceinline__ double fast_rcp1(double z) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(z));
+    const double e = fma(-z, x, 1.0);
+    return fma(x, e, x);
+}
 __device__ __forceinline__ float fast_rcp(float z) {
     float x;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(z));
@@ -154,6 +161,28 @@ __device__ __forceinline__ double fast_sqrt(double a) {  // a >= 0; returns 0 fo
     double s = a * y;
     s = fma(0.5 * y, fma(-s, s, a), s);  // one correction of sqrt itself
     return a > 0.0 ? s : 0.0;
+}
+
+// sin/cos of a small angle (|d| <= 0.5): Taylor to d^15 / d^14, remainder < 1e-17; two independent Horner
+// chains of 7 fused multiply-adds instead of the ~80-instruction library sincos on the serial LM path.
+__device__ __forceinline__ void sincos_small(double d, double* s, double* c) {
+    const double d2 = d * d;
+    double ps = -1.0 / 1307674368000.0;              // -1/15!
+    ps = fma(ps, d2, 1.0 / 6227020800.0);             //  1/13!
+    ps = fma(ps, d2, -1.0 / 39916800.0);              // -1/11!
+    ps = fma(ps, d2, 1.0 / 362880.0);                 //  1/9!
+    ps = fma(ps, d2, -1.0 / 5040.0);                  // -1/7!
+    ps = fma(ps, d2, 1.0 / 120.0);                    //  1/5!
+    ps = fma(ps, d2, -1.0 / 6.0);                     // -1/3!
+    double pc = -1.0 / 87178291200.0;                 // -1/14!
+    pc = fma(pc, d2, 1.0 / 479001600.0);              //  1/12!
+    pc = fma(pc, d2, -1.0 / 3628800.0);               // -1/10!
+    pc = fma(pc, d2, 1.0 / 40320.0);                  //  1/8!
+    pc = fma(pc, d2, -1.0 / 720.0);                   // -1/6!
+    pc = fma(pc, d2, 1.0 / 24.0);                     //  1/4!
+    pc = fma(pc, d2, -0.5);                           // -1/2!
+    *s = fma(ps * d2, d, d);
+    *c = fma(pc, d2, 1.0);
 }
 
 template <typename T>
@@ -300,13 +329,12 @@ __device__ __noinline__ void eval_pass_fp64(const KParams& kp, int obj, const fl
 template <int WMODE, int LAYOUT>
 __device__ __forceinline__ void eval_pass_mixed(const float* __restrict__ s3, const float* __restrict__ s2,
                                                 const float* __restrict__ sw, int P, int n, int lane,
-                                                const double x[4], const Camera<double>& cam,
-                                                const Camera<float>& camf, double acc[16], double* scratch,
-                                                bool& flagged_out) {
+                                                const double x[4], double sn, double cs,
+                                                const Camera<double>& cam, const Camera<float>& camf,
+                                                double acc[16], double* scratch, bool& flagged_out,
+                                                bool& jfinite_out) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     constexpr int R = 2;  // rows carried through the dependent chains together (ILP; one row alone issues ~1/8 cycles)
-    double sn, cs;
-    sincos(x[0], &sn, &cs);
     const double tx = x[1], ty = x[2], tz = x[3];
     const float snf = (float)sn, csf = (float)cs, txf = (float)tx, tyf = (float)ty, tzf = (float)tz;
     // clip detection on the fp32 projection with a safety margin far above its rounding error (~1e-4 px)
@@ -423,6 +451,12 @@ __device__ __forceinline__ void eval_pass_mixed(const float* __restrict__ s3, co
     // cost: 5-step fp64 butterfly; the 14 fp32 sums: transposed reduction through the scratch
     cost2 = warp_sum(cost2);
     warp_allreduce16<float>(a, reinterpret_cast<float*>(scratch), lane);
+    // finite iff every Jacobian sum is finite (tree of |.| in fp32 instead of a 14-deep fp64 chain)
+    const float s01 = (fabsf(a[0]) + fabsf(a[1])) + (fabsf(a[2]) + fabsf(a[3]));
+    const float s23 = (fabsf(a[4]) + fabsf(a[5])) + (fabsf(a[6]) + fabsf(a[7]));
+    const float s45 = (fabsf(a[8]) + fabsf(a[9])) + (fabsf(a[10]) + fabsf(a[11]));
+    const float s67 = fabsf(a[12]) + fabsf(a[13]);
+    jfinite_out = ((s01 + s23) + (s45 + s67)) < 3.0e38f;
     acc[0] = cost2;
 #pragma unroll
     for (int i = 0; i < 14; ++i) acc[1 + i] = (double)a[i];
@@ -445,18 +479,18 @@ struct Ldl4 {
 __device__ __forceinline__ Ldl4 ldl4_factor(const double A[10]) {
     Ldl4 f;
     const double d0 = A[0];
-    f.i0 = fast_rcp(d0);
+    f.i0 = fast_rcp1(d0);
     f.l10 = A[1] * f.i0; f.l20 = A[2] * f.i0; f.l30 = A[3] * f.i0;
     const double d1 = fma(-f.l10, A[1], A[4]);
-    f.i1 = fast_rcp(d1);
+    f.i1 = fast_rcp1(d1);
     const double t21 = fma(-f.l20, A[1], A[5]), t31 = fma(-f.l30, A[1], A[6]);
     f.l21 = t21 * f.i1; f.l31 = t31 * f.i1;
     const double d2 = fma(-f.l21, t21, fma(-f.l20, A[2], A[7]));
-    f.i2 = fast_rcp(d2);
+    f.i2 = fast_rcp1(d2);
     const double t32 = fma(-f.l31, t21, fma(-f.l30, A[2], A[8]));
     f.l32 = t32 * f.i2;
     const double d3 = fma(-f.l32, t32, fma(-f.l31, t31, fma(-f.l30, A[3], A[9])));
-    f.i3 = fast_rcp(d3);
+    f.i3 = fast_rcp1(d3);
     f.ok = (d0 > 0.0) && (d1 > 0.0) && (d2 > 0.0) && (d3 > 0.0) && (d0 < 1.7e308) && (d1 < 1.7e308) &&
            (d2 < 1.7e308) && (d3 < 1.7e308);
     return f;

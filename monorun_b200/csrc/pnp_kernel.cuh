@@ -229,13 +229,29 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
         int term = kNoConvergence, iteration = 0, cost_evals = 0, num_invalid = 0;
         double radius = kInitialRadius, decrease_factor = 2.0, x_norm = 0.0, model_change = 1.0;
         bool reuse_diagonal = false, step_ok = true, clip_x = false, first = true;
+        double sn_x = 0.0, cs_x = 1.0, sn_p = 0.0, cs_p = 1.0;  // sin/cos of the accepted point / of pt
 
         while (true) {
             // ---- the fused pass at pt ----
             double acc[16];
-            bool clip_p = false;
+            bool clip_p = false, jfinite = true;
             bool exact = !MIXED;
-            if (MIXED) eval_pass_mixed<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, pt, cam, camf, acc, scratch, exact);
+            if (MIXED) {
+                // rotation at pt: library sincos once per object, then the angle-addition update from the accepted
+                // point with a small-angle polynomial (the step in yaw is tiny after the first iteration)
+                double sn, cs;
+                const double dyaw = pt[0] - x[0];
+                if (first || fabs(dyaw) > 0.5) {
+                    sincos(pt[0], &sn, &cs);
+                } else {
+                    double sd, cd;
+                    sincos_small(dyaw, &sd, &cd);
+                    sn = fma(sn_x, cd, cs_x * sd);
+                    cs = fma(cs_x, cd, -sn_x * sd);
+                }
+                sn_p = sn; cs_p = cs;
+                eval_pass_mixed<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, pt, sn, cs, cam, camf, acc, scratch, exact, jfinite);
+            }
             if (exact) {  // MRPNP_PREC_FP64, or a point near a clip bound in the mixed pass: exact fp64 clip semantics
                 __syncwarp();
                 if (lane < 4) {
@@ -250,13 +266,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
                 for (int i = 0; i < 16; ++i) acc[i] = scratch[kScrSums + i];
                 clip_p = scratch[kScrClip] != 0.0;
                 __syncwarp();
+                const double t0 = (fabs(acc[1]) + fabs(acc[2])) + (fabs(acc[3]) + fabs(acc[4]));
+                const double t1 = (fabs(acc[5]) + fabs(acc[6])) + (fabs(acc[7]) + fabs(acc[8]));
+                const double t2 = (fabs(acc[9]) + fabs(acc[10])) + (fabs(acc[11]) + fabs(acc[12]));
+                jfinite = finite_value((t0 + t1) + (t2 + (fabs(acc[13]) + fabs(acc[14]))));
             }
             ++cost_evals;
             const bool cfinite = finite_value(acc[0]);
-            double asum = 0.0;  // finite iff every Jacobian sum is finite
-#pragma unroll
-            for (int i = 1; i < 15; ++i) asum += fabs(acc[i]);
-            const bool jfinite = cfinite && finite_value(asum);
+            jfinite = jfinite && cfinite;
             bool accept = false;
             if (first) {  // IterationZero
                 first = false;
@@ -279,7 +296,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
                     if (!(kp.adopt_ftol && cand_cost < cost)) break;
                     accept = true;  // documented switch: take the candidate, then stop
                 }
-                const double rho = cost_change * fast_rcp(model_change);
+                const double rho = cost_change * fast_rcp1(model_change);
                 if (accept || rho > kMinRelDecrease) {  // HandleSuccessfulStep
                     if (!jfinite) { term = kFailure; break; }  // re-evaluation at the new point fails in Ceres
                     const bool stop = accept;
@@ -295,6 +312,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
 #pragma unroll
                         for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
                         clip_x = clip_p;
+                        sn_x = sn_p; cs_x = cs_p;
                         break;
                     }
                 } else {  // HandleUnsuccessfulStep
@@ -308,6 +326,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
 #pragma unroll
                 for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
                 clip_x = clip_p;
+                sn_x = sn_p; cs_x = cs_p;
                 x_norm = fast_sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
                 step_ok = true;
             }
@@ -336,7 +355,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
                     for (int i = 0; i < 4; ++i) diag[i] = fmin(fmax(Hs[tri(i, i)], kMinLmDiag), kMaxLmDiag);
                 }
                 reuse_diagonal = true;
-                const double inv_radius = fast_rcp(radius);
+                const double inv_radius = fast_rcp1(radius);
 #pragma unroll
                 for (int i = 0; i < 10; ++i) A[i] = Hs[i];
 #pragma unroll
@@ -345,17 +364,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
                 bool valid = f.ok;
                 if (valid) {
                     ldl4_solve(f, gs, y);  // step = -y
-                    // model_cost_change = -step^T gs - 1/2 step^T Hs step = y^T gs - 1/2 y^T Hs y
-                    double yg = 0.0, yhy = 0.0;
+                    // model_cost_change = y^T gs - 1/2 y^T Hs y with (Hs + D) y = gs  =>  1/2 (y^T gs + sum_i D_i y_i^2)
+                    double yg = 0.0, ydy = 0.0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        double t = 0.0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) t = fma(Hs[tri(i, j)], y[j], t);
                         yg = fma(y[i], gs[i], yg);
-                        yhy = fma(y[i], t, yhy);
+                        ydy = fma(diag[i] * inv_radius * y[i], y[i], ydy);
                     }
-                    model_change = fma(-0.5, yhy, yg);
+                    model_change = 0.5 * (yg + ydy);
                     valid = (model_change > 0.0) && finite_value(fabs(y[0]) + fabs(y[1]) + fabs(y[2]) + fabs(y[3]));
                 }
                 if (valid) {

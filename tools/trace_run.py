@@ -25,6 +25,7 @@ for rep in range(3):
 tr = tr.cpu().numpy(); res = result.cpu().numpy()
 evals = None
 names = ['load+cam', 'sweepA(S1)', 'masks(S2)', 'compact(S3)']
+tr[:, 3] = np.where(tr[:, 3] > 0, tr[:, 3], tr[:, 2])
 d = np.diff(tr[:, 0:5], axis=1)
 print('objects', n, 'mean LM iters', res[:, 21].mean())
 for i, nm in enumerate(names):
@@ -32,9 +33,15 @@ for i, nm in enumerate(names):
 tot = tr[:, 30] - tr[:, 0]
 print(f'total/object   mean {tot.mean():9.0f} p50 {np.median(tot):9.0f}   LM part {np.mean(tr[:,29]-tr[:,4]):9.0f}  epilogue {np.mean(tr[:,30]-tr[:,29]):9.0f}')
 for e in range(4):
-    ok = tr[:, 7 + 4 * e] > 0
+    ok = (tr[:, 7 + 4 * e] > 0) | (tr[:, 6 + 4 * e] > 0)
     if ok.sum() == 0: break
     a = tr[ok]
+    if a[:, 4 + 4 * e].min() == 0 or a[:, 7 + 4 * e].min() == 0:  # single-warp kernel: only 5+4e (pass start), 6+4e (pass end)
+        ok = tr[:, 6 + 4 * e] > 0; a = tr[ok]
+        pa = a[:, 6 + 4 * e] - a[:, 5 + 4 * e]
+        nxt = np.where(a[:, 9 + 4 * e] > 0, a[:, 9 + 4 * e], a[:, 29]) - a[:, 6 + 4 * e]
+        print(f'eval {e}: n={ok.sum():5d} pass {pa.mean():7.0f}  scalar-to-next-pass {nxt.mean():7.0f}')
+        continue
     pub = a[:, 5 + 4 * e] - a[:, 4 + 4 * e]
     pa = a[:, 6 + 4 * e] - a[:, 5 + 4 * e]
     wb = a[:, 7 + 4 * e] - a[:, 6 + 4 * e]
