@@ -111,6 +111,33 @@ int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p,
                 const uint32_t* inlier_in,
                 float* result, uint32_t* inlier_out, double* result64, void* stream);
 
+/* Fused head -> PnP entry: takes the dense head's RAW outputs and does, in the kernel prologue, what the reference
+ * does with ~15 torch launches between FCNNOCDecoder and the op:
+ *   NOCCoder.decode (core/bbox_3d/coord_coder/noc_coder.py:50-73), DistanceInvarProjErrorCoder.decode_logstd with
+ *   distance=None (core/bbox_3d/proj_error_coder/distance_invar_proj_error_coder.py:39-60), roi_align of the pixel
+ *   grid (models/roi_heads/monorun_roi_head.py:521-523, bin centres), exp(-logstd)/std_scale and the NCHW permutes
+ *   (uncert_prop_pnp_optimizer.py:73-84).
+ *   noc_pred    [N,3,H,W] float  class-sliced NOC map (FCNNOCDecoder.slice_pred, fcn_noc_decoder.py:242-267)
+ *   proj_logstd [N,2,H,W] float  class-sliced raw log-std
+ *   rois        [N,4] float      x1,y1,x2,y2 of each detection box at the test scale
+ *   dims        [N,3] float      decoded dimensions (l,h,w);  dims_var [N,3] float or NULL (epistemic variance)
+ *   distance    [N] float or NULL  predicted distance (global_head.pred_distance); NULL = scaling_denominator
+ * p->n_pts = H*W, p->layout / p->weight_mode are ignored (planar, log-std).  Other arguments as mrpnp_solve. */
+typedef struct mrpnp_dense_params {
+    float noc_mean[3];   /* NOCCoder.target_means (configs/kitti_multiclass.py:107)                               */
+    float noc_std[3];    /* NOCCoder.target_stds                                                                  */
+    float focal_gain;    /* ref_focal_y * epistemic_std_gain        (distance_invar_proj_error_coder.py:52)       */
+    float scaling_denominator; /* ref_length * ref_focal_y * target_std   (:23)                                   */
+    float distance_min;  /* clamp of the optional per-object distance (:41)                                       */
+    int32_t roi_w;       /* W of the H x W map (28)                                                               */
+} mrpnp_dense_params;
+
+int mrpnp_solve_dense(mrpnp_ctx* ctx, const mrpnp_params* p, const mrpnp_dense_params* dp,
+                      const float* noc_pred, const float* proj_logstd, const float* rois,
+                      const float* dims, const float* dims_var, const float* distance,
+                      const float* cam_mats, const float* uv_range, const float* init_pose,
+                      float* result, uint32_t* inlier_out, void* stream);
+
 /* Same contract on HOST pointers: copies inputs to the device in chunks overlapped with the solve,
  * copies `result` (and inlier_out) back, and returns when they are valid -- the calling convention of
  * the reference's CPU op (numpy buffers in, numpy buffers out; pnp_uncert_cpu.py:128-209). */

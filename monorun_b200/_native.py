@@ -82,5 +82,5 @@ def check(rc):
         raise RuntimeError(f'libmonorun_pnp error {rc}: {last_error()}')
 
 
-EXPORTED = ['mrpnp_default_params', 'mrpnp_create', 'mrpnp_destroy', 'mrpnp_solve', 'mrpnp_solve_host',
+EXPORTED = ['mrpnp_default_params', 'mrpnp_create', 'mrpnp_destroy', 'mrpnp_solve', 'mrpnp_solve_dense', 'mrpnp_solve_host',
             'mrpnp_launch_count', 'mrpnp_kernel_info', 'mrpnp_version', 'mrpnp_last_error']

@@ -116,7 +116,7 @@ def coords_2d_from_rois(rois, out_size=28):
     rois: (N, 5) [batch_idx, x1, y1, x2, y2] or (N, 4).  Returns (N, 2, S, S) float32.
     """
     b = rois[:, -4:].float()
-    k = (torch.arange(out_size, device=rois.device, dtype=torch.float32) + 0.5) / out_size
+    k = (torch.arange(out_size, device=rois.device, dtype=torch.float32) + 0.5) * (1.0 / out_size)
     u = b[:, 0:1] - 0.5 + k[None, :] * (b[:, 2:3] - b[:, 0:1])
     v = b[:, 1:2] - 0.5 + k[None, :] * (b[:, 3:4] - b[:, 1:2])
     n = b.shape[0]

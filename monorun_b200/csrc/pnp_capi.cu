@@ -137,14 +137,21 @@ cudaError_t dispatch(const mrpnp_params* p, const KParams& kp, const LaunchPlan&
     return cudaErrorInvalidValue;
 }
 
+struct DenseArgs {
+    const mrpnp_dense_params* dp;
+    const float* dims;
+    const float* dims_var;
+    const float* distance;
+};
+
 int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const float* c2d, const float* wgt,
                  const float* cam, const float* range, const float* init, const uint32_t* inl_in, float* result,
-                 uint32_t* inl_out, double* result64, cudaStream_t stream) {
+                 uint32_t* inl_out, double* result64, cudaStream_t stream, const DenseArgs* dense = nullptr) {
     if (p->n_obj == 0) return MRPNP_OK;
     if (!c3d || !c2d || !wgt || !cam || !range || !result) return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
     if (p->init_mode == MRPNP_INIT_GIVEN && !init) return fail(MRPNP_ERR_ARG, "init_pose is NULL with MRPNP_INIT_GIVEN%s");
     LaunchPlan plan;
-    int rc = plan_launch(ctx, p, c3d, c2d, wgt, &plan);
+    int rc = plan_launch(ctx, p, c3d, dense ? c3d : c2d, wgt, &plan);
     if (rc != MRPNP_OK) return rc;
     KParams kp;
     kp.c3d = c3d; kp.c2d = c2d; kp.wgt = wgt; kp.cam = cam; kp.range = range; kp.init = init;
@@ -157,6 +164,23 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     kp.use_tma = plan.use_tma;
     kp.slot_floats = plan.slot_floats;
     kp.z_min = p->z_min; kp.std_scale = p->std_scale; kp.istd_thres = p->istd_thres;
+    kp.dense = dense ? 1 : 0;
+    kp.roi_w = dense ? dense->dp->roi_w : 0;
+    kp.dims = dense ? dense->dims : nullptr;
+    kp.dims_var = dense ? dense->dims_var : nullptr;
+    for (int i = 0; i < 3; ++i) {
+        kp.noc_mean[i] = dense ? dense->dp->noc_mean[i] : 0.f;
+        kp.noc_std[i] = dense ? dense->dp->noc_std[i] : 1.f;
+    }
+    kp.distance = dense ? dense->distance : nullptr;
+    if (dense) {
+        const float g = dense->dp->focal_gain / dense->dp->scaling_denominator;
+        kp.proj_gain2 = g * g;
+        kp.inv_scaling_denominator = 1.f / dense->dp->scaling_denominator;
+        kp.distance_min = dense->dp->distance_min;
+    } else {
+        kp.proj_gain2 = 0.f; kp.inv_scaling_denominator = 1.f; kp.distance_min = 0.f;
+    }
     cudaError_t e = dispatch(p, kp, plan, stream);
     if (e != cudaSuccess) return fail(MRPNP_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
     ctx->launches += 1;
@@ -245,6 +269,28 @@ int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_3d, c
     g_err[0] = 0;
     return solve_device(ctx, p, coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose, inlier_in, result,
                         inlier_out, result64, static_cast<cudaStream_t>(stream));
+}
+
+int mrpnp_solve_dense(mrpnp_ctx* ctx, const mrpnp_params* p, const mrpnp_dense_params* dp, const float* noc_pred,
+                      const float* proj_logstd, const float* rois, const float* dims, const float* dims_var,
+                      const float* distance, const float* cam_mats, const float* uv_range, const float* init_pose, float* result,
+                      uint32_t* inlier_out, void* stream) {
+    if (!ctx || !dp) return fail(MRPNP_ERR_ARG, "ctx or dense params is NULL%s");
+    if (!p) return fail(MRPNP_ERR_ARG, "params is NULL%s");
+    mrpnp_params q = *p;
+    q.layout = MRPNP_LAYOUT_PLANAR;
+    q.weight_mode = MRPNP_W_LOGSTD;
+    int rc = check_params(&q);
+    if (rc != MRPNP_OK) return rc;
+    if (!dims || !rois) return fail(MRPNP_ERR_ARG, "rois / dims is NULL%s");
+    if (dp->roi_w <= 0 || p->n_pts % dp->roi_w != 0) return fail(MRPNP_ERR_ARG, "n_pts is not a multiple of roi_w%s");
+    if (!(dp->scaling_denominator > 0.f)) return fail(MRPNP_ERR_ARG, "scaling_denominator must be positive%s");
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    const DenseArgs da{dp, dims, dims_var, distance};
+    // alignment for the TMA path is decided on the two streamed tensors; `rois` rides in the coords_2d slot
+    return solve_device(ctx, &q, noc_pred, rois, proj_logstd, cam_mats, uv_range, init_pose, nullptr, result,
+                        inlier_out, nullptr, static_cast<cudaStream_t>(stream), &da);
 }
 
 // Host-buffer entry: objects are cut into chunks; chunk i+1's host->device copies run on the other

@@ -48,6 +48,14 @@ struct KParams {
     int cov_mode, init_mode, inlier_opt_only, max_iter, adopt_ftol;
     int use_tma, slot_floats;
     float z_min, std_scale, istd_thres;
+    // fused head -> PnP entry (mrpnp_solve_dense): c3d = noc_pred [N,3,P], wgt = proj_logstd [N,2,P], c2d = rois [N,4]
+    int dense, roi_w;
+    const float* dims;      // [N,3] decoded dimensions (l,h,w)
+    const float* dims_var;  // [N,3] or NULL
+    float noc_mean[3], noc_std[3];
+    const float* distance;  // [N] or NULL
+    float proj_gain2;       // (ref_focal_y * epistemic_std_gain / scaling_denominator)^2
+    float inv_scaling_denominator, distance_min;
 };
 
 // ------------------------------------------------------------------ PTX wrappers (TMA bulk copy + mbarrier)

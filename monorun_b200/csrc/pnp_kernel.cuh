@@ -30,7 +30,7 @@ __device__ __forceinline__ void load_object(const KParams& kp, int obj, float* s
                                             int lane) {
     const int P = kp.n_pts;
     const float* g3 = kp.c3d + (size_t)obj * 3 * P;
-    const float* g2 = kp.c2d + (size_t)obj * 2 * P;
+    const float* g2 = kp.c2d + (size_t)obj * (kp.dense ? 0 : 2 * P);
     const float* gw = kp.wgt + (size_t)obj * WC * P;
     float* s3 = slot;
     float* s2 = slot + 3 * P;
@@ -39,16 +39,22 @@ __device__ __forceinline__ void load_object(const KParams& kp, int obj, float* s
     if (kp.use_tma) {
         if (lane == 0) {
             fence_proxy_async();  // order our generic-proxy accesses before the async-proxy writes
-            mbar_expect_tx(bar, (uint32_t)((5 + WC) * P * sizeof(float)));
-            bulk_g2s(s3, g3, (uint32_t)(3 * P * sizeof(float)), bar);
-            bulk_g2s(s2, g2, (uint32_t)(2 * P * sizeof(float)), bar);
-            bulk_g2s(sw, gw, (uint32_t)(WC * P * sizeof(float)), bar);
+            if (kp.dense) {  // fused head entry: only the NOC map and the raw log-std come from HBM
+                mbar_expect_tx(bar, (uint32_t)(5 * P * sizeof(float)));
+                bulk_g2s(s3, g3, (uint32_t)(3 * P * sizeof(float)), bar);
+                bulk_g2s(sw, gw, (uint32_t)(2 * P * sizeof(float)), bar);
+            } else {
+                mbar_expect_tx(bar, (uint32_t)((5 + WC) * P * sizeof(float)));
+                bulk_g2s(s3, g3, (uint32_t)(3 * P * sizeof(float)), bar);
+                bulk_g2s(s2, g2, (uint32_t)(2 * P * sizeof(float)), bar);
+                bulk_g2s(sw, gw, (uint32_t)(WC * P * sizeof(float)), bar);
+            }
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
     } else {
         for (int i = lane; i < 3 * P; i += 32) s3[i] = __ldg(g3 + i);
-        for (int i = lane; i < 2 * P; i += 32) s2[i] = __ldg(g2 + i);
+        if (!kp.dense) for (int i = lane; i < 2 * P; i += 32) s2[i] = __ldg(g2 + i);
         for (int i = lane; i < WC * P; i += 32) sw[i] = __ldg(gw + i);
         __syncwarp();
     }
@@ -73,6 +79,66 @@ __device__ __forceinline__ void weights_and_thresholds(const KParams& kp, float*
             sw[sidx<LAYOUT, WC>(p, 0, P)] = wu;
             sw[sidx<LAYOUT, WC>(p, CV, P)] = wv;
         }
+        su += wu;
+        sv += wv;
+    }
+    su = warp_sum(su);
+    sv = warp_sum(sv);
+    const float invP = 1.f / (float)P;
+    thr_u = kp.istd_thres * (su * invP);
+    thr_v = kp.istd_thres * (sv * invP);
+    __syncwarp();
+}
+
+// Fused head -> PnP prologue (planar layout, log-std weights): the slot holds the dense head's raw outputs, NOC map in
+// the coords_3d planes and proj_logstd in the weight planes.  One sweep decodes them in place and generates coords_2d:
+//   coords_3d = (noc*std + mean) * dims                                   NOCCoder.decode, coord_coder/noc_coder.py:50-73
+//   var_3d    = dims_var * (noc*std + mean)^2                              (noc_var is None, :68-69)
+//   var_2d    = (0.5 (var_x + var_z), var_y)                              distance_invar_proj_error_coder.py:46-50
+//   logstd'   = 0.5 log(var_2d (f gain / sd)^2 + exp(2 logstd))           :52-55 with distance = scaling_denominator
+//   istd      = exp(-logstd') / std_scale                                 uncert_prop_pnp_optimizer.py:73
+//   u[j] = x1 - 0.5 + (j + 0.5)(x2 - x1)/W,  v[i] likewise                roi_align of the pixel grid, monorun_roi_head.py:521-523
+// and accumulates the per-axis weight sums for the inlier thresholds (pnp_uncert_cpu.py:164-165).
+__device__ __forceinline__ void dense_decode_and_thresholds(const KParams& kp, int obj, float* slot, int lane,
+                                                            float& thr_u, float& thr_v) {
+    const int P = kp.n_pts, W = kp.roi_w, H = P / W;
+    float* s3 = slot;
+    float* s2 = slot + 3 * P;
+    float* sw = slot + 5 * P;
+    const float* roi = kp.c2d + (size_t)obj * 4;
+    const float x1 = __ldg(roi + 0), y1 = __ldg(roi + 1), x2 = __ldg(roi + 2), y2 = __ldg(roi + 3);
+    const float dx = x2 - x1, dy = y2 - y1, x0 = x1 - 0.5f, y0 = y1 - 0.5f;
+    const float inv_w = 1.f / (float)W, inv_h = 1.f / (float)H;
+    const float* dm = kp.dims + (size_t)obj * 3;
+    const float d0 = __ldg(dm + 0), d1 = __ldg(dm + 1), d2 = __ldg(dm + 2);
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (kp.dims_var) {
+        const float* dv = kp.dims_var + (size_t)obj * 3;
+        v0 = __ldg(dv + 0); v1 = __ldg(dv + 1); v2 = __ldg(dv + 2);
+    }
+    // distance given: the variance is divided by clamp(distance)^2 instead of scaling_denominator^2 (:41-44)
+    float inv_scale = 1.f / kp.std_scale;
+    if (kp.distance) inv_scale *= fmaxf(__ldg(kp.distance + obj), kp.distance_min) * kp.inv_scaling_denominator;
+    float su = 0.f, sv = 0.f;
+    // coords_3d and coords_2d use un-contracted roundings so that they are bit-identical to the separate torch
+    // launches of the unfused path (mul, add, mul  /  (j+0.5)/W, mul, add)
+#pragma unroll 2
+    for (int p = lane; p < P; p += 32) {
+        const int i = p / W, j = p - i * W;
+        const float pn0 = __fadd_rn(__fmul_rn(s3[p], kp.noc_std[0]), kp.noc_mean[0]);
+        const float pn1 = __fadd_rn(__fmul_rn(s3[P + p], kp.noc_std[1]), kp.noc_mean[1]);
+        const float pn2 = __fadd_rn(__fmul_rn(s3[2 * P + p], kp.noc_std[2]), kp.noc_mean[2]);
+        s3[p] = pn0 * d0;
+        s3[P + p] = pn1 * d1;
+        s3[2 * P + p] = pn2 * d2;
+        const float vu = 0.5f * (v0 * pn0 * pn0 + v2 * pn2 * pn2), vv = v1 * pn1 * pn1;
+        const float lu = sw[p], lv = sw[P + p];
+        const float wu = rsqrtf(fmaf(vu, kp.proj_gain2, __expf(2.f * lu))) * inv_scale;
+        const float wv = rsqrtf(fmaf(vv, kp.proj_gain2, __expf(2.f * lv))) * inv_scale;
+        sw[p] = wu;
+        sw[P + p] = wv;
+        s2[p] = __fadd_rn(x0, __fmul_rn(__fmul_rn((float)j + 0.5f, inv_w), dx));
+        s2[P + p] = __fadd_rn(y0, __fmul_rn(__fmul_rn((float)i + 0.5f, inv_h), dy));
         su += wu;
         sv += wv;
     }
@@ -192,7 +258,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
         for (int attempt = 0; attempt < 2; ++attempt) {
             load_object<WC>(kp, obj, slot, bar, parity, lane);
             float thr_u, thr_v;
-            weights_and_thresholds<WMODE, LAYOUT, MIXED>(kp, slot + 5 * P, lane, thr_u, thr_v);
+            if (WMODE == MRPNP_W_LOGSTD && LAYOUT == MRPNP_LAYOUT_PLANAR && kp.dense)
+                dense_decode_and_thresholds(kp, obj, slot, lane, thr_u, thr_v);
+            else
+                weights_and_thresholds<WMODE, LAYOUT, MIXED>(kp, slot + 5 * P, lane, thr_u, thr_v);
             // second attempt == pnp_uncert_cpu.py:28-32: <= 4 inliers -> every point is an inlier (slot re-staged)
             const bool all = attempt == 1;
             const bool compact = !all && kp.inlier_opt_only != 0;

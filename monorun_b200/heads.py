@@ -58,17 +58,32 @@ class UncertPropPnPOptimizer(nn.Module):
             ret_val (Nbatch,) bool, yaw_pred (Nbatch, 1), t_vec_pred (Nbatch, 3),
             pose_cov_pred (Nbatch, 4, 4), pose_cov_calib (Nbatch, 4, 4)
         """
+        ret_val, yaw_pred, t_vec_pred, pose_cov_pred, _ = self.pnp.forward_dense(
+            coords_2d, coords_2d_logstd, coords_3d, cam_intrinsic, self._uv_range(img_shapes), self.std_scale,
+            init_pose=init_pose)
+        return ret_val, yaw_pred, t_vec_pred, pose_cov_pred, self._calibrate(pose_cov_pred)
+
+    def _uv_range(self, img_shapes):
         b = float(self.allowed_border)
-        uv_range = coords_2d.new_empty((img_shapes.size(0), 4))
+        uv_range = img_shapes.new_empty((img_shapes.size(0), 4), dtype=torch.float32)
         uv_range[:, 0] = -b                      # :75-80
         uv_range[:, 1] = img_shapes[:, 1] + b
         uv_range[:, 2] = -b
         uv_range[:, 3] = img_shapes[:, 0] + b
-        ret_val, yaw_pred, t_vec_pred, pose_cov_pred, _ = self.pnp.forward_dense(
-            coords_2d, coords_2d_logstd, coords_3d, cam_intrinsic, uv_range, self.std_scale, init_pose=init_pose)
+        return uv_range
+
+    def _calibrate(self, pose_cov_pred):
         cov_calib_scale = torch.exp(self.cov_calib_logscale)
-        pose_cov_calib = (cov_calib_scale * cov_calib_scale[:, None]) * pose_cov_pred  # :96-97
-        return ret_val, yaw_pred, t_vec_pred, pose_cov_pred, pose_cov_calib
+        return (cov_calib_scale * cov_calib_scale[:, None]) * pose_cov_pred  # :96-97
+
+    def forward_fused(self, noc_pred, proj_logstd, rois, dimensions, dimensions_var, cam_intrinsic, img_shapes,
+                      coord_coder, proj_error_coder, distance=None, init_pose=None):
+        """Same five outputs as :meth:`forward`, from the dense head's RAW maps: NOC decode, variance-propagated
+        log-std and the RoI pixel grid run inside the PnP kernel (one launch for monorun_roi_head.py:513-529)."""
+        ret_val, yaw_pred, t_vec_pred, pose_cov_pred, _ = self.pnp.forward_fused(
+            noc_pred, proj_logstd, rois, dimensions, dimensions_var, cam_intrinsic, self._uv_range(img_shapes),
+            self.std_scale, coord_coder, proj_error_coder, distance=distance, init_pose=init_pose)
+        return ret_val, yaw_pred, t_vec_pred, pose_cov_pred, self._calibrate(pose_cov_pred)
 
 
 class ConvModule(nn.Module):
@@ -273,7 +288,7 @@ class MonoRUnRoIHead(nn.Module):
             self.noc_head.init_weights()
 
     def forward_3d(self, noc_feats, bbox_3d_rois, det_labels, latent_pred, dimensions_pred, dimensions_var,
-                   cam_intrinsic, img_shape, flip=False, distance_pred=None, cov_correction=True):
+                   cam_intrinsic, img_shape, flip=False, distance_pred=None, cov_correction=True, fused=False):
         """monorun_roi_head.py:509-534: dense head -> decode -> analytic coords_2d -> PnP -> covariance correction.
 
         noc_feats (N,256,14,14), bbox_3d_rois (N,5), det_labels (N,), latent_pred (N,16), dimensions_pred (N,3),
@@ -281,12 +296,21 @@ class MonoRUnRoIHead(nn.Module):
         Returns dict(ret_val, yaw_pred, t_vec_pred, pose_cov_pred, pose_cov_calib, coords_3d, proj_logstd).
         """
         noc_pred, noc_var, proj_logstd, _ = self.noc_head(noc_feats, latent_pred, None, det_labels, flip=flip)
+        img_shapes = cam_intrinsic.new_tensor(img_shape[:2])[None, ...]
+        if fused:  # :513-529 as ONE launch; only valid without an aleatoric NOC variance map (every shipped config)
+            assert noc_var is None, 'fused head->PnP entry expects noc_var=None'
+            ret_val, yaw, t_vec, cov, cov_calib = self.pose_head.forward_fused(
+                noc_pred, proj_logstd, bbox_3d_rois, dimensions_pred, dimensions_var, cam_intrinsic, img_shapes,
+                self.noc_head.coord_coder, self.projection_head.proj_error_coder, distance=distance_pred)
+            if cov_correction:
+                distance = self.projection_head.get_distance(t_vec)
+                cov_calib = self.projection_head.proj_error_coder.cov_correction(cov_calib, distance)
+            return dict(ret_val=ret_val, yaw_pred=yaw, t_vec_pred=t_vec, pose_cov_pred=cov, pose_cov_calib=cov_calib)
         coords_3d, coords_3d_var = self.noc_head.coord_coder.decode(           # :513-515
             noc_pred, noc_var, dimensions_pred, dimensions_var, flip)
         proj_logstd = self.projection_head.proj_error_coder.decode_logstd(     # :516-519
             proj_logstd, coords_3d_var, distance_pred)
         coords_2d_roi = coords_2d_from_rois(bbox_3d_rois, noc_pred.shape[-1])  # :521-523
-        img_shapes = cam_intrinsic.new_tensor(img_shape[:2])[None, ...]
         ret_val, yaw, t_vec, cov, cov_calib = self.pose_head(                  # :525-529
             coords_2d_roi, proj_logstd, coords_3d, cam_intrinsic, img_shapes)
         if cov_correction:                                                     # :530-534

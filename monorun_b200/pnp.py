@@ -143,6 +143,54 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
     return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None), res64
 
 
+def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, *, noc_mean, noc_std, focal_gain,
+                scaling_denominator, distance=None, distance_min=0.1, init_pose=None, z_min=0.5, std_scale=10.0,
+                istd_thres=0.6, inlier_opt_only=True, cov_mode='pipeline', precision='mixed', max_iterations=50,
+                return_inlier_mask=True):
+    """Fused head -> PnP launch -- direct wrapper of ``mrpnp_solve_dense``: the dense head's raw class-sliced
+    ``noc_pred`` [N,3,H,W] and ``proj_logstd`` [N,2,H,W], the detection boxes ``rois`` [N,4|5] and the decoded
+    ``dims`` [N,3] (+ ``dims_var`` [N,3] | None, ``distance`` [N] | None) go in; NOCCoder.decode, the variance
+    propagation of DistanceInvarProjErrorCoder.decode_logstd and the RoI pixel grid are evaluated in the kernel
+    prologue.  Returns (result [N,24], inlier_mask [N,H*W] bool | None)."""
+    dev = noc_pred.device
+    ctx = get_ctx(dev)
+    n, _, h, w = noc_pred.shape
+    n_pts = h * w
+    result = torch.empty((n, RESULT_STRIDE), dtype=torch.float32, device=dev)
+    inl_out = torch.empty((n, (n_pts + 31) // 32), dtype=torch.int32, device=dev) if return_inlier_mask else None
+    if n == 0:
+        return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None)
+    noc, ls = _f32c(noc_pred), _f32c(proj_logstd)
+    boxes = _f32c(rois[:, -4:])
+    dm = _f32c(dims)
+    dv = _f32c(dims_var) if dims_var is not None else None
+    dist = _f32c(distance).reshape(-1) if distance is not None else None
+    if dm.shape != (n, 3) or boxes.shape != (n, 4) or ls.shape != (n, 2, h, w) or (dist is not None and dist.numel() != n):
+        raise ValueError('solve_dense: inconsistent shapes')
+    cam, rng = _f32c(cam_mats).reshape(-1, 9), _f32c(uv_range).reshape(-1, 4)
+    if cam.shape[0] not in (1, n) or rng.shape[0] not in (1, n):
+        raise ValueError('cam_mats / uv_range must have batch size 1 or N')
+    init = _f32c(init_pose) if init_pose is not None else None
+    p = make_params(
+        n, n_pts, cam_stride=9 if cam.shape[0] == n and n > 1 else 0,
+        range_stride=4 if rng.shape[0] == n and n > 1 else 0, precision=_PREC[precision],
+        cov_mode={'none': 0, 'pipeline': 1, 'ceres': 2}[cov_mode],
+        init_mode=C['MRPNP_INIT_GIVEN'] if init is not None else C['MRPNP_INIT_LINEAR'],
+        inlier_opt_only=int(bool(inlier_opt_only)), max_iterations=int(max_iterations),
+        z_min=float(z_min), std_scale=float(std_scale), istd_thres=float(istd_thres))
+    dp = _native.ffi.new('mrpnp_dense_params*')
+    for i in range(3):
+        dp.noc_mean[i], dp.noc_std[i] = float(noc_mean[i]), float(noc_std[i])
+    dp.focal_gain, dp.scaling_denominator = float(focal_gain), float(scaling_denominator)
+    dp.distance_min, dp.roi_w = float(distance_min), int(w)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_solve_dense(
+            ctx.ptr, p, dp, _ptr(noc), _ptr(ls), _ptr(boxes), _ptr(dm), _ptr(dv), _ptr(dist), _ptr(cam), _ptr(rng),
+            _ptr(init), _ptr(result), _ptr(inl_out, 'uint32_t*'), _native.ffi.cast('void*', stream)))
+    return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None)
+
+
 def solve_host(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None, *, device=0, layout='planar',
                weight_mode='logstd', result=None, **kw):
     """``mrpnp_solve_host`` on CPU tensors / numpy-backed memory (pinned for full speed): the reference op's
@@ -253,4 +301,22 @@ class PnPUncert(torch.nn.Module):
                 coords_3d, coords_2d, coords_2d_logstd, cam_mats, uv_range, init_pose=init_pose, layout='planar',
                 weight_mode='logstd', z_min=self.z_min, std_scale=std_scale, istd_thres=self.epnp_istd_thres,
                 inlier_opt_only=self.inlier_opt_only, cov_mode='pipeline', precision=self.precision)
+            return _unpack(result, inlier_mask)
+
+    def forward_fused(self, noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, std_scale, coord_coder,
+                      proj_error_coder, distance=None, init_pose=None):
+        """Fused head -> PnP entry (``mrpnp_solve_dense``): takes what FCNNOCDecoder returns plus the decoded
+        dimensions and the boxes; ``coord_coder`` (NOCCoder) and ``proj_error_coder``
+        (DistanceInvarProjErrorCoder) only supply their constants."""
+        with torch.no_grad():
+            if self.coord_istd_normalize:
+                raise NotImplementedError('coord_istd_normalize with the fused entry')
+            result, inlier_mask = solve_dense(
+                noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range,
+                noc_mean=coord_coder.target_means, noc_std=coord_coder.target_stds,
+                focal_gain=proj_error_coder.ref_focal_y * proj_error_coder.epistemic_std_gain,
+                scaling_denominator=proj_error_coder.scaling_denomitor, distance=distance,
+                distance_min=proj_error_coder.distance_min, init_pose=init_pose, z_min=self.z_min,
+                std_scale=std_scale, istd_thres=self.epnp_istd_thres, inlier_opt_only=self.inlier_opt_only,
+                cov_mode='pipeline', precision=self.precision)
             return _unpack(result, inlier_mask)

@@ -217,3 +217,29 @@ def to_op_level(batch, std_scale=STD_SCALE, allowed_border=ALLOWED_BORDER):
     out['u_range'] = np.array([[-allowed_border, iw + allowed_border]], np.float32)
     out['v_range'] = np.array([[-allowed_border, ih + allowed_border]], np.float32)
     return out
+
+
+NOC_MEANS = (-0.1, -0.5, 0.0)   # configs/kitti_multiclass.py:106-108 (NOCCoder target_means / target_stds)
+NOC_STDS = (0.35, 0.23, 0.34)
+
+
+def to_head_raw(batch, rng=None, dims_var_scale=0.3):
+    """An 'S1' batch -> what the fused head->PnP entry consumes: the dense head's RAW maps and per-object rows.
+
+    noc_pred [n,3,r,r] = (coords_3d / dims - mean) / std   (inverse of NOCCoder.decode, noc_coder.py:50-73),
+    proj_logstd [n,2,r,r] raw log-std, rois [n,5] = (0, x1, y1, x2, y2), dims [n,3], dims_var [n,3] =
+    (dims_var_scale * class sigma)^2 -- the epistemic variance MC dropout would produce -- all float32."""
+    if 'boxes' not in batch:
+        raise ValueError("to_head_raw needs a grid-faithful batch (mode='S1')")
+    n = batch['dims'].shape[0]
+    dims = batch['dims'].astype(np.float64)
+    mean = np.asarray(NOC_MEANS)[None, :, None, None]
+    std = np.asarray(NOC_STDS)[None, :, None, None]
+    noc = (batch['coords_3d'].astype(np.float64) / dims[:, :, None, None] - mean) / std
+    sd = DIM_STDS[batch['labels']] * dims_var_scale
+    if rng is not None:
+        sd = sd * np.exp(rng.uniform(-0.5, 0.5, sd.shape))
+    rois = np.concatenate([np.zeros((n, 1)), batch['boxes']], 1)
+    return dict(noc_pred=noc.astype(np.float32), proj_logstd=batch['logstd'].astype(np.float32),
+                rois=rois.astype(np.float32), dims=batch['dims'].astype(np.float32),
+                dims_var=(sd * sd).astype(np.float32))

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import monorun_b200
-from monorun_b200 import _native, coders, heads, pnp, registry
+from monorun_b200 import _native, coders, heads, pnp, registry, synth
 from monorun_b200.config import ConfigDict, build_roi_head, load_config
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -251,3 +251,18 @@ def test_sharded_gather_world_size_2_gloo(n_total):
     [p.start() for p in procs]
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs) and ret.get(0) and ret.get(1)
+
+
+def test_head_raw_generator_inverts_the_decoders():
+    """synth.to_head_raw: NOCCoder.decode(noc_pred) gives back coords_3d, the RoI grid gives back coords_2d."""
+    from monorun_b200 import coders
+    b = synth.make_batch(16, config=3, weights='diag', mode='S1')
+    raw = synth.to_head_raw(b, rng=np.random.default_rng(5))
+    cc = coders.NOCCoder(synth.NOC_MEANS, synth.NOC_STDS)
+    c3, c3v = cc.decode(torch.from_numpy(raw['noc_pred']), None, torch.from_numpy(raw['dims']),
+                        torch.from_numpy(raw['dims_var']), False)
+    assert np.abs(c3.numpy() - b['coords_3d']).max() < 1e-5 and (c3v >= 0).all()
+    c2 = coders.coords_2d_from_rois(torch.from_numpy(raw['rois']))
+    assert np.abs(c2.numpy() - b['coords_2d']).max() < 2e-4
+    with pytest.raises(ValueError):
+        synth.to_head_raw(synth.make_batch(2, config=2, mode='S0'))

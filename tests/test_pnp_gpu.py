@@ -325,3 +325,129 @@ def test_full_size_properties(cuda_lib):
 def test_smoke_entry(cuda_lib):
     import __graft_entry__ as g
     g.smoke()
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+def test_clipped_points_follow_ceres_jet_semantics(cuda_lib, oracle, precision):
+    """A narrow u/v range clamps a good share of the projections (pnp_uncert_cpu.cpp:41-42) and a large z_min clips
+    depths (:36): the clamped rows lose their derivative, a clipped depth keeps d/dx' -- same decisions, same pose
+    and same Ceres-style covariance as the oracle.  In mixed mode the near-clip flag routes these passes to the exact
+    fp64 routine."""
+    from monorun_b200 import pnp
+    b, op, full, w = case(96, 2, 'diag', 'S0')
+    gt = b['gt_pose']
+    uvc, _ = synth.project(synth.KITTI_K, gt[:, 0], gt[:, 1:], op['coords_3d'].astype(np.float64))
+    # per object: u range cuts ~25 % of the points on one side, v range ~15 % on the other
+    u_hi = np.quantile(uvc[..., 0], 0.75, axis=1)
+    v_lo = np.quantile(uvc[..., 1], 0.15, axis=1)
+    rng = np.stack([np.full(96, -200.0), u_hi, v_lo, np.full(96, 575.0)], 1).astype(np.float32)
+    mask = host_mask(oracle, w, False)
+    cl = np.concatenate([np.full((96, 1), 0.5), rng], 1).astype(np.float64)
+    ref = oracle.lm_batch(op['coords_2d'], op['coords_3d'], w, op['cam_mats'], b['init_pose'], cl, mask,
+                          with_pose_cov=True, threads=0)
+    res, _, r64 = pnp.solve_batched(dev(op['coords_3d']), dev(op['coords_2d']), dev(w), dev(op['cam_mats']), dev(rng),
+                                    init_pose=dev(b['init_pose']), inlier_mask=dev(mask), layout='interleaved',
+                                    weight_mode='istd', precision=precision, cov_mode='ceres', return_fp64=True)
+    res, r64 = res.cpu().numpy(), r64.cpu().numpy()
+    assert np.array_equal(res[:, 20] == 1, ref['val'])
+    ok = ref['val']
+    assert ok.sum() > 48
+    t_err, r_err = pose_errors(r64[ok], ref['pose'][ok])
+    tol_t, tol_r = (1e-9, 1e-9) if precision == 'fp64' else (T_TOL, R_TOL)
+    assert t_err.max() < tol_t and r_err.max() < tol_r, (t_err.max(), r_err.max())
+    assert (r64[ok, 6].astype(int) == ref['stats'][ok, 1]).mean() > (0.999 if precision == 'fp64' else 0.97)
+    cov = res[ok, 4:20].reshape(-1, 4, 4)
+    rel = np.linalg.norm(cov - ref['cov'][ok], axis=(1, 2)) / np.linalg.norm(ref['cov'][ok], axis=(1, 2))
+    assert rel.max() < 1e-3, rel.max()
+
+
+def _unfused_from_raw(raw, b, distance=None, use_dims_var=True):
+    """The reference's launch sequence between the dense head and the op (monorun_roi_head.py:513-523)."""
+    from monorun_b200 import coders
+    cc, pc = coders.NOCCoder(synth.NOC_MEANS, synth.NOC_STDS), coders.DistanceInvarProjErrorCoder()
+    dv = dev(raw['dims_var']) if use_dims_var else None
+    c3, c3v = cc.decode(dev(raw['noc_pred']), None, dev(raw['dims']), dv, False)
+    ls = pc.decode_logstd(dev(raw['proj_logstd']), c3v, distance)
+    c2 = coders.coords_2d_from_rois(dev(raw['rois']), raw['noc_pred'].shape[-1]).contiguous()
+    return cc, pc, c3, c2, ls
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+@pytest.mark.parametrize('variant', ['dims_var', 'plain', 'distance'])
+def test_fused_head_entry_matches_unfused_sequence(cuda_lib, oracle, precision, variant):
+    """mrpnp_solve_dense (decode + variance propagation + RoI grid in the kernel prologue) against the unfused
+    torch sequence feeding mrpnp_solve, and against the oracle on the tensors that sequence produced."""
+    from monorun_b200 import pnp
+    n = 512
+    b = synth.make_batch(n, config=3, weights='diag', mode='S1')
+    raw = synth.to_head_raw(b, rng=np.random.default_rng(5))
+    distance = dev(np.linalg.norm(b['gt_pose'][:, 1:4], axis=1, keepdims=True).astype(np.float32)) \
+        if variant == 'distance' else None   # (N,1) like global_head's distance_pred
+    cc, pc, c3, c2, ls = _unfused_from_raw(raw, b, distance, use_dims_var=variant != 'plain')
+    ih, iw = b['img_shape']
+    rng_uv = torch.tensor([[-200.0, iw + 200.0, -200.0, ih + 200.0]], device='cuda')
+    cam = dev(b['cam_mat'][None])
+    init = dev(b['init_pose'])
+    r_u, m_u, _ = pnp.solve_batched(c3, c2, ls, cam, rng_uv, init_pose=init, layout='planar', weight_mode='logstd',
+                                    precision=precision)
+    r_f, m_f = pnp.solve_dense(
+        dev(raw['noc_pred']), dev(raw['proj_logstd']), dev(raw['rois']), dev(raw['dims']),
+        dev(raw['dims_var']) if variant != 'plain' else None, cam, rng_uv, noc_mean=cc.target_means,
+        noc_std=cc.target_stds, focal_gain=pc.ref_focal_y * pc.epistemic_std_gain,
+        scaling_denominator=pc.scaling_denomitor, distance=distance, distance_min=pc.distance_min, init_pose=init,
+        precision=precision)
+    r_u, r_f = r_u.cpu().numpy(), r_f.cpu().numpy()
+    assert (r_u[:, 20] == 1).all() and (r_f[:, 20] == 1).all()
+    # weights differ by a few ulp (rsqrt(exp) vs exp(-0.5 log)): a borderline point may change sides
+    assert (m_u != m_f).float().mean().item() < 1e-4
+    same = (m_u == m_f).all(dim=1).cpu().numpy()      # objects whose inlier sets are identical in both paths
+    assert same.mean() > 0.99
+    t_err, r_err = pose_errors(r_f[:, 0:4].astype(np.float64), r_u[:, 0:4].astype(np.float64))
+    assert t_err[same].max() < T_TOL and r_err[same].max() < R_TOL, (t_err[same].max(), r_err[same].max())
+    assert t_err.max() < 5e-3 and r_err.max() < 5e-3     # one flipped borderline point moves the optimum slightly
+    r_f, r_u = r_f[same], r_u[same]
+    cov_f, cov_u = r_f[:, 4:20].reshape(-1, 4, 4), r_u[:, 4:20].reshape(-1, 4, 4)
+    sd = np.sqrt(np.einsum('nii->ni', cov_u))
+    assert (np.abs(cov_f - cov_u) / (sd[:, :, None] * sd[:, None, :])).max() < 2e-3   # relative to sigma_i sigma_j
+    # and against the oracle, fed with the unfused tensors and the fused path's own inlier mask
+    c3n = c3.permute(0, 2, 3, 1).reshape(n, -1, 3).cpu().numpy()
+    c2n = c2.permute(0, 2, 3, 1).reshape(n, -1, 2).cpu().numpy()
+    istd = (torch.exp(-ls) / synth.STD_SCALE).permute(0, 2, 3, 1).reshape(n, -1, 2).cpu().numpy()
+    ref = oracle.lm_batch(c2n, c3n, istd, b['cam_mat'][None], b['init_pose'],
+                          np.array([[0.5, -200.0, iw + 200.0, -200.0, ih + 200.0]]), m_f.cpu().numpy(), threads=0)
+    t_err, r_err = pose_errors(r_f[:, 0:4].astype(np.float64), ref['pose'][same])
+    assert t_err.max() < T_TOL and r_err.max() < R_TOL, (t_err.max(), r_err.max())
+
+
+def test_fused_entry_through_pose_head_and_roi_head(cuda_lib):
+    """UncertPropPnPOptimizer.forward_fused == forward on decoded tensors (on-device linear initialiser), and
+    MonoRUnRoIHead.forward_3d(fused=True) launches exactly one PnP kernel."""
+    from monorun_b200 import heads, pnp
+    n = 128
+    b = synth.make_batch(n, config=2, weights='diag', mode='S1')
+    raw = synth.to_head_raw(b)
+    cc, pc, c3, c2, ls = _unfused_from_raw(raw, b)
+    head = heads.UncertPropPnPOptimizer().cuda()
+    cam = dev(b['cam_mat'][None])
+    img_shapes = dev(b['img_shape'][None])
+    out_u = head(c2, ls, c3, cam, img_shapes)
+    out_f = head.forward_fused(dev(raw['noc_pred']), dev(raw['proj_logstd']), dev(raw['rois']), dev(raw['dims']),
+                               dev(raw['dims_var']), cam, img_shapes, cc, pc)
+    assert out_u[0].all() and out_f[0].all()
+    t_rel = (out_f[2] - out_u[2]).norm(dim=1) / out_u[2].norm(dim=1)
+    assert t_rel.max().item() < T_TOL and (out_f[1] - out_u[1]).abs().max().item() < R_TOL
+    sd = out_u[4].diagonal(dim1=1, dim2=2).sqrt()
+    assert ((out_f[4] - out_u[4]).abs() / (sd[:, :, None] * sd[:, None, :])).max().item() < 2e-3
+
+    import monorun_b200
+    from tests.test_host import _roi_head_cfg
+    torch.manual_seed(0)
+    roi_head = monorun_b200.build_head(_roi_head_cfg()).cuda().eval()
+    roi_head.init_weights()
+    before = pnp.launch_count()
+    with torch.no_grad():
+        out = roi_head.forward_3d(torch.randn(8, 256, 14, 14, device='cuda'), dev(raw['rois'][:8]), dev(b['labels'][:8]),
+                                  torch.randn(8, 16, device='cuda'), dev(raw['dims'][:8]), dev(raw['dims_var'][:8]),
+                                  cam, (375, 1242), fused=True)
+    assert pnp.launch_count() == before + 1
+    assert out['t_vec_pred'].shape == (8, 3) and out['pose_cov_calib'].shape == (8, 4, 4)
