@@ -120,6 +120,7 @@ int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p,
  *   noc_pred    [N,3,H,W] float  class-sliced NOC map (FCNNOCDecoder.slice_pred, fcn_noc_decoder.py:242-267)
  *   proj_logstd [N,2,H,W] float  class-sliced raw log-std
  *   rois        [N,4] float      x1,y1,x2,y2 of each detection box at the test scale
+ *   labels      [N] int64 or NULL class ids, only read when dp->num_classes > 0
  *   dims        [N,3] float      decoded dimensions (l,h,w);  dims_var [N,3] float or NULL (epistemic variance)
  *   distance    [N] float or NULL  predicted distance (global_head.pred_distance); NULL = scaling_denominator
  * p->n_pts = H*W, p->layout / p->weight_mode are ignored (planar, log-std).  Other arguments as mrpnp_solve. */
@@ -130,11 +131,16 @@ typedef struct mrpnp_dense_params {
     float scaling_denominator; /* ref_length * ref_focal_y * target_std   (:23)                                   */
     float distance_min;  /* clamp of the optional per-object distance (:41)                                       */
     int32_t roi_w;       /* W of the H x W map (28)                                                               */
+    int32_t num_classes; /* 0: noc_pred / proj_logstd are class-sliced maps.  C > 0: fused slice_pred -- noc_pred  */
+                         /* points at the head's full output all_pred [N, >= 5*C, H, W] (the flip half already      */
+                         /* selected by the pointer), proj_logstd is ignored and `labels` picks channels            */
+                         /* [3c,3c+3) and [3C+2c, 3C+2c+2) of each object (fcn_noc_decoder.py:242-267)              */
+    int64_t pred_stride; /* floats between consecutive objects of all_pred (2*5*C*H*W for the flip-paired view)    */
 } mrpnp_dense_params;
 
 int mrpnp_solve_dense(mrpnp_ctx* ctx, const mrpnp_params* p, const mrpnp_dense_params* dp,
                       const float* noc_pred, const float* proj_logstd, const float* rois,
-                      const float* dims, const float* dims_var, const float* distance,
+                      const int64_t* labels, const float* dims, const float* dims_var, const float* distance,
                       const float* cam_mats, const float* uv_range, const float* init_pose,
                       float* result, uint32_t* inlier_out, void* stream);
 

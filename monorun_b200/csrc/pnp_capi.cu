@@ -142,6 +142,7 @@ struct DenseArgs {
     const float* dims;
     const float* dims_var;
     const float* distance;
+    const int64_t* labels;
 };
 
 int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const float* c2d, const float* wgt,
@@ -173,6 +174,8 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
         kp.noc_std[i] = dense ? dense->dp->noc_std[i] : 1.f;
     }
     kp.distance = dense ? dense->distance : nullptr;
+    kp.labels = dense ? reinterpret_cast<const long long*>(dense->labels) : nullptr;
+    kp.pred_stride = (dense && dense->dp->num_classes > 0) ? dense->dp->pred_stride : 0;
     if (dense) {
         const float g = dense->dp->focal_gain / dense->dp->scaling_denominator;
         kp.proj_gain2 = g * g;
@@ -272,8 +275,8 @@ int mrpnp_solve(mrpnp_ctx* ctx, const mrpnp_params* p, const float* coords_3d, c
 }
 
 int mrpnp_solve_dense(mrpnp_ctx* ctx, const mrpnp_params* p, const mrpnp_dense_params* dp, const float* noc_pred,
-                      const float* proj_logstd, const float* rois, const float* dims, const float* dims_var,
-                      const float* distance, const float* cam_mats, const float* uv_range, const float* init_pose, float* result,
+                      const float* proj_logstd, const float* rois, const int64_t* labels, const float* dims,
+                      const float* dims_var, const float* distance, const float* cam_mats, const float* uv_range, const float* init_pose, float* result,
                       uint32_t* inlier_out, void* stream) {
     if (!ctx || !dp) return fail(MRPNP_ERR_ARG, "ctx or dense params is NULL%s");
     if (!p) return fail(MRPNP_ERR_ARG, "params is NULL%s");
@@ -287,7 +290,16 @@ int mrpnp_solve_dense(mrpnp_ctx* ctx, const mrpnp_params* p, const mrpnp_dense_p
     if (!(dp->scaling_denominator > 0.f)) return fail(MRPNP_ERR_ARG, "scaling_denominator must be positive%s");
     MR_CUDA(cudaSetDevice(ctx->device));
     g_err[0] = 0;
-    const DenseArgs da{dp, dims, dims_var, distance};
+    const int C = dp->num_classes;
+    if (C < 0) return fail(MRPNP_ERR_ARG, "num_classes < 0%s");
+    if (C > 0) {
+        if (!labels) return fail(MRPNP_ERR_ARG, "labels is NULL with num_classes > 0%s");
+        if (dp->pred_stride < (int64_t)5 * C * p->n_pts) return fail(MRPNP_ERR_ARG, "pred_stride smaller than 5*C*H*W%s");
+        if (p->n_pts % 4 == 0 && dp->pred_stride % 4 != 0)  // keeps every object's slice 16-byte aligned for the bulk copies
+            return fail(MRPNP_ERR_ARG, "pred_stride must be a multiple of 4 floats%s");
+        proj_logstd = noc_pred + (size_t)3 * C * p->n_pts;
+    }
+    const DenseArgs da{dp, dims, dims_var, distance, C > 0 ? labels : nullptr};
     // alignment for the TMA path is decided on the two streamed tensors; `rois` rides in the coords_2d slot
     return solve_device(ctx, &q, noc_pred, rois, proj_logstd, cam_mats, uv_range, init_pose, nullptr, result,
                         inlier_out, nullptr, static_cast<cudaStream_t>(stream), &da);

@@ -54,6 +54,8 @@ struct KParams {
     const float* dims_var;  // [N,3] or NULL
     float noc_mean[3], noc_std[3];
     const float* distance;  // [N] or NULL
+    const long long* labels;  // [N] class ids or NULL; used when pred_stride != 0 (c3d/wgt point into all_pred)
+    long long pred_stride;    // floats between consecutive objects of all_pred, 0 = pre-sliced maps
     float proj_gain2;       // (ref_focal_y * epistemic_std_gain / scaling_denominator)^2
     float inv_scaling_denominator, distance_min;
 };

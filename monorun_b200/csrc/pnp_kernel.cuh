@@ -32,6 +32,13 @@ __device__ __forceinline__ void load_object(const KParams& kp, int obj, float* s
     const float* g3 = kp.c3d + (size_t)obj * 3 * P;
     const float* g2 = kp.c2d + (size_t)obj * (kp.dense ? 0 : 2 * P);
     const float* gw = kp.wgt + (size_t)obj * WC * P;
+    if (kp.dense && kp.pred_stride) {
+        // class slice of the head's full output (FCNNOCDecoder.slice_pred, fcn_noc_decoder.py:242-267): channels
+        // [3c, 3c+3) of the NOC block and [2c, 2c+2) of the log-std block that follows the 3*C NOC channels
+        const long long c = kp.labels ? __ldg(kp.labels + obj) : 0;
+        g3 = kp.c3d + (size_t)obj * kp.pred_stride + (size_t)(3 * c) * P;
+        gw = kp.wgt + (size_t)obj * kp.pred_stride + (size_t)(2 * c) * P;
+    }
     float* s3 = slot;
     float* s2 = slot + 3 * P;
     float* sw = slot + 5 * P;

@@ -77,12 +77,13 @@ class UncertPropPnPOptimizer(nn.Module):
         return (cov_calib_scale * cov_calib_scale[:, None]) * pose_cov_pred  # :96-97
 
     def forward_fused(self, noc_pred, proj_logstd, rois, dimensions, dimensions_var, cam_intrinsic, img_shapes,
-                      coord_coder, proj_error_coder, distance=None, init_pose=None):
+                      coord_coder, proj_error_coder, distance=None, init_pose=None, labels=None, num_classes=0):
         """Same five outputs as :meth:`forward`, from the dense head's RAW maps: NOC decode, variance-propagated
         log-std and the RoI pixel grid run inside the PnP kernel (one launch for monorun_roi_head.py:513-529)."""
         ret_val, yaw_pred, t_vec_pred, pose_cov_pred, _ = self.pnp.forward_fused(
             noc_pred, proj_logstd, rois, dimensions, dimensions_var, cam_intrinsic, self._uv_range(img_shapes),
-            self.std_scale, coord_coder, proj_error_coder, distance=distance, init_pose=init_pose)
+            self.std_scale, coord_coder, proj_error_coder, distance=distance, init_pose=init_pose, labels=labels,
+            num_classes=num_classes)
         return ret_val, yaw_pred, t_vec_pred, pose_cov_pred, self._calibrate(pose_cov_pred)
 
 
@@ -189,6 +190,12 @@ class FCNNOCDecoder(nn.Module):
             nn.init.constant_(self.latent_decoder.bias, 0)
 
     def forward(self, x, latent_pred, latent_var, labels, flip=False):
+        noc_pred, noc_var, proj_logstd = self.slice_pred(self.forward_all(x, latent_pred, flip), labels)
+        return noc_pred, noc_var, proj_logstd, None
+
+    def forward_all(self, x, latent_pred, flip=False):
+        """fcn_noc_decoder.py:189-235 up to (not including) slice_pred: the unsliced ``all_pred`` [N, 5*C, 2h, 2w]
+        (a strided view of the flip-paired conv output).  The fused PnP entry slices it by class itself."""
         if self.use_dropout2d and self.num_dropout2d_layers > 0:
             x = self.dropout2d(x)
         for i, conv in enumerate(self.convs):
@@ -215,8 +222,7 @@ class FCNNOCDecoder(nn.Module):
                 else:
                     inds = torch.arange(0, all_pred.size(0), dtype=torch.long, device=all_pred.device)
                     all_pred = all_pred[inds, inds.new_tensor(flip)]
-        noc_pred, noc_var, proj_logstd = self.slice_pred(all_pred, labels)
-        return noc_pred, noc_var, proj_logstd, None
+        return all_pred
 
     def slice_pred(self, all_pred, labels):
         k = 1 if self.class_agnostic else self.num_classes
@@ -295,17 +301,25 @@ class MonoRUnRoIHead(nn.Module):
         dimensions_var (N,3)|None, cam_intrinsic (1|N,3,3), img_shape (h, w).
         Returns dict(ret_val, yaw_pred, t_vec_pred, pose_cov_pred, pose_cov_calib, coords_3d, proj_logstd).
         """
-        noc_pred, noc_var, proj_logstd, _ = self.noc_head(noc_feats, latent_pred, None, det_labels, flip=flip)
         img_shapes = cam_intrinsic.new_tensor(img_shape[:2])[None, ...]
-        if fused:  # :513-529 as ONE launch; only valid without an aleatoric NOC variance map (every shipped config)
-            assert noc_var is None, 'fused head->PnP entry expects noc_var=None'
+        if fused:  # slice_pred + :513-529 as ONE launch on the head's unsliced output (noc_var is None in this head)
+            head = self.noc_head
+            all_pred = head.forward_all(noc_feats, latent_pred, flip)
+            sliced = head.class_agnostic or head.uncert_channels != 2 or all_pred.stride()[1:] != \
+                (all_pred.shape[2] * all_pred.shape[3], all_pred.shape[3], 1)
+            if sliced:   # layouts the in-kernel class gather does not cover: slice with torch, still one PnP launch
+                noc_pred, _, proj_logstd = head.slice_pred(all_pred, det_labels)
+                kw = {}
+            else:
+                noc_pred, proj_logstd, kw = all_pred, None, dict(labels=det_labels, num_classes=head.num_classes)
             ret_val, yaw, t_vec, cov, cov_calib = self.pose_head.forward_fused(
                 noc_pred, proj_logstd, bbox_3d_rois, dimensions_pred, dimensions_var, cam_intrinsic, img_shapes,
-                self.noc_head.coord_coder, self.projection_head.proj_error_coder, distance=distance_pred)
+                head.coord_coder, self.projection_head.proj_error_coder, distance=distance_pred, **kw)
             if cov_correction:
                 distance = self.projection_head.get_distance(t_vec)
                 cov_calib = self.projection_head.proj_error_coder.cov_correction(cov_calib, distance)
             return dict(ret_val=ret_val, yaw_pred=yaw, t_vec_pred=t_vec, pose_cov_pred=cov, pose_cov_calib=cov_calib)
+        noc_pred, noc_var, proj_logstd, _ = self.noc_head(noc_feats, latent_pred, None, det_labels, flip=flip)
         coords_3d, coords_3d_var = self.noc_head.coord_coder.decode(           # :513-515
             noc_pred, noc_var, dimensions_pred, dimensions_var, flip)
         proj_logstd = self.projection_head.proj_error_coder.decode_logstd(     # :516-519

@@ -146,26 +146,39 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
 def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, *, noc_mean, noc_std, focal_gain,
                 scaling_denominator, distance=None, distance_min=0.1, init_pose=None, z_min=0.5, std_scale=10.0,
                 istd_thres=0.6, inlier_opt_only=True, cov_mode='pipeline', precision='mixed', max_iterations=50,
-                return_inlier_mask=True):
+                return_inlier_mask=True, labels=None, num_classes=0):
     """Fused head -> PnP launch -- direct wrapper of ``mrpnp_solve_dense``: the dense head's raw class-sliced
     ``noc_pred`` [N,3,H,W] and ``proj_logstd`` [N,2,H,W], the detection boxes ``rois`` [N,4|5] and the decoded
     ``dims`` [N,3] (+ ``dims_var`` [N,3] | None, ``distance`` [N] | None) go in; NOCCoder.decode, the variance
     propagation of DistanceInvarProjErrorCoder.decode_logstd and the RoI pixel grid are evaluated in the kernel
-    prologue.  Returns (result [N,24], inlier_mask [N,H*W] bool | None)."""
+    prologue.  Returns (result [N,24], inlier_mask [N,H*W] bool | None).
+
+    With ``labels`` [N] int64 and ``num_classes`` = C, ``noc_pred`` is instead the head's full output ``all_pred``
+    [N, 5*C, H, W] (any object stride: a ``[:, half]`` view of the flip-paired [N,2,5*C,H,W] tensor works) and the
+    class slice of FCNNOCDecoder.slice_pred is taken by the kernel's loads; ``proj_logstd`` is ignored."""
     dev = noc_pred.device
     ctx = get_ctx(dev)
     n, _, h, w = noc_pred.shape
     n_pts = h * w
+    pred_stride = 0
+    if num_classes:
+        if noc_pred.dtype != torch.float32 or noc_pred.shape[1] != 5 * num_classes or noc_pred[0].stride() != (h * w, w, 1):
+            raise ValueError('solve_dense: all_pred must be float32 [N, 5*C, H, W] with contiguous objects')
+        pred_stride = noc_pred.stride(0) if n > 1 else 5 * num_classes * n_pts
+        labels = labels.to(torch.int64).contiguous()
+        proj_logstd = None
     result = torch.empty((n, RESULT_STRIDE), dtype=torch.float32, device=dev)
     inl_out = torch.empty((n, (n_pts + 31) // 32), dtype=torch.int32, device=dev) if return_inlier_mask else None
     if n == 0:
         return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None)
-    noc, ls = _f32c(noc_pred), _f32c(proj_logstd)
+    noc = noc_pred if num_classes else _f32c(noc_pred)
+    ls = _f32c(proj_logstd) if proj_logstd is not None else None
     boxes = _f32c(rois[:, -4:])
     dm = _f32c(dims)
     dv = _f32c(dims_var) if dims_var is not None else None
     dist = _f32c(distance).reshape(-1) if distance is not None else None
-    if dm.shape != (n, 3) or boxes.shape != (n, 4) or ls.shape != (n, 2, h, w) or (dist is not None and dist.numel() != n):
+    if dm.shape != (n, 3) or boxes.shape != (n, 4) or (ls is not None and ls.shape != (n, 2, h, w)) or \
+            (dist is not None and dist.numel() != n):
         raise ValueError('solve_dense: inconsistent shapes')
     cam, rng = _f32c(cam_mats).reshape(-1, 9), _f32c(uv_range).reshape(-1, 4)
     if cam.shape[0] not in (1, n) or rng.shape[0] not in (1, n):
@@ -183,10 +196,12 @@ def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range,
         dp.noc_mean[i], dp.noc_std[i] = float(noc_mean[i]), float(noc_std[i])
     dp.focal_gain, dp.scaling_denominator = float(focal_gain), float(scaling_denominator)
     dp.distance_min, dp.roi_w = float(distance_min), int(w)
+    dp.num_classes, dp.pred_stride = int(num_classes), int(pred_stride)
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
         _native.check(_native.lib().mrpnp_solve_dense(
-            ctx.ptr, p, dp, _ptr(noc), _ptr(ls), _ptr(boxes), _ptr(dm), _ptr(dv), _ptr(dist), _ptr(cam), _ptr(rng),
+            ctx.ptr, p, dp, _ptr(noc), _ptr(ls), _ptr(boxes), _ptr(labels if num_classes else None, 'int64_t*'), _ptr(dm),
+            _ptr(dv), _ptr(dist), _ptr(cam), _ptr(rng),
             _ptr(init), _ptr(result), _ptr(inl_out, 'uint32_t*'), _native.ffi.cast('void*', stream)))
     return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None)
 
@@ -304,10 +319,11 @@ class PnPUncert(torch.nn.Module):
             return _unpack(result, inlier_mask)
 
     def forward_fused(self, noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, std_scale, coord_coder,
-                      proj_error_coder, distance=None, init_pose=None):
+                      proj_error_coder, distance=None, init_pose=None, labels=None, num_classes=0):
         """Fused head -> PnP entry (``mrpnp_solve_dense``): takes what FCNNOCDecoder returns plus the decoded
         dimensions and the boxes; ``coord_coder`` (NOCCoder) and ``proj_error_coder``
-        (DistanceInvarProjErrorCoder) only supply their constants."""
+        (DistanceInvarProjErrorCoder) only supply their constants.  With ``labels`` / ``num_classes`` the first
+        argument is the head's unsliced ``all_pred`` (see :func:`solve_dense`)."""
         with torch.no_grad():
             if self.coord_istd_normalize:
                 raise NotImplementedError('coord_istd_normalize with the fused entry')
@@ -318,5 +334,5 @@ class PnPUncert(torch.nn.Module):
                 scaling_denominator=proj_error_coder.scaling_denomitor, distance=distance,
                 distance_min=proj_error_coder.distance_min, init_pose=init_pose, z_min=self.z_min,
                 std_scale=std_scale, istd_thres=self.epnp_istd_thres, inlier_opt_only=self.inlier_opt_only,
-                cov_mode='pipeline', precision=self.precision)
+                cov_mode='pipeline', precision=self.precision, labels=labels, num_classes=num_classes)
             return _unpack(result, inlier_mask)

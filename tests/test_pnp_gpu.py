@@ -462,3 +462,33 @@ def test_fused_entry_through_pose_head_and_roi_head(cuda_lib):
                                   cam, (375, 1242), fused=True)
     assert pnp.launch_count() == before + 1
     assert out['t_vec_pred'].shape == (8, 3) and out['pose_cov_calib'].shape == (8, 4, 4)
+
+
+def test_fused_entry_slices_classes_like_slice_pred(cuda_lib):
+    """num_classes > 0: the kernel's loads pick channels [3c,3c+3) / [3C+2c,3C+2c+2) of the unsliced all_pred -- same
+    result, bit for bit, as FCNNOCDecoder.slice_pred followed by the pre-sliced fused entry; also through the
+    strided [:, half] view of the flip-paired [N,2,15,28,28] tensor."""
+    from monorun_b200 import coders, pnp
+    n, C = 96, 3
+    b = synth.make_batch(n, config=3, weights='diag', mode='S1')
+    raw = synth.to_head_raw(b, rng=np.random.default_rng(1))
+    rng = np.random.default_rng(2)
+    paired = rng.standard_normal((n, 2, 5 * C, 28, 28)).astype(np.float32)      # every other class/half is junk
+    lab = b['labels']
+    for half in (0, 1):
+        for i in range(n):
+            paired[i, half, 3 * lab[i]:3 * lab[i] + 3] = raw['noc_pred'][i]
+            paired[i, half, 3 * C + 2 * lab[i]:3 * C + 2 * lab[i] + 2] = raw['proj_logstd'][i]
+    paired = dev(paired)
+    cc, pc = coders.NOCCoder(synth.NOC_MEANS, synth.NOC_STDS), coders.DistanceInvarProjErrorCoder()
+    ih, iw = b['img_shape']
+    kw = dict(noc_mean=cc.target_means, noc_std=cc.target_stds, focal_gain=pc.ref_focal_y * pc.epistemic_std_gain,
+              scaling_denominator=pc.scaling_denomitor, init_pose=dev(b['init_pose']))
+    args = (dev(raw['rois']), dev(raw['dims']), dev(raw['dims_var']), dev(b['cam_mat'][None]),
+            torch.tensor([[-200.0, iw + 200.0, -200.0, ih + 200.0]], device='cuda'))
+    r_ref, m_ref = pnp.solve_dense(dev(raw['noc_pred']), dev(raw['proj_logstd']), *args, **kw)
+    for half in (0, 1):
+        r, m = pnp.solve_dense(paired[:, half], None, *args, labels=dev(lab), num_classes=C, **kw)
+        assert torch.equal(r, r_ref) and torch.equal(m, m_ref)
+    with pytest.raises(ValueError):
+        pnp.solve_dense(paired[:, 0, :14], None, *args, labels=dev(lab), num_classes=C, **kw)
