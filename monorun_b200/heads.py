@@ -193,9 +193,20 @@ class FCNNOCDecoder(nn.Module):
         noc_pred, noc_var, proj_logstd = self.slice_pred(self.forward_all(x, latent_pred, flip), labels)
         return noc_pred, noc_var, proj_logstd, None
 
-    def forward_all(self, x, latent_pred, flip=False):
+    def forward_all(self, x, latent_pred, flip=False, native=False):
         """fcn_noc_decoder.py:189-235 up to (not including) slice_pred: the unsliced ``all_pred`` [N, 5*C, 2h, 2w]
-        (a strided view of the flip-paired conv output).  The fused PnP entry slices it by class itself."""
+        (a strided view of the flip-paired conv output).  The fused PnP entry slices it by class itself.
+
+        ``native=True`` runs the layers in libmonorun_head.so (tcgen05 implicit-GEMM convolutions + CARAFE kernel,
+        bf16 operands / fp32 accumulation, inference only) instead of the fp32 torch modules below."""
+        if native and x.size(0) > 0:
+            from .dense_head import DenseHeadB200
+            runner = getattr(self, '_b200_runner', None)
+            if runner is None or runner.device != x.device:
+                runner = DenseHeadB200(self)      # packs the weights once; call drop_native_cache() after changing them
+                object.__setattr__(self, '_b200_runner', runner)
+            all_pred = runner.forward(x, latent_pred)
+            return self._select_flip_half(all_pred, flip)
         if self.use_dropout2d and self.num_dropout2d_layers > 0:
             x = self.dropout2d(x)
         for i, conv in enumerate(self.convs):
@@ -214,14 +225,20 @@ class FCNNOCDecoder(nn.Module):
             x = self.upsample(x)
             for conv_upsampled in self.convs_upsampled:
                 x = conv_upsampled(x)
-            all_pred = self.conv_final(x)
-            if self.flip_correction:
-                all_pred = all_pred.view(all_pred.size(0), 2, all_pred.size(1) // 2, all_pred.size(2), all_pred.size(3))
-                if isinstance(flip, bool):
-                    all_pred = all_pred[:, 1 if flip else 0]
-                else:
-                    inds = torch.arange(0, all_pred.size(0), dtype=torch.long, device=all_pred.device)
-                    all_pred = all_pred[inds, inds.new_tensor(flip)]
+            all_pred = self._select_flip_half(self.conv_final(x), flip)
+        return all_pred
+
+    def drop_native_cache(self):
+        object.__setattr__(self, '_b200_runner', None)
+
+    def _select_flip_half(self, all_pred, flip):
+        if self.flip_correction:   # :225-235
+            all_pred = all_pred.view(all_pred.size(0), 2, all_pred.size(1) // 2, all_pred.size(2), all_pred.size(3))
+            if isinstance(flip, bool):
+                all_pred = all_pred[:, 1 if flip else 0]
+            else:
+                inds = torch.arange(0, all_pred.size(0), dtype=torch.long, device=all_pred.device)
+                all_pred = all_pred[inds, inds.new_tensor(flip)]
         return all_pred
 
     def slice_pred(self, all_pred, labels):
@@ -294,7 +311,8 @@ class MonoRUnRoIHead(nn.Module):
             self.noc_head.init_weights()
 
     def forward_3d(self, noc_feats, bbox_3d_rois, det_labels, latent_pred, dimensions_pred, dimensions_var,
-                   cam_intrinsic, img_shape, flip=False, distance_pred=None, cov_correction=True, fused=False):
+                   cam_intrinsic, img_shape, flip=False, distance_pred=None, cov_correction=True, fused=False,
+                   native_head=False):
         """monorun_roi_head.py:509-534: dense head -> decode -> analytic coords_2d -> PnP -> covariance correction.
 
         noc_feats (N,256,14,14), bbox_3d_rois (N,5), det_labels (N,), latent_pred (N,16), dimensions_pred (N,3),
@@ -304,7 +322,7 @@ class MonoRUnRoIHead(nn.Module):
         img_shapes = cam_intrinsic.new_tensor(img_shape[:2])[None, ...]
         if fused:  # slice_pred + :513-529 as ONE launch on the head's unsliced output (noc_var is None in this head)
             head = self.noc_head
-            all_pred = head.forward_all(noc_feats, latent_pred, flip)
+            all_pred = head.forward_all(noc_feats, latent_pred, flip, native=native_head)
             sliced = head.class_agnostic or head.uncert_channels != 2 or all_pred.stride()[1:] != \
                 (all_pred.shape[2] * all_pred.shape[3], all_pred.shape[3], 1)
             if sliced:   # layouts the in-kernel class gather does not cover: slice with torch, still one PnP launch
@@ -319,7 +337,11 @@ class MonoRUnRoIHead(nn.Module):
                 distance = self.projection_head.get_distance(t_vec)
                 cov_calib = self.projection_head.proj_error_coder.cov_correction(cov_calib, distance)
             return dict(ret_val=ret_val, yaw_pred=yaw, t_vec_pred=t_vec, pose_cov_pred=cov, pose_cov_calib=cov_calib)
-        noc_pred, noc_var, proj_logstd, _ = self.noc_head(noc_feats, latent_pred, None, det_labels, flip=flip)
+        if native_head:
+            noc_pred, noc_var, proj_logstd = self.noc_head.slice_pred(
+                self.noc_head.forward_all(noc_feats, latent_pred, flip, native=True), det_labels)
+        else:
+            noc_pred, noc_var, proj_logstd, _ = self.noc_head(noc_feats, latent_pred, None, det_labels, flip=flip)
         coords_3d, coords_3d_var = self.noc_head.coord_coder.decode(           # :513-515
             noc_pred, noc_var, dimensions_pred, dimensions_var, flip)
         proj_logstd = self.projection_head.proj_error_coder.decode_logstd(     # :516-519
