@@ -46,7 +46,11 @@ extern "C" {
 
 /* arithmetic of the solver */
 #define MRPNP_PREC_FP64 0  /* residual, Jacobian and normal equations in fp64: reproduces the fp64 reference decisions */
-#define MRPNP_PREC_MIXED 1 /* fp64 residual/cost chain + fp32 Jacobian sums, fp64 4x4 solve: the fast path            */
+#define MRPNP_PREC_MIXED 1 /* fp64 residual/cost chain + fp32 Jacobian sums in every pass, fp64 4x4 solve              */
+#define MRPNP_PREC_FAST 2  /* residuals evaluated once in fp64, then tracked incrementally: candidate evaluations are   */
+                           /* pure fp32 "delta" passes whose cost CHANGE is accurate to ~1e-6 of itself; objects with a */
+                           /* point near a clip bound are re-solved by the MIXED kernel in a follow-up launch on the    */
+                           /* same stream.  Needs inlier_opt_only = 1 (otherwise the solve runs as MIXED).              */
 
 /* pose covariance written to the result row */
 #define MRPNP_COV_NONE 0

@@ -7,6 +7,8 @@
 
 #include "monorun_pnp.h"
 #include "pnp_kernel.cuh"
+#include "pnp_kernel_fast.cuh"
+#include <stdlib.h>
 #ifdef MRPNP_WITH_PAIR_KERNEL  // experiment kept for reference, see DESIGN.md section 5
 #include "pnp_kernel_pair.cuh"
 #endif
@@ -28,6 +30,7 @@ int fail(int code, const char* fmt, const char* detail = "") {
 
 constexpr int kHostStreams = 2;
 constexpr int kCounterSets = 8;
+constexpr int kCounterInts = 4;  // per set: next work item, finished CTAs, redo-list length, pad
 
 }  // namespace
 
@@ -35,7 +38,9 @@ struct mrpnp_ctx {
     int device = 0;
     int num_sms = 0;
     int max_smem_optin = 0;
-    int* counters = nullptr;  // kCounterSets x 2 ints, all zero between launches
+    int* counters = nullptr;  // kCounterSets x kCounterInts ints, all zero between launches
+    int* redo_lists = nullptr;  // kCounterSets x redo_cap object indices (MRPNP_PREC_FAST hand-over to the exact kernel)
+    int redo_cap = 0;
     int next_counter = 0;
     int64_t launches = 0;
     // host-path staging
@@ -51,11 +56,29 @@ namespace {
 using mrpnp::KParams;
 
 struct LaunchPlan {
-    int warps, groups, ctas, smem, use_tma, slot_floats;
+    int warps, groups, ctas, smem, use_tma, slot_floats, team;
 };
 
-int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, const void* c3d, const void* c2d, const void* wgt,
-                LaunchPlan* plan) {
+int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, int precision, const void* c3d, const void* c2d,
+                const void* wgt, LaunchPlan* plan) {
+    if (precision == MRPNP_PREC_FAST) {
+        const int wc = p->weight_mode == MRPNP_W_FULL ? 3 : 2;
+        size_t slot_bytes = ((size_t)(5 + wc) * p->n_pts * sizeof(float) + 15) & ~size_t(15);
+        int groups = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, (size_t)ctx->max_smem_optin / (slot_bytes + mrpnp::kFastHeaderBytes));
+        if (groups < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
+        const int per_sm = (p->n_obj + ctx->num_sms - 1) / ctx->num_sms;
+        groups = std::max(1, std::min(groups, per_sm));
+        plan->team = 1;
+        plan->warps = groups;
+        plan->groups = groups;
+        plan->ctas = std::min(ctx->num_sms, (p->n_obj + groups - 1) / groups);
+        plan->smem = (int)(groups * (slot_bytes + mrpnp::kFastHeaderBytes));
+        plan->slot_floats = (int)(slot_bytes / sizeof(float));
+        const bool aligned = (p->n_pts % 4 == 0) && (((uintptr_t)c3d | (uintptr_t)c2d | (uintptr_t)wgt) % 16 == 0);
+        plan->use_tma = aligned ? 1 : 0;
+        return MRPNP_OK;
+    }
+    plan->team = 1;
     const int wc = p->weight_mode == MRPNP_W_FULL ? 3 : 2;
     const size_t slot_floats = (size_t)(5 + wc) * p->n_pts;
     size_t slot_bytes = slot_floats * sizeof(float);
@@ -94,7 +117,7 @@ int check_params(const mrpnp_params* p) {
     if (p->layout != MRPNP_LAYOUT_PLANAR && p->layout != MRPNP_LAYOUT_INTERLEAVED)
         return fail(MRPNP_ERR_ARG, "bad layout%s");
     if (p->weight_mode < 0 || p->weight_mode > 2) return fail(MRPNP_ERR_ARG, "bad weight_mode%s");
-    if (p->precision != MRPNP_PREC_FP64 && p->precision != MRPNP_PREC_MIXED) return fail(MRPNP_ERR_ARG, "bad precision%s");
+    if (p->precision < MRPNP_PREC_FP64 || p->precision > MRPNP_PREC_FAST) return fail(MRPNP_ERR_ARG, "bad precision%s");
     if (p->cov_mode < 0 || p->cov_mode > 2) return fail(MRPNP_ERR_ARG, "bad cov_mode%s");
     if (p->init_mode != MRPNP_INIT_GIVEN && p->init_mode != MRPNP_INIT_LINEAR) return fail(MRPNP_ERR_ARG, "bad init_mode%s");
     if (p->cam_stride != 0 && p->cam_stride != 9) return fail(MRPNP_ERR_ARG, "cam_stride must be 0 or 9%s");
@@ -111,6 +134,11 @@ cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan,
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
+    } else if (precision == MRPNP_PREC_FAST) {
+        void (*k)(const KParams) = kp.n_pts == 784 ? mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 0>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
+        if (e != cudaSuccess) return e;
+        k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
     } else {
 #ifdef MRPNP_WITH_PAIR_KERNEL
         auto k = mrpnp::pnp_lm_pair_kernel<WMODE, LAYOUT>;
@@ -124,9 +152,9 @@ cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan,
     return cudaGetLastError();
 }
 
-cudaError_t dispatch(const mrpnp_params* p, const KParams& kp, const LaunchPlan& plan, cudaStream_t stream) {
+cudaError_t dispatch(const mrpnp_params* p, int precision, const KParams& kp, const LaunchPlan& plan, cudaStream_t stream) {
 #define MR_CASE(W, L) \
-    if (p->weight_mode == W && p->layout == L) return launch_one<W, L>(p->precision, kp, plan, stream);
+    if (p->weight_mode == W && p->layout == L) return launch_one<W, L>(precision, kp, plan, stream);
     MR_CASE(MRPNP_W_LOGSTD, MRPNP_LAYOUT_PLANAR)
     MR_CASE(MRPNP_W_ISTD, MRPNP_LAYOUT_PLANAR)
     MR_CASE(MRPNP_W_FULL, MRPNP_LAYOUT_PLANAR)
@@ -151,14 +179,30 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     if (p->n_obj == 0) return MRPNP_OK;
     if (!c3d || !c2d || !wgt || !cam || !range || !result) return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
     if (p->init_mode == MRPNP_INIT_GIVEN && !init) return fail(MRPNP_ERR_ARG, "init_pose is NULL with MRPNP_INIT_GIVEN%s");
+    // MRPNP_PREC_FAST needs compacted inliers (the observations are overwritten by tracked residuals)
+    const int precision = (p->precision == MRPNP_PREC_FAST && !p->inlier_opt_only) ? MRPNP_PREC_MIXED : p->precision;
     LaunchPlan plan;
-    int rc = plan_launch(ctx, p, c3d, dense ? c3d : c2d, wgt, &plan);
+    int rc = plan_launch(ctx, p, precision, c3d, dense ? c3d : c2d, wgt, &plan);
     if (rc != MRPNP_OK) return rc;
     KParams kp;
     kp.c3d = c3d; kp.c2d = c2d; kp.wgt = wgt; kp.cam = cam; kp.range = range; kp.init = init;
     kp.inl_in = inl_in; kp.result = result; kp.inl_out = inl_out; kp.result64 = result64;
-    kp.counters = ctx->counters + 2 * ctx->next_counter;
+    const int set = ctx->next_counter;
+    kp.counters = ctx->counters + kCounterInts * set;
     ctx->next_counter = (ctx->next_counter + 1) % kCounterSets;
+    kp.redo_list = nullptr; kp.redo_count = nullptr; kp.work_list = nullptr; kp.work_count = nullptr;
+    if (precision == MRPNP_PREC_FAST) {
+        if (p->n_obj > ctx->redo_cap) {  // grow the hand-over lists (cudaFree waits for launches still using them)
+            if (ctx->redo_lists) MR_CUDA(cudaFree(ctx->redo_lists));
+            ctx->redo_lists = nullptr;
+            ctx->redo_cap = 0;
+            const int cap = std::max(p->n_obj, 1024);
+            MR_CUDA(cudaMalloc(&ctx->redo_lists, sizeof(int) * (size_t)cap * kCounterSets));
+            ctx->redo_cap = cap;
+        }
+        kp.redo_list = ctx->redo_lists + (size_t)ctx->redo_cap * set;
+        kp.redo_count = kp.counters + 2;
+    }
     kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride;
     kp.cov_mode = p->cov_mode; kp.init_mode = p->init_mode; kp.inlier_opt_only = p->inlier_opt_only;
     kp.max_iter = p->max_iterations; kp.adopt_ftol = p->adopt_candidate_on_ftol;
@@ -184,9 +228,28 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     } else {
         kp.proj_gain2 = 0.f; kp.inv_scaling_denominator = 1.f; kp.distance_min = 0.f;
     }
-    cudaError_t e = dispatch(p, kp, plan, stream);
+    kp.prefetch_distance = plan.ctas * plan.groups;
+    cudaError_t e = dispatch(p, precision, kp, plan, stream);
     if (e != cudaSuccess) return fail(MRPNP_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
     ctx->launches += 1;
+    if (precision == MRPNP_PREC_FAST) {
+        // follow-up launch of the exact kernel over the redo list (normally empty: its CTAs read the count and exit)
+        KParams kr = kp;
+        kr.work_list = kp.redo_list;
+        kr.work_count = kp.redo_count;
+        kr.redo_list = nullptr; kr.redo_count = nullptr;
+        kr.counters = ctx->counters + kCounterInts * ctx->next_counter;
+        ctx->next_counter = (ctx->next_counter + 1) % kCounterSets;
+        LaunchPlan pr;
+        rc = plan_launch(ctx, p, MRPNP_PREC_MIXED, c3d, dense ? c3d : c2d, wgt, &pr);
+        if (rc != MRPNP_OK) return rc;
+        pr.ctas = std::min(pr.ctas, 32);
+        kr.use_tma = pr.use_tma;
+        kr.slot_floats = pr.slot_floats;
+        e = dispatch(p, MRPNP_PREC_MIXED, kr, pr, stream);
+        if (e != cudaSuccess) return fail(MRPNP_ERR_CUDA, "follow-up kernel launch: %s", cudaGetErrorString(e));
+        ctx->launches += 1;
+    }
     return MRPNP_OK;
 }
 
@@ -231,8 +294,8 @@ int mrpnp_create(mrpnp_ctx** out, int device) {
     }
     c->num_sms = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    MR_CUDA(cudaMalloc(&c->counters, sizeof(int) * 2 * kCounterSets));
-    MR_CUDA(cudaMemset(c->counters, 0, sizeof(int) * 2 * kCounterSets));
+    MR_CUDA(cudaMalloc(&c->counters, sizeof(int) * kCounterInts * kCounterSets));
+    MR_CUDA(cudaMemset(c->counters, 0, sizeof(int) * kCounterInts * kCounterSets));
     *out = c;
     return MRPNP_OK;
 }
@@ -246,6 +309,7 @@ void mrpnp_destroy(mrpnp_ctx* c) {
     }
     if (c->small_buf) cudaFree(c->small_buf);
     if (c->counters) cudaFree(c->counters);
+    if (c->redo_lists) cudaFree(c->redo_lists);
     delete c;
 }
 
@@ -256,7 +320,8 @@ int mrpnp_kernel_info(mrpnp_ctx* ctx, const mrpnp_params* p, int32_t info[4]) {
     int rc = check_params(p);
     if (rc != MRPNP_OK) return rc;
     LaunchPlan plan;
-    rc = plan_launch(ctx, p, nullptr, nullptr, nullptr, &plan);
+    const int precision = (p->precision == MRPNP_PREC_FAST && !p->inlier_opt_only) ? MRPNP_PREC_MIXED : p->precision;
+    rc = plan_launch(ctx, p, precision, nullptr, nullptr, nullptr, &plan);
     if (rc != MRPNP_OK) return rc;
     info[0] = plan.warps; info[1] = plan.ctas; info[2] = plan.smem; info[3] = plan.use_tma;
     return MRPNP_OK;

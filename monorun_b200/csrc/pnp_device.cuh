@@ -58,6 +58,13 @@ struct KParams {
     long long pred_stride;    // floats between consecutive objects of all_pred, 0 = pre-sliced maps
     float proj_gain2;       // (ref_focal_y * epistemic_std_gain / scaling_denominator)^2
     float inv_scaling_denominator, distance_min;
+    // MRPNP_PREC_FAST: objects the fast kernel cannot finish (a point near a clip bound) are appended here ...
+    int* redo_list;
+    int* redo_count;
+    // ... and the follow-up launch of the exact kernel reads them back as its work list (NULL = objects 0..n_obj-1)
+    const int* work_list;
+    int* work_count;
+    int prefetch_distance;    // objects between the one a team starts and the one it prefetches into L2
 };
 
 // ------------------------------------------------------------------ PTX wrappers (TMA bulk copy + mbarrier)
@@ -81,6 +88,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
@@ -194,6 +204,54 @@ __device__ __forceinline__ void sincos_small(double d, double* s, double* c) {
     *s = fma(ps * d2, d, d);
     *c = fma(pc, d2, 1.0);
 }
+// Same, also returning cos d - 1 with full relative precision.
+__device__ __forceinline__ void sincos_small(double d, double* s, double* c, double* cm1) {
+    const double d2 = d * d;
+    double ps = -1.0 / 1307674368000.0;
+    ps = fma(ps, d2, 1.0 / 6227020800.0);
+    ps = fma(ps, d2, -1.0 / 39916800.0);
+    ps = fma(ps, d2, 1.0 / 362880.0);
+    ps = fma(ps, d2, -1.0 / 5040.0);
+    ps = fma(ps, d2, 1.0 / 120.0);
+    ps = fma(ps, d2, -1.0 / 6.0);
+    double pc = -1.0 / 87178291200.0;
+    pc = fma(pc, d2, 1.0 / 479001600.0);
+    pc = fma(pc, d2, -1.0 / 3628800.0);
+    pc = fma(pc, d2, 1.0 / 40320.0);
+    pc = fma(pc, d2, -1.0 / 720.0);
+    pc = fma(pc, d2, 1.0 / 24.0);
+    pc = fma(pc, d2, -0.5);
+    *s = fma(ps * d2, d, d);
+    *cm1 = pc * d2;
+    *c = 1.0 + *cm1;
+}
+
+// ------------------------------------------------------------------ which rows of the slot a warp works on
+// After compaction the inliers of an object sit in up to two segments of the slot (one per warp that compacted):
+// segment 0 = points [0, n0), segment 1 = points [base1, base1 + n1).  Their rows of 32 points are numbered through
+// ("virtual rows": rows of segment 0, then rows of segment 1) and dealt round-robin to the `team` warps, so every
+// warp always revisits the same points (it owns their tracked residuals) and the load is balanced to one row.
+// The warp-per-object kernel uses the degenerate form TeamRows(n, 0, 0, 0, 1).
+struct TeamRows {
+    int n0, n1, base1, rows0, rows_total, t, team, safe;
+    __device__ __forceinline__ TeamRows(int n0_, int n1_, int base1_, int t_, int team_)
+        : n0(n0_), n1(n1_), base1(base1_), rows0((n0_ + 31) >> 5), rows_total(((n0_ + 31) >> 5) + ((n1_ + 31) >> 5)),
+          t(t_), team(team_), safe(n0_ > 0 ? 0 : base1_) {}
+    // number of R-row groups this warp runs
+    __device__ __forceinline__ int groups(int R) const {
+        const int mine = rows_total > t ? (rows_total - t + team - 1) / team : 0;
+        return (mine + R - 1) / R;
+    }
+    // slot index of lane `lane` of this warp's row r of group g; invalid lanes get a valid index to read (the
+    // caller zeroes their weights)
+    __device__ __forceinline__ int point(int g, int r, int R, int lane, bool& valid) const {
+        const int v = (g * R + r) * team + t;
+        const bool s1 = v >= rows0;
+        const int k = (s1 ? v - rows0 : v) * 32 + lane;
+        valid = (v < rows_total) && (k < (s1 ? n1 : n0));
+        return valid ? (s1 ? base1 + k : k) : safe;
+    }
+};
 
 template <typename T>
 struct Camera {
@@ -580,7 +638,7 @@ __device__ __forceinline__ bool chol_solve_dense(double A[N][N], const double b[
 // fp32 accumulation of the (well-scaled, normalised-coordinate) normal equations, fp64 solves.
 template <int WMODE, int LAYOUT>
 __device__ __forceinline__ bool linear_init_impl(const float* __restrict__ s3, const float* __restrict__ s2,
-                                            const float* __restrict__ sw, int P, int n, int lane,
+                                            const float* __restrict__ sw, int P, const TeamRows& rows, int lane,
                                             const Camera<float>& cam, float* scratch, double* x) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     const float ifx = 1.f / cam.fx, ify = 1.f / cam.fy;
@@ -588,7 +646,11 @@ __device__ __forceinline__ bool linear_init_impl(const float* __restrict__ s3, c
     float m[16], r[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { m[i] = 0.f; r[i] = 0.f; }
-    for (int p = lane; p < n; p += 32) {
+    const int ngroups = rows.groups(1);
+    for (int gi = 0; gi < ngroups; ++gi) {
+        bool valid;
+        const int p = rows.point(gi, 0, 1, lane, valid);
+        if (!valid) continue;
         const float X = s3[sidx<LAYOUT, 3>(p, 0, P)], Y = s3[sidx<LAYOUT, 3>(p, 1, P)], Z = s3[sidx<LAYOUT, 3>(p, 2, P)];
         const float un = (s2[sidx<LAYOUT, 2>(p, 0, P)] - cam.cx) * ifx;
         const float vn = (s2[sidx<LAYOUT, 2>(p, 1, P)] - cam.cy) * ify;
@@ -628,7 +690,10 @@ __device__ __forceinline__ bool linear_init_impl(const float* __restrict__ s3, c
     float m3[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) m3[i] = 0.f;
-    for (int p = lane; p < n; p += 32) {
+    for (int gi = 0; gi < ngroups; ++gi) {
+        bool valid;
+        const int p = rows.point(gi, 0, 1, lane, valid);
+        if (!valid) continue;
         const float X = s3[sidx<LAYOUT, 3>(p, 0, P)], Y = s3[sidx<LAYOUT, 3>(p, 1, P)], Z = s3[sidx<LAYOUT, 3>(p, 2, P)];
         const float un = (s2[sidx<LAYOUT, 2>(p, 0, P)] - cam.cx) * ifx;
         const float vn = (s2[sidx<LAYOUT, 2>(p, 1, P)] - cam.cy) * ify;
@@ -667,8 +732,8 @@ __device__ __noinline__ bool linear_init(const KParams& kp, int obj, const float
     const int P = kp.n_pts;
     const Camera<float> cam = load_camera<float>(kp, obj);
     double x[4];
-    const bool ok = linear_init_impl<WMODE, LAYOUT>(slot, slot + 3 * P, slot + 5 * P, P, n, lane, cam,
-                                                    reinterpret_cast<float*>(scratch), x);
+    const bool ok = linear_init_impl<WMODE, LAYOUT>(slot, slot + 3 * P, slot + 5 * P, P, TeamRows(n, 0, 0, 0, 1), lane,
+                                                    cam, reinterpret_cast<float*>(scratch), x);
     __syncwarp();
     if (lane == 0) {
 #pragma unroll

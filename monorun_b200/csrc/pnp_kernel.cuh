@@ -239,6 +239,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
     const float* s2 = slot + 3 * P;
     const float* sw = slot + 5 * P;
 
+    // work list: all objects, or (follow-up launch of a FAST solve) the objects the fast kernel handed back
+    int n_work = kp.n_obj;
+    if (kp.work_list) n_work = *reinterpret_cast<const volatile int*>(kp.work_count);
+
     if (lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -250,9 +254,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
 
     while (true) {
         int obj = 0;
-        if (lane == 0) obj = atomicAdd(kp.counters, 1);
+        if (lane == 0) {
+            obj = atomicAdd(kp.counters, 1);
+            if (obj >= n_work) obj = -1;
+            else if (kp.work_list) obj = kp.work_list[obj];
+        }
         obj = __shfl_sync(kFull, obj, 0);
-        if (obj >= kp.n_obj) break;
+        if (obj < 0) break;
 
         const Camera<float> camf = load_camera<float>(kp, obj);
         Camera<double> cam;
@@ -528,6 +536,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
         if (done == (int)gridDim.x - 1) {
             kp.counters[0] = 0;
             kp.counters[1] = 0;
+            if (kp.work_list) *kp.work_count = 0;  // the follow-up launch consumed the redo list
             __threadfence();
         }
     }

@@ -20,7 +20,7 @@ from .registry import PNP, build_pnp  # noqa: F401  (re-exported like monorun.op
 C = _native.CONST
 RESULT_STRIDE = C['MRPNP_RESULT_STRIDE']
 
-_PREC = {'fp64': C['MRPNP_PREC_FP64'], 'mixed': C['MRPNP_PREC_MIXED']}
+_PREC = {'fp64': C['MRPNP_PREC_FP64'], 'mixed': C['MRPNP_PREC_MIXED'], 'fast': C['MRPNP_PREC_FAST']}
 
 _ctx_cache = {}
 

@@ -2,7 +2,8 @@
 seeded inputs, against the committed golden vectors, and through size-independent properties at full size.
 
 Tolerances (BASELINE.json north_star): translation 1e-4 relative, rotation 1e-3 rad.  MRPNP_PREC_FP64 is held to
-1e-9 (it reproduces the fp64 oracle's decisions exactly); MRPNP_PREC_MIXED to the north_star tolerances.
+1e-9 (it reproduces the fp64 oracle's decisions exactly); MRPNP_PREC_MIXED and MRPNP_PREC_FAST to the north_star
+tolerances.
 """
 import os
 
@@ -54,7 +55,7 @@ CASES = [(256, 1, 'identity', 'S0'), (1024, 2, 'diag', 'S0'), (1024, 2, 'diag', 
 
 
 @pytest.mark.parametrize('n,cfg,weights,mode', CASES)
-@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+@pytest.mark.parametrize('precision', ['fp64', 'mixed', 'fast'])
 def test_lm_parity_with_oracle(cuda_lib, oracle, n, cfg, weights, mode, precision):
     """Same inputs, same init, same inlier mask -> same pose, cost and number of evaluations."""
     from monorun_b200 import pnp
@@ -83,7 +84,7 @@ def test_lm_parity_with_oracle(cuda_lib, oracle, n, cfg, weights, mode, precisio
 
 
 @pytest.mark.parametrize('cfg', [1, 2, 3])
-@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+@pytest.mark.parametrize('precision', ['fp64', 'mixed', 'fast'])
 def test_golden_vectors(cuda_lib, cfg, precision):
     """Committed inputs + oracle outputs (tests/golden/make_golden.py); head-level planar tensors, log-std in."""
     from monorun_b200 import pnp
@@ -107,7 +108,7 @@ def test_golden_vectors(cuda_lib, cfg, precision):
     assert rel.max() < 1e-3, rel.max()
 
 
-@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+@pytest.mark.parametrize('precision', ['fp64', 'mixed', 'fast'])
 def test_covariance_masks_against_reference_torch_outputs(cuda_lib, precision):
     """hessian_ref.npz: H from the reference's own hessian.py at fixed poses with z-/uv-clipped points and
     outliers.  The kernel evaluates at init_pose without stepping (max_iterations < 0)."""
@@ -327,7 +328,7 @@ def test_smoke_entry(cuda_lib):
     g.smoke()
 
 
-@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+@pytest.mark.parametrize('precision', ['fp64', 'mixed', 'fast'])
 def test_clipped_points_follow_ceres_jet_semantics(cuda_lib, oracle, precision):
     """A narrow u/v range clamps a good share of the projections (pnp_uncert_cpu.cpp:41-42) and a large z_min clips
     depths (:36): the clamped rows lose their derivative, a clipped depth keeps d/dx' -- same decisions, same pose
@@ -372,7 +373,7 @@ def _unfused_from_raw(raw, b, distance=None, use_dims_var=True):
     return cc, pc, c3, c2, ls
 
 
-@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+@pytest.mark.parametrize('precision', ['fp64', 'mixed', 'fast'])
 @pytest.mark.parametrize('variant', ['dims_var', 'plain', 'distance'])
 def test_fused_head_entry_matches_unfused_sequence(cuda_lib, oracle, precision, variant):
     """mrpnp_solve_dense (decode + variance propagation + RoI grid in the kernel prologue) against the unfused

@@ -10,7 +10,7 @@ for weights, cfg in (('diag', 2), ('full', 3)):
     full = weights == 'full'
     ih, iw = b['img_shape']
     uvr = torch.tensor([[-200., iw + 200., -200., ih + 200.]], device='cuda')
-    for prec in ('fp64', 'mixed'):
+    for prec in ('fp64', 'mixed', 'fast'):
         for layout in ('planar', 'interleaved'):
             if layout == 'planar':
                 args = (t(b['coords_3d']), t(b['coords_2d']), t(b['w_full'] if full else b['logstd']))
@@ -28,6 +28,6 @@ b = synth.make_batch(9, config=2, roi=7)
 op = synth.to_op_level(b)
 res, _, _ = pnp.solve_batched(t(op['coords_3d']), t(op['coords_2d']), t(op['coords_2d_istd']), t(b['cam_mat'][None]),
                               torch.tensor([[550., 650., 150., 220.]], device='cuda'), init_pose=t(b['init_pose']),
-                              layout='interleaved', weight_mode='istd', precision='mixed')
+                              layout='interleaved', weight_mode='istd', precision='fast')
 torch.cuda.synchronize()
 print('clip case valid', res[:, 20].mean().item())
