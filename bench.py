@@ -6,8 +6,9 @@ correspondences, % of the HBM roofline, next to the reference-equivalent CPU pat
 
 A "step" is one pass of the hot path over one batch: 8192 objects per GPU (BASELINE.json configs[2]; configs[4]
 shards 65,536 objects over 8 GPUs = the same 8192 per GPU, so scaling is weak), each with 784 correspondences,
-full 2x2 per-pixel covariance and pose-covariance output.  One kernel launch per step; for N > 1 the step also
-contains the single NCCL all-gather of the [N_local, 24] result rows.  Prints ONE JSON line on rank 0.
+full 2x2 per-pixel covariance and pose-covariance output.  One solver launch per step (precision 'fast': plus the
+follow-up launch of the exact kernel over the -- normally empty -- redo list); for N > 1 the step also contains the
+single NCCL all-gather of the [N_local, 24] result rows.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -165,7 +166,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--workload', choices=['full', 'diag'], default='full')
-    ap.add_argument('--precision', choices=['mixed', 'fp64'], default='mixed')
+    ap.add_argument('--precision', choices=['fast', 'mixed', 'fp64'], default='fast')
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--streams', type=int, default=2, help='CUDA streams the K timed steps alternate between')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -327,8 +328,9 @@ def main():
         line = {
             'metric': METRIC, 'value': n_total * args.steps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 residual/cost + f32 Jacobian'
-            if args.precision == 'mixed' else 'f64', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'fast': 'f32 (residuals evaluated once in f64, then tracked in f32; f64 covariance)',
+                      'mixed': 'f64 residual/cost + f32 Jacobian', 'fp64': 'f64'}[args.precision], 'data': 'synthetic',
             'config': {'workload': workload_name(args.workload), 'objects_per_gpu': n_local, 'points_per_object': 784,
                        'precision': args.precision, 'init': 'ground truth perturbed (5e-2 rad, 2% depth), shared with the oracle',
                        'l2': 'two alternating input sets of %.0f MB each (> 126 MB L2)' % (alg / 1e6),
@@ -341,7 +343,8 @@ def main():
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(args.workload), 'peak_source': peak_src,
-                         'kernel': 'mrpnp::pnp_lm_kernel', 'kernel_ms': kernel_ms,
+                         'kernel': 'mrpnp::pnp_lm_fast_kernel' if args.precision == 'fast' else 'mrpnp::pnp_lm_kernel',
+                         'kernel_ms': kernel_ms,
                          'algorithmic_bytes_per_object': ALG_BYTES[args.workload], 'objects_per_launch': n_local},
             'lm_iterations_histogram': hist, 'valid_fraction': valid_frac, 'parity_check': parity,
         }

@@ -5,8 +5,8 @@
 // cost(x) - cost(x + delta) and stop at |change| <= 1e-6 cost, so that difference has to be right to ~1e-4 of ITSELF.
 // Recomputing residuals in fp32 at every point cannot deliver that (1e-4 px rounding on ~1 px residuals), which is why
 // MRPNP_PREC_MIXED keeps the whole residual chain in fp64.  Here the residuals are evaluated ONCE per object in fp64
-// (at the initial point, eval_pass_first) and kept in shared memory in place of the observations; every later
-// evaluation computes only the CHANGE of each residual between the accepted point x and the candidate x + delta, from
+// (at the point reached by the first step, eval_pass_first) and kept in shared memory in place of the observations;
+// every later evaluation computes only the CHANGE of each residual between the accepted point x and the candidate x + delta, from
 // formulas in which every operand is small when the step is small:
 //
 //     q'  = R_y(yaw') X,  x' = q' + t'                      (candidate camera-frame point, plain fp32)
@@ -66,25 +66,29 @@ __device__ __forceinline__ float warp_reduce16_scatter(float v[16], int lane) {
     return v[0] + __shfl_xor_sync(kFull, v[0], 1);
 }
 
-// ------------------------------------------------------------------ first evaluation (fp64 residual chain)
-// As eval_pass_mixed (fp64 residual + cost, fp32 Jacobian sums), and it replaces the observations in the slot by the
-// residuals the delta passes track: diagonal weights store r = w d and fold the focal lengths into the weights
-// (w_u fx, w_v fy); full weights store the pixel differences d themselves.
+// ------------------------------------------------------------------ evaluations from the observations
+// The two evaluations that read the observations (u, v) instead of tracked residuals:
+//   anchor == false  the very first one, at the initial point: plain fp32 (residuals of many pixels there: the 1e-4 px
+//                    rounding of an fp32 projection is irrelevant, and the decision on the first step is never close);
+//   anchor == true   the second one, at the point after the first step: the residual chain runs in fp64 (as in
+//                    eval_pass_mixed) and the residuals REPLACE the observations in the slot -- the delta passes track
+//                    them from here on.  Diagonal weights store r = w d and fold the focal lengths into the weights
+//                    (w_u fx, w_v fy); full weights store the pixel differences d themselves.
+// Anchoring after the first (large) step instead of at the initial point matters: a delta pass leaves ~1e-7 of the
+// residual CHANGE behind as a fixed error of the tracked residuals, and only the first step changes them by many pixels.
 // Out: per-lane partial sums a[0..13] (J^T r, J^T J; layout of eval_pass_fp64 minus the cost), a[14] = this lane's
 // share of sum |r|^2, a[15] = 0; flagged = some point is within the margin of a clip bound.
 template <int WMODE, int LAYOUT>
-__device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, float* sw, int P, int n, int lane,
-                                                const double x[4], double sn, double cs, const Camera<double>& cam,
-                                                const Camera<float>& camf, float a[16], bool& flagged) {
+__device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, float* sw, int P, int n, int lane, bool anchor,
+                                                const float x[4], float snf, float csf, const Camera<float>& camf,
+                                                float a[16], bool& flagged) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
-    constexpr int R = 1;
-    const double tx = x[1], ty = x[2], tz = x[3];
-    const float snf = (float)sn, csf = (float)cs, txf = (float)tx, tyf = (float)ty, tzf = (float)tz;
+    constexpr int R = 2;
+    const float txf = x[1], tyf = x[2], tzf = x[3];
+    const double sn = (double)snf, cs = (double)csf, tx = (double)txf, ty = (double)tyf, tz = (double)tzf;
+    const double fx = (double)camf.fx, fy = (double)camf.fy, cx = (double)camf.cx, cy = (double)camf.cy;
     const float zlo = camf.z_min * 1.001f + 1e-3f;
     const float ulo = camf.u_min + 0.05f, uhi = camf.u_max - 0.05f, vlo = camf.v_min + 0.05f, vhi = camf.v_max - 0.05f;
-    double cost[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) cost[r] = 0.0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = 0.f;
     float margin = 1e30f;
@@ -106,24 +110,8 @@ __device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, floa
             w2[r] = (WMODE == MRPNP_W_FULL) ? sw[sidx<LAYOUT, WC>(p, WC - 1, P)] : 0.f;
             if (!valid[r]) { w0[r] = 0.f; w1[r] = 0.f; w2[r] = 0.f; }
         }
-        // ---- fp64 residual chain ----
-        double xc[R], yc[R], zc[R], iz[R], du[R], dv[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const double X = (double)Xf[r], Y = (double)Yf[r], Z = (double)Zf[r];
-            xc[r] = fma(cs, X, fma(sn, Z, tx));
-            zc[r] = fma(cs, Z, fma(-sn, X, tz));
-            yc[r] = Y + ty;
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) iz[r] = fast_rcp(zc[r]);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            du[r] = fma(cam.fx, xc[r] * iz[r], cam.cx) - (double)uf[r];
-            dv[r] = fma(cam.fy, yc[r] * iz[r], cam.cy) - (double)vf[r];
-        }
-        // ---- fp32 projection: Jacobian + clip detection ----
-        float qxf[R], qzf[R], izf[R], xnf[R], ynf[R];
+        // ---- fp32 projection: Jacobian, clip detection, (first evaluation) residuals ----
+        float qxf[R], qzf[R], izf[R], xnf[R], ynf[R], euf[R], evf[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             qxf[r] = fmaf(csf, Xf[r], snf * Zf[r]);
@@ -135,6 +123,21 @@ __device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, floa
             ynf[r] = (Yf[r] + tyf) * izf[r];
             const float puf = fmaf(camf.fx, xnf[r], camf.cx), pvf = fmaf(camf.fy, ynf[r], camf.cy);
             margin = fminf(margin, fminf(fminf(puf - ulo, uhi - puf), fminf(pvf - vlo, vhi - pvf)));
+            euf[r] = puf - uf[r];
+            evf[r] = pvf - vf[r];
+        }
+        if (anchor) {
+            // ---- fp64 residual chain: the pixel differences to ~1e-13 px before they are rounded to fp32 ----
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double X = (double)Xf[r], Y = (double)Yf[r], Z = (double)Zf[r];
+                const double xc = fma(cs, X, fma(sn, Z, tx));
+                const double zc = fma(cs, Z, fma(-sn, X, tz));
+                const double yc = Y + ty;
+                const double iz = fast_rcp(zc);
+                euf[r] = (float)(fma(fx, xc * iz, cx) - (double)uf[r]);
+                evf[r] = (float)(fma(fy, yc * iz, cy) - (double)vf[r]);
+            }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -142,10 +145,9 @@ __device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, floa
             const float bu = -au * xnf[r], bv = -av * ynf[r];
             const float ju0 = fmaf(au, qzf[r], -bu * qxf[r]), jv0 = -bv * qxf[r];
             if (WMODE != MRPNP_W_FULL) {
-                const double ru = (double)w0[r] * du[r], rv = (double)w1[r] * dv[r];
-                cost[r] = fma(ru, ru, fma(rv, rv, cost[r]));
-                const float ruf = (float)ru, rvf = (float)rv;
-                if (valid[r]) {
+                const float ruf = w0[r] * euf[r], rvf = w1[r] * evf[r];
+                a[14] = fmaf(ruf, ruf, fmaf(rvf, rvf, a[14]));
+                if (anchor && valid[r]) {
                     s2[sidx<LAYOUT, 2>(pidx[r], 0, P)] = ruf; s2[sidx<LAYOUT, 2>(pidx[r], 1, P)] = rvf;
                     sw[sidx<LAYOUT, WC>(pidx[r], 0, P)] = w0[r] * camf.fx;
                     sw[sidx<LAYOUT, WC>(pidx[r], 1, P)] = w1[r] * camf.fy;
@@ -166,12 +168,9 @@ __device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, floa
                 a[12] = fmaf(b2, b3, a[12]);
                 a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
             } else {
-                const double r0 = fma((double)w0[r], du[r], (double)w1[r] * dv[r]);
-                const double r1 = fma((double)w1[r], du[r], (double)w2[r] * dv[r]);
-                cost[r] = fma(r0, r0, fma(r1, r1, cost[r]));
-                const float euf = (float)du[r], evf = (float)dv[r];
-                if (valid[r]) { s2[sidx<LAYOUT, 2>(pidx[r], 0, P)] = euf; s2[sidx<LAYOUT, 2>(pidx[r], 1, P)] = evf; }
-                const float r0f = fmaf(w0[r], euf, w1[r] * evf), r1f = fmaf(w1[r], euf, w2[r] * evf);
+                if (anchor && valid[r]) { s2[sidx<LAYOUT, 2>(pidx[r], 0, P)] = euf[r]; s2[sidx<LAYOUT, 2>(pidx[r], 1, P)] = evf[r]; }
+                const float r0f = fmaf(w0[r], euf[r], w1[r] * evf[r]), r1f = fmaf(w1[r], euf[r], w2[r] * evf[r]);
+                a[14] = fmaf(r0f, r0f, fmaf(r1f, r1f, a[14]));
                 const float a0 = fmaf(w0[r], ju0, w1[r] * jv0), a1 = w0[r] * au, a2 = w1[r] * av, a3 = fmaf(w0[r], bu, w1[r] * bv);
                 const float b0 = fmaf(w1[r], ju0, w2[r] * jv0), b1 = w1[r] * au, b2 = w2[r] * av, b3 = fmaf(w1[r], bu, w2[r] * bv);
                 a[0] = fmaf(a0, r0f, fmaf(b0, r1f, a[0]));
@@ -192,10 +191,6 @@ __device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, floa
         }
     }
     flagged = __any_sync(kFull, !(margin >= 0.f));
-    double c = cost[0];
-#pragma unroll
-    for (int r = 1; r < R; ++r) c += cost[r];
-    a[14] = (float)c;  // positive terms: the fp32 cross-lane sum keeps ~1e-7 relative accuracy
 }
 
 // ------------------------------------------------------------------ candidate evaluation (fp32 delta pass)

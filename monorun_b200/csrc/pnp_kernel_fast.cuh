@@ -66,6 +66,39 @@ __device__ __noinline__ void stage_object_plain(const KParams& kp, int obj, floa
     __syncwarp();
 }
 
+// Take the next object off the work counter and start its bulk copies into the slot (lane 0 issues; the caller has
+// made sure that every lane is done with the slot).  Returns the object index or -1.
+template <int WC>
+__device__ __forceinline__ int fetch_and_stage(const KParams& kp, float* slot, int P, uint64_t* bar, int lane) {
+    int obj = 0;
+    if (lane == 0) {
+        obj = atomicAdd(kp.counters, 1);
+        if (obj >= kp.n_obj) obj = -1;
+        if (obj >= 0 && kp.use_tma) {
+            const float *g3, *g2, *gw;
+            object_slabs<WC>(kp, obj, g3, g2, gw);
+            fence_proxy_async();  // order our generic-proxy accesses before the async-proxy writes
+            if (kp.dense) {
+                mbar_expect_tx(bar, (uint32_t)(5 * P * sizeof(float)));
+                bulk_g2s(slot, g3, (uint32_t)(3 * P * sizeof(float)), bar);
+                bulk_g2s(slot + 5 * P, gw, (uint32_t)(2 * P * sizeof(float)), bar);
+            } else {
+                mbar_expect_tx(bar, (uint32_t)((5 + WC) * P * sizeof(float)));
+                bulk_g2s(slot, g3, (uint32_t)(3 * P * sizeof(float)), bar);
+                bulk_g2s(slot + 3 * P, g2, (uint32_t)(2 * P * sizeof(float)), bar);
+                bulk_g2s(slot + 5 * P, gw, (uint32_t)(WC * P * sizeof(float)), bar);
+            }
+        }
+    }
+    return __shfl_sync(kFull, obj, 0);
+}
+
+__device__ __forceinline__ float fast_ex2(float a) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    return y;
+}
+
 // weights -> inverse std in place (uncert_prop_pnp_optimizer.py:73) and the per-axis sums for the inlier thresholds
 // (pnp_uncert_cpu.py:164-165)
 template <int WMODE, int LAYOUT>
@@ -75,12 +108,12 @@ __device__ __forceinline__ void fast_weights(const KParams& kp, float* sw, int P
     // exp(-l) / s = exp2(-l log2(e) - log2(s)): one FFMA + one MUFU.EX2 per weight
     const float k2 = -1.4426950408889634f, off = -__log2f(kp.std_scale);
     su = 0.f; sv = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int p = lane; p < P; p += 32) {
         float wu = sw[sidx<LAYOUT, WC>(p, 0, P)], wv = sw[sidx<LAYOUT, WC>(p, CV, P)];
         if (WMODE == MRPNP_W_LOGSTD) {
-            wu = exp2f(fmaf(wu, k2, off));
-            wv = exp2f(fmaf(wv, k2, off));
+            wu = fast_ex2(fmaf(wu, k2, off));
+            wv = fast_ex2(fmaf(wv, k2, off));
             sw[sidx<LAYOUT, WC>(p, 0, P)] = wu;
             sw[sidx<LAYOUT, WC>(p, CV, P)] = wv;
         }
@@ -101,14 +134,14 @@ __device__ __noinline__ void fast_dense_decode(const KParams& kp, int obj, float
 }
 
 // Inlier decision + packed inlier_out + in-place order-preserving compaction (boolean-mask indexing of
-// pnp_uncert_cpu.py:24-27,62-66).  Rows are handled two at a time: two independent load batches, one warp barrier,
-// two store batches.  Returns the number of inliers.
+// pnp_uncert_cpu.py:24-27,62-66).  Rows are handled four at a time: four independent load batches, one warp barrier,
+// four store batches.  Returns the number of inliers.
 template <int WMODE, int LAYOUT>
 __device__ __forceinline__ int fast_mask_and_compact(const KParams& kp, int obj, float* slot, int P, int lane, float thr_u,
                                                      float thr_v, bool all_inliers) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     constexpr int CV = WC - 1;
-    constexpr int U = 2;
+    constexpr int U = 4;
     float* s3 = slot;
     float* s2 = slot + 3 * P;
     float* sw = slot + 5 * P;
@@ -277,8 +310,14 @@ __device__ __forceinline__ void ldl4f_solve(const Ldl4f& f, const float b[4], fl
     y[0] = fmaf(-f.l30, y[3], fmaf(-f.l20, y[2], fmaf(-f.l10, y[1], z0 * f.i0)));
 }
 
-// sin, cos - 1 of a yaw step: |d| <= 0.5 by polynomial (relative error < 1e-8), otherwise the library routine
-__device__ __forceinline__ void yaw_step_sincos(float d, float& sd, float& cdm1) {
+// sin(d) and cos(d) - 1 with fp32 RELATIVE accuracy: polynomials for |d| <= 0.5 (every yaw step but a wild first one;
+// truncation < 1e-8), the library routine -- out of line, it is ~100 instructions -- otherwise and for the initial yaw.
+__device__ __noinline__ void sincos_cold(float d, float* sd, float* cdm1) {
+    float cd;
+    sincosf(d, sd, &cd);
+    *cdm1 = cd - 1.f;
+}
+__device__ __forceinline__ void sincos_cm1(float d, float& sd, float& cdm1) {
     if (fabsf(d) <= 0.5f) {
         const float d2 = d * d;
         float ps = fmaf(d2, 2.7557319e-6f, -1.9841270e-4f);   // 1/9!, -1/7!
@@ -291,9 +330,7 @@ __device__ __forceinline__ void yaw_step_sincos(float d, float& sd, float& cdm1)
         pc = fmaf(pc, d2, -0.5f);
         cdm1 = pc * d2;
     } else {
-        float cd;
-        sincosf(d, &sd, &cd);
-        cdm1 = cd - 1.f;
+        sincos_cold(d, &sd, &cdm1);
     }
 }
 
@@ -331,12 +368,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
     __syncwarp();
     uint32_t parity = 0;
 
+    // The bulk copies of an object are started as soon as the slot is free, i.e. BEFORE the covariance / result row of
+    // the previous object, so that part of the staging latency is hidden behind it.
+    int obj = fetch_and_stage<WC>(kp, slot, P, bar, lane);
 #pragma unroll 1
-    while (true) {
-        int obj = 0;
-        if (lane == 0) obj = atomicAdd(kp.counters, 1);
-        obj = __shfl_sync(kFull, obj, 0);
-        if (obj >= kp.n_obj) break;
+    while (obj >= 0) {
         TR_DECL
         const Camera<float> camf = load_camera<float>(kp, obj);
 
@@ -344,21 +380,23 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
         int n = P;
 #pragma unroll 1
         for (int attempt = 0; attempt < 2; ++attempt) {
-            __syncwarp();  // every lane is done with the previous contents of the slot
             if (kp.use_tma) {
-                if (lane == 0) {
-                    const float *g3, *g2, *gw;
-                    object_slabs<WC>(kp, obj, g3, g2, gw);
-                    fence_proxy_async();  // order our generic-proxy accesses before the async-proxy writes
-                    if (kp.dense) {
-                        mbar_expect_tx(bar, (uint32_t)(5 * P * sizeof(float)));
-                        bulk_g2s(s3, g3, (uint32_t)(3 * P * sizeof(float)), bar);
-                        bulk_g2s(sw, gw, (uint32_t)(2 * P * sizeof(float)), bar);
-                    } else {
-                        mbar_expect_tx(bar, (uint32_t)((5 + WC) * P * sizeof(float)));
-                        bulk_g2s(s3, g3, (uint32_t)(3 * P * sizeof(float)), bar);
-                        bulk_g2s(s2, g2, (uint32_t)(2 * P * sizeof(float)), bar);
-                        bulk_g2s(sw, gw, (uint32_t)(WC * P * sizeof(float)), bar);
+                if (attempt) {  // re-stage the same object (the first attempt compacted the slot)
+                    __syncwarp();
+                    if (lane == 0) {
+                        const float *g3, *g2, *gw;
+                        object_slabs<WC>(kp, obj, g3, g2, gw);
+                        fence_proxy_async();
+                        if (kp.dense) {
+                            mbar_expect_tx(bar, (uint32_t)(5 * P * sizeof(float)));
+                            bulk_g2s(s3, g3, (uint32_t)(3 * P * sizeof(float)), bar);
+                            bulk_g2s(sw, gw, (uint32_t)(2 * P * sizeof(float)), bar);
+                        } else {
+                            mbar_expect_tx(bar, (uint32_t)((5 + WC) * P * sizeof(float)));
+                            bulk_g2s(s3, g3, (uint32_t)(3 * P * sizeof(float)), bar);
+                            bulk_g2s(s2, g2, (uint32_t)(2 * P * sizeof(float)), bar);
+                            bulk_g2s(sw, gw, (uint32_t)(WC * P * sizeof(float)), bar);
+                        }
                     }
                 }
                 mbar_wait(bar, parity);
@@ -400,7 +438,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[i] = pt[i];
         float sn_x, cs_x;
-        sincosf(pt[0], &sn_x, &cs_x);
+        sincos_cold(pt[0], &sn_x, &cs_x);
+        cs_x += 1.f;
         float sn_p = sn_x, cs_p = cs_x;
         TR_MARK(2)
 
@@ -421,11 +460,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
             // ---- the fused pass at pt: 15 sums, transposed warp reduction, broadcast through the scratch ----
             float a[16];
             bool flagged;
-            if (first) {
-                Camera<double> cam;
-                cam.fx = camf.fx; cam.fy = camf.fy; cam.cx = camf.cx; cam.cy = camf.cy;
-                const double ptd[4] = {(double)pt[0], (double)pt[1], (double)pt[2], (double)pt[3]};
-                eval_pass_first<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, ptd, (double)sn_p, (double)cs_p, cam, camf, a, flagged);
+            const bool from_observations = cost_evals < 2;  // initial point (plain fp32), then the fp64 anchor
+            if (from_observations) {
+                eval_pass_first<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, cost_evals == 1, pt, sn_p, cs_p, camf, a, flagged);
             } else {
                 eval_pass_delta<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, dstep, camf, cwin, a, flagged);
             }
@@ -435,10 +472,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
             __syncwarp();
             if ((lane & 1) == 0) scratch[lane >> 1] = tot;
             __syncwarp();
-            TR_MARK(first ? 3 : 4)
+            TR_MARK(from_observations ? 3 : 4)
             if (flagged) { redo = true; break; }
             ++cost_evals;
-            const float c_term = scratch[14];  // first: sum |r|^2; afterwards: its change
+            const float c_term = scratch[14];  // first two evaluations: sum |r|^2; afterwards: its change
             const bool cfinite = fabsf(c_term) < kFltMax;
             const bool jfinite = jfin && cfinite;
             bool accept = false;
@@ -453,7 +490,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
                 const float ptol = (float)kParameterTol * (x_norm + (float)kParameterTol);
                 if (step_norm2 <= ptol * ptol) { term = kConvergence; break; }
                 // FunctionToleranceReached (Ceres 1.14: the candidate is not adopted on this exit)
-                const float cost_change = cfinite ? -0.5f * c_term : -kFltMax;  // cost - candidate cost
+                // cost - candidate cost
+                const float cost_change = !cfinite ? -kFltMax : (from_observations ? cost - 0.5f * c_term : -0.5f * c_term);
                 bool stop_after = false;
                 if (fabsf(cost_change) <= (float)kFunctionTol * cost) {
                     term = kConvergence;
@@ -464,7 +502,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
                 if (stop_after || rho > (float)kMinRelDecrease) {  // HandleSuccessfulStep
                     if (!jfinite) { term = kFailure; break; }
                     accept = true;
-                    cost -= cost_change;
+                    cost = from_observations ? 0.5f * c_term : cost - cost_change;
                     const float q = 2.f * rho - 1.f;
                     radius = fminf((float)kMaxRadius, radius * fast_rcp(fmaxf(1.f / 3.f, 1.f - q * q * q)));
                     decrease_factor = 2.f;
@@ -480,6 +518,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
                     radius = radius * fast_rcp(decrease_factor);
                     decrease_factor *= 2.f;
                     TR_MARK(5)
+                    // the slot holds the residuals at the rejected candidate (also after the anchor evaluation)
                     undo_pass_delta<WMODE, LAYOUT>(slot, P, n, lane, dstep, camf.fx, camf.fy);
                     TR_MARK(6)
                 }
@@ -558,7 +597,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
             if (stop) { TR_MARK(5) break; }
             // rotation at the candidate by angle addition; the same sin / cos - 1 of the yaw step drive the delta pass
             float sd, cdm1;
-            yaw_step_sincos(delta[0], sd, cdm1);
+            sincos_cm1(delta[0], sd, cdm1);
             sn_p = fmaf(sn_x, cdm1, fmaf(cs_x, sd, sn_x));
             cs_p = fmaf(cs_x, cdm1, fmaf(-sn_x, sd, cs_x));
             dstep.cp = cs_p; dstep.sp = sn_p;
@@ -567,12 +606,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
             dstep.dtx = delta[1]; dstep.dty = delta[2]; dstep.dtz = delta[3];
             TR_MARK(5)
         }
+        // the slot is free: start staging the next object before finishing this one
+        __syncwarp();
+        const int next_obj = fetch_and_stage<WC>(kp, slot, P, bar, lane);
         if (redo) {  // a point near a clip bound: the exact kernel solves this object
             if (lane == 0) kp.redo_list[atomicAdd(kp.redo_count, 1)] = obj;
+            obj = next_obj;
             continue;
         }
         // ---------------- pose covariance + result row (out of line, fp64) ----------------
-        __syncwarp();
         if (lane == 0) {  // every lane holds the same H and x
 #pragma unroll
             for (int i = 0; i < 10; ++i) scratch[i] = H[i];
@@ -590,6 +632,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
             tr[11] = (double)tr_t0; tr[12] = (double)tr_t; tr[13] = (double)blockIdx.x; tr[14] = (double)warp;
         }
 #endif
+        obj = next_obj;
     }
 
     // self-resetting work counters: the last CTA to finish rearms them for the next launch

@@ -92,7 +92,7 @@ def _ptr(t, ctype='float*'):
 
 def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None, inlier_mask=None, *,
                   layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, istd_thres=0.6,
-                  inlier_opt_only=True, cov_mode='pipeline', precision='mixed', max_iterations=50,
+                  inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
                   adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False):
     """Batched uncertainty-PnP on device tensors -- direct wrapper of ``mrpnp_solve``.
 
@@ -145,7 +145,7 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
 
 def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, *, noc_mean, noc_std, focal_gain,
                 scaling_denominator, distance=None, distance_min=0.1, init_pose=None, z_min=0.5, std_scale=10.0,
-                istd_thres=0.6, inlier_opt_only=True, cov_mode='pipeline', precision='mixed', max_iterations=50,
+                istd_thres=0.6, inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
                 return_inlier_mask=True, labels=None, num_classes=0):
     """Fused head -> PnP launch -- direct wrapper of ``mrpnp_solve_dense``: the dense head's raw class-sliced
     ``noc_pred`` [N,3,H,W] and ``proj_logstd`` [N,2,H,W], the detection boxes ``rois`` [N,4|5] and the decoded
@@ -221,7 +221,7 @@ def solve_host(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None
         n, n_pts, layout=C['MRPNP_LAYOUT_PLANAR'] if layout == 'planar' else C['MRPNP_LAYOUT_INTERLEAVED'],
         weight_mode=wmode, cam_stride=9 if cam.shape[0] == n and n > 1 else 0,
         range_stride=4 if rng.shape[0] == n and n > 1 else 0,
-        precision=_PREC[kw.get('precision', 'mixed')],
+        precision=_PREC[kw.get('precision', 'fast')],
         cov_mode={'none': 0, 'pipeline': 1, 'ceres': 2}[kw.get('cov_mode', 'pipeline')],
         init_mode=C['MRPNP_INIT_GIVEN'] if init_pose is not None else C['MRPNP_INIT_LINEAR'],
         z_min=float(kw.get('z_min', 0.5)), std_scale=float(kw.get('std_scale', 10.0)),
@@ -245,7 +245,7 @@ def _unpack(result, inlier_mask):
 
 def pnp_uncert(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range, z_min=0.5, epnp_istd_thres=1.0,
                epnp_ransac_thres=None, inlier_opt_only=False, forward_exact_hessian=False, use_6dof=False,
-               init_pose=None, precision='mixed'):
+               init_pose=None, precision='fast'):
     """Drop-in for monorun/ops/least_squares/pnp_uncert.py:7-87.
 
     Args (as in the reference):
@@ -284,7 +284,7 @@ class PnPUncert(torch.nn.Module):
     """Drop-in for monorun/ops/least_squares/pnp_uncert.py:90-142 (same constructor kwargs and forward)."""
 
     def __init__(self, z_min=0.5, epnp_istd_thres=0.6, inlier_opt_only=True, coord_istd_normalize=False,
-                 forward_exact_hessian=False, use_6dof=False, eps=1e-6, precision='mixed'):
+                 forward_exact_hessian=False, use_6dof=False, eps=1e-6, precision='fast'):
         super(PnPUncert, self).__init__()
         self.z_min = z_min
         self.epnp_istd_thres = epnp_istd_thres
