@@ -8,6 +8,9 @@
 #include "monorun_pnp.h"
 #include "pnp_kernel.cuh"
 #include "pnp_kernel_fast.cuh"
+#ifdef MRPNP_WITH_PAIR_FAST  // two warps per object: measured slower, kept for reference
+#include "pnp_kernel_fast2.cuh"
+#endif
 #include <stdlib.h>
 #ifdef MRPNP_WITH_PAIR_KERNEL  // experiment kept for reference, see DESIGN.md section 5
 #include "pnp_kernel_pair.cuh"
@@ -59,20 +62,35 @@ struct LaunchPlan {
     int warps, groups, ctas, smem, use_tma, slot_floats, team;
 };
 
+// warps per object of the MRPNP_PREC_FAST kernel: 1, or (experiment build only) MRPNP_TEAM=2 from the environment
+int team_size() {
+#ifdef MRPNP_WITH_PAIR_FAST
+    static const int team = [] {
+        const char* e = getenv("MRPNP_TEAM");
+        return (e && atoi(e) == 2) ? 2 : 1;
+    }();
+    return team;
+#else
+    return 1;
+#endif
+}
+
 int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, int precision, const void* c3d, const void* c2d,
                 const void* wgt, LaunchPlan* plan) {
     if (precision == MRPNP_PREC_FAST) {
         const int wc = p->weight_mode == MRPNP_W_FULL ? 3 : 2;
         size_t slot_bytes = ((size_t)(5 + wc) * p->n_pts * sizeof(float) + 15) & ~size_t(15);
-        int groups = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, (size_t)ctx->max_smem_optin / (slot_bytes + mrpnp::kFastHeaderBytes));
+        const int team = team_size();
+        const size_t header = team == 2 ? 512 : mrpnp::kFastHeaderBytes;
+        int groups = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, (size_t)ctx->max_smem_optin / (slot_bytes + header));
         if (groups < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
         const int per_sm = (p->n_obj + ctx->num_sms - 1) / ctx->num_sms;
         groups = std::max(1, std::min(groups, per_sm));
-        plan->team = 1;
-        plan->warps = groups;
+        plan->team = team;
+        plan->warps = groups * plan->team;
         plan->groups = groups;
         plan->ctas = std::min(ctx->num_sms, (p->n_obj + groups - 1) / groups);
-        plan->smem = (int)(groups * (slot_bytes + mrpnp::kFastHeaderBytes));
+        plan->smem = (int)(groups * (slot_bytes + header));
         plan->slot_floats = (int)(slot_bytes / sizeof(float));
         const bool aligned = (p->n_pts % 4 == 0) && (((uintptr_t)c3d | (uintptr_t)c2d | (uintptr_t)wgt) % 16 == 0);
         plan->use_tma = aligned ? 1 : 0;
@@ -136,6 +154,9 @@ cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan,
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
     } else if (precision == MRPNP_PREC_FAST) {
         void (*k)(const KParams) = kp.n_pts == 784 ? mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 0>;
+#ifdef MRPNP_WITH_PAIR_FAST
+        if (plan.team == 2) k = kp.n_pts == 784 ? mrpnp::pnp_lm_fast2_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_fast2_kernel<WMODE, LAYOUT, 0>;
+#endif
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);

@@ -35,6 +35,38 @@ struct DeltaStep {
     float dtx, dty, dtz;           // t' - t
 };
 
+// Which rows of the slot a warp works on.  RowMap<1>: one warp owns all n compacted points.  RowMap<2>: two warps
+// share an object; each compacted its own half of the rows, so the inliers sit in two segments [0, n0) and
+// [base1, base1 + n1) whose rows of 32 points are numbered through and dealt alternately to the two warps (every
+// warp always revisits the same points: it owns their tracked residuals; the load is balanced to one row).
+template <int TEAM> struct RowMap;
+template <> struct RowMap<1> {
+    int n;
+    __device__ __forceinline__ int groups(int R) const { return (((n + 31) >> 5) + R - 1) / R; }
+    __device__ __forceinline__ int point(int g, int r, int R, int lane, bool& valid) const {
+        const int pr = (g * R + r) * 32 + lane;
+        valid = pr < n;
+        return valid ? pr : 0;
+    }
+};
+template <> struct RowMap<2> {
+    int n0, n1, base1, rows0, rows_total, t, safe;
+    __device__ __forceinline__ RowMap(int n0_, int n1_, int base1_, int t_)
+        : n0(n0_), n1(n1_), base1(base1_), rows0((n0_ + 31) >> 5), rows_total(((n0_ + 31) >> 5) + ((n1_ + 31) >> 5)),
+          t(t_), safe(n0_ > 0 ? 0 : base1_) {}
+    __device__ __forceinline__ int groups(int R) const {
+        const int mine = rows_total > t ? (rows_total - t + 1) >> 1 : 0;
+        return (mine + R - 1) / R;
+    }
+    __device__ __forceinline__ int point(int g, int r, int R, int lane, bool& valid) const {
+        const int v = (g * R + r) * 2 + t;
+        const bool s1 = v >= rows0;
+        const int k = (s1 ? v - rows0 : v) * 32 + lane;
+        valid = (v < rows_total) && (k < (s1 ? n1 : n0));
+        return valid ? (s1 ? base1 + k : k) : safe;
+    }
+};
+
 // Clip window in normalised coordinates with the safety margins of eval_pass_mixed (0.05 px, z_min * 1.001 + 1e-3).
 struct ClipWindow {
     float xmid, xhalf, ymid, yhalf, zlo;
@@ -78,12 +110,11 @@ __device__ __forceinline__ float warp_reduce16_scatter(float v[16], int lane) {
 // residual CHANGE behind as a fixed error of the tracked residuals, and only the first step changes them by many pixels.
 // Out: per-lane partial sums a[0..13] (J^T r, J^T J; layout of eval_pass_fp64 minus the cost), a[14] = this lane's
 // share of sum |r|^2, a[15] = 0; flagged = some point is within the margin of a clip bound.
-template <int WMODE, int LAYOUT>
-__device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, float* sw, int P, int n, int lane, bool anchor,
-                                                const float x[4], float snf, float csf, const Camera<float>& camf,
-                                                float a[16], bool& flagged) {
+template <int WMODE, int LAYOUT, int R = 2, class ROWS = RowMap<1>>
+__device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, float* sw, int P, const ROWS rows, int lane,
+                                                bool anchor, const float x[4], float snf, float csf,
+                                                const Camera<float>& camf, float a[16], bool& flagged) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
-    constexpr int R = 2;
     const float txf = x[1], tyf = x[2], tzf = x[3];
     const double sn = (double)snf, cs = (double)csf, tx = (double)txf, ty = (double)tyf, tz = (double)tzf;
     const double fx = (double)camf.fx, fy = (double)camf.fy, cx = (double)camf.cx, cy = (double)camf.cy;
@@ -92,7 +123,7 @@ __device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, floa
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = 0.f;
     float margin = 1e30f;
-    const int ngroups = (((n + 31) >> 5) + R - 1) / R;
+    const int ngroups = rows.groups(R);
 #pragma unroll 1
     for (int g = 0; g < ngroups; ++g) {
         float Xf[R], Yf[R], Zf[R], uf[R], vf[R], w0[R], w1[R], w2[R];
@@ -100,9 +131,7 @@ __device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, floa
         int pidx[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int pr = (g * R + r) * 32 + lane;
-            valid[r] = pr < n;
-            const int p = valid[r] ? pr : 0;
+            const int p = rows.point(g, r, R, lane, valid[r]);
             pidx[r] = p;
             Xf[r] = s3[sidx<LAYOUT, 3>(p, 0, P)]; Yf[r] = s3[sidx<LAYOUT, 3>(p, 1, P)]; Zf[r] = s3[sidx<LAYOUT, 3>(p, 2, P)];
             uf[r] = s2[sidx<LAYOUT, 2>(p, 0, P)]; vf[r] = s2[sidx<LAYOUT, 2>(p, 1, P)];
@@ -217,19 +246,18 @@ __device__ __forceinline__ PointDelta point_delta(float X, float Y, float Z, con
 
 // In: tracked residuals at the accepted point in the s2 planes.  Out (per-lane partial sums): a[0..13] = J^T r' and
 // J^T J at the candidate, a[14] = sum |r'|^2 - sum |r|^2 (twice the cost change), a[15] = 0; the s2 planes now hold r'.
-template <int WMODE, int LAYOUT>
-__device__ __forceinline__ void eval_pass_delta(const float* s3, float* s2, const float* sw, int P, int n, int lane,
-                                                const DeltaStep& st, const Camera<float>& camf, const ClipWindow& cw,
-                                                float a[16], bool& flagged) {
+template <int WMODE, int LAYOUT, int R = 2, class ROWS = RowMap<1>>
+__device__ __forceinline__ void eval_pass_delta(const float* s3, float* s2, const float* sw, int P, const ROWS rows,
+                                                int lane, const DeltaStep& st, const Camera<float>& camf,
+                                                const ClipWindow& cw, float a[16], bool& flagged) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
-    constexpr int R = 2;
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = 0.f;
     float dc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) dc[r] = 0.f;
     float mx = 0.f, my = 0.f, mz = 1e30f;
-    const int ngroups = (((n + 31) >> 5) + R - 1) / R;
+    const int ngroups = rows.groups(R);
 #pragma unroll 1
     for (int g = 0; g < ngroups; ++g) {
         float X[R], Y[R], Z[R], e0[R], e1[R], w0[R], w1[R], w2[R];
@@ -237,9 +265,7 @@ __device__ __forceinline__ void eval_pass_delta(const float* s3, float* s2, cons
         int pidx[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int pr = (g * R + r) * 32 + lane;
-            valid[r] = pr < n;
-            const int p = valid[r] ? pr : 0;
+            const int p = rows.point(g, r, R, lane, valid[r]);
             pidx[r] = p;
             X[r] = s3[sidx<LAYOUT, 3>(p, 0, P)]; Y[r] = s3[sidx<LAYOUT, 3>(p, 1, P)]; Z[r] = s3[sidx<LAYOUT, 3>(p, 2, P)];
             e0[r] = s2[sidx<LAYOUT, 2>(p, 0, P)]; e1[r] = s2[sidx<LAYOUT, 2>(p, 1, P)];
@@ -322,14 +348,18 @@ __device__ __forceinline__ void eval_pass_delta(const float* s3, float* s2, cons
 
 // Roll the speculative residual update of a rejected candidate back: r = r' - dr with dr recomputed from the same
 // inputs (at most one fp32 rounding away from the value before the candidate; a perturbation of ~6e-8 |r|).
-template <int WMODE, int LAYOUT>
-__device__ __noinline__ void undo_pass_delta(float* slot, int P, int n, int lane, DeltaStep st, float fx, float fy) {
+template <int WMODE, int LAYOUT, class ROWS = RowMap<1>>
+__device__ __noinline__ void undo_pass_delta(float* slot, int P, const ROWS rows, int lane, DeltaStep st, float fx, float fy) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     const float* s3 = slot;
     float* s2 = slot + 3 * P;
     const float* sw = slot + 5 * P;
+    const int ngroups = rows.groups(1);
 #pragma unroll 1
-    for (int p = lane; p < n; p += 32) {
+    for (int g = 0; g < ngroups; ++g) {
+        bool valid;
+        const int p = rows.point(g, 0, 1, lane, valid);
+        if (!valid) continue;
         const PointDelta d = point_delta(s3[sidx<LAYOUT, 3>(p, 0, P)], s3[sidx<LAYOUT, 3>(p, 1, P)],
                                          s3[sidx<LAYOUT, 3>(p, 2, P)], st);
         float d0, d1;

@@ -462,9 +462,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
             bool flagged;
             const bool from_observations = cost_evals < 2;  // initial point (plain fp32), then the fp64 anchor
             if (from_observations) {
-                eval_pass_first<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, cost_evals == 1, pt, sn_p, cs_p, camf, a, flagged);
+                eval_pass_first<WMODE, LAYOUT>(s3, s2, sw, P, RowMap<1>{n}, lane, cost_evals == 1, pt, sn_p, cs_p, camf, a, flagged);
             } else {
-                eval_pass_delta<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, dstep, camf, cwin, a, flagged);
+                eval_pass_delta<WMODE, LAYOUT>(s3, s2, sw, P, RowMap<1>{n}, lane, dstep, camf, cwin, a, flagged);
             }
             const float tot = warp_reduce16_scatter(a, lane);  // lane L: total of sum (L >> 1)
             // finite iff every total is finite
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
                     decrease_factor *= 2.f;
                     TR_MARK(5)
                     // the slot holds the residuals at the rejected candidate (also after the anchor evaluation)
-                    undo_pass_delta<WMODE, LAYOUT>(slot, P, n, lane, dstep, camf.fx, camf.fy);
+                    undo_pass_delta<WMODE, LAYOUT>(slot, P, RowMap<1>{n}, lane, dstep, camf.fx, camf.fy);
                     TR_MARK(6)
                 }
             }
