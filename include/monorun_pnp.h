@@ -50,7 +50,7 @@ extern "C" {
 #define MRPNP_PREC_FAST 2  /* residuals evaluated once in fp64, then tracked incrementally: candidate evaluations are   */
                            /* pure fp32 "delta" passes whose cost CHANGE is accurate to ~1e-6 of itself; objects with a */
                            /* point near a clip bound are re-solved by the MIXED kernel in a follow-up launch on the    */
-                           /* same stream.  Needs inlier_opt_only = 1 (otherwise the solve runs as MIXED).              */
+                           /* same stream.  Needs inlier_opt_only = 1 (otherwise the solve runs as MIXED).  Default.    */
 
 /* pose covariance written to the result row */
 #define MRPNP_COV_NONE 0
@@ -88,7 +88,8 @@ typedef struct mrpnp_params {
 
 typedef struct mrpnp_ctx mrpnp_ctx;
 
-/* Fills `p` with the reference defaults (configs/kitti_multiclass.py:122-132) for n_obj x n_pts. */
+/* Fills `p` with the reference defaults (configs/kitti_multiclass.py:122-132) for n_obj x n_pts; planar layout,
+ * log-std weights, caller-supplied init_pose, pipeline covariance, precision MRPNP_PREC_FAST. */
 void mrpnp_default_params(mrpnp_params* p, int32_t n_obj, int32_t n_pts);
 
 /* Creates a context on CUDA device `device` (scratch buffers, work counter, streams for the host path). */

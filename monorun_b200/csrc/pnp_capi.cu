@@ -289,7 +289,7 @@ void mrpnp_default_params(mrpnp_params* p, int32_t n_obj, int32_t n_pts) {
     p->weight_mode = MRPNP_W_LOGSTD;
     p->cam_stride = 0;
     p->range_stride = 0;
-    p->precision = MRPNP_PREC_FP64;
+    p->precision = MRPNP_PREC_FAST;
     p->cov_mode = MRPNP_COV_PIPELINE;
     p->init_mode = MRPNP_INIT_GIVEN;
     p->inlier_opt_only = 1;      // configs/kitti_multiclass.py:127
