@@ -152,7 +152,7 @@ def run_reference(args, rank, world):
                                    f'shared init, {threads} OpenMP threads (reference native op needs ceres 1.14: absent)'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(w):
@@ -160,7 +160,20 @@ def workload_name(w):
             else 'cfg2-style: 8192 car ROIs/GPU x 28x28 corr, diagonal covariance (log-std in), pose-cov out')
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints there (NCCL's version banner ...)
+    was redirected to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
@@ -169,6 +182,8 @@ def main():
     ap.add_argument('--precision', choices=['fast', 'mixed', 'fp64'], default='fast')
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--streams', type=int, default=2, help='CUDA streams the K timed steps alternate between')
+    ap.add_argument('--gather', choices=['fused', 'nccl'], default='fused',
+                    help='N > 1: result rows by peer-to-peer stores from the kernel + symmetric-memory barrier, or NCCL all-gather')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -206,8 +221,17 @@ def main():
     kw = dict(layout='planar', weight_mode='full' if full else 'logstd', precision=args.precision,
               cov_mode='pipeline', return_inlier_mask=False)
 
+    # N > 1, --gather fused: one symmetric result buffer per stream (a buffer is rewritten by the next solve on it)
+    gathers = []
+    if world > 1 and args.gather == 'fused':
+        gathers = [mdist.FusedGather(n_total, dev) for _ in range(max(1, args.streams))]
+
     def step(i):
         d = dsets[i % 2]
+        if gathers:
+            fg = gathers[i % len(gathers)]
+            pnp.solve_batched(d['c3'], d['c2'], d['w'], d['cam'], d['rng'], init_pose=d['init'], **kw, **fg.solve_kwargs())
+            return fg.finish()
         rows, _, _ = pnp.solve_batched(d['c3'], d['c2'], d['w'], d['cam'], d['rng'], init_pose=d['init'], **kw)
         if world > 1:
             rows = mdist.all_gather_rows(rows, n_total)
@@ -335,7 +359,9 @@ def main():
                        'precision': args.precision, 'init': 'ground truth perturbed (5e-2 rad, 2% depth), shared with the oracle',
                        'l2': 'two alternating input sets of %.0f MB each (> 126 MB L2)' % (alg / 1e6),
                        'streams': nstreams, 'serialized_ms_per_step': kernel_ms,
-                       'parallelism': f'objects sharded contiguously over {world} GPU(s)' + (', 1 NCCL all-gather of [N,24] rows per step' if world > 1 else '')},
+                       'parallelism': f'objects sharded contiguously over {world} GPU(s)' + (
+                           '' if world == 1 else ', result rows stored peer-to-peer into every rank\'s symmetric buffer by the kernel + 1 symmetric-memory barrier per step'
+                           if gathers else ', 1 NCCL all-gather of [N,24] rows per step')},
             'clocks': clocks,
             'e2e': {'value': n_total * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d * world,
                     'd2h_bytes_per_step': d2h * world, 'steps': e2e_steps,
@@ -360,7 +386,7 @@ def main():
                           f'single thread (what the reference does, pnp_uncert_cpu.py:180-191): {one_rate:.0f} objects/s '
                           f'({done1} solves in {dt1:.1f} s)',
                 'single_thread_value': one_rate}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

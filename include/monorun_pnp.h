@@ -34,6 +34,7 @@ extern "C" {
 #define MRPNP_VERSION 1
 #define MRPNP_MAX_POINTS 1024   /* points per object (H*W); 28x28 = 784 in every reference config */
 #define MRPNP_RESULT_STRIDE 24  /* floats per result row */
+#define MRPNP_MAX_PEERS 8       /* GPUs of one NVLink / NVSwitch domain whose gathered buffers a launch can write */
 
 /* tensor layout of the correspondence arrays */
 #define MRPNP_LAYOUT_PLANAR 0      /* [N, C, P]  == [N, C, H, W] head-level tensors (monorun_roi_head.py:513-529) */
@@ -84,6 +85,17 @@ typedef struct mrpnp_params {
     float std_scale;        /* UncertPropPnPOptimizer(std_scale=10); only for MRPNP_W_LOGSTD           */
     float istd_thres;       /* epnp_istd_thres (0.6); <= 0 disables the istd inlier test               */
     float reserved;
+    /* Fused all-gather of the result rows (multi-GPU; objects are sharded contiguously over the ranks):
+     * with n_peers > 0 the kernel stores the row of local object i into EVERY peer's gathered buffer at row
+     * row_offset + i -- peer-to-peer stores over NVLink / NVSwitch from the solver's epilogue -- instead of into
+     * `result` (which may then be NULL).  peer_results[r] = device pointer, valid on THIS device, of rank r's
+     * [n_total, 24] float buffer (this rank's own buffer included); e.g. the buffer_ptrs of a torch symmetric-memory
+     * allocation.  The rows are complete on all ranks once every rank's launch has finished: follow the call with a
+     * cross-rank barrier on the same stream (7 us on NVSwitch, against ~20 us for an NCCL all-gather of the rows). */
+    int32_t n_peers;
+    int32_t reserved2;
+    int64_t row_offset;
+    float* peer_results[MRPNP_MAX_PEERS];
 } mrpnp_params;
 
 typedef struct mrpnp_ctx mrpnp_ctx;

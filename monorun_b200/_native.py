@@ -34,6 +34,8 @@ def _cdef_from_header(path=None):
     body = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
     body = '\n'.join(l for l in body.splitlines()
                      if not l.lstrip().startswith('#') and 'extern "C"' not in l and l.strip() != '}')
+    for k, v in consts:   # cffi's cdef has no preprocessor: array bounds written with a #define become numbers
+        body = re.sub(r'\[\s*%s\s*\]' % k, '[%s]' % v, body)
     return body, {k: int(v) for k, v in consts}
 
 

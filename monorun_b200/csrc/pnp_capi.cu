@@ -198,7 +198,10 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
                  const float* cam, const float* range, const float* init, const uint32_t* inl_in, float* result,
                  uint32_t* inl_out, double* result64, cudaStream_t stream, const DenseArgs* dense = nullptr) {
     if (p->n_obj == 0) return MRPNP_OK;
-    if (!c3d || !c2d || !wgt || !cam || !range || !result) return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    if (!c3d || !c2d || !wgt || !cam || !range || (!result && p->n_peers == 0)) return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    if (p->n_peers < 0 || p->n_peers > MRPNP_MAX_PEERS) return fail(MRPNP_ERR_ARG, "n_peers outside [0, 8]%s");
+    for (int r = 0; r < p->n_peers; ++r)
+        if (!p->peer_results[r]) return fail(MRPNP_ERR_ARG, "NULL peer result buffer%s");
     if (p->init_mode == MRPNP_INIT_GIVEN && !init) return fail(MRPNP_ERR_ARG, "init_pose is NULL with MRPNP_INIT_GIVEN%s");
     // MRPNP_PREC_FAST needs compacted inliers (the observations are overwritten by tracked residuals)
     const int precision = (p->precision == MRPNP_PREC_FAST && !p->inlier_opt_only) ? MRPNP_PREC_MIXED : p->precision;
@@ -208,6 +211,8 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     KParams kp;
     kp.c3d = c3d; kp.c2d = c2d; kp.wgt = wgt; kp.cam = cam; kp.range = range; kp.init = init;
     kp.inl_in = inl_in; kp.result = result; kp.inl_out = inl_out; kp.result64 = result64;
+    kp.n_peers = p->n_peers; kp.row_offset = p->row_offset;
+    for (int r = 0; r < MRPNP_MAX_PEERS; ++r) kp.peer[r] = r < p->n_peers ? p->peer_results[r] : nullptr;
     const int set = ctx->next_counter;
     kp.counters = ctx->counters + kCounterInts * set;
     ctx->next_counter = (ctx->next_counter + 1) % kCounterSets;

@@ -65,7 +65,24 @@ struct KParams {
     const int* work_list;
     int* work_count;
     int prefetch_distance;    // objects between the one a team starts and the one it prefetches into L2
+    // fused all-gather of the result rows: with n_peers > 0 the row of local object i is stored into EVERY peer's
+    // gathered buffer at row row_offset + i (peer-to-peer stores over NVLink), instead of into `result`
+    float* peer[MRPNP_MAX_PEERS];
+    int n_peers;
+    long long row_offset;
 };
+
+// The 96-byte result row of one object: lanes 0..23 hold its floats.
+__device__ __forceinline__ void store_result_row(const KParams& kp, int obj, int lane, float v) {
+    if (lane >= MRPNP_RESULT_STRIDE) return;
+    if (kp.n_peers == 0) {
+        kp.result[(size_t)obj * MRPNP_RESULT_STRIDE + lane] = v;
+    } else {
+        const size_t at = (size_t)(kp.row_offset + obj) * MRPNP_RESULT_STRIDE + lane;
+#pragma unroll 1
+        for (int r = 0; r < kp.n_peers; ++r) kp.peer[r][at] = v;
+    }
+}
 
 // ------------------------------------------------------------------ PTX wrappers (TMA bulk copy + mbarrier)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

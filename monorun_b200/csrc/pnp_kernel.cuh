@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
             v = (lane == 21) ? (float)iteration : v;
             v = (lane == 22) ? (float)cost : v;
             v = (lane == 23) ? (float)radius : v;
-            if (lane < MRPNP_RESULT_STRIDE) kp.result[(size_t)obj * MRPNP_RESULT_STRIDE + lane] = v;
+            store_result_row(kp, obj, lane, v);
             if (kp.result64) {
                 double d = 0.0;
 #pragma unroll
@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
     // self-resetting work counters: the last CTA to finish rearms them for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (kp.n_peers) __threadfence_system();  // rows stored into peer memory are performed before the kernel ends
         __threadfence();
         const int done = atomicAdd(kp.counters + 1, 1);
         if (done == (int)gridDim.x - 1) {

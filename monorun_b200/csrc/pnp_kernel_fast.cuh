@@ -260,7 +260,7 @@ __device__ __noinline__ void fast_finish_object(const KParams& kp, int obj, int 
     v = (lane == 21) ? (float)iteration : v;
     v = (lane == 22) ? cost : v;
     v = (lane == 23) ? radius : v;
-    if (lane < MRPNP_RESULT_STRIDE) kp.result[(size_t)obj * MRPNP_RESULT_STRIDE + lane] = v;
+    store_result_row(kp, obj, lane, v);
 #ifndef MRPNP_TRACE
     if (kp.result64) {
         double d = 0.0;
@@ -638,6 +638,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __gri
     // self-resetting work counters: the last CTA to finish rearms them for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (kp.n_peers) __threadfence_system();  // rows stored into peer memory are performed before the kernel ends
         __threadfence();
         const int done = atomicAdd(kp.counters + 1, 1);
         if (done == (int)gridDim.x - 1) {

@@ -93,13 +93,17 @@ def _ptr(t, ctype='float*'):
 def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None, inlier_mask=None, *,
                   layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, istd_thres=0.6,
                   inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
-                  adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False):
+                  adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False, peers=None, row_offset=0):
     """Batched uncertainty-PnP on device tensors -- direct wrapper of ``mrpnp_solve``.
 
     layout 'planar':      coords_3d [N,3,*], coords_2d [N,2,*], weights [N,2|3,*]   (head level)
     layout 'interleaved': coords_3d [N,P,3], coords_2d [N,P,2], weights [N,P,2|3]   (op level)
     weight_mode 'logstd' | 'istd' | 'full';  cam_mats [N|1,3,3];  uv_range [N|1,4] = u_min,u_max,v_min,v_max;
     init_pose [N,4] or None (on-device linear initialiser);  inlier_mask [N,P] bool/uint8 or None.
+
+    peers: device pointers (ints, valid on this device) of every rank's gathered [n_total,24] buffer -- the kernel then
+    stores each result row into ALL of them at row ``row_offset + i`` (fused all-gather, see ``dist.FusedGather``) and
+    the returned ``result`` is None.
 
     Returns (result [N,24] float32, inlier_mask [N,P] bool | None, result64 [N,8] float64 | None); the result
     row is ``yaw,tx,ty,tz | cov(16) | valid, lm_iterations, final_cost, trust_region_radius``.
@@ -110,7 +114,7 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
     planar = layout == 'planar'
     n_pts = coords_3d[0].numel() // 3 if n else (coords_3d.shape[2:].numel() if planar else coords_3d.shape[1])
     wmode = {'logstd': C['MRPNP_W_LOGSTD'], 'istd': C['MRPNP_W_ISTD'], 'full': C['MRPNP_W_FULL']}[weight_mode]
-    result = torch.empty((n, RESULT_STRIDE), dtype=torch.float32, device=dev)
+    result = torch.empty((n, RESULT_STRIDE), dtype=torch.float32, device=dev) if not peers else None
     n_words = (n_pts + 31) // 32
     inl_out = torch.empty((n, n_words), dtype=torch.int32, device=dev) if return_inlier_mask else None
     res64 = torch.empty((n, 8), dtype=torch.float64, device=dev) if return_fp64 else None
@@ -134,6 +138,12 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
         inlier_opt_only=int(bool(inlier_opt_only)), max_iterations=int(max_iterations),
         adopt_candidate_on_ftol=int(bool(adopt_candidate_on_ftol)),
         z_min=float(z_min), std_scale=float(std_scale), istd_thres=float(istd_thres))
+    if peers:
+        if len(peers) > C['MRPNP_MAX_PEERS']:
+            raise ValueError('at most %d peers' % C['MRPNP_MAX_PEERS'])
+        p.n_peers, p.row_offset = len(peers), int(row_offset)
+        for r, ptr in enumerate(peers):
+            p.peer_results[r] = _native.ffi.cast('float*', int(ptr))
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
         _native.check(_native.lib().mrpnp_solve(
