@@ -8,6 +8,9 @@
 #include "monorun_pnp.h"
 #include "pnp_kernel.cuh"
 #include "pnp_kernel_fast.cuh"
+#ifdef MRPNP_WITH_POOL  // pooled staging buffers + small slots: measured slower, kept for reference
+#include "pnp_kernel_pool.cuh"
+#endif
 #ifdef MRPNP_WITH_PAIR_FAST  // two warps per object: measured slower, kept for reference
 #include "pnp_kernel_fast2.cuh"
 #endif
@@ -60,7 +63,21 @@ using mrpnp::KParams;
 
 struct LaunchPlan {
     int warps, groups, ctas, smem, use_tma, slot_floats, team;
+    int pool_stage;  // > 0: pooled kernel with this many staging buffers per CTA
 };
+
+// experiment build only: MRPNP_POOL=1 in the environment selects the pooled kernel
+bool pool_enabled() {
+#ifdef MRPNP_WITH_POOL
+    static const bool on = [] {
+        const char* e = getenv("MRPNP_POOL");
+        return e && atoi(e) == 1;
+    }();
+    return on;
+#else
+    return false;
+#endif
+}
 
 // warps per object of the MRPNP_PREC_FAST kernel: 1, or (experiment build only) MRPNP_TEAM=2 from the environment
 int team_size() {
@@ -87,6 +104,31 @@ int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, int precision, cons
         const int per_sm = (p->n_obj + ctx->num_sms - 1) / ctx->num_sms;
         groups = std::max(1, std::min(groups, per_sm));
         plan->team = team;
+        plan->pool_stage = 0;
+#ifdef MRPNP_WITH_POOL
+        if (team == 1 && pool_enabled() && p->n_pts > mrpnp::kPoolCap) {
+            // pooled shared memory: NS slab-sized staging buffers + NSM small slots, NS + NSM warps
+            const size_t small_bytes = (size_t)(5 + wc) * mrpnp::kPoolCap * sizeof(float);
+            int ns = wc == 3 ? 3 : 4;
+            if (const char* e = getenv("MRPNP_POOL_NS")) ns = std::max(1, std::min(atoi(e), mrpnp::kPoolMaxStage));
+            const size_t fixed = mrpnp::kPoolCtaHeaderBytes + (size_t)ns * (slot_bytes + mrpnp::kFastHeaderBytes);
+            if ((size_t)ctx->max_smem_optin > fixed) {
+                int nsm = (int)(((size_t)ctx->max_smem_optin - fixed) / (small_bytes + mrpnp::kFastHeaderBytes));
+                nsm = std::min(nsm, mrpnp::kPoolMaxWarps - ns);
+                if (nsm >= 1 && ns + nsm > groups && per_sm >= ns + nsm) {
+                    plan->pool_stage = ns;
+                    plan->warps = ns + nsm;
+                    plan->groups = ns + nsm;
+                    plan->ctas = std::min(ctx->num_sms, (p->n_obj + plan->warps - 1) / plan->warps);
+                    plan->smem = (int)(fixed + (size_t)nsm * (small_bytes + mrpnp::kFastHeaderBytes));
+                    plan->slot_floats = (int)(slot_bytes / sizeof(float));
+                    const bool aligned = (p->n_pts % 4 == 0) && (((uintptr_t)c3d | (uintptr_t)c2d | (uintptr_t)wgt) % 16 == 0);
+                    plan->use_tma = aligned ? 1 : 0;
+                    return MRPNP_OK;
+                }
+            }
+        }
+#endif
         plan->warps = groups * plan->team;
         plan->groups = groups;
         plan->ctas = std::min(ctx->num_sms, (p->n_obj + groups - 1) / groups);
@@ -97,6 +139,7 @@ int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, int precision, cons
         return MRPNP_OK;
     }
     plan->team = 1;
+    plan->pool_stage = 0;
     const int wc = p->weight_mode == MRPNP_W_FULL ? 3 : 2;
     const size_t slot_floats = (size_t)(5 + wc) * p->n_pts;
     size_t slot_bytes = slot_floats * sizeof(float);
@@ -154,6 +197,10 @@ cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan,
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
     } else if (precision == MRPNP_PREC_FAST) {
         void (*k)(const KParams) = kp.n_pts == 784 ? mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 0>;
+#ifdef MRPNP_WITH_POOL
+        if (plan.pool_stage > 0)
+            k = kp.n_pts == 784 ? mrpnp::pnp_lm_pool_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_pool_kernel<WMODE, LAYOUT, 0>;
+#endif
 #ifdef MRPNP_WITH_PAIR_FAST
         if (plan.team == 2) k = kp.n_pts == 784 ? mrpnp::pnp_lm_fast2_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_fast2_kernel<WMODE, LAYOUT, 0>;
 #endif
@@ -211,6 +258,7 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     KParams kp;
     kp.c3d = c3d; kp.c2d = c2d; kp.wgt = wgt; kp.cam = cam; kp.range = range; kp.init = init;
     kp.inl_in = inl_in; kp.result = result; kp.inl_out = inl_out; kp.result64 = result64;
+    kp.pool_stage = plan.pool_stage;
     kp.n_peers = p->n_peers; kp.row_offset = p->row_offset;
     for (int r = 0; r < MRPNP_MAX_PEERS; ++r) kp.peer[r] = r < p->n_peers ? p->peer_results[r] : nullptr;
     const int set = ctx->next_counter;

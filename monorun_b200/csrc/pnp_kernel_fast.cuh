@@ -35,6 +35,10 @@
 
 namespace mrpnp {
 
+#ifndef MRPNP_FAST_WARPS
+#define MRPNP_FAST_WARPS 10
+#endif
+constexpr int kFastMaxWarps = MRPNP_FAST_WARPS;   // resident warps (= objects in flight) per SM
 constexpr int kFastHeaderBytes = 128;  // per warp: mbarrier (8 B) + 24-float scratch at +16 (reduction broadcast)
 constexpr int kFastScratch = 16;       // byte offset of the scratch
 
@@ -345,7 +349,7 @@ __device__ __forceinline__ float fast_sqrtf(float a) {
 // PCT: points per object known at compile time (784 = 28 x 28, every reference config) or 0 = kp.n_pts; with a
 // compile-time P the plane offsets of the slot become immediates of the shared-memory loads.
 template <int WMODE, int LAYOUT, int PCT>
-__global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_fast_kernel(const __grid_constant__ KParams kp) {
+__global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(const __grid_constant__ KParams kp) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
