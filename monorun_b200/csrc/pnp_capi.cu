@@ -66,18 +66,16 @@ struct LaunchPlan {
     int pool_stage;  // > 0: pooled kernel with this many staging buffers per CTA
 };
 
+#ifdef MRPNP_WITH_POOL
 // experiment build only: MRPNP_POOL=1 in the environment selects the pooled kernel
 bool pool_enabled() {
-#ifdef MRPNP_WITH_POOL
     static const bool on = [] {
         const char* e = getenv("MRPNP_POOL");
         return e && atoi(e) == 1;
     }();
     return on;
-#else
-    return false;
-#endif
 }
+#endif
 
 // warps per object of the MRPNP_PREC_FAST kernel: 1, or (experiment build only) MRPNP_TEAM=2 from the environment
 int team_size() {
