@@ -241,7 +241,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
 
     // work list: all objects, or (follow-up launch of a FAST solve) the objects the fast kernel handed back
     int n_work = kp.n_obj;
-    if (kp.work_list) n_work = *reinterpret_cast<const volatile int*>(kp.work_count);
+    if (kp.work_list) {
+        n_work = *reinterpret_cast<const volatile int*>(kp.work_count);
+        if (n_work == 0) return;  // the usual case of the follow-up launch: nothing was handed back, no counter was touched
+    }
 
     if (lane == 0) {
         mbar_init(bar, 1);

@@ -22,7 +22,7 @@ def main():
     ap.add_argument('--objects', type=int, default=8192)
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--precision', default='mixed')
+    ap.add_argument('--precision', default='fast')
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
     t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
