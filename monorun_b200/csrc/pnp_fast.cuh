@@ -110,7 +110,10 @@ __device__ __forceinline__ float warp_reduce16_scatter(float v[16], int lane) {
 // residual CHANGE behind as a fixed error of the tracked residuals, and only the first step changes them by many pixels.
 // Out: per-lane partial sums a[0..13] (J^T r, J^T J; layout of eval_pass_fp64 minus the cost), a[14] = this lane's
 // share of sum |r|^2, a[15] = 0; flagged = some point is within the margin of a clip bound.
-template <int WMODE, int LAYOUT, int R = 2, class ROWS = RowMap<1>>
+#ifndef MRPNP_FIRST_R
+#define MRPNP_FIRST_R 2
+#endif
+template <int WMODE, int LAYOUT, int R = MRPNP_FIRST_R, class ROWS = RowMap<1>>
 __device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, float* sw, int P, const ROWS rows, int lane,
                                                 bool anchor, const float x[4], float snf, float csf,
                                                 const Camera<float>& camf, float a[16], bool& flagged) {
