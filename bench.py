@@ -222,9 +222,16 @@ def main():
               cov_mode='pipeline', return_inlier_mask=False)
 
     # N > 1, --gather fused: one symmetric result buffer per stream (a buffer is rewritten by the next solve on it)
-    gathers = []
+    gathers, gather_note = [], ''
     if world > 1 and args.gather == 'fused':
-        gathers = [mdist.FusedGather(n_total, dev) for _ in range(max(1, args.streams))]
+        try:
+            gathers = [mdist.FusedGather(n_total, dev) for _ in range(max(1, args.streams))]
+            ok = torch.ones(1, device=dev)
+        except Exception as exc:  # symmetric memory unavailable on this box: NCCL all-gather instead, and say so
+            gathers, gather_note, ok = [], f' (symmetric memory unavailable: {type(exc).__name__})', torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # every rank takes the same path
+        if ok.item() == 0:
+            gathers = []
 
     def step(i):
         d = dsets[i % 2]
@@ -361,7 +368,7 @@ def main():
                        'streams': nstreams, 'serialized_ms_per_step': kernel_ms,
                        'parallelism': f'objects sharded contiguously over {world} GPU(s)' + (
                            '' if world == 1 else ', result rows stored peer-to-peer into every rank\'s symmetric buffer by the kernel + 1 symmetric-memory barrier per step'
-                           if gathers else ', 1 NCCL all-gather of [N,24] rows per step')},
+                           if gathers else ', 1 NCCL all-gather of [N,24] rows per step' + gather_note)},
             'clocks': clocks,
             'e2e': {'value': n_total * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d * world,
                     'd2h_bytes_per_step': d2h * world, 'steps': e2e_steps,
