@@ -170,6 +170,26 @@ int mrpnp_solve_host(mrpnp_ctx* ctx, const mrpnp_params* p,
                      const uint32_t* inlier_in,
                      float* result, uint32_t* inlier_out);
 
+/* The immediate consumer of (pose, covariance), fused: covariance calibration (uncert_prop_pnp_optimizer.py:96-97),
+ * test-time covariance correction cov * (sd / distance)^2 (distance_invar_proj_error_coder.py:62-63,
+ * monorun_roi_head.py:530-534), the lower triangle + concatenation [yaw, t, tril(cov), dims] and the eval-mode
+ * pose_norm that open MLPScoreHead.forward (mlp_score_head.py:99-106, :177-178).  One launch instead of ~12.
+ *   rows [N,24] result rows; dims [N,3]; cov_calib_logscale [4] or NULL (DEVICE pointer, the nn.Parameter);
+ *   cov_correction_sd: scaling_denominator, 0 = no correction; distance_z_depth: distance = t_z instead of |t|;
+ *   use_calib: features take the calibrated covariance (test_cfg.calib_scoring);
+ *   norm_mean/var/weight/bias [17] or all NULL; feat [N,17] out; cov_calib [N,16] out or NULL. */
+int mrpnp_pose_features(mrpnp_ctx* ctx, const float* rows, const float* dims, const float* cov_calib_logscale,
+                        float cov_correction_sd, int32_t distance_z_depth, int32_t use_calib,
+                        const float* norm_mean, const float* norm_var, const float* norm_weight, const float* norm_bias,
+                        float norm_eps, float* feat, float* cov_calib, int32_t n, void* stream);
+
+/* After the score head's last Linear layer (monorun_roi_head.py:544-556, :612-613): sigmoid (pre_sigmoid != 0),
+ * invalid objects -> 0, product with the 2-D detection score (det_scores, NULL = mult_2d_score off), and the
+ * [l,h,w,x,y,z,ry,score] rows of get_bbox_3d_result.  scores [N] and/or bbox_3d [N,8] may be NULL. */
+int mrpnp_finish_scores(mrpnp_ctx* ctx, const float* score_logits, const float* rows, const float* dims,
+                        const float* det_scores, int32_t pre_sigmoid, float* scores, float* bbox_3d, int32_t n,
+                        void* stream);
+
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);
 

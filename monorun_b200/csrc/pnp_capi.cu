@@ -8,6 +8,7 @@
 #include "monorun_pnp.h"
 #include "pnp_kernel.cuh"
 #include "pnp_kernel_fast.cuh"
+#include "pnp_score.cuh"
 #ifdef MRPNP_WITH_POOL  // pooled staging buffers + small slots: measured slower, kept for reference
 #include "pnp_kernel_pool.cuh"
 #endif
@@ -386,6 +387,47 @@ void mrpnp_destroy(mrpnp_ctx* c) {
 }
 
 int64_t mrpnp_launch_count(const mrpnp_ctx* c) { return c ? c->launches : 0; }
+
+int mrpnp_pose_features(mrpnp_ctx* ctx, const float* rows, const float* dims, const float* cov_calib_logscale,
+                        float cov_correction_sd, int32_t distance_z_depth, int32_t use_calib,
+                        const float* norm_mean, const float* norm_var, const float* norm_weight, const float* norm_bias,
+                        float norm_eps, float* feat, float* cov_calib, int32_t n, void* stream) {
+    if (!ctx) return fail(MRPNP_ERR_ARG, "ctx is NULL%s");
+    if (n < 0) return fail(MRPNP_ERR_ARG, "n < 0%s");
+    if (n == 0) return MRPNP_OK;
+    if (!rows || !dims || !feat) return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    const bool any_norm = norm_mean || norm_var || norm_weight || norm_bias;
+    if (any_norm && !(norm_mean && norm_var && norm_weight && norm_bias))
+        return fail(MRPNP_ERR_ARG, "pose_norm needs mean, var, weight and bias%s");
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    mrpnp::ScoreParams sp;
+    sp.rows = rows; sp.dims = dims;
+    sp.calib_logscale = cov_calib_logscale;
+    sp.corr_sd = cov_correction_sd; sp.corr_z_depth = distance_z_depth; sp.use_calib = use_calib;
+    sp.norm_mean = norm_mean; sp.norm_var = norm_var; sp.norm_weight = norm_weight; sp.norm_bias = norm_bias;
+    sp.norm_eps = norm_eps; sp.feat = feat; sp.cov_calib = cov_calib; sp.n = n;
+    mrpnp::pose_features_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sp);
+    MR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return MRPNP_OK;
+}
+
+int mrpnp_finish_scores(mrpnp_ctx* ctx, const float* score_logits, const float* rows, const float* dims,
+                        const float* det_scores, int32_t pre_sigmoid, float* scores, float* bbox_3d, int32_t n,
+                        void* stream) {
+    if (!ctx) return fail(MRPNP_ERR_ARG, "ctx is NULL%s");
+    if (n < 0) return fail(MRPNP_ERR_ARG, "n < 0%s");
+    if (n == 0) return MRPNP_OK;
+    if (!score_logits || !rows || (bbox_3d && !dims) || (!scores && !bbox_3d)) return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    mrpnp::finish_scores_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        score_logits, rows, dims, det_scores, pre_sigmoid, scores, bbox_3d, n);
+    MR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return MRPNP_OK;
+}
 
 int mrpnp_kernel_info(mrpnp_ctx* ctx, const mrpnp_params* p, int32_t info[4]) {
     if (!ctx || !info) return fail(MRPNP_ERR_ARG, "NULL argument%s");

@@ -270,7 +270,100 @@ class UncertProjectionHead(nn.Module):
         return t_vec[:, 2] if self.distance_mode == 'z-depth' else torch.norm(t_vec, p=2, dim=1)
 
 
-_OUT_OF_SCOPE = ('bbox_roi_extractor', 'bbox_head', 'global_head', 'score_head', 'noc_roi_extractor',
+class BatchNormSmooth1D(nn.modules.batchnorm._NormBase):
+    """mlp_score_head.py:142-184: batch norm that ALWAYS normalises with the running statistics (updated first when
+    training).  Inference only here: ``forward`` is the eval branch (:177-178)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super(BatchNormSmooth1D, self).__init__(num_features, eps, momentum, affine, track_running_stats)
+
+    def _check_input_dim(self, input):
+        if input.dim() != 2 and input.dim() != 3:
+            raise ValueError('expected 2D or 3D input (got {}D input)'.format(input.dim()))
+
+    def forward(self, input):
+        self._check_input_dim(input)
+        if self.training:
+            raise RuntimeError('BatchNormSmooth1D: inference only in this repo (call .eval())')
+        return input.sub(self.running_mean).div((self.running_var + self.eps).sqrt()).mul(self.weight).add(self.bias)
+
+
+@HEADS.register_module()
+class MLPScoreHead(nn.Module):
+    """Score head (mlp_score_head.py:11-115), inference side: same constructor kwargs, sub-module names and
+    state-dict keys (``pose_norm``, ``pose_fcs``, ``fused_fcs``, ``fc_out``).
+
+    ``forward`` is the reference's torch sequence (and the fp32 reference of the tests).  ``forward_rows`` is the
+    B200 path: one launch builds the normalised 17-feature rows straight from the solver's result rows (covariance
+    calibration, test-time correction, lower triangle, concatenation, pose_norm: ``mrpnp_pose_features``), the Linear
+    layers run as library GEMMs, one launch finishes (sigmoid, invalid -> 0, product with the 2-D score, the
+    [l,h,w,x,y,z,ry,score] rows: ``mrpnp_finish_scores``)."""
+
+    def __init__(self, reg_fc_out_channels=1024, num_pose_fcs=1, pose_fc_out_channels=1024, fusion_type='add',
+                 num_fused_fcs=1, fc_out_channels=256, loss_score=None, mode='linear_average', iou_thres=0.7,
+                 linear_coefs=(-0.5, 2), detach_preds=True, use_pose_norm=True, train_cfg=None):
+        super(MLPScoreHead, self).__init__()
+        assert mode in ['average', 'thres', 'linear_average'] and fusion_type in ['add', 'concat']
+        assert num_pose_fcs > 0 and num_fused_fcs > 0
+        self.num_pose_fcs, self.num_fused_fcs = num_pose_fcs, num_fused_fcs
+        self.fc_out_channels, self.pose_fc_out_channels = fc_out_channels, pose_fc_out_channels
+        self.reg_fc_out_channels, self.fusion_type, self.use_pose_norm = reg_fc_out_channels, fusion_type, use_pose_norm
+        self.mode, self.iou_thres, self.linear_coefs, self.detach_preds = mode, iou_thres, linear_coefs, detach_preds
+        self.loss_score, self.train_cfg = loss_score, train_cfg   # training is out of scope: kept as configuration
+        self.fp16_enabled = False
+        self.pre_sigmoid = True
+        self.relu = nn.ReLU(inplace=True)
+        layer_dim = reg_fc_out_channels
+        if fusion_type == 'add':
+            assert pose_fc_out_channels == reg_fc_out_channels
+        else:
+            layer_dim += pose_fc_out_channels
+        pose_last_layer_dim = 1 + 3 + 10 + 3  # only the lower triangle of the covariance
+        if use_pose_norm:
+            self.pose_norm = BatchNormSmooth1D(pose_last_layer_dim, momentum=0.01)
+        self.pose_fcs = nn.ModuleList(nn.Linear(pose_last_layer_dim if i == 0 else pose_fc_out_channels,
+                                                pose_fc_out_channels) for i in range(num_pose_fcs))
+        self.fused_fcs = nn.ModuleList(nn.Linear(layer_dim if i == 0 else fc_out_channels, fc_out_channels)
+                                       for i in range(num_fused_fcs))
+        self.fc_out = nn.Linear(fc_out_channels, 1)
+
+    def init_weights(self):
+        for m in list(self.pose_fcs) + list(self.fused_fcs):
+            nn.init.xavier_uniform_(m.weight)
+            nn.init.constant_(m.bias, 0)
+        nn.init.normal_(self.fc_out.weight, 0, 0.01)
+        nn.init.constant_(self.fc_out.bias, 0)
+
+    def _mlp(self, x, reg_fc_out):
+        for fc in self.pose_fcs:
+            x = self.relu(fc(x))
+        x = x + reg_fc_out if self.fusion_type == 'add' else torch.cat([x, reg_fc_out], dim=1)
+        for fc in self.fused_fcs:
+            x = self.relu(fc(x))
+        return self.fc_out(x).squeeze(1)
+
+    def forward(self, reg_fc_out, yaw, t_vec, pose_cov, dimensions):
+        """mlp_score_head.py:94-115 (raw scores, shape (n,))."""
+        cov_x_inds, cov_y_inds = torch.tril_indices(4, 4, device=pose_cov.device)
+        x = torch.cat([yaw, t_vec, pose_cov[:, cov_x_inds, cov_y_inds], dimensions], dim=1)
+        if self.use_pose_norm:
+            x = self.pose_norm(x)
+        return self._mlp(x, reg_fc_out)
+
+    def forward_rows(self, reg_fc_out, rows, dimensions, cov_calib_logscale=None, cov_correction_sd=0.0,
+                     distance_z_depth=False, calib_scoring=False, det_scores=None):
+        """Solver result rows [N,24] -> (scores [N], bbox_3d [N,8], pose_cov_calib [N,4,4]); the test-time tail of
+        MonoRUnRoIHead.simple_test (monorun_roi_head.py:530-556) with two launches around the GEMMs."""
+        from . import pnp
+        norm = self.pose_norm if self.use_pose_norm else None
+        feat, cov_calib = pnp.pose_features(rows, dimensions, cov_calib_logscale, cov_correction_sd, distance_z_depth,
+                                            calib_scoring, norm)
+        logits = self._mlp(feat, reg_fc_out)
+        scores, bbox_3d = pnp.finish_scores(logits, rows, dimensions, det_scores, self.pre_sigmoid)
+        return scores, bbox_3d, cov_calib.view(-1, 4, 4)
+
+
+_OUT_OF_SCOPE = ('bbox_roi_extractor', 'bbox_head', 'global_head', 'noc_roi_extractor',
                  'shared_head', 'mask_roi_extractor', 'mask_head')
 
 
@@ -285,8 +378,8 @@ class MonoRUnRoIHead(nn.Module):
     def __init__(self, noc_roi_extractor=None, noc_head=None, global_head=None, projection_head=None,
                  pose_head=None, score_head=None, debug=False, train_cfg=None, test_cfg=None, **kwargs):
         super(MonoRUnRoIHead, self).__init__()
-        self.deferred = {k: v for k, v in dict(kwargs, noc_roi_extractor=noc_roi_extractor, global_head=global_head,
-                                               score_head=score_head).items() if v is not None}
+        self.deferred = {k: v for k, v in dict(kwargs, noc_roi_extractor=noc_roi_extractor,
+                                               global_head=global_head).items() if v is not None}
         unknown = set(kwargs) - set(_OUT_OF_SCOPE)
         if unknown:
             raise TypeError(f'unexpected MonoRUnRoIHead arguments: {sorted(unknown)}')
@@ -297,6 +390,8 @@ class MonoRUnRoIHead(nn.Module):
             self.projection_head = build_head(projection_head)
         if pose_head is not None:
             self.pose_head = build_head(pose_head)
+        if score_head is not None:
+            self.score_head = build_head(score_head)
 
     @property
     def with_noc(self):
@@ -306,9 +401,26 @@ class MonoRUnRoIHead(nn.Module):
     def with_pose(self):
         return hasattr(self, 'pose_head') and self.pose_head is not None
 
+    @property
+    def with_score(self):
+        return hasattr(self, 'score_head') and self.score_head is not None
+
     def init_weights(self):
         if self.with_noc:
             self.noc_head.init_weights()
+        if self.with_score:
+            self.score_head.init_weights()
+
+    def forward_scores(self, rows, reg_fc_out, dimensions_pred, det_scores=None, cov_correction=True, calib_scoring=False,
+                       mult_2d_score=True):
+        """monorun_roi_head.py:530-556 on the solver's result rows: covariance correction, score head, sigmoid,
+        invalid -> 0, product with the 2-D score.  Returns (scores [N], bbox_3d [N,8], pose_cov_calib [N,4,4])."""
+        ph = self.projection_head
+        return self.score_head.forward_rows(
+            reg_fc_out, rows, dimensions_pred, cov_calib_logscale=self.pose_head.cov_calib_logscale.detach(),
+            cov_correction_sd=ph.proj_error_coder.scaling_denomitor if cov_correction else 0.0,
+            distance_z_depth=ph.distance_mode == 'z-depth', calib_scoring=calib_scoring,
+            det_scores=det_scores if mult_2d_score else None)
 
     def forward_3d(self, noc_feats, bbox_3d_rois, det_labels, latent_pred, dimensions_pred, dimensions_var,
                    cam_intrinsic, img_shape, flip=False, distance_pred=None, cov_correction=True, fused=False,

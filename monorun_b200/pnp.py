@@ -153,6 +153,51 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
     return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None), res64
 
 
+def pose_features(rows, dims, cov_calib_logscale=None, cov_correction_sd=0.0, distance_z_depth=False, use_calib=False,
+                  pose_norm=None):
+    """``mrpnp_pose_features``: result rows [N,24] + dims [N,3] -> (features [N,17], pose_cov_calib [N,16])."""
+    dev = rows.device
+    ctx = get_ctx(dev)
+    n = rows.shape[0]
+    rows, dims = _f32c(rows), _f32c(dims)
+    feat = torch.empty((n, 17), dtype=torch.float32, device=dev)
+    cal = torch.empty((n, 16), dtype=torch.float32, device=dev)
+    if n == 0:
+        return feat, cal
+    ls = _f32c(cov_calib_logscale) if cov_calib_logscale is not None else None
+    nm = [None] * 4
+    eps = 0.0
+    if pose_norm is not None:
+        nm = [_f32c(t.detach()) for t in (pose_norm.running_mean, pose_norm.running_var, pose_norm.weight, pose_norm.bias)]
+        eps = float(pose_norm.eps)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_pose_features(
+            ctx.ptr, _ptr(rows), _ptr(dims), _ptr(ls), float(cov_correction_sd), int(bool(distance_z_depth)),
+            int(bool(use_calib)), _ptr(nm[0]), _ptr(nm[1]), _ptr(nm[2]), _ptr(nm[3]), eps, _ptr(feat), _ptr(cal), n,
+            _native.ffi.cast('void*', stream)))
+    return feat, cal
+
+
+def finish_scores(score_logits, rows, dims, det_scores=None, pre_sigmoid=True):
+    """``mrpnp_finish_scores``: -> (scores [N], bbox_3d [N,8] = l,h,w,x,y,z,ry,score)."""
+    dev = rows.device
+    ctx = get_ctx(dev)
+    n = rows.shape[0]
+    scores = torch.empty((n,), dtype=torch.float32, device=dev)
+    bbox = torch.empty((n, 8), dtype=torch.float32, device=dev)
+    if n == 0:
+        return scores, bbox
+    lg, rows, dims = _f32c(score_logits), _f32c(rows), _f32c(dims)
+    ds = _f32c(det_scores) if det_scores is not None else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_finish_scores(ctx.ptr, _ptr(lg), _ptr(rows), _ptr(dims), _ptr(ds),
+                                                        int(bool(pre_sigmoid)), _ptr(scores), _ptr(bbox), n,
+                                                        _native.ffi.cast('void*', stream)))
+    return scores, bbox
+
+
 def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, *, noc_mean, noc_std, focal_gain,
                 scaling_denominator, distance=None, distance_min=0.1, init_pose=None, z_min=0.5, std_scale=10.0,
                 istd_thres=0.6, inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
