@@ -190,6 +190,15 @@ int mrpnp_finish_scores(mrpnp_ctx* ctx, const float* score_logits, const float* 
                         const float* det_scores, int32_t pre_sigmoid, float* scores, float* bbox_3d, int32_t n,
                         void* stream);
 
+/* Class-wise 3-D NMS on bird's-eye-view rotated boxes (MonoRUnRoIHead.multiclass_3d_result_nms,
+ * monorun_roi_head.py:619-680; mmdet3d nms_gpu on centre (x, z), extent (l, w), angle ry): per image and class, in
+ * descending score order, a box is dropped if its rotated IoU with an earlier kept box exceeds iou_thr.
+ *   bbox_3d [N,8] l,h,w,x,y,z,ry,score (mrpnp_finish_scores); labels [N] int64 or NULL (one class);
+ *   group_offsets [G+1] int32 DEVICE: image g owns objects [off[g], off[g+1]); max_group: an upper bound of the
+ *   largest group (<= 4096); keep [N] uint8 out (1 = kept). */
+int mrpnp_nms_bev(mrpnp_ctx* ctx, const float* bbox_3d, const int64_t* labels, const int32_t* group_offsets,
+                  int32_t n_groups, int32_t max_group, float iou_thr, uint8_t* keep, void* stream);
+
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);
 

@@ -9,6 +9,7 @@
 #include "pnp_kernel.cuh"
 #include "pnp_kernel_fast.cuh"
 #include "pnp_score.cuh"
+#include "pnp_nms.cuh"
 #ifdef MRPNP_WITH_POOL  // pooled staging buffers + small slots: measured slower, kept for reference
 #include "pnp_kernel_pool.cuh"
 #endif
@@ -408,6 +409,26 @@ int mrpnp_pose_features(mrpnp_ctx* ctx, const float* rows, const float* dims, co
     sp.norm_mean = norm_mean; sp.norm_var = norm_var; sp.norm_weight = norm_weight; sp.norm_bias = norm_bias;
     sp.norm_eps = norm_eps; sp.feat = feat; sp.cov_calib = cov_calib; sp.n = n;
     mrpnp::pose_features_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sp);
+    MR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return MRPNP_OK;
+}
+
+int mrpnp_nms_bev(mrpnp_ctx* ctx, const float* bbox_3d, const int64_t* labels, const int32_t* group_offsets,
+                  int32_t n_groups, int32_t max_group, float iou_thr, uint8_t* keep, void* stream) {
+    if (!ctx) return fail(MRPNP_ERR_ARG, "ctx is NULL%s");
+    if (n_groups < 0 || max_group < 0) return fail(MRPNP_ERR_ARG, "negative size%s");
+    if (n_groups == 0 || max_group == 0) return MRPNP_OK;
+    if (!bbox_3d || !group_offsets || !keep) return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    if (max_group > 4096) return fail(MRPNP_ERR_ARG, "more than 4096 objects in one image%s");
+    int cap = 1;
+    while (cap < max_group) cap <<= 1;
+    const size_t smem = (size_t)cap * (4 * sizeof(int) + sizeof(mrpnp::BevBox));
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    MR_CUDA(cudaFuncSetAttribute(mrpnp::nms_bev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mrpnp::nms_bev_kernel<<<n_groups, mrpnp::kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        bbox_3d, reinterpret_cast<const long long*>(labels), group_offsets, iou_thr, cap, keep);
     MR_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return MRPNP_OK;

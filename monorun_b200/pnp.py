@@ -198,6 +198,34 @@ def finish_scores(score_logits, rows, dims, det_scores=None, pre_sigmoid=True):
     return scores, bbox
 
 
+def nms_bev(bbox_3d, labels=None, group_offsets=None, iou_thr=0.25):
+    """``mrpnp_nms_bev``: class-wise rotated BEV NMS per image.  bbox_3d [N,8] (l,h,w,x,y,z,ry,score), labels [N]
+    int64 or None, group_offsets [G+1] int32 tensor or python list (None = one image).  Returns keep [N] bool."""
+    dev = bbox_3d.device
+    ctx = get_ctx(dev)
+    n = bbox_3d.shape[0]
+    keep = torch.zeros((n,), dtype=torch.uint8, device=dev)
+    if n == 0:
+        return keep.bool()
+    if group_offsets is None:
+        group_offsets = [0, n]
+    if not torch.is_tensor(group_offsets):
+        sizes = [b - a for a, b in zip(group_offsets[:-1], group_offsets[1:])]
+        max_group = max(sizes) if sizes else 0
+        group_offsets = torch.tensor(group_offsets, dtype=torch.int32, device=dev)
+    else:
+        max_group = int((group_offsets[1:] - group_offsets[:-1]).max().item())
+        group_offsets = group_offsets.to(device=dev, dtype=torch.int32).contiguous()
+    b = _f32c(bbox_3d)
+    lab = labels.to(torch.int64).contiguous() if labels is not None else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_nms_bev(
+            ctx.ptr, _ptr(b), _ptr(lab, 'int64_t*'), _ptr(group_offsets, 'int32_t*'), group_offsets.numel() - 1,
+            int(max_group), float(iou_thr), _ptr(keep, 'uint8_t*'), _native.ffi.cast('void*', stream)))
+    return keep.bool()
+
+
 def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, *, noc_mean, noc_std, focal_gain,
                 scaling_denominator, distance=None, distance_min=0.1, init_pose=None, z_min=0.5, std_scale=10.0,
                 istd_thres=0.6, inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,

@@ -52,3 +52,76 @@ def finish_scores_ref(logits, rows, dims, det_scores=None, pre_sigmoid=True):
         s = np.asarray(det_scores, np.float64) * s                      # :548-550
     bbox = np.concatenate([np.asarray(dims, np.float64), rows[:, 1:4], rows[:, 0:1], s[:, None]], 1)  # :612-613
     return s, bbox
+
+
+# ------------------------------------------------------------------ class-wise rotated BEV NMS
+# MonoRUnRoIHead.multiclass_3d_result_nms (monorun_roi_head.py:619-655) with boxes_for_nms =
+# xywhr2xyxyr(bbox_3d[:, [3, 5, 0, 2, 6]]) (:660-680) handed to mmdet3d.ops.iou3d.nms_gpu.  mmdet3d is NOT in the
+# reference tree or this container; its nms_gpu (mmdet3d 0.6-0.8, from OpenPCDet's iou3d_nms) sorts by descending
+# score and drops a box whose rotated-rectangle IoU in the (x, z) plane with an earlier kept box is > thresh.  The
+# IoU is restated here as exact polygon clipping in fp64 (parity unpinned against mmdet3d's own fp32 routine).
+def _corners(cx, cz, l, w, ry):
+    c, s = np.cos(ry), np.sin(ry)
+    u = np.array([l / 2, -l / 2, -l / 2, l / 2]); v = np.array([w / 2, w / 2, -w / 2, -w / 2])
+    return np.stack([cx + c * u + s * v, cz - s * u + c * v], 1)
+
+
+def _clip(poly, a, b):
+    """Sutherland-Hodgman: keep the part of `poly` on the left of the directed line a -> b."""
+    out = []
+    n = len(poly)
+    for i in range(n):
+        p, q = poly[i], poly[(i + 1) % n]
+        sp = (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])
+        sq = (b[0] - a[0]) * (q[1] - a[1]) - (b[1] - a[1]) * (q[0] - a[0])
+        if sp >= 0:
+            out.append(p)
+        if (sp >= 0) != (sq >= 0):
+            t = sp / (sp - sq)
+            out.append(p + t * (q - p))
+    return out
+
+
+def bev_iou_ref(b1, b2):
+    """b = (l, h, w, x, y, z, ry, ...) rows of get_bbox_3d_result."""
+    p1 = _corners(b1[3], b1[5], b1[0], b1[2], b1[6])
+    p2 = _corners(b2[3], b2[5], b2[0], b2[2], b2[6])
+    def area(p):
+        p = np.asarray(p)
+        return 0.5 * (p[:, 0] * np.roll(p[:, 1], -1) - np.roll(p[:, 0], -1) * p[:, 1]).sum()
+    if area(p2) < 0:
+        p2 = p2[::-1]
+    poly = [p for p in p1]
+    for i in range(4):
+        poly = _clip(poly, p2[i], p2[(i + 1) % 4])
+        if not poly:
+            return 0.0
+    inter = abs(area(poly))
+    return inter / max(b1[0] * b1[2] + b2[0] * b2[2] - inter, 1e-12)
+
+
+def nms_bev_ref(bbox_3d, labels=None, group_offsets=None, iou_thr=0.25):
+    """Returns (keep [N] bool, min |IoU - thr| over the pairs that were compared)."""
+    b = np.asarray(bbox_3d, np.float64)
+    n = b.shape[0]
+    labels = np.zeros(n, np.int64) if labels is None else np.asarray(labels)
+    group_offsets = [0, n] if group_offsets is None else list(group_offsets)
+    keep = np.zeros(n, bool)
+    margin = np.inf
+    for lo, hi in zip(group_offsets[:-1], group_offsets[1:]):
+        for c in np.unique(labels[lo:hi]):
+            ids = lo + np.flatnonzero(labels[lo:hi] == c)
+            order = ids[np.argsort(-b[ids, 7], kind='stable')]
+            kept = []
+            for i in order:
+                ok = True
+                for j in kept:
+                    iou = bev_iou_ref(b[j], b[i])
+                    margin = min(margin, abs(iou - iou_thr))
+                    if iou > iou_thr:
+                        ok = False
+                        break
+                if ok:
+                    kept.append(i)
+            keep[kept] = True
+    return keep, margin

@@ -142,3 +142,50 @@ def test_score_head_rows_path_matches_reference_sequence(cuda_lib):
     assert torch.allclose(scores, ref, rtol=1e-3, atol=1e-5)
     assert torch.equal(bbox[:, :3], dims) and torch.equal(bbox[:, 3:6], t_vec) and torch.equal(bbox[:, 6], rows[:, 0])
     assert torch.equal(bbox[:, 7], scores)
+
+
+def _random_boxes(n, n_groups, seed):
+    rng = np.random.default_rng(seed)
+    b = np.zeros((n, 8), np.float32)
+    b[:, 0:3] = np.abs(rng.normal([3.9, 1.5, 1.6], [0.4, 0.1, 0.1], (n, 3)))
+    b[:, 3] = rng.uniform(-12, 12, n); b[:, 4] = 1.6; b[:, 5] = rng.uniform(5, 30, n)   # crowded: many overlaps
+    b[:, 6] = rng.uniform(-np.pi, np.pi, n)
+    b[:, 7] = rng.random(n)
+    b[::17, 7] = b[1::17, 7][:len(b[::17])]                                             # some exactly equal scores
+    labels = rng.integers(0, 3, n)
+    cuts = np.sort(rng.choice(np.arange(1, n), n_groups - 1, replace=False)) if n_groups > 1 else np.array([], int)
+    offsets = [0] + cuts.tolist() + [n]
+    return b, labels, offsets
+
+
+def test_bev_iou_oracle_known_answers():
+    a = np.array([4.0, 1.5, 2.0, 0.0, 0, 10.0, 0.0, 1.0])
+    assert so.bev_iou_ref(a, a) == pytest.approx(1.0)
+    b = a.copy(); b[3] = 2.0                     # shifted by half the length along x
+    assert so.bev_iou_ref(a, b) == pytest.approx(4.0 / 12.0)
+    c = a.copy(); c[6] = np.pi / 2               # same centre, rotated by 90 degrees: 2 x 2 square in common
+    assert so.bev_iou_ref(a, c) == pytest.approx(4.0 / 12.0)
+    d = a.copy(); d[6] = np.pi                   # a rectangle is symmetric under 180 degrees
+    assert so.bev_iou_ref(a, d) == pytest.approx(1.0)
+    e = a.copy(); e[3] = 10.0
+    assert so.bev_iou_ref(a, e) == 0.0
+    f = np.array([2.0, 1.5, 2.0, 0.0, 0, 10.0, np.pi / 4, 1.0])    # square rotated by 45 degrees vs the same square
+    g = f.copy(); g[6] = 0.0
+    assert so.bev_iou_ref(f, g) == pytest.approx((8 * (np.sqrt(2) - 1)) / (8 - 8 * (np.sqrt(2) - 1)), rel=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,n_groups,thr', [(400, 1, 0.25), (1500, 7, 0.25), (300, 40, 0.1), (64, 64, 0.25), (700, 1, 0.5)])
+def test_bev_nms_kernel_matches_oracle(cuda_lib, n, n_groups, thr):
+    from monorun_b200 import pnp
+    b, labels, offsets = _random_boxes(n, n_groups, seed=n + n_groups)
+    keep_ref, margin = so.nms_bev_ref(b, labels, offsets, thr)
+    keep = pnp.nms_bev(torch.from_numpy(b).cuda(), torch.from_numpy(labels).cuda(), offsets, thr).cpu().numpy()
+    assert margin > 1e-5, 'regenerate: an IoU sits on the threshold'     # fp32 on the device vs fp64 in the oracle
+    assert np.array_equal(keep, keep_ref), (keep != keep_ref).sum()
+    assert 0 < keep.sum() < n or n_groups == n
+    # one class, one image, defaults
+    k1 = pnp.nms_bev(torch.from_numpy(b).cuda()).cpu().numpy()
+    r1, m1 = so.nms_bev_ref(b)
+    assert m1 > 1e-5 and np.array_equal(k1, r1)
+    assert pnp.nms_bev(torch.zeros((0, 8), device='cuda')).shape == (0,)
