@@ -136,11 +136,15 @@ __device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, floa
         for (int r = 0; r < R; ++r) {
             const int p = rows.point(g, r, R, lane, valid[r]);
             pidx[r] = p;
-            Xf[r] = s3[sidx<LAYOUT, 3>(p, 0, P)]; Yf[r] = s3[sidx<LAYOUT, 3>(p, 1, P)]; Zf[r] = s3[sidx<LAYOUT, 3>(p, 2, P)];
-            uf[r] = s2[sidx<LAYOUT, 2>(p, 0, P)]; vf[r] = s2[sidx<LAYOUT, 2>(p, 1, P)];
-            w0[r] = sw[sidx<LAYOUT, WC>(p, 0, P)]; w1[r] = sw[sidx<LAYOUT, WC>(p, 1, P)];
-            w2[r] = (WMODE == MRPNP_W_FULL) ? sw[sidx<LAYOUT, WC>(p, WC - 1, P)] : 0.f;
-            if (!valid[r]) { w0[r] = 0.f; w1[r] = 0.f; w2[r] = 0.f; }
+            // padding lanes touch no memory (another lane may be rewriting the slot): a point at the object's origin
+            // with zero weights contributes nothing
+            Xf[r] = Yf[r] = Zf[r] = uf[r] = vf[r] = w0[r] = w1[r] = w2[r] = 0.f;
+            if (valid[r]) {
+                Xf[r] = s3[sidx<LAYOUT, 3>(p, 0, P)]; Yf[r] = s3[sidx<LAYOUT, 3>(p, 1, P)]; Zf[r] = s3[sidx<LAYOUT, 3>(p, 2, P)];
+                uf[r] = s2[sidx<LAYOUT, 2>(p, 0, P)]; vf[r] = s2[sidx<LAYOUT, 2>(p, 1, P)];
+                w0[r] = sw[sidx<LAYOUT, WC>(p, 0, P)]; w1[r] = sw[sidx<LAYOUT, WC>(p, 1, P)];
+                if (WMODE == MRPNP_W_FULL) w2[r] = sw[sidx<LAYOUT, WC>(p, WC - 1, P)];
+            }
         }
         // ---- fp32 projection: Jacobian, clip detection, (first evaluation) residuals ----
         float qxf[R], qzf[R], izf[R], xnf[R], ynf[R], euf[R], evf[R];
@@ -270,11 +274,14 @@ __device__ __forceinline__ void eval_pass_delta(const float* s3, float* s2, cons
         for (int r = 0; r < R; ++r) {
             const int p = rows.point(g, r, R, lane, valid[r]);
             pidx[r] = p;
-            X[r] = s3[sidx<LAYOUT, 3>(p, 0, P)]; Y[r] = s3[sidx<LAYOUT, 3>(p, 1, P)]; Z[r] = s3[sidx<LAYOUT, 3>(p, 2, P)];
-            e0[r] = s2[sidx<LAYOUT, 2>(p, 0, P)]; e1[r] = s2[sidx<LAYOUT, 2>(p, 1, P)];
-            w0[r] = sw[sidx<LAYOUT, WC>(p, 0, P)]; w1[r] = sw[sidx<LAYOUT, WC>(p, 1, P)];
-            w2[r] = (WMODE == MRPNP_W_FULL) ? sw[sidx<LAYOUT, WC>(p, WC - 1, P)] : 0.f;
-            if (!valid[r]) { w0[r] = 0.f; w1[r] = 0.f; w2[r] = 0.f; }  // padding lanes contribute nothing
+            // padding lanes touch no memory: a point at the object's origin with zero weights contributes nothing
+            X[r] = Y[r] = Z[r] = e0[r] = e1[r] = w0[r] = w1[r] = w2[r] = 0.f;
+            if (valid[r]) {
+                X[r] = s3[sidx<LAYOUT, 3>(p, 0, P)]; Y[r] = s3[sidx<LAYOUT, 3>(p, 1, P)]; Z[r] = s3[sidx<LAYOUT, 3>(p, 2, P)];
+                e0[r] = s2[sidx<LAYOUT, 2>(p, 0, P)]; e1[r] = s2[sidx<LAYOUT, 2>(p, 1, P)];
+                w0[r] = sw[sidx<LAYOUT, WC>(p, 0, P)]; w1[r] = sw[sidx<LAYOUT, WC>(p, 1, P)];
+                if (WMODE == MRPNP_W_FULL) w2[r] = sw[sidx<LAYOUT, WC>(p, WC - 1, P)];
+            }
         }
         PointDelta d[R];
 #pragma unroll
