@@ -145,40 +145,77 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             const bool in_range = row < cp.rows_total;
             const bool interior = in_range && y >= 1 && y <= cp.h && x >= 1 && x <= cp.w;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * cp.cout_pad);
-            for (int c0 = 0; c0 < cp.cout_pad; c0 += 16) {
-                uint32_t v[16];
+            // 32 accumulator columns per TMEM round trip (two 16-column loads, one wait); bias and per-RoI latent bias
+            // come in as float4 (every lane reads the same bias: broadcast loads)
+            const float* rb = (cp.row_bias && in_range) ? cp.row_bias + (size_t)roi * cp.cout : nullptr;
+            for (int c0 = 0; c0 < cp.cout_pad; c0 += 32) {
+                uint32_t v[32];
+                const bool two = c0 + 16 < cp.cout_pad;
                 tmem_ld16(taddr + (uint32_t)c0, v);   // whole warp, also for rows past the end
+                if (two) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);
                 tmem_ld_wait();
-                float f[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = c0 + j;
-                    float a = __uint_as_float(v[j]);
-                    if (c < cp.cout) {
-                        if (cp.bias) a += __ldg(cp.bias + c);
-                        if (cp.relu) a = fmaxf(a, 0.f);
-                        if (cp.row_bias && in_range) a += __ldg(cp.row_bias + (size_t)roi * cp.cout + c);
-                    }
-                    f[j] = interior ? a : 0.f;
-                }
-                if (cp.out_mode == kOutBf16Rows) {
-                    if (in_range && c0 < cp.cout) {
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(cp.out) + (size_t)row * cp.cout + c0);
-                        dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                        dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
-                    }
-                } else if (cp.out_mode == kOutF32Rows) {
-                    if (in_range) {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(cp.out) + (size_t)row * cp.cout_pad + c0);
+                for (int hh = 0; hh < 2; ++hh) {
+                    if (hh == 1 && !two) break;
+                    const int cb = c0 + 16 * hh;
+                    float f[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    }
-                } else {
-                    if (interior) {
-                        float* dst = reinterpret_cast<float*>(cp.out) + ((size_t)roi * cp.cout * cp.h + (y - 1)) * cp.w + (x - 1);
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[16 * hh + j]);
+                    if (cb + 16 <= cp.cout && (cp.cout & 3) == 0) {   // full chunk: vector loads
+                        if (cp.bias) {
+                            const float4* b4 = reinterpret_cast<const float4*>(cp.bias + cb);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < cp.cout) dst[(size_t)(c0 + j) * cp.h * cp.w] = f[j];
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 t = __ldg(b4 + q);
+                                f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w;
+                            }
+                        }
+                        if (cp.relu) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        if (rb) {
+                            const float4* r4 = reinterpret_cast<const float4*>(rb + cb);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 t = __ldg(r4 + q);
+                                f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int c = cb + j;
+                            if (c < cp.cout) {
+                                if (cp.bias) f[j] += __ldg(cp.bias + c);
+                                if (cp.relu) f[j] = fmaxf(f[j], 0.f);
+                                if (rb) f[j] += __ldg(rb + c);
+                            }
+                        }
+                    }
+                    if (!interior) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+                    }
+                    if (cp.out_mode == kOutBf16Rows) {
+                        if (in_range && cb < cp.cout) {
+                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(cp.out) + (size_t)row * cp.cout + cb);
+                            dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                            dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                        }
+                    } else if (cp.out_mode == kOutF32Rows) {
+                        if (in_range) {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(cp.out) + (size_t)row * cp.cout_pad + cb);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        }
+                    } else {
+                        if (interior) {
+                            float* dst = reinterpret_cast<float*>(cp.out) + ((size_t)roi * cp.cout * cp.h + (y - 1)) * cp.w + (x - 1);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (cb + j < cp.cout) dst[(size_t)(cb + j) * cp.h * cp.w] = f[j];
+                        }
                     }
                 }
             }
