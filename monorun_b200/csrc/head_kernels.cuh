@@ -258,25 +258,31 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
     }
     const int np = pmax - pmin + 1;
     const float* src = x + (size_t)n * c * hw;
+    // one channel per warp iteration (no per-element division), lanes along the contiguous pixels
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     if (np > 0) {
-        for (int i = threadIdx.x; i < c * np; i += blockDim.x) {
-            const int ch = i / np, p = i - ch * np;
-            tile[p * ld + ch] = __float2bfloat16_rn(__ldg(src + (size_t)ch * hw + pmin + p));
+        for (int ch = warp; ch < c; ch += nwarps) {
+            const float* sp = src + (size_t)ch * hw + pmin;
+            for (int p = lane; p < np; p += 32) tile[p * ld + ch] = __float2bfloat16_rn(__ldg(sp + p));
         }
     }
     __syncthreads();
     __nv_bfloat16* dst = out + (size_t)n * hp * wp * c;
     const int pairs = c / 2;
-    for (int i = threadIdx.x; i < (r1 - r0) * pairs; i += blockDim.x) {
-        const int r = r0 + i / pairs, cc = (i % pairs) * 2;
+    // one padded row per warp iteration, lanes along the channel pairs
+    for (int r = r0 + warp; r < r1; r += nwarps) {
         const int y = r / wp, xx = r - y * wp;
-        __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
-        if (y >= 1 && y <= h && xx >= 1 && xx <= w) {
-            const __nv_bfloat16* t = tile + ((y - 1) * w + (xx - 1) - pmin) * ld + cc;
-            v.x = t[0];
-            v.y = t[1];
+        const bool interior = y >= 1 && y <= h && xx >= 1 && xx <= w;
+        const __nv_bfloat16* t = tile + ((y - 1) * w + (xx - 1) - pmin) * ld;
+        __nv_bfloat162* drow = reinterpret_cast<__nv_bfloat162*>(dst + (size_t)r * c);
+        for (int q = lane; q < pairs; q += 32) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+            if (interior) {
+                v.x = t[2 * q];
+                v.y = t[2 * q + 1];
+            }
+            drow[q] = v;
         }
-        *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)r * c + cc) = v;
     }
 }
 
