@@ -422,13 +422,13 @@ class MonoRUnRoIHead(nn.Module):
             distance_z_depth=ph.distance_mode == 'z-depth', calib_scoring=calib_scoring,
             det_scores=det_scores if mult_2d_score else None)
 
-    def nms_3d(self, bbox_3d, det_labels, group_offsets=None, nms_thr=None):
+    def nms_3d(self, bbox_3d, det_labels, group_offsets=None, nms_thr=None, max_group=None):
         """monorun_roi_head.py:619-655 for all images and classes in one launch: keep mask [N] of the class-wise rotated
         BEV NMS (``nms_thr`` defaults to test_cfg.nms_3d_thr, configs/kitti_multiclass.py:195-210)."""
         from . import pnp
         if nms_thr is None:
             nms_thr = getattr(self.test_cfg, 'nms_3d_thr', 0.25) if self.test_cfg is not None else 0.25
-        return pnp.nms_bev(bbox_3d, det_labels, group_offsets, nms_thr)
+        return pnp.nms_bev(bbox_3d, det_labels, group_offsets, nms_thr, max_group=max_group)
 
     def forward_3d(self, noc_feats, bbox_3d_rois, det_labels, latent_pred, dimensions_pred, dimensions_var,
                    cam_intrinsic, img_shape, flip=False, distance_pred=None, cov_correction=True, fused=False,

@@ -198,9 +198,11 @@ def finish_scores(score_logits, rows, dims, det_scores=None, pre_sigmoid=True):
     return scores, bbox
 
 
-def nms_bev(bbox_3d, labels=None, group_offsets=None, iou_thr=0.25):
+def nms_bev(bbox_3d, labels=None, group_offsets=None, iou_thr=0.25, max_group=None):
     """``mrpnp_nms_bev``: class-wise rotated BEV NMS per image.  bbox_3d [N,8] (l,h,w,x,y,z,ry,score), labels [N]
-    int64 or None, group_offsets [G+1] int32 tensor or python list (None = one image).  Returns keep [N] bool."""
+    int64 or None, group_offsets [G+1] int32 tensor or python list (None = one image).  Returns keep [N] bool.
+    With a device tensor of offsets pass ``max_group`` (an upper bound of the largest image) to avoid a host sync --
+    required inside CUDA-graph capture."""
     dev = bbox_3d.device
     ctx = get_ctx(dev)
     n = bbox_3d.shape[0]
@@ -214,7 +216,8 @@ def nms_bev(bbox_3d, labels=None, group_offsets=None, iou_thr=0.25):
         max_group = max(sizes) if sizes else 0
         group_offsets = torch.tensor(group_offsets, dtype=torch.int32, device=dev)
     else:
-        max_group = int((group_offsets[1:] - group_offsets[:-1]).max().item())
+        if max_group is None:
+            max_group = int((group_offsets[1:] - group_offsets[:-1]).max().item())
         group_offsets = group_offsets.to(device=dev, dtype=torch.int32).contiguous()
     b = _f32c(bbox_3d)
     lab = labels.to(torch.int64).contiguous() if labels is not None else None

@@ -189,3 +189,60 @@ def test_bev_nms_kernel_matches_oracle(cuda_lib, n, n_groups, thr):
     r1, m1 = so.nms_bev_ref(b)
     assert m1 > 1e-5 and np.array_equal(k1, r1)
     assert pnp.nms_bev(torch.zeros((0, 8), device='cuda')).shape == (0,)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_of_the_native_sequence(cuda_lib):
+    """RoI features -> dense head (tcgen05) -> fused PnP -> score stage -> 3-D NMS captured into one CUDA graph
+    (monorun_b200.graph.GraphedSequence): no entry point synchronises or allocates outside torch's allocator, and the
+    replay returns bitwise what the eager sequence returns -- also on fresh inputs copied into the static buffers."""
+    from tests.test_host import _roi_head_cfg
+    from monorun_b200 import synth
+    from monorun_b200.graph import GraphedSequence
+    torch.manual_seed(0)
+    head = monorun_b200.build_head(_roi_head_cfg()).cuda().eval()
+    head.init_weights()
+    n = 48
+    nh, ph = head.noc_head, head.pose_head
+    C = nh.num_classes
+    cam = None
+
+    def inputs(seed):
+        b = synth.make_batch(n, config=3, mode='S1', rng=np.random.default_rng(seed))
+        raw = synth.to_head_raw(b, rng=np.random.default_rng(seed + 1))
+        d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        lab = d(b['labels']).long()
+        all_pred = torch.zeros(n, 5 * C, 28, 28, device='cuda')
+        idx = torch.arange(n, device='cuda')
+        for c in range(3):
+            all_pred[idx, 3 * lab + c] = d(raw['noc_pred'])[:, c]
+        for c in range(2):
+            all_pred[idx, 3 * C + 2 * lab + c] = d(raw['proj_logstd'])[:, c]
+        g = torch.Generator(device='cuda').manual_seed(seed)
+        return (torch.randn(n, 256, 14, 14, device='cuda', generator=g), torch.randn(n, 16, device='cuda', generator=g),
+                all_pred, d(raw['rois']), d(raw['dims']), d(raw['dims_var']), torch.randn(n, 1024, device='cuda', generator=g),
+                torch.rand(n, device='cuda', generator=g), lab), d(b['cam_mat'][None])
+
+    ins, cam = inputs(3)
+    img_shapes = cam.new_tensor((375, 1242))[None]
+    off = torch.tensor([0, 20, n], dtype=torch.int32, device='cuda')
+
+    def sequence(feats, latent, all_pred, rois, dims, dims_var, reg, det, lab):
+        head_out = nh.forward_all(feats, latent, False, native=True)
+        ret_val, yaw, t_vec, cov, _ = ph.forward_fused(all_pred, None, rois, dims, dims_var, cam, img_shapes, nh.coord_coder,
+                                                       head.projection_head.proj_error_coder, labels=lab, num_classes=C)
+        rows = torch.cat([yaw, t_vec, cov.reshape(n, 16), ret_val.float()[:, None], torch.zeros(n, 3, device='cuda')], 1)
+        scores, bbox, _ = head.forward_scores(rows, reg, dims, det_scores=det, cov_correction=True, calib_scoring=True)
+        keep = head.nms_3d(bbox, lab, off, max_group=28)
+        return head_out, bbox, keep
+
+    graphed = GraphedSequence(sequence, ins)
+    for seed in (3, 11):
+        ins, _ = inputs(seed)
+        with torch.no_grad():
+            eager = [t.clone() for t in sequence(*ins)]
+        out = graphed(*ins)
+        torch.cuda.synchronize()
+        for a, b in zip(out, eager):
+            assert torch.equal(a, b)
+        assert (eager[1][:, 7] >= 0).all() and eager[2].any()

@@ -80,3 +80,33 @@ print(json.dumps({'rois': n, 'images': a.images,
                          'score stage (2 launches + 3 library GEMMs)': acc[2], '3-D NMS (1 launch)': acc[3], 'total': acc.sum()},
                   'rois_per_s': n / acc.sum() * 1e3, 'valid_poses': float(ret_val.float().mean().item()),
                   'kept_after_nms': int(keep.sum().item())}))
+
+# ---- the same sequence captured into ONE CUDA graph (launch-bound regime: one image's worth of RoIs) ----
+from monorun_b200.graph import GraphedSequence
+off_t = torch.tensor(offsets, dtype=torch.int32, device='cuda')
+max_group = max(b - a_ for a_, b in zip(offsets[:-1], offsets[1:]))
+
+def sequence(feats_, latent_, all_pred_, rois_, dims_, dims_var_, reg_, det_, lab_):
+    head_out = nh.forward_all(feats_, latent_, False, native=True)
+    ret_val, yaw, t_vec, cov, _ = ph.forward_fused(all_pred_, None, rois_, dims_, dims_var_, cam, img_shapes, nh.coord_coder,
+                                                   head.projection_head.proj_error_coder, labels=lab_, num_classes=C)
+    rows = torch.cat([yaw, t_vec, cov.reshape(n, 16), ret_val.float()[:, None], torch.zeros(n, 3, device='cuda')], 1)
+    scores, bbox, cal = head.forward_scores(rows, reg_, dims_, det_scores=det_, cov_correction=True, calib_scoring=True)
+    keep = head.nms_3d(bbox, lab_, off_t, max_group=max_group)
+    return head_out, bbox, keep
+
+ins = (feats, latent, all_pred, rois4, dimsr, dims_varr, reg, det, lab)
+try:
+    g = GraphedSequence(sequence, ins)
+    for _ in range(3): g(*ins)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps): out_g = g(*ins)
+    e1.record(); torch.cuda.synchronize()
+    ms_graph = e0.elapsed_time(e1) / a.steps
+    same = bool(torch.equal(out_g[2], keep))
+    print(json.dumps({'rois': n, 'cuda_graph_ms': ms_graph, 'eager_ms': float(acc.sum()), 'rois_per_s_graph': n / ms_graph * 1e3,
+                      'keep_mask_equal_to_eager': same}))
+except Exception as exc:
+    print(json.dumps({'cuda_graph': 'failed', 'error': f'{type(exc).__name__}: {exc}'[:300]}))
