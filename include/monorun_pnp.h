@@ -199,6 +199,37 @@ int mrpnp_finish_scores(mrpnp_ctx* ctx, const float* score_logits, const float* 
 int mrpnp_nms_bev(mrpnp_ctx* ctx, const float* bbox_3d, const int64_t* labels, const int32_t* group_offsets,
                   int32_t n_groups, int32_t max_group, float iou_thr, uint8_t* keep, void* stream);
 
+/* The reference's two 7-parameter solvers, batched on the device -- one call replaces N calls of
+ *   pnp_noc_uncert      (monorun/ops/least_squares/src/ext.h:15-28, pnp_uncert_cpu.cpp:294-334)  weight_mode MRPNP_W_ISTD
+ *   pnp_noc_cov_uncert  (monorun/ops/least_squares/src/ext.h:30-43, pnp_uncert_cpu.cpp:336-377)  weight_mode MRPNP_W_FULL
+ * Unknowns per object: [log l, log h, log w, yaw, tx, ty, tz].  The points are NORMALISED object coordinates; the
+ * solver scales them by exp(log dims), so the dimensions are refined together with the pose under a prior
+ * r_k = logdim_wgt_k (x_k - logdim_k) (DimErrorArray, .cpp:77-104).  Every residual block (one per point, one for
+ * the prior) goes through ceres::HuberLoss(huber_delta).  Ceres 1.14 default trust-region options, fp64 arithmetic.
+ *   coords_3d [N,3,P]|[N,P,3], coords_2d [N,2,P]|[N,P,2], weights [N,2|3,P]|[N,P,2|3] float (layout as mrpnp_solve)
+ *   logdim, logdim_wgt [N,3] float;  cam_mats [N|1,3,3];  uv_range [N|1,4];  init_dimpose [N,7] float
+ *   inlier_in [N,ceil(P/32)] packed uint32 or NULL (all points; the reference passes the points it wants solved)
+ *   result [N,12] DOUBLE: dimpose[7], valid (summary.IsSolutionUsable), lm_iterations, final_cost, cost_evals,
+ *   termination (0 convergence, 1 no convergence, 2 failure). */
+typedef struct mrpnp_noc_params {
+    int32_t n_obj;
+    int32_t n_pts;          /* 1 <= P <= MRPNP_MAX_POINTS */
+    int32_t layout;         /* MRPNP_LAYOUT_* */
+    int32_t weight_mode;    /* MRPNP_W_ISTD or MRPNP_W_FULL */
+    int32_t cam_stride;     /* 0 or 9 */
+    int32_t range_stride;   /* 0 or 4 */
+    int32_t max_iterations; /* 0: Ceres default 50 */
+    int32_t reserved;
+    float z_min;            /* clips[0] */
+    float huber_delta;      /* `delta` of ext.h:27 / :42 */
+} mrpnp_noc_params;
+
+int mrpnp_solve_noc(mrpnp_ctx* ctx, const mrpnp_noc_params* p,
+                    const float* coords_3d, const float* coords_2d, const float* weights,
+                    const float* logdim, const float* logdim_wgt,
+                    const float* cam_mats, const float* uv_range, const float* init_dimpose,
+                    const uint32_t* inlier_in, double* result, void* stream);
+
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);
 

@@ -10,6 +10,7 @@
 #include "pnp_kernel_fast.cuh"
 #include "pnp_score.cuh"
 #include "pnp_nms.cuh"
+#include "pnp_noc.cuh"
 #ifdef MRPNP_WITH_POOL  // pooled staging buffers + small slots: measured slower, kept for reference
 #include "pnp_kernel_pool.cuh"
 #endif
@@ -429,6 +430,44 @@ int mrpnp_nms_bev(mrpnp_ctx* ctx, const float* bbox_3d, const int64_t* labels, c
     MR_CUDA(cudaFuncSetAttribute(mrpnp::nms_bev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mrpnp::nms_bev_kernel<<<n_groups, mrpnp::kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         bbox_3d, reinterpret_cast<const long long*>(labels), group_offsets, iou_thr, cap, keep);
+    MR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return MRPNP_OK;
+}
+
+int mrpnp_solve_noc(mrpnp_ctx* ctx, const mrpnp_noc_params* p,
+                    const float* coords_3d, const float* coords_2d, const float* weights,
+                    const float* logdim, const float* logdim_wgt,
+                    const float* cam_mats, const float* uv_range, const float* init_dimpose,
+                    const uint32_t* inlier_in, double* result, void* stream) {
+    if (!ctx || !p) return fail(MRPNP_ERR_ARG, "NULL argument%s");
+    if (p->n_obj < 0) return fail(MRPNP_ERR_ARG, "n_obj < 0%s");
+    if (p->n_pts < 1 || p->n_pts > MRPNP_MAX_POINTS) return fail(MRPNP_ERR_ARG, "n_pts out of range%s");
+    if (p->layout != MRPNP_LAYOUT_PLANAR && p->layout != MRPNP_LAYOUT_INTERLEAVED) return fail(MRPNP_ERR_ARG, "bad layout%s");
+    if (p->weight_mode != MRPNP_W_ISTD && p->weight_mode != MRPNP_W_FULL)
+        return fail(MRPNP_ERR_ARG, "weight_mode must be MRPNP_W_ISTD or MRPNP_W_FULL%s");
+    if ((p->cam_stride != 0 && p->cam_stride != 9) || (p->range_stride != 0 && p->range_stride != 4))
+        return fail(MRPNP_ERR_ARG, "bad cam_stride / range_stride%s");
+    if (!(p->huber_delta > 0.f)) return fail(MRPNP_ERR_ARG, "huber_delta must be positive%s");
+    if (p->max_iterations < 0) return fail(MRPNP_ERR_ARG, "max_iterations < 0%s");
+    if (p->n_obj == 0) return MRPNP_OK;
+    if (!coords_3d || !coords_2d || !weights || !logdim || !logdim_wgt || !cam_mats || !uv_range || !init_dimpose || !result)
+        return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    mrnoc::KParams kp;
+    kp.coords_3d = coords_3d; kp.coords_2d = coords_2d; kp.weights = weights;
+    kp.logdim = logdim; kp.logdim_wgt = logdim_wgt; kp.cam_mats = cam_mats; kp.uv_range = uv_range;
+    kp.init = init_dimpose; kp.inlier = inlier_in; kp.result = result;
+    kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.planar = p->layout == MRPNP_LAYOUT_PLANAR;
+    kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride; kp.max_iterations = p->max_iterations;
+    kp.z_min = p->z_min; kp.delta = p->huber_delta;
+    const int ctas = std::min((p->n_obj + mrnoc::kWarpsPerCta - 1) / mrnoc::kWarpsPerCta, ctx->num_sms * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->weight_mode == MRPNP_W_FULL)
+        mrnoc::pnp_noc_kernel<true><<<ctas, mrnoc::kWarpsPerCta * 32, 0, st>>>(kp);
+    else
+        mrnoc::pnp_noc_kernel<false><<<ctas, mrnoc::kWarpsPerCta * 32, 0, st>>>(kp);
     MR_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return MRPNP_OK;

@@ -153,6 +153,49 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
     return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None), res64
 
 
+def solve_noc_batched(coords_3d, coords_2d, weights, logdim, logdim_wgt, cam_mats, uv_range, init_dimpose,
+                      inlier_mask=None, *, layout='planar', weight_mode='istd', z_min=0.5, huber_delta=1.0,
+                      max_iterations=50):
+    """The reference's 7-parameter solvers, batched on the device -- direct wrapper of ``mrpnp_solve_noc``
+    (``pnp_noc_uncert`` for weight_mode 'istd', ``pnp_noc_cov_uncert`` for 'full'; ext.h:15-43).
+
+    coords_3d holds NORMALISED object coordinates; the unknowns are [log l, log h, log w, yaw, tx, ty, tz] with the
+    prior ``logdim_wgt * (x[:3] - logdim)`` and ``HuberLoss(huber_delta)`` on every residual block.  Tensor shapes as
+    :func:`solve_batched`; logdim, logdim_wgt [N,3]; init_dimpose [N,7].
+
+    Returns result [N,12] float64: dimpose[7], valid, lm_iterations, final_cost, cost_evals, termination."""
+    dev = coords_3d.device
+    ctx = get_ctx(dev)
+    n = coords_3d.shape[0]
+    planar = layout == 'planar'
+    n_pts = coords_3d[0].numel() // 3 if n else (coords_3d.shape[2:].numel() if planar else coords_3d.shape[1])
+    if weight_mode not in ('istd', 'full'):
+        raise ValueError("weight_mode must be 'istd' or 'full'")
+    result = torch.empty((n, 12), dtype=torch.float64, device=dev)
+    if n == 0:
+        return result
+    c3, c2, w = _f32c(coords_3d), _f32c(coords_2d), _f32c(weights)
+    cam, rng = _f32c(cam_mats).reshape(-1, 9), _f32c(uv_range).reshape(-1, 4)
+    if cam.shape[0] not in (1, n) or rng.shape[0] not in (1, n):
+        raise ValueError('cam_mats / uv_range must have batch size 1 or N')
+    ld, lw, init = _f32c(logdim).reshape(n, 3), _f32c(logdim_wgt).reshape(n, 3), _f32c(init_dimpose).reshape(n, 7)
+    inl_in = pack_mask(inlier_mask.reshape(n, n_pts).bool()) if inlier_mask is not None else None
+    p = _native.ffi.new('mrpnp_noc_params*')
+    p.n_obj, p.n_pts = n, n_pts
+    p.layout = C['MRPNP_LAYOUT_PLANAR'] if planar else C['MRPNP_LAYOUT_INTERLEAVED']
+    p.weight_mode = C['MRPNP_W_FULL'] if weight_mode == 'full' else C['MRPNP_W_ISTD']
+    p.cam_stride = 9 if cam.shape[0] == n and n > 1 else 0
+    p.range_stride = 4 if rng.shape[0] == n and n > 1 else 0
+    p.max_iterations = int(max_iterations)
+    p.z_min, p.huber_delta = float(z_min), float(huber_delta)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_solve_noc(
+            ctx.ptr, p, _ptr(c3), _ptr(c2), _ptr(w), _ptr(ld), _ptr(lw), _ptr(cam), _ptr(rng), _ptr(init),
+            _ptr(inl_in, 'uint32_t*'), _ptr(result, 'double*'), _native.ffi.cast('void*', stream)))
+    return result
+
+
 def pose_features(rows, dims, cov_calib_logscale=None, cov_correction_sd=0.0, distance_z_depth=False, use_calib=False,
                   pose_norm=None):
     """``mrpnp_pose_features``: result rows [N,24] + dims [N,3] -> (features [N,17], pose_cov_calib [N,16])."""

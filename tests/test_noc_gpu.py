@@ -1,0 +1,122 @@
+"""GPU parity tests (-m gpu) of mrpnp_solve_noc -- the batched CUDA form of the reference's pnp_noc_uncert /
+pnp_noc_cov_uncert (ext.h:15-43) -- against the CPU oracle (oracle/pnp_noc_oracle.cpp) on identical seeded inputs,
+called through the C ABI.  The kernel computes in fp64; it is held to 1e-7 on objects whose trust-region decisions
+match the oracle's (>= 95 %; the rest differ by a function-tolerance decision and must end at the same cost)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.noc_cases import make_case, oracle_solve
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nd():
+    from oracle import noc_driver
+    noc_driver.build()
+    return noc_driver
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_solve(c, delta, full, mask=None, layout='interleaved', per_object_cam=False):
+    from monorun_b200 import pnp
+    n = c['noc'].shape[0]
+    noc, c2, w = dev(c['noc']), dev(c['c2']), dev(c['w'])
+    if layout == 'planar':
+        noc, c2, w = (t.permute(0, 2, 1).contiguous() for t in (noc, c2, w))
+    cam, rg = dev(c['cam']), dev(c['uv_range'])
+    if per_object_cam:
+        cam, rg = cam.expand(n, 3, 3).contiguous(), rg.expand(n, 4).contiguous()
+    res = pnp.solve_noc_batched(noc, c2, w, dev(c['logdim']), dev(c['logdim_wgt']), cam, rg, dev(c['init']),
+                                dev(mask) if mask is not None else None, layout=layout,
+                                weight_mode='full' if full else 'istd', huber_delta=delta)
+    torch.cuda.synchronize()
+    return res.cpu().numpy()
+
+
+def check(g, r, min_same=0.95):
+    same = g[:, 10] == r['stats'][:, 1]
+    assert same.mean() >= min_same, same.mean()
+    np.testing.assert_allclose(g[same, :7], r['dimpose'][same], rtol=1e-7, atol=1e-8)
+    np.testing.assert_array_equal(g[same, 8], r['stats'][same, 0])
+    np.testing.assert_array_equal(g[:, 7] > 0, r['val'])
+    np.testing.assert_allclose(g[:, 9], r['cost'], rtol=1e-4)
+    np.testing.assert_allclose(g[same, 9], r['cost'][same], rtol=1e-10)
+
+
+@pytest.mark.parametrize('full', [False, True])
+@pytest.mark.parametrize('layout', ['interleaved', 'planar'])
+def test_noc_parity_with_oracle(cuda_lib, nd, full, layout):
+    c = make_case(256, full=full, mode='S1' if full else 'S0', cfg=3 if full else 2)
+    for delta in (0.5, 1.5, 1e9):
+        check(gpu_solve(c, delta, full, layout=layout), oracle_solve(nd, c, delta, full), min_same=0.99)
+
+
+def test_noc_far_start_masks_and_per_object_cameras(cuda_lib, nd):
+    c = make_case(256, far=True, seed=5)
+    rng = np.random.default_rng(3)
+    mask = rng.uniform(size=c['noc'].shape[:2]) < rng.uniform(0.2, 1.0, (256, 1))
+    mask[0] = False
+    mask[0, :3] = True
+    r = oracle_solve(nd, c, 1.0, False, mask=mask)
+    assert (r['stats'][:, 1] > r['stats'][:, 2]).any()
+    for layout in ('interleaved', 'planar'):
+        check(gpu_solve(c, 1.0, False, mask=mask, layout=layout, per_object_cam=True), r)
+
+
+def test_noc_odd_point_counts(cuda_lib, nd):
+    """P not a multiple of 32, and a single point (the prior alone keeps the dimensions determined)."""
+    c = make_case(32)
+    for p in (1, 7, 33, 500):
+        cc = dict(c, noc=np.ascontiguousarray(c['noc'][:, :p]), c2=np.ascontiguousarray(c['c2'][:, :p]),
+                  w=np.ascontiguousarray(c['w'][:, :p]))
+        r = oracle_solve(nd, cc, 1.5, False)
+        g = gpu_solve(cc, 1.5, False)
+        np.testing.assert_array_equal(g[:, 7] > 0, r['val'])
+        same = g[:, 10] == r['stats'][:, 1]
+        assert same.mean() >= 0.9
+        np.testing.assert_allclose(g[same, :7], r['dimpose'][same], rtol=1e-6, atol=1e-7)
+
+
+def test_noc_stiff_prior_equals_the_4_parameter_solver_at_full_size(cuda_lib):
+    """Size-independent property at 8192 objects: with the dimensions pinned and the loss off, mrpnp_solve_noc must
+    return the pose mrpnp_solve returns (fp64 kernel) for the metric points."""
+    from monorun_b200 import pnp
+    n = 8192
+    c = make_case(n, prior_sd=0.0, prior_wgt=1e6, mode='S1', cfg=3)
+    g = gpu_solve(c, 1e9, False)
+    metric = c['noc'].astype(np.float64) * np.exp(c['logdim'].astype(np.float64))[:, None, :]
+    res, _, r64 = pnp.solve_batched(dev(metric.astype(np.float32)), dev(c['c2']), dev(c['w']), dev(c['cam']),
+                                    dev(c['uv_range']), dev(c['init'][:, 3:]),
+                                    torch.ones((n, c['noc'].shape[1]), dtype=torch.bool, device='cuda'),
+                                    layout='interleaved', weight_mode='istd', precision='fp64', cov_mode='none',
+                                    return_inlier_mask=False, return_fp64=True)
+    torch.cuda.synchronize()
+    r64 = r64.cpu().numpy()
+    assert (g[:, 7] > 0).all()
+    t_err = np.linalg.norm(g[:, 4:7] - r64[:, 1:4], axis=1) / np.linalg.norm(r64[:, 1:4], axis=1)
+    # metric points are rounded to fp32 for mrpnp_solve, normalised ones times exp(logdim) are not: 1e-5, not 1e-9
+    assert np.quantile(t_err, 0.99) < 1e-5 and t_err.max() < 1e-3, (np.quantile(t_err, 0.99), t_err.max())
+    assert np.abs(g[:, 3] - r64[:, 0]).max() < 1e-4
+    np.testing.assert_allclose(g[:, :3], c['logdim'], atol=1e-6)
+
+
+def test_noc_argument_errors(cuda_lib):
+    from monorun_b200 import pnp
+    c = make_case(2)
+    with pytest.raises(ValueError):
+        pnp.solve_noc_batched(dev(c['noc']), dev(c['c2']), dev(c['w']), dev(c['logdim']), dev(c['logdim_wgt']),
+                              dev(c['cam']), dev(c['uv_range']), dev(c['init']), layout='interleaved',
+                              weight_mode='logstd')
+    with pytest.raises(RuntimeError):
+        pnp.solve_noc_batched(dev(c['noc']), dev(c['c2']), dev(c['w']), dev(c['logdim']), dev(c['logdim_wgt']),
+                              dev(c['cam']), dev(c['uv_range']), dev(c['init']), layout='interleaved',
+                              huber_delta=0.0)
+    out = pnp.solve_noc_batched(dev(c['noc'][:0]), dev(c['c2'][:0]), dev(c['w'][:0]), dev(c['logdim'][:0]),
+                                dev(c['logdim_wgt'][:0]), dev(c['cam']), dev(c['uv_range']), dev(c['init'][:0]),
+                                layout='interleaved')
+    assert out.shape == (0, 12)

@@ -1,0 +1,62 @@
+"""Times mrpnp_solve_noc (7-parameter Huber solvers, fp64 kernel) on the B200 next to the CPU oracle.
+Usage: python tools/bench_noc.py [--n 8192] [--out gpurun_out/noc_bench.json]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from monorun_b200 import pnp  # noqa: E402
+from tests.noc_cases import make_case, oracle_solve  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=8192)
+    ap.add_argument('--cpu-sample', type=int, default=512)
+    ap.add_argument('--out', default='gpurun_out/noc_bench.json')
+    a = ap.parse_args()
+    out = {}
+    for full in (False, True):
+        c = make_case(a.n, full=full, mode='S1', cfg=3)
+        d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in c.items()
+             if k in ('noc', 'c2', 'w', 'logdim', 'logdim_wgt', 'cam', 'uv_range', 'init')}
+        planar = [d[k].permute(0, 2, 1).contiguous() for k in ('noc', 'c2', 'w')]
+
+        def run():
+            return pnp.solve_noc_batched(planar[0], planar[1], planar[2], d['logdim'], d['logdim_wgt'], d['cam'],
+                                         d['uv_range'], d['init'], layout='planar',
+                                         weight_mode='full' if full else 'istd', huber_delta=1.5)
+        for _ in range(3):
+            res = run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            res = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        res = res.cpu().numpy()
+        from oracle import noc_driver as nd
+        m = a.cpu_sample
+        cs = {k: (v[:m] if isinstance(v, np.ndarray) and v.shape[0] == a.n else v) for k, v in c.items()}
+        t0 = time.perf_counter()
+        r = oracle_solve(nd, cs, 1.5, full, threads=0)
+        cpu_s = time.perf_counter() - t0
+        same = (res[:m, 10] == r['stats'][:, 1]).mean()
+        out['full' if full else 'diag'] = dict(
+            n=a.n, ms=ms, objects_per_s=a.n / ms * 1e3, mean_cost_evals=float(res[:, 10].mean()),
+            cpu_objects_per_s=m / cpu_s, cpu_threads=os.cpu_count(), cpu_sample=m, same_decisions=float(same),
+            max_param_diff=float(np.abs(res[:m, :7] - r['dimpose']).max()), valid=float((res[:, 7] > 0).mean()))
+        print(out)
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump(out, open(a.out, 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()
