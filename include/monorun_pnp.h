@@ -230,6 +230,20 @@ int mrpnp_solve_noc(mrpnp_ctx* ctx, const mrpnp_noc_params* p,
                     const float* cam_mats, const float* uv_range, const float* init_dimpose,
                     const uint32_t* inlier_in, double* result, void* stream);
 
+/* PnPUncert(forward_exact_hessian=True): the second-order pose Hessian of monorun/ops/least_squares/hessian.py:5-64
+ * (autograd of J^T e through jacobian.py) at `pose`, and its inverse as the pose covariance (pnp_uncert.py:63-85).
+ * Uses p->n_obj, n_pts, layout, weight_mode (MRPNP_W_LOGSTD or MRPNP_W_ISTD), cam_stride, range_stride, z_min,
+ * std_scale.  Tensors as mrpnp_solve;
+ *   pose [N, pose_stride] float: yaw,tx,ty,tz lead each row (pose_stride = 24 reads the result rows of mrpnp_solve)
+ *   inlier_in packed mask or NULL (all points; pass mrpnp_solve's inlier_out)
+ *   hessian [N,16] float out or NULL;  rows [N,24] result rows or NULL: the inverse is written into the covariance
+ *   slots, and `valid` is cleared (covariance = identity) when the Hessian is not invertible. */
+int mrpnp_exact_hessian(mrpnp_ctx* ctx, const mrpnp_params* p,
+                        const float* coords_3d, const float* coords_2d, const float* weights,
+                        const float* cam_mats, const float* uv_range,
+                        const float* pose, int32_t pose_stride, const uint32_t* inlier_in,
+                        float* hessian, float* rows, void* stream);
+
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);
 

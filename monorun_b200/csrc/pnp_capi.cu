@@ -11,6 +11,7 @@
 #include "pnp_score.cuh"
 #include "pnp_nms.cuh"
 #include "pnp_noc.cuh"
+#include "pnp_exact_hessian.cuh"
 #ifdef MRPNP_WITH_POOL  // pooled staging buffers + small slots: measured slower, kept for reference
 #include "pnp_kernel_pool.cuh"
 #endif
@@ -430,6 +431,38 @@ int mrpnp_nms_bev(mrpnp_ctx* ctx, const float* bbox_3d, const int64_t* labels, c
     MR_CUDA(cudaFuncSetAttribute(mrpnp::nms_bev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mrpnp::nms_bev_kernel<<<n_groups, mrpnp::kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         bbox_3d, reinterpret_cast<const long long*>(labels), group_offsets, iou_thr, cap, keep);
+    MR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return MRPNP_OK;
+}
+
+int mrpnp_exact_hessian(mrpnp_ctx* ctx, const mrpnp_params* p,
+                        const float* coords_3d, const float* coords_2d, const float* weights,
+                        const float* cam_mats, const float* uv_range,
+                        const float* pose, int32_t pose_stride, const uint32_t* inlier_in,
+                        float* hessian, float* rows, void* stream) {
+    if (!ctx || !p) return fail(MRPNP_ERR_ARG, "NULL argument%s");
+    if (p->n_obj < 0) return fail(MRPNP_ERR_ARG, "n_obj < 0%s");
+    if (p->n_pts < 1 || p->n_pts > MRPNP_MAX_POINTS) return fail(MRPNP_ERR_ARG, "n_pts out of range%s");
+    if (p->layout != MRPNP_LAYOUT_PLANAR && p->layout != MRPNP_LAYOUT_INTERLEAVED) return fail(MRPNP_ERR_ARG, "bad layout%s");
+    if (p->weight_mode != MRPNP_W_LOGSTD && p->weight_mode != MRPNP_W_ISTD)
+        return fail(MRPNP_ERR_ARG, "the exact Hessian is defined for per-axis weights only (MRPNP_W_LOGSTD / MRPNP_W_ISTD)%s");
+    if ((p->cam_stride != 0 && p->cam_stride != 9) || (p->range_stride != 0 && p->range_stride != 4))
+        return fail(MRPNP_ERR_ARG, "bad cam_stride / range_stride%s");
+    if (pose_stride < 4) return fail(MRPNP_ERR_ARG, "pose_stride < 4%s");
+    if (p->n_obj == 0) return MRPNP_OK;
+    if (!coords_3d || !coords_2d || !weights || !cam_mats || !uv_range || !pose || (!hessian && !rows))
+        return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    mrxh::KParams kp;
+    kp.coords_3d = coords_3d; kp.coords_2d = coords_2d; kp.weights = weights; kp.cam_mats = cam_mats;
+    kp.uv_range = uv_range; kp.pose = pose; kp.inlier = inlier_in; kp.hessian = hessian; kp.rows = rows;
+    kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.planar = p->layout == MRPNP_LAYOUT_PLANAR;
+    kp.logstd = p->weight_mode == MRPNP_W_LOGSTD; kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride;
+    kp.pose_stride = pose_stride; kp.z_min = p->z_min; kp.std_scale = p->std_scale;
+    const int ctas = std::min((p->n_obj + mrxh::kWarpsPerCta - 1) / mrxh::kWarpsPerCta, ctx->num_sms * 16);
+    mrxh::exact_hessian_kernel<<<ctas, mrxh::kWarpsPerCta * 32, 0, static_cast<cudaStream_t>(stream)>>>(kp);
     MR_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return MRPNP_OK;

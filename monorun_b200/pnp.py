@@ -196,6 +196,44 @@ def solve_noc_batched(coords_3d, coords_2d, weights, logdim, logdim_wgt, cam_mat
     return result
 
 
+def exact_hessian(coords_3d, coords_2d, weights, cam_mats, uv_range, pose, inlier_mask=None, *, layout='planar',
+                  weight_mode='logstd', z_min=0.5, std_scale=10.0, rows=None, return_hessian=True):
+    """``mrpnp_exact_hessian``: the second-order pose Hessian of the reference's ``exact_hessian`` (hessian.py:5-64)
+    at ``pose`` ([N,4] yaw,t -- or the [N,24] result rows of :func:`solve_batched`).  With ``rows`` ([N,24], may be
+    the same tensor as ``pose``) the inverse is written into the rows' covariance slots and ``valid`` is cleared where
+    the Hessian is singular.  Returns H [N,4,4] float32 (or None with return_hessian=False)."""
+    dev = coords_3d.device
+    ctx = get_ctx(dev)
+    n = coords_3d.shape[0]
+    planar = layout == 'planar'
+    n_pts = coords_3d[0].numel() // 3 if n else (coords_3d.shape[2:].numel() if planar else coords_3d.shape[1])
+    if weight_mode not in ('logstd', 'istd'):
+        raise ValueError("the exact Hessian takes per-axis weights: weight_mode 'logstd' or 'istd'")
+    h = torch.empty((n, 4, 4), dtype=torch.float32, device=dev) if return_hessian else None
+    if n == 0:
+        return h
+    if pose.dtype != torch.float32 or not pose.is_contiguous() or pose.dim() != 2 or pose.shape[1] < 4:
+        raise ValueError('pose must be a contiguous float32 [N, >=4] tensor')
+    if rows is not None and (rows.dtype != torch.float32 or not rows.is_contiguous() or rows.shape != (n, RESULT_STRIDE)):
+        raise ValueError('rows must be a contiguous float32 [N,%d] tensor' % RESULT_STRIDE)
+    c3, c2, w = _f32c(coords_3d), _f32c(coords_2d), _f32c(weights)
+    cam, rng = _f32c(cam_mats).reshape(-1, 9), _f32c(uv_range).reshape(-1, 4)
+    if cam.shape[0] not in (1, n) or rng.shape[0] not in (1, n):
+        raise ValueError('cam_mats / uv_range must have batch size 1 or N')
+    inl_in = pack_mask(inlier_mask.reshape(n, n_pts).bool()) if inlier_mask is not None else None
+    p = make_params(
+        n, n_pts, layout=C['MRPNP_LAYOUT_PLANAR'] if planar else C['MRPNP_LAYOUT_INTERLEAVED'],
+        weight_mode=C['MRPNP_W_LOGSTD'] if weight_mode == 'logstd' else C['MRPNP_W_ISTD'],
+        cam_stride=9 if cam.shape[0] == n and n > 1 else 0, range_stride=4 if rng.shape[0] == n and n > 1 else 0,
+        z_min=float(z_min), std_scale=float(std_scale))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_exact_hessian(
+            ctx.ptr, p, _ptr(c3), _ptr(c2), _ptr(w), _ptr(cam), _ptr(rng), _ptr(pose), pose.shape[1],
+            _ptr(inl_in, 'uint32_t*'), _ptr(h), _ptr(rows), _native.ffi.cast('void*', stream)))
+    return h
+
+
 def pose_features(rows, dims, cov_calib_logscale=None, cov_correction_sd=0.0, distance_z_depth=False, use_calib=False,
                   pose_norm=None):
     """``mrpnp_pose_features``: result rows [N,24] + dims [N,3] -> (features [N,17], pose_cov_calib [N,16])."""
@@ -384,15 +422,14 @@ def pnp_uncert(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range,
         epnp_ransac_thres (None | Tensor): accepted for signature compatibility.  OpenCV's RANSAC-EPnP
             (pnp_uncert_cpu.py:34-51) is not reproduced on the GPU; the on-device linear initialiser uses the
             istd inliers (documented deviation).
-        forward_exact_hessian: only False is supported (all shipped configs; the reference's exact_hessian
-            does not run on torch >= 2).  use_6dof: accepted and unused, exactly as in the reference.
+        forward_exact_hessian: True replaces the Gauss-Newton covariance by the inverse of the second-order
+            Hessian (hessian.py:5-64; one more launch, ``mrpnp_exact_hessian``).  use_6dof: accepted and unused,
+            exactly as in the reference.
         init_pose (Tensor | None): extension -- (Nbatch, 4) [yaw, t] to start LM from (e.g. an EPnP result).
     Returns:
         ret_val (Nbatch,) bool, r_vec (Nbatch, 1), t_vec (Nbatch, 3), pose_cov (Nbatch, 4, 4),
         inlier_mask (Nbatch, Npoint) bool -- all on the input device.
     """
-    if forward_exact_hessian:
-        raise NotImplementedError('forward_exact_hessian=True is not supported (unused by every reference config)')
     with torch.no_grad():
         n = coords_2d.shape[0]
         if n == 0:  # pnp_uncert.py:60-61, pnp_uncert_cpu.py:201-207
@@ -404,7 +441,10 @@ def pnp_uncert(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range,
         result, inlier_mask, _ = solve_batched(
             coords_3d, coords_2d, coords_2d_istd, cam_mats, uv_range, init_pose=init_pose, layout='interleaved',
             weight_mode='istd', z_min=z_min, istd_thres=epnp_istd_thres, inlier_opt_only=inlier_opt_only,
-            cov_mode='pipeline', precision=precision)
+            cov_mode='none' if forward_exact_hessian else 'pipeline', precision=precision)
+        if forward_exact_hessian:  # pnp_uncert.py:63-69, :77-85
+            exact_hessian(coords_3d, coords_2d, coords_2d_istd, cam_mats, uv_range, result, inlier_mask,
+                          layout='interleaved', weight_mode='istd', z_min=z_min, rows=result, return_hessian=False)
         return _unpack(result, inlier_mask)
 
 
@@ -444,7 +484,12 @@ class PnPUncert(torch.nn.Module):
             result, inlier_mask, _ = solve_batched(
                 coords_3d, coords_2d, coords_2d_logstd, cam_mats, uv_range, init_pose=init_pose, layout='planar',
                 weight_mode='logstd', z_min=self.z_min, std_scale=std_scale, istd_thres=self.epnp_istd_thres,
-                inlier_opt_only=self.inlier_opt_only, cov_mode='pipeline', precision=self.precision)
+                inlier_opt_only=self.inlier_opt_only,
+                cov_mode='none' if self.forward_exact_hessian else 'pipeline', precision=self.precision)
+            if self.forward_exact_hessian:
+                exact_hessian(coords_3d, coords_2d, coords_2d_logstd, cam_mats, uv_range, result, inlier_mask,
+                              layout='planar', weight_mode='logstd', z_min=self.z_min, std_scale=std_scale,
+                              rows=result, return_hessian=False)
             return _unpack(result, inlier_mask)
 
     def forward_fused(self, noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, std_scale, coord_coder,
@@ -456,6 +501,9 @@ class PnPUncert(torch.nn.Module):
         with torch.no_grad():
             if self.coord_istd_normalize:
                 raise NotImplementedError('coord_istd_normalize with the fused entry')
+            if self.forward_exact_hessian:
+                raise NotImplementedError('forward_exact_hessian with the fused entry (the decoded tensors it needs '
+                                          'are never materialised); use forward_dense')
             result, inlier_mask = solve_dense(
                 noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range,
                 noc_mean=coord_coder.target_means, noc_std=coord_coder.target_stds,

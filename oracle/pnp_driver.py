@@ -165,6 +165,51 @@ def approx_hessian(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_ra
     return h
 
 
+def exact_hessian(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range, z_min, yaw, t_vec,
+                  inlier_mask):
+    """fp64 restatement of hessian.py:5-64 (same argument order). Returns H (N,4,4).
+
+    The reference differentiates g = J^T e with autograd, J and e from jacobian.py:4-98 & :157-184.  Rows in
+    ``zero_mask`` (z-clipped point, own coordinate clipped, outlier; jacobian.py:52-59) have a constant zero
+    Jacobian and drop out of g; on every other row J is the true derivative of e (nothing it depends on is
+    clamped), so H = sum_rows J^T J + e * Hess(e) with the unclipped projection's second derivatives:
+    for f = x'/z' (or y'/z'):  f_pq = (x'_pq - f z'_pq - f_q z'_p - f_p z'_q) / z'.
+    Pinned to the reference's own autograd result by tests/golden/exact_hessian_ref.npz."""
+    c2, w, c3 = _c64(coords_2d), _c64(coords_2d_istd), _c64(coords_3d)
+    n = c2.shape[0]
+    cam = np.broadcast_to(np.asarray(cam_mats, np.float64), (n, 3, 3))
+    ur = np.broadcast_to(np.asarray(u_range, np.float64), (n, 2))[:, None, :]
+    vr = np.broadcast_to(np.asarray(v_range, np.float64), (n, 2))[:, None, :]
+    yaw = np.asarray(yaw, np.float64).reshape(n, 1)
+    t = np.asarray(t_vec, np.float64).reshape(n, 1, 3)
+    fx, fy, cx, cy = (cam[:, i, j][:, None] for i, j in ((0, 0), (1, 1), (0, 2), (1, 2)))
+    sn, cs = np.sin(yaw), np.cos(yaw)
+    qx = cs * c3[..., 0] + sn * c3[..., 2]
+    qz = -sn * c3[..., 0] + cs * c3[..., 2]
+    xc, yc, zc = qx + t[..., 0], c3[..., 1] + t[..., 1], qz + t[..., 2]
+    z_free = ~(zc < z_min)                                            # jacobian.py:28
+    iz = 1.0 / np.where(z_free, zc, z_min)
+    zero = np.zeros_like(iz)
+    h = np.zeros((n, 4, 4))
+    inl = np.ones_like(z_free) if inlier_mask is None else np.asarray(inlier_mask, bool)
+    for f, num_p, focal, centre, rng_, obs, wgt in (
+            (xc * iz, (qz, 1.0 + zero, zero, zero), fx, cx, ur, c2[..., 0], w[..., 0]),
+            (yc * iz, (zero, zero, 1.0 + zero, zero), fy, cy, vr, c2[..., 1], w[..., 1])):
+        proj = focal * f + centre
+        free = z_free & inl & ~((proj < rng_[..., 0]) | (proj > rng_[..., 1]))   # jacobian.py:38-40, :52-59
+        e = wgt * (proj - obs)                                        # jacobian.py:181
+        zp = (-qx, zero, zero, 1.0 + zero)                            # d z' / d(yaw, tx, ty, tz)
+        fp = [(num_p[k] - f * zp[k]) * iz for k in range(4)]
+        for a in range(4):
+            for b in range(4):
+                num_pq = -qx if (a == 0 and b == 0 and num_p[0] is qz) else zero   # d2 x'/dyaw2 = -qx; y' is linear
+                z_pq = -qz if (a == 0 and b == 0) else zero                       # d2 z'/dyaw2 = -qz
+                f_pq = (num_pq - f * z_pq - fp[b] * zp[a] - fp[a] * zp[b]) * iz
+                term = (wgt * focal) ** 2 * fp[a] * fp[b] + e * wgt * focal * f_pq
+                h[:, a, b] += np.where(free, term, 0.0).sum(1)
+    return h
+
+
 # --------------------------------------------------------------------------------------
 # restated reference driver
 # --------------------------------------------------------------------------------------

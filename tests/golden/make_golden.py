@@ -10,6 +10,11 @@
    results (pose, cost, evaluation counts, covariance).  The oracle restates Ceres 1.14 (parity unpinned for the
    control flow, see oracle/pnp_oracle.cpp); these vectors freeze its behaviour so that oracle or generator drift
    is caught, and give the GPU tests fixed targets that do not depend on /root/reference.
+3. ``exact_hessian_ref.npz`` -- outputs of the REFERENCE's ``exact_hessian`` (hessian.py:5-64, double autograd
+   through jacobian.py) on the inputs of ``hessian_ref.npz`` at two poses per object.  On torch >= 2 the reference
+   code raises (jacobian.py:28-29 writes in place into the views ``Tensor.split`` returns, which autograd now
+   forbids), so the generator runs it with ``Tensor.split`` replaced by a version that returns clones of the same
+   pieces -- same values, same autograd graph semantics, no aliasing.  Nothing else is touched.
 """
 import importlib.util
 import os
@@ -80,6 +85,34 @@ def make_hessian_fixture():
     np.savez_compressed(os.path.join(HERE, 'hessian_ref.npz'), **out)
 
 
+def make_exact_hessian_fixture():
+    import torch
+    jac, hes = load_reference_hessian()
+    g = np.load(os.path.join(HERE, 'hessian_ref.npz'))
+    rng = np.random.default_rng(23)
+    pose2 = g['pose'].astype(np.float64)
+    pose2[:, 0] += rng.normal(0, 0.01, 8)
+    pose2[:, 1:] += rng.normal(0, 0.02, (8, 3))
+    pose2 = pose2.astype(np.float32)
+    orig_split = torch.Tensor.split
+    torch.Tensor.split = lambda self, *a, **k: tuple(x.clone() for x in orig_split(self, *a, **k))
+    out = dict(pose2=pose2)
+    try:
+        for tag, dt in (('64', torch.float64), ('32', torch.float32)):
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+            for name, pose in (('', g['pose']), ('_pose2', pose2)):
+                for mtag, mask in (('', torch.from_numpy(g['inlier_mask'])), ('_nomask', None)):
+                    h = hes.exact_hessian(t(g['coords_2d']), t(g['coords_2d_istd']), t(g['coords_3d']),
+                                          t(g['cam_mats']).expand(8, 3, 3).contiguous(), t(g['u_range']),
+                                          t(g['v_range']), 0.5, t(pose[:, :1]), t(pose[:, 1:]), mask)
+                    out[f'H_exact{tag}{name}{mtag}'] = h.detach().numpy()
+    finally:
+        torch.Tensor.split = orig_split
+        torch.set_grad_enabled(True)
+    np.savez_compressed(os.path.join(HERE, 'exact_hessian_ref.npz'), **out)
+    print('exact hessian fixture:', sorted(out))
+
+
 def make_lm_fixtures():
     from monorun_b200 import synth
     from oracle import pnp_driver as od
@@ -110,8 +143,10 @@ def make_lm_fixtures():
 
 
 if __name__ == '__main__':
-    make_hessian_fixture()
-    make_lm_fixtures()
+    if '--exact-hessian-only' not in sys.argv:
+        make_hessian_fixture()
+        make_lm_fixtures()
+    make_exact_hessian_fixture()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
