@@ -54,6 +54,35 @@ def main():
             cpu_objects_per_s=m / cpu_s, cpu_threads=os.cpu_count(), cpu_sample=m, same_decisions=float(same),
             max_param_diff=float(np.abs(res[:m, :7] - r['dimpose']).max()), valid=float((res[:, 7] > 0).mean()))
         print(out)
+    # second-order covariance pass (mrpnp_exact_hessian): one read of the correspondences at the final pose
+    c = make_case(a.n, mode='S1', cfg=3)
+    metric = torch.from_numpy((c['coords_3d']).astype(np.float32)).cuda().permute(0, 2, 1).contiguous()
+    c2 = torch.from_numpy(c['c2']).cuda().permute(0, 2, 1).contiguous()
+    w = torch.from_numpy(c['w']).cuda().permute(0, 2, 1).contiguous()
+    cam, rg = torch.from_numpy(c['cam']).cuda(), torch.from_numpy(c['uv_range']).cuda()
+    rows = torch.zeros((a.n, 24), device='cuda')
+    rows[:, :4] = torch.from_numpy(c['init_pose'].astype(np.float32)).cuda()
+    rows[:, 20] = 1
+    for layout, t3, t2, tw in (('planar', metric, c2, w),
+                               ('interleaved', metric.permute(0, 2, 1).contiguous(), c2.permute(0, 2, 1).contiguous(),
+                                w.permute(0, 2, 1).contiguous())):
+        def run_xh():
+            return pnp.exact_hessian(t3, t2, tw, cam, rg, rows, None, layout=layout, weight_mode='istd', rows=rows,
+                                     return_hessian=False)
+        for _ in range(3):
+            run_xh()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            run_xh()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        nbytes = a.n * t3.shape[1 if layout == 'interleaved' else 2] * 7 * 4
+        out['exact_hessian_' + layout] = dict(n=a.n, ms=ms, objects_per_s=a.n / ms * 1e3, bytes=nbytes,
+                                              gb_per_s=nbytes / ms / 1e6)
+    print({k: v for k, v in out.items() if k.startswith('exact')})
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(out, open(a.out, 'w'), indent=1)
 
