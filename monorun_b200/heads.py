@@ -4,6 +4,9 @@
 * FCNNOCDecoder           <- monorun/models/roi_heads/bbox_3d_heads/dense_decoders/fcn_noc_decoder.py:15-267
 * UncertProjectionHead    <- .../reprojection_heads/uncert_projection_head.py (test-time parts: get_distance, coder)
 * MonoRUnRoIHead          <- monorun/models/roi_heads/monorun_roi_head.py:13-40, hot sequence :509-534
+* FCExtractor[MonteCarlo] <- .../global_extractors/fc_extractor.py:12-156, fc_extractor_monte_carlo.py:21-82 (the caller-side
+                             stage that produces latent / dimensions / reg_fc_out; torch Linear layers, not a kernel of
+                             this path)
 
 Constructor kwargs, attribute names, state-dict keys and return tuples follow the reference so that the
 ``roi_head`` blocks of configs/kitti_*.py build and pretrained weights would load.  Training-only members
@@ -15,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .coders import coords_2d_from_rois
-from .registry import (HEADS, build_coord_coder, build_head, build_pnp, build_proj_error_coder,
+from .registry import (HEADS, build_coord_coder, build_dim_coder, build_head, build_pnp, build_proj_error_coder,
                        build_rotation_coder)
 
 
@@ -363,6 +366,103 @@ class MLPScoreHead(nn.Module):
         return scores, bbox_3d, cov_calib.view(-1, 4, 4)
 
 
+@HEADS.register_module()
+class FCExtractor(nn.Module):
+    """Global extractor (fc_extractor.py:12-156): RoI feature (N, 256, 7, 7) -> [dimensions | latent vector] per class
+    and the 1024-d feature the score head reuses.  Same kwargs and state-dict keys (``fcs.i``, ``fc_reg``); the loss
+    config is accepted and ignored (training is out of scope)."""
+
+    def __init__(self, with_dim=True, with_latent_vec=True, latent_channels=16, num_fcs=2, in_channels=256,
+                 fc_out_channels=1024, num_classes=3, roi_feat_size=7, latent_class_agnostic=False, loss_dim=None,
+                 dim_coder=dict(type='MultiClassNormDimCoder'), dropout_rate=0.5, dropout2d_rate=0.2,
+                 num_dropout_layers=2):
+        super(FCExtractor, self).__init__()
+        assert num_fcs > 0
+        self.with_dim, self.with_latent_vec = with_dim, with_latent_vec
+        self.dim_dim = 3
+        self.latent_channels = latent_channels if with_latent_vec else 0
+        rs = (roi_feat_size, roi_feat_size) if isinstance(roi_feat_size, int) else tuple(roi_feat_size)
+        self.roi_feat_size, self.roi_feat_area = rs, rs[0] * rs[1]
+        self.in_channels, self.fc_out_channels, self.num_classes = in_channels, fc_out_channels, num_classes
+        self.latent_class_agnostic = latent_class_agnostic
+        self.dim_coder = build_dim_coder(dim_coder)
+        self.use_dropout, self.use_dropout2d = dropout_rate > 0, dropout2d_rate > 0
+        self.dropout_rate, self.dropout2d_rate = dropout_rate, dropout2d_rate
+        self.num_dropout_layers = num_dropout_layers
+        self.fcs = nn.ModuleList(
+            nn.Linear(in_channels * self.roi_feat_area if i == 0 else fc_out_channels, fc_out_channels)
+            for i in range(num_fcs))
+        out_dim_reg = self.dim_dim + self.latent_channels
+        if not latent_class_agnostic:
+            out_dim_reg *= num_classes
+        self.fc_reg = nn.Linear(fc_out_channels, out_dim_reg)
+        self.mc_dropout = False  # FCExtractorMonteCarlo keeps dropout active at test time
+
+    def init_weights(self):  # fc_extractor.py:85-91
+        for m in self.fcs:
+            nn.init.xavier_uniform_(m.weight, gain=0.33)
+            nn.init.normal_(m.bias, mean=0.02, std=0.04)
+        nn.init.normal_(self.fc_reg.weight, 0, 0.001)
+        nn.init.constant_(self.fc_reg.bias, 0)
+
+    def _fc_forward(self, x):  # fc_extractor.py:94-105
+        active = self.training or self.mc_dropout
+        if self.use_dropout2d:
+            x = F.dropout2d(x, self.dropout2d_rate, active)
+        x = x.flatten(1)
+        for i, fc in enumerate(self.fcs):
+            x = F.relu(fc(x))
+            if self.use_dropout and i < self.num_dropout_layers:
+                x = F.dropout(x, self.dropout_rate, active)
+        return self.fc_reg(x), x
+
+    def forward(self, x):
+        dim_latent_pred, feat = self._fc_forward(x)
+        return dim_latent_pred, None, None, None, feat
+
+    def _per_class(self, t, labels):
+        if self.latent_class_agnostic:
+            return t
+        inds = torch.arange(len(labels), device=labels.device)
+        return t.view(t.size(0), -1, self.dim_dim + self.latent_channels)[inds, labels]
+
+    def slice_pred(self, dim_latent_pred, dim_latent_var, labels):  # fc_extractor.py:135-146
+        dim_pred, latent_pred = self._per_class(dim_latent_pred, labels).split(
+            [self.dim_dim, self.latent_channels], dim=1)
+        return dim_pred, None, latent_pred, None
+
+
+@HEADS.register_module()
+class FCExtractorMonteCarlo(FCExtractor):
+    """MC-dropout global extractor (fc_extractor_monte_carlo.py:21-82): at test time the batch is repeated
+    ``num_samples`` times with dropout active; the sample mean / variance give the prediction and its epistemic
+    variance (``dimensions_var`` of NOCCoder.decode), the feature is the sample mean."""
+
+    def __init__(self, num_samples=50, dropout_rate=0.5, dropout2d_rate=0.2, **kwargs):
+        super(FCExtractorMonteCarlo, self).__init__(dropout_rate=dropout_rate, dropout2d_rate=dropout2d_rate, **kwargs)
+        assert self.use_dropout and self.use_dropout2d
+        self.num_samples = num_samples
+        self.mc_dropout = True
+
+    def forward(self, x):
+        if self.training:
+            return super(FCExtractorMonteCarlo, self).forward(x)
+        n = x.size(0)
+        pred, feat = self._fc_forward(x.repeat(self.num_samples, 1, 1, 1))      # :44-47
+        var, mean = torch.var_mean(pred.view(self.num_samples, n, -1), dim=0)   # :52-56
+        feat = feat.view(self.num_samples, n, -1).mean(dim=0)                   # :60-61
+        return mean, var, None, None, feat
+
+    def slice_pred(self, dim_latent_pred, dim_latent_var, labels):  # :65-82
+        if self.training:
+            return super(FCExtractorMonteCarlo, self).slice_pred(dim_latent_pred, dim_latent_var, labels)
+        dim_pred, latent_pred = self._per_class(dim_latent_pred, labels).split(
+            [self.dim_dim, self.latent_channels], dim=1)
+        dim_var, latent_var = self._per_class(dim_latent_var, labels).split(
+            [self.dim_dim, self.latent_channels], dim=1)
+        return dim_pred, dim_var, latent_pred, latent_var
+
+
 _OUT_OF_SCOPE = ('bbox_roi_extractor', 'bbox_head', 'global_head', 'noc_roi_extractor',
                  'shared_head', 'mask_roi_extractor', 'mask_head')
 
@@ -384,6 +484,8 @@ class MonoRUnRoIHead(nn.Module):
         if unknown:
             raise TypeError(f'unexpected MonoRUnRoIHead arguments: {sorted(unknown)}')
         self.train_cfg, self.test_cfg, self.debug = train_cfg, test_cfg, debug
+        if global_head is not None and global_head.get('type') in HEADS and len(global_head) > 1:
+            self.global_head = build_head(global_head)   # a bare dict(type=...) stub stays deferred
         if noc_head is not None:
             self.noc_head = build_head(noc_head)
         if projection_head is not None:
@@ -406,10 +508,22 @@ class MonoRUnRoIHead(nn.Module):
         return hasattr(self, 'score_head') and self.score_head is not None
 
     def init_weights(self):
+        if hasattr(self, 'global_head'):
+            self.global_head.init_weights()
         if self.with_noc:
             self.noc_head.init_weights()
         if self.with_score:
             self.score_head.init_weights()
+
+    def reg_forward(self, reg_feats, det_labels):
+        """``_reg_forward`` + the decode that follows it (monorun_roi_head.py:489-507) on the 7x7 RoI features:
+        returns dict(latent_pred, latent_var, dimensions_pred, dimensions_var, reg_fc_out)."""
+        gh = self.global_head
+        dim_latent_pred, dim_latent_var, _, _, reg_fc_out = gh(reg_feats)
+        dim_pred, dim_var, latent_pred, latent_var = gh.slice_pred(dim_latent_pred, dim_latent_var, det_labels)
+        dimensions_pred, dimensions_var = gh.dim_coder.decode(dim_pred, dim_var, det_labels)
+        return dict(latent_pred=latent_pred, latent_var=latent_var, dimensions_pred=dimensions_pred,
+                    dimensions_var=dimensions_var, reg_fc_out=reg_fc_out)
 
     def forward_scores(self, rows, reg_fc_out, dimensions_pred, det_scores=None, cov_correction=True, calib_scoring=False,
                        mult_2d_score=True):
