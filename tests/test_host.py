@@ -266,3 +266,38 @@ def test_head_raw_generator_inverts_the_decoders():
     assert np.abs(c2.numpy() - b['coords_2d']).max() < 2e-4
     with pytest.raises(ValueError):
         synth.to_head_raw(synth.make_batch(2, config=2, mode='S0'))
+
+
+def test_global_extractor_mirrors_reference_interface():
+    """FCExtractorMonteCarlo (fc_extractor.py:12-156, fc_extractor_monte_carlo.py:21-82): state-dict keys, the
+    5-tuple, sample mean / variance over num_samples dropout passes, per-class slicing and dimension decode."""
+    g = monorun_b200.build_head(dict(type='FCExtractorMonteCarlo', num_samples=8, num_classes=3, latent_channels=16,
+                                     in_channels=4, fc_out_channels=32, roi_feat_size=7,
+                                     loss_dim=dict(type='SmoothL1LossMod', loss_weight=1.0, beta=1.0),
+                                     dim_coder=dict(type='MultiClassNormDimCoder'))).eval()
+    g.init_weights()
+    assert set(g.state_dict()) == {'fcs.0.weight', 'fcs.0.bias', 'fcs.1.weight', 'fcs.1.bias', 'fc_reg.weight',
+                                   'fc_reg.bias'}
+    assert g.fcs[0].in_features == 4 * 49 and g.fc_reg.out_features == (3 + 16) * 3
+    x, labels = torch.randn(5, 4, 7, 7), torch.tensor([0, 2, 1, 1, 0])
+    torch.manual_seed(3)
+    mean, var, dist, dist_logstd, feat = g(x)
+    assert mean.shape == (5, 57) and var.shape == (5, 57) and feat.shape == (5, 32) and dist is None and dist_logstd is None
+    torch.manual_seed(3)   # same dropout masks: the reference's repeat -> forward -> view(num_samples, n, -1) -> var_mean
+    pred, f = g._fc_forward(x.repeat(8, 1, 1, 1))
+    v_ref, m_ref = torch.var_mean(pred.view(8, 5, -1), dim=0)
+    assert torch.equal(mean, m_ref) and torch.equal(var, v_ref) and torch.equal(feat, f.view(8, 5, -1).mean(0))
+    assert (var > 0).any()   # dropout is active at test time
+    dim_pred, dim_var, latent_pred, latent_var = g.slice_pred(mean, var, labels)
+    assert torch.equal(dim_pred[1], mean[1, 2 * 19:2 * 19 + 3]) and torch.equal(latent_var[2], var[2, 19 + 3:2 * 19])
+    dims, dims_var = g.dim_coder.decode(dim_pred, dim_var, labels)
+    assert torch.allclose(dims[1], dim_pred[1] * torch.tensor([0.15, 0.10, 0.14]) + torch.tensor([1.77, 1.72, 0.57]))
+    assert torch.allclose(dims_var[1], dim_var[1] * torch.tensor([0.15, 0.10, 0.14]) ** 2)
+    # the deterministic parent: no variance, dropout off in eval
+    d = monorun_b200.build_head(dict(type='FCExtractor', in_channels=4, fc_out_channels=32)).eval()
+    a, b = d(x), d(x)
+    assert torch.equal(a[0], b[0]) and a[1] is None
+    h = monorun_b200.build_head(dict(_roi_head_cfg(), global_head=dict(type='FCExtractorMonteCarlo', in_channels=4,
+                                                                        fc_out_channels=32)))
+    out = h.eval().reg_forward(x, labels)
+    assert out['dimensions_pred'].shape == (5, 3) and out['latent_pred'].shape == (5, 16) and out['reg_fc_out'].shape == (5, 32)
