@@ -244,6 +244,21 @@ int mrpnp_exact_hessian(mrpnp_ctx* ctx, const mrpnp_params* p,
                         const float* pose, int32_t pose_stride, const uint32_t* inlier_in,
                         float* hessian, float* rows, void* stream);
 
+/* 6-DoF extension of the uncertainty PnP (the north star's "6-DoF LM normal-equation solve"): unknowns
+ * [rx, ry, rz, tx, ty, tz], rotation as ceres::AngleAxisRotatePoint; residuals, clips, whitening, Ceres 1.14 LM and
+ * covariance (J^T J)^-1 as in pnp_uncert (ext.h:1-13, pnp_uncert_cpu.cpp:245-292).  The reference has no 6-DoF solver
+ * (its rotation vector is (0, yaw, 0), pnp_uncert_cpu.cpp:28; `use_6dof` is never read, pnp_uncert.py:11,98,122,142),
+ * so this entry has no reference interface to replace: PnPUncert(use_6dof=True).forward_6dof calls it.
+ * Uses p->n_obj, n_pts, layout, weight_mode (any MRPNP_W_*), cam_stride, range_stride, z_min, std_scale,
+ * max_iterations.  Tensors as mrpnp_solve; init_pose6 [N,6] float (e.g. (0, yaw, 0, t) from mrpnp_solve);
+ * inlier_in packed mask or NULL (all points).
+ *   result [N,48] DOUBLE: rvec(3), t(3) | cov 6x6 row-major | valid, lm_iterations, final_cost, cost_evals,
+ *   termination, pad. */
+int mrpnp_solve_6dof(mrpnp_ctx* ctx, const mrpnp_params* p,
+                     const float* coords_3d, const float* coords_2d, const float* weights,
+                     const float* cam_mats, const float* uv_range, const float* init_pose6,
+                     const uint32_t* inlier_in, double* result, void* stream);
+
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);
 

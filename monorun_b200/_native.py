@@ -18,7 +18,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get('MRPNP_LIB') or os.path.join(_PKG, 'libmonorun_pnp.so')   # MRPNP_LIB: A/B builds of tools/
 HEADER = os.path.join(_ROOT, 'include', 'monorun_pnp.h')
-SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('pnp_capi.cu', 'pnp_kernel.cuh', 'pnp_device.cuh', 'pnp_fast.cuh', 'pnp_kernel_fast.cuh', 'pnp_kernel_fast2.cuh', 'pnp_kernel_pool.cuh', 'pnp_score.cuh', 'pnp_nms.cuh', 'pnp_noc.cuh', 'pnp_exact_hessian.cuh', 'pnp_kernel_pair.cuh')]
+SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('pnp_capi.cu', 'pnp_kernel.cuh', 'pnp_device.cuh', 'pnp_fast.cuh', 'pnp_kernel_fast.cuh', 'pnp_kernel_fast2.cuh', 'pnp_kernel_pool.cuh', 'pnp_score.cuh', 'pnp_nms.cuh', 'pnp_noc.cuh', 'pnp_exact_hessian.cuh', 'pnp_6dof.cuh', 'lm_dense.cuh', 'pnp_kernel_pair.cuh')]
 HEAD_LIB_PATH = os.path.join(_PKG, 'libmonorun_head.so')
 HEAD_HEADER = os.path.join(_ROOT, 'include', 'monorun_head.h')
 HEAD_SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('head_capi.cu', 'head_kernels.cuh', 'head_tc.cuh')]
@@ -119,7 +119,7 @@ def check(rc):
 
 EXPORTED = ['mrpnp_default_params', 'mrpnp_create', 'mrpnp_destroy', 'mrpnp_solve', 'mrpnp_solve_dense', 'mrpnp_solve_host',
             'mrpnp_launch_count', 'mrpnp_kernel_info', 'mrpnp_version', 'mrpnp_last_error', 'mrpnp_pose_features',
-            'mrpnp_finish_scores', 'mrpnp_nms_bev', 'mrpnp_solve_noc', 'mrpnp_exact_hessian']
+            'mrpnp_finish_scores', 'mrpnp_nms_bev', 'mrpnp_solve_noc', 'mrpnp_exact_hessian', 'mrpnp_solve_6dof']
 HEAD_EXPORTED = ['mrhead_create', 'mrhead_destroy', 'mrhead_version', 'mrhead_last_error', 'mrhead_launch_count',
                  'mrhead_pack_input', 'mrhead_conv', 'mrhead_latent_bias', 'mrhead_carafe', 'mrhead_workspace_bytes',
                  'mrhead_forward']

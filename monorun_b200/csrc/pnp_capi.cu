@@ -12,6 +12,7 @@
 #include "pnp_nms.cuh"
 #include "pnp_noc.cuh"
 #include "pnp_exact_hessian.cuh"
+#include "pnp_6dof.cuh"
 #ifdef MRPNP_WITH_POOL  // pooled staging buffers + small slots: measured slower, kept for reference
 #include "pnp_kernel_pool.cuh"
 #endif
@@ -463,6 +464,40 @@ int mrpnp_exact_hessian(mrpnp_ctx* ctx, const mrpnp_params* p,
     kp.pose_stride = pose_stride; kp.z_min = p->z_min; kp.std_scale = p->std_scale;
     const int ctas = std::min((p->n_obj + mrxh::kWarpsPerCta - 1) / mrxh::kWarpsPerCta, ctx->num_sms * 16);
     mrxh::exact_hessian_kernel<<<ctas, mrxh::kWarpsPerCta * 32, 0, static_cast<cudaStream_t>(stream)>>>(kp);
+    MR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return MRPNP_OK;
+}
+
+int mrpnp_solve_6dof(mrpnp_ctx* ctx, const mrpnp_params* p,
+                     const float* coords_3d, const float* coords_2d, const float* weights,
+                     const float* cam_mats, const float* uv_range, const float* init_pose6,
+                     const uint32_t* inlier_in, double* result, void* stream) {
+    if (!ctx || !p) return fail(MRPNP_ERR_ARG, "NULL argument%s");
+    if (p->n_obj < 0) return fail(MRPNP_ERR_ARG, "n_obj < 0%s");
+    if (p->n_pts < 1 || p->n_pts > MRPNP_MAX_POINTS) return fail(MRPNP_ERR_ARG, "n_pts out of range%s");
+    if (p->layout != MRPNP_LAYOUT_PLANAR && p->layout != MRPNP_LAYOUT_INTERLEAVED) return fail(MRPNP_ERR_ARG, "bad layout%s");
+    if (p->weight_mode < MRPNP_W_LOGSTD || p->weight_mode > MRPNP_W_FULL) return fail(MRPNP_ERR_ARG, "bad weight_mode%s");
+    if ((p->cam_stride != 0 && p->cam_stride != 9) || (p->range_stride != 0 && p->range_stride != 4))
+        return fail(MRPNP_ERR_ARG, "bad cam_stride / range_stride%s");
+    if (p->max_iterations < 0) return fail(MRPNP_ERR_ARG, "max_iterations < 0%s");
+    if (p->n_obj == 0) return MRPNP_OK;
+    if (!coords_3d || !coords_2d || !weights || !cam_mats || !uv_range || !init_pose6 || !result)
+        return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    mr6::KParams kp;
+    kp.coords_3d = coords_3d; kp.coords_2d = coords_2d; kp.weights = weights; kp.cam_mats = cam_mats;
+    kp.uv_range = uv_range; kp.init = init_pose6; kp.inlier = inlier_in; kp.result = result;
+    kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.planar = p->layout == MRPNP_LAYOUT_PLANAR;
+    kp.wmode = p->weight_mode; kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride;
+    kp.max_iterations = p->max_iterations; kp.z_min = p->z_min; kp.std_scale = p->std_scale;
+    const int ctas = std::min((p->n_obj + mr6::kWarpsPerCta - 1) / mr6::kWarpsPerCta, ctx->num_sms * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->weight_mode == MRPNP_W_FULL)
+        mr6::pnp_6dof_kernel<true><<<ctas, mr6::kWarpsPerCta * 32, 0, st>>>(kp);
+    else
+        mr6::pnp_6dof_kernel<false><<<ctas, mr6::kWarpsPerCta * 32, 0, st>>>(kp);
     MR_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return MRPNP_OK;

@@ -21,6 +21,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "lm_dense.cuh"
+
 #ifdef __CUDACC__
 #define MRNOC_HD __host__ __device__ __forceinline__
 #define MRNOC_HD_NOINLINE __host__ __device__ __noinline__
@@ -31,12 +33,17 @@
 
 namespace mrnoc {
 
-constexpr int kNP = 7;                  // parameters
-constexpr int kNH = kNP * (kNP + 1) / 2;  // upper triangle of J^T J
-constexpr int kNAcc = 1 + kNP + kNH;    // cost | gradient | J^T J
-constexpr int kAccG = 1, kAccH = 1 + kNP;
+constexpr int kNP = 7;  // parameters
+constexpr int kNAcc = mrlm::Layout<kNP>::kNAcc;  // cost | gradient | upper triangle of J^T J  (36)
+constexpr int kAccG = mrlm::Layout<kNP>::kAccG, kAccH = mrlm::Layout<kNP>::kAccH;
+using mrlm::LMOptions;
+using mrlm::LMResult;
+using mrlm::default_options;
+using mrlm::kConvergence;
+using mrlm::kNoConvergence;
+using mrlm::kFailure;
 
-MRNOC_HD int tri(int a, int b) { return a * kNP - a * (a - 1) / 2 + (b - a); }  // a <= b
+MRNOC_HD int tri(int a, int b) { return mrlm::tri<kNP>(a, b); }
 
 struct Camera { double fx, fy, cx, cy, z_min, u_min, u_max, v_min, v_max; };
 
@@ -143,195 +150,6 @@ MRNOC_HD void add_dim_prior(const double* x, const double* logdim, const double*
     add_block<3, JAC>(delta, r, j, acc);
 }
 
-// Cholesky solve of the symmetric 7x7 system A y = b (A full, row-major).  false when A is not
-// numerically positive definite or y is not finite -- the step is then "invalid", like a failed
-// DenseQRSolver::Solve.
-MRNOC_HD_NOINLINE bool cholesky_solve7(const double* A, const double* b, double* y) {
-    double L[kNP * kNP];
-    for (int i = 0; i < kNP; ++i)
-        for (int j = 0; j <= i; ++j) {
-            double s = A[i * kNP + j];
-            for (int k = 0; k < j; ++k) s -= L[i * kNP + k] * L[j * kNP + k];
-            if (i == j) {
-                if (!(s > 0.0) || !isfinite(s)) return false;
-                L[i * kNP + i] = sqrt(s);
-            } else {
-                L[i * kNP + j] = s / L[j * kNP + j];
-            }
-        }
-    double z[kNP];
-    for (int i = 0; i < kNP; ++i) {
-        double s = b[i];
-        for (int k = 0; k < i; ++k) s -= L[i * kNP + k] * z[k];
-        z[i] = s / L[i * kNP + i];
-    }
-    for (int i = kNP - 1; i >= 0; --i) {
-        double s = z[i];
-        for (int k = i + 1; k < kNP; ++k) s -= L[k * kNP + i] * y[k];
-        y[i] = s / L[i * kNP + i];
-    }
-    bool ok = true;
-    for (int i = 0; i < kNP; ++i) ok = ok && isfinite(y[i]);
-    return ok;
-}
-
-enum Termination { kConvergence = 0, kNoConvergence = 1, kFailure = 2 };
-
-struct LMResult {
-    int term, iterations, cost_evals, jac_evals;
-    double final_cost;
-};
-
-// ceres::Solver::Options defaults of 1.14 (cpp:318-319 and :361-362 only choose DENSE_QR).
-struct LMOptions {
-    int max_num_iterations;
-    double function_tolerance, gradient_tolerance, parameter_tolerance;
-    double initial_radius, max_radius, min_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
-    int max_consecutive_invalid;
-};
-
-MRNOC_HD LMOptions default_options() {
-    LMOptions o;
-    o.max_num_iterations = 50;
-    o.function_tolerance = 1e-6; o.gradient_tolerance = 1e-10; o.parameter_tolerance = 1e-8;
-    o.initial_radius = 1e4; o.max_radius = 1e16; o.min_radius = 1e-32;
-    o.min_relative_decrease = 1e-3; o.min_lm_diagonal = 1e-6; o.max_lm_diagonal = 1e32;
-    o.max_consecutive_invalid = 5;
-    return o;
-}
-
-MRNOC_HD bool all_finite(const double* acc, int n) {
-    bool ok = true;
-    for (int i = 0; i < n; ++i) ok = ok && isfinite(acc[i]);
-    return ok;
-}
-
-// ceres::internal::TrustRegionMinimizer::Minimize (1.14) for one 7-vector parameter block: LM
-// strategy, Jacobi scaling, monotonic steps, no bounds, no inner iterations.  `pass(x, jac, acc)`
-// fills acc[0] (jac == false) or acc[0..36) (jac == true) for the parameter vector x.
-// x_io: initial parameters in, best accepted parameters out (cpp:302 memcpy + in-place solve).
-template <class Pass>
-MRNOC_HD_NOINLINE LMResult minimize(Pass& pass, double* x_io, const LMOptions& opt) {
-    double x[kNP], grad[kNP], scale[kNP], diag[kNP], Hs[kNP * kNP], bs[kNP], A[kNP * kNP], step[kNP],
-        delta[kNP], cand[kNP], acc[kNAcc];
-    for (int k = 0; k < kNP; ++k) x[k] = x_io[k];
-    for (int i = 0; i < kNAcc; ++i) acc[i] = 0.0;
-    LMResult out;
-    out.term = kFailure; out.iterations = 0; out.cost_evals = 0; out.jac_evals = 0; out.final_cost = 0.0;
-    double radius = opt.initial_radius, decrease_factor = 2.0, x_cost, x_norm, gradient_max_norm;
-    bool reuse_diagonal = false;
-    int num_invalid = 0;
-    double minimum_cost = 1.7976931348623157e308;
-
-    // the scaled Gauss-Newton system of the current point: Hs = S J^T J S, bs = S J^T r
-    auto load_point = [&](bool first) {
-        x_cost = acc[0];
-        gradient_max_norm = 0.0;
-        for (int k = 0; k < kNP; ++k) {
-            grad[k] = acc[kAccG + k];
-            gradient_max_norm = fmax(gradient_max_norm, fabs(grad[k]));
-        }
-        if (first)  // Jacobi scaling from the initial Jacobian only: 1 / (1 + |column|)
-            for (int k = 0; k < kNP; ++k) scale[k] = 1.0 / (1.0 + sqrt(acc[kAccH + tri(k, k)]));
-        for (int a = 0; a < kNP; ++a) {
-            bs[a] = scale[a] * grad[a];
-            for (int b = a; b < kNP; ++b) {
-                const double h = acc[kAccH + tri(a, b)] * scale[a] * scale[b];
-                Hs[a * kNP + b] = h;
-                Hs[b * kNP + a] = h;
-            }
-        }
-        x_norm = 0.0;
-        for (int k = 0; k < kNP; ++k) x_norm += x[k] * x[k];
-        x_norm = sqrt(x_norm);
-    };
-
-    pass(x, true, acc);
-    out.cost_evals++; out.jac_evals++;
-    if (!all_finite(acc, kNAcc)) { out.final_cost = acc[0]; return out; }
-    load_point(true);
-
-    int iteration = 0;
-    bool step_is_successful = true;
-    out.term = kNoConvergence;
-    while (true) {
-        if (step_is_successful && x_cost < minimum_cost) {
-            minimum_cost = x_cost;
-            for (int k = 0; k < kNP; ++k) x_io[k] = x[k];
-        }
-        out.iterations = iteration;
-        if (iteration >= opt.max_num_iterations) { out.term = kNoConvergence; break; }
-        if (step_is_successful && gradient_max_norm <= opt.gradient_tolerance) { out.term = kConvergence; break; }
-        if (radius <= opt.min_radius) { out.term = kConvergence; break; }
-        ++iteration;
-        step_is_successful = false;
-
-        // LevenbergMarquardtStrategy::ComputeStep
-        if (!reuse_diagonal)
-            for (int k = 0; k < kNP; ++k)
-                diag[k] = fmin(fmax(Hs[k * kNP + k], opt.min_lm_diagonal), opt.max_lm_diagonal);
-        for (int i = 0; i < kNP * kNP; ++i) A[i] = Hs[i];
-        for (int k = 0; k < kNP; ++k) A[k * kNP + k] += diag[k] / radius;
-        const bool solved = cholesky_solve7(A, bs, step);
-        reuse_diagonal = true;
-        bool step_is_valid = false;
-        double model_cost_change = 0.0;
-        if (solved) {
-            double lin = 0.0, quad = 0.0;  // -(J s)^T (r + J s / 2) with s = -y
-            for (int a = 0; a < kNP; ++a) {
-                step[a] = -step[a];
-            }
-            for (int a = 0; a < kNP; ++a) {
-                double hs = 0.0;
-                for (int b = 0; b < kNP; ++b) hs += Hs[a * kNP + b] * step[b];
-                lin += step[a] * bs[a];
-                quad += step[a] * hs;
-            }
-            model_cost_change = -(lin + 0.5 * quad);
-            step_is_valid = model_cost_change > 0.0;
-        }
-        if (!step_is_valid) {  // HandleInvalidStep
-            if (++num_invalid >= opt.max_consecutive_invalid) { out.term = kFailure; break; }
-            radius /= decrease_factor; decrease_factor *= 2.0;
-            continue;
-        }
-        num_invalid = 0;
-        double step_norm = 0.0;
-        for (int k = 0; k < kNP; ++k) {
-            delta[k] = step[k] * scale[k];
-            cand[k] = x[k] + delta[k];
-            step_norm += delta[k] * delta[k];
-        }
-        step_norm = sqrt(step_norm);
-        acc[0] = 0.0;
-        pass(cand, false, acc);
-        out.cost_evals++;
-        const double cand_cost = isfinite(acc[0]) ? acc[0] : 1.7976931348623157e308;
-        if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) { out.term = kConvergence; break; }
-        const double cost_change = x_cost - cand_cost;
-        if (fabs(cost_change) <= opt.function_tolerance * x_cost) { out.term = kConvergence; break; }
-        const double relative_decrease = cost_change / model_cost_change;
-        if (relative_decrease > opt.min_relative_decrease) {  // HandleSuccessfulStep
-            for (int k = 0; k < kNP; ++k) x[k] = cand[k];
-            for (int i = 0; i < kNAcc; ++i) acc[i] = 0.0;
-            pass(x, true, acc);
-            out.jac_evals++;
-            if (!all_finite(acc, kNAcc)) { out.term = kFailure; break; }
-            load_point(false);
-            step_is_successful = true;
-            const double q = 2.0 * relative_decrease - 1.0;  // LevenbergMarquardtStrategy::StepAccepted
-            radius = radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
-            radius = fmin(opt.max_radius, radius);
-            decrease_factor = 2.0;
-            reuse_diagonal = false;
-        } else {  // StepRejected
-            radius /= decrease_factor; decrease_factor *= 2.0;
-        }
-    }
-    out.final_cost = minimum_cost;
-    return out;
-}
-
 // Kernel arguments (device pointers).  Layout codes as MRPNP_LAYOUT_* of monorun_pnp.h.
 struct KParams {
     const float* coords_3d;   // normalised object coordinates
@@ -429,7 +247,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pnp_noc_kernel(const KParam
         for (int k = 0; k < kNP; ++k) x[k] = kp.init[(size_t)obj * kNP + k];
         LMOptions opt = default_options();
         if (kp.max_iterations > 0) opt.max_num_iterations = kp.max_iterations;
-        const LMResult r = minimize(pass, x, opt);
+        const LMResult r = mrlm::minimize<kNP>(pass, x, opt);
         if (lane == 0) {
             double* out = kp.result + (size_t)obj * kResultStride;
             for (int k = 0; k < kNP; ++k) out[k] = x[k];

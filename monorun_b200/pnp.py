@@ -196,6 +196,38 @@ def solve_noc_batched(coords_3d, coords_2d, weights, logdim, logdim_wgt, cam_mat
     return result
 
 
+def solve_6dof_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose6, inlier_mask=None, *,
+                       layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, max_iterations=50):
+    """6-DoF extension of the solver -- direct wrapper of ``mrpnp_solve_6dof``: unknowns [rvec(3), t(3)] (angle-axis
+    as ceres::AngleAxisRotatePoint), everything else as :func:`solve_batched`.  init_pose6 [N,6].
+    Returns result [N,48] float64: rvec, t | cov 6x6 | valid, lm_iterations, final_cost, cost_evals, termination, pad."""
+    dev = coords_3d.device
+    ctx = get_ctx(dev)
+    n = coords_3d.shape[0]
+    planar = layout == 'planar'
+    n_pts = coords_3d[0].numel() // 3 if n else (coords_3d.shape[2:].numel() if planar else coords_3d.shape[1])
+    wmode = {'logstd': C['MRPNP_W_LOGSTD'], 'istd': C['MRPNP_W_ISTD'], 'full': C['MRPNP_W_FULL']}[weight_mode]
+    result = torch.empty((n, 48), dtype=torch.float64, device=dev)
+    if n == 0:
+        return result
+    c3, c2, w = _f32c(coords_3d), _f32c(coords_2d), _f32c(weights)
+    cam, rng = _f32c(cam_mats).reshape(-1, 9), _f32c(uv_range).reshape(-1, 4)
+    if cam.shape[0] not in (1, n) or rng.shape[0] not in (1, n):
+        raise ValueError('cam_mats / uv_range must have batch size 1 or N')
+    init = _f32c(init_pose6).reshape(n, 6)
+    inl_in = pack_mask(inlier_mask.reshape(n, n_pts).bool()) if inlier_mask is not None else None
+    p = make_params(
+        n, n_pts, layout=C['MRPNP_LAYOUT_PLANAR'] if planar else C['MRPNP_LAYOUT_INTERLEAVED'], weight_mode=wmode,
+        cam_stride=9 if cam.shape[0] == n and n > 1 else 0, range_stride=4 if rng.shape[0] == n and n > 1 else 0,
+        max_iterations=int(max_iterations), z_min=float(z_min), std_scale=float(std_scale))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_solve_6dof(
+            ctx.ptr, p, _ptr(c3), _ptr(c2), _ptr(w), _ptr(cam), _ptr(rng), _ptr(init), _ptr(inl_in, 'uint32_t*'),
+            _ptr(result, 'double*'), _native.ffi.cast('void*', stream)))
+    return result
+
+
 def exact_hessian(coords_3d, coords_2d, weights, cam_mats, uv_range, pose, inlier_mask=None, *, layout='planar',
                   weight_mode='logstd', z_min=0.5, std_scale=10.0, rows=None, return_hessian=True):
     """``mrpnp_exact_hessian``: the second-order pose Hessian of the reference's ``exact_hessian`` (hessian.py:5-64)
@@ -474,6 +506,30 @@ class PnPUncert(torch.nn.Module):
             epnp_istd_thres=self.epnp_istd_thres, epnp_ransac_thres=epnp_ransac_thres,
             inlier_opt_only=self.inlier_opt_only, forward_exact_hessian=self.forward_exact_hessian,
             use_6dof=self.use_6dof, init_pose=init_pose, precision=self.precision)
+
+    def forward_6dof(self, coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range, init_pose=None):
+        """``use_6dof=True`` extension (the reference accepts the flag and never reads it, pnp_uncert.py:11,98,122,142):
+        the 4-DoF solve of :meth:`forward` supplies the start (0, yaw, 0, t) and the inlier mask, then all six pose
+        parameters are refined.  Returns (ret_val (N,), r_vec (N,3) angle-axis, t_vec (N,3), pose_cov (N,6,6),
+        inlier_mask (N,P))."""
+        with torch.no_grad():
+            ret_val, yaw, t_vec, _, inlier_mask = self.forward(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range,
+                                                               v_range, init_pose=init_pose)
+            n = coords_2d.shape[0]
+            if n == 0:
+                return ret_val, coords_2d.new_zeros((0, 3)), t_vec, coords_2d.new_zeros((0, 6, 6)), inlier_mask
+            zero = torch.zeros_like(yaw)
+            init6 = torch.cat([zero, yaw, zero, t_vec], 1)
+            rows = max(u_range.shape[0], v_range.shape[0])
+            uv_range = torch.cat([u_range.expand(rows, 2), v_range.expand(rows, 2)], dim=1)
+            istd = coords_2d_istd
+            if self.coord_istd_normalize:
+                istd = istd / torch.mean(istd, dim=(1, 2), keepdim=True).clamp(min=self.eps)
+            res = solve_6dof_batched(coords_3d, coords_2d, istd, cam_mats, uv_range, init6,
+                                     inlier_mask if self.inlier_opt_only else None, layout='interleaved',
+                                     weight_mode='istd', z_min=self.z_min)
+            ok = ret_val & (res[:, 42] > 0.5)
+            return (ok, res[:, 0:3].float(), res[:, 3:6].float(), res[:, 6:42].reshape(n, 6, 6).float(), inlier_mask)
 
     def forward_dense(self, coords_2d, coords_2d_logstd, coords_3d, cam_mats, uv_range, std_scale, init_pose=None):
         """Head-level entry used by UncertPropPnPOptimizer: NCHW tensors and log-std straight into the kernel

@@ -63,7 +63,7 @@ void solve(const float* c3, const float* c2, const float* cw, const unsigned cha
     for (int k = 0; k < 3; ++k) { pass.logdim[k] = logdim[k]; pass.logdim_wgt[k] = logdim_wgt[k]; }
     for (int k = 0; k < mrnoc::kNP; ++k) x[k] = init[k];
     const mrnoc::LMOptions opt = mrnoc::default_options();
-    const mrnoc::LMResult r = mrnoc::minimize(pass, x, opt);
+    const mrnoc::LMResult r = mrlm::minimize<mrnoc::kNP>(pass, x, opt);
     for (int k = 0; k < mrnoc::kNP; ++k) result[k] = x[k];
     result[7] = (r.term == mrnoc::kConvergence || r.term == mrnoc::kNoConvergence) ? 1.0 : 0.0;
     result[8] = r.iterations; result[9] = r.final_cost; result[10] = r.cost_evals; result[11] = r.term;
