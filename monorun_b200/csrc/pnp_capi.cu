@@ -492,9 +492,12 @@ int mrpnp_solve_6dof(mrpnp_ctx* ctx, const mrpnp_params* p,
     kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.planar = p->layout == MRPNP_LAYOUT_PLANAR;
     kp.wmode = p->weight_mode; kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride;
     kp.max_iterations = p->max_iterations; kp.z_min = p->z_min; kp.std_scale = p->std_scale;
-    const int ctas = std::min((p->n_obj + mr6::kWarpsPerCta - 1) / mr6::kWarpsPerCta, ctx->num_sms * 8);
+    // one object per warp, CTAs handed out by the hardware scheduler: objects differ in LM iterations, and a
+    // persistent grid with static striding measured 10 % slower (profiles/r01b_ncu_noc_summary.txt)
+    const bool full = p->weight_mode == MRPNP_W_FULL;
+    const int ctas = (p->n_obj + mr6::kWarpsPerCta - 1) / mr6::kWarpsPerCta;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (p->weight_mode == MRPNP_W_FULL)
+    if (full)
         mr6::pnp_6dof_kernel<true><<<ctas, mr6::kWarpsPerCta * 32, 0, st>>>(kp);
     else
         mr6::pnp_6dof_kernel<false><<<ctas, mr6::kWarpsPerCta * 32, 0, st>>>(kp);
@@ -530,7 +533,8 @@ int mrpnp_solve_noc(mrpnp_ctx* ctx, const mrpnp_noc_params* p,
     kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.planar = p->layout == MRPNP_LAYOUT_PLANAR;
     kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride; kp.max_iterations = p->max_iterations;
     kp.z_min = p->z_min; kp.delta = p->huber_delta;
-    const int ctas = std::min((p->n_obj + mrnoc::kWarpsPerCta - 1) / mrnoc::kWarpsPerCta, ctx->num_sms * 8);
+    // one object per warp, CTAs handed out by the hardware scheduler (see mrpnp_solve_6dof)
+    const int ctas = (p->n_obj + mrnoc::kWarpsPerCta - 1) / mrnoc::kWarpsPerCta;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (p->weight_mode == MRPNP_W_FULL)
         mrnoc::pnp_noc_kernel<true><<<ctas, mrnoc::kWarpsPerCta * 32, 0, st>>>(kp);

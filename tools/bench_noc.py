@@ -54,6 +54,40 @@ def main():
             cpu_objects_per_s=m / cpu_s, cpu_threads=os.cpu_count(), cpu_sample=m, same_decisions=float(same),
             max_param_diff=float(np.abs(res[:m, :7] - r['dimpose']).max()), valid=float((res[:, 7] > 0).mean()))
         print(out)
+    # 6-DoF extension (mrpnp_solve_6dof)
+    from tests.sixdof_cases import make_case as make6, oracle_solve as oracle6
+    from oracle import sixdof_driver as sd
+    for full in (False, True):
+        c = make6(a.n, full=full, cfg=3, mode='S1')
+        d = {k: torch.from_numpy(np.ascontiguousarray(c[k])).cuda() for k in ('c3', 'c2', 'w', 'cam', 'uv_range', 'init')}
+        pl = [d[k].permute(0, 2, 1).contiguous() for k in ('c3', 'c2', 'w')]
+
+        def run6():
+            return pnp.solve_6dof_batched(pl[0], pl[1], pl[2], d['cam'], d['uv_range'], d['init'], layout='planar',
+                                          weight_mode='full' if full else 'istd')
+        for _ in range(3):
+            res = run6()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            res = run6()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        res = res.cpu().numpy()
+        m = a.cpu_sample
+        cs = {k: (v[:m] if isinstance(v, np.ndarray) and v.shape[0] == a.n else v) for k, v in c.items()}
+        t0 = time.perf_counter()
+        r = oracle6(sd, cs, full, threads=0)
+        cpu_s = time.perf_counter() - t0
+        same = (res[:m, 45] == r['stats'][:, 1]) & (np.abs(res[:m, 44] - r['cost']) <= 1e-9 * r['cost'])
+        out['6dof_' + ('full' if full else 'diag')] = dict(
+            n=a.n, ms=ms, objects_per_s=a.n / ms * 1e3, mean_cost_evals=float(res[:, 45].mean()),
+            cpu_objects_per_s=m / cpu_s, cpu_threads=os.cpu_count(), cpu_sample=m, same_lm_paths=float(same.mean()),
+            max_pose_diff_same_paths=float(np.abs(res[:m, :6] - r['pose'])[same].max()), valid=float((res[:, 42] > 0).mean()))
+    print({k: v for k, v in out.items() if k.startswith('6dof')})
+
     # second-order covariance pass (mrpnp_exact_hessian): one read of the correspondences at the final pose
     c = make_case(a.n, mode='S1', cfg=3)
     metric = torch.from_numpy((c['coords_3d']).astype(np.float32)).cuda().permute(0, 2, 1).contiguous()
