@@ -155,6 +155,9 @@ struct KParams {
 #ifdef __CUDACC__
 
 constexpr int kWarpsPerCta = 4;
+#ifndef MR6_MIN_BLOCKS
+#define MR6_MIN_BLOCKS 2  // CTAs per SM the register allocation aims at (3 measured 10 % slower: Pose6 spills)
+#endif
 
 template <bool FULLW>
 struct WarpPass {
@@ -201,7 +204,7 @@ struct WarpPass {
 };
 
 template <bool FULLW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) pnp_6dof_kernel(const KParams kp) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MR6_MIN_BLOCKS) pnp_6dof_kernel(const KParams kp) {
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * kWarpsPerCta;

@@ -171,6 +171,9 @@ constexpr int kResultStride = 12;  // dimpose[7], valid, iterations, final_cost,
 #ifdef __CUDACC__
 
 constexpr int kWarpsPerCta = 4;
+#ifndef MRNOC_MIN_BLOCKS
+#define MRNOC_MIN_BLOCKS 3  // CTAs per SM the register allocation aims at (168 registers; 2 measured 8-12 % slower)
+#endif
 
 __device__ __forceinline__ double shfl_xor_f64(double v, int m) {
     return __shfl_xor_sync(0xffffffffu, v, m);
@@ -222,7 +225,7 @@ struct WarpPass {
 };
 
 template <bool FULLW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) pnp_noc_kernel(const KParams kp) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MRNOC_MIN_BLOCKS) pnp_noc_kernel(const KParams kp) {
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * kWarpsPerCta;
