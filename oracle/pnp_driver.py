@@ -8,7 +8,8 @@ reference's per-object driver so parity tests read like the reference's own call
 * ``pnp_uncert_ref``      <- monorun/ops/least_squares/pnp_uncert.py:7-87 (numpy fp32 in/out, covariance
                              through the restated approx_hessian, hessian.py:67-87)
 
-PARITY UNPINNED for the Ceres control flow (see the header of pnp_oracle.cpp).  Only tests/,
+No output of the reference binary exists to pin against; the minimiser is pinned to Ceres' own published tutorial
+tables instead (see the header of pnp_oracle.cpp).  Only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may import this module.
 """
 import os
@@ -38,6 +39,8 @@ void pnp_approx_hessian(const double* pts2d, const double* pts3d, const double* 
                         const double* pose, const unsigned char* inlier, int pn, const double* clips,
                         double* H);
 int pnp_spd_inverse4(const double* H, double* inv);
+int ceres_kat_hello_world(double* trace, int max_rows, double* x_final, double* summary);
+int ceres_kat_powell(double* trace, int max_rows, double* x_final, double* summary);
 void pnp_oracle_set_adopt_candidate_on_ftol(int v);
 int pnp_oracle_num_threads(void);
 """
@@ -127,6 +130,16 @@ def lm_batch(coords_2d, coords_3d, wgt, cam_mats, init_pose, clips, inlier_mask=
         ffi.cast('long long*', off.ctypes.data), _dp(cl), n, int(full_w),
         ffi.cast('int*', stats.ctypes.data), _dp(cost), int(threads))
     return dict(val=val > 0, pose=pose, cov=cov, tr=tr, stats=stats, cost=cost)
+
+
+def ceres_tutorial_trace(problem):
+    """Runs the oracle's minimiser (the same template that solves the PnP problems) on a Ceres tutorial problem:
+    'hello_world' (examples/helloworld.cc) or 'powell' (examples/powell.cc).  Returns (rows [k,7] = iteration, cost,
+    cost_change, |gradient|, |step|, tr_ratio, tr_radius; x_final; (termination, iterations, final |gradient|))."""
+    fn, n = {'hello_world': (lib().ceres_kat_hello_world, 1), 'powell': (lib().ceres_kat_powell, 4)}[problem]
+    trace, x, summary = np.zeros((64, 7)), np.zeros(n), np.zeros(3)
+    k = fn(_dp(trace), 64, _dp(x), _dp(summary))
+    return trace[:k], x, summary
 
 
 def eval_cost_grad_hess(coord_2d, coord_3d, wgt, cam_mat, pose, clips, full_w=False):

@@ -5,13 +5,21 @@
 // parity checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs.  Nothing under monorun_b200/ may import, link or call it.
 //
-// PARITY UNPINNED for the solver control flow: the reference links ceres-solver
+// PARITY UNPINNED AGAINST THE REFERENCE BINARY (pinned to Ceres' published known answers instead, see
+// below): the reference links ceres-solver
 // 1.14.0 (INSTALL.md:13,29-30; monorun/ops/least_squares/setup.py:20-22), which is
 // neither vendored in /root/reference nor installable here (no Ceres/Eigen/glog, no
 // network), and the reference ships no tests or golden vectors for this path.  The
 // trust-region Levenberg-Marquardt loop below restates the published algorithm of
 // Ceres 1.14 (TrustRegionMinimizer + LevenbergMarquardtStrategy + DenseQRSolver with
-// default Solver::Options) from knowledge of the upstream source.  What IS pinned:
+// default Solver::Options) from knowledge of the upstream source.  So no output of the reference BINARY
+// on a PnP input exists to compare with.  What IS pinned:
+//   * the minimiser itself against Ceres' OWN published known answers: the same template that solves the
+//     PnP problems (trust_region_lm_n) reproduces, to every printed digit, the iteration tables of the Ceres
+//     tutorial problems (helloworld.cc: 3 rows; powell.cc: all 15 rows of cost / cost_change / |gradient| /
+//     |step| / tr_ratio / tr_radius, the final x and "Gradient max norm 3.642190e-11") --
+//     tests/test_oracle.py::test_minimiser_reproduces_the_ceres_tutorial_tables.  That fixes Jacobi scaling,
+//     the LM diagonal, step acceptance, the radius update and the termination tests;
 //   * the residual / clip semantics follow the reference functor line by line
 //     (monorun/ops/least_squares/src/pnp_uncert_cpu.cpp:24-51 diag weights,
 //      :189-217 full 2x2 weights restricted to the 4 pose parameters);
@@ -145,11 +153,12 @@ bool evaluate(const Problem& P, const double* x, double* cost, double* res, doub
 }
 
 // DenseQRSolver::SolveImpl (Ceres 1.14): least squares  min |[A; diag(D)] y - [b; 0]|
-// by unpivoted Householder QR (Eigen householderQr().solve()).  A is m x 4 row-major,
+// by unpivoted Householder QR (Eigen householderQr().solve()).  A is m x n row-major,
 // already column-scaled.  Returns false if y is not finite.
+template <int n>
 bool dense_qr_solve(const double* A, const double* b, const double* D, int m, double* y,
                     std::vector<double>& work) {
-    const int n = 4, M = m + n;
+    const int M = m + n;
     work.resize(static_cast<size_t>(M) * (n + 1));
     double* W = work.data();  // M x (n+1): augmented [A | b ; D | 0]
     for (int i = 0; i < m; ++i) {
@@ -198,13 +207,20 @@ struct LMResult {
     double tr_radius;      // summary.iterations.back().trust_region_radius (cpp:277)
 };
 
-// TrustRegionMinimizer::Minimize of Ceres 1.14 specialised to: one 4-vector parameter
-// block, no bounds, no inner iterations, monotonic steps, Jacobi scaling on, LM strategy,
-// DENSE_QR.  x holds init on entry and the returned parameters on exit.
-LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
-    const int m = 2 * P.pn;
-    std::vector<double> res(m), jac(static_cast<size_t>(m) * 4), model_res(m), work;
-    double x[4], grad[4], scale[4], diag[4], lm_diag[4], step[4], delta[4], cand[4];
+// One row of Solver::Summary::iterations as minimizer_progress_to_stdout prints it:
+// iteration, cost, cost_change, |gradient|_max, |step|, tr_ratio, tr_radius (successful steps and iteration 0).
+struct TraceRow { double v[7]; };
+
+// TrustRegionMinimizer::Minimize of Ceres 1.14 for one N-vector parameter block: no bounds, no inner
+// iterations, monotonic steps, Jacobi scaling on, LM strategy, DENSE_QR.  x holds init on entry and the
+// returned parameters on exit.  eval(x, &cost, res | NULL, jac | NULL, grad | NULL) -> evaluation is valid;
+// m = number of residuals.  The PnP solver below instantiates it with N = 4; the known-answer tests at the
+// end of this file (Ceres' own tutorial problems) with N = 1 and N = 4.
+template <int N, class Eval>
+LMResult trust_region_lm_n(const Eval& eval, int m, double* x_io, const LMOptions& opt,
+                           std::vector<TraceRow>* trace = nullptr) {
+    std::vector<double> res(m), jac(static_cast<size_t>(m) * N), model_res(m), work;
+    double x[N], grad[N], scale[N], diag[N], lm_diag[N], step[N], delta[N], cand[N];
     std::memcpy(x, x_io, sizeof(x));
     LMResult out{FAILURE, 0, 0, 0, 0.0, opt.initial_trust_region_radius};
 
@@ -215,24 +231,26 @@ LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
     double minimum_cost = std::numeric_limits<double>::max();
 
     // ---- IterationZero -> EvaluateGradientAndJacobian(new_point) ----
-    bool ok = evaluate(P, x, &x_cost, res.data(), jac.data(), grad);
+    bool ok = eval(x, &x_cost, res.data(), jac.data(), grad);
     out.num_cost_evals++; out.num_jac_evals++;
     if (!ok) { out.final_cost = x_cost; return out; }  // FAILURE, parameters untouched
     {   // jacobi_scaling: 1 / (1 + sqrt(squared column norm)), from the initial Jacobian only
-        double cn[4] = {0, 0, 0, 0};
-        for (int i = 0; i < m; ++i) for (int k = 0; k < 4; ++k) cn[k] += jac[i * 4 + k] * jac[i * 4 + k];
-        for (int k = 0; k < 4; ++k) scale[k] = 1.0 / (1.0 + std::sqrt(cn[k]));
+        double cn[N];
+        for (int k = 0; k < N; ++k) cn[k] = 0.0;
+        for (int i = 0; i < m; ++i) for (int k = 0; k < N; ++k) cn[k] += jac[i * N + k] * jac[i * N + k];
+        for (int k = 0; k < N; ++k) scale[k] = 1.0 / (1.0 + std::sqrt(cn[k]));
     }
     auto scale_columns = [&]() {
-        for (int i = 0; i < m; ++i) for (int k = 0; k < 4; ++k) jac[i * 4 + k] *= scale[k];
+        for (int i = 0; i < m; ++i) for (int k = 0; k < N; ++k) jac[i * N + k] *= scale[k];
     };
     scale_columns();
     auto max_norm = [](const double* g) {
-        double v = 0; for (int k = 0; k < 4; ++k) v = std::max(v, std::fabs(g[k])); return v; };
-    auto norm4 = [](const double* v) {
-        double s = 0; for (int k = 0; k < 4; ++k) s += v[k] * v[k]; return std::sqrt(s); };
-    double x_norm = norm4(x);
+        double v = 0; for (int k = 0; k < N; ++k) v = std::max(v, std::fabs(g[k])); return v; };
+    auto norm_n = [](const double* v) {
+        double s = 0; for (int k = 0; k < N; ++k) s += v[k] * v[k]; return std::sqrt(s); };
+    double x_norm = norm_n(x);
     double gradient_max_norm = max_norm(grad);
+    if (trace) trace->push_back(TraceRow{{0.0, x_cost, 0.0, gradient_max_norm, 0.0, 0.0, radius}});
 
     int iteration = 0;
     bool step_is_successful = true;  // iteration 0 counts as successful
@@ -253,22 +271,22 @@ LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
 
         // ---- ComputeTrustRegionStep -> LevenbergMarquardtStrategy::ComputeStep ----
         if (!reuse_diagonal) {
-            for (int k = 0; k < 4; ++k) diag[k] = 0.0;
-            for (int i = 0; i < m; ++i) for (int k = 0; k < 4; ++k) diag[k] += jac[i * 4 + k] * jac[i * 4 + k];
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < N; ++k) diag[k] = 0.0;
+            for (int i = 0; i < m; ++i) for (int k = 0; k < N; ++k) diag[k] += jac[i * N + k] * jac[i * N + k];
+            for (int k = 0; k < N; ++k)
                 diag[k] = std::min(std::max(diag[k], opt.min_lm_diagonal), opt.max_lm_diagonal);
         }
-        for (int k = 0; k < 4; ++k) lm_diag[k] = std::sqrt(diag[k] / radius);
-        bool solved = dense_qr_solve(jac.data(), res.data(), lm_diag, m, step, work);
+        for (int k = 0; k < N; ++k) lm_diag[k] = std::sqrt(diag[k] / radius);
+        bool solved = dense_qr_solve<N>(jac.data(), res.data(), lm_diag, m, step, work);
         reuse_diagonal = true;
         bool step_is_valid = false;
         double model_cost_change = 0.0;
         if (solved) {
-            for (int k = 0; k < 4; ++k) step[k] = -step[k];
+            for (int k = 0; k < N; ++k) step[k] = -step[k];
             double dot = 0.0;  // -(J step)^T (f + J step / 2)
             for (int i = 0; i < m; ++i) {
                 double mr = 0.0;
-                for (int k = 0; k < 4; ++k) mr += jac[i * 4 + k] * step[k];
+                for (int k = 0; k < N; ++k) mr += jac[i * N + k] * step[k];
                 dot += mr * (res[i] + mr / 2.0);
             }
             model_cost_change = -dot;
@@ -281,20 +299,18 @@ LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
             continue;
         }
         num_invalid = 0;
-        for (int k = 0; k < 4; ++k) delta[k] = step[k] * scale[k];  // undo column scaling
+        for (int k = 0; k < N; ++k) delta[k] = step[k] * scale[k];  // undo column scaling
 
         // ---- ComputeCandidatePointAndEvaluateCost ----
-        for (int k = 0; k < 4; ++k) cand[k] = x[k] + delta[k];
-        if (!evaluate(P, cand, &cand_cost, nullptr, nullptr, nullptr))
+        for (int k = 0; k < N; ++k) cand[k] = x[k] + delta[k];
+        if (!eval(cand, &cand_cost, nullptr, nullptr, nullptr))
             cand_cost = std::numeric_limits<double>::max();
         out.num_cost_evals++;
 
         // ---- ParameterToleranceReached ----
-        {
-            const double step_norm = norm4(delta);
-            if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
-                out.term = CONVERGENCE; break;
-            }
+        const double step_norm = norm_n(delta);
+        if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+            out.term = CONVERGENCE; break;
         }
         // ---- FunctionToleranceReached ----
         const double cost_change = x_cost - cand_cost;
@@ -310,8 +326,8 @@ LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
         if (relative_decrease > opt.min_relative_decrease) {
             // ---- HandleSuccessfulStep ----
             std::memcpy(x, cand, sizeof(x));
-            x_norm = norm4(x);
-            ok = evaluate(P, x, &x_cost, res.data(), jac.data(), grad);
+            x_norm = norm_n(x);
+            ok = eval(x, &x_cost, res.data(), jac.data(), grad);
             out.num_jac_evals++;
             if (!ok) { out.term = FAILURE; break; }
             scale_columns();
@@ -322,6 +338,8 @@ LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
             radius = std::min(opt.max_trust_region_radius, radius);
             decrease_factor = 2.0;
             reuse_diagonal = false;
+            if (trace) trace->push_back(TraceRow{{double(iteration), x_cost, cost_change, gradient_max_norm, step_norm,
+                                                  relative_decrease, radius}});
         } else {
             // ---- HandleUnsuccessfulStep -> StepRejected ----
             radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
@@ -329,6 +347,14 @@ LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
     }
     out.final_cost = minimum_cost;
     return out;
+}
+
+// The PnP problem through the minimiser above (one 4-vector parameter block: yaw, t).
+LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
+    auto eval = [&P](const double* x, double* cost, double* res, double* jac, double* grad) {
+        return evaluate(P, x, cost, res, jac, grad);
+    };
+    return trust_region_lm_n<4>(eval, 2 * P.pn, x_io, opt);
 }
 
 // (J^T J)^-1 for a symmetric positive definite 4x4 via Cholesky; false if not SPD.
@@ -506,6 +532,59 @@ void pnp_approx_hessian(const double* pts2d, const double* pts3d, const double* 
 
 // inverse of an SPD 4x4 (torch.inverse(h) in pnp_uncert.py:77-78); returns 0 if not SPD.
 int pnp_spd_inverse4(const double* H, double* inv) { return spd_inverse4(H, inv) ? 1 : 0; }
+
+// ---- Known-answer tests of the minimiser: the two problems of the Ceres Solver tutorial
+// (examples/helloworld.cc: f = 10 - x from x = 0.5;  examples/powell.cc: Powell's singular function from
+// (3, -1, 0, 1), both with DENSE_QR and default options), whose minimizer_progress_to_stdout tables are printed in
+// docs/source/nnls_tutorial.rst.  trace: up to max_rows x 7 doubles (iteration, cost, cost_change, |gradient|,
+// |step|, tr_ratio, tr_radius); returns the number of rows.  x_final: 1 / 4 doubles; summary: termination,
+// iterations, final gradient max norm.
+int ceres_kat_hello_world(double* trace, int max_rows, double* x_final, double* summary) {
+    auto eval = [](const double* x, double* cost, double* res, double* jac, double* grad) {
+        const double r = 10.0 - x[0];
+        *cost = 0.5 * r * r;
+        if (res) res[0] = r;
+        if (jac) jac[0] = -1.0;
+        if (grad) grad[0] = -r;
+        return true;
+    };
+    std::vector<TraceRow> rows;
+    double x[1] = {0.5};
+    const LMResult r = trust_region_lm_n<1>(eval, 1, x, LMOptions(), &rows);
+    const int n = std::min<int>(max_rows, rows.size());
+    for (int i = 0; i < n; ++i) std::memcpy(trace + i * 7, rows[i].v, sizeof(rows[i].v));
+    x_final[0] = x[0];
+    summary[0] = r.term; summary[1] = r.iterations; summary[2] = rows.back().v[3];
+    return n;
+}
+
+int ceres_kat_powell(double* trace, int max_rows, double* x_final, double* summary) {
+    auto eval = [](const double* x, double* cost, double* res, double* jac, double* grad) {
+        const double s5 = std::sqrt(5.0), s10 = std::sqrt(10.0);
+        const double f[4] = {x[0] + 10.0 * x[1], s5 * (x[2] - x[3]), (x[1] - 2.0 * x[2]) * (x[1] - 2.0 * x[2]),
+                             s10 * (x[0] - x[3]) * (x[0] - x[3])};
+        *cost = 0.5 * (f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3]);
+        if (res) std::memcpy(res, f, sizeof(f));
+        if (jac) {
+            const double a = x[1] - 2.0 * x[2], b = x[0] - x[3];
+            const double J[16] = {1.0, 10.0, 0.0, 0.0,
+                                  0.0, 0.0, s5, -s5,
+                                  0.0, 2.0 * a, -4.0 * a, 0.0,
+                                  2.0 * s10 * b, 0.0, 0.0, -2.0 * s10 * b};
+            std::memcpy(jac, J, sizeof(J));
+            if (grad) for (int k = 0; k < 4; ++k) grad[k] = J[k] * f[0] + J[4 + k] * f[1] + J[8 + k] * f[2] + J[12 + k] * f[3];
+        }
+        return true;
+    };
+    std::vector<TraceRow> rows;
+    double x[4] = {3.0, -1.0, 0.0, 1.0};
+    const LMResult r = trust_region_lm_n<4>(eval, 4, x, LMOptions(), &rows);
+    const int n = std::min<int>(max_rows, rows.size());
+    for (int i = 0; i < n; ++i) std::memcpy(trace + i * 7, rows[i].v, sizeof(rows[i].v));
+    std::memcpy(x_final, x, sizeof(x));
+    summary[0] = r.term; summary[1] = r.iterations; summary[2] = rows.back().v[3];
+    return n;
+}
 
 void pnp_oracle_set_adopt_candidate_on_ftol(int v) { g_options.adopt_candidate_on_ftol = v; }
 int pnp_oracle_num_threads(void) {

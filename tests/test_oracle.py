@@ -173,3 +173,58 @@ def test_too_few_inliers_uses_all_points(oracle):
                                     op['cam_mats'][0], op['u_range'][0], op['v_range'][0], None,
                                     inlier_opt_only=True, init_pose=b['init_pose'][0])
     assert out[0] and out[5].all()
+
+
+# ---------------------------------------------------------------- Ceres' own published known answers
+# The iteration tables the Ceres Solver tutorial prints for its two introductory problems
+# (docs/source/nnls_tutorial.rst: output of examples/helloworld.cc and examples/powell.cc, DENSE_QR, default
+# Solver::Options, minimizer_progress_to_stdout).  Columns: iter, cost, cost_change, |gradient|, |step|, tr_ratio,
+# tr_radius.  Ceres is not vendored by the reference and there is no network here, so these rows are transcribed
+# from the public documentation; they pin the trust-region control flow of the restated minimiser (Jacobi scaling,
+# LM diagonal, step acceptance, radius update, termination tests) to Ceres' own output, to every printed digit.
+HELLO_WORLD = """
+   0  4.512500e+01    0.00e+00    9.50e+00   0.00e+00   0.00e+00  1.00e+04
+   1  4.511598e-07    4.51e+01    9.50e-04   9.50e+00   1.00e+00  3.00e+04
+   2  5.012552e-16    4.51e-07    3.17e-08   9.50e-04   1.00e+00  9.00e+04
+"""
+POWELL = """
+   0  1.075000e+02    0.00e+00    1.55e+02   0.00e+00   0.00e+00  1.00e+04
+   1  5.036190e+00    1.02e+02    2.00e+01   2.16e+00   9.53e-01  3.00e+04
+   2  3.148168e-01    4.72e+00    2.50e+00   6.23e-01   9.37e-01  9.00e+04
+   3  1.967760e-02    2.95e-01    3.13e-01   3.08e-01   9.37e-01  2.70e+05
+   4  1.229900e-03    1.84e-02    3.91e-02   1.54e-01   9.37e-01  8.10e+05
+   5  7.687123e-05    1.15e-03    4.89e-03   7.69e-02   9.37e-01  2.43e+06
+   6  4.804625e-06    7.21e-05    6.11e-04   3.85e-02   9.37e-01  7.29e+06
+   7  3.003028e-07    4.50e-06    7.64e-05   1.92e-02   9.37e-01  2.19e+07
+   8  1.877006e-08    2.82e-07    9.54e-06   9.62e-03   9.37e-01  6.56e+07
+   9  1.173223e-09    1.76e-08    1.19e-06   4.81e-03   9.37e-01  1.97e+08
+  10  7.333425e-11    1.10e-09    1.49e-07   2.40e-03   9.37e-01  5.90e+08
+  11  4.584044e-12    6.88e-11    1.86e-08   1.20e-03   9.37e-01  1.77e+09
+  12  2.865573e-13    4.30e-12    2.33e-09   6.02e-04   9.37e-01  5.31e+09
+  13  1.791438e-14    2.69e-13    2.91e-10   3.01e-04   9.37e-01  1.59e+10
+  14  1.120029e-15    1.68e-14    3.64e-11   1.51e-04   9.37e-01  4.78e+10
+"""
+
+
+def _printed(rows):
+    """Format like Ceres' progress table so the comparison is on the printed digits."""
+    return ['%4d  %.6e    %.2e    %.2e   %.2e   %.2e  %.2e' % (int(r[0]), *r[1:]) for r in rows]
+
+
+@pytest.mark.parametrize('problem,table', [('hello_world', HELLO_WORLD), ('powell', POWELL)])
+def test_minimiser_reproduces_the_ceres_tutorial_tables(oracle, problem, table):
+    rows, x, summary = oracle.ceres_tutorial_trace(problem)
+    expected = [ln for ln in table.strip('\n').split('\n')]
+    got = _printed(rows)
+    assert len(got) == len(expected)
+    for g, e in zip(got, expected):
+        assert g.split() == e.split(), (g, e)
+    assert summary[0] == 0  # CONVERGENCE
+    if problem == 'hello_world':
+        # "x : 0.5 -> 10", "Iterations: 2": a third step ends on the parameter tolerance and is not adopted
+        assert '%.6g' % x[0] == '10' and summary[1] == 2
+    else:
+        # "Final x1 = 0.000146222, x2 = -1.46222e-05, x3 = 2.40957e-05, x4 = 2.40957e-05";
+        # "Gradient tolerance reached. Gradient max norm 3.642190e-11 <= 1.000000e-10"
+        assert ['%.6g' % v for v in x] == ['0.000146222', '-1.46222e-05', '2.40957e-05', '2.40957e-05']
+        assert '%.6e' % summary[2] == '3.642190e-11' and summary[1] == 14
