@@ -228,3 +228,38 @@ def test_minimiser_reproduces_the_ceres_tutorial_tables(oracle, problem, table):
         # "Gradient tolerance reached. Gradient max norm 3.642190e-11 <= 1.000000e-10"
         assert ['%.6g' % v for v in x] == ['0.000146222', '-1.46222e-05', '2.40957e-05', '2.40957e-05']
         assert '%.6e' % summary[2] == '3.642190e-11' and summary[1] == 14
+
+
+@pytest.fixture(scope='session')
+def lm_dense_kat():
+    import ctypes
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, 'harness', 'lm_dense_kat_harness.cpp')
+    hdr = os.path.join(os.path.dirname(here), 'monorun_b200', 'csrc', 'lm_dense.cuh')
+    out = os.path.join(here, 'harness', 'liblm_dense_kat_harness.so')
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(['/usr/bin/g++', '-O2', '-fPIC', '-std=c++17', '-Wno-unknown-pragmas', '-shared',
+                               '-I', os.path.dirname(hdr), '-o', out, src])
+    return ctypes.CDLL(out)
+
+
+@pytest.mark.parametrize('problem,table,n', [('hello_world', HELLO_WORLD, 1), ('powell', POWELL, 4)])
+def test_kernel_controller_reproduces_the_ceres_tutorial_tables(lm_dense_kat, problem, table, n):
+    """The trust-region controller the fp64 CUDA kernels execute (monorun_b200/csrc/lm_dense.cuh: normal equations +
+    Cholesky instead of Ceres' QR), compiled for the host, on the same two problems: cost, cost_change, |gradient| and
+    |step| of every iteration as printed in Ceres' documentation (tr_ratio / tr_radius are internal to it)."""
+    import ctypes
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rows, x, summary = np.zeros((64, 2 + n)), np.zeros(n), np.zeros(3)
+    k = getattr(lm_dense_kat, 'lm_dense_kat_' + problem)(fp(rows), 64, fp(x), fp(summary))
+    expected = [ln.split() for ln in table.strip('\n').split('\n')]
+    assert k == len(expected)
+    for i in range(k):
+        step = np.linalg.norm(rows[i, 2:] - rows[i - 1, 2:]) if i else 0.0
+        change = rows[i - 1, 0] - rows[i, 0] if i else 0.0
+        got = ('%d  %.6e  %.2e  %.2e  %.2e' % (i, rows[i, 0], change, rows[i, 1], step)).split()
+        assert got == expected[i][:5], (got, expected[i])
+    assert summary[0] == 0 and summary[1] == k - 1
+    if problem == 'powell':
+        assert ['%.6g' % v for v in x] == ['0.000146222', '-1.46222e-05', '2.40957e-05', '2.40957e-05']
