@@ -36,7 +36,8 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(_HERE, 'pnp_noc_oracle.cpp')
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, 'ceres_lm.h'))):
         subprocess.check_call(['make', '-C', _HERE, '-s', 'libpnp_noc_oracle.so'] + (['-B'] if force else []))
     return _LIB_PATH
 

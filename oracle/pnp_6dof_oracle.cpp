@@ -23,25 +23,14 @@
 #include <omp.h>
 #endif
 
+#include "ceres_lm.h"
+
 namespace {
+
+using namespace ceres_lm;
 
 constexpr int N = 6;
 
-struct LMOptions {  // ceres::Solver::Options defaults of 1.14 (cpp:318-319 only sets DENSE_QR)
-    int max_num_iterations = 50;
-    double function_tolerance = 1e-6;
-    double gradient_tolerance = 1e-10;
-    double parameter_tolerance = 1e-8;
-    double initial_trust_region_radius = 1e4;
-    double max_trust_region_radius = 1e16;
-    double min_trust_region_radius = 1e-32;
-    double min_relative_decrease = 1e-3;
-    double min_lm_diagonal = 1e-6;
-    double max_lm_diagonal = 1e32;
-    int max_num_consecutive_invalid_steps = 5;
-};
-
-enum Termination { CONVERGENCE = 0, NO_CONVERGENCE = 1, FAILURE = 2 };
 
 // ceres::Jet<double, 6>, the operations the functor needs.
 struct Jet {
@@ -144,141 +133,6 @@ bool evaluate(const Problem& P, const double* x, double* cost, double* res, doub
     return ok && std::isfinite(acc);
 }
 
-// DenseQRSolver::SolveImpl: min |[A; diag(D)] y - [b; 0]| by unpivoted Householder QR.
-bool dense_qr_solve(const double* A, const double* b, const double* D, int m, double* y,
-                    std::vector<double>& work) {
-    const int n = N, M = m + n, ld = n + 1;
-    work.assign(static_cast<size_t>(M) * ld, 0.0);
-    double* W = work.data();
-    for (int i = 0; i < m; ++i) {
-        for (int k = 0; k < n; ++k) W[i * ld + k] = A[i * n + k];
-        W[i * ld + n] = b[i];
-    }
-    for (int i = 0; i < n; ++i) W[(m + i) * ld + i] = D[i];
-    for (int k = 0; k < n; ++k) {
-        double tail = 0.0;
-        for (int i = k + 1; i < M; ++i) tail += W[i * ld + k] * W[i * ld + k];
-        const double c0 = W[k * ld + k];
-        if (tail <= std::numeric_limits<double>::min()) continue;
-        double beta = std::sqrt(c0 * c0 + tail);
-        if (c0 >= 0) beta = -beta;
-        const double inv = 1.0 / (c0 - beta), tau = (beta - c0) / beta;
-        for (int i = k + 1; i < M; ++i) W[i * ld + k] *= inv;
-        W[k * ld + k] = beta;
-        for (int col = k + 1; col <= n; ++col) {
-            double dot = W[k * ld + col];
-            for (int i = k + 1; i < M; ++i) dot += W[i * ld + k] * W[i * ld + col];
-            dot *= tau;
-            W[k * ld + col] -= dot;
-            for (int i = k + 1; i < M; ++i) W[i * ld + col] -= dot * W[i * ld + k];
-        }
-    }
-    for (int k = n - 1; k >= 0; --k) {
-        double v = W[k * ld + n];
-        for (int j = k + 1; j < n; ++j) v -= W[k * ld + j] * y[j];
-        y[k] = v / W[k * ld + k];
-    }
-    for (int k = 0; k < n; ++k) if (!std::isfinite(y[k])) return false;
-    return true;
-}
-
-struct LMResult { Termination term; int iterations, num_cost_evals, num_jac_evals; double final_cost; };
-
-// TrustRegionMinimizer::Minimize of Ceres 1.14, one 6-vector parameter block (same control flow
-// as pnp_oracle.cpp's trust_region_lm, which documents each step against the Ceres functions).
-LMResult trust_region_lm(const Problem& P, double* x_io, const LMOptions& opt) {
-    const int m = 2 * P.pn;
-    std::vector<double> res(m), jac(static_cast<size_t>(m) * N), work;
-    double x[N], grad[N], scale[N], diag[N], lm_diag[N], step[N], delta[N], cand[N];
-    std::memcpy(x, x_io, sizeof(x));
-    LMResult out{FAILURE, 0, 0, 0, 0.0};
-    double x_cost, cand_cost, radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
-    bool reuse_diagonal = false;
-    int num_invalid = 0;
-    double minimum_cost = std::numeric_limits<double>::max();
-
-    bool ok = evaluate(P, x, &x_cost, res.data(), jac.data(), grad);
-    out.num_cost_evals++; out.num_jac_evals++;
-    if (!ok) { out.final_cost = x_cost; return out; }
-    {
-        double cn[N] = {0};
-        for (int i = 0; i < m; ++i) for (int k = 0; k < N; ++k) cn[k] += jac[i * N + k] * jac[i * N + k];
-        for (int k = 0; k < N; ++k) scale[k] = 1.0 / (1.0 + std::sqrt(cn[k]));
-    }
-    auto scale_columns = [&]() { for (int i = 0; i < m; ++i) for (int k = 0; k < N; ++k) jac[i * N + k] *= scale[k]; };
-    scale_columns();
-    auto max_norm = [](const double* g) { double v = 0; for (int k = 0; k < N; ++k) v = std::max(v, std::fabs(g[k])); return v; };
-    auto norm = [](const double* v) { double s = 0; for (int k = 0; k < N; ++k) s += v[k] * v[k]; return std::sqrt(s); };
-    double x_norm = norm(x), gradient_max_norm = max_norm(grad);
-
-    int iteration = 0;
-    bool step_is_successful = true;
-    out.term = NO_CONVERGENCE;
-    while (true) {
-        if (step_is_successful && x_cost < minimum_cost) { minimum_cost = x_cost; std::memcpy(x_io, x, sizeof(x)); }
-        out.iterations = iteration;
-        if (iteration >= opt.max_num_iterations) { out.term = NO_CONVERGENCE; break; }
-        if (step_is_successful && gradient_max_norm <= opt.gradient_tolerance) { out.term = CONVERGENCE; break; }
-        if (radius <= opt.min_trust_region_radius) { out.term = CONVERGENCE; break; }
-        ++iteration;
-        step_is_successful = false;
-
-        if (!reuse_diagonal) {
-            for (int k = 0; k < N; ++k) diag[k] = 0.0;
-            for (int i = 0; i < m; ++i) for (int k = 0; k < N; ++k) diag[k] += jac[i * N + k] * jac[i * N + k];
-            for (int k = 0; k < N; ++k) diag[k] = std::min(std::max(diag[k], opt.min_lm_diagonal), opt.max_lm_diagonal);
-        }
-        for (int k = 0; k < N; ++k) lm_diag[k] = std::sqrt(diag[k] / radius);
-        const bool solved = dense_qr_solve(jac.data(), res.data(), lm_diag, m, step, work);
-        reuse_diagonal = true;
-        bool step_is_valid = false;
-        double model_cost_change = 0.0;
-        if (solved) {
-            for (int k = 0; k < N; ++k) step[k] = -step[k];
-            double dot = 0.0;
-            for (int i = 0; i < m; ++i) {
-                double mr = 0.0;
-                for (int k = 0; k < N; ++k) mr += jac[i * N + k] * step[k];
-                dot += mr * (res[i] + mr / 2.0);
-            }
-            model_cost_change = -dot;
-            step_is_valid = model_cost_change > 0.0;
-        }
-        if (!step_is_valid) {
-            if (++num_invalid >= opt.max_num_consecutive_invalid_steps) { out.term = FAILURE; break; }
-            radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
-            continue;
-        }
-        num_invalid = 0;
-        for (int k = 0; k < N; ++k) delta[k] = step[k] * scale[k];
-        for (int k = 0; k < N; ++k) cand[k] = x[k] + delta[k];
-        if (!evaluate(P, cand, &cand_cost, nullptr, nullptr, nullptr)) cand_cost = std::numeric_limits<double>::max();
-        out.num_cost_evals++;
-        if (norm(delta) <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) { out.term = CONVERGENCE; break; }
-        const double cost_change = x_cost - cand_cost;
-        if (std::fabs(cost_change) <= opt.function_tolerance * x_cost) { out.term = CONVERGENCE; break; }
-        const double relative_decrease = cost_change / model_cost_change;
-        if (relative_decrease > opt.min_relative_decrease) {
-            std::memcpy(x, cand, sizeof(x));
-            x_norm = norm(x);
-            ok = evaluate(P, x, &x_cost, res.data(), jac.data(), grad);
-            out.num_jac_evals++;
-            if (!ok) { out.term = FAILURE; break; }
-            scale_columns();
-            gradient_max_norm = max_norm(grad);
-            step_is_successful = true;
-            radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3));
-            radius = std::min(opt.max_trust_region_radius, radius);
-            decrease_factor = 2.0;
-            reuse_diagonal = false;
-        } else {
-            radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
-        }
-    }
-    out.final_cost = minimum_cost;
-    return out;
-}
-
 // (J^T J)^-1 by Cholesky (ceres::Covariance on a full-rank problem); false if not positive definite.
 bool spd_inverse(const double* H, double* inv) {
     double L[N * N] = {0};
@@ -325,7 +179,10 @@ void solve_one(const double* pts2d, const double* pts3d, const double* wgt2d, co
     const Problem P = make_problem(pts2d, pts3d, wgt2d, K, pn, clips, full_w);
     std::memcpy(result_pose, init, N * sizeof(double));
     LMOptions opt;
-    const LMResult r = trust_region_lm(P, result_pose, opt);
+    auto eval = [&P](const double* x, double* cost, double* res, double* jac, double* grad) {
+        return evaluate(P, x, cost, res, jac, grad);
+    };
+    const LMResult r = trust_region_lm_n<N>(eval, 2 * pn, result_pose, opt);  // oracle/ceres_lm.h
     *result_val = (r.term == CONVERGENCE || r.term == NO_CONVERGENCE);
     if (stats) { stats[0] = r.iterations; stats[1] = r.num_cost_evals; stats[2] = r.num_jac_evals; stats[3] = r.term; }
     if (final_cost) *final_cost = r.final_cost;

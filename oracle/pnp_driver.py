@@ -53,7 +53,8 @@ _lib = None
 def build(force=False):
     """Compile the oracle with its Makefile (g++ -O2 -fopenmp, the reference's own flags)."""
     src = os.path.join(_HERE, 'pnp_oracle.cpp')
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, 'ceres_lm.h'))):
         subprocess.check_call(['make', '-C', _HERE, '-s'] + (['-B'] if force else []))
     return _LIB_PATH
 
