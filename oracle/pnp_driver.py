@@ -41,6 +41,7 @@ void pnp_approx_hessian(const double* pts2d, const double* pts3d, const double* 
 int pnp_spd_inverse4(const double* H, double* inv);
 int ceres_kat_hello_world(double* trace, int max_rows, double* x_final, double* summary);
 int ceres_kat_powell(double* trace, int max_rows, double* x_final, double* summary);
+void ceres_lm_expfit(const double* t, const double* y, int m, double* x, double* summary);
 void pnp_oracle_set_adopt_candidate_on_ftol(int v);
 int pnp_oracle_num_threads(void);
 """
@@ -141,6 +142,15 @@ def ceres_tutorial_trace(problem):
     trace, x, summary = np.zeros((64, 7)), np.zeros(n), np.zeros(3)
     k = fn(_dp(trace), 64, _dp(x), _dp(summary))
     return trace[:k], x, summary
+
+
+def expfit(t, y, x0):
+    """The oracle's minimiser on r_i = x0 exp(x1 t_i) + x2 + x3 t_i - y_i.  Returns (x[4], (termination, iterations,
+    cost evaluations, final cost))."""
+    t, y, x = _c64(t), _c64(y), _c64(x0).copy()
+    summary = np.zeros(4)
+    lib().ceres_lm_expfit(_dp(t), _dp(y), t.shape[0], _dp(x), _dp(summary))
+    return x, summary
 
 
 def eval_cost_grad_hess(coord_2d, coord_3d, wgt, cam_mat, pose, clips, full_w=False):

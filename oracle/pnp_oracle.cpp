@@ -370,6 +370,30 @@ int ceres_kat_powell(double* trace, int max_rows, double* x_final, double* summa
     return n;
 }
 
+// A third, randomisable test problem for cross-checks between minimisers (tests/test_oracle.py): the 4-parameter
+// curve fit  r_i = x0 exp(x1 t_i) + x2 + x3 t_i - y_i.  x: start in, result out; summary: termination, iterations,
+// cost evaluations, final cost.
+void ceres_lm_expfit(const double* t, const double* y, int m, double* x, double* summary) {
+    auto eval = [t, y, m](const double* x, double* cost, double* res, double* jac, double* grad) {
+        double acc = 0.0, g[4] = {0, 0, 0, 0};
+        bool ok = true;
+        for (int i = 0; i < m; ++i) {
+            const double e = std::exp(x[1] * t[i]), r = x[0] * e + x[2] + x[3] * t[i] - y[i];
+            acc += r * r;
+            if (res) res[i] = r;
+            if (jac) {
+                const double J[4] = {e, x[0] * t[i] * e, 1.0, t[i]};
+                for (int k = 0; k < 4; ++k) { jac[i * 4 + k] = J[k]; g[k] += J[k] * r; ok = ok && std::isfinite(J[k]); }
+            }
+        }
+        *cost = 0.5 * acc;
+        if (grad) std::memcpy(grad, g, sizeof(g));
+        return ok && std::isfinite(acc);
+    };
+    const LMResult r = trust_region_lm_n<4>(eval, m, x, LMOptions());
+    summary[0] = r.term; summary[1] = r.iterations; summary[2] = r.num_cost_evals; summary[3] = r.final_cost;
+}
+
 void pnp_oracle_set_adopt_candidate_on_ftol(int v) { g_options.adopt_candidate_on_ftol = v; }
 int pnp_oracle_num_threads(void) {
 #ifdef _OPENMP

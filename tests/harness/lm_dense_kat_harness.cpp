@@ -75,3 +75,33 @@ extern "C" int lm_dense_kat_powell(double* rows, int max_rows, double* x_final, 
     const double x0[4] = {3.0, -1.0, 0.0, 1.0};
     return run<4>(p, x0, rows, max_rows, x_final, summary);
 }
+
+namespace {
+
+struct ExpFit {
+    const double *t, *y;
+    int m, cost_evals;
+    void operator()(const double* x, bool jac, double* acc) {
+        ++cost_evals;
+        for (int i = 0; i < m; ++i) {
+            const double e = std::exp(x[1] * t[i]), r = x[0] * e + x[2] + x[3] * t[i] - y[i];
+            acc[0] += 0.5 * r * r;
+            if (!jac) continue;
+            const double J[4] = {e, x[0] * t[i] * e, 1.0, t[i]};
+            for (int p = 0; p < 4; ++p) {
+                acc[mrlm::Layout<4>::kAccG + p] += J[p] * r;
+                for (int q = p; q < 4; ++q) acc[mrlm::Layout<4>::kAccH + mrlm::tri<4>(p, q)] += J[p] * J[q];
+            }
+        }
+    }
+};
+
+}  // namespace
+
+// The kernels' controller on r_i = x0 exp(x1 t_i) + x2 + x3 t_i - y_i.  summary: termination, iterations,
+// cost evaluations (as Ceres counts them), final cost.
+extern "C" void lm_dense_expfit(const double* t, const double* y, int m, double* x, double* summary) {
+    ExpFit p{t, y, m, 0};
+    const mrlm::LMResult r = mrlm::minimize<4>(p, x, mrlm::default_options());
+    summary[0] = r.term; summary[1] = r.iterations; summary[2] = r.cost_evals; summary[3] = r.final_cost;
+}
