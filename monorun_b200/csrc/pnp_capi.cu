@@ -13,16 +13,7 @@
 #include "pnp_noc.cuh"
 #include "pnp_exact_hessian.cuh"
 #include "pnp_6dof.cuh"
-#ifdef MRPNP_WITH_POOL  // pooled staging buffers + small slots: measured slower, kept for reference
-#include "pnp_kernel_pool.cuh"
-#endif
-#ifdef MRPNP_WITH_PAIR_FAST  // two warps per object: measured slower, kept for reference
-#include "pnp_kernel_fast2.cuh"
-#endif
 #include <stdlib.h>
-#ifdef MRPNP_WITH_PAIR_KERNEL  // experiment kept for reference, see DESIGN.md section 5
-#include "pnp_kernel_pair.cuh"
-#endif
 
 namespace {
 
@@ -67,104 +58,20 @@ namespace {
 using mrpnp::KParams;
 
 struct LaunchPlan {
-    int warps, groups, ctas, smem, use_tma, slot_floats, team;
-    int pool_stage;  // > 0: pooled kernel with this many staging buffers per CTA
+    int warps, groups, ctas, smem, use_tma, slot_floats;
 };
-
-#ifdef MRPNP_WITH_POOL
-// experiment build only: MRPNP_POOL=1 in the environment selects the pooled kernel
-bool pool_enabled() {
-    static const bool on = [] {
-        const char* e = getenv("MRPNP_POOL");
-        return e && atoi(e) == 1;
-    }();
-    return on;
-}
-#endif
-
-// warps per object of the MRPNP_PREC_FAST kernel: 1, or (experiment build only) MRPNP_TEAM=2 from the environment
-int team_size() {
-#ifdef MRPNP_WITH_PAIR_FAST
-    static const int team = [] {
-        const char* e = getenv("MRPNP_TEAM");
-        return (e && atoi(e) == 2) ? 2 : 1;
-    }();
-    return team;
-#else
-    return 1;
-#endif
-}
 
 int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, int precision, const void* c3d, const void* c2d,
                 const void* wgt, LaunchPlan* plan) {
-    if (precision == MRPNP_PREC_FAST) {
-        const int wc = p->weight_mode == MRPNP_W_FULL ? 3 : 2;
-        size_t slot_bytes = ((size_t)(5 + wc) * p->n_pts * sizeof(float) + 15) & ~size_t(15);
-        const int team = team_size();
-        const size_t header = team == 2 ? 512 : mrpnp::kFastHeaderBytes;
-        int groups = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, (size_t)ctx->max_smem_optin / (slot_bytes + header));
-        if (groups < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
-        const int per_sm = (p->n_obj + ctx->num_sms - 1) / ctx->num_sms;
-        groups = std::max(1, std::min(groups, per_sm));
-        plan->team = team;
-        plan->pool_stage = 0;
-#ifdef MRPNP_WITH_POOL
-        if (team == 1 && pool_enabled() && p->n_pts > mrpnp::kPoolCap) {
-            // pooled shared memory: NS slab-sized staging buffers + NSM small slots, NS + NSM warps
-            const size_t small_bytes = (size_t)(5 + wc) * mrpnp::kPoolCap * sizeof(float);
-            int ns = wc == 3 ? 3 : 4;
-            if (const char* e = getenv("MRPNP_POOL_NS")) ns = std::max(1, std::min(atoi(e), mrpnp::kPoolMaxStage));
-            const size_t fixed = mrpnp::kPoolCtaHeaderBytes + (size_t)ns * (slot_bytes + mrpnp::kFastHeaderBytes);
-            if ((size_t)ctx->max_smem_optin > fixed) {
-                int nsm = (int)(((size_t)ctx->max_smem_optin - fixed) / (small_bytes + mrpnp::kFastHeaderBytes));
-                nsm = std::min(nsm, mrpnp::kPoolMaxWarps - ns);
-                if (nsm >= 1 && ns + nsm > groups && per_sm >= ns + nsm) {
-                    plan->pool_stage = ns;
-                    plan->warps = ns + nsm;
-                    plan->groups = ns + nsm;
-                    plan->ctas = std::min(ctx->num_sms, (p->n_obj + plan->warps - 1) / plan->warps);
-                    plan->smem = (int)(fixed + (size_t)nsm * (small_bytes + mrpnp::kFastHeaderBytes));
-                    plan->slot_floats = (int)(slot_bytes / sizeof(float));
-                    const bool aligned = (p->n_pts % 4 == 0) && (((uintptr_t)c3d | (uintptr_t)c2d | (uintptr_t)wgt) % 16 == 0);
-                    plan->use_tma = aligned ? 1 : 0;
-                    return MRPNP_OK;
-                }
-            }
-        }
-#endif
-        plan->warps = groups * plan->team;
-        plan->groups = groups;
-        plan->ctas = std::min(ctx->num_sms, (p->n_obj + groups - 1) / groups);
-        plan->smem = (int)(groups * (slot_bytes + header));
-        plan->slot_floats = (int)(slot_bytes / sizeof(float));
-        const bool aligned = (p->n_pts % 4 == 0) && (((uintptr_t)c3d | (uintptr_t)c2d | (uintptr_t)wgt) % 16 == 0);
-        plan->use_tma = aligned ? 1 : 0;
-        return MRPNP_OK;
-    }
-    plan->team = 1;
-    plan->pool_stage = 0;
     const int wc = p->weight_mode == MRPNP_W_FULL ? 3 : 2;
-    const size_t slot_floats = (size_t)(5 + wc) * p->n_pts;
-    size_t slot_bytes = slot_floats * sizeof(float);
-    slot_bytes = (slot_bytes + 15) & ~size_t(15);
-#ifdef MRPNP_WITH_PAIR_KERNEL
-    const bool pair = p->precision == MRPNP_PREC_MIXED;
-#else
-    const bool pair = false;  // the two-warps-per-object kernel (pnp_kernel_pair.cuh) measured no faster: off by default
-#endif
-#ifdef MRPNP_WITH_PAIR_KERNEL
-    const size_t header = pair ? mrpnp::kPairHeaderBytes : mrpnp::kWarpHeaderBytes;
-    const int max_groups = pair ? mrpnp::kMaxPairsPerCta : mrpnp::kMaxWarpsPerCta;
-#else
-    const size_t header = mrpnp::kWarpHeaderBytes;
-    const int max_groups = mrpnp::kMaxWarpsPerCta;
-#endif
-    int groups = (int)std::min<size_t>(max_groups, (size_t)ctx->max_smem_optin / (slot_bytes + header));
+    const size_t slot_bytes = ((size_t)(5 + wc) * p->n_pts * sizeof(float) + 15) & ~size_t(15);
+    const size_t header = precision == MRPNP_PREC_FAST ? mrpnp::kFastHeaderBytes : mrpnp::kWarpHeaderBytes;
+    int groups = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, (size_t)ctx->max_smem_optin / (slot_bytes + header));
     if (groups < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
     // keep every SM busy before stacking objects on one SM: at small N spread objects over CTAs
     const int per_sm = (p->n_obj + ctx->num_sms - 1) / ctx->num_sms;
     groups = std::max(1, std::min(groups, per_sm));
-    plan->warps = groups * (pair ? 2 : 1);
+    plan->warps = groups;
     plan->groups = groups;
     plan->ctas = std::min(ctx->num_sms, (p->n_obj + groups - 1) / groups);
     plan->smem = (int)(groups * (slot_bytes + header));
@@ -200,22 +107,11 @@ cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan,
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
     } else if (precision == MRPNP_PREC_FAST) {
         void (*k)(const KParams) = kp.n_pts == 784 ? mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 0>;
-#ifdef MRPNP_WITH_POOL
-        if (plan.pool_stage > 0)
-            k = kp.n_pts == 784 ? mrpnp::pnp_lm_pool_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_pool_kernel<WMODE, LAYOUT, 0>;
-#endif
-#ifdef MRPNP_WITH_PAIR_FAST
-        if (plan.team == 2) k = kp.n_pts == 784 ? mrpnp::pnp_lm_fast2_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_fast2_kernel<WMODE, LAYOUT, 0>;
-#endif
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
     } else {
-#ifdef MRPNP_WITH_PAIR_KERNEL
-        auto k = mrpnp::pnp_lm_pair_kernel<WMODE, LAYOUT>;
-#else
         auto k = mrpnp::pnp_lm_kernel<true, WMODE, LAYOUT>;
-#endif
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
@@ -261,7 +157,6 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     KParams kp;
     kp.c3d = c3d; kp.c2d = c2d; kp.wgt = wgt; kp.cam = cam; kp.range = range; kp.init = init;
     kp.inl_in = inl_in; kp.result = result; kp.inl_out = inl_out; kp.result64 = result64;
-    kp.pool_stage = plan.pool_stage;
     kp.n_peers = p->n_peers; kp.row_offset = p->row_offset;
     for (int r = 0; r < MRPNP_MAX_PEERS; ++r) kp.peer[r] = r < p->n_peers ? p->peer_results[r] : nullptr;
     const int set = ctx->next_counter;

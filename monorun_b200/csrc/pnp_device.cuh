@@ -70,7 +70,6 @@ struct KParams {
     float* peer[MRPNP_MAX_PEERS];
     int n_peers;
     long long row_offset;
-    int pool_stage;           // pooled kernel (pnp_kernel_pool.cuh): staging buffers per CTA; the other warps' worth are small slots
 };
 
 // The 96-byte result row of one object: lanes 0..23 hold its floats.
