@@ -49,9 +49,12 @@ extern "C" {
 #define MRPNP_PREC_FP64 0  /* residual, Jacobian and normal equations in fp64: reproduces the fp64 reference decisions */
 #define MRPNP_PREC_MIXED 1 /* fp64 residual/cost chain + fp32 Jacobian sums in every pass, fp64 4x4 solve              */
 #define MRPNP_PREC_FAST 2  /* residuals evaluated once in fp64, then tracked incrementally: candidate evaluations are   */
-                           /* pure fp32 "delta" passes whose cost CHANGE is accurate to ~1e-6 of itself; objects with a */
-                           /* point near a clip bound are re-solved by the MIXED kernel in a follow-up launch on the    */
-                           /* same stream.  Needs inlier_opt_only = 1 (otherwise the solve runs as MIXED).  Default.    */
+                           /* packed-fp32 "delta" passes whose cost CHANGE is accurate to ~1e-6 of itself.  Objects the */
+                           /* fp32 path must not decide (a point near a clip bound, an accept / function-tolerance      */
+                           /* decision within the rounding band of its threshold -- a handful per 8192) are solved by   */
+                           /* the exact fp64 routine inside the same launch, so the results follow the fp64 reference   */
+                           /* decision for decision.  Needs inlier_opt_only = 1 and an even n_pts (otherwise the solve  */
+                           /* runs as MIXED).  Default.                                                                  */
 
 /* pose covariance written to the result row */
 #define MRPNP_COV_NONE 0
@@ -96,6 +99,12 @@ typedef struct mrpnp_params {
     int32_t reserved2;
     int64_t row_offset;
     float* peer_results[MRPNP_MAX_PEERS];
+    /* MRPNP_PREC_FAST: half-widths of the bands around Ceres' decision thresholds (|cost change| = 1e-6 cost,
+     * rho = 1e-3) inside which a decision is left to the exact fp64 routine.  band_first: error of the FIRST step's cost
+     * change relative to the cost (two independently rounded fp32 sums); later steps: band_rel |change| +
+     * band_mix sqrt(model change * cost).  mrpnp_default_params sets 8e-6, 4e-3, 2e-6; 0 disables a term. */
+    float band_first, band_rel, band_mix;
+    float reserved3;
 } mrpnp_params;
 
 typedef struct mrpnp_ctx mrpnp_ctx;
@@ -261,6 +270,10 @@ int mrpnp_solve_6dof(mrpnp_ctx* ctx, const mrpnp_params* p,
 
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);
+
+/* MRPNP_PREC_FAST: number of objects the fp32 path handed to the exact fp64 routine (a point near a clip bound, a
+ * decision inside its rounding band) since the context was created.  Synchronises the device. */
+int64_t mrpnp_handed_back_count(mrpnp_ctx* ctx);
 
 /* Static facts about the solver kernel for the given problem: writes warps per CTA, CTAs, dynamic
  * shared memory bytes and whether the TMA path is taken into info[0..3]. */

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <new>
 
 #include "monorun_pnp.h"
@@ -32,7 +33,7 @@ int fail(int code, const char* fmt, const char* detail = "") {
 
 constexpr int kHostStreams = 2;
 constexpr int kCounterSets = 8;
-constexpr int kCounterInts = 4;  // per set: next work item, finished CTAs, redo-list length, pad
+constexpr int kCounterInts = 8;  // per set: the five counters of pnp_kernel_fast.cuh (the exact kernels use the first two)
 
 }  // namespace
 
@@ -40,10 +41,17 @@ struct mrpnp_ctx {
     int device = 0;
     int num_sms = 0;
     int max_smem_optin = 0;
-    int* counters = nullptr;  // kCounterSets x kCounterInts ints, all zero between launches
-    int* redo_lists = nullptr;  // kCounterSets x redo_cap object indices (MRPNP_PREC_FAST hand-over to the exact kernel)
+    // Work-counter sets (and hand-back lists) rotate between launches so that solves on different streams can overlap;
+    // a set is re-used only after the launch that used it last has finished: the next user's stream waits on that
+    // launch's event (no host block).  `mu` serialises the context's bookkeeping between host threads.
+    std::mutex mu;
+    int* counters = nullptr;    // kCounterSets x kCounterInts ints, all zero between launches
+    unsigned long long* stats = nullptr;   // device: [0] objects handed back to the exact routine since creation
+    int* redo_lists = nullptr;  // kCounterSets x redo_cap entries (MRPNP_PREC_FAST hand-back lists, all zero between launches)
     int redo_cap = 0;
     int next_counter = 0;
+    cudaEvent_t set_done[kCounterSets] = {};
+    bool set_used[kCounterSets] = {};
     int64_t launches = 0;
     // host-path staging
     cudaStream_t streams[kHostStreams] = {nullptr, nullptr};
@@ -77,8 +85,16 @@ int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, int precision, cons
     plan->smem = (int)(groups * (slot_bytes + header));
     plan->slot_floats = (int)(slot_bytes / sizeof(float));
     const bool aligned = (p->n_pts % 4 == 0) && (((uintptr_t)c3d | (uintptr_t)c2d | (uintptr_t)wgt) % 16 == 0);
-    plan->use_tma = aligned ? 1 : 0;
+    // the fast kernel keeps a planar slot: [N,P,C] tensors are transposed by plain loads instead of bulk copies
+    plan->use_tma = (aligned && !(precision == MRPNP_PREC_FAST && p->layout == MRPNP_LAYOUT_INTERLEAVED)) ? 1 : 0;
     return MRPNP_OK;
+}
+
+// MRPNP_PREC_FAST needs compacted inliers (the observations are overwritten by tracked residuals) and an even number
+// of points per object (two points per 64-bit shared-memory access); other problems run as MRPNP_PREC_MIXED.
+int effective_precision(const mrpnp_params* p) {
+    if (p->precision == MRPNP_PREC_FAST && (!p->inlier_opt_only || (p->n_pts & 1))) return MRPNP_PREC_MIXED;
+    return p->precision;
 }
 
 int check_params(const mrpnp_params* p) {
@@ -98,15 +114,10 @@ int check_params(const mrpnp_params* p) {
 }
 
 template <int WMODE, int LAYOUT>
-cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan, cudaStream_t stream) {
+cudaError_t launch_exact(int precision, const KParams& kp, const LaunchPlan& plan, cudaStream_t stream) {
     cudaError_t e;
     if (precision == MRPNP_PREC_FP64) {
         auto k = mrpnp::pnp_lm_kernel<false, WMODE, LAYOUT>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
-        if (e != cudaSuccess) return e;
-        k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
-    } else if (precision == MRPNP_PREC_FAST) {
-        void (*k)(const KParams) = kp.n_pts == 784 ? mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 784> : mrpnp::pnp_lm_fast_kernel<WMODE, LAYOUT, 0>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
         if (e != cudaSuccess) return e;
         k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
@@ -119,9 +130,23 @@ cudaError_t launch_one(int precision, const KParams& kp, const LaunchPlan& plan,
     return cudaGetLastError();
 }
 
+template <int WMODE>
+cudaError_t launch_fast(const KParams& kp, const LaunchPlan& plan, cudaStream_t stream) {
+    void (*k)(const KParams) = kp.n_pts == 784 ? mrpnp::pnp_lm_fast_kernel<WMODE, 784> : mrpnp::pnp_lm_fast_kernel<WMODE, 0>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
+    if (e != cudaSuccess) return e;
+    k<<<plan.ctas, plan.warps * 32, plan.smem, stream>>>(kp);
+    return cudaGetLastError();
+}
+
 cudaError_t dispatch(const mrpnp_params* p, int precision, const KParams& kp, const LaunchPlan& plan, cudaStream_t stream) {
+    if (precision == MRPNP_PREC_FAST) {
+        if (p->weight_mode == MRPNP_W_LOGSTD) return launch_fast<MRPNP_W_LOGSTD>(kp, plan, stream);
+        if (p->weight_mode == MRPNP_W_ISTD) return launch_fast<MRPNP_W_ISTD>(kp, plan, stream);
+        return launch_fast<MRPNP_W_FULL>(kp, plan, stream);
+    }
 #define MR_CASE(W, L) \
-    if (p->weight_mode == W && p->layout == L) return launch_one<W, L>(precision, kp, plan, stream);
+    if (p->weight_mode == W && p->layout == L) return launch_exact<W, L>(precision, kp, plan, stream);
     MR_CASE(MRPNP_W_LOGSTD, MRPNP_LAYOUT_PLANAR)
     MR_CASE(MRPNP_W_ISTD, MRPNP_LAYOUT_PLANAR)
     MR_CASE(MRPNP_W_FULL, MRPNP_LAYOUT_PLANAR)
@@ -149,8 +174,7 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     for (int r = 0; r < p->n_peers; ++r)
         if (!p->peer_results[r]) return fail(MRPNP_ERR_ARG, "NULL peer result buffer%s");
     if (p->init_mode == MRPNP_INIT_GIVEN && !init) return fail(MRPNP_ERR_ARG, "init_pose is NULL with MRPNP_INIT_GIVEN%s");
-    // MRPNP_PREC_FAST needs compacted inliers (the observations are overwritten by tracked residuals)
-    const int precision = (p->precision == MRPNP_PREC_FAST && !p->inlier_opt_only) ? MRPNP_PREC_MIXED : p->precision;
+    const int precision = effective_precision(p);
     LaunchPlan plan;
     int rc = plan_launch(ctx, p, precision, c3d, dense ? c3d : c2d, wgt, &plan);
     if (rc != MRPNP_OK) return rc;
@@ -159,22 +183,34 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     kp.inl_in = inl_in; kp.result = result; kp.inl_out = inl_out; kp.result64 = result64;
     kp.n_peers = p->n_peers; kp.row_offset = p->row_offset;
     for (int r = 0; r < MRPNP_MAX_PEERS; ++r) kp.peer[r] = r < p->n_peers ? p->peer_results[r] : nullptr;
-    const int set = ctx->next_counter;
-    kp.counters = ctx->counters + kCounterInts * set;
-    ctx->next_counter = (ctx->next_counter + 1) % kCounterSets;
-    kp.redo_list = nullptr; kp.redo_count = nullptr; kp.work_list = nullptr; kp.work_count = nullptr;
-    if (precision == MRPNP_PREC_FAST) {
-        if (p->n_obj > ctx->redo_cap) {  // grow the hand-over lists (cudaFree waits for launches still using them)
-            if (ctx->redo_lists) MR_CUDA(cudaFree(ctx->redo_lists));
-            ctx->redo_lists = nullptr;
-            ctx->redo_cap = 0;
-            const int cap = std::max(p->n_obj, 1024);
-            MR_CUDA(cudaMalloc(&ctx->redo_lists, sizeof(int) * (size_t)cap * kCounterSets));
-            ctx->redo_cap = cap;
-        }
-        kp.redo_list = ctx->redo_lists + (size_t)ctx->redo_cap * set;
-        kp.redo_count = kp.counters + 2;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (precision == MRPNP_PREC_FAST && p->n_obj > ctx->redo_cap) {
+        // grow the hand-back lists (cudaFree waits for the launches still using them)
+        if (ctx->redo_lists) MR_CUDA(cudaFree(ctx->redo_lists));
+        ctx->redo_lists = nullptr;
+        ctx->redo_cap = 0;
+        const int cap = std::max(p->n_obj, 1024);
+        MR_CUDA(cudaMalloc(&ctx->redo_lists, sizeof(int) * (size_t)cap * kCounterSets));
+        MR_CUDA(cudaMemset(ctx->redo_lists, 0, sizeof(int) * (size_t)cap * kCounterSets));
+        ctx->redo_cap = cap;
     }
+    // take the next counter set; if the launch that used it last may still be running, this stream waits for it
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &capturing);
+    int set = kCounterSets - 1;   // launches captured into a CUDA graph share the last set (replays are stream-ordered)
+    if (capturing == cudaStreamCaptureStatusNone) {
+        set = ctx->next_counter;
+        ctx->next_counter = (ctx->next_counter + 1) % (kCounterSets - 1);
+        if (ctx->set_used[set] && cudaEventQuery(ctx->set_done[set]) != cudaSuccess)
+            MR_CUDA(cudaStreamWaitEvent(stream, ctx->set_done[set], 0));
+        (void)cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
+    }
+    kp.counters = ctx->counters + kCounterInts * set;
+    kp.redo_list = precision == MRPNP_PREC_FAST ? ctx->redo_lists + (size_t)ctx->redo_cap * set : nullptr;
+    kp.work_list = nullptr; kp.work_count = nullptr;
+    kp.stats = ctx->stats;
+    kp.band_first = p->band_first; kp.band_rel = p->band_rel; kp.band_mix = p->band_mix;
+    kp.global_interleaved = (precision == MRPNP_PREC_FAST && p->layout == MRPNP_LAYOUT_INTERLEAVED) ? 1 : 0;
     kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride;
     kp.cov_mode = p->cov_mode; kp.init_mode = p->init_mode; kp.inlier_opt_only = p->inlier_opt_only;
     kp.max_iter = p->max_iterations; kp.adopt_ftol = p->adopt_candidate_on_ftol;
@@ -204,23 +240,9 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     cudaError_t e = dispatch(p, precision, kp, plan, stream);
     if (e != cudaSuccess) return fail(MRPNP_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
     ctx->launches += 1;
-    if (precision == MRPNP_PREC_FAST) {
-        // follow-up launch of the exact kernel over the redo list (normally empty: its CTAs read the count and exit)
-        KParams kr = kp;
-        kr.work_list = kp.redo_list;
-        kr.work_count = kp.redo_count;
-        kr.redo_list = nullptr; kr.redo_count = nullptr;
-        kr.counters = ctx->counters + kCounterInts * ctx->next_counter;
-        ctx->next_counter = (ctx->next_counter + 1) % kCounterSets;
-        LaunchPlan pr;
-        rc = plan_launch(ctx, p, MRPNP_PREC_MIXED, c3d, dense ? c3d : c2d, wgt, &pr);
-        if (rc != MRPNP_OK) return rc;
-        pr.ctas = std::min(pr.ctas, 32);
-        kr.use_tma = pr.use_tma;
-        kr.slot_floats = pr.slot_floats;
-        e = dispatch(p, MRPNP_PREC_MIXED, kr, pr, stream);
-        if (e != cudaSuccess) return fail(MRPNP_ERR_CUDA, "follow-up kernel launch: %s", cudaGetErrorString(e));
-        ctx->launches += 1;
+    if (capturing == cudaStreamCaptureStatusNone) {
+        MR_CUDA(cudaEventRecord(ctx->set_done[set], stream));
+        ctx->set_used[set] = true;
     }
     return MRPNP_OK;
 }
@@ -249,6 +271,9 @@ void mrpnp_default_params(mrpnp_params* p, int32_t n_obj, int32_t n_pts) {
     p->z_min = 0.5f;             // configs/kitti_multiclass.py:125
     p->std_scale = 10.f;         // uncert_prop_pnp_optimizer.py:28
     p->istd_thres = 0.6f;        // configs/kitti_multiclass.py:126
+    p->band_first = 8e-6f;
+    p->band_rel = 4e-3f;
+    p->band_mix = 2e-6f;
 }
 
 int mrpnp_create(mrpnp_ctx** out, int device) {
@@ -268,6 +293,9 @@ int mrpnp_create(mrpnp_ctx** out, int device) {
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     MR_CUDA(cudaMalloc(&c->counters, sizeof(int) * kCounterInts * kCounterSets));
     MR_CUDA(cudaMemset(c->counters, 0, sizeof(int) * kCounterInts * kCounterSets));
+    MR_CUDA(cudaMalloc(&c->stats, sizeof(unsigned long long) * 4));
+    MR_CUDA(cudaMemset(c->stats, 0, sizeof(unsigned long long) * 4));
+    for (int i = 0; i < kCounterSets; ++i) MR_CUDA(cudaEventCreateWithFlags(&c->set_done[i], cudaEventDisableTiming));
     *out = c;
     return MRPNP_OK;
 }
@@ -279,13 +307,24 @@ void mrpnp_destroy(mrpnp_ctx* c) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
         if (c->chunk_buf[i]) cudaFree(c->chunk_buf[i]);
     }
+    for (int i = 0; i < kCounterSets; ++i)
+        if (c->set_done[i]) cudaEventDestroy(c->set_done[i]);
     if (c->small_buf) cudaFree(c->small_buf);
     if (c->counters) cudaFree(c->counters);
+    if (c->stats) cudaFree(c->stats);
     if (c->redo_lists) cudaFree(c->redo_lists);
     delete c;
 }
 
 int64_t mrpnp_launch_count(const mrpnp_ctx* c) { return c ? c->launches : 0; }
+
+int64_t mrpnp_handed_back_count(mrpnp_ctx* c) {
+    if (!c || !c->stats) return 0;
+    unsigned long long v = 0;
+    cudaSetDevice(c->device);
+    if (cudaMemcpy(&v, c->stats, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;   // synchronises the device
+    return (int64_t)v;
+}
 
 int mrpnp_pose_features(mrpnp_ctx* ctx, const float* rows, const float* dims, const float* cov_calib_logscale,
                         float cov_correction_sd, int32_t distance_z_depth, int32_t use_calib,
@@ -461,7 +500,7 @@ int mrpnp_kernel_info(mrpnp_ctx* ctx, const mrpnp_params* p, int32_t info[4]) {
     int rc = check_params(p);
     if (rc != MRPNP_OK) return rc;
     LaunchPlan plan;
-    const int precision = (p->precision == MRPNP_PREC_FAST && !p->inlier_opt_only) ? MRPNP_PREC_MIXED : p->precision;
+    const int precision = effective_precision(p);
     rc = plan_launch(ctx, p, precision, nullptr, nullptr, nullptr, &plan);
     if (rc != MRPNP_OK) return rc;
     info[0] = plan.warps; info[1] = plan.ctas; info[2] = plan.smem; info[3] = plan.use_tma;

@@ -43,7 +43,7 @@ struct KParams {
     float* result;
     uint32_t* inl_out;        // packed, same layout
     double* result64;
-    int* counters;            // [0] next object, [1] finished CTAs (self-resetting)
+    int* counters;            // work counters of one launch (self-resetting; see pnp_kernel_fast.cuh for the fast kernel's five)
     int n_obj, n_pts, cam_stride, range_stride;
     int cov_mode, init_mode, inlier_opt_only, max_iter, adopt_ftol;
     int use_tma, slot_floats;
@@ -58,10 +58,14 @@ struct KParams {
     long long pred_stride;    // floats between consecutive objects of all_pred, 0 = pre-sliced maps
     float proj_gain2;       // (ref_focal_y * epistemic_std_gain / scaling_denominator)^2
     float inv_scaling_denominator, distance_min;
-    // MRPNP_PREC_FAST: objects the fast kernel cannot finish (a point near a clip bound) are appended here ...
+    // MRPNP_PREC_FAST: objects the fp32 path must not decide (a point near a clip bound, a decision within the rounding
+    // band of its threshold) are handed back through this list (entries object + 1, 0 = empty) and solved by the exact
+    // fp64 routine inside the same launch
     int* redo_list;
-    int* redo_count;
-    // ... and the follow-up launch of the exact kernel reads them back as its work list (NULL = objects 0..n_obj-1)
+    unsigned long long* stats;   // [0] running total of handed-back objects (mrpnp_handed_back_count)
+    float band_first, band_rel, band_mix;   // half-widths of the decision bands (mrpnp_params)
+    int global_interleaved;   // the tensors in global memory are [N,P,C] although the slot is planar (staging transposes)
+    // exact kernels: optional work list (NULL = objects 0..n_obj-1)
     const int* work_list;
     int* work_count;
     int prefetch_distance;    // objects between the one a team starts and the one it prefetches into L2

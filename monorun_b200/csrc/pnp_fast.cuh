@@ -1,71 +1,101 @@
-// pnp_fast.cuh -- MRPNP_PREC_FAST passes: candidate evaluations of the LM loop in fp32 with incrementally tracked
-// residuals (device functions of pnp_kernel_fast.cuh).
+// pnp_fast.cuh -- MRPNP_PREC_FAST passes (device functions of pnp_kernel_fast.cuh): the evaluations of the LM loop on
+// incrementally TRACKED residuals, two points per lane in packed fp32 (sm_100 FFMA2 / FADD2 / FMUL2).
 //
-// Why: Ceres' accept / function-tolerance tests (TrustRegionMinimizer, defaults of pnp_uncert_cpu.cpp:270-271) read
-// cost(x) - cost(x + delta) and stop at |change| <= 1e-6 cost, so that difference has to be right to ~1e-4 of ITSELF.
-// Recomputing residuals in fp32 at every point cannot deliver that (1e-4 px rounding on ~1 px residuals), which is why
-// MRPNP_PREC_MIXED keeps the whole residual chain in fp64.  Here the residuals are evaluated ONCE per object in fp64
-// (at the point reached by the first step, eval_pass_first) and kept in shared memory in place of the observations;
-// every later evaluation computes only the CHANGE of each residual between the accepted point x and the candidate x + delta, from
-// formulas in which every operand is small when the step is small:
+// Why tracked residuals: Ceres' accept / function-tolerance tests (TrustRegionMinimizer, defaults of
+// pnp_uncert_cpu.cpp:270-271) read cost(x) - cost(x + delta) and stop at |change| <= 1e-6 cost, so that difference has
+// to be right to ~1e-4 of ITSELF.  Recomputing residuals in fp32 at every point cannot deliver that (1e-4 px rounding on
+// ~1 px residuals).  Here the residuals are evaluated ONCE per object in fp64 (at the point reached by the first step,
+// the "anchor") and kept in shared memory in place of the observations; every later evaluation computes only the CHANGE
+// of each residual between the accepted point x and the candidate x + delta, from formulas in which every operand is
+// small when the step is small:
 //
 //     q'  = R_y(yaw') X,  x' = q' + t'                      (candidate camera-frame point, plain fp32)
 //     Dq  = q' - R_y(-dyaw) q' = (-(cos dyaw - 1) q'_x + sin dyaw q'_z , -sin dyaw q'_x - (cos dyaw - 1) q'_z)
 //     Dx  = Dq_x + dt_x,  Dz = Dq_z + dt_z,  Dy = dt_y      (motion of the point, exact to fp32 RELATIVE precision)
 //     D(x/z) = (Dx - (x'/z') Dz) / z_old,  z_old = z' - Dz  (change of the normalised projection, same for y)
-//     dr  = w f D(x/z),   r' = r + dr,   cost' - cost = 1/2 sum dr (r + r')
 //
-// so cost differences carry a relative error of ~1e-6 however small the step, and the stored residuals pick up one
-// fp32 rounding (~6e-8 of |r|) per accepted step.  No fp64 instruction and no conversion is left in the pass; the
-// Jacobian, J^T r and J^T J at the candidate come out of the same quantities.  The stored residuals are updated
-// speculatively in place (most steps are accepted); a rejected step is rolled back by undo_pass_delta.
+// Formulation (round 2).  The tracked quantity is the NORMALISED reprojection difference e = (x'/z' - un, y'/z' - vn),
+// un = (u - cx) / fx, and each point carries M = F W^T W F (F = diag(fx, fy); W the whitening matrix of
+// pnp_uncert_cpu.cpp:214-215, or diag(w_u, w_v) of :44-45), so that with the normalised Jacobian rows
+// Ju = (ju, 1, 0, -xn) / z', Jv = (jv, 0, 1, -yn) / z'  (ju = qz + xn qx, jv = yn qx; order yaw, tx, ty, tz)
 //
-// Objects for which any point comes near a clip bound (z_min or the u/v ranges of pnp_uncert_cpu.cpp:36-42) are not
-// handled here: the kernel appends them to a redo list that the exact kernel (MRPNP_PREC_MIXED with its fp64 cold
-// path) processes afterwards, so clip semantics stay those of the reference.
+//     cost = 1/2 sum e^T M e        J^T r = sum [Ju; Jv]^T M e        J^T J = sum [Ju; Jv]^T M [Ju; Jv]
+//
+// -- identical to the whitened sums of the reference, but the unit / zero columns turn 9 of the 24 multiply-adds of
+// J^T J and J^T r into plain adds, and W itself is never needed again.  The cost change of a candidate is
+// 1/2 sum De^T (2 M e' - M De): relative accuracy ~1e-6 however small the step.
+//
+// Two points per lane: a lane owns the compacted points 64 g + 2 lane and + 1 of every group g of 64, loads them with
+// one 64-bit shared-memory access per plane and runs every arithmetic step once for both in a packed fp32 instruction.
+// The compacted arrays are padded to a multiple of 64 with null points (M = 0), so the loops carry no validity
+// predicates; when the padding does not fit (more than floor64(P) inliers) the remainder goes through the same code
+// instantiated for one point per lane with a validity flag, out of line.
+//
+// Objects for which a point comes near a clip bound (z_min or the u/v ranges of pnp_uncert_cpu.cpp:36-42) are not
+// handled here: the kernel hands them to the exact fp64 routine (solve_object_exact), so clip semantics stay the
+// reference's.  The per-point test is skipped when a bounding box of the object is inside the clip window.
 #pragma once
 #include "pnp_device.cuh"
 
 namespace mrpnp {
 
-// Per-evaluation constants of the delta pass (all derived from fp64 scalars, then rounded once).
+// ------------------------------------------------------------------ packed / scalar arithmetic behind one set of names
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 vneg(float2 a) { return make_float2(-a.x, -a.y); }  // folds into operand modifiers
+__device__ __forceinline__ float2 vsub(float2 a, float2 b) { return __fadd2_rn(a, vneg(b)); }
+__device__ __forceinline__ float2 vrcp(float2 a) { return make_float2(fast_rcp(a.x), fast_rcp(a.y)); }
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float vmul(float a, float b) { return a * b; }
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+__device__ __forceinline__ float vsub(float a, float b) { return a - b; }
+__device__ __forceinline__ float vrcp(float a) { return fast_rcp(a); }
+
+template <class V> struct Lanes;
+template <> struct Lanes<float2> {
+    static constexpr int kWidth = 2;
+    static __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }  // scalar-broadcast operand in SASS
+    static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+    static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+    static __device__ __forceinline__ float hsum(float2 v) { return v.x + v.y; }
+    static __device__ __forceinline__ float hmin(float2 v) { return fminf(v.x, v.y); }
+    static __device__ __forceinline__ float habsmax(float2 v) { return fmaxf(fabsf(v.x), fabsf(v.y)); }
+    static __device__ __forceinline__ float get(float2 v, int k) { return k ? v.y : v.x; }
+    static __device__ __forceinline__ float2 make(float a, float b) { return make_float2(a, b); }
+};
+template <> struct Lanes<float> {
+    static constexpr int kWidth = 1;
+    static __device__ __forceinline__ float bc(float s) { return s; }
+    static __device__ __forceinline__ float ld(const float* p) { return *p; }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+    static __device__ __forceinline__ float hsum(float v) { return v; }
+    static __device__ __forceinline__ float hmin(float v) { return v; }
+    static __device__ __forceinline__ float habsmax(float v) { return fabsf(v); }
+    static __device__ __forceinline__ float get(float v, int) { return v; }
+    static __device__ __forceinline__ float make(float a, float) { return a; }
+};
+
+// ------------------------------------------------------------------ per-evaluation constants
+// Per-evaluation constants of the delta pass.
 struct DeltaStep {
     float cp, sp, txp, typ, tzp;   // candidate pose: cos/sin yaw', t'
     float ncdm1, sd;               // -(cos dyaw - 1), sin dyaw          (dyaw = yaw' - yaw)
     float dtx, dty, dtz;           // t' - t
 };
 
-// Which rows of the slot a warp works on.  RowMap<1>: one warp owns all n compacted points.  RowMap<2>: two warps
-// share an object; each compacted its own half of the rows, so the inliers sit in two segments [0, n0) and
-// [base1, base1 + n1) whose rows of 32 points are numbered through and dealt alternately to the two warps (every
-// warp always revisits the same points: it owns their tracked residuals; the load is balanced to one row).
-template <int TEAM> struct RowMap;
-template <> struct RowMap<1> {
-    int n;
-    __device__ __forceinline__ int groups(int R) const { return (((n + 31) >> 5) + R - 1) / R; }
-    __device__ __forceinline__ int point(int g, int r, int R, int lane, bool& valid) const {
-        const int pr = (g * R + r) * 32 + lane;
-        valid = pr < n;
-        return valid ? pr : 0;
-    }
+// Camera constants in the normalised formulation.
+struct CamN {
+    float fx, fy, cx, cy, ifx, ify, ncxi, ncyi;  // 1/fx, 1/fy, -cx/fx, -cy/fy
 };
-template <> struct RowMap<2> {
-    int n0, n1, base1, rows0, rows_total, t, safe;
-    __device__ __forceinline__ RowMap(int n0_, int n1_, int base1_, int t_)
-        : n0(n0_), n1(n1_), base1(base1_), rows0((n0_ + 31) >> 5), rows_total(((n0_ + 31) >> 5) + ((n1_ + 31) >> 5)),
-          t(t_), safe(n0_ > 0 ? 0 : base1_) {}
-    __device__ __forceinline__ int groups(int R) const {
-        const int mine = rows_total > t ? (rows_total - t + 1) >> 1 : 0;
-        return (mine + R - 1) / R;
-    }
-    __device__ __forceinline__ int point(int g, int r, int R, int lane, bool& valid) const {
-        const int v = (g * R + r) * 2 + t;
-        const bool s1 = v >= rows0;
-        const int k = (s1 ? v - rows0 : v) * 32 + lane;
-        valid = (v < rows_total) && (k < (s1 ? n1 : n0));
-        return valid ? (s1 ? base1 + k : k) : safe;
-    }
-};
+__device__ __forceinline__ CamN make_camn(const Camera<float>& c) {
+    CamN n;
+    n.fx = c.fx; n.fy = c.fy; n.cx = c.cx; n.cy = c.cy;
+    n.ifx = 1.f / c.fx; n.ify = 1.f / c.fy;
+    n.ncxi = -c.cx * n.ifx; n.ncyi = -c.cy * n.ify;
+    return n;
+}
 
 // Clip window in normalised coordinates with the safety margins of eval_pass_mixed (0.05 px, z_min * 1.001 + 1e-3).
 struct ClipWindow {
@@ -80,6 +110,212 @@ __device__ __forceinline__ ClipWindow make_clip_window(const Camera<float>& c) {
     w.ymid = 0.5f * (ylo + yhi); w.yhalf = 0.5f * (yhi - ylo);
     w.zlo = c.z_min * 1.001f + 1e-3f;
     return w;
+}
+
+// max |X|, |Y|, |Z| over the inliers of the object (object frame), from the first evaluation
+struct Extent {
+    float xm, ym, zm;
+};
+
+// Is the object's bounding box, posed at (cos, sin, t), inside the clip window?  Then no point can be near a clip bound
+// and the pass skips its per-point tests.  |x' - xmid z'| <= |tx - xmid tz| + ex + |xmid| ez and z' >= tz - ez for
+// every point, ex = |c| Xm + |s| Zm, ez = |s| Xm + |c| Zm the half extents of the rotated box.
+__device__ __forceinline__ bool box_inside_window(const ClipWindow& w, const Extent& e, float c, float s, float tx,
+                                                  float ty, float tz) {
+    const float ac = fabsf(c), as = fabsf(s);
+    const float ex = fmaf(ac, e.xm, as * e.zm), ez = fmaf(as, e.xm, ac * e.zm);
+    const float zmin = tz - ez;
+    const float lx = (fabsf(fmaf(-w.xmid, tz, tx)) + fmaf(fabsf(w.xmid), ez, ex)) * 1.0001f;
+    const float ly = (fabsf(fmaf(-w.ymid, tz, ty)) + fmaf(fabsf(w.ymid), ez, e.ym)) * 1.0001f;
+    return (zmin >= w.zlo) && (lx <= w.xhalf * zmin) && (ly <= w.yhalf * zmin);  // false for NaN
+}
+
+// ------------------------------------------------------------------ the sums
+// a[0..3]  J^T r (yaw, tx, ty, tz)          a[4..13] J^T J upper triangle (00 01 02 03 11 12 13 22 23 33)
+// a[14]    sum |r|^2 (evaluations from the observations) or its CHANGE (delta pass)
+// a[3], a[7], a[10], a[12] are accumulated with the opposite sign (see kNegatedSums).
+constexpr unsigned kNegatedSums = (1u << 3) | (1u << 7) | (1u << 10) | (1u << 12);
+
+// One point (pair): normal-equation terms from the candidate-frame quantities, v = M e, and M.
+template <int WMODE, class V>
+__device__ __forceinline__ void accumulate_normal(V a[15], V qx, V qz, V xn, V yn, V iz, V v0, V v1, V m00, V m01, V m11) {
+    const V h0 = vmul(iz, v0), h1 = vmul(iz, v1);
+    const V ju = vfma(xn, qx, qz), jv = vmul(yn, qx);
+    a[0] = vfma(ju, h0, vfma(jv, h1, a[0]));
+    a[1] = vadd(a[1], h0);
+    a[2] = vadd(a[2], h1);
+    a[3] = vfma(xn, h0, vfma(yn, h1, a[3]));
+    const V iz2 = vmul(iz, iz);
+    const V n00 = vmul(iz2, m00), n11 = vmul(iz2, m11);
+    V p00, p10, q03, q13;
+    if (WMODE == MRPNP_W_FULL) {
+        const V n01 = vmul(iz2, m01);
+        p00 = vfma(n00, ju, vmul(n01, jv));
+        p10 = vfma(n01, ju, vmul(n11, jv));
+        q03 = vfma(n00, xn, vmul(n01, yn));
+        q13 = vfma(n01, xn, vmul(n11, yn));
+        a[9] = vadd(a[9], n01);
+    } else {
+        p00 = vmul(n00, ju);
+        p10 = vmul(n11, jv);
+        q03 = vmul(n00, xn);
+        q13 = vmul(n11, yn);
+    }
+    a[4] = vfma(ju, p00, vfma(jv, p10, a[4]));
+    a[5] = vadd(a[5], p00);
+    a[6] = vadd(a[6], p10);
+    a[7] = vfma(ju, q03, vfma(jv, q13, a[7]));
+    a[8] = vadd(a[8], n00);
+    a[10] = vadd(a[10], q03);
+    a[11] = vadd(a[11], n11);
+    a[12] = vadd(a[12], q13);
+    a[13] = vfma(xn, q03, vfma(yn, q13, a[13]));
+}
+
+// Running clip / extent observations of a pass.
+struct PassFlags {
+    float mz, mx, my;      // min z', max |xn - xmid|, max |yn - ymid|
+    float ex, ey, ez;      // max |X|, |Y|, |Z|  (first evaluation only)
+};
+
+// kPassFirst: an evaluation from the observations -- the initial point (plain fp32; also turns W into M) or, with
+// PassArgs::anchor, the fp64 anchor.  One body for both keeps the hot code small (instruction cache).
+enum PassKind { kPassFirst = 0, kPassDelta = 2, kPassUndo = 3 };
+
+// Uniform inputs of a pass (one struct for all kinds keeps the out-of-line remainder routine to one signature).
+struct PassArgs {
+    float cs, sn, tx, ty, tz;   // evaluation point (kPassFirst); for the other kinds see `step`
+    DeltaStep step;
+    CamN cam;
+    ClipWindow win;
+    bool check;                 // per-point clip tests (always on for kPassFirst)
+    bool anchor;                // kPassFirst: the fp64 anchor evaluation instead of the initial one
+};
+
+// The body of every pass for one point (V = float) or one pair of points (V = float2) at slot index idx.
+// `live`: only read for V = float (the remainder path): a dead lane computes on point 0 with M = 0 and stores nothing.
+template <int WMODE, int KIND, class V>
+__device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int idx, bool live, const PassArgs& u, V a[15],
+                                           PassFlags& f) {
+    using L = Lanes<V>;
+    constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
+    float* s3 = slot;
+    float* s2 = slot + 3 * P;
+    float* sw = slot + 5 * P;
+    const V X = L::ld(s3 + idx), Y = L::ld(s3 + P + idx), Z = L::ld(s3 + 2 * P + idx);
+    V o0 = L::ld(s2 + idx), o1 = L::ld(s2 + P + idx);            // observations (u, v) or tracked e
+    V m00 = L::ld(sw + idx), m11 = L::ld(sw + (WC - 1) * P + idx), m01 = L::bc(0.f);
+    if (WMODE == MRPNP_W_FULL) m01 = L::ld(sw + P + idx);
+    if (L::kWidth == 1 && !live) { m00 = L::bc(0.f); m11 = L::bc(0.f); m01 = L::bc(0.f); }
+
+    if (KIND == kPassFirst) {
+        if (!u.anchor) {
+            // weights -> M = F W^T W F, stored in place of W for the later passes
+            if (WMODE == MRPNP_W_FULL) {
+                const V wxx = m00, wxy = m01, wyy = m11;
+                m00 = vmul(vfma(wxx, wxx, vmul(wxy, wxy)), L::bc(u.cam.fx * u.cam.fx));
+                m11 = vmul(vfma(wyy, wyy, vmul(wxy, wxy)), L::bc(u.cam.fy * u.cam.fy));
+                m01 = vmul(vmul(wxy, vadd(wxx, wyy)), L::bc(u.cam.fx * u.cam.fy));
+            } else {
+                const V t0 = vmul(m00, L::bc(u.cam.fx)), t1 = vmul(m11, L::bc(u.cam.fy));
+                m00 = vmul(t0, t0);
+                m11 = vmul(t1, t1);
+            }
+            if (L::kWidth == 2 || live) {
+                L::st(sw + idx, m00);
+                L::st(sw + (WC - 1) * P + idx, m11);
+                if (WMODE == MRPNP_W_FULL) L::st(sw + P + idx, m01);
+            }
+            f.ex = fmaxf(f.ex, L::habsmax(X));
+            f.ey = fmaxf(f.ey, L::habsmax(Y));
+            f.ez = fmaxf(f.ez, L::habsmax(Z));
+        }
+        const V qx = vfma(L::bc(u.cs), X, vmul(L::bc(u.sn), Z));
+        const V qz = vfma(L::bc(u.cs), Z, vmul(L::bc(-u.sn), X));
+        const V x1 = vadd(qx, L::bc(u.tx)), y1 = vadd(Y, L::bc(u.ty)), z1 = vadd(qz, L::bc(u.tz));
+        const V iz = vrcp(z1);
+        const V xn = vmul(x1, iz), yn = vmul(y1, iz);
+        V e0, e1;
+        if (!u.anchor) {
+            // plain fp32: the residuals are many pixels here, and the decision on the first step is checked against
+            // its own rounding (see the LM loop)
+            e0 = vsub(xn, vfma(o0, L::bc(u.cam.ifx), L::bc(u.cam.ncxi)));
+            e1 = vsub(yn, vfma(o1, L::bc(u.cam.ify), L::bc(u.cam.ncyi)));
+        } else {
+            // the anchor: residual chain in fp64, rounded once to fp32, REPLACES the observations in the slot
+            const double cs = (double)u.cs, sn = (double)u.sn, tx = (double)u.tx, ty = (double)u.ty, tz = (double)u.tz;
+            const double ifx = 1.0 / (double)u.cam.fx, ify = 1.0 / (double)u.cam.fy;   // loop-invariant
+            const double ncxi = -(double)u.cam.cx * ifx, ncyi = -(double)u.cam.cy * ify;
+            float r0[2], r1[2];
+#pragma unroll
+            for (int k = 0; k < L::kWidth; ++k) {
+                const double Xd = (double)L::get(X, k), Yd = (double)L::get(Y, k), Zd = (double)L::get(Z, k);
+                const double xc = fma(cs, Xd, fma(sn, Zd, tx));
+                const double zc = fma(cs, Zd, fma(-sn, Xd, tz));
+                const double yc = Yd + ty;
+                const double izd = fast_rcp(zc);
+                const double un = fma((double)L::get(o0, k), ifx, ncxi);   // (u - cx) / fx
+                const double vn = fma((double)L::get(o1, k), ify, ncyi);
+                r0[k] = (float)fma(xc, izd, -un);
+                r1[k] = (float)fma(yc, izd, -vn);
+            }
+            e0 = L::make(r0[0], r0[L::kWidth - 1]);
+            e1 = L::make(r1[0], r1[L::kWidth - 1]);
+            if (L::kWidth == 2 || live) { L::st(s2 + idx, e0); L::st(s2 + P + idx, e1); }
+        }
+        // clip proximity on the fp32 projection (margins far above its rounding)
+        f.mz = fminf(f.mz, L::hmin(z1));
+        f.mx = fmaxf(f.mx, L::habsmax(vsub(xn, L::bc(u.win.xmid))));
+        f.my = fmaxf(f.my, L::habsmax(vsub(yn, L::bc(u.win.ymid))));
+        V v0, v1;
+        if (WMODE == MRPNP_W_FULL) {
+            v0 = vfma(m00, e0, vmul(m01, e1));
+            v1 = vfma(m01, e0, vmul(m11, e1));
+        } else {
+            v0 = vmul(m00, e0);
+            v1 = vmul(m11, e1);
+        }
+        a[14] = vfma(e0, v0, vfma(e1, v1, a[14]));
+        accumulate_normal<WMODE, V>(a, qx, qz, xn, yn, iz, v0, v1, m00, m01, m11);
+    } else {
+        const DeltaStep& s = u.step;
+        const V qx = vfma(L::bc(s.cp), X, vmul(L::bc(s.sp), Z));
+        const V qz = vfma(L::bc(s.cp), Z, vmul(L::bc(-s.sp), X));
+        const V x1 = vadd(qx, L::bc(s.txp)), y1 = vadd(Y, L::bc(s.typ)), z1 = vadd(qz, L::bc(s.tzp));
+        const V izp = vrcp(z1);
+        const V xnp = vmul(x1, izp), ynp = vmul(y1, izp);
+        const V Dx = vfma(L::bc(s.ncdm1), qx, vfma(L::bc(s.sd), qz, L::bc(s.dtx)));
+        const V Dz = vfma(L::bc(s.ncdm1), qz, vfma(L::bc(-s.sd), qx, L::bc(s.dtz)));
+        const V izo = vrcp(vsub(z1, Dz));
+        const V Du = vmul(vfma(vneg(xnp), Dz, Dx), izo);
+        const V Dv = vmul(vfma(vneg(ynp), Dz, L::bc(s.dty)), izo);
+        if (KIND == kPassUndo) {  // roll a rejected candidate back: e = e' - De (one fp32 rounding away from the old e)
+            if (L::kWidth == 2 || live) { L::st(s2 + idx, vsub(o0, Du)); L::st(s2 + P + idx, vsub(o1, Dv)); }
+            return;
+        }
+        const V e0 = vadd(o0, Du), e1 = vadd(o1, Dv);
+        if (L::kWidth == 2 || live) { L::st(s2 + idx, e0); L::st(s2 + P + idx, e1); }   // speculative: most steps are accepted
+        if (u.check) {
+            f.mz = fminf(f.mz, L::hmin(z1));
+            f.mx = fmaxf(f.mx, L::habsmax(vsub(xnp, L::bc(u.win.xmid))));
+            f.my = fmaxf(f.my, L::habsmax(vsub(ynp, L::bc(u.win.ymid))));
+        }
+        V v0, v1, d0, d1;
+        if (WMODE == MRPNP_W_FULL) {
+            v0 = vfma(m00, e0, vmul(m01, e1));
+            v1 = vfma(m01, e0, vmul(m11, e1));
+            d0 = vfma(m00, Du, vmul(m01, Dv));
+            d1 = vfma(m01, Du, vmul(m11, Dv));
+        } else {
+            v0 = vmul(m00, e0);
+            v1 = vmul(m11, e1);
+            d0 = vmul(m00, Du);
+            d1 = vmul(m11, Dv);
+        }
+        // |r'|^2 - |r|^2 = De^T (2 M e' - M De)
+        a[14] = vfma(Du, vfma(L::bc(2.f), v0, vneg(d0)), vfma(Dv, vfma(L::bc(2.f), v1, vneg(d1)), a[14]));
+        accumulate_normal<WMODE, V>(a, qx, qz, xnp, ynp, izp, v0, v1, m00, m01, m11);
+    }
 }
 
 // Transposed reduction of 16 per-lane partial sums, WITHOUT the broadcast: lane L ends with the warp total of value
@@ -98,291 +334,124 @@ __device__ __forceinline__ float warp_reduce16_scatter(float v[16], int lane) {
     return v[0] + __shfl_xor_sync(kFull, v[0], 1);
 }
 
-// ------------------------------------------------------------------ evaluations from the observations
-// The two evaluations that read the observations (u, v) instead of tracked residuals:
-//   anchor == false  the very first one, at the initial point: plain fp32 (residuals of many pixels there: the 1e-4 px
-//                    rounding of an fp32 projection is irrelevant, and the decision on the first step is never close);
-//   anchor == true   the second one, at the point after the first step: the residual chain runs in fp64 (as in
-//                    eval_pass_mixed) and the residuals REPLACE the observations in the slot -- the delta passes track
-//                    them from here on.  Diagonal weights store r = w d and fold the focal lengths into the weights
-//                    (w_u fx, w_v fy); full weights store the pixel differences d themselves.
-// Anchoring after the first (large) step instead of at the initial point matters: a delta pass leaves ~1e-7 of the
-// residual CHANGE behind as a fixed error of the tracked residuals, and only the first step changes them by many pixels.
-// Out: per-lane partial sums a[0..13] (J^T r, J^T J; layout of eval_pass_fp64 minus the cost), a[14] = this lane's
-// share of sum |r|^2, a[15] = 0; flagged = some point is within the margin of a clip bound.
-#ifndef MRPNP_FIRST_R
-#define MRPNP_FIRST_R 2
-#endif
-template <int WMODE, int LAYOUT, int R = MRPNP_FIRST_R, class ROWS = RowMap<1>>
-__device__ __forceinline__ void eval_pass_first(const float* s3, float* s2, float* sw, int P, const ROWS rows, int lane,
-                                                bool anchor, const float x[4], float snf, float csf,
-                                                const Camera<float>& camf, float a[16], bool& flagged) {
-    constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
-    const float txf = x[1], tyf = x[2], tzf = x[3];
-    const double sn = (double)snf, cs = (double)csf, tx = (double)txf, ty = (double)tyf, tz = (double)tzf;
-    const double fx = (double)camf.fx, fy = (double)camf.fy, cx = (double)camf.cx, cy = (double)camf.cy;
-    const float zlo = camf.z_min * 1.001f + 1e-3f;
-    const float ulo = camf.u_min + 0.05f, uhi = camf.u_max - 0.05f, vlo = camf.v_min + 0.05f, vhi = camf.v_max - 0.05f;
+__device__ __forceinline__ bool flags_raised(const PassFlags& f, const ClipWindow& w) {
+    return !(f.mz >= w.zlo) || !(f.mx <= w.xhalf) || !(f.my <= w.yhalf);
+}
+
+// The out-of-line routines (remainder, roll-back) take their PassArgs through the warp's shared-memory scratch: a struct
+// passed by value or reference to a non-inlined function would be given a home in LOCAL memory, and with ~106 KB of
+// local memory per CTA against ~28 KB of L1 every access to it from the hot loop would be an L2 round trip.
+constexpr int kPassArgWords = (int)(sizeof(PassArgs) / sizeof(float));
+static_assert(sizeof(PassArgs) % sizeof(float) == 0 && kPassArgWords <= 48, "PassArgs must fit the scratch");
+__device__ __forceinline__ void stash_args(float* smem, const PassArgs& u, int lane) {
+    if (lane == 0) {
+        smem[0] = u.cs; smem[1] = u.sn; smem[2] = u.tx; smem[3] = u.ty; smem[4] = u.tz;
+        smem[5] = u.step.cp; smem[6] = u.step.sp; smem[7] = u.step.txp; smem[8] = u.step.typ; smem[9] = u.step.tzp;
+        smem[10] = u.step.ncdm1; smem[11] = u.step.sd; smem[12] = u.step.dtx; smem[13] = u.step.dty; smem[14] = u.step.dtz;
+        smem[15] = u.cam.fx; smem[16] = u.cam.fy; smem[17] = u.cam.cx; smem[18] = u.cam.cy;
+        smem[19] = u.cam.ifx; smem[20] = u.cam.ify; smem[21] = u.cam.ncxi; smem[22] = u.cam.ncyi;
+        smem[23] = u.win.xmid; smem[24] = u.win.xhalf; smem[25] = u.win.ymid; smem[26] = u.win.yhalf; smem[27] = u.win.zlo;
+        smem[28] = u.anchor ? 1.f : 0.f;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ PassArgs fetch_args(const float* smem) {
+    PassArgs u;
+    u.cs = smem[0]; u.sn = smem[1]; u.tx = smem[2]; u.ty = smem[3]; u.tz = smem[4];
+    u.step.cp = smem[5]; u.step.sp = smem[6]; u.step.txp = smem[7]; u.step.typ = smem[8]; u.step.tzp = smem[9];
+    u.step.ncdm1 = smem[10]; u.step.sd = smem[11]; u.step.dtx = smem[12]; u.step.dty = smem[13]; u.step.dtz = smem[14];
+    u.cam.fx = smem[15]; u.cam.fy = smem[16]; u.cam.cx = smem[17]; u.cam.cy = smem[18];
+    u.cam.ifx = smem[19]; u.cam.ify = smem[20]; u.cam.ncxi = smem[21]; u.cam.ncyi = smem[22];
+    u.win.xmid = smem[23]; u.win.xhalf = smem[24]; u.win.ymid = smem[25]; u.win.yhalf = smem[26]; u.win.zlo = smem[27];
+    u.anchor = smem[28] != 0.f;
+    u.check = true;
+    return u;
+}
+
+// Remainder of a pass (cold, out of line): the points [start, n) that the padded 64-point groups do not cover, one
+// point per lane.  Adds its 15 totals to scratch[0..14] (which hold the totals of the main loop), merges the extents
+// (initial evaluation) into scratch[16..18] and returns the clip flag.  kind: PassKind; args: stash_args().
+template <int WMODE>
+__device__ __noinline__ bool pass_remainder(float* slot, int P, int start, int n, int lane, int kind, const float* args,
+                                            float* scratch) {
+    const PassArgs u = fetch_args(args);
+    float a[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = 0.f;
-    float margin = 1e30f;
-    const int ngroups = rows.groups(R);
-#pragma unroll 1
-    for (int g = 0; g < ngroups; ++g) {
-        float Xf[R], Yf[R], Zf[R], uf[R], vf[R], w0[R], w1[R], w2[R];
-        bool valid[R];
-        int pidx[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int p = rows.point(g, r, R, lane, valid[r]);
-            pidx[r] = p;
-            // padding lanes touch no memory (another lane may be rewriting the slot): a point at the object's origin
-            // with zero weights contributes nothing
-            Xf[r] = Yf[r] = Zf[r] = uf[r] = vf[r] = w0[r] = w1[r] = w2[r] = 0.f;
-            if (valid[r]) {
-                Xf[r] = s3[sidx<LAYOUT, 3>(p, 0, P)]; Yf[r] = s3[sidx<LAYOUT, 3>(p, 1, P)]; Zf[r] = s3[sidx<LAYOUT, 3>(p, 2, P)];
-                uf[r] = s2[sidx<LAYOUT, 2>(p, 0, P)]; vf[r] = s2[sidx<LAYOUT, 2>(p, 1, P)];
-                w0[r] = sw[sidx<LAYOUT, WC>(p, 0, P)]; w1[r] = sw[sidx<LAYOUT, WC>(p, 1, P)];
-                if (WMODE == MRPNP_W_FULL) w2[r] = sw[sidx<LAYOUT, WC>(p, WC - 1, P)];
-            }
-        }
-        // ---- fp32 projection: Jacobian, clip detection, (first evaluation) residuals ----
-        float qxf[R], qzf[R], izf[R], xnf[R], ynf[R], euf[R], evf[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            qxf[r] = fmaf(csf, Xf[r], snf * Zf[r]);
-            qzf[r] = fmaf(csf, Zf[r], -snf * Xf[r]);
-            const float zcf = qzf[r] + tzf;
-            margin = fminf(margin, zcf - zlo);
-            izf[r] = fast_rcp(zcf);
-            xnf[r] = (qxf[r] + txf) * izf[r];
-            ynf[r] = (Yf[r] + tyf) * izf[r];
-            const float puf = fmaf(camf.fx, xnf[r], camf.cx), pvf = fmaf(camf.fy, ynf[r], camf.cy);
-            margin = fminf(margin, fminf(fminf(puf - ulo, uhi - puf), fminf(pvf - vlo, vhi - pvf)));
-            euf[r] = puf - uf[r];
-            evf[r] = pvf - vf[r];
-        }
-        if (anchor) {
-            // ---- fp64 residual chain: the pixel differences to ~1e-13 px before they are rounded to fp32 ----
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const double X = (double)Xf[r], Y = (double)Yf[r], Z = (double)Zf[r];
-                const double xc = fma(cs, X, fma(sn, Z, tx));
-                const double zc = fma(cs, Z, fma(-sn, X, tz));
-                const double yc = Y + ty;
-                const double iz = fast_rcp(zc);
-                euf[r] = (float)(fma(fx, xc * iz, cx) - (double)uf[r]);
-                evf[r] = (float)(fma(fy, yc * iz, cy) - (double)vf[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float au = camf.fx * izf[r], av = camf.fy * izf[r];
-            const float bu = -au * xnf[r], bv = -av * ynf[r];
-            const float ju0 = fmaf(au, qzf[r], -bu * qxf[r]), jv0 = -bv * qxf[r];
-            if (WMODE != MRPNP_W_FULL) {
-                const float ruf = w0[r] * euf[r], rvf = w1[r] * evf[r];
-                a[14] = fmaf(ruf, ruf, fmaf(rvf, rvf, a[14]));
-                if (anchor && valid[r]) {
-                    s2[sidx<LAYOUT, 2>(pidx[r], 0, P)] = ruf; s2[sidx<LAYOUT, 2>(pidx[r], 1, P)] = rvf;
-                    sw[sidx<LAYOUT, WC>(pidx[r], 0, P)] = w0[r] * camf.fx;
-                    sw[sidx<LAYOUT, WC>(pidx[r], 1, P)] = w1[r] * camf.fy;
-                }
-                const float a0 = w0[r] * ju0, a1 = w0[r] * au, a3 = w0[r] * bu;
-                const float b0 = w1[r] * jv0, b2 = w1[r] * av, b3 = w1[r] * bv;
-                a[0] = fmaf(a0, ruf, fmaf(b0, rvf, a[0]));
-                a[1] = fmaf(a1, ruf, a[1]);
-                a[2] = fmaf(b2, rvf, a[2]);
-                a[3] = fmaf(a3, ruf, fmaf(b3, rvf, a[3]));
-                a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
-                a[5] = fmaf(a0, a1, a[5]);
-                a[6] = fmaf(b0, b2, a[6]);
-                a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
-                a[8] = fmaf(a1, a1, a[8]);
-                a[10] = fmaf(a1, a3, a[10]);
-                a[11] = fmaf(b2, b2, a[11]);
-                a[12] = fmaf(b2, b3, a[12]);
-                a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
-            } else {
-                if (anchor && valid[r]) { s2[sidx<LAYOUT, 2>(pidx[r], 0, P)] = euf[r]; s2[sidx<LAYOUT, 2>(pidx[r], 1, P)] = evf[r]; }
-                const float r0f = fmaf(w0[r], euf[r], w1[r] * evf[r]), r1f = fmaf(w1[r], euf[r], w2[r] * evf[r]);
-                a[14] = fmaf(r0f, r0f, fmaf(r1f, r1f, a[14]));
-                const float a0 = fmaf(w0[r], ju0, w1[r] * jv0), a1 = w0[r] * au, a2 = w1[r] * av, a3 = fmaf(w0[r], bu, w1[r] * bv);
-                const float b0 = fmaf(w1[r], ju0, w2[r] * jv0), b1 = w1[r] * au, b2 = w2[r] * av, b3 = fmaf(w1[r], bu, w2[r] * bv);
-                a[0] = fmaf(a0, r0f, fmaf(b0, r1f, a[0]));
-                a[1] = fmaf(a1, r0f, fmaf(b1, r1f, a[1]));
-                a[2] = fmaf(a2, r0f, fmaf(b2, r1f, a[2]));
-                a[3] = fmaf(a3, r0f, fmaf(b3, r1f, a[3]));
-                a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
-                a[5] = fmaf(a0, a1, fmaf(b0, b1, a[5]));
-                a[6] = fmaf(a0, a2, fmaf(b0, b2, a[6]));
-                a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
-                a[8] = fmaf(a1, a1, fmaf(b1, b1, a[8]));
-                a[9] = fmaf(a1, a2, fmaf(b1, b2, a[9]));
-                a[10] = fmaf(a1, a3, fmaf(b1, b3, a[10]));
-                a[11] = fmaf(a2, a2, fmaf(b2, b2, a[11]));
-                a[12] = fmaf(a2, a3, fmaf(b2, b3, a[12]));
-                a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
-            }
+    PassFlags f = {1e30f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int base = start; base < n; base += 32) {
+        const int idx = base + lane;
+        const bool live = idx < n;
+        if (kind == kPassFirst) pass_point<WMODE, kPassFirst, float>(slot, P, live ? idx : 0, live, u, a, f);
+        else if (kind == kPassDelta) pass_point<WMODE, kPassDelta, float>(slot, P, live ? idx : 0, live, u, a, f);
+        else pass_point<WMODE, kPassUndo, float>(slot, P, live ? idx : 0, live, u, a, f);
+    }
+    __syncwarp();
+    if (kind == kPassUndo) return false;
+    const float tot = warp_reduce16_scatter(a, lane);
+    if ((lane & 1) == 0 && lane < 30) scratch[lane >> 1] += ((kNegatedSums >> (lane >> 1)) & 1u) ? -tot : tot;
+    if (kind == kPassFirst && !u.anchor) {
+        const unsigned ex = __reduce_max_sync(kFull, __float_as_uint(f.ex)), ey = __reduce_max_sync(kFull, __float_as_uint(f.ey)),
+                       ez = __reduce_max_sync(kFull, __float_as_uint(f.ez));
+        if (lane == 0) {
+            scratch[16] = fmaxf(scratch[16], __uint_as_float(ex));
+            scratch[17] = fmaxf(scratch[17], __uint_as_float(ey));
+            scratch[18] = fmaxf(scratch[18], __uint_as_float(ez));
         }
     }
-    flagged = __any_sync(kFull, !(margin >= 0.f));
+    __syncwarp();
+    return __any_sync(kFull, flags_raised(f, u.win));
 }
 
-// ------------------------------------------------------------------ candidate evaluation (fp32 delta pass)
-// Candidate-frame quantities of one point and the change of its normalised projection since the accepted point.
-struct PointDelta {
-    float qx, qz, z1, izp, xnp, ynp, Du, Dv;
-};
-__device__ __forceinline__ PointDelta point_delta(float X, float Y, float Z, const DeltaStep& s) {
-    PointDelta d;
-    d.qx = fmaf(s.cp, X, s.sp * Z);
-    d.qz = fmaf(s.cp, Z, -s.sp * X);
-    const float x1 = d.qx + s.txp, y1 = Y + s.typ;
-    d.z1 = d.qz + s.tzp;
-    d.izp = fast_rcp(d.z1);
-    d.xnp = x1 * d.izp;
-    d.ynp = y1 * d.izp;
-    const float Dx = fmaf(s.ncdm1, d.qx, fmaf(s.sd, d.qz, s.dtx));
-    const float Dz = fmaf(s.ncdm1, d.qz, fmaf(-s.sd, d.qx, s.dtz));
-    const float izo = fast_rcp(d.z1 - Dz);
-    d.Du = fmaf(-d.xnp, Dz, Dx) * izo;
-    d.Dv = fmaf(-d.ynp, Dz, s.dty) * izo;
-    return d;
-}
-
-// In: tracked residuals at the accepted point in the s2 planes.  Out (per-lane partial sums): a[0..13] = J^T r' and
-// J^T J at the candidate, a[14] = sum |r'|^2 - sum |r|^2 (twice the cost change), a[15] = 0; the s2 planes now hold r'.
-template <int WMODE, int LAYOUT, int R = 2, class ROWS = RowMap<1>>
-__device__ __forceinline__ void eval_pass_delta(const float* s3, float* s2, const float* sw, int P, const ROWS rows,
-                                                int lane, const DeltaStep& st, const Camera<float>& camf,
-                                                const ClipWindow& cw, float a[16], bool& flagged) {
-    constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
+// One evaluation: the packed loop over the 64-point groups [0, n_main) -- from the observations (first == true: the
+// initial point or the anchor, PassArgs::anchor) or as a delta pass -- then ONE copy of the transposed reduction, the
+// totals through the warp's scratch (scratch[0..14]; [16..18] = extents after the initial evaluation), and the
+// remainder [n_main, n) if any.  Returns false if a total is not finite.
+template <int WMODE>
+__device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, int lane, const PassArgs& u, bool first,
+                                         float* scratch, float* arg_stash, bool& flagged) {
+    float2 a[15];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] = 0.f;
-    float dc[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) dc[r] = 0.f;
-    float mx = 0.f, my = 0.f, mz = 1e30f;
-    const int ngroups = rows.groups(R);
+    for (int i = 0; i < 15; ++i) a[i] = make_float2(0.f, 0.f);
+    PassFlags f = {1e30f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int end = n_main + 2 * lane;
+    if (first) {
 #pragma unroll 1
-    for (int g = 0; g < ngroups; ++g) {
-        float X[R], Y[R], Z[R], e0[R], e1[R], w0[R], w1[R], w2[R];
-        bool valid[R];
-        int pidx[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int p = rows.point(g, r, R, lane, valid[r]);
-            pidx[r] = p;
-            // padding lanes touch no memory: a point at the object's origin with zero weights contributes nothing
-            X[r] = Y[r] = Z[r] = e0[r] = e1[r] = w0[r] = w1[r] = w2[r] = 0.f;
-            if (valid[r]) {
-                X[r] = s3[sidx<LAYOUT, 3>(p, 0, P)]; Y[r] = s3[sidx<LAYOUT, 3>(p, 1, P)]; Z[r] = s3[sidx<LAYOUT, 3>(p, 2, P)];
-                e0[r] = s2[sidx<LAYOUT, 2>(p, 0, P)]; e1[r] = s2[sidx<LAYOUT, 2>(p, 1, P)];
-                w0[r] = sw[sidx<LAYOUT, WC>(p, 0, P)]; w1[r] = sw[sidx<LAYOUT, WC>(p, 1, P)];
-                if (WMODE == MRPNP_W_FULL) w2[r] = sw[sidx<LAYOUT, WC>(p, WC - 1, P)];
-            }
-        }
-        PointDelta d[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            d[r] = point_delta(X[r], Y[r], Z[r], st);
-            mz = fminf(mz, d[r].z1);
-            mx = fmaxf(mx, fabsf(d[r].xnp - cw.xmid));
-            my = fmaxf(my, fabsf(d[r].ynp - cw.ymid));
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float qx = d[r].qx, qz = d[r].qz, izp = d[r].izp, xnp = d[r].xnp, ynp = d[r].ynp;
-            if (WMODE != MRPNP_W_FULL) {
-                // tracked r = (w_u fx) (x/z - un), (w_v fy) (y/z - vn); the weights already carry the focal lengths
-                const float dru = w0[r] * d[r].Du, drv = w1[r] * d[r].Dv;
-                const float ru = e0[r] + dru, rv = e1[r] + drv;
-                dc[r] = fmaf(dru, e0[r] + ru, fmaf(drv, e1[r] + rv, dc[r]));
-                if (valid[r]) { s2[sidx<LAYOUT, 2>(pidx[r], 0, P)] = ru; s2[sidx<LAYOUT, 2>(pidx[r], 1, P)] = rv; }
-                const float a1 = w0[r] * izp, b2 = w1[r] * izp;
-                const float a3 = -a1 * xnp, b3 = -b2 * ynp;
-                const float a0 = fmaf(a1, qz, -a3 * qx), b0 = -b3 * qx;
-                a[0] = fmaf(a0, ru, fmaf(b0, rv, a[0]));
-                a[1] = fmaf(a1, ru, a[1]);
-                a[2] = fmaf(b2, rv, a[2]);
-                a[3] = fmaf(a3, ru, fmaf(b3, rv, a[3]));
-                a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
-                a[5] = fmaf(a0, a1, a[5]);
-                a[6] = fmaf(b0, b2, a[6]);
-                a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
-                a[8] = fmaf(a1, a1, a[8]);
-                a[10] = fmaf(a1, a3, a[10]);
-                a[11] = fmaf(b2, b2, a[11]);
-                a[12] = fmaf(b2, b3, a[12]);
-                a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
-            } else {
-                // tracked e = pixel differences; r = W e (pnp_uncert_cpu.cpp:214-215)
-                const float deu = camf.fx * d[r].Du, dev = camf.fy * d[r].Dv;
-                const float eu = e0[r] + deu, ev = e1[r] + dev;
-                if (valid[r]) { s2[sidx<LAYOUT, 2>(pidx[r], 0, P)] = eu; s2[sidx<LAYOUT, 2>(pidx[r], 1, P)] = ev; }
-                const float dr0 = fmaf(w0[r], deu, w1[r] * dev), dr1 = fmaf(w1[r], deu, w2[r] * dev);
-                const float r0 = fmaf(w0[r], eu, w1[r] * ev), r1 = fmaf(w1[r], eu, w2[r] * ev);
-                dc[r] = fmaf(dr0, fmaf(2.f, r0, -dr0), fmaf(dr1, fmaf(2.f, r1, -dr1), dc[r]));
-                const float au = camf.fx * izp, av = camf.fy * izp;
-                const float bu = -au * xnp, bv = -av * ynp;
-                const float ju0 = fmaf(au, qz, -bu * qx), jv0 = -bv * qx;
-                const float a0 = fmaf(w0[r], ju0, w1[r] * jv0), a1 = w0[r] * au, a2 = w1[r] * av, a3 = fmaf(w0[r], bu, w1[r] * bv);
-                const float b0 = fmaf(w1[r], ju0, w2[r] * jv0), b1 = w1[r] * au, b2 = w2[r] * av, b3 = fmaf(w1[r], bu, w2[r] * bv);
-                a[0] = fmaf(a0, r0, fmaf(b0, r1, a[0]));
-                a[1] = fmaf(a1, r0, fmaf(b1, r1, a[1]));
-                a[2] = fmaf(a2, r0, fmaf(b2, r1, a[2]));
-                a[3] = fmaf(a3, r0, fmaf(b3, r1, a[3]));
-                a[4] = fmaf(a0, a0, fmaf(b0, b0, a[4]));
-                a[5] = fmaf(a0, a1, fmaf(b0, b1, a[5]));
-                a[6] = fmaf(a0, a2, fmaf(b0, b2, a[6]));
-                a[7] = fmaf(a0, a3, fmaf(b0, b3, a[7]));
-                a[8] = fmaf(a1, a1, fmaf(b1, b1, a[8]));
-                a[9] = fmaf(a1, a2, fmaf(b1, b2, a[9]));
-                a[10] = fmaf(a1, a3, fmaf(b1, b3, a[10]));
-                a[11] = fmaf(a2, a2, fmaf(b2, b2, a[11]));
-                a[12] = fmaf(a2, a3, fmaf(b2, b3, a[12]));
-                a[13] = fmaf(a3, a3, fmaf(b3, b3, a[13]));
-            }
-        }
+        for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassFirst, float2>(slot, P, idx, true, u, a, f);
+    } else {
+#pragma unroll 2
+        for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassDelta, float2>(slot, P, idx, true, u, a, f);
     }
-    flagged = __any_sync(kFull, !(mz >= cw.zlo) || !(mx <= cw.xhalf) || !(my <= cw.yhalf));
-    // cost change: fp32 per-lane partials and an fp32 cross-lane tree.  The partials cancel (the gradient is ~0 near the
-    // optimum), which bounds the relative error of the total by ~1e-7 |r| / |dr| ~ 2e-4 at the function-tolerance
-    // threshold -- a band in which ~1e-4 of all decisions fall.
-    float dcs = dc[0];
+    float s[16];
 #pragma unroll
-    for (int r = 1; r < R; ++r) dcs += dc[r];
-    a[14] = dcs;
+    for (int i = 0; i < 15; ++i) s[i] = a[i].x + a[i].y;
+    s[15] = 0.f;
+    const float tot = warp_reduce16_scatter(s, lane);
+    __syncwarp();
+    if ((lane & 1) == 0) scratch[lane >> 1] = ((kNegatedSums >> (lane >> 1)) & 1u) ? -tot : tot;
+    const unsigned ex = __reduce_max_sync(kFull, __float_as_uint(f.ex)), ey = __reduce_max_sync(kFull, __float_as_uint(f.ey)),
+                   ez = __reduce_max_sync(kFull, __float_as_uint(f.ez));
+    if (lane == 0) { scratch[16] = __uint_as_float(ex); scratch[17] = __uint_as_float(ey); scratch[18] = __uint_as_float(ez); }
+    __syncwarp();
+    flagged = (first || u.check) && __any_sync(kFull, flags_raised(f, u.win));
+    if (n > n_main) {
+        stash_args(arg_stash, u, lane);
+        flagged = pass_remainder<WMODE>(slot, P, n_main, n, lane, first ? kPassFirst : kPassDelta, arg_stash, scratch) || flagged;
+    }
+    return __all_sync(kFull, fabsf(scratch[lane & 15]) < 3.0e38f);
 }
 
-// Roll the speculative residual update of a rejected candidate back: r = r' - dr with dr recomputed from the same
-// inputs (at most one fp32 rounding away from the value before the candidate; a perturbation of ~6e-8 |r|).
-template <int WMODE, int LAYOUT, class ROWS = RowMap<1>>
-__device__ __noinline__ void undo_pass_delta(float* slot, int P, const ROWS rows, int lane, DeltaStep st, float fx, float fy) {
-    constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
-    const float* s3 = slot;
-    float* s2 = slot + 3 * P;
-    const float* sw = slot + 5 * P;
-    const int ngroups = rows.groups(1);
+// Roll the speculative residual update of a rejected candidate back (out of line: rare).  args: stash_args().
+template <int WMODE>
+__device__ __noinline__ void undo_pass(float* slot, int P, int n_main, int n, int lane, const float* args) {
+    const PassArgs u = fetch_args(args);
+    float2 a[15];
+    PassFlags f;
+    const int end = n_main + 2 * lane;
 #pragma unroll 1
-    for (int g = 0; g < ngroups; ++g) {
-        bool valid;
-        const int p = rows.point(g, 0, 1, lane, valid);
-        if (!valid) continue;
-        const PointDelta d = point_delta(s3[sidx<LAYOUT, 3>(p, 0, P)], s3[sidx<LAYOUT, 3>(p, 1, P)],
-                                         s3[sidx<LAYOUT, 3>(p, 2, P)], st);
-        float d0, d1;
-        if (WMODE != MRPNP_W_FULL) {
-            d0 = sw[sidx<LAYOUT, WC>(p, 0, P)] * d.Du;
-            d1 = sw[sidx<LAYOUT, WC>(p, 1, P)] * d.Dv;
-        } else {
-            d0 = fx * d.Du;
-            d1 = fy * d.Dv;
-        }
-        s2[sidx<LAYOUT, 2>(p, 0, P)] -= d0;
-        s2[sidx<LAYOUT, 2>(p, 1, P)] -= d1;
-    }
+    for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassUndo, float2>(slot, P, idx, true, u, a, f);
+    if (n > n_main) pass_remainder<WMODE>(slot, P, n_main, n, lane, kPassUndo, args, nullptr);
+    __syncwarp();
 }
 
 }  // namespace mrpnp

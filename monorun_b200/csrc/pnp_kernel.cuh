@@ -59,6 +59,12 @@ __device__ __forceinline__ void load_object(const KParams& kp, int obj, float* s
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
+    } else if (kp.global_interleaved) {
+        // [N,P,C] tensors into a PLANAR slot (the exact routine inside the fast kernel): transpose on the way
+        for (int i = lane; i < 3 * P; i += 32) { const int p = i / 3; s3[(i - 3 * p) * P + p] = __ldg(g3 + i); }
+        for (int i = lane; i < 2 * P; i += 32) { const int p = i >> 1; s2[(i & 1) * P + p] = __ldg(g2 + i); }
+        for (int i = lane; i < WC * P; i += 32) { const int p = i / WC; sw[(i - WC * p) * P + p] = __ldg(gw + i); }
+        __syncwarp();
     } else {
         for (int i = lane; i < 3 * P; i += 32) s3[i] = __ldg(g3 + i);
         if (!kp.dense) for (int i = lane; i < 2 * P; i += 32) s2[i] = __ldg(g2 + i);
@@ -224,6 +230,286 @@ __device__ __forceinline__ int mask_and_compact(const KParams& kp, int obj, floa
     return base;
 }
 
+// One object, start to finish, by one warp: stage, weights, inlier mask, compaction, Ceres-1.14 LM, covariance, result
+// row.  Out of line: it is the whole body of pnp_lm_kernel below AND the routine the MRPNP_PREC_FAST kernel calls
+// (MIXED = false, exact fp64 decisions) for the few objects it hands back (a point near a clip bound, an accept /
+// function-tolerance decision within rounding of its threshold).  `scratch`: 40 doubles of the warp's header.
+template <bool MIXED, int WMODE, int LAYOUT>
+__device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, float* slot, uint64_t* bar, uint32_t parity,
+                                                    double* scratch, int lane) {
+    constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
+    const int P = kp.n_pts;
+    const float* s3 = slot;
+    const float* s2 = slot + 3 * P;
+    const float* sw = slot + 5 * P;
+    const int max_iter = kp.max_iter > 0 ? kp.max_iter : (kp.max_iter < 0 ? 0 : 50);
+    const Camera<float> camf = load_camera<float>(kp, obj);
+    Camera<double> cam;
+    cam.fx = camf.fx; cam.fy = camf.fy; cam.cx = camf.cx; cam.cy = camf.cy;  // only these four are used inline
+
+    // ---------------- stage + istd + inlier mask + compaction ----------------
+    uint32_t bits = 0u;
+    int n_inliers = P, n = P;
+    bool compacted = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        load_object<WC>(kp, obj, slot, bar, parity, lane);
+        float thr_u, thr_v;
+        if (WMODE == MRPNP_W_LOGSTD && LAYOUT == MRPNP_LAYOUT_PLANAR && kp.dense)
+            dense_decode_and_thresholds(kp, obj, slot, lane, thr_u, thr_v);
+        else
+            weights_and_thresholds<WMODE, LAYOUT, MIXED>(kp, slot + 5 * P, lane, thr_u, thr_v);
+        // second attempt == pnp_uncert_cpu.py:28-32: <= 4 inliers -> every point is an inlier (slot re-staged)
+        const bool all = attempt == 1;
+        const bool compact = !all && kp.inlier_opt_only != 0;
+        n_inliers = mask_and_compact<WMODE, LAYOUT>(kp, obj, slot, lane, thr_u, thr_v, all, compact, bits);
+        if (all || n_inliers > 4) {
+            compacted = compact;
+            break;
+        }
+    }
+    n = compacted ? n_inliers : P;
+
+    // ---------------- Levenberg-Marquardt, Ceres 1.14 TrustRegionMinimizer control flow ----------------
+    // One evaluation site: `pt` is the initial point in phase 0 and the candidate x + delta afterwards.
+    double x[4], pt[4];
+    bool init_ok = true;
+    if (kp.init_mode == MRPNP_INIT_GIVEN) {
+        const float* ip = kp.init + (size_t)obj * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pt[i] = (double)__ldg(ip + i);
+    } else {
+        init_ok = linear_init<WMODE, LAYOUT>(kp, obj, slot, n, lane, scratch);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pt[i] = scratch[kScrPt + i];
+        __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = pt[i];
+
+    double cost = 0.0, g[4], H[10], scale[4], diag[4], delta[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { g[i] = 0.0; scale[i] = 1.0; diag[i] = 1.0; delta[i] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) H[i] = 0.0;
+    int term = kNoConvergence, iteration = 0, cost_evals = 0, num_invalid = 0;
+    double radius = kInitialRadius, decrease_factor = 2.0, x_norm = 0.0, model_change = 1.0;
+    bool reuse_diagonal = false, step_ok = true, clip_x = false, first = true;
+    double sn_x = 0.0, cs_x = 1.0, sn_p = 0.0, cs_p = 1.0;  // sin/cos of the accepted point / of pt
+
+    while (true) {
+        // ---- the fused pass at pt ----
+        double acc[16];
+        bool clip_p = false, jfinite = true;
+        bool exact = !MIXED;
+        if (MIXED) {
+            // rotation at pt: library sincos once per object, then the angle-addition update from the accepted
+            // point with a small-angle polynomial (the step in yaw is tiny after the first iteration)
+            double sn, cs;
+            const double dyaw = pt[0] - x[0];
+            if (first || fabs(dyaw) > 0.5) {
+                sincos(pt[0], &sn, &cs);
+            } else {
+                double sd, cd;
+                sincos_small(dyaw, &sd, &cd);
+                sn = fma(sn_x, cd, cs_x * sd);
+                cs = fma(cs_x, cd, -sn_x * sd);
+            }
+            sn_p = sn; cs_p = cs;
+            eval_pass_mixed<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, pt, sn, cs, cam, camf, acc, scratch, exact, jfinite);
+        }
+        if (exact) {  // MRPNP_PREC_FP64, or a point near a clip bound in the mixed pass: exact fp64 clip semantics
+            __syncwarp();
+            if (lane < 4) {
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v = (lane == i) ? pt[i] : v;
+                scratch[kScrPt + lane] = v;
+            }
+            __syncwarp();
+            eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 0, false, scratch);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = scratch[kScrSums + i];
+            clip_p = scratch[kScrClip] != 0.0;
+            __syncwarp();
+            const double t0 = (fabs(acc[1]) + fabs(acc[2])) + (fabs(acc[3]) + fabs(acc[4]));
+            const double t1 = (fabs(acc[5]) + fabs(acc[6])) + (fabs(acc[7]) + fabs(acc[8]));
+            const double t2 = (fabs(acc[9]) + fabs(acc[10])) + (fabs(acc[11]) + fabs(acc[12]));
+            jfinite = finite_value((t0 + t1) + (t2 + (fabs(acc[13]) + fabs(acc[14]))));
+        }
+        ++cost_evals;
+        const bool cfinite = finite_value(acc[0]);
+        jfinite = jfinite && cfinite;
+        bool accept = false;
+        if (first) {  // IterationZero
+            first = false;
+            if (!jfinite || !init_ok) { term = kFailure; break; }  // parameters stay at init
+            accept = true;
+            cost = 0.5 * acc[0];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)  // jacobi_scaling from the initial Jacobian only
+                scale[i] = fast_rcp(1.0 + fast_sqrt(acc[5 + tri(i, i)]));
+        } else {
+            const double cand_cost = cfinite ? 0.5 * acc[0] : kDblMax;
+            // ParameterToleranceReached
+            const double step_norm2 = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2] + delta[3] * delta[3];
+            const double ptol = kParameterTol * (x_norm + kParameterTol);
+            if (step_norm2 <= ptol * ptol) { term = kConvergence; break; }
+            // FunctionToleranceReached (Ceres 1.14: the candidate is not adopted on this exit)
+            const double cost_change = cost - cand_cost;
+            if (fabs(cost_change) <= kFunctionTol * cost) {
+                term = kConvergence;
+                if (!(kp.adopt_ftol && cand_cost < cost)) break;
+                accept = true;  // documented switch: take the candidate, then stop
+            }
+            const double rho = cost_change * fast_rcp1(model_change);
+            if (accept || rho > kMinRelDecrease) {  // HandleSuccessfulStep
+                if (!jfinite) { term = kFailure; break; }  // re-evaluation at the new point fails in Ceres
+                const bool stop = accept;
+                accept = true;
+                cost = cand_cost;
+                const double q = 2.0 * rho - 1.0;
+                radius = fmin(kMaxRadius, radius * fast_rcp(fmax(1.0 / 3.0, 1.0 - q * q * q)));
+                decrease_factor = 2.0;
+                reuse_diagonal = false;
+                if (stop) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { x[i] = pt[i]; g[i] = acc[1 + i]; }
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
+                    clip_x = clip_p;
+                    sn_x = sn_p; cs_x = cs_p;
+                    break;
+                }
+            } else {  // HandleUnsuccessfulStep
+                radius /= decrease_factor;
+                decrease_factor *= 2.0;
+            }
+        }
+        if (accept) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { x[i] = pt[i]; g[i] = acc[1 + i]; }
+#pragma unroll
+            for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
+            clip_x = clip_p;
+            sn_x = sn_p; cs_x = cs_p;
+            x_norm = fast_sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+            step_ok = true;
+        }
+        // ---- next trust-region step (invalid steps shrink the radius without a new evaluation) ----
+        bool stop = false;
+        while (true) {
+            // FinalizeIterationAndCheckIfMinimizerCanContinue
+            if (iteration >= max_iter) { term = kNoConvergence; stop = true; break; }
+            if (step_ok) {
+                const double gmax = fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3])));
+                if (gmax <= kGradientTol) { term = kConvergence; stop = true; break; }
+            }
+            if (radius <= kMinRadius) { term = kConvergence; stop = true; break; }
+            ++iteration;
+            step_ok = false;
+            // LevenbergMarquardtStrategy::ComputeStep on the column-scaled system
+            double Hs[10], gs[4], A[10], y[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                gs[i] = g[i] * scale[i];
+#pragma unroll
+                for (int j = i; j < 4; ++j) Hs[tri(i, j)] = H[tri(i, j)] * (scale[i] * scale[j]);
+            }
+            if (!reuse_diagonal) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) diag[i] = fmin(fmax(Hs[tri(i, i)], kMinLmDiag), kMaxLmDiag);
+            }
+            reuse_diagonal = true;
+            const double inv_radius = fast_rcp1(radius);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) A[i] = Hs[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) A[tri(i, i)] = fma(diag[i], inv_radius, A[tri(i, i)]);
+            const Ldl4 f = ldl4_factor(A);
+            bool valid = f.ok;
+            if (valid) {
+                ldl4_solve(f, gs, y);  // step = -y
+                // model_cost_change = y^T gs - 1/2 y^T Hs y with (Hs + D) y = gs  =>  1/2 (y^T gs + sum_i D_i y_i^2)
+                double yg = 0.0, ydy = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    yg = fma(y[i], gs[i], yg);
+                    ydy = fma(diag[i] * inv_radius * y[i], y[i], ydy);
+                }
+                model_change = 0.5 * (yg + ydy);
+                valid = (model_change > 0.0) && finite_value(fabs(y[0]) + fabs(y[1]) + fabs(y[2]) + fabs(y[3]));
+            }
+            if (valid) {
+                num_invalid = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { delta[i] = -y[i] * scale[i]; pt[i] = x[i] + delta[i]; }
+                break;
+            }
+            // HandleInvalidStep
+            if (++num_invalid >= kMaxInvalidSteps) { term = kFailure; stop = true; break; }
+            radius /= decrease_factor;
+            decrease_factor *= 2.0;
+        }
+        if (stop) break;
+    }
+    bool usable = term != kFailure;  // Summary::IsSolutionUsable (pnp_uncert_cpu.cpp:276)
+
+    // ---------------- pose covariance ----------------
+    double cov[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cov[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    if (kp.cov_mode != MRPNP_COV_NONE && usable) {
+        // H already holds J^T J at the returned x with Ceres masks.  The pipeline covariance
+        // (hessian.py:67-87) differs only when a point is clipped at x or outliers were kept in LM.
+        const bool any_clip = __any_sync(kFull, clip_x);
+        const bool need_pass = kp.cov_mode == MRPNP_COV_PIPELINE && (any_clip || (!compacted && n_inliers < P));
+        if (need_pass) {
+            __syncwarp();
+            if (lane < 4) {
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v = (lane == i) ? x[i] : v;
+                scratch[kScrPt + lane] = v;
+            }
+            __syncwarp();
+            eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 1, !compacted, scratch);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) H[i] = scratch[kScrSums + 5 + i];
+            __syncwarp();
+        }
+        if (!spd_inverse4(H, cov)) {  // pnp_uncert.py:79-85 fallback: H := I, object invalid
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cov[i] = (i % 5 == 0) ? 1.0 : 0.0;
+            usable = false;
+        }
+    }
+
+    // ---------------- result row: one coalesced 96-byte store ----------------
+    {
+        float v = 0.f;  // unrolled selects: no dynamically indexed local arrays
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v = (lane == i) ? (float)x[i] : v;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v = (lane == 4 + i) ? (float)cov[i] : v;
+        v = (lane == 20) ? (usable ? 1.f : 0.f) : v;
+        v = (lane == 21) ? (float)iteration : v;
+        v = (lane == 22) ? (float)cost : v;
+        v = (lane == 23) ? (float)radius : v;
+        store_result_row(kp, obj, lane, v);
+        if (kp.result64) {
+            double d = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d = (lane == i) ? x[i] : d;
+            d = (lane == 4) ? cost : d;
+            d = (lane == 5) ? radius : d;
+            d = (lane == 6) ? (double)cost_evals : d;
+            d = (lane == 7) ? (double)term : d;
+            if (lane < 8) kp.result64[(size_t)obj * 8 + lane] = d;
+        }
+    }
+    return parity;   // mbarrier phase after this object's copies (by value: no local of the caller has its address taken)
+}
+
 template <bool MIXED, int WMODE, int LAYOUT>
 __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_constant__ KParams kp) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
@@ -234,10 +520,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
     uint64_t* bar = reinterpret_cast<uint64_t*>(header);
     double* scratch = reinterpret_cast<double*>(header + 128);
     float* slot = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * kWarpHeaderBytes) + (size_t)warp * kp.slot_floats;
-    const int P = kp.n_pts;
-    const float* s3 = slot;
-    const float* s2 = slot + 3 * P;
-    const float* sw = slot + 5 * P;
 
     // work list: all objects, or (follow-up launch of a FAST solve) the objects the fast kernel handed back
     int n_work = kp.n_obj;
@@ -253,7 +535,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
     }
     __syncwarp();
     uint32_t parity = 0;
-    const int max_iter = kp.max_iter > 0 ? kp.max_iter : (kp.max_iter < 0 ? 0 : 50);
 
     while (true) {
         int obj = 0;
@@ -265,270 +546,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
         obj = __shfl_sync(kFull, obj, 0);
         if (obj < 0) break;
 
-        const Camera<float> camf = load_camera<float>(kp, obj);
-        Camera<double> cam;
-        cam.fx = camf.fx; cam.fy = camf.fy; cam.cx = camf.cx; cam.cy = camf.cy;  // only these four are used inline
-
-        // ---------------- stage + istd + inlier mask + compaction ----------------
-        uint32_t bits = 0u;
-        int n_inliers = P, n = P;
-        bool compacted = false;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            load_object<WC>(kp, obj, slot, bar, parity, lane);
-            float thr_u, thr_v;
-            if (WMODE == MRPNP_W_LOGSTD && LAYOUT == MRPNP_LAYOUT_PLANAR && kp.dense)
-                dense_decode_and_thresholds(kp, obj, slot, lane, thr_u, thr_v);
-            else
-                weights_and_thresholds<WMODE, LAYOUT, MIXED>(kp, slot + 5 * P, lane, thr_u, thr_v);
-            // second attempt == pnp_uncert_cpu.py:28-32: <= 4 inliers -> every point is an inlier (slot re-staged)
-            const bool all = attempt == 1;
-            const bool compact = !all && kp.inlier_opt_only != 0;
-            n_inliers = mask_and_compact<WMODE, LAYOUT>(kp, obj, slot, lane, thr_u, thr_v, all, compact, bits);
-            if (all || n_inliers > 4) {
-                compacted = compact;
-                break;
-            }
-        }
-        n = compacted ? n_inliers : P;
-
-        // ---------------- Levenberg-Marquardt, Ceres 1.14 TrustRegionMinimizer control flow ----------------
-        // One evaluation site: `pt` is the initial point in phase 0 and the candidate x + delta afterwards.
-        double x[4], pt[4];
-        bool init_ok = true;
-        if (kp.init_mode == MRPNP_INIT_GIVEN) {
-            const float* ip = kp.init + (size_t)obj * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) pt[i] = (double)__ldg(ip + i);
-        } else {
-            init_ok = linear_init<WMODE, LAYOUT>(kp, obj, slot, n, lane, scratch);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) pt[i] = scratch[kScrPt + i];
-            __syncwarp();
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = pt[i];
-
-        double cost = 0.0, g[4], H[10], scale[4], diag[4], delta[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { g[i] = 0.0; scale[i] = 1.0; diag[i] = 1.0; delta[i] = 0.0; }
-#pragma unroll
-        for (int i = 0; i < 10; ++i) H[i] = 0.0;
-        int term = kNoConvergence, iteration = 0, cost_evals = 0, num_invalid = 0;
-        double radius = kInitialRadius, decrease_factor = 2.0, x_norm = 0.0, model_change = 1.0;
-        bool reuse_diagonal = false, step_ok = true, clip_x = false, first = true;
-        double sn_x = 0.0, cs_x = 1.0, sn_p = 0.0, cs_p = 1.0;  // sin/cos of the accepted point / of pt
-
-        while (true) {
-            // ---- the fused pass at pt ----
-            double acc[16];
-            bool clip_p = false, jfinite = true;
-            bool exact = !MIXED;
-            if (MIXED) {
-                // rotation at pt: library sincos once per object, then the angle-addition update from the accepted
-                // point with a small-angle polynomial (the step in yaw is tiny after the first iteration)
-                double sn, cs;
-                const double dyaw = pt[0] - x[0];
-                if (first || fabs(dyaw) > 0.5) {
-                    sincos(pt[0], &sn, &cs);
-                } else {
-                    double sd, cd;
-                    sincos_small(dyaw, &sd, &cd);
-                    sn = fma(sn_x, cd, cs_x * sd);
-                    cs = fma(cs_x, cd, -sn_x * sd);
-                }
-                sn_p = sn; cs_p = cs;
-                eval_pass_mixed<WMODE, LAYOUT>(s3, s2, sw, P, n, lane, pt, sn, cs, cam, camf, acc, scratch, exact, jfinite);
-            }
-            if (exact) {  // MRPNP_PREC_FP64, or a point near a clip bound in the mixed pass: exact fp64 clip semantics
-                __syncwarp();
-                if (lane < 4) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v = (lane == i) ? pt[i] : v;
-                    scratch[kScrPt + lane] = v;
-                }
-                __syncwarp();
-                eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 0, false, scratch);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = scratch[kScrSums + i];
-                clip_p = scratch[kScrClip] != 0.0;
-                __syncwarp();
-                const double t0 = (fabs(acc[1]) + fabs(acc[2])) + (fabs(acc[3]) + fabs(acc[4]));
-                const double t1 = (fabs(acc[5]) + fabs(acc[6])) + (fabs(acc[7]) + fabs(acc[8]));
-                const double t2 = (fabs(acc[9]) + fabs(acc[10])) + (fabs(acc[11]) + fabs(acc[12]));
-                jfinite = finite_value((t0 + t1) + (t2 + (fabs(acc[13]) + fabs(acc[14]))));
-            }
-            ++cost_evals;
-            const bool cfinite = finite_value(acc[0]);
-            jfinite = jfinite && cfinite;
-            bool accept = false;
-            if (first) {  // IterationZero
-                first = false;
-                if (!jfinite || !init_ok) { term = kFailure; break; }  // parameters stay at init
-                accept = true;
-                cost = 0.5 * acc[0];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)  // jacobi_scaling from the initial Jacobian only
-                    scale[i] = fast_rcp(1.0 + fast_sqrt(acc[5 + tri(i, i)]));
-            } else {
-                const double cand_cost = cfinite ? 0.5 * acc[0] : kDblMax;
-                // ParameterToleranceReached
-                const double step_norm2 = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2] + delta[3] * delta[3];
-                const double ptol = kParameterTol * (x_norm + kParameterTol);
-                if (step_norm2 <= ptol * ptol) { term = kConvergence; break; }
-                // FunctionToleranceReached (Ceres 1.14: the candidate is not adopted on this exit)
-                const double cost_change = cost - cand_cost;
-                if (fabs(cost_change) <= kFunctionTol * cost) {
-                    term = kConvergence;
-                    if (!(kp.adopt_ftol && cand_cost < cost)) break;
-                    accept = true;  // documented switch: take the candidate, then stop
-                }
-                const double rho = cost_change * fast_rcp1(model_change);
-                if (accept || rho > kMinRelDecrease) {  // HandleSuccessfulStep
-                    if (!jfinite) { term = kFailure; break; }  // re-evaluation at the new point fails in Ceres
-                    const bool stop = accept;
-                    accept = true;
-                    cost = cand_cost;
-                    const double q = 2.0 * rho - 1.0;
-                    radius = fmin(kMaxRadius, radius * fast_rcp(fmax(1.0 / 3.0, 1.0 - q * q * q)));
-                    decrease_factor = 2.0;
-                    reuse_diagonal = false;
-                    if (stop) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { x[i] = pt[i]; g[i] = acc[1 + i]; }
-#pragma unroll
-                        for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
-                        clip_x = clip_p;
-                        sn_x = sn_p; cs_x = cs_p;
-                        break;
-                    }
-                } else {  // HandleUnsuccessfulStep
-                    radius /= decrease_factor;
-                    decrease_factor *= 2.0;
-                }
-            }
-            if (accept) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { x[i] = pt[i]; g[i] = acc[1 + i]; }
-#pragma unroll
-                for (int i = 0; i < 10; ++i) H[i] = acc[5 + i];
-                clip_x = clip_p;
-                sn_x = sn_p; cs_x = cs_p;
-                x_norm = fast_sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-                step_ok = true;
-            }
-            // ---- next trust-region step (invalid steps shrink the radius without a new evaluation) ----
-            bool stop = false;
-            while (true) {
-                // FinalizeIterationAndCheckIfMinimizerCanContinue
-                if (iteration >= max_iter) { term = kNoConvergence; stop = true; break; }
-                if (step_ok) {
-                    const double gmax = fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3])));
-                    if (gmax <= kGradientTol) { term = kConvergence; stop = true; break; }
-                }
-                if (radius <= kMinRadius) { term = kConvergence; stop = true; break; }
-                ++iteration;
-                step_ok = false;
-                // LevenbergMarquardtStrategy::ComputeStep on the column-scaled system
-                double Hs[10], gs[4], A[10], y[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    gs[i] = g[i] * scale[i];
-#pragma unroll
-                    for (int j = i; j < 4; ++j) Hs[tri(i, j)] = H[tri(i, j)] * (scale[i] * scale[j]);
-                }
-                if (!reuse_diagonal) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) diag[i] = fmin(fmax(Hs[tri(i, i)], kMinLmDiag), kMaxLmDiag);
-                }
-                reuse_diagonal = true;
-                const double inv_radius = fast_rcp1(radius);
-#pragma unroll
-                for (int i = 0; i < 10; ++i) A[i] = Hs[i];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) A[tri(i, i)] = fma(diag[i], inv_radius, A[tri(i, i)]);
-                const Ldl4 f = ldl4_factor(A);
-                bool valid = f.ok;
-                if (valid) {
-                    ldl4_solve(f, gs, y);  // step = -y
-                    // model_cost_change = y^T gs - 1/2 y^T Hs y with (Hs + D) y = gs  =>  1/2 (y^T gs + sum_i D_i y_i^2)
-                    double yg = 0.0, ydy = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        yg = fma(y[i], gs[i], yg);
-                        ydy = fma(diag[i] * inv_radius * y[i], y[i], ydy);
-                    }
-                    model_change = 0.5 * (yg + ydy);
-                    valid = (model_change > 0.0) && finite_value(fabs(y[0]) + fabs(y[1]) + fabs(y[2]) + fabs(y[3]));
-                }
-                if (valid) {
-                    num_invalid = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { delta[i] = -y[i] * scale[i]; pt[i] = x[i] + delta[i]; }
-                    break;
-                }
-                // HandleInvalidStep
-                if (++num_invalid >= kMaxInvalidSteps) { term = kFailure; stop = true; break; }
-                radius /= decrease_factor;
-                decrease_factor *= 2.0;
-            }
-            if (stop) break;
-        }
-        bool usable = term != kFailure;  // Summary::IsSolutionUsable (pnp_uncert_cpu.cpp:276)
-
-        // ---------------- pose covariance ----------------
-        double cov[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cov[i] = (i % 5 == 0) ? 1.0 : 0.0;
-        if (kp.cov_mode != MRPNP_COV_NONE && usable) {
-            // H already holds J^T J at the returned x with Ceres masks.  The pipeline covariance
-            // (hessian.py:67-87) differs only when a point is clipped at x or outliers were kept in LM.
-            const bool any_clip = __any_sync(kFull, clip_x);
-            const bool need_pass = kp.cov_mode == MRPNP_COV_PIPELINE && (any_clip || (!compacted && n_inliers < P));
-            if (need_pass) {
-                __syncwarp();
-                if (lane < 4) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v = (lane == i) ? x[i] : v;
-                    scratch[kScrPt + lane] = v;
-                }
-                __syncwarp();
-                eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 1, !compacted, scratch);
-#pragma unroll
-                for (int i = 0; i < 10; ++i) H[i] = scratch[kScrSums + 5 + i];
-                __syncwarp();
-            }
-            if (!spd_inverse4(H, cov)) {  // pnp_uncert.py:79-85 fallback: H := I, object invalid
-#pragma unroll
-                for (int i = 0; i < 16; ++i) cov[i] = (i % 5 == 0) ? 1.0 : 0.0;
-                usable = false;
-            }
-        }
-
-        // ---------------- result row: one coalesced 96-byte store ----------------
-        {
-            float v = 0.f;  // unrolled selects: no dynamically indexed local arrays
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v = (lane == i) ? (float)x[i] : v;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v = (lane == 4 + i) ? (float)cov[i] : v;
-            v = (lane == 20) ? (usable ? 1.f : 0.f) : v;
-            v = (lane == 21) ? (float)iteration : v;
-            v = (lane == 22) ? (float)cost : v;
-            v = (lane == 23) ? (float)radius : v;
-            store_result_row(kp, obj, lane, v);
-            if (kp.result64) {
-                double d = 0.0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) d = (lane == i) ? x[i] : d;
-                d = (lane == 4) ? cost : d;
-                d = (lane == 5) ? radius : d;
-                d = (lane == 6) ? (double)cost_evals : d;
-                d = (lane == 7) ? (double)term : d;
-                if (lane < 8) kp.result64[(size_t)obj * 8 + lane] = d;
-            }
-        }
+        parity = solve_object_exact<MIXED, WMODE, LAYOUT>(kp, obj, slot, bar, parity, scratch, lane);
     }
 
     // self-resetting work counters: the last CTA to finish rearms them for the next launch

@@ -55,6 +55,11 @@ def launch_count(device='cuda'):
     return get_ctx(device).launches
 
 
+def handed_back_count(device='cuda'):
+    """Objects the fp32 fast path handed to the exact fp64 routine so far on this device (synchronises)."""
+    return int(_native.lib().mrpnp_handed_back_count(get_ctx(device).ptr))
+
+
 def make_params(n_obj, n_pts, **kw):
     p = _native.ffi.new('mrpnp_params*')
     _native.lib().mrpnp_default_params(p, n_obj, n_pts)
@@ -93,7 +98,8 @@ def _ptr(t, ctype='float*'):
 def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None, inlier_mask=None, *,
                   layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, istd_thres=0.6,
                   inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
-                  adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False, peers=None, row_offset=0):
+                  adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False, peers=None, row_offset=0,
+                  decision_bands=None):
     """Batched uncertainty-PnP on device tensors -- direct wrapper of ``mrpnp_solve``.
 
     layout 'planar':      coords_3d [N,3,*], coords_2d [N,2,*], weights [N,2|3,*]   (head level)
@@ -138,6 +144,8 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
         inlier_opt_only=int(bool(inlier_opt_only)), max_iterations=int(max_iterations),
         adopt_candidate_on_ftol=int(bool(adopt_candidate_on_ftol)),
         z_min=float(z_min), std_scale=float(std_scale), istd_thres=float(istd_thres))
+    if decision_bands is not None:   # (band_first, band_rel, band_mix) of mrpnp_params; the defaults are the product's
+        p.band_first, p.band_rel, p.band_mix = (float(v) for v in decision_bands)
     if peers:
         if len(peers) > C['MRPNP_MAX_PEERS']:
             raise ValueError('at most %d peers' % C['MRPNP_MAX_PEERS'])

@@ -96,15 +96,10 @@ def lm_single(coord_2d, coord_3d, wgt, cam_mat, init_pose, clips, with_pose_cov=
     return result_val[0] > 0, result_pose, result_cov, result_tr[0]
 
 
-def lm_batch(coords_2d, coords_3d, wgt, cam_mats, init_pose, clips, inlier_mask=None, full_w=False,
-             with_pose_cov=False, threads=1):
-    """Batched LM from a given init and a given inlier mask (the LM-parity contract).
-
-    coords_2d (N,P,2), coords_3d (N,P,3), wgt (N,P,2|3), cam_mats (N|1,3,3), init_pose (N,4),
-    clips (N|1,5), inlier_mask (N,P) bool or None.  Inliers are compacted per object exactly like
-    pnp_uncert_cpu.py:24-27,62-66 (boolean-mask indexing keeps point order).
-    Returns dict(val, pose, cov, tr, stats[N,4]=(iters, cost evals, jac evals, termination), cost).
-    """
+def pack_lm_batch(coords_2d, coords_3d, wgt, cam_mats, init_pose, clips, inlier_mask=None, full_w=False):
+    """The fp64 buffers ``pnp_uncert_batch`` reads: inliers compacted per object exactly like
+    pnp_uncert_cpu.py:24-27,62-66 (boolean-mask indexing keeps point order), K and clips broadcast.  Separate from
+    the solve so that a timing loop (bench.py's CPU legs) can pack once and time the native calls only."""
     n, p = coords_2d.shape[:2]
     wc = 3 if full_w else 2
     if inlier_mask is None:
@@ -114,12 +109,18 @@ def lm_batch(coords_2d, coords_3d, wgt, cam_mats, init_pose, clips, inlier_mask=
     off = np.zeros(n, np.int64)
     off[1:] = np.cumsum(pn[:-1])
     flat = inlier_mask.reshape(-1)
-    p2 = _c64(np.asarray(coords_2d).reshape(-1, 2)[flat])
-    p3 = _c64(np.asarray(coords_3d).reshape(-1, 3)[flat])
-    w = _c64(np.asarray(wgt).reshape(-1, wc)[flat])
-    k = _c64(np.broadcast_to(np.asarray(cam_mats, np.float64).reshape(-1, 9), (n, 9)))
-    cl = _c64(np.broadcast_to(np.asarray(clips, np.float64).reshape(-1, 5), (n, 5)))
-    init_pose = _c64(init_pose)
+    return dict(
+        n=n, full_w=bool(full_w), pn=pn, off=off,
+        p2=_c64(np.asarray(coords_2d).reshape(-1, 2)[flat]), p3=_c64(np.asarray(coords_3d).reshape(-1, 3)[flat]),
+        w=_c64(np.asarray(wgt).reshape(-1, wc)[flat]),
+        k=_c64(np.broadcast_to(np.asarray(cam_mats, np.float64).reshape(-1, 9), (n, 9))),
+        cl=_c64(np.broadcast_to(np.asarray(clips, np.float64).reshape(-1, 5), (n, 5))), init=_c64(init_pose))
+
+
+def lm_batch_packed(pk, with_pose_cov=False, threads=1):
+    """``pnp_uncert_batch`` on the buffers of :func:`pack_lm_batch`.  Returns dict(val, pose, cov, tr,
+    stats[N,4]=(iters, cost evals, jac evals, termination), cost)."""
+    n = pk['n']
     val = np.zeros(n, np.int32)
     pose = np.zeros((n, 4), np.float64)
     cov = np.tile(np.eye(4), (n, 1, 1)) if with_pose_cov else None
@@ -127,11 +128,23 @@ def lm_batch(coords_2d, coords_3d, wgt, cam_mats, init_pose, clips, inlier_mask=
     stats = np.zeros((n, 4), np.int32)
     cost = np.zeros(n, np.float64)
     lib().pnp_uncert_batch(
-        _dp(p2), _dp(p3), _dp(w), _dp(k), _dp(init_pose), ffi.cast('int*', val.ctypes.data), _dp(pose),
-        _dp(cov) if with_pose_cov else ffi.NULL, _dp(tr), ffi.cast('int*', pn.ctypes.data),
-        ffi.cast('long long*', off.ctypes.data), _dp(cl), n, int(full_w),
+        _dp(pk['p2']), _dp(pk['p3']), _dp(pk['w']), _dp(pk['k']), _dp(pk['init']), ffi.cast('int*', val.ctypes.data),
+        _dp(pose), _dp(cov) if with_pose_cov else ffi.NULL, _dp(tr), ffi.cast('int*', pk['pn'].ctypes.data),
+        ffi.cast('long long*', pk['off'].ctypes.data), _dp(pk['cl']), n, int(pk['full_w']),
         ffi.cast('int*', stats.ctypes.data), _dp(cost), int(threads))
     return dict(val=val > 0, pose=pose, cov=cov, tr=tr, stats=stats, cost=cost)
+
+
+def lm_batch(coords_2d, coords_3d, wgt, cam_mats, init_pose, clips, inlier_mask=None, full_w=False,
+             with_pose_cov=False, threads=1):
+    """Batched LM from a given init and a given inlier mask (the LM-parity contract).
+
+    coords_2d (N,P,2), coords_3d (N,P,3), wgt (N,P,2|3), cam_mats (N|1,3,3), init_pose (N,4),
+    clips (N|1,5), inlier_mask (N,P) bool or None.
+    Returns dict(val, pose, cov, tr, stats[N,4]=(iters, cost evals, jac evals, termination), cost).
+    """
+    return lm_batch_packed(pack_lm_batch(coords_2d, coords_3d, wgt, cam_mats, init_pose, clips, inlier_mask, full_w),
+                           with_pose_cov=with_pose_cov, threads=threads)
 
 
 def ceres_tutorial_trace(problem):

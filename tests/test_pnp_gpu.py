@@ -331,7 +331,7 @@ def test_full_size_properties(cuda_lib, precision):
     pnp.solve_batched(c3[:64], c2[:64], logstd[:64], cam, rng_t, init_pose=dev(init)[:64], precision='mixed')
     assert pnp.launch_count() == before + 1
     pnp.solve_batched(c3[:64], c2[:64], logstd[:64], cam, rng_t, init_pose=dev(init)[:64], precision='fast')
-    assert pnp.launch_count() == before + 3   # fast kernel + the follow-up launch over its redo list
+    assert pnp.launch_count() == before + 2   # one launch each: handed-back objects are solved inside the fast kernel
 
 
 @pytest.mark.parametrize('cfg,weights', [(3, 'full'), (2, 'diag')])
@@ -543,7 +543,7 @@ def test_fused_entry_through_pose_head_and_roi_head(cuda_lib):
         out = roi_head.forward_3d(torch.randn(8, 256, 14, 14, device='cuda'), dev(raw['rois'][:8]), dev(b['labels'][:8]),
                                   torch.randn(8, 16, device='cuda'), dev(raw['dims'][:8]), dev(raw['dims_var'][:8]),
                                   cam, (375, 1242), fused=True)
-    assert pnp.launch_count() == before + 2   # one solve: the fast kernel + its follow-up launch over the redo list
+    assert pnp.launch_count() == before + 1   # one solve = one launch (handed-back objects are solved inside it)
     assert out['t_vec_pred'].shape == (8, 3) and out['pose_cov_calib'].shape == (8, 4, 4)
 
 
