@@ -104,7 +104,16 @@ typedef struct mrpnp_params {
      * change relative to the cost (two independently rounded fp32 sums); later steps: band_rel |change| +
      * band_mix sqrt(model change * cost).  mrpnp_default_params sets 8e-6, 4e-3, 2e-6; 0 disables a term. */
     float band_first, band_rel, band_mix;
-    float reserved3;
+    /* Reprojection-threshold consensus after the start pose -- the deterministic counterpart of the inlier refinement
+     * the reference gets from cv2.solvePnPRansac (pnp_uncert_cpu.py:34-51): with the start pose (on-device linear
+     * initialiser or init_pose) as the model, an istd inlier whose reprojection error exceeds the threshold is dropped,
+     * provided more than four points survive; LM, the covariance and inlier_out then see the survivors only, and the
+     * linear initialiser is run again on them.  ransac_thres: DEVICE pointer to [N] thresholds in pixels
+     * (epnp_ransac_thres of pnp_uncert.py:9; NULL = off).  mrpnp_solve_dense instead takes ransac_ratio
+     * (epnp_ransac_thres_ratio, uncert_prop_pnp_optimizer.py:86-88: threshold = ratio * (v[last row] - v[first row]);
+     * 0 = off).  Needs inlier_opt_only = 1. */
+    float ransac_ratio;
+    const float* ransac_thres;
 } mrpnp_params;
 
 typedef struct mrpnp_ctx mrpnp_ctx;
@@ -267,6 +276,14 @@ int mrpnp_solve_6dof(mrpnp_ctx* ctx, const mrpnp_params* p,
                      const float* coords_3d, const float* coords_2d, const float* weights,
                      const float* cam_mats, const float* uv_range, const float* init_pose6,
                      const uint32_t* inlier_in, double* result, void* stream);
+
+/* The reference's native entry point itself, GPU-backed: the signature of monorun/ops/least_squares/src/ext.h:1-13, so
+ * that the reference's own binding (pnp_uncert_cpu.py:102-106: ``lib.pnp_uncert(...)`` on numpy fp64 buffers, one object
+ * per call) can load this library unchanged.  Host pointers; clips = z_min, u_min, u_max, v_min, v_max; every point
+ * handed in is used; result_cov (4x4, may be NULL) is Ceres' covariance (pnp_uncert_cpu.cpp:279-291); no return code:
+ * success is *result_val != 0.  pn is limited to MRPNP_MAX_POINTS.  Runs on the current CUDA device, fp64 precision. */
+void pnp_uncert(double* pts2d, double* pts3d, double* wgt2d, double* K, double* init_pose, int* result_val,
+                double* result_pose, double* result_cov, double* result_tr, int pn, double* clips);
 
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);

@@ -74,7 +74,8 @@ int plan_launch(const mrpnp_ctx* ctx, const mrpnp_params* p, int precision, cons
     const int wc = p->weight_mode == MRPNP_W_FULL ? 3 : 2;
     const size_t slot_bytes = ((size_t)(5 + wc) * p->n_pts * sizeof(float) + 15) & ~size_t(15);
     const size_t header = precision == MRPNP_PREC_FAST ? mrpnp::kFastHeaderBytes : mrpnp::kWarpHeaderBytes;
-    int groups = (int)std::min<size_t>(mrpnp::kMaxWarpsPerCta, (size_t)ctx->max_smem_optin / (slot_bytes + header));
+    const int max_warps = precision == MRPNP_PREC_FAST ? mrpnp::kFastMaxWarps : mrpnp::kMaxWarpsPerCta;
+    int groups = (int)std::min<size_t>(max_warps, (size_t)ctx->max_smem_optin / (slot_bytes + header));
     if (groups < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for shared memory%s");
     // keep every SM busy before stacking objects on one SM: at small N spread objects over CTAs
     const int per_sm = (p->n_obj + ctx->num_sms - 1) / ctx->num_sms;
@@ -211,6 +212,8 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     kp.stats = ctx->stats;
     kp.band_first = p->band_first; kp.band_rel = p->band_rel; kp.band_mix = p->band_mix;
     kp.global_interleaved = (precision == MRPNP_PREC_FAST && p->layout == MRPNP_LAYOUT_INTERLEAVED) ? 1 : 0;
+    kp.ransac_thres = (!dense && p->inlier_opt_only) ? p->ransac_thres : nullptr;
+    kp.ransac_ratio = (dense && p->inlier_opt_only) ? p->ransac_ratio : 0.f;
     kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride;
     kp.cov_mode = p->cov_mode; kp.init_mode = p->init_mode; kp.inlier_opt_only = p->inlier_opt_only;
     kp.max_iter = p->max_iterations; kp.adopt_ftol = p->adopt_candidate_on_ftol;
@@ -548,6 +551,59 @@ int mrpnp_solve_dense(mrpnp_ctx* ctx, const mrpnp_params* p, const mrpnp_dense_p
     // alignment for the TMA path is decided on the two streamed tensors; `rois` rides in the coords_2d slot
     return solve_device(ctx, &q, noc_pred, rois, proj_logstd, cam_mats, uv_range, init_pose, nullptr, result,
                         inlier_out, nullptr, static_cast<cudaStream_t>(stream), &da);
+}
+
+// The reference's own native entry point (monorun/ops/least_squares/src/ext.h:1-13), GPU-backed: one object, host fp64
+// buffers, no return code -- success is *result_val != 0 (pnp_uncert_cpu.cpp:276, :287).  A process-wide context on the
+// current CUDA device serves these calls (the reference op is re-entrant; calls here are serialised by a mutex).  The
+// solve runs as MRPNP_PREC_FP64 on every point handed in (the reference passes the points it wants solved,
+// pnp_uncert_cpu.py:62-66), Ceres-style covariance when result_cov is not NULL (pnp_uncert_cpu.cpp:279-291).
+void pnp_uncert(double* pts2d, double* pts3d, double* wgt2d, double* K, double* init_pose, int* result_val,
+                double* result_pose, double* result_cov, double* result_tr, int pn, double* clips) {
+    static std::mutex mu;
+    static mrpnp_ctx* ctx = nullptr;
+    static float* dbuf = nullptr;   // device: [pts3d 3P | pts2d 2P | wgt 2P | cam 9 | range 4 | init 4 | result 24] + result64 after it
+    static float* hbuf = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (result_val) *result_val = 0;
+    for (int i = 0; i < 4; ++i) result_pose[i] = init_pose[i];   // pnp_uncert_cpu.cpp:259
+    if (pn < 4 || pn > MRPNP_MAX_POINTS) { fail(MRPNP_ERR_ARG, "pnp_uncert: pn outside [4, 1024]%s"); return; }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if (!ctx && mrpnp_create(&ctx, dev) != MRPNP_OK) return;
+    const size_t cap = 7 * MRPNP_MAX_POINTS + 9 + 4 + 4 + MRPNP_RESULT_STRIDE + 16;
+    if (!dbuf && (cudaMalloc(&dbuf, cap * sizeof(float) + 64) != cudaSuccess || cudaMallocHost(&hbuf, cap * sizeof(float) + 64) != cudaSuccess)) return;
+    const size_t P = (size_t)pn;
+    float* h3 = hbuf; float* h2 = h3 + 3 * P; float* hw = h2 + 2 * P; float* hc = hw + 2 * P; float* hr = hc + 9; float* hi = hr + 4;
+    for (size_t i = 0; i < 3 * P; ++i) h3[i] = (float)pts3d[i];
+    for (size_t i = 0; i < 2 * P; ++i) { h2[i] = (float)pts2d[i]; hw[i] = (float)wgt2d[i]; }
+    for (int i = 0; i < 9; ++i) hc[i] = (float)K[i];
+    for (int i = 0; i < 4; ++i) { hr[i] = (float)clips[1 + i]; hi[i] = (float)init_pose[i]; }
+    const size_t n_in = 7 * P + 17;
+    float* d_res = dbuf + ((n_in + 3) & ~size_t(3));
+    double* d_res64 = reinterpret_cast<double*>(dbuf + ((n_in + 3) & ~size_t(3)) + MRPNP_RESULT_STRIDE);   // 8-byte aligned: offsets are multiples of 4 floats
+    mrpnp_params p;
+    mrpnp_default_params(&p, 1, pn);
+    p.layout = MRPNP_LAYOUT_INTERLEAVED;
+    p.weight_mode = MRPNP_W_ISTD;
+    p.precision = MRPNP_PREC_FP64;
+    p.cov_mode = result_cov ? MRPNP_COV_CERES : MRPNP_COV_NONE;
+    p.init_mode = MRPNP_INIT_GIVEN;
+    p.istd_thres = 0.f;   // every point handed in takes part
+    p.z_min = (float)clips[0];
+    cudaStream_t st = nullptr;
+    if (cudaMemcpyAsync(dbuf, hbuf, n_in * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) return;
+    if (mrpnp_solve(ctx, &p, dbuf, dbuf + 3 * P, dbuf + 5 * P, dbuf + 7 * P, dbuf + 7 * P + 9, dbuf + 7 * P + 13, nullptr, d_res, nullptr,
+                    d_res64, st) != MRPNP_OK) return;
+    float row[MRPNP_RESULT_STRIDE];
+    double r64[8];
+    if (cudaMemcpyAsync(row, d_res, sizeof(row), cudaMemcpyDeviceToHost, st) != cudaSuccess) return;
+    if (cudaMemcpyAsync(r64, d_res64, sizeof(r64), cudaMemcpyDeviceToHost, st) != cudaSuccess) return;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return;
+    for (int i = 0; i < 4; ++i) result_pose[i] = r64[i];
+    if (result_cov) for (int i = 0; i < 16; ++i) result_cov[i] = (double)row[4 + i];
+    if (result_tr) *result_tr = r64[5];
+    if (result_val) *result_val = row[20] > 0.5f ? 1 : 0;
 }
 
 // Host-buffer entry: objects are cut into chunks; chunk i+1's host->device copies run on the other

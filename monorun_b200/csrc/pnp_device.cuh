@@ -65,6 +65,10 @@ struct KParams {
     unsigned long long* stats;   // [0] running total of handed-back objects (mrpnp_handed_back_count)
     float band_first, band_rel, band_mix;   // half-widths of the decision bands (mrpnp_params)
     int global_interleaved;   // the tensors in global memory are [N,P,C] although the slot is planar (staging transposes)
+    // reprojection-threshold consensus after the start pose (replaces the inlier refinement of cv2.solvePnPRansac,
+    // pnp_uncert_cpu.py:34-51): per-object threshold in pixels, or (fused head entry) ratio * RoI height
+    const float* ransac_thres;
+    float ransac_ratio;
     // exact kernels: optional work list (NULL = objects 0..n_obj-1)
     const int* work_list;
     int* work_count;
@@ -657,12 +661,29 @@ __device__ __forceinline__ bool chol_solve_dense(double A[N][N], const double b[
 }
 
 // fp32 accumulation of the (well-scaled, normalised-coordinate) normal equations, fp64 solves.
+// With a `prior` pose (yaw, t) and gate2 > 0 only the points whose reprojection error at the prior is within sqrt(gate2)
+// pixels take part: the trimmed fits of the consensus stage (see consensus_prune).
 template <int WMODE, int LAYOUT>
 __device__ __forceinline__ bool linear_init_impl(const float* __restrict__ s3, const float* __restrict__ s2,
                                             const float* __restrict__ sw, int P, const TeamRows& rows, int lane,
-                                            const Camera<float>& cam, float* scratch, double* x) {
+                                            const Camera<float>& cam, float* scratch, double* x,
+                                            const float* prior = nullptr, float gate2 = 0.f) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     const float ifx = 1.f / cam.fx, ify = 1.f / cam.fy;
+    const bool gated = prior != nullptr && gate2 > 0.f;
+    float psn = 0.f, pcs = 1.f, ptx = 0.f, pty = 0.f, ptz = 1.f;
+    if (gated) {
+        sincosf(prior[0], &psn, &pcs);
+        ptx = prior[1]; pty = prior[2]; ptz = prior[3];
+    }
+    __syncwarp();
+    // reprojection error^2 of point (X, Y, Z) -> (u, v) at the prior
+    auto outside = [&](float X, float Y, float Z, float u, float v) {
+        const float iz = 1.f / fmaxf(fmaf(pcs, Z, fmaf(-psn, X, ptz)), cam.z_min);
+        const float du = fmaf(cam.fx, fmaf(pcs, X, fmaf(psn, Z, ptx)) * iz, cam.cx) - u;
+        const float dv = fmaf(cam.fy, (Y + pty) * iz, cam.cy) - v;
+        return !(fmaf(du, du, dv * dv) <= gate2);
+    };
     // ---- stage A: 5 unknowns: 15 matrix entries + 5 rhs = 20 sums -> two transposed reductions ----
     float m[16], r[16];
 #pragma unroll
@@ -673,6 +694,7 @@ __device__ __forceinline__ bool linear_init_impl(const float* __restrict__ s3, c
         const int p = rows.point(gi, 0, 1, lane, valid);
         if (!valid) continue;
         const float X = s3[sidx<LAYOUT, 3>(p, 0, P)], Y = s3[sidx<LAYOUT, 3>(p, 1, P)], Z = s3[sidx<LAYOUT, 3>(p, 2, P)];
+        if (gated && outside(X, Y, Z, s2[sidx<LAYOUT, 2>(p, 0, P)], s2[sidx<LAYOUT, 2>(p, 1, P)])) continue;
         const float un = (s2[sidx<LAYOUT, 2>(p, 0, P)] - cam.cx) * ifx;
         const float vn = (s2[sidx<LAYOUT, 2>(p, 1, P)] - cam.cy) * ify;
         const float wu = sw[sidx<LAYOUT, WC>(p, 0, P)] * cam.fx, wv = sw[sidx<LAYOUT, WC>(p, WC - 1, P)] * cam.fy;
@@ -716,6 +738,7 @@ __device__ __forceinline__ bool linear_init_impl(const float* __restrict__ s3, c
         const int p = rows.point(gi, 0, 1, lane, valid);
         if (!valid) continue;
         const float X = s3[sidx<LAYOUT, 3>(p, 0, P)], Y = s3[sidx<LAYOUT, 3>(p, 1, P)], Z = s3[sidx<LAYOUT, 3>(p, 2, P)];
+        if (gated && outside(X, Y, Z, s2[sidx<LAYOUT, 2>(p, 0, P)], s2[sidx<LAYOUT, 2>(p, 1, P)])) continue;
         const float un = (s2[sidx<LAYOUT, 2>(p, 0, P)] - cam.cx) * ifx;
         const float vn = (s2[sidx<LAYOUT, 2>(p, 1, P)] - cam.cy) * ify;
         const float wu = sw[sidx<LAYOUT, WC>(p, 0, P)] * cam.fx, wv = sw[sidx<LAYOUT, WC>(p, WC - 1, P)] * cam.fy;
@@ -747,21 +770,111 @@ __device__ __forceinline__ bool linear_init_impl(const float* __restrict__ s3, c
 }
 
 // Out-of-line wrapper used by the warp-per-object kernel (keeps its hot code small); pose -> scratch[kScrPt..].
+// gate > 0: trimmed fit around the pose currently in scratch[kScrPt..] (see linear_init_impl).
 template <int WMODE, int LAYOUT>
 __device__ __noinline__ bool linear_init(const KParams& kp, int obj, const float* __restrict__ slot, int n, int lane,
-                                         double* scratch) {
+                                         double* scratch, float gate = 0.f) {
     const int P = kp.n_pts;
     const Camera<float> cam = load_camera<float>(kp, obj);
     double x[4];
-    const bool ok = linear_init_impl<WMODE, LAYOUT>(slot, slot + 3 * P, slot + 5 * P, P, TeamRows(n, 0, 0, 0, 1), lane,
-                                                    cam, reinterpret_cast<float*>(scratch), x);
+    float prior[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) prior[i] = gate > 0.f ? (float)scratch[kScrPt + i] : 0.f;
     __syncwarp();
-    if (lane == 0) {
+    const bool ok = linear_init_impl<WMODE, LAYOUT>(slot, slot + 3 * P, slot + 5 * P, P, TeamRows(n, 0, 0, 0, 1), lane,
+                                                    cam, reinterpret_cast<float*>(scratch), x, gate > 0.f ? prior : nullptr,
+                                                    gate * gate);
+    __syncwarp();
+    if (lane == 0 && (ok || !(gate > 0.f))) {   // a failed TRIMMED fit leaves the pose it started from in place
 #pragma unroll
         for (int i = 0; i < 4; ++i) scratch[kScrPt + i] = ok ? (double)(float)x[i] : 0.0;  // fp32 hand-over; .py:119-125
     }
     __syncwarp();
     return ok;
+}
+
+// ------------------------------------------------------------------ reprojection-threshold consensus
+// The reference starts LM from cv2.solvePnPRansac(EPNP, 30 iterations, reprojectionError = thr) and, when more than four
+// points agree with the returned model, keeps only those: LM, the covariance and the returned mask then see the
+// RANSAC survivors of the istd inliers (pnp_uncert_cpu.py:34-51; thr = 0.2 x RoI height,
+// uncert_prop_pnp_optimizer.py:86-88).  OpenCV's random sampling is not reproduced; the deterministic counterpart here
+// takes the START POSE as the model (the on-device linear initialiser, or the caller's init_pose): a compacted inlier
+// whose reprojection error exceeds thr pixels is dropped, provided more than four survive.  The slot is compacted again
+// in place (order preserved) and the packed mask in kp.inl_out is narrowed accordingly.
+// pose: 4 floats (yaw, t); returns the new inlier count (== n if nothing changes).
+template <int WMODE, int LAYOUT>
+__device__ __noinline__ int consensus_prune(const KParams& kp, int obj, float* slot, int n, int lane, const float* pose, float thr) {
+    constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
+    const int P = kp.n_pts;
+    float* s3 = slot;
+    float* s2 = slot + 3 * P;
+    float* sw = slot + 5 * P;
+    const Camera<float> cam = load_camera<float>(kp, obj);
+    float sn, cs;
+    sincosf(pose[0], &sn, &cs);
+    const float tx = pose[1], ty = pose[2], tz = pose[3], thr2 = thr * thr;
+    const int rows = (n + 31) >> 5;   // <= 32 because n <= MRPNP_MAX_POINTS
+    uint32_t keep_word = 0u;          // lane r: survivors of compacted row r
+    int count = 0;
+    for (int r = 0; r < rows; ++r) {
+        const int j = r * 32 + lane;
+        const bool live = j < n;
+        const int jc = live ? j : 0;
+        const float X = s3[sidx<LAYOUT, 3>(jc, 0, P)], Y = s3[sidx<LAYOUT, 3>(jc, 1, P)], Z = s3[sidx<LAYOUT, 3>(jc, 2, P)];
+        const float zc = fmaf(cs, Z, fmaf(-sn, X, tz));
+        const float iz = 1.f / fmaxf(zc, cam.z_min);   // pnp_uncert_cpu.cpp:36 projection rule
+        const float du = fmaf(cam.fx, fmaf(cs, X, fmaf(sn, Z, tx)) * iz, cam.cx) - s2[sidx<LAYOUT, 2>(jc, 0, P)];
+        const float dv = fmaf(cam.fy, (Y + ty) * iz, cam.cy) - s2[sidx<LAYOUT, 2>(jc, 1, P)];
+        const bool keep = live && (fmaf(du, du, dv * dv) <= thr2);   // false for NaN
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (lane == r) keep_word = m;
+        count += __popc(m);
+    }
+    if (count <= 4 || count == n) return n;   // pnp_uncert_cpu.py:43: the refinement applies only if > 4 survive
+    int base = 0;
+    for (int r = 0; r < rows; ++r) {
+        const int j = r * 32 + lane;
+        const int jc = j < n ? j : 0;
+        float v3[3], v2[2], w[WC];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v3[c] = s3[sidx<LAYOUT, 3>(jc, c, P)];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) v2[c] = s2[sidx<LAYOUT, 2>(jc, c, P)];
+#pragma unroll
+        for (int c = 0; c < WC; ++c) w[c] = sw[sidx<LAYOUT, WC>(jc, c, P)];
+        const unsigned m = __shfl_sync(kFull, keep_word, r);
+        __syncwarp();   // the reads of this row happen before any lane's compacted writes
+        if ((m >> lane) & 1u) {
+            const int d = base + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s3[sidx<LAYOUT, 3>(d, c, P)] = v3[c];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) s2[sidx<LAYOUT, 2>(d, c, P)] = v2[c];
+#pragma unroll
+            for (int c = 0; c < WC; ++c) sw[sidx<LAYOUT, WC>(d, c, P)] = w[c];
+        }
+        base += __popc(m);
+    }
+    __syncwarp();
+    if (kp.inl_out) {
+        // narrow the packed mask: the i-th set bit of the old mask keeps its bit iff compacted point i survived
+        const int rows_p = (P + 31) >> 5;
+        uint32_t* words = kp.inl_out + (size_t)obj * rows_p;
+        const uint32_t mine = lane < rows_p ? words[lane] : 0u;   // written by this very lane during compaction
+        uint32_t out = 0u;
+        int off = 0;
+        for (int k = 0; k < rows_p; ++k) {
+            const uint32_t w = __shfl_sync(kFull, mine, k);
+            const uint32_t lo = __shfl_sync(kFull, keep_word, (off >> 5) & 31), hi = __shfl_sync(kFull, keep_word, ((off >> 5) + 1) & 31);
+            const uint32_t bits = __funnelshift_r(lo, hi, off & 31);   // survivors of compacted points off .. off + 31
+            const int rank = __popc(w & ((1u << lane) - 1u));
+            const unsigned nw = __ballot_sync(kFull, ((w >> lane) & 1u) && ((bits >> rank) & 1u));
+            if (lane == k) out = nw;
+            off += __popc(w);
+        }
+        if (lane < rows_p) words[lane] = out;
+    }
+    return count;
 }
 
 }  // namespace mrpnp

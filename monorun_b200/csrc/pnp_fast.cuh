@@ -41,6 +41,11 @@ namespace mrpnp {
 
 // ------------------------------------------------------------------ packed / scalar arithmetic behind one set of names
 __device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// Three per-point operands: measured on B200 (tools/microbench5.cu) an FFMA2 reading three register PAIRS issues every
+// 3.9 cycles per scheduler -- slower than the two scalar FFMAs (2 x 1.56) it replaces -- while a packed instruction with
+// a scalar-broadcast operand or only two operands (FMUL2 / FADD2) issues every 2.0 (against 2 x 1.19 scalar).
+__device__ __forceinline__ float2 vfma3(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float vfma3(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 vneg(float2 a) { return make_float2(-a.x, -a.y); }  // folds into operand modifiers
@@ -140,20 +145,20 @@ constexpr unsigned kNegatedSums = (1u << 3) | (1u << 7) | (1u << 10) | (1u << 12
 template <int WMODE, class V>
 __device__ __forceinline__ void accumulate_normal(V a[15], V qx, V qz, V xn, V yn, V iz, V v0, V v1, V m00, V m01, V m11) {
     const V h0 = vmul(iz, v0), h1 = vmul(iz, v1);
-    const V ju = vfma(xn, qx, qz), jv = vmul(yn, qx);
-    a[0] = vfma(ju, h0, vfma(jv, h1, a[0]));
+    const V ju = vfma3(xn, qx, qz), jv = vmul(yn, qx);
+    a[0] = vfma3(ju, h0, vfma3(jv, h1, a[0]));
     a[1] = vadd(a[1], h0);
     a[2] = vadd(a[2], h1);
-    a[3] = vfma(xn, h0, vfma(yn, h1, a[3]));
+    a[3] = vfma3(xn, h0, vfma3(yn, h1, a[3]));
     const V iz2 = vmul(iz, iz);
     const V n00 = vmul(iz2, m00), n11 = vmul(iz2, m11);
     V p00, p10, q03, q13;
     if (WMODE == MRPNP_W_FULL) {
         const V n01 = vmul(iz2, m01);
-        p00 = vfma(n00, ju, vmul(n01, jv));
-        p10 = vfma(n01, ju, vmul(n11, jv));
-        q03 = vfma(n00, xn, vmul(n01, yn));
-        q13 = vfma(n01, xn, vmul(n11, yn));
+        p00 = vfma3(n00, ju, vmul(n01, jv));
+        p10 = vfma3(n01, ju, vmul(n11, jv));
+        q03 = vfma3(n00, xn, vmul(n01, yn));
+        q13 = vfma3(n01, xn, vmul(n11, yn));
         a[9] = vadd(a[9], n01);
     } else {
         p00 = vmul(n00, ju);
@@ -161,15 +166,15 @@ __device__ __forceinline__ void accumulate_normal(V a[15], V qx, V qz, V xn, V y
         q03 = vmul(n00, xn);
         q13 = vmul(n11, yn);
     }
-    a[4] = vfma(ju, p00, vfma(jv, p10, a[4]));
+    a[4] = vfma3(ju, p00, vfma3(jv, p10, a[4]));
     a[5] = vadd(a[5], p00);
     a[6] = vadd(a[6], p10);
-    a[7] = vfma(ju, q03, vfma(jv, q13, a[7]));
+    a[7] = vfma3(ju, q03, vfma3(jv, q13, a[7]));
     a[8] = vadd(a[8], n00);
     a[10] = vadd(a[10], q03);
     a[11] = vadd(a[11], n11);
     a[12] = vadd(a[12], q13);
-    a[13] = vfma(xn, q03, vfma(yn, q13, a[13]));
+    a[13] = vfma3(xn, q03, vfma3(yn, q13, a[13]));
 }
 
 // Running clip / extent observations of a pass.
@@ -213,8 +218,8 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
             // weights -> M = F W^T W F, stored in place of W for the later passes
             if (WMODE == MRPNP_W_FULL) {
                 const V wxx = m00, wxy = m01, wyy = m11;
-                m00 = vmul(vfma(wxx, wxx, vmul(wxy, wxy)), L::bc(u.cam.fx * u.cam.fx));
-                m11 = vmul(vfma(wyy, wyy, vmul(wxy, wxy)), L::bc(u.cam.fy * u.cam.fy));
+                m00 = vmul(vfma3(wxx, wxx, vmul(wxy, wxy)), L::bc(u.cam.fx * u.cam.fx));
+                m11 = vmul(vfma3(wyy, wyy, vmul(wxy, wxy)), L::bc(u.cam.fy * u.cam.fy));
                 m01 = vmul(vmul(wxy, vadd(wxx, wyy)), L::bc(u.cam.fx * u.cam.fy));
             } else {
                 const V t0 = vmul(m00, L::bc(u.cam.fx)), t1 = vmul(m11, L::bc(u.cam.fy));
@@ -269,13 +274,13 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
         f.my = fmaxf(f.my, L::habsmax(vsub(yn, L::bc(u.win.ymid))));
         V v0, v1;
         if (WMODE == MRPNP_W_FULL) {
-            v0 = vfma(m00, e0, vmul(m01, e1));
-            v1 = vfma(m01, e0, vmul(m11, e1));
+            v0 = vfma3(m00, e0, vmul(m01, e1));
+            v1 = vfma3(m01, e0, vmul(m11, e1));
         } else {
             v0 = vmul(m00, e0);
             v1 = vmul(m11, e1);
         }
-        a[14] = vfma(e0, v0, vfma(e1, v1, a[14]));
+        a[14] = vfma3(e0, v0, vfma3(e1, v1, a[14]));
         accumulate_normal<WMODE, V>(a, qx, qz, xn, yn, iz, v0, v1, m00, m01, m11);
     } else {
         const DeltaStep& s = u.step;
@@ -287,7 +292,7 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
         const V Dx = vfma(L::bc(s.ncdm1), qx, vfma(L::bc(s.sd), qz, L::bc(s.dtx)));
         const V Dz = vfma(L::bc(s.ncdm1), qz, vfma(L::bc(-s.sd), qx, L::bc(s.dtz)));
         const V izo = vrcp(vsub(z1, Dz));
-        const V Du = vmul(vfma(vneg(xnp), Dz, Dx), izo);
+        const V Du = vmul(vfma3(vneg(xnp), Dz, Dx), izo);
         const V Dv = vmul(vfma(vneg(ynp), Dz, L::bc(s.dty)), izo);
         if (KIND == kPassUndo) {  // roll a rejected candidate back: e = e' - De (one fp32 rounding away from the old e)
             if (L::kWidth == 2 || live) { L::st(s2 + idx, vsub(o0, Du)); L::st(s2 + P + idx, vsub(o1, Dv)); }
@@ -302,10 +307,10 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
         }
         V v0, v1, d0, d1;
         if (WMODE == MRPNP_W_FULL) {
-            v0 = vfma(m00, e0, vmul(m01, e1));
-            v1 = vfma(m01, e0, vmul(m11, e1));
-            d0 = vfma(m00, Du, vmul(m01, Dv));
-            d1 = vfma(m01, Du, vmul(m11, Dv));
+            v0 = vfma3(m00, e0, vmul(m01, e1));
+            v1 = vfma3(m01, e0, vmul(m11, e1));
+            d0 = vfma3(m00, Du, vmul(m01, Dv));
+            d1 = vfma3(m01, Du, vmul(m11, Dv));
         } else {
             v0 = vmul(m00, e0);
             v1 = vmul(m11, e1);
@@ -313,7 +318,7 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
             d1 = vmul(m11, Dv);
         }
         // |r'|^2 - |r|^2 = De^T (2 M e' - M De)
-        a[14] = vfma(Du, vfma(L::bc(2.f), v0, vneg(d0)), vfma(Dv, vfma(L::bc(2.f), v1, vneg(d1)), a[14]));
+        a[14] = vfma3(Du, vfma(L::bc(2.f), v0, vneg(d0)), vfma3(Dv, vfma(L::bc(2.f), v1, vneg(d1)), a[14]));
         accumulate_normal<WMODE, V>(a, qx, qz, xnp, ynp, izp, v0, v1, m00, m01, m11);
     }
 }
@@ -419,7 +424,11 @@ __device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, 
 #pragma unroll 1
         for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassFirst, float2>(slot, P, idx, true, u, a, f);
     } else {
-#pragma unroll 2
+#ifndef MRPNP_EXP_DELTA_UNROLL
+#define MRPNP_EXP_DELTA_UNROLL 1   // 2 measured 4 % slower (instruction cache)
+#endif
+        constexpr int kDeltaUnroll = MRPNP_EXP_DELTA_UNROLL;
+#pragma unroll kDeltaUnroll
         for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassDelta, float2>(slot, P, idx, true, u, a, f);
     }
     float s[16];

@@ -283,6 +283,43 @@ __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, 
         for (int i = 0; i < 4; ++i) pt[i] = scratch[kScrPt + i];
         __syncwarp();
     }
+    if ((kp.ransac_thres || kp.ransac_ratio > 0.f) && compacted && init_ok) {
+        // reprojection-threshold consensus with the start pose as the model (consensus_prune, pnp_device.cuh)
+        float thr;
+        if (kp.dense) {
+            const float* roi = kp.c2d + (size_t)obj * 4;
+            const int Hh = P / kp.roi_w;
+            thr = kp.ransac_ratio * (__ldg(roi + 3) - __ldg(roi + 1)) * (float)(Hh - 1) / (float)Hh;
+        } else {
+            thr = __ldg(kp.ransac_thres + obj);
+        }
+        if (thr > 0.f) {
+            // model = the linear initialiser's pose (init_pose only says where LM starts)
+            bool model_ok = init_ok;
+            if (kp.init_mode == MRPNP_INIT_GIVEN) model_ok = linear_init<WMODE, LAYOUT>(kp, obj, slot, n, lane, scratch);
+            for (int round = 0; round < 3 && model_ok; ++round)   // graduated trimmed fits, as in the fast kernel
+                if (!linear_init<WMODE, LAYOUT>(kp, obj, slot, n, lane, scratch, thr * (round == 0 ? 3.f : round == 1 ? 2.f : 1.4f))) break;
+            if (model_ok) {
+                float* fs = reinterpret_cast<float*>(scratch + 24);
+                __syncwarp();
+                if (lane < 4) fs[lane] = (float)scratch[kScrPt + lane];
+                __syncwarp();
+                const int n2 = consensus_prune<WMODE, LAYOUT>(kp, obj, slot, n, lane, fs, thr);
+                __syncwarp();
+                if (n2 != n) {
+                    n = n2;
+                    n_inliers = n2;
+                    model_ok = linear_init<WMODE, LAYOUT>(kp, obj, slot, n, lane, scratch);
+                }
+            }
+            if (kp.init_mode != MRPNP_INIT_GIVEN) {
+                init_ok = model_ok;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pt[i] = scratch[kScrPt + i];
+                __syncwarp();
+            }
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = pt[i];
 
@@ -512,7 +549,6 @@ __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, 
 
 template <bool MIXED, int WMODE, int LAYOUT>
 __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_constant__ KParams kp) {
-    constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;

@@ -36,7 +36,15 @@
 
 namespace mrpnp {
 
-constexpr int kFastMaxWarps = 10;      // resident warps (= objects in flight) per SM
+// Resident warps (= objects in flight) per SM.  Shared memory would hold 9 (full 2x2 weights) or 10 (diagonal) slots,
+// but registers are handed out per four warps: above 8 warps a thread gets 168 registers, and at 168 the kernel
+// spills its warp-uniform LM state to LOCAL memory -- ~106 KB per CTA against ~28 KB of L1 at this shared-memory
+// carve-out, i.e. an L2 round trip per reload.  Measured (profiles/r02_ab_variants.txt): 8 warps x 255 registers, no
+// spills, 162 us; 9 warps x 168 registers 196 us.
+#ifndef MRPNP_FAST_WARPS
+#define MRPNP_FAST_WARPS 8
+#endif
+constexpr int kFastMaxWarps = MRPNP_FAST_WARPS;
 // Per-warp header, 512 B = 128 floats: [0] mbarrier | [4..27] sums buffer A | [32..55] sums buffer B | [56..63] Jacobi
 // scale, LM diagonal | [64..95] argument stash of the out-of-line routines.  The exact routine's 40-double scratch
 // starts at float 32: it only runs between objects, when the fast path's state is dead.
@@ -112,12 +120,15 @@ __device__ __forceinline__ void issue_bulk_copies(const KParams& kp, int obj, fl
     }
 }
 
-// Next job of this warp: an object some warp handed back (kCntRedoCount / kCntRedoTaken over kp.redo_list; taken first,
-// so that the slow exact solves start early instead of forming the tail of the launch), else the next fresh object
-// (kCntFresh), else none.  A warp that hands an object back fetches right afterwards, so it finds its own entry unless
-// another warp took it first: no entry is ever stranded, and a warp that finds neither kind of work may leave.  A fresh
-// index drawn while a handed-back object was taken instead is kept in `pending`.
-// Returns the object or -1; is_redo tells which kind.  For a fresh object on the TMA path the bulk copies are started.
+// Work distribution.  Every warp draws fresh objects from one counter (kCntFresh) and, before each of them, looks at
+// the list of objects some warp handed back (kCntRedoCount / kCntRedoTaken over kp.redo_list; taken first, so that the
+// slow exact solves start early instead of forming the tail of the launch).  A warp that hands an object back looks
+// at the list right afterwards, so it finds its own entry unless another warp took it first: no entry is ever
+// stranded, and a warp that finds neither kind of work may leave.  A fresh index drawn while a handed-back object was
+// taken instead is kept in `pending`.  (Measured and dropped: drawing the ticket one object ahead, prefetching the next
+// object's slabs into L2 and its initial pose into registers -- 5 to 10 % slower, profiles/r02_ab_variants.txt.)
+// Returns the object, -1 (nothing left) or -2 (lost a race for a list entry: look again); is_redo tells which kind.
+// For a fresh object on the TMA path the bulk copies are started.
 template <int WC>
 __device__ __forceinline__ int fetch_job(const KParams& kp, float* slot, int P, uint64_t* bar, int lane, int& pending,
                                          bool& is_redo) {
@@ -142,7 +153,7 @@ __device__ __forceinline__ int fetch_job(const KParams& kp, float* slot, int P, 
             pending = kNoPending;
             if (kp.use_tma) issue_bulk_copies<WC>(kp, obj, slot, P, bar);
         } else if (rt < rc) {
-            obj = -2;   // lost the race for an entry and no fresh object left: look again
+            obj = -2;
         }
     }
     obj = __shfl_sync(kFull, obj, 0);
@@ -315,16 +326,22 @@ __device__ __forceinline__ void fast_pad(float* slot, int P, int n, int n_pad, i
 }
 
 // Out-of-line wrapper of the on-device linear initialiser (cold for callers that pass init_pose)
+// gate > 0: trimmed fit around the pose currently in scratch[20..23] (see linear_init_impl).
 template <int WMODE>
-__device__ __noinline__ bool fast_linear_init(const KParams& kp, int obj, float* slot, int n, int lane, float* scratch) {
+__device__ __noinline__ bool fast_linear_init(const KParams& kp, int obj, float* slot, int n, int lane, float* scratch,
+                                              float gate = 0.f) {
     const int P = kp.n_pts;
     const Camera<float> cam = load_camera<float>(kp, obj);
     double x[4];
-    const bool ok = linear_init_impl<WMODE, MRPNP_LAYOUT_PLANAR>(slot, slot + 3 * P, slot + 5 * P, P, TeamRows(n, 0, 0, 0, 1),
-                                                                 lane, cam, scratch, x);
-    __syncwarp();
-    if (lane == 0) {   // result through the scratch (scratch[20..23]): fp32 hand-over; .py:119-125
+    float prior[4];
 #pragma unroll
+    for (int i = 0; i < 4; ++i) prior[i] = gate > 0.f ? scratch[20 + i] : 0.f;
+    __syncwarp();
+    const bool ok = linear_init_impl<WMODE, MRPNP_LAYOUT_PLANAR>(slot, slot + 3 * P, slot + 5 * P, P, TeamRows(n, 0, 0, 0, 1),
+                                                                 lane, cam, scratch, x, gate > 0.f ? prior : nullptr, gate * gate);
+    __syncwarp();
+    if (lane == 0 && (ok || !(gate > 0.f))) {   // result through the scratch (scratch[20..23]): fp32 hand-over; .py:119-125
+#pragma unroll                                  // (a failed TRIMMED fit leaves the pose it started from in place)
         for (int i = 0; i < 4; ++i) scratch[20 + i] = ok ? (float)x[i] : 0.f;
     }
     __syncwarp();
@@ -483,6 +500,9 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
     uint32_t parity = 0;
     int pending = kNoPending;
     bool is_redo = false;
+    // camera and clip ranges shared by all objects (cam_mats / uv_range of batch size 1): read once
+    const bool shared_cam = kp.cam_stride == 0 && kp.range_stride == 0;
+    const Camera<float> cam0 = load_camera<float>(kp, 0);
 
     // The bulk copies of an object are started as soon as the slot is free, i.e. BEFORE the covariance / result row of
     // the previous object, so that part of the staging latency is hidden behind it.
@@ -499,7 +519,7 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
             continue;
         }
         TR_DECL
-        const Camera<float> camf = load_camera<float>(kp, obj);
+        const Camera<float> camf = shared_cam ? cam0 : load_camera<float>(kp, obj);
 
         // ---------------- stage + weights + inlier mask + compaction ----------------
         int n = P;
@@ -550,6 +570,44 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) pt[i] = hdr[kFastBufA + 20 + i];
             __syncwarp();
+        }
+        if (kp.ransac_thres || kp.ransac_ratio > 0.f) {
+            // reprojection-threshold consensus with the start pose as the model (consensus_prune, pnp_device.cuh)
+            float thr;
+            if (kp.dense) {   // uncert_prop_pnp_optimizer.py:86-88 on the analytic RoI grid: v[H-1] - v[0] = (H-1)/H (y2 - y1)
+                const float* roi = kp.c2d + (size_t)obj * 4;
+                const int Hh = P / kp.roi_w;
+                thr = kp.ransac_ratio * (__ldg(roi + 3) - __ldg(roi + 1)) * (float)(Hh - 1) / (float)Hh;
+            } else {
+                thr = __ldg(kp.ransac_thres + obj);
+            }
+            if (thr > 0.f) {
+                // the model of the consensus is always the linear initialiser's pose (init_pose only says where LM starts)
+                bool model_ok = init_ok;
+                if (kp.init_mode == MRPNP_INIT_GIVEN) model_ok = fast_linear_init<WMODE>(kp, obj, slot, n, lane, hdr + kFastBufA);
+                // graduated trimmed fits make the model robust to gross outliers before anything is dropped
+#pragma unroll 1
+                for (int round = 0; round < 3 && model_ok; ++round)
+                    if (!fast_linear_init<WMODE>(kp, obj, slot, n, lane, hdr + kFastBufA, thr * (round == 0 ? 3.f : round == 1 ? 2.f : 1.4f))) break;
+                if (model_ok) {
+                    __syncwarp();
+                    if (lane < 4) hdr[kFastBufB + lane] = hdr[kFastBufA + 20 + lane];
+                    __syncwarp();
+                    const int n2 = consensus_prune<WMODE, MRPNP_LAYOUT_PLANAR>(kp, obj, slot, n, lane, hdr + kFastBufB, thr);
+                    if (n2 != n) {
+                        n = n2;
+                        n_main = (n + 63) & ~63;
+                        if (n_main <= pad_cap) fast_pad<WMODE>(slot, P, n, n_main, lane); else n_main = n & ~63;
+                        model_ok = fast_linear_init<WMODE>(kp, obj, slot, n, lane, hdr + kFastBufA);   // like OpenCV's final fit on the consensus set
+                    }
+                }
+                if (kp.init_mode != MRPNP_INIT_GIVEN) {
+                    init_ok = model_ok;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) pt[i] = hdr[kFastBufA + 20 + i];
+                    __syncwarp();
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[i] = pt[i];

@@ -3,7 +3,10 @@
 * UncertPropPnPOptimizer  <- monorun/models/roi_heads/bbox_3d_heads/optimizers/uncert_prop_pnp_optimizer.py:12-99
 * FCNNOCDecoder           <- monorun/models/roi_heads/bbox_3d_heads/dense_decoders/fcn_noc_decoder.py:15-267
 * UncertProjectionHead    <- .../reprojection_heads/uncert_projection_head.py (test-time parts: get_distance, coder)
-* MonoRUnRoIHead          <- monorun/models/roi_heads/monorun_roi_head.py:13-40, hot sequence :509-534
+* MonoRUnRoIHead          <- monorun/models/roi_heads/monorun_roi_head.py:13-40, simple_test :442-605 (hot sequence
+                             :509-534), result packaging :607-655
+* SingleRoIExtractor      <- mmdet.models.roi_heads.roi_extractors.SingleRoIExtractor as configured at
+                             configs/kitti_multiclass.py:38-43, 83-88 (RoIAlign per FPN level; a caller-side stage)
 * FCExtractor[MonteCarlo] <- .../global_extractors/fc_extractor.py:12-156, fc_extractor_monte_carlo.py:21-82 (the caller-side
                              stage that produces latent / dimensions / reg_fc_out; torch Linear layers, not a kernel of
                              this path)
@@ -18,8 +21,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .coders import coords_2d_from_rois
-from .registry import (HEADS, build_coord_coder, build_dim_coder, build_head, build_pnp, build_proj_error_coder,
-                       build_rotation_coder)
+from .registry import (HEADS, ROI_EXTRACTORS, build_coord_coder, build_dim_coder, build_head, build_pnp,
+                       build_proj_error_coder, build_roi_extractor, build_rotation_coder)
 
 
 @HEADS.register_module()
@@ -61,9 +64,13 @@ class UncertPropPnPOptimizer(nn.Module):
             ret_val (Nbatch,) bool, yaw_pred (Nbatch, 1), t_vec_pred (Nbatch, 3),
             pose_cov_pred (Nbatch, 4, 4), pose_cov_calib (Nbatch, 4, 4)
         """
+        epnp_ransac_thres = None
+        if self.epnp_ransac_thres_ratio is not None and coords_2d.size(0):   # :86-88
+            roi_heights = coords_2d[:, 1, -1, 0] - coords_2d[:, 1, 0, 0]
+            epnp_ransac_thres = self.epnp_ransac_thres_ratio * roi_heights
         ret_val, yaw_pred, t_vec_pred, pose_cov_pred, _ = self.pnp.forward_dense(
             coords_2d, coords_2d_logstd, coords_3d, cam_intrinsic, self._uv_range(img_shapes), self.std_scale,
-            init_pose=init_pose)
+            init_pose=init_pose, epnp_ransac_thres=epnp_ransac_thres)
         return ret_val, yaw_pred, t_vec_pred, pose_cov_pred, self._calibrate(pose_cov_pred)
 
     def _uv_range(self, img_shapes):
@@ -86,7 +93,7 @@ class UncertPropPnPOptimizer(nn.Module):
         ret_val, yaw_pred, t_vec_pred, pose_cov_pred, _ = self.pnp.forward_fused(
             noc_pred, proj_logstd, rois, dimensions, dimensions_var, cam_intrinsic, self._uv_range(img_shapes),
             self.std_scale, coord_coder, proj_error_coder, distance=distance, init_pose=init_pose, labels=labels,
-            num_classes=num_classes)
+            num_classes=num_classes, ransac_ratio=self.epnp_ransac_thres_ratio or 0.0)
         return ret_val, yaw_pred, t_vec_pred, pose_cov_pred, self._calibrate(pose_cov_pred)
 
 
@@ -463,6 +470,69 @@ class FCExtractorMonteCarlo(FCExtractor):
         return dim_pred, dim_var, latent_pred, latent_var
 
 
+@ROI_EXTRACTORS.register_module()
+class SingleRoIExtractor(nn.Module):
+    """mmdet's SingleRoIExtractor for the two extractors of the config (configs/kitti_multiclass.py:38-43, 83-88):
+    every RoI is pooled from ONE pyramid level, ``floor(log2(sqrt(w h) / finest_scale + 1e-6))`` clamped to the levels,
+    with RoIAlign(output_size, sampling_ratio, aligned=True) at that level's stride.  torchvision's ``roi_align`` is the
+    operator (mmcv is not a dependency); this stage feeds the path, it is not part of it."""
+
+    def __init__(self, roi_layer, out_channels, featmap_strides, finest_scale=56):
+        super(SingleRoIExtractor, self).__init__()
+        cfg = dict(roi_layer)
+        assert cfg.pop('type', 'RoIAlign') == 'RoIAlign'
+        size = cfg.pop('output_size')
+        self.output_size = (size, size) if isinstance(size, int) else tuple(size)
+        self.sampling_ratio = cfg.pop('sampling_ratio', 0)
+        self.aligned = cfg.pop('aligned', True)
+        self.out_channels, self.featmap_strides, self.finest_scale = out_channels, list(featmap_strides), finest_scale
+        self.fp16_enabled = False
+
+    @property
+    def num_inputs(self):
+        return len(self.featmap_strides)
+
+    def init_weights(self):
+        pass
+
+    def map_roi_levels(self, rois, num_levels):
+        scale = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
+        return torch.floor(torch.log2(scale / self.finest_scale + 1e-6)).clamp(min=0, max=num_levels - 1).long()
+
+    def forward(self, feats, rois):
+        from torchvision.ops import roi_align
+        feats = feats[:self.num_inputs]
+        out = feats[0].new_zeros((rois.size(0), self.out_channels) + self.output_size)
+        if rois.size(0) == 0:
+            return out
+        if len(feats) == 1:
+            return roi_align(feats[0], rois, self.output_size, 1.0 / self.featmap_strides[0], self.sampling_ratio, self.aligned)
+        lvls = self.map_roi_levels(rois, len(feats))
+        for i, stride in enumerate(self.featmap_strides):
+            idx = (lvls == i).nonzero(as_tuple=True)[0]
+            if idx.numel():
+                out[idx] = roi_align(feats[i], rois[idx], self.output_size, 1.0 / stride, self.sampling_ratio, self.aligned)
+        return out
+
+
+def bbox2roi(bbox_list):
+    """mmdet.core.bbox2roi: list of (n_i, >=4) boxes per image -> (sum n_i, 5) [batch_idx, x1, y1, x2, y2]."""
+    rois = []
+    for img_id, bboxes in enumerate(bbox_list):
+        ind = bboxes.new_full((bboxes.size(0), 1), img_id)
+        rois.append(torch.cat([ind, bboxes[:, :4]], dim=-1))
+    return torch.cat(rois, 0) if rois else torch.zeros((0, 5))
+
+
+def bbox2result(bboxes, labels, num_classes):
+    """mmdet.core.bbox2result: (n, 5) boxes + (n,) labels -> list of per-class (k, 5) numpy arrays."""
+    import numpy as np
+    if bboxes.shape[0] == 0:
+        return [np.zeros((0, 5), dtype=np.float32) for _ in range(num_classes)]
+    bboxes, labels = bboxes.detach().cpu().numpy(), labels.detach().cpu().numpy()
+    return [bboxes[labels == i, :] for i in range(num_classes)]
+
+
 _OUT_OF_SCOPE = ('bbox_roi_extractor', 'bbox_head', 'global_head', 'noc_roi_extractor',
                  'shared_head', 'mask_roi_extractor', 'mask_head')
 
@@ -483,7 +553,15 @@ class MonoRUnRoIHead(nn.Module):
         unknown = set(kwargs) - set(_OUT_OF_SCOPE)
         if unknown:
             raise TypeError(f'unexpected MonoRUnRoIHead arguments: {sorted(unknown)}')
-        self.train_cfg, self.test_cfg, self.debug = train_cfg, test_cfg, debug
+        from .config import ConfigDict
+        wrap = lambda c: ConfigDict(c) if isinstance(c, dict) and not isinstance(c, ConfigDict) else c
+        self.train_cfg, self.test_cfg, self.debug = wrap(train_cfg), wrap(test_cfg), debug
+        self.new_version = True      # mmdet >= 2.4: simple_test returns a list with one dict per image (:601-604)
+        self.bbox_stage = None       # the 2-D detection stage of simple_test, see set_bbox_stage
+        for name in ('bbox_roi_extractor', 'noc_roi_extractor'):   # caller-side stages simple_test needs
+            cfg = self.deferred.get(name)
+            if cfg is not None and cfg.get('type') in ROI_EXTRACTORS and len(cfg) > 1:
+                setattr(self, name, build_roi_extractor(cfg))
         if global_head is not None and global_head.get('type') in HEADS and len(global_head) > 1:
             self.global_head = build_head(global_head)   # a bare dict(type=...) stub stays deferred
         if noc_head is not None:
@@ -541,7 +619,7 @@ class MonoRUnRoIHead(nn.Module):
         BEV NMS (``nms_thr`` defaults to test_cfg.nms_3d_thr, configs/kitti_multiclass.py:195-210)."""
         from . import pnp
         if nms_thr is None:
-            nms_thr = getattr(self.test_cfg, 'nms_3d_thr', 0.25) if self.test_cfg is not None else 0.25
+            nms_thr = self._test('nms_3d_thr', 0.25)
         return pnp.nms_bev(bbox_3d, det_labels, group_offsets, nms_thr, max_group=max_group)
 
     def forward_3d(self, noc_feats, bbox_3d_rois, det_labels, latent_pred, dimensions_pred, dimensions_var,
@@ -588,3 +666,133 @@ class MonoRUnRoIHead(nn.Module):
             cov_calib = self.projection_head.proj_error_coder.cov_correction(cov_calib, distance)
         return dict(ret_val=ret_val, yaw_pred=yaw, t_vec_pred=t_vec, pose_cov_pred=cov, pose_cov_calib=cov_calib,
                     coords_3d=coords_3d, proj_logstd=proj_logstd, coords_2d=coords_2d_roi)
+
+    # ------------------------------------------------------------------ simple_test (monorun_roi_head.py:442-605)
+    def _test(self, key, default=None):
+        cfg = self.test_cfg
+        if cfg is None:
+            return default
+        return cfg.get(key, default) if isinstance(cfg, dict) else getattr(cfg, key, default)
+
+    def set_bbox_stage(self, fn):
+        """The 2-D detection stage of ``simple_test`` (:460-469: ``_bbox_forward`` + ``bbox_head.get_bboxes``) belongs
+        to mmdet (Shared2FCBBoxHead, its coder and NMS) and is outside this path; it is injected instead:
+        ``fn(x, proposal_list, img_metas, rescale, test_cfg) -> (det_bboxes (n, 5) [x1, y1, x2, y2, score],
+        det_labels (n,) int64)`` -- an mmdet ``StandardRoIHead.simple_test_bboxes`` bound method has this shape."""
+        self.bbox_stage = fn
+        return self
+
+    @property
+    def with_bbox(self):
+        return self.bbox_stage is not None
+
+    def _reg_forward(self, x, rois, labels):
+        """:272-288 plus the decode that follows it in simple_test (:503-507)."""
+        reg_feats = self.bbox_roi_extractor(x[:self.bbox_roi_extractor.num_inputs], rois)
+        out = self.reg_forward(reg_feats, labels)
+        out['roi_feats'] = reg_feats
+        return out
+
+    def get_bbox_3d_result(self, dimensions, yaw, t_vec, scores, labels, to_np=False):
+        """:607-613: per-class lists of [l, h, w, x, y, z, ry, score] rows."""
+        bboxes_3d = torch.cat((dimensions, t_vec, yaw, scores.unsqueeze(1)), dim=1)
+        if to_np:
+            bboxes_3d, labels = bboxes_3d.cpu().numpy(), labels.cpu().numpy()
+        return [bboxes_3d[labels == i] for i in range(self.noc_head.num_classes)]
+
+    def multiclass_3d_result_nms(self, bbox_3d_result, nms_thr=0.25, to_np=True):
+        """:619-655 -- per class, rotated-BEV NMS; returns (kept boxes, kept indices into the class's rows), both in
+        descending score order like mmdet3d's ``nms_gpu``.  One ``mrpnp_nms_bev`` launch covers all classes."""
+        from . import pnp
+        sizes = [int(b.size(0)) for b in bbox_3d_result]
+        out_boxes, out_inds = [], []
+        keep_all = None
+        if sum(sizes) > 0:
+            allb = torch.cat(bbox_3d_result, 0)
+            labels = torch.cat([allb.new_full((k,), i, dtype=torch.long) for i, k in enumerate(sizes)])
+            keep_all = pnp.nms_bev(allb, labels, None, nms_thr)
+        start = 0
+        for boxes, k in zip(bbox_3d_result, sizes):
+            if k > 1:
+                keep = keep_all[start:start + k]
+                inds = keep.nonzero(as_tuple=True)[0]
+                inds = inds[torch.argsort(boxes[inds, 7], descending=True, stable=True)]
+                kept = boxes[inds]
+            else:   # :645-654: zero or one box is returned as is, with indices zeros(n)
+                inds, kept = boxes.new_zeros((k,), dtype=torch.int64), boxes
+            out_boxes.append(kept.cpu().numpy() if to_np else kept)
+            out_inds.append(inds.cpu().numpy() if to_np else inds)
+            start += k
+        return out_boxes, out_inds
+
+    def simple_test(self, x, proposal_list, img_metas, proposals=None, coord_2d=None, cam_intrinsic=None, rescale=False,
+                    native=True):
+        """Drop-in for ``MonoRUnRoIHead.simple_test`` (monorun_roi_head.py:442-605): one image in, ``[dict(bbox_results,
+        bbox_3d_results)]`` out (per-class numpy arrays; 3-D rows [l, h, w, x, y, z, ry, score]).
+
+        The 2-D stage is the injected ``bbox_stage``.  From its detections on, everything is this repo's native
+        sequence: RoI features -> MC-dropout global extractor -> dense head (tcgen05 convolutions) -> fused decode +
+        uncertainty PnP (one launch, incl. the reprojection-threshold consensus of ``epnp_ransac_thres_ratio``) -> score
+        stage -> 3-D NMS.  ``coord_2d`` is accepted for signature compatibility: the RoI pixel grid is generated
+        analytically from the boxes, which assumes the untransformed pixel grid of the shipped test
+        pipelines (scale_factor 1, no flip); other metas fall back to resampling ``coord_2d`` with ``roi_align``.
+        ``native=False`` runs the fp32 torch modules instead of the kernels (the reference of the tests)."""
+        import numpy as np
+        assert self.with_bbox and self.with_noc and self.with_pose and self.with_score, \
+            'simple_test needs the bbox stage (set_bbox_stage) and the noc / pose / score heads'
+        assert len(img_metas) == 1, 'batch inference is not supported yet'   # :452
+        meta = img_metas[0]
+        img_shape, scale_factor = meta['img_shape'], meta.get('scale_factor', 1.0)
+        flip = bool(meta.get('flip', False))
+        cam_intrinsic = cam_intrinsic[0][0][None, ...]                        # :458
+        num_classes = self.noc_head.num_classes
+
+        det_bboxes, det_labels = self.bbox_stage(x, proposal_list, img_metas, rescale, self.test_cfg)   # :460-469
+        if det_bboxes.shape[0] > 0:                                           # :471-478
+            sf = det_bboxes.new_tensor(scale_factor) if not isinstance(scale_factor, float) else scale_factor
+            _bboxes = det_bboxes[:, :4] * sf if rescale else det_bboxes
+            bbox_3d_rois = bbox2roi([_bboxes])
+        else:
+            bbox_3d_rois = None
+        bbox_result = bbox2result(det_bboxes, det_labels, num_classes)       # :481-482
+        if bbox_3d_rois is None:                                              # :485-487
+            bbox_3d_result = [np.zeros((0, 8), dtype=np.float32) for _ in range(num_classes)]
+            return [dict(bbox_results=bbox_result, bbox_3d_results=bbox_3d_result)]
+
+        with torch.no_grad():
+            reg = self._reg_forward(x, bbox_3d_rois, det_labels)             # :489-507
+            noc_feats = self.noc_roi_extractor(x[:self.noc_roi_extractor.num_inputs], bbox_3d_rois)   # :331-332
+            unit_scale = isinstance(scale_factor, float) and scale_factor == 1.0 or \
+                (not isinstance(scale_factor, float) and bool((np.asarray(scale_factor) == 1).all()))
+            fused = native and x[0].is_cuda and not flip and unit_scale
+            if fused or coord_2d is None:
+                out = self.forward_3d(noc_feats, bbox_3d_rois, det_labels, reg['latent_pred'], reg['dimensions_pred'],
+                                      reg['dimensions_var'], cam_intrinsic, img_shape, flip=flip,
+                                      cov_correction=False, fused=fused, native_head=fused)
+            else:   # transformed pixel grid: resample it like the reference does (:521-523)
+                out = self._forward_3d_resampled(noc_feats, bbox_3d_rois, det_labels, reg, cam_intrinsic, img_shape, flip,
+                                                 coord_2d[0])
+            n = det_labels.numel()
+            rows = torch.cat([out['yaw_pred'], out['t_vec_pred'], out['pose_cov_pred'].reshape(n, 16),
+                              out['ret_val'].float()[:, None], out['yaw_pred'].new_zeros(n, 3)], 1)
+            scores, bbox_3d, _ = self.forward_scores(                         # :530-550
+                rows, reg['reg_fc_out'], reg['dimensions_pred'], det_scores=det_bboxes[:, -1],
+                cov_correction=bool(self._test('cov_correction', False)), calib_scoring=bool(self._test('calib_scoring', False)),
+                mult_2d_score=bool(self._test('mult_2d_score', False)))
+            per_class = [bbox_3d[det_labels == i] for i in range(num_classes)]            # :552-558
+            bbox_3d_result, keep_inds_3d = self.multiclass_3d_result_nms(per_class, self._test('nms_3d_thr', 0.25), to_np=True)
+        bbox_result = [b[k] for b, k in zip(bbox_result, keep_inds_3d)]      # :561-565
+        return [dict(bbox_results=bbox_result, bbox_3d_results=bbox_3d_result)]
+
+    def _forward_3d_resampled(self, noc_feats, rois, det_labels, reg, cam_intrinsic, img_shape, flip, coord_2d):
+        """The unfused sequence with ``coords_2d_roi = roi_align(coord_2d, rois, ...)`` (:513-529) for pixel grids that went
+        through Resize / Flip / Pad."""
+        from torchvision.ops import roi_align
+        noc_pred, noc_var, proj_logstd, _ = self.noc_head(noc_feats, reg['latent_pred'], None, det_labels, flip=flip)
+        coords_3d, coords_3d_var = self.noc_head.coord_coder.decode(noc_pred, noc_var, reg['dimensions_pred'],
+                                                                    reg['dimensions_var'], flip)
+        proj_logstd = self.projection_head.proj_error_coder.decode_logstd(proj_logstd, coords_3d_var, None)
+        coords_2d_roi = roi_align(coord_2d[None] if coord_2d.dim() == 3 else coord_2d, rois, noc_pred.shape[-2:], 1.0, 0, True)
+        img_shapes = cam_intrinsic.new_tensor(img_shape[:2])[None, ...]
+        ret_val, yaw, t_vec, cov, cov_calib = self.pose_head(coords_2d_roi, proj_logstd, coords_3d, cam_intrinsic, img_shapes)
+        return dict(ret_val=ret_val, yaw_pred=yaw, t_vec_pred=t_vec, pose_cov_pred=cov, pose_cov_calib=cov_calib)

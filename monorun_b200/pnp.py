@@ -99,13 +99,16 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
                   layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, istd_thres=0.6,
                   inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
                   adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False, peers=None, row_offset=0,
-                  decision_bands=None):
+                  decision_bands=None, ransac_thres=None):
     """Batched uncertainty-PnP on device tensors -- direct wrapper of ``mrpnp_solve``.
 
     layout 'planar':      coords_3d [N,3,*], coords_2d [N,2,*], weights [N,2|3,*]   (head level)
     layout 'interleaved': coords_3d [N,P,3], coords_2d [N,P,2], weights [N,P,2|3]   (op level)
     weight_mode 'logstd' | 'istd' | 'full';  cam_mats [N|1,3,3];  uv_range [N|1,4] = u_min,u_max,v_min,v_max;
     init_pose [N,4] or None (on-device linear initialiser);  inlier_mask [N,P] bool/uint8 or None.
+
+    ransac_thres [N] float (pixels) or None: reprojection-threshold consensus after the start pose, the deterministic
+    counterpart of the inlier refinement of cv2.solvePnPRansac (pnp_uncert_cpu.py:34-51; include/monorun_pnp.h).
 
     peers: device pointers (ints, valid on this device) of every rank's gathered [n_total,24] buffer -- the kernel then
     stores each result row into ALL of them at row ``row_offset + i`` (fused all-gather, see ``dist.FusedGather``) and
@@ -144,6 +147,12 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
         inlier_opt_only=int(bool(inlier_opt_only)), max_iterations=int(max_iterations),
         adopt_candidate_on_ftol=int(bool(adopt_candidate_on_ftol)),
         z_min=float(z_min), std_scale=float(std_scale), istd_thres=float(istd_thres))
+    thr = None
+    if ransac_thres is not None:
+        thr = _f32c(ransac_thres).reshape(-1)
+        if thr.numel() != n or thr.device != dev:
+            raise ValueError('ransac_thres must be a device tensor with one threshold per object')
+        p.ransac_thres = _ptr(thr)
     if decision_bands is not None:   # (band_first, band_rel, band_mix) of mrpnp_params; the defaults are the product's
         p.band_first, p.band_rel, p.band_mix = (float(v) for v in decision_bands)
     if peers:
@@ -353,7 +362,7 @@ def nms_bev(bbox_3d, labels=None, group_offsets=None, iou_thr=0.25, max_group=No
 def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, *, noc_mean, noc_std, focal_gain,
                 scaling_denominator, distance=None, distance_min=0.1, init_pose=None, z_min=0.5, std_scale=10.0,
                 istd_thres=0.6, inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
-                return_inlier_mask=True, labels=None, num_classes=0):
+                return_inlier_mask=True, labels=None, num_classes=0, ransac_ratio=0.0):
     """Fused head -> PnP launch -- direct wrapper of ``mrpnp_solve_dense``: the dense head's raw class-sliced
     ``noc_pred`` [N,3,H,W] and ``proj_logstd`` [N,2,H,W], the detection boxes ``rois`` [N,4|5] and the decoded
     ``dims`` [N,3] (+ ``dims_var`` [N,3] | None, ``distance`` [N] | None) go in; NOCCoder.decode, the variance
@@ -397,7 +406,8 @@ def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range,
         cov_mode={'none': 0, 'pipeline': 1, 'ceres': 2}[cov_mode],
         init_mode=C['MRPNP_INIT_GIVEN'] if init is not None else C['MRPNP_INIT_LINEAR'],
         inlier_opt_only=int(bool(inlier_opt_only)), max_iterations=int(max_iterations),
-        z_min=float(z_min), std_scale=float(std_scale), istd_thres=float(istd_thres))
+        z_min=float(z_min), std_scale=float(std_scale), istd_thres=float(istd_thres),
+        ransac_ratio=float(ransac_ratio or 0.0))   # threshold = ratio * (v[last row] - v[first row]), evaluated in the kernel
     dp = _native.ffi.new('mrpnp_dense_params*')
     for i in range(3):
         dp.noc_mean[i], dp.noc_std[i] = float(noc_mean[i]), float(noc_std[i])
@@ -442,6 +452,31 @@ def solve_host(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None
     return result
 
 
+def u2d_pnp_cpu(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range, z_min=0.5, epnp_istd_thres=1.0,
+                epnp_ransac_thres=None, inlier_opt_only=False, with_pose_cov=True, device=0):
+    """Drop-in for the module-level export ``monorun.ops.u2d_pnp_cpu`` (pnp_uncert_cpu.py:128-209): numpy fp32 arrays
+    in, numpy out -- ``(ret_val (N,) bool, yaw (N,1), t_vec (N,3), pose_cov (N,4,4) | None, tr_radius (N,1),
+    inlier_mask (N,P) bool)`` -- solved on CUDA device ``device`` (there is no CPU implementation behind this name;
+    the arrays are copied to the device and back, like the reference copies tensors to the host).  pose_cov is Ceres'
+    own covariance (``with_pose_cov``; pnp_uncert_cpu.cpp:279-291), as in the reference's native call."""
+    import numpy as np
+    n, p = coords_2d.shape[0], coords_2d.shape[1]
+    if n == 0:   # pnp_uncert_cpu.py:201-207
+        return (np.zeros((0,), bool), np.zeros((0, 1), np.float32), np.zeros((0, 3), np.float32),
+                np.zeros((0, 4, 4), np.float32) if with_pose_cov else None, np.zeros((0, 1), np.float32), np.zeros((0, p), bool))
+    dev = torch.device('cuda', device)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(dev)
+    ur, vr = t(np.broadcast_to(u_range, (max(len(u_range), len(v_range)), 2))), t(np.broadcast_to(v_range, (max(len(u_range), len(v_range)), 2)))
+    thr = t(epnp_ransac_thres) if epnp_ransac_thres is not None and inlier_opt_only else None
+    result, inlier_mask, _ = solve_batched(
+        t(coords_3d), t(coords_2d), t(coords_2d_istd), t(cam_mats), torch.cat([ur, vr], 1), layout='interleaved',
+        weight_mode='istd', z_min=z_min, istd_thres=epnp_istd_thres, inlier_opt_only=inlier_opt_only,
+        cov_mode='ceres' if with_pose_cov else 'none', ransac_thres=thr)
+    r = result.cpu().numpy()
+    return (r[:, 20] > 0.5, r[:, 0:1].copy(), r[:, 1:4].copy(), r[:, 4:20].reshape(n, 4, 4).copy() if with_pose_cov else None,
+            r[:, 23:24].copy(), inlier_mask.cpu().numpy())
+
+
 def _unpack(result, inlier_mask):
     ret_val = result[:, 20] > 0.5
     r_vec = result[:, 0:1].clone()
@@ -459,9 +494,11 @@ def pnp_uncert(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range,
         coords_2d (Tensor): (Nbatch, Npoint, 2);  coords_2d_istd (Tensor): (Nbatch, Npoint, 2)
         coords_3d (Tensor): (Nbatch, Npoint, 3);  cam_mats (Tensor): (Nbatch, 3, 3) or (1, 3, 3)
         u_range, v_range (Tensor): (Nbatch, 2) or (1, 2);  z_min, epnp_istd_thres (float)
-        epnp_ransac_thres (None | Tensor): accepted for signature compatibility.  OpenCV's RANSAC-EPnP
-            (pnp_uncert_cpu.py:34-51) is not reproduced on the GPU; the on-device linear initialiser uses the
-            istd inliers (documented deviation).
+        epnp_ransac_thres (None | Tensor): (Nbatch,) reprojection threshold in pixels.  The reference hands it to
+            cv2.solvePnPRansac, whose consensus set narrows the inliers LM, the covariance and the returned mask see
+            (pnp_uncert_cpu.py:34-51).  Here the start pose (on-device linear initialiser, or init_pose) is the model
+            of a deterministic consensus pass on the device with the same rule (dropped only if > 4 points survive);
+            OpenCV's random sampling itself is not reproduced.
         forward_exact_hessian: True replaces the Gauss-Newton covariance by the inverse of the second-order
             Hessian (hessian.py:5-64; one more launch, ``mrpnp_exact_hessian``).  use_6dof: accepted and unused,
             exactly as in the reference.
@@ -481,7 +518,8 @@ def pnp_uncert(coords_2d, coords_2d_istd, coords_3d, cam_mats, u_range, v_range,
         result, inlier_mask, _ = solve_batched(
             coords_3d, coords_2d, coords_2d_istd, cam_mats, uv_range, init_pose=init_pose, layout='interleaved',
             weight_mode='istd', z_min=z_min, istd_thres=epnp_istd_thres, inlier_opt_only=inlier_opt_only,
-            cov_mode='none' if forward_exact_hessian else 'pipeline', precision=precision)
+            cov_mode='none' if forward_exact_hessian else 'pipeline', precision=precision,
+            ransac_thres=epnp_ransac_thres if inlier_opt_only else None)
         if forward_exact_hessian:  # pnp_uncert.py:63-69, :77-85
             exact_hessian(coords_3d, coords_2d, coords_2d_istd, cam_mats, uv_range, result, inlier_mask,
                           layout='interleaved', weight_mode='istd', z_min=z_min, rows=result, return_hessian=False)
@@ -539,7 +577,8 @@ class PnPUncert(torch.nn.Module):
             ok = ret_val & (res[:, 42] > 0.5)
             return (ok, res[:, 0:3].float(), res[:, 3:6].float(), res[:, 6:42].reshape(n, 6, 6).float(), inlier_mask)
 
-    def forward_dense(self, coords_2d, coords_2d_logstd, coords_3d, cam_mats, uv_range, std_scale, init_pose=None):
+    def forward_dense(self, coords_2d, coords_2d_logstd, coords_3d, cam_mats, uv_range, std_scale, init_pose=None,
+                      epnp_ransac_thres=None):
         """Head-level entry used by UncertPropPnPOptimizer: NCHW tensors and log-std straight into the kernel
         (fuses uncert_prop_pnp_optimizer.py:73 and the three permute copies of :82-84)."""
         with torch.no_grad():
@@ -549,7 +588,8 @@ class PnPUncert(torch.nn.Module):
                 coords_3d, coords_2d, coords_2d_logstd, cam_mats, uv_range, init_pose=init_pose, layout='planar',
                 weight_mode='logstd', z_min=self.z_min, std_scale=std_scale, istd_thres=self.epnp_istd_thres,
                 inlier_opt_only=self.inlier_opt_only,
-                cov_mode='none' if self.forward_exact_hessian else 'pipeline', precision=self.precision)
+                cov_mode='none' if self.forward_exact_hessian else 'pipeline', precision=self.precision,
+                ransac_thres=epnp_ransac_thres if self.inlier_opt_only else None)
             if self.forward_exact_hessian:
                 exact_hessian(coords_3d, coords_2d, coords_2d_logstd, cam_mats, uv_range, result, inlier_mask,
                               layout='planar', weight_mode='logstd', z_min=self.z_min, std_scale=std_scale,
@@ -557,7 +597,7 @@ class PnPUncert(torch.nn.Module):
             return _unpack(result, inlier_mask)
 
     def forward_fused(self, noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, std_scale, coord_coder,
-                      proj_error_coder, distance=None, init_pose=None, labels=None, num_classes=0):
+                      proj_error_coder, distance=None, init_pose=None, labels=None, num_classes=0, ransac_ratio=0.0):
         """Fused head -> PnP entry (``mrpnp_solve_dense``): takes what FCNNOCDecoder returns plus the decoded
         dimensions and the boxes; ``coord_coder`` (NOCCoder) and ``proj_error_coder``
         (DistanceInvarProjErrorCoder) only supply their constants.  With ``labels`` / ``num_classes`` the first
@@ -575,5 +615,6 @@ class PnPUncert(torch.nn.Module):
                 scaling_denominator=proj_error_coder.scaling_denomitor, distance=distance,
                 distance_min=proj_error_coder.distance_min, init_pose=init_pose, z_min=self.z_min,
                 std_scale=std_scale, istd_thres=self.epnp_istd_thres, inlier_opt_only=self.inlier_opt_only,
-                cov_mode='pipeline', precision=self.precision, labels=labels, num_classes=num_classes)
+                cov_mode='pipeline', precision=self.precision, labels=labels, num_classes=num_classes,
+                ransac_ratio=ransac_ratio if self.inlier_opt_only else 0.0)
             return _unpack(result, inlier_mask)

@@ -88,6 +88,7 @@ PROJ_ERROR_CODERS = Registry('proj_error_coder') # monorun/core/bbox_3d/builder.
 DIM_CODERS = Registry('dim_coder')               # monorun/core/bbox_3d/builder.py:3
 ROTATION_CODERS = Registry('rotation_coder')     # monorun/core/bbox_3d/builder.py:5
 LOSSES = Registry('loss')                        # mmdet.models.builder.LOSSES (training only; stubs)
+ROI_EXTRACTORS = Registry('roi_extractor')       # mmdet.models.builder.ROI_EXTRACTORS
 
 
 def build_pnp(cfg, **default_args):
@@ -97,6 +98,10 @@ def build_pnp(cfg, **default_args):
 
 def build_head(cfg, **default_args):
     return build_from_cfg(cfg, HEADS, default_args)
+
+
+def build_roi_extractor(cfg, **default_args):
+    return build_from_cfg(cfg, ROI_EXTRACTORS, default_args)
 
 
 def build_coord_coder(cfg, **default_args):

@@ -268,8 +268,87 @@ def test_head_level_matches_op_level(cuda_lib):
     ret2, yaw2, t2, cov2, _ = monorun_b200.pnp_uncert(
         c2.permute(0, 2, 3, 1).reshape(n, 784, 2), istd.permute(0, 2, 3, 1).reshape(n, 784, 2),
         c3.permute(0, 2, 3, 1).reshape(n, 784, 3), cam, u_range, v_range, z_min=0.5, epnp_istd_thres=0.6,
+        epnp_ransac_thres=0.2 * (c2[:, 1, -1, 0] - c2[:, 1, 0, 0]),   # :86-88, epnp_ransac_thres_ratio = 0.2
         inlier_opt_only=True, init_pose=init, precision='fp64')
     assert torch.allclose(t, t2, rtol=2e-6) and torch.allclose(yaw, yaw2, atol=2e-6) and torch.allclose(cov, cov2, rtol=1e-3)
+
+
+def _with_gross_outliers(b, frac=0.15, seed=3):
+    """A copy of an S1 batch in which a fraction of the well-weighted points observe a wrong pixel, off by +- half the RoI
+    height (at least 40 px) on both axes: the istd test keeps them, only a reprojection test can reject them."""
+    rng = np.random.default_rng(seed)
+    out = dict(b)
+    c2 = b['coords_2d'].copy()
+    n = c2.shape[0]
+    bad = (rng.random((n, 28, 28)) < frac) & b['hit'].reshape(n, 28, 28)
+    shift = np.maximum(40.0, 0.5 * (c2[:, 1, -1, 0] - c2[:, 1, 0, 0]))[:, None, None] * np.ones((1, 28, 28))
+    c2[:, 0][bad] += rng.choice([-1.0, 1.0], size=int(bad.sum())) * shift[bad]
+    c2[:, 1][bad] += rng.choice([-1.0, 1.0], size=int(bad.sum())) * shift[bad]
+    out['coords_2d'] = c2.astype(np.float32)
+    return out, bad.reshape(n, 784)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fast'])
+@pytest.mark.parametrize('given_init', [True, False])
+def test_consensus_prune_rejects_gross_outliers(cuda_lib, oracle, precision, given_init):
+    """epnp_ransac_thres (pnp_uncert_cpu.py:34-51): the on-device consensus pass drops the points that disagree with the
+    start pose by more than the threshold, LM runs on the survivors (parity with the oracle GIVEN the returned mask and
+    start), and without a threshold nothing changes."""
+    from monorun_b200 import pnp
+    n = 256
+    b0 = synth.make_batch(n, config=2, weights='diag', mode='S1')
+    b, bad = _with_gross_outliers(b0)
+    op = synth.to_op_level(b)
+    w = op['coords_2d_istd']
+    c2 = dev(b['coords_2d'])
+    c2_clean = dev(b0['coords_2d'])
+    thr = torch.clamp(0.2 * (c2_clean[:, 1, -1, 0] - c2_clean[:, 1, 0, 0]), min=8.0)   # above the synthetic pixel noise
+    kw = dict(layout='interleaved', weight_mode='istd', precision=precision, return_fp64=True)
+    args = (dev(op['coords_3d']), dev(op['coords_2d']), dev(w), dev(op['cam_mats']), uvr(op))
+    init = dev(b['init_pose']) if given_init else None
+    res0, inl0, _ = pnp.solve_batched(*args, init_pose=init, **kw)
+    res1, inl1, r64 = pnp.solve_batched(*args, init_pose=init, ransac_thres=thr, **kw)
+    inl0, inl1 = inl0.cpu().numpy(), inl1.cpu().numpy()
+    istd_mask = host_mask(oracle, w, False)
+    assert np.array_equal(inl0, istd_mask)                       # no threshold: the istd test alone
+    assert (inl1 <= inl0).all() and (res1[:, 20] == 1).all()     # the consensus pass only narrows the mask
+    kept_bad = (inl1 & bad).sum() / max((inl0 & bad).sum(), 1)
+    kept_good = (inl1 & ~bad).sum() / (inl0 & ~bad).sum()
+    assert kept_bad < 0.03 and kept_good > 0.97, (kept_bad, kept_good)
+    gt = b['gt_pose']
+    e0, _ = pose_errors(res0.cpu().numpy().astype(np.float64), gt)
+    e1, _ = pose_errors(res1.cpu().numpy().astype(np.float64), gt)
+    assert np.median(e1) < 0.5 * np.median(e0)                   # and the pose is closer to the truth
+    if given_init:   # LM parity given the returned mask and the shared start
+        ref = oracle.lm_batch(op['coords_2d'], op['coords_3d'], w, op['cam_mats'], b['init_pose'], clips(op), inl1, threads=0)
+        t_err, r_err = pose_errors(r64.cpu().numpy(), ref['pose'])
+        assert t_err.max() < T_TOL and r_err.max() < R_TOL, (t_err.max(), r_err.max())
+
+
+def test_consensus_prune_against_opencv_ransac(cuda_lib, oracle):
+    """Against the reference's own inlier refinement (restated driver with cv2.solvePnPRansac, pnp_uncert_cpu.py:34-51):
+    the consensus sets overlap almost entirely and the final poses agree to the size of OpenCV's sampling noise."""
+    from monorun_b200 import pnp
+    n = 96
+    b0 = synth.make_batch(n, config=2, weights='diag', mode='S1')
+    b, bad = _with_gross_outliers(b0)
+    op = synth.to_op_level(b)
+    c2 = dev(b0['coords_2d'])
+    thr = torch.clamp(0.2 * (c2[:, 1, -1, 0] - c2[:, 1, 0, 0]), min=8.0)
+    res, inl, _ = pnp.solve_batched(dev(op['coords_3d']), dev(op['coords_2d']), dev(op['coords_2d_istd']), dev(op['cam_mats']),
+                                    uvr(op), ransac_thres=thr, layout='interleaved', weight_mode='istd', precision='fast')
+    ref = oracle.pnp_uncert_ref(op['coords_2d'], op['coords_2d_istd'], op['coords_3d'], op['cam_mats'], op['u_range'],
+                                op['v_range'], z_min=0.5, epnp_istd_thres=0.6, epnp_ransac_thres=thr.cpu().numpy(),
+                                inlier_opt_only=True)
+    inl = inl.cpu().numpy()
+    iou = (inl & ref[4]).sum(1) / np.maximum((inl | ref[4]).sum(1), 1)
+    pose = res.cpu().numpy().astype(np.float64)
+    ref_pose = np.concatenate([ref[1], ref[2]], 1).astype(np.float64)
+    t_err, r_err = pose_errors(pose, ref_pose)
+    ok = ref[0] & (res[:, 20] == 1).cpu().numpy()
+    assert ok.mean() > 0.95
+    assert np.median(iou[ok]) > 0.97 and np.percentile(iou[ok], 5) > 0.9, (np.median(iou[ok]), np.percentile(iou[ok], 5))
+    assert np.median(t_err[ok]) < 2e-3, np.median(t_err[ok])
 
 
 def test_roi_head_hot_sequence_runs(cuda_lib):
