@@ -355,8 +355,15 @@ def main():
             raise SystemExit(f'parity check failed: {parity}')
 
     # ---- (1) the kernel alone: K serialized launches on one stream, CUDA events around each (roofline source) ----
-    for i in range(args.warmup):
+    # The parity check above left the GPU idle for seconds: besides the W warm-up steps, keep it busy for a quarter of a
+    # second (untimed) so that the launches below run at the clocks of a loaded device, as they do inside a long job.
+    t_warm = time.perf_counter()
+    i = 0
+    while i < args.warmup or time.perf_counter() - t_warm < 0.25:
         step(i)
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize(dev)
     fence()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
@@ -365,7 +372,8 @@ def main():
         rows, _, _ = pnp.solve_batched(d['c3'], d['c2'], d['w'], d['cam'], d['rng'], init_pose=d['init'], **kw)
         kev[i][1].record()
     fence()
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    kernel_us = [1e3 * a.elapsed_time(b) for a, b in kev]
+    kernel_ms = float(np.mean(kernel_us)) * 1e-3
 
     # ---- (2) device-resident throughput: exactly K steps between fences.  Consecutive steps are independent
     #      batches, so they alternate between `--streams` CUDA streams: the ramp-down of one persistent launch (a
@@ -467,6 +475,7 @@ def main():
             'precision': args.precision, 'init': 'ground truth perturbed (5e-2 rad, 2% depth), shared with the oracle',
             'l2': 'two alternating input sets of %.0f MB each (%s 126 MB L2)' % (alg / 1e6, '>' if alg > 126e6 else 'NOT larger than the'),
             'streams': nstreams, 'serialized_ms_per_step': kernel_ms,
+            'serialized_us_per_launch': [round(v, 1) for v in kernel_us],
             'parallelism': f'objects sharded contiguously over {world} GPU(s)' + (
                 '' if world == 1 else ', result rows stored peer-to-peer into every rank\'s symmetric buffer by the kernel + 1 symmetric-memory barrier per step'
                 if gathers else ', 1 NCCL all-gather of [N,24] rows per step' + gather_note)})

@@ -93,12 +93,25 @@ typedef struct mrpnp_params {
      * row_offset + i -- peer-to-peer stores over NVLink / NVSwitch from the solver's epilogue -- instead of into
      * `result` (which may then be NULL).  peer_results[r] = device pointer, valid on THIS device, of rank r's
      * [n_total, 24] float buffer (this rank's own buffer included); e.g. the buffer_ptrs of a torch symmetric-memory
-     * allocation.  The rows are complete on all ranks once every rank's launch has finished: follow the call with a
-     * cross-rank barrier on the same stream (7 us on NVSwitch, against ~20 us for an NCCL all-gather of the rows). */
+     * allocation.  The rows are complete on all ranks once every rank's launch has finished: either follow the call
+     * with a cross-rank barrier on the same stream, or let the kernel signal completion itself (below).
+     *
+     * Completion flags (no barrier, no rank waits for another rank's solve): with peer_flags[0] != NULL the LAST thread
+     * block of the launch, after a system-scope fence, stores flag_value into peer_flags[r][flag_slot] of every rank r
+     * (release store into that rank's flag array, `flag_slot` = this rank).  A consumer waits for all ranks' slots of ITS
+     * array to reach the value (mrpnp_gather_wait) when it needs the rows, not before.  Write-after-read protection for
+     * the next use of the same buffers: with acks != NULL the launch first waits until acks[r] >= ack_value for every
+     * r < n_peers -- `acks` is THIS rank's array, which rank r's consumer advances with mrpnp_gather_wait(...,
+     * peer_acks) once it has read the previous contents.  Both waits give up after about a second and count a
+     * time-out (mrpnp_gather_timeouts) instead of hanging the device. */
     int32_t n_peers;
-    int32_t reserved2;
+    int32_t flag_slot;
     int64_t row_offset;
     float* peer_results[MRPNP_MAX_PEERS];
+    uint32_t* peer_flags[MRPNP_MAX_PEERS];
+    uint32_t flag_value;
+    uint32_t ack_value;
+    const uint32_t* acks;
     /* MRPNP_PREC_FAST: half-widths of the bands around Ceres' decision thresholds (|cost change| = 1e-6 cost,
      * rho = 1e-3) inside which a decision is left to the exact fp64 routine.  band_first: error of the FIRST step's cost
      * change relative to the cost (two independently rounded fp32 sums); later steps: band_rel |change| +
@@ -171,6 +184,15 @@ typedef struct mrpnp_dense_params {
                          /* selected by the pointer), proj_logstd is ignored and `labels` picks channels            */
                          /* [3c,3c+3) and [3C+2c, 3C+2c+2) of each object (fcn_noc_decoder.py:242-267)              */
     int64_t pred_stride; /* floats between consecutive objects of all_pred (2*5*C*H*W for the flip-paired view)    */
+    /* MultiClassNormDimCoder.decode in the prologue (dim_coder/multiclass_norm_dim_coder.py:28-36).  dim_means != NULL: */
+    /* `dims` / `dims_var` of mrpnp_solve_dense are the ENCODED regression outputs, decoded per object with its label   */
+    /* (required then): dims = dim * std_c + mean_c, dims_var = dim_var * std_c^2.  The decoded values are also written  */
+    /* to dims_out / dims_var_out [N,3] when those are not NULL (the score stage and the result rows need them).         */
+    const float* dim_means;   /* [n_dim_classes, 3] device, or NULL = dims are already decoded                          */
+    const float* dim_stds;    /* [n_dim_classes, 3] device                                                             */
+    int32_t n_dim_classes;    /* labels outside [0, n_dim_classes) fail the object (result_val 0)                       */
+    float* dims_out;          /* [N,3] or NULL                                                                         */
+    float* dims_var_out;      /* [N,3] or NULL                                                                         */
 } mrpnp_dense_params;
 
 int mrpnp_solve_dense(mrpnp_ctx* ctx, const mrpnp_params* p, const mrpnp_dense_params* dp,
@@ -207,6 +229,20 @@ int mrpnp_pose_features(mrpnp_ctx* ctx, const float* rows, const float* dims, co
 int mrpnp_finish_scores(mrpnp_ctx* ctx, const float* score_logits, const float* rows, const float* dims,
                         const float* det_scores, int32_t pre_sigmoid, float* scores, float* bbox_3d, int32_t n,
                         void* stream);
+
+/* The whole score stage in ONE launch: mrpnp_pose_features -> MLPScoreHead's layers -> mrpnp_finish_scores, for the
+ * network shape of every reference config (mlp_score_head.py:11-115 with num_pose_fcs = num_fused_fcs = 1, fusion 'add'):
+ *   h1 = relu(W1 x + b1) + reg_fc_out;   h2 = relu(W2 h1 + b2);   logit = w3 . h2 + b3
+ * w1 [H1,17] = pose_fcs[0].weight, w2t [H1,H2] = fused_fcs[0].weight TRANSPOSED, w3 [H2] = fc_out.weight, b3 [1];
+ * reg_fc_out [N,H1] or NULL.  The first twelve arguments are those of mrpnp_pose_features, det_scores / pre_sigmoid /
+ * scores / bbox_3d those of mrpnp_finish_scores; cov_calib [N,16] and logits [N] (raw scores) may be NULL. */
+int mrpnp_score_stage(mrpnp_ctx* ctx, const float* rows, const float* dims, const float* cov_calib_logscale,
+                      float cov_correction_sd, int32_t distance_z_depth, int32_t use_calib,
+                      const float* norm_mean, const float* norm_var, const float* norm_weight, const float* norm_bias,
+                      float norm_eps, const float* reg_fc_out, const float* w1, const float* b1, const float* w2t,
+                      const float* b2, const float* w3, const float* b3, int32_t h1, int32_t h2,
+                      const float* det_scores, int32_t pre_sigmoid, float* scores, float* bbox_3d, float* cov_calib,
+                      float* logits, int32_t n, void* stream);
 
 /* Class-wise 3-D NMS on bird's-eye-view rotated boxes (MonoRUnRoIHead.multiclass_3d_result_nms,
  * monorun_roi_head.py:619-680; mmdet3d nms_gpu on centre (x, z), extent (l, w), angle ry): per image and class, in
@@ -291,6 +327,19 @@ int64_t mrpnp_launch_count(const mrpnp_ctx* ctx);
 /* MRPNP_PREC_FAST: number of objects the fp32 path handed to the exact fp64 routine (a point near a clip bound, a
  * decision inside its rounding band) since the context was created.  Synchronises the device. */
 int64_t mrpnp_handed_back_count(mrpnp_ctx* ctx);
+
+/* Consumer side of the fused all-gather's completion flags, asynchronous on `stream` (one warp):
+ *   flags != NULL: wait until flags[r] >= value for every r < n (this rank's flag array; slot r is written by rank r's
+ *                  solver launch, see mrpnp_params.peer_flags) -- afterwards all n ranks' rows are in the local buffer;
+ *   peer_acks != NULL: then store ack_value into peer_acks[r][ack_slot] for every r < n (release, system scope): "this
+ *                  rank has finished reading", the signal mrpnp_params.acks waits for before the buffers are rewritten.
+ * Call it with flags only before the consumer, with peer_acks only after it, or with both when nothing reads the rows
+ * in between.  The wait gives up after about a second (mrpnp_gather_timeouts). */
+int mrpnp_gather_wait(mrpnp_ctx* ctx, const uint32_t* flags, int32_t n, uint32_t value, uint32_t* const* peer_acks,
+                      int32_t ack_slot, uint32_t ack_value, void* stream);
+
+/* Number of flag / ack waits that timed out since the context was created (0 in a healthy run).  Synchronises. */
+int64_t mrpnp_gather_timeouts(mrpnp_ctx* ctx);
 
 /* Static facts about the solver kernel for the given problem: writes warps per CTA, CTAs, dynamic
  * shared memory bytes and whether the TMA path is taken into info[0..3]. */

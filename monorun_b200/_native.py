@@ -118,8 +118,8 @@ def check(rc):
 
 
 EXPORTED = ['mrpnp_default_params', 'mrpnp_create', 'mrpnp_destroy', 'mrpnp_solve', 'mrpnp_solve_dense', 'mrpnp_solve_host',
-            'mrpnp_launch_count', 'mrpnp_handed_back_count', 'mrpnp_kernel_info', 'mrpnp_version', 'mrpnp_last_error', 'mrpnp_pose_features',
-            'mrpnp_finish_scores', 'mrpnp_nms_bev', 'mrpnp_solve_noc', 'mrpnp_exact_hessian', 'mrpnp_solve_6dof', 'pnp_uncert']
+            'mrpnp_launch_count', 'mrpnp_handed_back_count', 'mrpnp_gather_wait', 'mrpnp_gather_timeouts', 'mrpnp_kernel_info', 'mrpnp_version', 'mrpnp_last_error', 'mrpnp_pose_features',
+            'mrpnp_finish_scores', 'mrpnp_score_stage', 'mrpnp_nms_bev', 'mrpnp_solve_noc', 'mrpnp_exact_hessian', 'mrpnp_solve_6dof', 'pnp_uncert']
 HEAD_EXPORTED = ['mrhead_create', 'mrhead_destroy', 'mrhead_version', 'mrhead_last_error', 'mrhead_launch_count',
                  'mrhead_pack_input', 'mrhead_conv', 'mrhead_latent_bias', 'mrhead_carafe', 'mrhead_workspace_bytes',
                  'mrhead_forward']

@@ -163,7 +163,8 @@ struct DenseArgs {
     const float* dims;
     const float* dims_var;
     const float* distance;
-    const int64_t* labels;
+    const int64_t* labels;       // channel selection (NULL for pre-sliced maps)
+    const int64_t* dim_labels;   // class of each object for the dimension coder (NULL without dim_means)
 };
 
 int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const float* c2d, const float* wgt,
@@ -184,6 +185,15 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     kp.inl_in = inl_in; kp.result = result; kp.inl_out = inl_out; kp.result64 = result64;
     kp.n_peers = p->n_peers; kp.row_offset = p->row_offset;
     for (int r = 0; r < MRPNP_MAX_PEERS; ++r) kp.peer[r] = r < p->n_peers ? p->peer_results[r] : nullptr;
+    const bool flags = p->n_peers > 0 && p->peer_flags[0] != nullptr;
+    for (int r = 0; r < MRPNP_MAX_PEERS; ++r) kp.peer_flag[r] = (flags && r < p->n_peers) ? p->peer_flags[r] : nullptr;
+    if (flags) {
+        for (int r = 0; r < p->n_peers; ++r)
+            if (!p->peer_flags[r]) return fail(MRPNP_ERR_ARG, "peer_flags[r] is NULL for r < n_peers%s");
+        if (p->flag_slot < 0 || p->flag_slot >= MRPNP_MAX_PEERS) return fail(MRPNP_ERR_ARG, "flag_slot outside [0, 8)%s");
+    }
+    kp.flag_slot = p->flag_slot; kp.flag_value = p->flag_value;
+    kp.acks = p->n_peers > 0 ? p->acks : nullptr; kp.ack_value = p->ack_value;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (precision == MRPNP_PREC_FAST && p->n_obj > ctx->redo_cap) {
         // grow the hand-back lists (cudaFree waits for the launches still using them)
@@ -224,6 +234,12 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     kp.roi_w = dense ? dense->dp->roi_w : 0;
     kp.dims = dense ? dense->dims : nullptr;
     kp.dims_var = dense ? dense->dims_var : nullptr;
+    kp.dim_means = dense ? dense->dp->dim_means : nullptr;
+    kp.dim_stds = dense ? dense->dp->dim_stds : nullptr;
+    kp.dim_labels = dense ? reinterpret_cast<const long long*>(dense->dim_labels) : nullptr;
+    kp.n_dim_classes = dense ? dense->dp->n_dim_classes : 0;
+    kp.dims_out = dense ? dense->dp->dims_out : nullptr;
+    kp.dims_var_out = dense ? dense->dp->dims_var_out : nullptr;
     for (int i = 0; i < 3; ++i) {
         kp.noc_mean[i] = dense ? dense->dp->noc_mean[i] : 0.f;
         kp.noc_std[i] = dense ? dense->dp->noc_std[i] : 1.f;
@@ -321,6 +337,35 @@ void mrpnp_destroy(mrpnp_ctx* c) {
 
 int64_t mrpnp_launch_count(const mrpnp_ctx* c) { return c ? c->launches : 0; }
 
+int mrpnp_gather_wait(mrpnp_ctx* ctx, const uint32_t* flags, int32_t n, uint32_t value, uint32_t* const* peer_acks,
+                      int32_t ack_slot, uint32_t ack_value, void* stream) {
+    if (!ctx) return fail(MRPNP_ERR_ARG, "ctx is NULL%s");
+    if (n < 1 || n > MRPNP_MAX_PEERS) return fail(MRPNP_ERR_ARG, "n outside [1, 8]%s");
+    if (!flags && !peer_acks) return fail(MRPNP_ERR_ARG, "neither flags nor peer_acks given%s");
+    if (peer_acks && (ack_slot < 0 || ack_slot >= MRPNP_MAX_PEERS)) return fail(MRPNP_ERR_ARG, "ack_slot outside [0, 8)%s");
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    mrpnp::KParams kp{};   // carries the peer pointers by value
+    if (peer_acks)
+        for (int r = 0; r < n; ++r) {
+            if (!peer_acks[r]) return fail(MRPNP_ERR_ARG, "peer_acks[r] is NULL for r < n%s");
+            kp.peer_flag[r] = peer_acks[r];
+        }
+    mrpnp::gather_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags, n, value, kp, peer_acks ? n : 0, ack_slot,
+                                                                             ack_value, ctx->stats);
+    MR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return MRPNP_OK;
+}
+
+int64_t mrpnp_gather_timeouts(mrpnp_ctx* c) {
+    if (!c || !c->stats) return 0;
+    unsigned long long v = 0;
+    cudaSetDevice(c->device);
+    if (cudaMemcpy(&v, c->stats + 1, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;   // synchronises the device
+    return (int64_t)v;
+}
+
 int64_t mrpnp_handed_back_count(mrpnp_ctx* c) {
     if (!c || !c->stats) return 0;
     unsigned long long v = 0;
@@ -349,6 +394,43 @@ int mrpnp_pose_features(mrpnp_ctx* ctx, const float* rows, const float* dims, co
     sp.norm_mean = norm_mean; sp.norm_var = norm_var; sp.norm_weight = norm_weight; sp.norm_bias = norm_bias;
     sp.norm_eps = norm_eps; sp.feat = feat; sp.cov_calib = cov_calib; sp.n = n;
     mrpnp::pose_features_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sp);
+    MR_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return MRPNP_OK;
+}
+
+int mrpnp_score_stage(mrpnp_ctx* ctx, const float* rows, const float* dims, const float* cov_calib_logscale,
+                      float cov_correction_sd, int32_t distance_z_depth, int32_t use_calib,
+                      const float* norm_mean, const float* norm_var, const float* norm_weight, const float* norm_bias,
+                      float norm_eps, const float* reg_fc_out, const float* w1, const float* b1, const float* w2t,
+                      const float* b2, const float* w3, const float* b3, int32_t h1, int32_t h2,
+                      const float* det_scores, int32_t pre_sigmoid, float* scores, float* bbox_3d, float* cov_calib,
+                      float* logits, int32_t n, void* stream) {
+    if (!ctx) return fail(MRPNP_ERR_ARG, "ctx is NULL%s");
+    if (n < 0) return fail(MRPNP_ERR_ARG, "n < 0%s");
+    if (n == 0) return MRPNP_OK;
+    if (!rows || !dims || !w1 || !b1 || !w2t || !b2 || !w3 || !b3 || (!scores && !bbox_3d && !logits))
+        return fail(MRPNP_ERR_ARG, "NULL tensor pointer%s");
+    if (h1 < 1 || h2 < 1 || h1 > 4096 || h2 > 4096) return fail(MRPNP_ERR_ARG, "layer widths outside [1, 4096]%s");
+    const bool any_norm = norm_mean || norm_var || norm_weight || norm_bias;
+    if (any_norm && !(norm_mean && norm_var && norm_weight && norm_bias))
+        return fail(MRPNP_ERR_ARG, "pose_norm needs mean, var, weight and bias%s");
+    MR_CUDA(cudaSetDevice(ctx->device));
+    g_err[0] = 0;
+    mrpnp::ScoreParams sp;
+    sp.rows = rows; sp.dims = dims; sp.calib_logscale = cov_calib_logscale;
+    sp.corr_sd = cov_correction_sd; sp.corr_z_depth = distance_z_depth; sp.use_calib = use_calib;
+    sp.norm_mean = norm_mean; sp.norm_var = norm_var; sp.norm_weight = norm_weight; sp.norm_bias = norm_bias;
+    sp.norm_eps = norm_eps; sp.feat = nullptr; sp.cov_calib = cov_calib; sp.n = n;
+    mrpnp::MlpParams mp;
+    mp.reg_fc_out = reg_fc_out; mp.w1 = w1; mp.b1 = b1; mp.w2t = w2t; mp.b2 = b2; mp.w3 = w3; mp.b3 = b3;
+    mp.h1 = h1; mp.h2 = h2; mp.det_scores = det_scores; mp.pre_sigmoid = pre_sigmoid;
+    mp.logits = logits; mp.scores = scores; mp.bbox3d = bbox_3d;
+    const size_t smem = sizeof(float) * ((size_t)mrpnp::kScoreTile * (20 + h1 + mrpnp::kScoreThreads / 32));
+    if (smem > (size_t)ctx->max_smem_optin) return fail(MRPNP_ERR_ARG, "pose layer too wide for shared memory%s");
+    MR_CUDA(cudaFuncSetAttribute(mrpnp::score_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ctas = (n + mrpnp::kScoreTile - 1) / mrpnp::kScoreTile;
+    mrpnp::score_stage_kernel<<<ctas, mrpnp::kScoreThreads, smem, static_cast<cudaStream_t>(stream)>>>(sp, mp);
     MR_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return MRPNP_OK;
@@ -547,7 +629,11 @@ int mrpnp_solve_dense(mrpnp_ctx* ctx, const mrpnp_params* p, const mrpnp_dense_p
             return fail(MRPNP_ERR_ARG, "pred_stride must be a multiple of 4 floats%s");
         proj_logstd = noc_pred + (size_t)3 * C * p->n_pts;
     }
-    const DenseArgs da{dp, dims, dims_var, distance, C > 0 ? labels : nullptr};
+    if (dp->dim_means) {
+        if (!dp->dim_stds || !labels || dp->n_dim_classes < 1)
+            return fail(MRPNP_ERR_ARG, "dim_means needs dim_stds, labels and n_dim_classes >= 1%s");
+    }
+    const DenseArgs da{dp, dims, dims_var, distance, C > 0 ? labels : nullptr, dp->dim_means ? labels : nullptr};
     // alignment for the TMA path is decided on the two streamed tensors; `rois` rides in the coords_2d slot
     return solve_device(ctx, &q, noc_pred, rois, proj_logstd, cam_mats, uv_range, init_pose, nullptr, result,
                         inlier_out, nullptr, static_cast<cudaStream_t>(stream), &da);

@@ -50,8 +50,14 @@ struct KParams {
     float z_min, std_scale, istd_thres;
     // fused head -> PnP entry (mrpnp_solve_dense): c3d = noc_pred [N,3,P], wgt = proj_logstd [N,2,P], c2d = rois [N,4]
     int dense, roi_w;
-    const float* dims;      // [N,3] decoded dimensions (l,h,w)
+    const float* dims;      // [N,3] dimensions (l,h,w): decoded, or encoded when dim_means is set
     const float* dims_var;  // [N,3] or NULL
+    const float* dim_means; // [n_dim_classes,3] or NULL: MultiClassNormDimCoder.decode in the prologue
+    const float* dim_stds;
+    const long long* dim_labels;
+    int n_dim_classes;
+    float* dims_out;        // [N,3] or NULL: decoded dimensions
+    float* dims_var_out;
     float noc_mean[3], noc_std[3];
     const float* distance;  // [N] or NULL
     const long long* labels;  // [N] class ids or NULL; used when pred_stride != 0 (c3d/wgt point into all_pred)
@@ -78,7 +84,71 @@ struct KParams {
     float* peer[MRPNP_MAX_PEERS];
     int n_peers;
     long long row_offset;
+    // completion flags of the fused gather (mrpnp_params.peer_flags / acks)
+    unsigned int* peer_flag[MRPNP_MAX_PEERS];
+    int flag_slot;
+    unsigned int flag_value, ack_value;
+    const unsigned int* acks;
 };
+
+// ------------------------------------------------------------------ cross-GPU flags (system scope)
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kFlagTimeoutNs = 1000000000ull;
+
+// Spin until *p >= value (wrap-around safe: the flags are step counters).  False after kFlagTimeoutNs.
+__device__ __forceinline__ bool wait_flag(const unsigned int* p, unsigned int value) {
+    if ((int)(ld_acquire_sys(p) - value) >= 0) return true;
+    const unsigned long long t0 = global_timer_ns();
+    while ((int)(ld_acquire_sys(p) - value) < 0) {
+        __nanosleep(100);
+        if (global_timer_ns() - t0 > kFlagTimeoutNs) return false;
+    }
+    return true;
+}
+
+// First thing a launch with peers does: the consumers of every rank have released the buffers it is about to rewrite.
+__device__ __forceinline__ void wait_for_acks(const KParams& kp) {
+    if (kp.n_peers == 0 || kp.acks == nullptr) return;
+    if ((int)threadIdx.x < kp.n_peers) {
+        if (!wait_flag(kp.acks + threadIdx.x, kp.ack_value) && kp.stats) atomicAdd(kp.stats + 1, 1ull);
+    }
+    __syncthreads();
+}
+
+// Last thing the LAST thread block does (its thread 0, after it observed every other block's arrival on the launch's
+// counter): the rows of all blocks are performed system-wide, then every rank's flag slot of this rank is raised.
+__device__ __forceinline__ void raise_peer_flags(const KParams& kp) {
+    if (kp.n_peers == 0 || kp.peer_flag[0] == nullptr) return;
+    __threadfence_system();
+#pragma unroll 1
+    for (int r = 0; r < kp.n_peers; ++r) st_release_sys(kp.peer_flag[r] + kp.flag_slot, kp.flag_value);
+}
+
+// Consumer side (mrpnp_gather_wait): one warp.
+__global__ void gather_wait_kernel(const unsigned int* flags, int n, unsigned int value, KParams kp_acks, int n_acks,
+                                   int ack_slot, unsigned int ack_value, unsigned long long* stats) {
+    const int lane = threadIdx.x;
+    if (flags && lane < n) {
+        if (!wait_flag(flags + lane, value) && stats) atomicAdd(stats + 1, 1ull);
+    }
+    __syncwarp();
+    if (lane < n_acks) {
+        __threadfence_system();
+        st_release_sys(kp_acks.peer_flag[lane] + ack_slot, ack_value);
+    }
+}
 
 // The 96-byte result row of one object: lanes 0..23 hold its floats.
 __device__ __forceinline__ void store_result_row(const KParams& kp, int obj, int lane, float v) {

@@ -41,10 +41,16 @@ namespace mrpnp {
 
 // ------------------------------------------------------------------ packed / scalar arithmetic behind one set of names
 __device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-// Three per-point operands: measured on B200 (tools/microbench5.cu) an FFMA2 reading three register PAIRS issues every
+// Three per-point operands.  In isolation (tools/microbench5.cu) an FFMA2 reading three register PAIRS issues every
 // 3.9 cycles per scheduler -- slower than the two scalar FFMAs (2 x 1.56) it replaces -- while a packed instruction with
-// a scalar-broadcast operand or only two operands (FMUL2 / FADD2) issues every 2.0 (against 2 x 1.19 scalar).
+// a scalar-broadcast operand or only two operands (FMUL2 / FADD2) issues every 2.0 (against 2 x 1.19 scalar).  Inside
+// the kernel the packed form still wins by 2-3 % at 8 warps (profiles/r02_ab_variants.txt, c_w8p3 against c_w8): the
+// passes are short of instruction-cache and issue slots, not of FMA-pipe cycles.  MRPNP_EXP_SCALAR3 builds the other.
+#ifndef MRPNP_EXP_SCALAR3
+__device__ __forceinline__ float2 vfma3(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
 __device__ __forceinline__ float2 vfma3(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
 __device__ __forceinline__ float vfma3(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
@@ -191,17 +197,37 @@ enum PassKind { kPassFirst = 0, kPassDelta = 2, kPassUndo = 3 };
 struct PassArgs {
     float cs, sn, tx, ty, tz;   // evaluation point (kPassFirst); for the other kinds see `step`
     DeltaStep step;
-    CamN cam;
-    ClipWindow win;
+    const float* consts;        // shared memory: CamN (8 floats) then ClipWindow (5 floats) of the object -- read inside
+                                // the passes, so that they are not live in registers across the scalar LM algebra
     bool check;                 // per-point clip tests (always on for kPassFirst)
     bool anchor;                // kPassFirst: the fp64 anchor evaluation instead of the initial one
 };
 
+__device__ __forceinline__ CamN args_cam(const PassArgs& u) {
+    CamN c;
+    c.fx = u.consts[0]; c.fy = u.consts[1]; c.cx = u.consts[2]; c.cy = u.consts[3];
+    c.ifx = u.consts[4]; c.ify = u.consts[5]; c.ncxi = u.consts[6]; c.ncyi = u.consts[7];
+    return c;
+}
+__device__ __forceinline__ ClipWindow args_win(const PassArgs& u) {
+    ClipWindow w;
+    w.xmid = u.consts[8]; w.xhalf = u.consts[9]; w.ymid = u.consts[10]; w.yhalf = u.consts[11]; w.zlo = u.consts[12];
+    return w;
+}
+__device__ __forceinline__ void store_consts(float* consts, const CamN& c, const ClipWindow& w, int lane) {
+    if (lane == 0) {
+        consts[0] = c.fx; consts[1] = c.fy; consts[2] = c.cx; consts[3] = c.cy;
+        consts[4] = c.ifx; consts[5] = c.ify; consts[6] = c.ncxi; consts[7] = c.ncyi;
+        consts[8] = w.xmid; consts[9] = w.xhalf; consts[10] = w.ymid; consts[11] = w.yhalf; consts[12] = w.zlo;
+    }
+    __syncwarp();
+}
+
 // The body of every pass for one point (V = float) or one pair of points (V = float2) at slot index idx.
 // `live`: only read for V = float (the remainder path): a dead lane computes on point 0 with M = 0 and stores nothing.
 template <int WMODE, int KIND, class V>
-__device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int idx, bool live, const PassArgs& u, V a[15],
-                                           PassFlags& f) {
+__device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int idx, bool live, const PassArgs& u,
+                                           const CamN& cam, const ClipWindow& win, V a[15], PassFlags& f) {
     using L = Lanes<V>;
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     float* s3 = slot;
@@ -218,11 +244,11 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
             // weights -> M = F W^T W F, stored in place of W for the later passes
             if (WMODE == MRPNP_W_FULL) {
                 const V wxx = m00, wxy = m01, wyy = m11;
-                m00 = vmul(vfma3(wxx, wxx, vmul(wxy, wxy)), L::bc(u.cam.fx * u.cam.fx));
-                m11 = vmul(vfma3(wyy, wyy, vmul(wxy, wxy)), L::bc(u.cam.fy * u.cam.fy));
-                m01 = vmul(vmul(wxy, vadd(wxx, wyy)), L::bc(u.cam.fx * u.cam.fy));
+                m00 = vmul(vfma3(wxx, wxx, vmul(wxy, wxy)), L::bc(cam.fx * cam.fx));
+                m11 = vmul(vfma3(wyy, wyy, vmul(wxy, wxy)), L::bc(cam.fy * cam.fy));
+                m01 = vmul(vmul(wxy, vadd(wxx, wyy)), L::bc(cam.fx * cam.fy));
             } else {
-                const V t0 = vmul(m00, L::bc(u.cam.fx)), t1 = vmul(m11, L::bc(u.cam.fy));
+                const V t0 = vmul(m00, L::bc(cam.fx)), t1 = vmul(m11, L::bc(cam.fy));
                 m00 = vmul(t0, t0);
                 m11 = vmul(t1, t1);
             }
@@ -244,13 +270,13 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
         if (!u.anchor) {
             // plain fp32: the residuals are many pixels here, and the decision on the first step is checked against
             // its own rounding (see the LM loop)
-            e0 = vsub(xn, vfma(o0, L::bc(u.cam.ifx), L::bc(u.cam.ncxi)));
-            e1 = vsub(yn, vfma(o1, L::bc(u.cam.ify), L::bc(u.cam.ncyi)));
+            e0 = vsub(xn, vfma(o0, L::bc(cam.ifx), L::bc(cam.ncxi)));
+            e1 = vsub(yn, vfma(o1, L::bc(cam.ify), L::bc(cam.ncyi)));
         } else {
             // the anchor: residual chain in fp64, rounded once to fp32, REPLACES the observations in the slot
             const double cs = (double)u.cs, sn = (double)u.sn, tx = (double)u.tx, ty = (double)u.ty, tz = (double)u.tz;
-            const double ifx = 1.0 / (double)u.cam.fx, ify = 1.0 / (double)u.cam.fy;   // loop-invariant
-            const double ncxi = -(double)u.cam.cx * ifx, ncyi = -(double)u.cam.cy * ify;
+            const double ifx = 1.0 / (double)cam.fx, ify = 1.0 / (double)cam.fy;   // loop-invariant
+            const double ncxi = -(double)cam.cx * ifx, ncyi = -(double)cam.cy * ify;
             float r0[2], r1[2];
 #pragma unroll
             for (int k = 0; k < L::kWidth; ++k) {
@@ -270,8 +296,8 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
         }
         // clip proximity on the fp32 projection (margins far above its rounding)
         f.mz = fminf(f.mz, L::hmin(z1));
-        f.mx = fmaxf(f.mx, L::habsmax(vsub(xn, L::bc(u.win.xmid))));
-        f.my = fmaxf(f.my, L::habsmax(vsub(yn, L::bc(u.win.ymid))));
+        f.mx = fmaxf(f.mx, L::habsmax(vsub(xn, L::bc(win.xmid))));
+        f.my = fmaxf(f.my, L::habsmax(vsub(yn, L::bc(win.ymid))));
         V v0, v1;
         if (WMODE == MRPNP_W_FULL) {
             v0 = vfma3(m00, e0, vmul(m01, e1));
@@ -302,8 +328,8 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
         if (L::kWidth == 2 || live) { L::st(s2 + idx, e0); L::st(s2 + P + idx, e1); }   // speculative: most steps are accepted
         if (u.check) {
             f.mz = fminf(f.mz, L::hmin(z1));
-            f.mx = fmaxf(f.mx, L::habsmax(vsub(xnp, L::bc(u.win.xmid))));
-            f.my = fmaxf(f.my, L::habsmax(vsub(ynp, L::bc(u.win.ymid))));
+            f.mx = fmaxf(f.mx, L::habsmax(vsub(xnp, L::bc(win.xmid))));
+            f.my = fmaxf(f.my, L::habsmax(vsub(ynp, L::bc(win.ymid))));
         }
         V v0, v1, d0, d1;
         if (WMODE == MRPNP_W_FULL) {
@@ -346,29 +372,22 @@ __device__ __forceinline__ bool flags_raised(const PassFlags& f, const ClipWindo
 // The out-of-line routines (remainder, roll-back) take their PassArgs through the warp's shared-memory scratch: a struct
 // passed by value or reference to a non-inlined function would be given a home in LOCAL memory, and with ~106 KB of
 // local memory per CTA against ~28 KB of L1 every access to it from the hot loop would be an L2 round trip.
-constexpr int kPassArgWords = (int)(sizeof(PassArgs) / sizeof(float));
-static_assert(sizeof(PassArgs) % sizeof(float) == 0 && kPassArgWords <= 48, "PassArgs must fit the scratch");
 __device__ __forceinline__ void stash_args(float* smem, const PassArgs& u, int lane) {
     if (lane == 0) {
         smem[0] = u.cs; smem[1] = u.sn; smem[2] = u.tx; smem[3] = u.ty; smem[4] = u.tz;
         smem[5] = u.step.cp; smem[6] = u.step.sp; smem[7] = u.step.txp; smem[8] = u.step.typ; smem[9] = u.step.tzp;
         smem[10] = u.step.ncdm1; smem[11] = u.step.sd; smem[12] = u.step.dtx; smem[13] = u.step.dty; smem[14] = u.step.dtz;
-        smem[15] = u.cam.fx; smem[16] = u.cam.fy; smem[17] = u.cam.cx; smem[18] = u.cam.cy;
-        smem[19] = u.cam.ifx; smem[20] = u.cam.ify; smem[21] = u.cam.ncxi; smem[22] = u.cam.ncyi;
-        smem[23] = u.win.xmid; smem[24] = u.win.xhalf; smem[25] = u.win.ymid; smem[26] = u.win.yhalf; smem[27] = u.win.zlo;
-        smem[28] = u.anchor ? 1.f : 0.f;
+        smem[15] = u.anchor ? 1.f : 0.f;
     }
     __syncwarp();
 }
-__device__ __forceinline__ PassArgs fetch_args(const float* smem) {
+__device__ __forceinline__ PassArgs fetch_args(const float* smem, const float* consts) {
     PassArgs u;
     u.cs = smem[0]; u.sn = smem[1]; u.tx = smem[2]; u.ty = smem[3]; u.tz = smem[4];
     u.step.cp = smem[5]; u.step.sp = smem[6]; u.step.txp = smem[7]; u.step.typ = smem[8]; u.step.tzp = smem[9];
     u.step.ncdm1 = smem[10]; u.step.sd = smem[11]; u.step.dtx = smem[12]; u.step.dty = smem[13]; u.step.dtz = smem[14];
-    u.cam.fx = smem[15]; u.cam.fy = smem[16]; u.cam.cx = smem[17]; u.cam.cy = smem[18];
-    u.cam.ifx = smem[19]; u.cam.ify = smem[20]; u.cam.ncxi = smem[21]; u.cam.ncyi = smem[22];
-    u.win.xmid = smem[23]; u.win.xhalf = smem[24]; u.win.ymid = smem[25]; u.win.yhalf = smem[26]; u.win.zlo = smem[27];
-    u.anchor = smem[28] != 0.f;
+    u.anchor = smem[15] != 0.f;
+    u.consts = consts;
     u.check = true;
     return u;
 }
@@ -378,8 +397,10 @@ __device__ __forceinline__ PassArgs fetch_args(const float* smem) {
 // (initial evaluation) into scratch[16..18] and returns the clip flag.  kind: PassKind; args: stash_args().
 template <int WMODE>
 __device__ __noinline__ bool pass_remainder(float* slot, int P, int start, int n, int lane, int kind, const float* args,
-                                            float* scratch) {
-    const PassArgs u = fetch_args(args);
+                                            const float* consts, float* scratch) {
+    const PassArgs u = fetch_args(args, consts);
+    const CamN cam = args_cam(u);
+    const ClipWindow win = args_win(u);
     float a[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = 0.f;
@@ -387,9 +408,9 @@ __device__ __noinline__ bool pass_remainder(float* slot, int P, int start, int n
     for (int base = start; base < n; base += 32) {
         const int idx = base + lane;
         const bool live = idx < n;
-        if (kind == kPassFirst) pass_point<WMODE, kPassFirst, float>(slot, P, live ? idx : 0, live, u, a, f);
-        else if (kind == kPassDelta) pass_point<WMODE, kPassDelta, float>(slot, P, live ? idx : 0, live, u, a, f);
-        else pass_point<WMODE, kPassUndo, float>(slot, P, live ? idx : 0, live, u, a, f);
+        if (kind == kPassFirst) pass_point<WMODE, kPassFirst, float>(slot, P, live ? idx : 0, live, u, cam, win, a, f);
+        else if (kind == kPassDelta) pass_point<WMODE, kPassDelta, float>(slot, P, live ? idx : 0, live, u, cam, win, a, f);
+        else pass_point<WMODE, kPassUndo, float>(slot, P, live ? idx : 0, live, u, cam, win, a, f);
     }
     __syncwarp();
     if (kind == kPassUndo) return false;
@@ -405,7 +426,7 @@ __device__ __noinline__ bool pass_remainder(float* slot, int P, int start, int n
         }
     }
     __syncwarp();
-    return __any_sync(kFull, flags_raised(f, u.win));
+    return __any_sync(kFull, flags_raised(f, win));
 }
 
 // One evaluation: the packed loop over the 64-point groups [0, n_main) -- from the observations (first == true: the
@@ -419,17 +440,19 @@ __device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, 
 #pragma unroll
     for (int i = 0; i < 15; ++i) a[i] = make_float2(0.f, 0.f);
     PassFlags f = {1e30f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const CamN cam = args_cam(u);
+    const ClipWindow win = args_win(u);
     const int end = n_main + 2 * lane;
     if (first) {
 #pragma unroll 1
-        for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassFirst, float2>(slot, P, idx, true, u, a, f);
+        for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassFirst, float2>(slot, P, idx, true, u, cam, win, a, f);
     } else {
 #ifndef MRPNP_EXP_DELTA_UNROLL
 #define MRPNP_EXP_DELTA_UNROLL 1   // 2 measured 4 % slower (instruction cache)
 #endif
         constexpr int kDeltaUnroll = MRPNP_EXP_DELTA_UNROLL;
 #pragma unroll kDeltaUnroll
-        for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassDelta, float2>(slot, P, idx, true, u, a, f);
+        for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassDelta, float2>(slot, P, idx, true, u, cam, win, a, f);
     }
     float s[16];
 #pragma unroll
@@ -442,24 +465,26 @@ __device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, 
                    ez = __reduce_max_sync(kFull, __float_as_uint(f.ez));
     if (lane == 0) { scratch[16] = __uint_as_float(ex); scratch[17] = __uint_as_float(ey); scratch[18] = __uint_as_float(ez); }
     __syncwarp();
-    flagged = (first || u.check) && __any_sync(kFull, flags_raised(f, u.win));
+    flagged = (first || u.check) && __any_sync(kFull, flags_raised(f, win));
     if (n > n_main) {
         stash_args(arg_stash, u, lane);
-        flagged = pass_remainder<WMODE>(slot, P, n_main, n, lane, first ? kPassFirst : kPassDelta, arg_stash, scratch) || flagged;
+        flagged = pass_remainder<WMODE>(slot, P, n_main, n, lane, first ? kPassFirst : kPassDelta, arg_stash, u.consts, scratch) || flagged;
     }
     return __all_sync(kFull, fabsf(scratch[lane & 15]) < 3.0e38f);
 }
 
 // Roll the speculative residual update of a rejected candidate back (out of line: rare).  args: stash_args().
 template <int WMODE>
-__device__ __noinline__ void undo_pass(float* slot, int P, int n_main, int n, int lane, const float* args) {
-    const PassArgs u = fetch_args(args);
+__device__ __noinline__ void undo_pass(float* slot, int P, int n_main, int n, int lane, const float* args, const float* consts) {
+    const PassArgs u = fetch_args(args, consts);
+    const CamN cam = args_cam(u);
+    const ClipWindow win = args_win(u);
     float2 a[15];
     PassFlags f;
     const int end = n_main + 2 * lane;
 #pragma unroll 1
-    for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassUndo, float2>(slot, P, idx, true, u, a, f);
-    if (n > n_main) pass_remainder<WMODE>(slot, P, n_main, n, lane, kPassUndo, args, nullptr);
+    for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassUndo, float2>(slot, P, idx, true, u, cam, win, a, f);
+    if (n > n_main) pass_remainder<WMODE>(slot, P, n_main, n, lane, kPassUndo, args, consts, nullptr);
     __syncwarp();
 }
 

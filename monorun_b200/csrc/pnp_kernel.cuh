@@ -112,6 +112,37 @@ __device__ __forceinline__ void weights_and_thresholds(const KParams& kp, float*
 //   istd      = exp(-logstd') / std_scale                                 uncert_prop_pnp_optimizer.py:73
 //   u[j] = x1 - 0.5 + (j + 0.5)(x2 - x1)/W,  v[i] likewise                roi_align of the pixel grid, monorun_roi_head.py:521-523
 // and accumulates the per-axis weight sums for the inlier thresholds (pnp_uncert_cpu.py:164-165).
+// Dimensions of one object, decoded when the caller passed the coder's tables (MultiClassNormDimCoder.decode,
+// dim_coder/multiclass_norm_dim_coder.py:28-36: dims = dim * std_c + mean_c, dims_var = dim_var * std_c^2; mul and add
+// rounded separately, as the two torch launches do).  A label outside the table leaves NaN dimensions: every residual
+// of the object is then NaN and the solve reports failure.
+__device__ __forceinline__ void object_dims(const KParams& kp, int obj, int lane, float d[3], float v[3]) {
+    const float* dm = kp.dims + (size_t)obj * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        d[k] = __ldg(dm + k);
+        v[k] = kp.dims_var ? __ldg(kp.dims_var + (size_t)obj * 3 + k) : 0.f;
+    }
+    if (kp.dim_means) {
+        const long long c = kp.dim_labels[obj];
+        const bool ok = c >= 0 && c < kp.n_dim_classes;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float sd = ok ? __ldg(kp.dim_stds + c * 3 + k) : __int_as_float(0x7fc00000);
+            const float mu = ok ? __ldg(kp.dim_means + c * 3 + k) : 0.f;
+            d[k] = __fadd_rn(__fmul_rn(d[k], sd), mu);
+            v[k] = __fmul_rn(v[k], __fmul_rn(sd, sd));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (kp.dims_out) kp.dims_out[(size_t)obj * 3 + k] = d[k];
+            if (kp.dims_var_out && kp.dims_var) kp.dims_var_out[(size_t)obj * 3 + k] = v[k];
+        }
+    }
+}
+
 __device__ __forceinline__ void dense_decode_and_thresholds(const KParams& kp, int obj, float* slot, int lane,
                                                             float& thr_u, float& thr_v) {
     const int P = kp.n_pts, W = kp.roi_w, H = P / W;
@@ -122,13 +153,9 @@ __device__ __forceinline__ void dense_decode_and_thresholds(const KParams& kp, i
     const float x1 = __ldg(roi + 0), y1 = __ldg(roi + 1), x2 = __ldg(roi + 2), y2 = __ldg(roi + 3);
     const float dx = x2 - x1, dy = y2 - y1, x0 = x1 - 0.5f, y0 = y1 - 0.5f;
     const float inv_w = 1.f / (float)W, inv_h = 1.f / (float)H;
-    const float* dm = kp.dims + (size_t)obj * 3;
-    const float d0 = __ldg(dm + 0), d1 = __ldg(dm + 1), d2 = __ldg(dm + 2);
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (kp.dims_var) {
-        const float* dv = kp.dims_var + (size_t)obj * 3;
-        v0 = __ldg(dv + 0); v1 = __ldg(dv + 1); v2 = __ldg(dv + 2);
-    }
+    float dm[3], dv[3];
+    object_dims(kp, obj, lane, dm, dv);
+    const float d0 = dm[0], d1 = dm[1], d2 = dm[2], v0 = dv[0], v1 = dv[1], v2 = dv[2];
     // distance given: the variance is divided by clamp(distance)^2 instead of scaling_denominator^2 (:41-44)
     float inv_scale = 1.f / kp.std_scale;
     if (kp.distance) inv_scale *= fmaxf(__ldg(kp.distance + obj), kp.distance_min) * kp.inv_scaling_denominator;
@@ -570,6 +597,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
         fence_proxy_async();
     }
     __syncwarp();
+    wait_for_acks(kp);
     uint32_t parity = 0;
 
     while (true) {
@@ -596,6 +624,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) pnp_lm_kernel(const __grid_con
             kp.counters[1] = 0;
             if (kp.work_list) *kp.work_count = 0;  // the follow-up launch consumed the redo list
             __threadfence();
+            raise_peer_flags(kp);
         }
     }
 }

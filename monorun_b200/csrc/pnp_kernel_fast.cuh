@@ -46,11 +46,11 @@ namespace mrpnp {
 #endif
 constexpr int kFastMaxWarps = MRPNP_FAST_WARPS;
 // Per-warp header, 512 B = 128 floats: [0] mbarrier | [4..27] sums buffer A | [32..55] sums buffer B | [56..63] Jacobi
-// scale, LM diagonal | [64..95] argument stash of the out-of-line routines.  The exact routine's 40-double scratch
+// scale, LM diagonal | [64..95] argument stash of the out-of-line routines | [96..111] camera + clip window (pass constants).  The exact routine's 40-double scratch
 // starts at float 32: it only runs between objects, when the fast path's state is dead.
 // A sums buffer: [0..3] J^T r, [4..13] J^T J, [14] cost term, [16..18] extents; [20..23] linear-initialiser result.
 constexpr int kFastHeaderBytes = 512;
-constexpr int kFastBufA = 4, kFastBufB = 32, kFastScaleDiag = 56, kFastArgStash = 64;
+constexpr int kFastBufA = 4, kFastBufB = 32, kFastScaleDiag = 56, kFastArgStash = 64, kFastConsts = 96;
 constexpr int kFastScratch64 = 128;   // byte offset
 constexpr int kNoPending = -1;
 // work counters of one launch (ints, all zero between launches; the last CTA re-arms them)
@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
         fence_proxy_async();
     }
     __syncwarp();
+    wait_for_acks(kp);
     uint32_t parity = 0;
     int pending = kNoPending;
     bool is_redo = false;
@@ -630,8 +631,8 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
         float radius = (float)kInitialRadius, decrease_factor = 2.f, x_norm = 0.f, model_change = 1.f;
         bool reuse_diagonal = false, step_ok = true, first = true, redo = false;
         PassArgs pa;
-        pa.cam = make_camn(camf);
-        pa.win = make_clip_window(camf);
+        store_consts(hdr + kFastConsts, make_camn(camf), make_clip_window(camf), lane);
+        pa.consts = hdr + kFastConsts;
         pa.check = true;
         pa.anchor = false;
         pa.step = DeltaStep{};
@@ -646,7 +647,7 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
                 pa.cs = cs_p; pa.sn = sn_p; pa.tx = pt[1]; pa.ty = pt[2]; pa.tz = pt[3];
                 pa.anchor = cost_evals == 1;
             } else {
-                pa.check = !box_inside_window(pa.win, ext, pa.step.cp, pa.step.sp, pa.step.txp, pa.step.typ, pa.step.tzp);
+                pa.check = !box_inside_window(args_win(pa), ext, pa.step.cp, pa.step.sp, pa.step.txp, pa.step.typ, pa.step.tzp);
             }
             jfin = run_pass<WMODE>(slot, P, n_main, n, lane, pa, from_observations, cand, arg_stash, flagged);
             if (cost_evals == 0) { ext.xm = cand[16]; ext.ym = cand[17]; ext.zm = cand[18]; }
@@ -715,7 +716,7 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
                     TR_MARK(5)
                     // the slot holds the residuals at the rejected candidate (also after the anchor evaluation)
                     stash_args(arg_stash, pa, lane);
-                    undo_pass<WMODE>(slot, P, n_main, n, lane, arg_stash);
+                    undo_pass<WMODE>(slot, P, n_main, n, lane, arg_stash, pa.consts);
                     TR_MARK(6)
                 }
             }
@@ -857,6 +858,7 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) kp.counters[i] = 0;
             __threadfence();
+            raise_peer_flags(kp);
         }
     }
 }

@@ -87,14 +87,18 @@ class UncertPropPnPOptimizer(nn.Module):
         return (cov_calib_scale * cov_calib_scale[:, None]) * pose_cov_pred  # :96-97
 
     def forward_fused(self, noc_pred, proj_logstd, rois, dimensions, dimensions_var, cam_intrinsic, img_shapes,
-                      coord_coder, proj_error_coder, distance=None, init_pose=None, labels=None, num_classes=0):
+                      coord_coder, proj_error_coder, distance=None, init_pose=None, labels=None, num_classes=0,
+                      dim_coder=None, dim_labels=None):
         """Same five outputs as :meth:`forward`, from the dense head's RAW maps: NOC decode, variance-propagated
-        log-std and the RoI pixel grid run inside the PnP kernel (one launch for monorun_roi_head.py:513-529)."""
-        ret_val, yaw_pred, t_vec_pred, pose_cov_pred, _ = self.pnp.forward_fused(
+        log-std and the RoI pixel grid run inside the PnP kernel (one launch for monorun_roi_head.py:513-529).
+        With ``dim_coder`` the dimensions come in encoded, are decoded by the same launch (:503-507) and the decoded
+        ``dimensions``, ``dimensions_var`` are appended to the outputs."""
+        ret_val, yaw_pred, t_vec_pred, pose_cov_pred, _, *decoded = self.pnp.forward_fused(
             noc_pred, proj_logstd, rois, dimensions, dimensions_var, cam_intrinsic, self._uv_range(img_shapes),
             self.std_scale, coord_coder, proj_error_coder, distance=distance, init_pose=init_pose, labels=labels,
-            num_classes=num_classes, ransac_ratio=self.epnp_ransac_thres_ratio or 0.0)
-        return ret_val, yaw_pred, t_vec_pred, pose_cov_pred, self._calibrate(pose_cov_pred)
+            num_classes=num_classes, ransac_ratio=self.epnp_ransac_thres_ratio or 0.0, dim_coder=dim_coder,
+            dim_labels=dim_labels)
+        return (ret_val, yaw_pred, t_vec_pred, pose_cov_pred, self._calibrate(pose_cov_pred), *decoded)
 
 
 class ConvModule(nn.Module):
@@ -304,10 +308,11 @@ class MLPScoreHead(nn.Module):
     state-dict keys (``pose_norm``, ``pose_fcs``, ``fused_fcs``, ``fc_out``).
 
     ``forward`` is the reference's torch sequence (and the fp32 reference of the tests).  ``forward_rows`` is the
-    B200 path: one launch builds the normalised 17-feature rows straight from the solver's result rows (covariance
-    calibration, test-time correction, lower triangle, concatenation, pose_norm: ``mrpnp_pose_features``), the Linear
-    layers run as library GEMMs, one launch finishes (sigmoid, invalid -> 0, product with the 2-D score, the
-    [l,h,w,x,y,z,ry,score] rows: ``mrpnp_finish_scores``)."""
+    B200 path: ONE launch (``mrpnp_score_stage``) builds the normalised 17-feature rows straight from the solver's result
+    rows (covariance calibration, test-time correction, lower triangle, concatenation, pose_norm), runs the three Linear
+    layers and finishes (sigmoid, invalid -> 0, product with the 2-D score, the [l,h,w,x,y,z,ry,score] rows).  Other
+    network shapes (more layers, fusion 'concat') fall back to ``mrpnp_pose_features`` + library GEMMs +
+    ``mrpnp_finish_scores``."""
 
     def __init__(self, reg_fc_out_channels=1024, num_pose_fcs=1, pose_fc_out_channels=1024, fusion_type='add',
                  num_fused_fcs=1, fc_out_channels=256, loss_score=None, mode='linear_average', iou_thres=0.7,
@@ -361,16 +366,40 @@ class MLPScoreHead(nn.Module):
         return self._mlp(x, reg_fc_out)
 
     def forward_rows(self, reg_fc_out, rows, dimensions, cov_calib_logscale=None, cov_correction_sd=0.0,
-                     distance_z_depth=False, calib_scoring=False, det_scores=None):
+                     distance_z_depth=False, calib_scoring=False, det_scores=None, native_mlp=True):
         """Solver result rows [N,24] -> (scores [N], bbox_3d [N,8], pose_cov_calib [N,4,4]); the test-time tail of
         MonoRUnRoIHead.simple_test (monorun_roi_head.py:530-556) with two launches around the GEMMs."""
         from . import pnp
         norm = self.pose_norm if self.use_pose_norm else None
+        if native_mlp and self.num_pose_fcs == 1 and self.num_fused_fcs == 1 and self.fusion_type == 'add':
+            # every reference config: the whole stage is ONE launch (mrpnp_score_stage)
+            w = self._native_weights()
+            scores, bbox_3d, cov_calib, _ = pnp.score_stage(
+                rows, dimensions, reg_fc_out, *w, cov_calib_logscale=cov_calib_logscale, cov_correction_sd=cov_correction_sd,
+                distance_z_depth=distance_z_depth, use_calib=calib_scoring, pose_norm=norm, det_scores=det_scores,
+                pre_sigmoid=self.pre_sigmoid)
+            return scores, bbox_3d, cov_calib.view(-1, 4, 4)
         feat, cov_calib = pnp.pose_features(rows, dimensions, cov_calib_logscale, cov_correction_sd, distance_z_depth,
                                             calib_scoring, norm)
         logits = self._mlp(feat, reg_fc_out)
         scores, bbox_3d = pnp.finish_scores(logits, rows, dimensions, det_scores, self.pre_sigmoid)
         return scores, bbox_3d, cov_calib.view(-1, 4, 4)
+
+    def _native_weights(self):
+        """fp32 contiguous weights in the layout of ``mrpnp_score_stage`` (fused layer transposed); rebuilt when a
+        parameter changes (``_version`` counts in-place updates such as load_state_dict / optimizer steps)."""
+        ps = [self.pose_fcs[0].weight, self.pose_fcs[0].bias, self.fused_fcs[0].weight, self.fused_fcs[0].bias,
+              self.fc_out.weight, self.fc_out.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        cache = getattr(self, '_b200_weights', None)
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                w = (ps[0].detach().float().contiguous(), ps[1].detach().float().contiguous(),
+                     ps[2].detach().float().t().contiguous(), ps[3].detach().float().contiguous(),
+                     ps[4].detach().float().reshape(-1).contiguous(), ps[5].detach().float().reshape(1).contiguous())
+            cache = (key, w)
+            object.__setattr__(self, '_b200_weights', cache)
+        return cache[1]
 
 
 @HEADS.register_module()
@@ -593,15 +622,19 @@ class MonoRUnRoIHead(nn.Module):
         if self.with_score:
             self.score_head.init_weights()
 
-    def reg_forward(self, reg_feats, det_labels):
+    def reg_forward(self, reg_feats, det_labels, decode_dims=True):
         """``_reg_forward`` + the decode that follows it (monorun_roi_head.py:489-507) on the 7x7 RoI features:
-        returns dict(latent_pred, latent_var, dimensions_pred, dimensions_var, reg_fc_out)."""
+        returns dict(latent_pred, latent_var, dimensions_pred, dimensions_var, reg_fc_out, dim_pred, dim_var).
+        ``decode_dims=False`` leaves ``dimensions_pred`` / ``dimensions_var`` None: the fused PnP entry decodes the
+        encoded ``dim_pred`` / ``dim_var`` in its prologue (``forward_3d(..., dim_coder=...)``)."""
         gh = self.global_head
         dim_latent_pred, dim_latent_var, _, _, reg_fc_out = gh(reg_feats)
         dim_pred, dim_var, latent_pred, latent_var = gh.slice_pred(dim_latent_pred, dim_latent_var, det_labels)
-        dimensions_pred, dimensions_var = gh.dim_coder.decode(dim_pred, dim_var, det_labels)
+        dimensions_pred = dimensions_var = None
+        if decode_dims:
+            dimensions_pred, dimensions_var = gh.dim_coder.decode(dim_pred, dim_var, det_labels)
         return dict(latent_pred=latent_pred, latent_var=latent_var, dimensions_pred=dimensions_pred,
-                    dimensions_var=dimensions_var, reg_fc_out=reg_fc_out)
+                    dimensions_var=dimensions_var, reg_fc_out=reg_fc_out, dim_pred=dim_pred, dim_var=dim_var)
 
     def forward_scores(self, rows, reg_fc_out, dimensions_pred, det_scores=None, cov_correction=True, calib_scoring=False,
                        mult_2d_score=True):
@@ -624,8 +657,11 @@ class MonoRUnRoIHead(nn.Module):
 
     def forward_3d(self, noc_feats, bbox_3d_rois, det_labels, latent_pred, dimensions_pred, dimensions_var,
                    cam_intrinsic, img_shape, flip=False, distance_pred=None, cov_correction=True, fused=False,
-                   native_head=False):
+                   native_head=False, dim_coder=None):
         """monorun_roi_head.py:509-534: dense head -> decode -> analytic coords_2d -> PnP -> covariance correction.
+
+        ``dim_coder`` (fused only): ``dimensions_pred`` / ``dimensions_var`` are the ENCODED regression outputs and
+        MultiClassNormDimCoder.decode (:503-507) runs in the PnP prologue; the decoded tensors come back in the dict.
 
         noc_feats (N,256,14,14), bbox_3d_rois (N,5), det_labels (N,), latent_pred (N,16), dimensions_pred (N,3),
         dimensions_var (N,3)|None, cam_intrinsic (1|N,3,3), img_shape (h, w).
@@ -642,13 +678,18 @@ class MonoRUnRoIHead(nn.Module):
                 kw = {}
             else:
                 noc_pred, proj_logstd, kw = all_pred, None, dict(labels=det_labels, num_classes=head.num_classes)
-            ret_val, yaw, t_vec, cov, cov_calib = self.pose_head.forward_fused(
+            if dim_coder is not None:
+                kw.update(dim_coder=dim_coder, dim_labels=det_labels)
+            ret_val, yaw, t_vec, cov, cov_calib, *decoded = self.pose_head.forward_fused(
                 noc_pred, proj_logstd, bbox_3d_rois, dimensions_pred, dimensions_var, cam_intrinsic, img_shapes,
                 head.coord_coder, self.projection_head.proj_error_coder, distance=distance_pred, **kw)
             if cov_correction:
                 distance = self.projection_head.get_distance(t_vec)
                 cov_calib = self.projection_head.proj_error_coder.cov_correction(cov_calib, distance)
-            return dict(ret_val=ret_val, yaw_pred=yaw, t_vec_pred=t_vec, pose_cov_pred=cov, pose_cov_calib=cov_calib)
+            out = dict(ret_val=ret_val, yaw_pred=yaw, t_vec_pred=t_vec, pose_cov_pred=cov, pose_cov_calib=cov_calib)
+            if dim_coder is not None:
+                out['dimensions_pred'], out['dimensions_var'] = decoded
+            return out
         if native_head:
             noc_pred, noc_var, proj_logstd = self.noc_head.slice_pred(
                 self.noc_head.forward_all(noc_feats, latent_pred, flip, native=True), det_labels)
@@ -686,10 +727,10 @@ class MonoRUnRoIHead(nn.Module):
     def with_bbox(self):
         return self.bbox_stage is not None
 
-    def _reg_forward(self, x, rois, labels):
+    def _reg_forward(self, x, rois, labels, decode_dims=True):
         """:272-288 plus the decode that follows it in simple_test (:503-507)."""
         reg_feats = self.bbox_roi_extractor(x[:self.bbox_roi_extractor.num_inputs], rois)
-        out = self.reg_forward(reg_feats, labels)
+        out = self.reg_forward(reg_feats, labels, decode_dims=decode_dims)
         out['roi_feats'] = reg_feats
         return out
 
@@ -760,15 +801,21 @@ class MonoRUnRoIHead(nn.Module):
             return [dict(bbox_results=bbox_result, bbox_3d_results=bbox_3d_result)]
 
         with torch.no_grad():
-            reg = self._reg_forward(x, bbox_3d_rois, det_labels)             # :489-507
-            noc_feats = self.noc_roi_extractor(x[:self.noc_roi_extractor.num_inputs], bbox_3d_rois)   # :331-332
             unit_scale = isinstance(scale_factor, float) and scale_factor == 1.0 or \
                 (not isinstance(scale_factor, float) and bool((np.asarray(scale_factor) == 1).all()))
             fused = native and x[0].is_cuda and not flip and unit_scale
-            if fused or coord_2d is None:
+            # fused: the dimension decode of :503-507 runs in the PnP prologue, on the encoded regression output
+            reg = self._reg_forward(x, bbox_3d_rois, det_labels, decode_dims=not fused)   # :489-507
+            noc_feats = self.noc_roi_extractor(x[:self.noc_roi_extractor.num_inputs], bbox_3d_rois)   # :331-332
+            if fused:
+                out = self.forward_3d(noc_feats, bbox_3d_rois, det_labels, reg['latent_pred'], reg['dim_pred'],
+                                      reg['dim_var'], cam_intrinsic, img_shape, flip=flip, cov_correction=False,
+                                      fused=True, native_head=True, dim_coder=self.global_head.dim_coder)
+                reg['dimensions_pred'], reg['dimensions_var'] = out['dimensions_pred'], out['dimensions_var']
+            elif coord_2d is None:
                 out = self.forward_3d(noc_feats, bbox_3d_rois, det_labels, reg['latent_pred'], reg['dimensions_pred'],
                                       reg['dimensions_var'], cam_intrinsic, img_shape, flip=flip,
-                                      cov_correction=False, fused=fused, native_head=fused)
+                                      cov_correction=False, fused=False, native_head=False)
             else:   # transformed pixel grid: resample it like the reference does (:521-523)
                 out = self._forward_3d_resampled(noc_feats, bbox_3d_rois, det_labels, reg, cam_intrinsic, img_shape, flip,
                                                  coord_2d[0])

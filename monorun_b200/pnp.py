@@ -328,6 +328,41 @@ def finish_scores(score_logits, rows, dims, det_scores=None, pre_sigmoid=True):
     return scores, bbox
 
 
+def score_stage(rows, dims, reg_fc_out, w1, b1, w2t, b2, w3, b3, cov_calib_logscale=None, cov_correction_sd=0.0,
+                distance_z_depth=False, use_calib=False, pose_norm=None, det_scores=None, pre_sigmoid=True,
+                return_logits=False):
+    """``mrpnp_score_stage``: result rows -> (scores [N], bbox_3d [N,8], pose_cov_calib [N,16], logits [N] | None) in
+    ONE launch (features, the three Linear layers of MLPScoreHead, sigmoid / invalid / 2-D score, result rows)."""
+    dev = rows.device
+    ctx = get_ctx(dev)
+    n = rows.shape[0]
+    scores = torch.empty((n,), dtype=torch.float32, device=dev)
+    bbox = torch.empty((n, 8), dtype=torch.float32, device=dev)
+    cal = torch.empty((n, 16), dtype=torch.float32, device=dev)
+    logits = torch.empty((n,), dtype=torch.float32, device=dev) if return_logits else None
+    if n == 0:
+        return scores, bbox, cal, logits
+    rows, dims = _f32c(rows), _f32c(dims)
+    reg = _f32c(reg_fc_out) if reg_fc_out is not None else None
+    ls = _f32c(cov_calib_logscale) if cov_calib_logscale is not None else None
+    nm, eps = [None] * 4, 0.0
+    if pose_norm is not None:
+        nm = [_f32c(t.detach()) for t in (pose_norm.running_mean, pose_norm.running_var, pose_norm.weight, pose_norm.bias)]
+        eps = float(pose_norm.eps)
+    ds = _f32c(det_scores) if det_scores is not None else None
+    h1, h2 = w1.shape[0], w2t.shape[1]
+    assert w1.shape == (h1, 17) and w2t.shape == (h1, h2) and w3.numel() == h2 and b3.numel() == 1
+    assert reg is None or reg.shape == (n, h1)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_score_stage(
+            ctx.ptr, _ptr(rows), _ptr(dims), _ptr(ls), float(cov_correction_sd), int(bool(distance_z_depth)),
+            int(bool(use_calib)), _ptr(nm[0]), _ptr(nm[1]), _ptr(nm[2]), _ptr(nm[3]), eps, _ptr(reg), _ptr(w1), _ptr(b1),
+            _ptr(w2t), _ptr(b2), _ptr(w3), _ptr(b3), h1, h2, _ptr(ds), int(bool(pre_sigmoid)), _ptr(scores), _ptr(bbox),
+            _ptr(cal), _ptr(logits), n, _native.ffi.cast('void*', stream)))
+    return scores, bbox, cal, logits
+
+
 def nms_bev(bbox_3d, labels=None, group_offsets=None, iou_thr=0.25, max_group=None):
     """``mrpnp_nms_bev``: class-wise rotated BEV NMS per image.  bbox_3d [N,8] (l,h,w,x,y,z,ry,score), labels [N]
     int64 or None, group_offsets [G+1] int32 tensor or python list (None = one image).  Returns keep [N] bool.
@@ -362,7 +397,7 @@ def nms_bev(bbox_3d, labels=None, group_offsets=None, iou_thr=0.25, max_group=No
 def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, *, noc_mean, noc_std, focal_gain,
                 scaling_denominator, distance=None, distance_min=0.1, init_pose=None, z_min=0.5, std_scale=10.0,
                 istd_thres=0.6, inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
-                return_inlier_mask=True, labels=None, num_classes=0, ransac_ratio=0.0):
+                return_inlier_mask=True, labels=None, num_classes=0, ransac_ratio=0.0, dim_coder=None, dim_labels=None):
     """Fused head -> PnP launch -- direct wrapper of ``mrpnp_solve_dense``: the dense head's raw class-sliced
     ``noc_pred`` [N,3,H,W] and ``proj_logstd`` [N,2,H,W], the detection boxes ``rois`` [N,4|5] and the decoded
     ``dims`` [N,3] (+ ``dims_var`` [N,3] | None, ``distance`` [N] | None) go in; NOCCoder.decode, the variance
@@ -371,7 +406,11 @@ def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range,
 
     With ``labels`` [N] int64 and ``num_classes`` = C, ``noc_pred`` is instead the head's full output ``all_pred``
     [N, 5*C, H, W] (any object stride: a ``[:, half]`` view of the flip-paired [N,2,5*C,H,W] tensor works) and the
-    class slice of FCNNOCDecoder.slice_pred is taken by the kernel's loads; ``proj_logstd`` is ignored."""
+    class slice of FCNNOCDecoder.slice_pred is taken by the kernel's loads; ``proj_logstd`` is ignored.
+
+    With ``dim_coder`` (a MultiClassNormDimCoder) and ``dim_labels`` [N] int64, ``dims`` / ``dims_var`` are the ENCODED
+    regression outputs: the kernel prologue decodes them per class (multiclass_norm_dim_coder.py:28-36) and the decoded
+    tensors are returned as third and fourth element: (result, inlier_mask, dims [N,3], dims_var [N,3] | None)."""
     dev = noc_pred.device
     ctx = get_ctx(dev)
     n, _, h, w = noc_pred.shape
@@ -385,8 +424,14 @@ def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range,
         proj_logstd = None
     result = torch.empty((n, RESULT_STRIDE), dtype=torch.float32, device=dev)
     inl_out = torch.empty((n, (n_pts + 31) // 32), dtype=torch.int32, device=dev) if return_inlier_mask else None
+    dims_dec = dims_var_dec = None
+    if dim_coder is not None:
+        dim_labels = (labels if dim_labels is None else dim_labels).to(torch.int64).contiguous()
+        dims_dec = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        dims_var_dec = torch.empty((n, 3), dtype=torch.float32, device=dev) if dims_var is not None else None
     if n == 0:
-        return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None)
+        mask = unpack_mask(inl_out, n_pts) if inl_out is not None else None
+        return (result, mask) if dim_coder is None else (result, mask, dims_dec, dims_var_dec)
     noc = noc_pred if num_classes else _f32c(noc_pred)
     ls = _f32c(proj_logstd) if proj_logstd is not None else None
     boxes = _f32c(rois[:, -4:])
@@ -414,13 +459,36 @@ def solve_dense(noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range,
     dp.focal_gain, dp.scaling_denominator = float(focal_gain), float(scaling_denominator)
     dp.distance_min, dp.roi_w = float(distance_min), int(w)
     dp.num_classes, dp.pred_stride = int(num_classes), int(pred_stride)
+    lab = labels if num_classes else None
+    if dim_coder is not None:
+        means, stds = _dim_tables(dim_coder, dev)
+        dp.dim_means, dp.dim_stds, dp.n_dim_classes = _ptr(means), _ptr(stds), means.shape[0]
+        dp.dims_out, dp.dims_var_out = _ptr(dims_dec), _ptr(dims_var_dec)
+        if lab is not None and lab.data_ptr() != dim_labels.data_ptr() and not torch.equal(lab, dim_labels):
+            raise ValueError('solve_dense: channel labels and dim_labels differ')
+        lab = dim_labels
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
         _native.check(_native.lib().mrpnp_solve_dense(
-            ctx.ptr, p, dp, _ptr(noc), _ptr(ls), _ptr(boxes), _ptr(labels if num_classes else None, 'int64_t*'), _ptr(dm),
+            ctx.ptr, p, dp, _ptr(noc), _ptr(ls), _ptr(boxes), _ptr(lab, 'int64_t*'), _ptr(dm),
             _ptr(dv), _ptr(dist), _ptr(cam), _ptr(rng),
             _ptr(init), _ptr(result), _ptr(inl_out, 'uint32_t*'), _native.ffi.cast('void*', stream)))
-    return result, (unpack_mask(inl_out, n_pts) if inl_out is not None else None)
+    mask = unpack_mask(inl_out, n_pts) if inl_out is not None else None
+    return (result, mask) if dim_coder is None else (result, mask, dims_dec, dims_var_dec)
+
+
+_DIM_TABLES = {}
+
+
+def _dim_tables(dim_coder, dev):
+    """Device copies of a MultiClassNormDimCoder's per-class tables ([C,3] each), cached per (values, device)."""
+    key = (tuple(map(tuple, dim_coder.target_means)), tuple(map(tuple, dim_coder.target_stds)), str(dev))
+    t = _DIM_TABLES.get(key)
+    if t is None:
+        t = (torch.tensor(dim_coder.target_means, dtype=torch.float32, device=dev).reshape(-1, 3).contiguous(),
+             torch.tensor(dim_coder.target_stds, dtype=torch.float32, device=dev).reshape(-1, 3).contiguous())
+        _DIM_TABLES[key] = t
+    return t
 
 
 def solve_host(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=None, *, device=0, layout='planar',
@@ -597,19 +665,21 @@ class PnPUncert(torch.nn.Module):
             return _unpack(result, inlier_mask)
 
     def forward_fused(self, noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, std_scale, coord_coder,
-                      proj_error_coder, distance=None, init_pose=None, labels=None, num_classes=0, ransac_ratio=0.0):
+                      proj_error_coder, distance=None, init_pose=None, labels=None, num_classes=0, ransac_ratio=0.0,
+                      dim_coder=None, dim_labels=None):
         """Fused head -> PnP entry (``mrpnp_solve_dense``): takes what FCNNOCDecoder returns plus the decoded
         dimensions and the boxes; ``coord_coder`` (NOCCoder) and ``proj_error_coder``
         (DistanceInvarProjErrorCoder) only supply their constants.  With ``labels`` / ``num_classes`` the first
-        argument is the head's unsliced ``all_pred`` (see :func:`solve_dense`)."""
+        argument is the head's unsliced ``all_pred``; with ``dim_coder`` / ``dim_labels`` the dimensions come in encoded
+        and the decoded (dims, dims_var) are appended to the five outputs (see :func:`solve_dense`)."""
         with torch.no_grad():
             if self.coord_istd_normalize:
                 raise NotImplementedError('coord_istd_normalize with the fused entry')
             if self.forward_exact_hessian:
                 raise NotImplementedError('forward_exact_hessian with the fused entry (the decoded tensors it needs '
                                           'are never materialised); use forward_dense')
-            result, inlier_mask = solve_dense(
-                noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range,
+            result, inlier_mask, *decoded = solve_dense(
+                noc_pred, proj_logstd, rois, dims, dims_var, cam_mats, uv_range, dim_coder=dim_coder, dim_labels=dim_labels,
                 noc_mean=coord_coder.target_means, noc_std=coord_coder.target_stds,
                 focal_gain=proj_error_coder.ref_focal_y * proj_error_coder.epistemic_std_gain,
                 scaling_denominator=proj_error_coder.scaling_denomitor, distance=distance,
@@ -617,4 +687,4 @@ class PnPUncert(torch.nn.Module):
                 std_scale=std_scale, istd_thres=self.epnp_istd_thres, inlier_opt_only=self.inlier_opt_only,
                 cov_mode='pipeline', precision=self.precision, labels=labels, num_classes=num_classes,
                 ransac_ratio=ransac_ratio if self.inlier_opt_only else 0.0)
-            return _unpack(result, inlier_mask)
+            return (*_unpack(result, inlier_mask), *decoded)

@@ -112,14 +112,18 @@ def test_simple_test_from_the_reference_config_block(cuda_lib, cfg_name):
         forced.view(n, 2 * 15, 28, 28), flip)
     dims = dev(raw['dims'])
     reg_forward = head.reg_forward
-    def forced_reg(reg_feats, det_labels):
-        out = reg_forward(reg_feats, det_labels)
-        out['dimensions_pred'], out['dimensions_var'] = dims, dev(raw['dims_var'])
+    coder = head.global_head.dim_coder
+    def forced_reg(reg_feats, det_labels, decode_dims=True):
+        out = reg_forward(reg_feats, det_labels, decode_dims=decode_dims)
+        means, stds = dims.new_tensor(coder.target_means)[det_labels], dims.new_tensor(coder.target_stds)[det_labels]
+        out['dim_pred'], out['dim_var'] = (dims - means) / stds, dev(raw['dims_var']) / stds.square()   # encoded
+        if decode_dims:
+            out['dimensions_pred'], out['dimensions_var'] = dims, dev(raw['dims_var'])
         return out
     head.reg_forward = forced_reg
     launches = pnp.launch_count()
     res = head.simple_test(feats, [det], metas, cam_intrinsic=cam, coord_2d=None, rescale=False)
-    assert pnp.launch_count() - launches == 4    # fused decode + PnP, pose features, score finish, 3-D NMS
+    assert pnp.launch_count() - launches == 3    # fused decode + PnP, score stage, 3-D NMS
     gt = b['gt_pose']
     kept = 0
     for c in range(3):
@@ -130,7 +134,7 @@ def test_simple_test_from_the_reference_config_block(cuda_lib, cfg_name):
         for row2, row3 in zip(a2, a3):
             j = cls[np.argmin(np.abs(b['boxes'][cls] - row2[None, :4]).sum(1))]   # which detection this row is
             assert np.abs(b['boxes'][j] - row2[:4]).max() < 1e-3
-            assert np.linalg.norm(row3[3:6] - gt[j, 1:]) / np.linalg.norm(gt[j, 1:]) < 2e-2
-            assert np.allclose(row3[:3], raw['dims'][j], rtol=1e-6)
+            assert np.linalg.norm(row3[3:6] - gt[j, 1:]) / np.linalg.norm(gt[j, 1:]) < 6e-2   # the generator adds pixel noise of several px
+            assert np.allclose(row3[:3], raw['dims'][j], rtol=1e-5)   # encode -> in-kernel decode round trip
         kept += a3.shape[0]
     assert 0 < kept <= n

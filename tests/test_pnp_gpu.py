@@ -75,18 +75,24 @@ def test_lm_parity_with_oracle(cuda_lib, oracle, n, cfg, weights, mode, precisio
     if precision == 'fp64':
         assert t_err.max() < 1e-9 and r_err.max() < 1e-9 and same_evals == 1.0
         np.testing.assert_allclose(r64[:, 4], ref['cost'], rtol=1e-11)
+    elif precision == 'fast':
+        # the default precision: every decision inside the rounding band of its threshold goes to the exact fp64
+        # routine, so no object may leave the north_star tolerances or take a different number of evaluations
+        off = (t_err >= T_TOL) | (r_err >= R_TOL)
+        assert off.sum() == 0 and same_evals == 1.0, (int(off.sum()), same_evals, t_err.max(), r_err.max())
+        # FAST tracks the cost through fp32 cost CHANGES: the first (large) step leaves ~1e-7 of its change behind
+        np.testing.assert_allclose(r64[:, 4], ref['cost'], rtol=1e-3)
     else:
-        # An object whose relative cost decrease lands within rounding of function_tolerance (1e-6) may stop one LM
-        # step apart from the oracle: both are valid Ceres termination points, their costs agree to that tolerance
-        # and the poses to the size of the last, un-adopted step.  At most 0.2 % of the objects may do so.
+        # MRPNP_PREC_MIXED (not the default; kept as the simple mixed-precision baseline): an object whose relative cost
+        # decrease lands within rounding of function_tolerance (1e-6) may stop one LM step apart from the oracle (its
+        # fp32 Jacobian moves the iterates by ~1e-7); at most 0.2 % of the objects may do so.
         off = (t_err >= T_TOL) | (r_err >= R_TOL)
         assert off.mean() <= 0.002, (off.sum(), t_err.max(), r_err.max())
         if off.any():
             np.testing.assert_allclose(r64[off, 4], ref['cost'][off], rtol=1e-5)
             assert t_err.max() < 1e-3 and r_err.max() < 5e-3, (t_err.max(), r_err.max())
         assert same_evals > 0.99
-        # FAST tracks the cost through fp32 cost CHANGES: the first (large) step leaves ~1e-7 of its change behind
-        np.testing.assert_allclose(r64[:, 4], ref['cost'], rtol=1e-6 if precision == 'mixed' else 1e-3)
+        np.testing.assert_allclose(r64[:, 4], ref['cost'], rtol=1e-6)
     # fp32 result row agrees with the fp64 side channel
     np.testing.assert_allclose(res[:, :4], r64[:, :4].astype(np.float32), rtol=1e-6, atol=1e-7)
 
@@ -415,10 +421,11 @@ def test_full_size_properties(cuda_lib, precision):
 
 @pytest.mark.parametrize('cfg,weights', [(3, 'full'), (2, 'diag')])
 def test_full_size_parity_with_oracle(cuda_lib, oracle, cfg, weights):
-    """BASELINE.json size (8192 objects x 784 points, grid-faithful S1 data, the bench's own workload) against the
-    oracle (OpenMP, a few seconds): the default precision must take the oracle's number of LM evaluations on
-    >= 99.8 % of the objects and stay within the north_star tolerances on all but <= 0.2 % (objects that stop one LM
-    step apart, see test_lm_parity_with_oracle); the device's own inlier masks are handed to the oracle."""
+    """BASELINE.json size (8192 objects x 784 points, grid-faithful S1 data, the bench's own two workloads) against
+    the oracle (OpenMP, a few seconds), default precision: ZERO objects outside the north_star tolerances and the
+    oracle's number of LM evaluations on every object -- the fp32 path hands every decision that falls inside the
+    rounding band of its threshold to the exact fp64 routine (a handful of objects per launch).  The device's own
+    inlier masks are handed to the oracle."""
     from monorun_b200 import pnp
     n = 8192
     b = synth.make_batch(n, config=cfg, weights=weights, mode='S1', classes=(0, 1, 2) if cfg == 3 else (0,))
@@ -426,24 +433,25 @@ def test_full_size_parity_with_oracle(cuda_lib, oracle, cfg, weights):
     full = weights == 'full'
     ih, iw = b['img_shape']
     rng = torch.tensor([[-200., iw + 200., -200., ih + 200.]], device='cuda')
+    hb0 = pnp.handed_back_count()
     res, inl, r64 = pnp.solve_batched(dev(b['coords_3d']), dev(b['coords_2d']), dev(b['w_full'] if full else b['logstd']),
                                       dev(b['cam_mat'][None]), rng, init_pose=dev(b['init_pose']), layout='planar',
                                       weight_mode='full' if full else 'logstd', return_fp64=True)
+    handed_back = pnp.handed_back_count() - hb0
     w = op['w_full'] if full else op['coords_2d_istd']
     ref = oracle.lm_batch(op['coords_2d'], op['coords_3d'], w, op['cam_mats'], b['init_pose'], clips(op),
                           inl.cpu().numpy(), full_w=full, threads=0)
     r64, res = r64.cpu().numpy(), res.cpu().numpy()
     assert ref['val'].all() and (res[:, 20] == 1).all()
     t_err, r_err = pose_errors(r64, ref['pose'])
-    same_evals = (r64[:, 6].astype(int) == ref['stats'][:, 1]).mean()
     off = (t_err >= T_TOL) | (r_err >= R_TOL)
-    assert same_evals >= 0.998, same_evals
-    assert off.mean() <= 0.002, (off.sum(), t_err.max(), r_err.max())
+    different = r64[:, 6].astype(int) != ref['stats'][:, 1]
+    print(f'{weights}: handed to the exact routine {handed_back} of {n}; max t_err {t_err.max():.2e}, max yaw err {r_err.max():.2e}')
+    assert off.sum() == 0, (int(off.sum()), t_err.max(), r_err.max())
+    assert different.sum() == 0, int(different.sum())
+    assert 0 < handed_back < 0.01 * n
     assert np.median(t_err) < 1e-6 and np.quantile(t_err, 0.99) < 1e-5
-    if off.any():
-        np.testing.assert_allclose(r64[off, 4], ref['cost'][off], rtol=1e-5)
-        assert t_err.max() < 1e-3 and r_err.max() < 5e-3, (t_err.max(), r_err.max())
-    np.testing.assert_allclose(r64[~off, 4], ref['cost'][~off], rtol=1e-4)
+    np.testing.assert_allclose(r64[:, 4], ref['cost'], rtol=1e-4)
 
 
 @pytest.mark.parametrize('weights,cfg', [('diag', 2), ('full', 3)])
@@ -654,3 +662,43 @@ def test_fused_entry_slices_classes_like_slice_pred(cuda_lib):
         assert torch.equal(r, r_ref) and torch.equal(m, m_ref)
     with pytest.raises(ValueError):
         pnp.solve_dense(paired[:, 0, :14], None, *args, labels=dev(lab), num_classes=C, **kw)
+
+
+@pytest.mark.parametrize('precision', ['fast', 'fp64'])
+def test_fused_entry_decodes_dimensions_like_the_dim_coder(cuda_lib, precision):
+    """MultiClassNormDimCoder.decode in the kernel prologue (multiclass_norm_dim_coder.py:28-36): encoded regression
+    outputs + labels in, bit for bit the result rows of the torch decode followed by the fused entry, and bit for bit
+    the decoded dimensions / variances of the torch coder.  A label outside the table fails that object only."""
+    from monorun_b200 import coders, pnp
+    n = 200
+    b = synth.make_batch(n, config=3, weights='diag', mode='S1')
+    raw = synth.to_head_raw(b, rng=np.random.default_rng(1))
+    coder = coders.MultiClassNormDimCoder()
+    lab = dev(b['labels']).long()
+    means, stds = torch.tensor(coder.target_means, device='cuda')[lab], torch.tensor(coder.target_stds, device='cuda')[lab]
+    enc, enc_var = (dev(raw['dims']) - means) / stds, dev(raw['dims_var']) / stds.square()
+    dims_t, var_t = coder.decode(enc, enc_var, lab)                        # the reference's two launches + gathers
+    cc, pc = coders.NOCCoder(synth.NOC_MEANS, synth.NOC_STDS), coders.DistanceInvarProjErrorCoder()
+    ih, iw = b['img_shape']
+    kw = dict(noc_mean=cc.target_means, noc_std=cc.target_stds, focal_gain=pc.ref_focal_y * pc.epistemic_std_gain,
+              scaling_denominator=pc.scaling_denomitor, precision=precision)
+    tail = (dev(b['cam_mat'][None]), torch.tensor([[-200.0, iw + 200.0, -200.0, ih + 200.0]], device='cuda'))
+    maps = (dev(raw['noc_pred']), dev(raw['proj_logstd']), dev(raw['rois']))
+    r_ref, m_ref = pnp.solve_dense(*maps, dims_t, var_t, *tail, **kw)
+    before = pnp.launch_count()
+    r, m, d, v = pnp.solve_dense(*maps, enc, enc_var, *tail, dim_coder=coder, dim_labels=lab, **kw)
+    assert pnp.launch_count() == before + 1
+    assert torch.equal(d, dims_t) and torch.equal(v, var_t)
+    assert torch.equal(r, r_ref) and torch.equal(m, m_ref)
+    r, m, d, v = pnp.solve_dense(*maps, enc, None, *tail, dim_coder=coder, dim_labels=lab, **kw)   # dims_var None
+    assert v is None and torch.equal(d, dims_t)
+    assert torch.equal(r, pnp.solve_dense(*maps, dims_t, None, *tail, **kw)[0])
+    bad = lab.clone()
+    bad[5], bad[77] = 3, -1
+    r_bad, _, d_bad, _ = pnp.solve_dense(*maps, enc, enc_var, *tail, dim_coder=coder, dim_labels=bad, **kw)
+    keep = torch.ones(n, dtype=torch.bool, device='cuda')
+    keep[[5, 77]] = False
+    assert torch.equal(r_bad[keep], r_ref[keep]) and (r_bad[~keep, 20] == 0).all() and torch.isnan(d_bad[~keep]).all()
+    e = torch.zeros((0, 3), device='cuda')
+    out = pnp.solve_dense(maps[0][:0], maps[1][:0], maps[2][:0], e, e, *tail, dim_coder=coder, dim_labels=lab[:0], **kw)
+    assert out[2].shape == (0, 3) and out[3].shape == (0, 3)

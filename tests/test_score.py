@@ -109,8 +109,9 @@ def test_pose_feature_kernel_matches_oracle(cuda_lib, use_calib, z_depth, sd):
 
 @pytest.mark.gpu
 def test_score_head_rows_path_matches_reference_sequence(cuda_lib):
-    """MLPScoreHead.forward_rows (2 launches + library GEMMs) == the reference's torch sequence
-    (monorun_roi_head.py:530-551) on the same result rows; and through MonoRUnRoIHead.forward_scores."""
+    """MLPScoreHead.forward_rows (ONE launch: mrpnp_score_stage; or 2 launches + library GEMMs for other network
+    shapes) == the reference's torch sequence (monorun_roi_head.py:530-551) on the same result rows; and through
+    MonoRUnRoIHead.forward_scores."""
     from tests.test_host import _roi_head_cfg
     from monorun_b200 import pnp
     torch.manual_seed(0)
@@ -129,7 +130,22 @@ def test_score_head_rows_path_matches_reference_sequence(cuda_lib):
     before = pnp.launch_count()
     with torch.no_grad():
         scores, bbox, cal = head.forward_scores(rows, reg, dims, det_scores=det, cov_correction=True, calib_scoring=True)
-        assert pnp.launch_count() == before + 2
+        assert pnp.launch_count() == before + 1
+        sh, ph_ = head.score_head, head.projection_head
+        s2, b2, c2 = sh.forward_rows(reg, rows, dims, cov_calib_logscale=head.pose_head.cov_calib_logscale.detach(),
+                                     cov_correction_sd=ph_.proj_error_coder.scaling_denomitor,
+                                     distance_z_depth=ph_.distance_mode == 'z-depth', calib_scoring=True, det_scores=det,
+                                     native_mlp=False)
+        assert pnp.launch_count() == before + 3
+        assert torch.allclose(scores, s2, rtol=1e-3, atol=1e-5) and torch.equal(cal.reshape(-1, 16), c2.reshape(-1, 16))
+        # a parameter update (optimizer step, load_state_dict) invalidates the transposed-weight cache
+        w_before = sh.fused_fcs[0].weight.clone()
+        sh.fused_fcs[0].weight.mul_(0.5)
+        s3 = head.forward_scores(rows, reg, dims, det_scores=det, cov_correction=True, calib_scoring=True)[0]
+        assert not torch.allclose(s3, scores, rtol=1e-3, atol=1e-5)
+        sh.fused_fcs[0].weight.copy_(w_before)
+        s4 = head.forward_scores(rows, reg, dims, det_scores=det, cov_correction=True, calib_scoring=True)[0]
+        assert torch.equal(s4, scores)
         # the reference's sequence with torch ops
         yaw, t_vec, cov = rows[:, :1], rows[:, 1:4], rows[:, 4:20].reshape(-1, 4, 4)
         s = torch.exp(head.pose_head.cov_calib_logscale)

@@ -8,8 +8,11 @@ What is whose:
   FPNplus): they are callers of the path, not part of it.  A random-init RPN / bbox head yields no meaningful
   detections, so the 2-D detections are synthetic (projected 3-D boxes of the seeded generator, KITTI statistics).
 * Everything from the RoI features on is this repo: ``MonoRUnRoIHead`` built from the reference's config block
-  (configs/kitti_multiclass.py:36-144 when /root/reference exists, else the hand-written equivalent), the native
-  dense head (libmonorun_head.so) and the native solver / score / NMS kernels (libmonorun_pnp.so).
+  (configs/kitti_multiclass.py:36-144 when /root/reference exists, else the committed copy of the same block,
+  tests/golden/roi_head_cfgs.json) including its two SingleRoIExtractors (featmap_strides [2,4,8,16,32], finest_scale
+  20 / 28), the native dense head (libmonorun_head.so) and the native solver / score / NMS kernels (libmonorun_pnp.so).
+* (C) ``MonoRUnRoIHead.simple_test`` -- the method a user of the reference calls -- is run per frame on the same
+  tensors and must return exactly the rows of the batched sequence.
 * A random-init dense head emits a constant NOC map (conv_final is initialised ~0), i.e. a rank-deficient PnP
   problem.  The frame is therefore run twice: (A) exactly as is -- shapes, finiteness and validity flags are checked;
   (B) with the head's output replaced at the head -> PnP boundary by a consistent synthetic correspondence map of the
@@ -33,27 +36,23 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import monorun_b200  # noqa: E402
 from monorun_b200 import synth  # noqa: E402
 from monorun_b200.coders import coords_2d_from_rois  # noqa: E402
-from monorun_b200.config import ConfigDict, build_roi_head, load_config  # noqa: E402
+from monorun_b200.config import build_roi_head, build_roi_head_from_fixture, load_config  # noqa: E402
 
 REF_CFG = '/root/reference/configs/kitti_multiclass.py'
-STRIDES = (4, 8, 16, 32)
 
 
 def roi_head_from_config():
+    """The reference's own ``roi_head`` / ``test_cfg.rcnn`` blocks: from the config file where the reference tree exists,
+    else from the committed copy of the same blocks (tests/golden/roi_head_cfgs.json) -- the GPU box has no reference."""
     if os.path.exists(REF_CFG):
         return build_roi_head(load_config(REF_CFG)), REF_CFG
-    from tests.test_host import _roi_head_cfg
-    cfg = _roi_head_cfg()
-    cfg['global_head'] = dict(type='FCExtractorMonteCarlo', with_dim=True, with_latent_vec=True, latent_channels=16,
-                              num_fcs=2, in_channels=256, fc_out_channels=1024, num_classes=3, roi_feat_size=7,
-                              latent_class_agnostic=False, dropout_rate=0.5, dropout2d_rate=0.2)
-    test_cfg = ConfigDict(score_thr=0.05, max_per_img=100, nms_3d_thr=0.01, mult_2d_score=True, calib_scoring=True,
-                          cov_correction=True)   # configs/kitti_multiclass.py:195-210
-    return monorun_b200.build_head(cfg, test_cfg=test_cfg), 'hand-written block (tests/test_host.py::_roi_head_cfg)'
+    return build_roi_head_from_fixture('kitti_multiclass.py'), 'tests/golden/roi_head_cfgs.json[kitti_multiclass.py]'
 
 
 class BackboneFPN(nn.Module):
-    """torchvision ResNet-101 (out_indices 0-3) + FeaturePyramidNetwork(256): configs/kitti_multiclass.py:5-21."""
+    """torchvision ResNet-101 (out_indices 0-3) + FeaturePyramidNetwork(256) + the extra stride-2 level of the
+    reference's FPNplus (necks/fpn_plus.py:76-90: bilinear x2 of the finest merged level, then a 3x3 conv), so that the
+    five levels match the extractors' featmap_strides [2, 4, 8, 16, 32] (configs/kitti_multiclass.py:5-21, :38-43, :83-88)."""
 
     def __init__(self):
         super().__init__()
@@ -64,6 +63,7 @@ class BackboneFPN(nn.Module):
         self.stem = nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool)
         self.layers = nn.ModuleList([r.layer1, r.layer2, r.layer3, r.layer4])
         self.fpn = torchvision.ops.FeaturePyramidNetwork([256, 512, 1024, 2048], 256)
+        self.lower_conv = nn.Conv2d(256, 256, 3, padding=1)
 
     def forward(self, img):
         x = self.stem(img)
@@ -71,20 +71,9 @@ class BackboneFPN(nn.Module):
         for i, layer in enumerate(self.layers):
             x = layer(x)
             feats[str(i)] = x
-        return list(self.fpn(feats).values())
-
-
-def roi_extract(feats, rois, out_size, finest_scale=56):
-    """mmdet SingleRoIExtractor: level = floor(log2(sqrt(w*h)/finest_scale + 1e-6)) clamped, RoIAlign(aligned) per level."""
-    from torchvision.ops import roi_align
-    scale = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
-    lvl = torch.floor(torch.log2(scale / finest_scale + 1e-6)).clamp(0, len(STRIDES) - 1).long()
-    out = feats[0].new_zeros((rois.shape[0], feats[0].shape[1], out_size, out_size))
-    for i, s in enumerate(STRIDES):
-        idx = (lvl == i).nonzero(as_tuple=True)[0]
-        if idx.numel():
-            out[idx] = roi_align(feats[i], rois[idx], out_size, 1.0 / s, 0, True)
-    return out
+        levels = list(self.fpn(feats).values())
+        lower = self.lower_conv(nn.functional.interpolate(levels[0], scale_factor=2, mode='bilinear'))
+        return [lower] + levels
 
 
 def main():
@@ -140,7 +129,8 @@ def main():
         with torch.no_grad():
             feats = net(img)
             marks.append(ev())
-            noc_feats, reg_feats = roi_extract(feats, rois, 14), roi_extract(feats, rois, 7)
+            noc_feats = head.noc_roi_extractor(feats[:head.noc_roi_extractor.num_inputs], rois)   # strides [2..32], finest 28
+            reg_feats = head.bbox_roi_extractor(feats[:head.bbox_roi_extractor.num_inputs], rois)  # strides [2..32], finest 20
             marks.append(ev())
             reg = head.reg_forward(reg_feats, labels)                                    # monorun_roi_head.py:489-507
             marks.append(ev())
@@ -159,7 +149,7 @@ def main():
             keep = head.nms_3d(bbox_3d, labels, offsets)                                  # :619-655
             marks.append(ev())
         return marks, dict(all_pred=all_pred, ret_val=ret_val, yaw=yaw, t_vec=t_vec, cov=cov, scores=scores,
-                           bbox_3d=bbox_3d, keep=keep, reg=reg, cov_calib=cov_calib)
+                           bbox_3d=bbox_3d, keep=keep, reg=reg, cov_calib=cov_calib, feats=feats)
 
     # ---- (A) the network exactly as initialised: shapes / finiteness / validity
     _, o = run()
@@ -175,9 +165,13 @@ def main():
 
     # ---- (B) teacher-forced correspondences: parity at the head -> PnP boundary against the oracle.
     # LM parity is defined given (init pose, inlier mask): both sides start from the generator's perturbed pose.
+    # The reprojection-threshold consensus (epnp_ransac_thres_ratio, the RANSAC counterpart) is switched off for this leg:
+    # it would drop points the oracle's mask keeps (random-init dimensions make many of them inconsistent).
     init = t(b['init_pose']).float()
+    ratio, ph.epnp_ransac_thres_ratio = ph.epnp_ransac_thres_ratio, None
     _, o = run(forced, init)
     torch.cuda.synchronize()
+    ph.epnp_ransac_thres_ratio = ratio
     with torch.no_grad():  # the boundary tensors, decoded the unfused way (monorun_roi_head.py:513-523)
         noc_pred, noc_var, proj_logstd = nh.slice_pred(forced, labels)
         coords_3d, coords_3d_var = nh.coord_coder.decode(noc_pred, noc_var, o['reg']['dimensions_pred'],
@@ -215,6 +209,47 @@ def main():
     t_err_epnp, _ = errs(np.concatenate([ref[1], ref[2]], 1), sel)
     pose = pose_keep
 
+    # ---- (C) the public method: MonoRUnRoIHead.simple_test per frame (monorun_roi_head.py:442-605), with the 2-D stage,
+    # the regression outputs and the dense head's output of (B) injected; its rows must be the batched sequence's rows
+    reg_all, feats_all = o_dev['reg'], o_dev['feats']
+    state = {}
+    head.set_bbox_stage(lambda x, proposals, metas, rescale, cfg: (
+        torch.cat([boxes[state['sel']], det_scores[state['sel'], None]], 1), labels[state['sel']]))
+    reg_forward, forward_all = head.reg_forward, nh.forward_all
+
+    def frame_reg(reg_feats, det_labels, decode_dims=True):
+        out = {k: (v[state['sel']] if v is not None else None) for k, v in reg_all.items()}
+        if not decode_dims:
+            out['dimensions_pred'] = out['dimensions_var'] = None
+        return out
+    meta = [dict(img_shape=img_shape + (3,), scale_factor=1.0, flip=False)]
+    st_rows, st_ms = 0, []
+    for f in range(B):
+        state['sel'] = torch.arange(f * K, (f + 1) * K, device=dev)
+        head.reg_forward = frame_reg
+        nh.forward_all = lambda x, latent, flip=False, native=False: forced[state['sel']]
+        x_f = [lvl[f:f + 1] for lvl in feats_all]
+        res = head.simple_test(x_f, None, meta, cam_intrinsic=[[cam[0]]], rescale=False)
+        for c in range(C):
+            sel = ((labels == c) & o_dev['keep'].bool())[state['sel']]
+            want = o_dev['bbox_3d'][state['sel']][sel]
+            want = want[torch.argsort(want[:, 7], descending=True, stable=True)].cpu().numpy()
+            got = res[0]['bbox_3d_results'][c]
+            assert got.shape == want.shape, (f, c, got.shape, want.shape)
+            assert np.allclose(got, want, rtol=1e-5, atol=1e-6), (f, c, np.abs(got - want).max())
+            assert res[0]['bbox_results'][c].shape == (got.shape[0], 5)
+            st_rows += got.shape[0]
+        # the method as a user calls it, network as initialised (only the 2-D stage injected): time per frame
+        head.reg_forward, nh.forward_all = reg_forward, forward_all
+        for rep in range(3):
+            e0 = ev()
+            head.simple_test(x_f, None, meta, cam_intrinsic=[[cam[0]]], rescale=False)
+            e1 = ev()
+            torch.cuda.synchronize()
+            if rep:
+                st_ms.append(e0.elapsed_time(e1))
+    assert st_rows == int(o_dev['keep'].sum())
+
     for _ in range(2):
         run(forced)
     torch.cuda.synchronize()
@@ -226,7 +261,7 @@ def main():
     acc /= a.steps
     names = ['backbone + FPN (torchvision, fp32)', 'RoI feature extraction 14x14 + 7x7 (torchvision roi_align)',
              'MC-dropout global extractor, 50 samples (torch Linear)', 'dense head (libmonorun_head, 10 launches)',
-             'fused decode + PnP (libmonorun_pnp, 2 launches)', 'score head + 3-D NMS (3 launches + 3 library GEMMs)']
+             'fused decode + PnP (libmonorun_pnp, 1 launch)', 'score stage + 3-D NMS (libmonorun_pnp, 2 launches)']
     out = dict(
         config='kitti_multiclass end-to-end, random-init weights, synthetic frames', roi_head_config=cfg_src,
         frames=B, objects_per_frame=K, image=[384, 1248],
@@ -238,6 +273,10 @@ def main():
             t_rel_err_vs_oracle_median=float(np.median(t_err)), t_rel_err_vs_oracle_max=float(t_err.max()),
             yaw_err_vs_oracle_max_rad=float(r_err.max()),
             t_rel_err_vs_generating_pose_median=float(np.median(gt_err))),
+        simple_test=dict(frames=B, rows_identical_to_batched_sequence=st_rows,
+                         ms_per_frame_3d_branch_incl_d2h=float(np.mean(st_ms)),
+                         note='MonoRUnRoIHead.simple_test on the FPN levels of one frame, synthetic 2-D detections injected as '
+                              'bbox_stage; includes the device->host copies of the per-class result arrays'),
         ms_per_frame_batch={k: float(v) for k, v in zip(names, acc)},
         ms_per_frame=float(acc.sum() / B), ms_per_frame_3d_branch=float(acc[2:].sum() / B),
         objects_per_s=float(n / acc.sum() * 1e3))
