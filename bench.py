@@ -235,8 +235,12 @@ def main():
     ap.add_argument('--precision', choices=['fast', 'mixed', 'fp64'], default='fast')
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--streams', type=int, default=2, help='CUDA streams the K timed steps alternate between')
-    ap.add_argument('--gather', choices=['fused', 'nccl'], default='fused',
+    ap.add_argument('--gather-lag', type=int, default=1,
+                    help='fused gather: steps (per stream) between a solve and the wait for its rows')
+    ap.add_argument('--gather', choices=['fused', 'fused-barrier', 'nccl'], default='fused',
                     help='N > 1: result rows by peer-to-peer stores from the kernel + symmetric-memory barrier, or NCCL all-gather')
+    ap.add_argument('--large-batch', type=int, default=4,
+                    help='N=1: also time one launch over this many concatenated batches (details.large_batch); 0/1 = skip')
     ap.add_argument('--total-objects', type=int, default=0,
                     help='strong scaling (BASELINE configs[4]: 65536): this many objects in total, split over the GPUs; '
                          'default 0 = 8192 objects per GPU (weak scaling)')
@@ -280,28 +284,56 @@ def main():
     kw = dict(layout='planar', weight_mode='full' if full else 'logstd', precision=args.precision,
               cov_mode='pipeline', return_inlier_mask=False)
 
-    # N > 1, --gather fused: one symmetric result buffer per stream (a buffer is rewritten by the next solve on it)
+    # N > 1, --gather fused: the kernel stores the rows into every rank's symmetric buffer and raises completion flags;
+    # the wait for step i (a one-warp kernel) is issued `--gather-lag` steps later on the same stream, so that no rank's
+    # next solve waits for the slowest rank's current one.  streams x (lag + 1) buffers rotate.
     gathers, gather_note = [], ''
-    if world > 1 and args.gather == 'fused':
+    nstreams = max(1, args.streams)
+    lag = max(0, args.gather_lag) if args.gather == 'fused' else 0
+    if world > 1 and args.gather in ('fused', 'fused-barrier'):
         try:
-            gathers = [mdist.FusedGather(n_total, dev) for _ in range(max(1, args.streams))]
+            gathers = [mdist.FusedGather(n_total, dev, signal='flags' if args.gather == 'fused' else 'barrier')
+                       for _ in range(nstreams * (lag + 1))]
             ok = torch.ones(1, device=dev)
         except Exception as exc:  # symmetric memory unavailable on this box: NCCL all-gather instead, and say so
             gathers, gather_note, ok = [], f' (symmetric memory unavailable: {type(exc).__name__})', torch.zeros(1, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # every rank takes the same path
         if ok.item() == 0:
             gathers = []
+    pending = []   # (stream index, FusedGather) of the solves whose rows have not been waited for yet
 
-    def step(i):
+    def submit(i):
+        """Step i on the current stream: solve (+ gather).  With the fused gather the wait for the rows of an EARLIER
+        step of this stream is issued here; drain() issues the remaining waits."""
         d = dsets[i % 2]
         if gathers:
             fg = gathers[i % len(gathers)]
             pnp.solve_batched(d['c3'], d['c2'], d['w'], d['cam'], d['rng'], init_pose=d['init'], **kw, **fg.solve_kwargs())
-            return fg.finish()
+            pending.append((i % nstreams, fg))
+            mine = [k for k, (st, _) in enumerate(pending) if st == i % nstreams]
+            if len(mine) > lag:
+                return pending.pop(mine[0])[1].finish()
+            return None
         rows, _, _ = pnp.solve_batched(d['c3'], d['c2'], d['w'], d['cam'], d['rng'], init_pose=d['init'], **kw)
         if world > 1:
             rows = mdist.all_gather_rows(rows, n_total)
         return rows
+
+    def drain(streams=None):
+        rows = None
+        while pending:
+            st, fg = pending.pop(0)
+            if streams is None:
+                rows = fg.finish()
+            else:
+                with torch.cuda.stream(streams[st]):
+                    rows = fg.finish()
+        return rows
+
+    def step(i):
+        rows = submit(i)
+        last = drain()
+        return last if last is not None else rows
 
     def fence():
         if world > 1:
@@ -320,7 +352,7 @@ def main():
         same = torch.equal(got, ref_rows) and torch.equal(ref_rows[rank * n_local:(rank + 1) * n_local], rows_l)
         flag = torch.tensor([1.0 if same else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        gather_check = {'method': 'fused peer-to-peer stores' if gathers else 'nccl all_gather_into_tensor',
+        gather_check = {'method': ('fused peer-to-peer stores + ' + ('completion flags' if args.gather == 'fused' else 'barrier')) if gathers else 'nccl all_gather_into_tensor',
                         'against': 'one NCCL all-gather of the same solve', 'rows': n_total,
                         'result': 'bitwise' if flag.item() == 1.0 else 'MISMATCH'}
         if flag.item() != 1.0:
@@ -357,10 +389,13 @@ def main():
     # ---- (1) the kernel alone: K serialized launches on one stream, CUDA events around each (roofline source) ----
     # The parity check above left the GPU idle for seconds: besides the W warm-up steps, keep it busy for a quarter of a
     # second (untimed) so that the launches below run at the clocks of a loaded device, as they do inside a long job.
+    # (Local solves only: a time-based loop runs a different number of iterations on every rank, so it must not
+    # contain anything the other ranks take part in.)
     t_warm = time.perf_counter()
     i = 0
     while i < args.warmup or time.perf_counter() - t_warm < 0.25:
-        step(i)
+        d = dsets[i % 2]
+        pnp.solve_batched(d['c3'], d['c2'], d['w'], d['cam'], d['rng'], init_pose=d['init'], **kw)
         i += 1
         if i % 64 == 0:
             torch.cuda.synchronize(dev)
@@ -375,15 +410,36 @@ def main():
     kernel_us = [1e3 * a.elapsed_time(b) for a, b in kev]
     kernel_ms = float(np.mean(kernel_us)) * 1e-3
 
+    # ---- (1b) the same kernel on a 4x larger batch (informative, not the headline): with one warp per object the last
+    #      few long Levenberg-Marquardt runs of a launch leave most SMs idle; the larger batch shows the rate the kernel
+    #      sustains per object when that ramp-down is amortised ----
+    large = None
+    if world == 1 and args.large_batch > 1 and not args.total_objects:
+        reps = args.large_batch
+        cat = {k: torch.cat([dsets[j % 2][k] for j in range(reps)]) for k in ('c3', 'c2', 'w', 'init')}
+        for _ in range(2):
+            pnp.solve_batched(cat['c3'], cat['c2'], cat['w'], dsets[0]['cam'], dsets[0]['rng'], init_pose=cat['init'], **kw)
+        fence()
+        lev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
+        for a, b in lev:
+            a.record()
+            pnp.solve_batched(cat['c3'], cat['c2'], cat['w'], dsets[0]['cam'], dsets[0]['rng'], init_pose=cat['init'], **kw)
+            b.record()
+        fence()
+        lus = float(np.mean([1e3 * a.elapsed_time(b) for a, b in lev]))
+        large = {'objects_per_launch': reps * n_local, 'us_per_launch': lus, 'us_per_8192_objects': lus / reps,
+                 'hbm_roofline_frac': ALG_BYTES[args.workload] * reps * n_local / (lus * 1e-6) / 1e9 / measured_peak()[0]}
+        del cat
+
     # ---- (2) device-resident throughput: exactly K steps between fences.  Consecutive steps are independent
     #      batches, so they alternate between `--streams` CUDA streams: the ramp-down of one persistent launch (a
     #      few long Levenberg-Marquardt runs on otherwise idle SMs) overlaps the ramp-up of the next one. ----
-    nstreams = max(1, args.streams)
     streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
     main = torch.cuda.current_stream(dev)
     for i in range(args.warmup):
         with torch.cuda.stream(streams[i % nstreams]):
-            step(i)
+            submit(i)
+    drain(streams)
     fence()
     launches0 = pnp.launch_count(dev)
     sampler = ClockSampler(local_rank)
@@ -394,9 +450,13 @@ def main():
     ev[0].record(main)
     for st in streams:
         st.wait_event(ev[0])
+    rows = None
     for i in range(args.steps):
         with torch.cuda.stream(streams[i % nstreams]):
-            rows = step(i)
+            r = submit(i)
+            rows = r if r is not None else rows
+    r = drain(streams)   # the waits still outstanding: every step's rows are complete inside the timed region
+    rows = r if r is not None else rows
     for st in streams:
         done = torch.cuda.Event()
         done.record(st)
@@ -414,6 +474,10 @@ def main():
     if args.sustain_seconds > 0:
         per_step = ms_total / args.steps * 1e-3
         k_sus = int(min(max(args.sustain_seconds / max(per_step, 1e-6), args.steps), 200000))
+        if world > 1:   # every rank must run the SAME number of steps: they all take part in each step's gather
+            kt = torch.tensor([k_sus], device=dev, dtype=torch.int64)
+            dist.broadcast(kt, src=0)
+            k_sus = int(kt.item())
         fence()
         ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev2[0].record(main)
@@ -421,7 +485,8 @@ def main():
             st.wait_event(ev2[0])
         for i in range(k_sus):
             with torch.cuda.stream(streams[i % nstreams]):
-                step(i)
+                submit(i)
+        drain(streams)
         for st in streams:
             done = torch.cuda.Event()
             done.record(st)
@@ -476,11 +541,19 @@ def main():
             'l2': 'two alternating input sets of %.0f MB each (%s 126 MB L2)' % (alg / 1e6, '>' if alg > 126e6 else 'NOT larger than the'),
             'streams': nstreams, 'serialized_ms_per_step': kernel_ms,
             'serialized_us_per_launch': [round(v, 1) for v in kernel_us],
+            'large_batch': large,
             'parallelism': f'objects sharded contiguously over {world} GPU(s)' + (
-                '' if world == 1 else ', result rows stored peer-to-peer into every rank\'s symmetric buffer by the kernel + 1 symmetric-memory barrier per step'
+                '' if world == 1 else (', result rows stored peer-to-peer into every rank\'s symmetric buffer by the kernel; completion flags '
+                                       f'raised by the kernel, waited for {lag} step(s) later on the same stream (1 one-warp launch per step)'
+                                       if args.gather == 'fused' else
+                                       ', result rows stored peer-to-peer into every rank\'s symmetric buffer by the kernel + 1 symmetric-memory barrier per step')
                 if gathers else ', 1 NCCL all-gather of [N,24] rows per step' + gather_note)})
         if world > 1:
             details['p2p_bytes_per_step_per_gpu'] = int(n_local * 96 * (world - 1))
+            if gathers and args.gather == 'fused':
+                details['gather_flag_timeouts'] = pnp.gather_timeouts(dev)
+                if details['gather_flag_timeouts']:
+                    raise SystemExit(f"fused gather: {details['gather_flag_timeouts']} flag waits timed out")
         line = {
             'metric': METRIC, 'value': n_total * args.steps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,

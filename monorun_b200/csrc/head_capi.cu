@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/monorun_head.h"
@@ -102,6 +103,42 @@ int conv_launch(mrhead_ctx* ctx, const mrhead_layer* l, const void* in, int n, i
     cp.relu = l->relu; cp.out_mode = out_mode;
     cp.tmem_cols = tmem_cols_for(l->cout_pad);
     cp.bias = l->bias; cp.row_bias = row_bias; cp.out = out;
+
+    // 3x3: one activation load per K chunk, the nine taps as shifted operand views (conv3x3_reuse_kernel); 128-row tiles
+    // with two accumulator sets when the channel count allows it.  MRHEAD_CONV = pertap | reuse256 | reuse128 (A/B).
+    static const int reuse_mode = [] {
+        const char* e = std::getenv("MRHEAD_CONV");
+        if (!e) return 128;
+        if (!std::strcmp(e, "pertap")) return 0;
+        if (!std::strcmp(e, "reuse256")) return 256;
+        return 128;
+    }();
+    if (l->taps == 9 && reuse_mode) {
+        const size_t budget = kSmemBudget - kSmemTail;
+        const int bm = (reuse_mode == 128 && l->cout_pad % 64 == 0) ? 128 : 256;
+        const mrhead::ReuseLayout L = mrhead::reuse_layout(bm, wp, l->cout_pad, budget);
+        if (L.b_stages >= 3) {
+            cp.stages = (int)budget;
+            cp.num_tiles = (int)((rows + bm - 1) / bm);
+            CUtensorMap ta, tw;
+            rc = make_tmap(ctx, &ta, in, (uint64_t)rows, (uint64_t)l->cin, mrhead::kHaloBox);
+            if (rc) return rc;
+            rc = make_tmap(ctx, &tw, l->weight, (uint64_t)l->taps * l->cout_pad, (uint64_t)l->cin, (uint32_t)l->cout_pad);
+            if (rc) return rc;
+            const size_t smem = L.a_stages * L.a_bytes + L.b_stages * L.b_bytes + kSmemTail;
+            static std::atomic<int> configured2{0};
+            if (!configured2.exchange(1)) {
+                MH_CUDA(cudaFuncSetAttribute(mrhead::conv3x3_reuse_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+                MH_CUDA(cudaFuncSetAttribute(mrhead::conv3x3_reuse_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+            }
+            const int grid = cp.num_tiles < ctx->sm_count ? cp.num_tiles : ctx->sm_count;
+            if (bm == 128) mrhead::conv3x3_reuse_kernel<128><<<grid, mrhead::kConvThreads, smem, stream>>>(ta, tw, cp);
+            else mrhead::conv3x3_reuse_kernel<256><<<grid, mrhead::kConvThreads, smem, stream>>>(ta, tw, cp);
+            MH_CUDA(cudaGetLastError());
+            ctx->launches++;
+            return MRHEAD_OK;
+        }
+    }
 
     CUtensorMap ta, tw;
     rc = make_tmap(ctx, &ta, in, (uint64_t)rows, (uint64_t)l->cin, 128);

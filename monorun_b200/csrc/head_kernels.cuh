@@ -40,6 +40,111 @@ __device__ __forceinline__ size_t conv_stage_bytes(int cout_pad) {
     return (size_t)2 * 128 * 128 + (size_t)cout_pad * 128;  // A0 + A1 (128 rows x 128 B each) + B (cout_pad rows x 128 B)
 }
 
+// Epilogue warps (4..11) of both convolution kernels: TMEM -> registers -> bias / ReLU / latent bias -> global, tile by
+// tile; arrives on tmem_empty when a tile's accumulators have been drained.
+// BM = 256: one accumulator set, warps 4-7 drain rows 0-127 (columns [0, cout_pad)), warps 8-11 rows 128-255
+// (columns [cout_pad, 2 cout_pad)).  BM = 128: TWO accumulator sets of cout_pad columns used by alternate tiles (full /
+// empty barrier pair per set), so that this epilogue overlaps the MMAs of the next tile; warps 4-7 drain the first half
+// of the columns, warps 8-11 the second half.
+template <int BM>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& cp, uint32_t tmem_base, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, int warp, int lane) {
+        const int quarter = warp & 3;            // TMEM lanes this warp may access: 32 * (warp % 4) ...
+        const int half = (warp - 4) >> 2;
+        const int roi_rows = cp.hp * cp.wp;
+        const int c_begin = BM == 256 ? 0 : half * (cp.cout_pad / 2), c_end = BM == 256 ? cp.cout_pad : c_begin + cp.cout_pad / 2;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < cp.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = BM == 256 ? 0u : (it & 1u), tphase = BM == 256 ? (it & 1u) : ((it >> 1) & 1u);
+            mbar_wait(tmem_full + buf, tphase);
+            tc_fence_after();
+            const int row = tile * BM + (BM == 256 ? half * 128 : 0) + quarter * 32 + lane;
+            const int roi = row / roi_rows;
+            const int pos = row - roi * roi_rows;
+            const int y = pos / cp.wp, x = pos - y * cp.wp;
+            const bool in_range = row < cp.rows_total;
+            const bool interior = in_range && y >= 1 && y <= cp.h && x >= 1 && x <= cp.w;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((BM == 256 ? half : (int)buf) * cp.cout_pad);
+            // 32 accumulator columns per TMEM round trip (two 16-column loads, one wait); bias and per-RoI latent bias
+            // come in as float4 (every lane reads the same bias: broadcast loads)
+            const float* rb = (cp.row_bias && in_range) ? cp.row_bias + (size_t)roi * cp.cout : nullptr;
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                uint32_t v[32];
+                const bool two = c0 + 16 < c_end;
+                tmem_ld16(taddr + (uint32_t)c0, v);   // whole warp, also for rows past the end
+                if (two) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    if (hh == 1 && !two) break;
+                    const int cb = c0 + 16 * hh;
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[16 * hh + j]);
+                    if (cb + 16 <= cp.cout && (cp.cout & 3) == 0) {   // full chunk: vector loads
+                        if (cp.bias) {
+                            const float4* b4 = reinterpret_cast<const float4*>(cp.bias + cb);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 t = __ldg(b4 + q);
+                                f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w;
+                            }
+                        }
+                        if (cp.relu) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        if (rb) {
+                            const float4* r4 = reinterpret_cast<const float4*>(rb + cb);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 t = __ldg(r4 + q);
+                                f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int c = cb + j;
+                            if (c < cp.cout) {
+                                if (cp.bias) f[j] += __ldg(cp.bias + c);
+                                if (cp.relu) f[j] = fmaxf(f[j], 0.f);
+                                if (rb) f[j] += __ldg(rb + c);
+                            }
+                        }
+                    }
+                    if (!interior) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+                    }
+                    if (cp.out_mode == kOutBf16Rows) {
+                        if (in_range && cb < cp.cout) {
+                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(cp.out) + (size_t)row * cp.cout + cb);
+                            dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                            dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                        }
+                    } else if (cp.out_mode == kOutF32Rows) {
+                        if (in_range) {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(cp.out) + (size_t)row * cp.cout_pad + cb);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        }
+                    } else {
+                        if (interior) {
+                            float* dst = reinterpret_cast<float*>(cp.out) + ((size_t)roi * cp.cout * cp.h + (y - 1)) * cp.w + (x - 1);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (cb + j < cp.cout) dst[(size_t)(cb + j) * cp.h * cp.w] = f[j];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + buf);
+        }
+}
+
 // D[rows, cout] = act( sum_taps A[rows + shift(tap), cin] * W_tap[cout, cin]^T + bias ) (+ row_bias), bf16 operands,
 // fp32 accumulation in TMEM.  Persistent: CTA b handles tiles b, b + gridDim.x, ...
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -130,100 +235,145 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: TMEM -> registers -> global =====================
-        const int quarter = warp & 3;            // TMEM lanes this warp may access: 32 * (warp % 4) ...
-        const int half = (warp - 4) >> 2;
-        const int roi_rows = cp.hp * cp.wp;
-        uint32_t tphase = 0;
-        for (int tile = blockIdx.x; tile < cp.num_tiles; tile += gridDim.x) {
-            mbar_wait(tmem_full, tphase);
-            tc_fence_after();
-            const int row = tile * kBlockM + half * 128 + quarter * 32 + lane;
-            const int roi = row / roi_rows;
-            const int pos = row - roi * roi_rows;
-            const int y = pos / cp.wp, x = pos - y * cp.wp;
-            const bool in_range = row < cp.rows_total;
-            const bool interior = in_range && y >= 1 && y <= cp.h && x >= 1 && x <= cp.w;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * cp.cout_pad);
-            // 32 accumulator columns per TMEM round trip (two 16-column loads, one wait); bias and per-RoI latent bias
-            // come in as float4 (every lane reads the same bias: broadcast loads)
-            const float* rb = (cp.row_bias && in_range) ? cp.row_bias + (size_t)roi * cp.cout : nullptr;
-            for (int c0 = 0; c0 < cp.cout_pad; c0 += 32) {
-                uint32_t v[32];
-                const bool two = c0 + 16 < cp.cout_pad;
-                tmem_ld16(taddr + (uint32_t)c0, v);   // whole warp, also for rows past the end
-                if (two) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);
-                tmem_ld_wait();
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    if (hh == 1 && !two) break;
-                    const int cb = c0 + 16 * hh;
-                    float f[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[16 * hh + j]);
-                    if (cb + 16 <= cp.cout && (cp.cout & 3) == 0) {   // full chunk: vector loads
-                        if (cp.bias) {
-                            const float4* b4 = reinterpret_cast<const float4*>(cp.bias + cb);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 t = __ldg(b4 + q);
-                                f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w;
-                            }
-                        }
-                        if (cp.relu) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-                        }
-                        if (rb) {
-                            const float4* r4 = reinterpret_cast<const float4*>(rb + cb);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 t = __ldg(r4 + q);
-                                f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int c = cb + j;
-                            if (c < cp.cout) {
-                                if (cp.bias) f[j] += __ldg(cp.bias + c);
-                                if (cp.relu) f[j] = fmaxf(f[j], 0.f);
-                                if (rb) f[j] += __ldg(rb + c);
-                            }
-                        }
-                    }
-                    if (!interior) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = 0.f;
-                    }
-                    if (cp.out_mode == kOutBf16Rows) {
-                        if (in_range && cb < cp.cout) {
-                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(cp.out) + (size_t)row * cp.cout + cb);
-                            dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                            dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
-                        }
-                    } else if (cp.out_mode == kOutF32Rows) {
-                        if (in_range) {
-                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(cp.out) + (size_t)row * cp.cout_pad + cb);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                        }
-                    } else {
-                        if (interior) {
-                            float* dst = reinterpret_cast<float*>(cp.out) + ((size_t)roi * cp.cout * cp.h + (y - 1)) * cp.w + (x - 1);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (cb + j < cp.cout) dst[(size_t)(cb + j) * cp.h * cp.w] = f[j];
-                        }
+        conv_epilogue<256>(cp, tmem_base, tmem_full, tmem_empty, warp, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, cp.tmem_cols);
+}
+
+// ------------------------------------------------------------------ 3x3 convolution with ONE activation load per K chunk
+// conv_gemm_kernel reads the activation tile once per TAP: nine loads of rows that are the same rows shifted by
+// (ky-1) wp + (kx-1).  Here the BM rows are loaded ONCE per 64-channel chunk together with their (wp + 1)-row halo on
+// either side (64-row TMA boxes), and the nine taps are nine UMMA operand views INTO that tile: the matrix descriptor's
+// start address moves by whole 128-byte rows.  (The 128-byte swizzle is a function of the absolute shared-memory address
+// bits, for TMA writes and UMMA reads alike, so a view that starts mid-pattern needs nothing else: verified on B200 by
+// tests/test_head_gpu.py; setting the descriptor's base-offset field to the row phase gives WRONG results.)
+// Only the weight tiles still stream per tap: 328 KB instead of 576 KB of L2 reads per 256 rows and chunk.  That alone
+// changed nothing (2.411 vs 2.416 ms per 1024 RoIs: the per-tap kernel was not L2-bound, profiles/r02_head_variants.txt);
+// what it buys is BM = 128: with half the rows per tile the accumulator needs cout_pad <= 256 of the 512 TMEM columns,
+// TWO sets fit, and the epilogue of tile i runs under the MMAs of tile i + 1 -- at +8 % L2 traffic instead of +50 %.
+constexpr int kHaloBox = 64;   // rows per TMA box of the activation super-tile
+
+struct ReuseLayout {
+    int a_boxes, a_lead;       // boxes per super-tile, rows in front of the tile's first row
+    int a_stages, b_stages;
+    size_t a_bytes, b_bytes;
+};
+
+__host__ __device__ inline ReuseLayout reuse_layout(int bm, int wp, int cout_pad, size_t budget) {
+    ReuseLayout L;
+    L.a_lead = wp + 1;
+    L.a_boxes = (bm + 2 * L.a_lead + kHaloBox - 1) / kHaloBox;
+    L.a_bytes = (size_t)L.a_boxes * kHaloBox * 128;
+    L.b_bytes = (size_t)cout_pad * 128;
+    L.a_stages = 2;
+    long long left = (long long)budget - (long long)(L.a_stages * L.a_bytes);
+    L.b_stages = left > 0 ? (int)(left / (long long)L.b_bytes) : 0;
+    if (L.b_stages > 9) L.b_stages = 9;
+    return L;
+}
+
+template <int BM>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_wgt,
+                     const __grid_constant__ ConvParams cp) {
+    static_assert(BM == 128 || BM == 256, "tile height");
+    constexpr int kSets = BM == 128 ? 2 : 1;     // accumulator sets
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const ReuseLayout L = reuse_layout(BM, cp.wp, cp.cout_pad, (size_t)cp.stages);   // cp.stages carries the operand budget in bytes
+    uint8_t* a_tiles = smem;
+    uint8_t* b_tiles = smem + (size_t)L.a_stages * L.a_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_tiles + (size_t)L.b_stages * L.b_bytes);
+    uint64_t* a_empty = a_full + L.a_stages;
+    uint64_t* b_full = a_empty + L.a_stages;
+    uint64_t* b_empty = b_full + L.b_stages;
+    uint64_t* tmem_full = b_empty + L.b_stages;
+    uint64_t* tmem_empty = tmem_full + kSets;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kSets);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = cp.cin / kBlockK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_act);
+        tma_prefetch_desc(&tmap_wgt);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < L.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < L.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < kSets; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpilogueWarps); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, cp.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int as = 0, bs = 0;
+            uint32_t aphase = 0, bphase = 0;
+            for (int tile = blockIdx.x; tile < cp.num_tiles; tile += gridDim.x) {
+                const int m0 = tile * BM;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_empty[as], aphase ^ 1u);
+                    uint8_t* at = a_tiles + (size_t)as * L.a_bytes;
+                    mbar_expect_tx(&a_full[as], (uint32_t)L.a_bytes);
+                    for (int b = 0; b < L.a_boxes; ++b)   // rows before the first / after the last are zero-filled
+                        tma_load_2d(at + (size_t)b * kHaloBox * 128, &tmap_act, kc * kBlockK, m0 - L.a_lead + b * kHaloBox, &a_full[as]);
+                    if (++as == L.a_stages) { as = 0; aphase ^= 1u; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&b_empty[bs], bphase ^ 1u);
+                        mbar_expect_tx(&b_full[bs], (uint32_t)L.b_bytes);
+                        tma_load_2d(b_tiles + (size_t)bs * L.b_bytes, &tmap_wgt, kc * kBlockK, tap * cp.cout_pad, &b_full[bs]);
+                        if (++bs == L.b_stages) { bs = 0; bphase ^= 1u; }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
-            tphase ^= 1u;
         }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, cp.cout_pad);
+            int as = 0, bs = 0;
+            uint32_t aphase = 0, bphase = 0, it = 0;
+            for (int tile = blockIdx.x; tile < cp.num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t set = kSets == 2 ? (it & 1u) : 0u, tphase = kSets == 2 ? ((it >> 1) & 1u) : (it & 1u);
+                mbar_wait(&tmem_empty[set], tphase ^ 1u);   // the epilogue has drained this set (two tiles ago for BM = 128)
+                tc_fence_after();
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_full[as], aphase);
+                    tc_fence_after();
+                    const uint8_t* at = a_tiles + (size_t)as * L.a_bytes;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&b_full[bs], bphase);
+                        tc_fence_after();
+                        const uint64_t b0 = umma_desc_k128(b_tiles + (size_t)bs * L.b_bytes);
+                        const int row0 = L.a_lead + (tap / 3 - 1) * cp.wp + (tap % 3 - 1);
+#pragma unroll
+                        for (int half = 0; half < BM / 128; ++half) {
+                            const uint64_t a0 = umma_desc_k128(at + (size_t)(row0 + half * 128) * 128);
+                            const uint32_t d = tmem_base + (uint32_t)((BM == 256 ? half : (int)set) * cp.cout_pad);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                                umma_bf16(d, a0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&b_empty[bs]);
+                        if (++bs == L.b_stages) { bs = 0; bphase ^= 1u; }
+                    }
+                    umma_commit(&a_empty[as]);   // all nine taps of this chunk have read the super-tile
+                    if (++as == L.a_stages) { as = 0; aphase ^= 1u; }
+                }
+                umma_commit(&tmem_full[set]);
+            }
+        }
+    } else if (warp >= 4) {
+        conv_epilogue<BM>(cp, tmem_base, tmem_full, tmem_empty, warp, lane);
     }
 
     tc_fence_before();
@@ -349,11 +499,12 @@ __global__ void __launch_bounds__(256) carafe_kernel(const __nv_bfloat16* __rest
             for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
             wgt[s] = e / t;
         }
-        float acc[SS][8];
+        // packed fp32: one FFMA2 (weight as the broadcast operand) per channel pair and sub-pixel
+        float2 acc[SS][4];
 #pragma unroll
         for (int s = 0; s < SS; ++s)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[s][j] = 0.f;
+            for (int j = 0; j < 4; ++j) acc[s][j] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < KK; ++k) {
             const int yy = y + k / K - K / 2, xx = x + k % K - K / 2;
@@ -365,19 +516,16 @@ __global__ void __launch_bounds__(256) carafe_kernel(const __nv_bfloat16* __rest
             const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float lo = __uint_as_float(u[j] << 16), hi = __uint_as_float(u[j] & 0xffff0000u);
+                const float2 v = make_float2(__uint_as_float(u[j] << 16), __uint_as_float(u[j] & 0xffff0000u));
 #pragma unroll
-                for (int s = 0; s < SS; ++s) {
-                    acc[s][2 * j] = fmaf(ws[s], lo, acc[s][2 * j]);
-                    acc[s][2 * j + 1] = fmaf(ws[s], hi, acc[s][2 * j + 1]);
-                }
+                for (int s = 0; s < SS; ++s) acc[s][j] = __ffma2_rn(make_float2(ws[s], ws[s]), v, acc[s][j]);
             }
         }
 #pragma unroll
         for (int s = 0; s < SS; ++s) {
             const int oy = S * y + s / S, ox = S * x + s % S;
-            const uint4 pk = make_uint4(pack_bf16(acc[s][0], acc[s][1]), pack_bf16(acc[s][2], acc[s][3]),
-                                        pack_bf16(acc[s][4], acc[s][5]), pack_bf16(acc[s][6], acc[s][7]));
+            const uint4 pk = make_uint4(pack_bf16(acc[s][0].x, acc[s][0].y), pack_bf16(acc[s][1].x, acc[s][1].y),
+                                        pack_bf16(acc[s][2].x, acc[s][2].y), pack_bf16(acc[s][3].x, acc[s][3].y));
             reinterpret_cast<uint4*>(o + ((size_t)(oy + 1) * wop + (ox + 1)) * C)[lane] = pk;
         }
     }

@@ -190,7 +190,8 @@ struct PassFlags {
 };
 
 // kPassFirst: an evaluation from the observations -- the initial point (plain fp32; also turns W into M) or, with
-// PassArgs::anchor, the fp64 anchor.  One body for both keeps the hot code small (instruction cache).
+// PassArgs::anchor, the fp64 anchor.  One body for both (the remainder routine reads the switch at run time; the main
+// loops instantiate it once per kind).
 enum PassKind { kPassFirst = 0, kPassDelta = 2, kPassUndo = 3 };
 
 // Uniform inputs of a pass (one struct for all kinds keeps the out-of-line remainder routine to one signature).
@@ -225,10 +226,11 @@ __device__ __forceinline__ void store_consts(float* consts, const CamN& c, const
 
 // The body of every pass for one point (V = float) or one pair of points (V = float2) at slot index idx.
 // `live`: only read for V = float (the remainder path): a dead lane computes on point 0 with M = 0 and stores nothing.
-template <int WMODE, int KIND, class V>
+template <int WMODE, int KIND, class V, int AN = -1>   // AN: PassArgs::anchor known at compile time (0 / 1), -1 = read it
 __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int idx, bool live, const PassArgs& u,
                                            const CamN& cam, const ClipWindow& win, V a[15], PassFlags& f) {
     using L = Lanes<V>;
+    const bool anchor = AN < 0 ? u.anchor : (AN != 0);
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     float* s3 = slot;
     float* s2 = slot + 3 * P;
@@ -240,7 +242,7 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
     if (L::kWidth == 1 && !live) { m00 = L::bc(0.f); m11 = L::bc(0.f); m01 = L::bc(0.f); }
 
     if (KIND == kPassFirst) {
-        if (!u.anchor) {
+        if (!anchor) {
             // weights -> M = F W^T W F, stored in place of W for the later passes
             if (WMODE == MRPNP_W_FULL) {
                 const V wxx = m00, wxy = m01, wyy = m11;
@@ -267,7 +269,7 @@ __device__ __forceinline__ void pass_point(float* __restrict__ slot, int P, int 
         const V iz = vrcp(z1);
         const V xn = vmul(x1, iz), yn = vmul(y1, iz);
         V e0, e1;
-        if (!u.anchor) {
+        if (!anchor) {
             // plain fp32: the residuals are many pixels here, and the decision on the first step is checked against
             // its own rounding (see the LM loop)
             e0 = vsub(xn, vfma(o0, L::bc(cam.ifx), L::bc(cam.ncxi)));
@@ -365,6 +367,24 @@ __device__ __forceinline__ float warp_reduce16_scatter(float v[16], int lane) {
     return v[0] + __shfl_xor_sync(kFull, v[0], 1);
 }
 
+// The same totals through shared memory: the 15 per-lane sums go to a [15][36] float tile (row stride 36 keeps the 128-bit
+// reads below free of bank conflicts), lane (k, h) = (lane & 15, lane >> 4) adds 16 of the 32 entries of value k with four
+// 128-bit loads and one shuffle joins the halves: lanes k and k + 16 end with the total of value k (k < 15).
+// 15 + 15 + 4 + 15 + 2 instructions against ~120 for the shuffle network above.
+constexpr int kReduceTileFloats = 15 * 36 + 4;
+__device__ __forceinline__ float warp_reduce15_smem(const float2 a[15], float* __restrict__ red, int lane) {
+#pragma unroll
+    for (int i = 0; i < 15; ++i) red[i * 36 + lane] = a[i].x + a[i].y;
+    __syncwarp();
+    const int k = min(lane & 15, 14), h = lane >> 4;
+    const float4* p = reinterpret_cast<const float4*>(red + k * 36 + h * 16);
+    const float4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
+    float t = (((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w))) +
+              (((q2.x + q2.y) + (q2.z + q2.w)) + ((q3.x + q3.y) + (q3.z + q3.w)));
+    t += __shfl_xor_sync(kFull, t, 16);
+    return t;
+}
+
 __device__ __forceinline__ bool flags_raised(const PassFlags& f, const ClipWindow& w) {
     return !(f.mz >= w.zlo) || !(f.mx <= w.xhalf) || !(f.my <= w.yhalf);
 }
@@ -435,7 +455,7 @@ __device__ __noinline__ bool pass_remainder(float* slot, int P, int start, int n
 // remainder [n_main, n) if any.  Returns false if a total is not finite.
 template <int WMODE>
 __device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, int lane, const PassArgs& u, bool first,
-                                         float* scratch, float* arg_stash, bool& flagged) {
+                                         float* scratch, float* arg_stash, float* red, bool& flagged) {
     float2 a[15];
 #pragma unroll
     for (int i = 0; i < 15; ++i) a[i] = make_float2(0.f, 0.f);
@@ -444,8 +464,18 @@ __device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, 
     const ClipWindow win = args_win(u);
     const int end = n_main + 2 * lane;
     if (first) {
+#ifndef MRPNP_EXP_MERGED_FIRST   // one loop per kind: 2-3 % faster than one loop with a runtime switch (r02_ab_variants.txt, call 16)
+        if (u.anchor) {
+#pragma unroll 1
+            for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassFirst, float2, 1>(slot, P, idx, true, u, cam, win, a, f);
+        } else {
+#pragma unroll 1
+            for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassFirst, float2, 0>(slot, P, idx, true, u, cam, win, a, f);
+        }
+#else
 #pragma unroll 1
         for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassFirst, float2>(slot, P, idx, true, u, cam, win, a, f);
+#endif
     } else {
 #ifndef MRPNP_EXP_DELTA_UNROLL
 #define MRPNP_EXP_DELTA_UNROLL 1   // 2 measured 4 % slower (instruction cache)
@@ -454,6 +484,7 @@ __device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, 
 #pragma unroll kDeltaUnroll
         for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassDelta, float2>(slot, P, idx, true, u, cam, win, a, f);
     }
+#ifdef MRPNP_EXP_SHFL_REDUCE
     float s[16];
 #pragma unroll
     for (int i = 0; i < 15; ++i) s[i] = a[i].x + a[i].y;
@@ -461,6 +492,11 @@ __device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, 
     const float tot = warp_reduce16_scatter(s, lane);
     __syncwarp();
     if ((lane & 1) == 0) scratch[lane >> 1] = ((kNegatedSums >> (lane >> 1)) & 1u) ? -tot : tot;
+#else
+    const float tot = warp_reduce15_smem(a, red, lane);
+    __syncwarp();
+    if (lane < 16) scratch[lane] = lane == 15 ? 0.f : (((kNegatedSums >> lane) & 1u) ? -tot : tot);   // [15]: read by the finite test
+#endif
     const unsigned ex = __reduce_max_sync(kFull, __float_as_uint(f.ex)), ey = __reduce_max_sync(kFull, __float_as_uint(f.ey)),
                    ez = __reduce_max_sync(kFull, __float_as_uint(f.ez));
     if (lane == 0) { scratch[16] = __uint_as_float(ex); scratch[17] = __uint_as_float(ey); scratch[18] = __uint_as_float(ez); }

@@ -49,7 +49,9 @@ constexpr int kFastMaxWarps = MRPNP_FAST_WARPS;
 // scale, LM diagonal | [64..95] argument stash of the out-of-line routines | [96..111] camera + clip window (pass constants).  The exact routine's 40-double scratch
 // starts at float 32: it only runs between objects, when the fast path's state is dead.
 // A sums buffer: [0..3] J^T r, [4..13] J^T J, [14] cost term, [16..18] extents; [20..23] linear-initialiser result.
-constexpr int kFastHeaderBytes = 512;
+// [128..671] the 15 x 36 tile of the passes' warp reduction (warp_reduce15_smem).
+constexpr int kFastReduce = 128;
+constexpr int kFastHeaderBytes = 512 + ((kReduceTileFloats * 4 + 127) / 128) * 128;
 constexpr int kFastBufA = 4, kFastBufB = 32, kFastScaleDiag = 56, kFastArgStash = 64, kFastConsts = 96;
 constexpr int kFastScratch64 = 128;   // byte offset
 constexpr int kNoPending = -1;
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
             } else {
                 pa.check = !box_inside_window(args_win(pa), ext, pa.step.cp, pa.step.sp, pa.step.txp, pa.step.typ, pa.step.tzp);
             }
-            jfin = run_pass<WMODE>(slot, P, n_main, n, lane, pa, from_observations, cand, arg_stash, flagged);
+            jfin = run_pass<WMODE>(slot, P, n_main, n, lane, pa, from_observations, cand, arg_stash, hdr + kFastReduce, flagged);
             if (cost_evals == 0) { ext.xm = cand[16]; ext.ym = cand[17]; ext.zm = cand[18]; }
             TR_MARK(from_observations ? 3 : 4)
             if (flagged) { redo = true; break; }

@@ -10,6 +10,8 @@ import torch.distributed as dist
 
 from .pnp import RESULT_STRIDE
 
+MAX_PEERS = 8   # MRPNP_MAX_PEERS
+
 
 def shard_range(n_total, rank, world_size):
     """Contiguous range [start, stop) of rank `rank`; the first n_total % world_size ranks get one extra object."""
@@ -52,31 +54,68 @@ class FusedGather:
     Every rank owns a symmetric-memory buffer ``rows [n_total, 24]`` (torch.distributed._symmetric_memory: the same
     allocation mapped into every peer over NVLink / NVSwitch).  ``solve_batched(..., **fg.solve_kwargs())`` makes the
     kernel store the row of local object i into ALL ranks' buffers at row ``start + i`` -- 96-byte peer-to-peer stores
-    from the epilogue of each object, no separate collective launch, no send / receive staging.  ``fg.finish()`` then
-    runs the symmetric-memory barrier on the current stream, after which ``fg.rows`` holds every rank's rows.
+    from the epilogue of each object, no separate collective launch, no send / receive staging.
 
-    The buffer is overwritten by the next solve of ANY rank: consume (or copy) ``rows`` and call ``finish`` / a
-    barrier before re-using the same FusedGather, or alternate between two instances.
+    Completion is signalled by the solver itself (``signal='flags'``, the default): the last thread block of each
+    rank's launch raises that rank's slot in every rank's flag array (a second, tiny symmetric allocation), and
+    ``fg.finish()`` is a one-warp kernel on the caller's stream that waits until all ranks' slots have reached the
+    current solve number -- no barrier, nothing that makes a rank's NEXT solve wait for the slowest rank's current one;
+    call it when the rows are needed, e.g. a few solves later when several FusedGather instances rotate.
+    ``fg.release()`` (or ``finish(release=True)``) tells the peers that this rank has read the rows: the next solve of
+    any rank into this buffer waits for every rank's release first (write-after-read), normally for zero time.
+    ``signal='barrier'`` is the round-1 protocol: ``finish()`` runs the symmetric-memory barrier.
     """
 
-    def __init__(self, n_total, device, group=None):
+    def __init__(self, n_total, device, group=None, signal='flags'):
         import torch.distributed._symmetric_memory as symm
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device)
         self.n_total = int(n_total)
         self.start, self.stop = shard_range(n_total, self.rank, self.world)
-        self.rows = symm.empty((self.n_total, RESULT_STRIDE), dtype=torch.float32, device=torch.device(device))
+        self.rows = symm.empty((self.n_total, RESULT_STRIDE), dtype=torch.float32, device=self.device)
         self.rows.zero_()
         self.handle = symm.rendezvous(self.rows, group.group_name)
         self.peers = [int(p) for p in self.handle.buffer_ptrs]
+        self.signal = signal
+        self.epoch = 0        # solves issued into this buffer
+        self.waited = 0       # last solve number finish() waited for
+        if signal == 'flags':
+            # [0, world): completion flags (slot r raised by rank r's launch); [world, 2 world): releases of the readers
+            self.sig = symm.empty((2 * MAX_PEERS,), dtype=torch.int32, device=self.device)
+            self.sig.zero_()
+            self.sig_handle = symm.rendezvous(self.sig, group.group_name)
+            self.sig_ptrs = [int(p) for p in self.sig_handle.buffer_ptrs]
+            torch.cuda.synchronize(self.device)
+            self.sig_handle.barrier()   # every rank's arrays are zero before anybody raises a flag
+            torch.cuda.synchronize(self.device)
 
     def solve_kwargs(self):
-        return dict(peers=self.peers, row_offset=self.start)
+        """Keyword arguments of ONE ``solve_batched`` call into this buffer (advances the solve number)."""
+        kw = dict(peers=self.peers, row_offset=self.start)
+        if self.signal == 'flags':
+            self.epoch += 1
+            kw.update(peer_flags=self.sig_ptrs, flag_slot=self.rank, flag_value=self.epoch,
+                      acks=self.sig_ptrs[self.rank] + 4 * MAX_PEERS, ack_value=self.epoch - 1)
+        return kw
 
-    def finish(self):
-        """Cross-rank barrier on the current stream: afterwards every rank's kernel has completed and ``rows`` is whole."""
-        self.handle.barrier()
+    def finish(self, release=True):
+        """On the current stream: afterwards every rank's rows of the latest solve are in ``rows``.  ``release=True``
+        also tells the peers that the rows may be overwritten by the next solve -- pass False and call ``release()``
+        after the consumer when something reads ``rows`` on this stream."""
+        if self.signal != 'flags':
+            self.handle.barrier()
+            return self.rows
+        from . import pnp
+        acks = [p + 4 * MAX_PEERS for p in self.sig_ptrs] if release else None
+        pnp.gather_wait(self.device, self.sig_ptrs[self.rank], self.world, self.epoch, acks, self.rank, self.epoch)
+        self.waited = self.epoch
         return self.rows
+
+    def release(self):
+        from . import pnp
+        if self.signal == 'flags':
+            pnp.gather_wait(self.device, None, self.world, 0, [p + 4 * MAX_PEERS for p in self.sig_ptrs], self.rank, self.waited)
 
 
 def solve_sharded(solve_fn, n_total, group=None):

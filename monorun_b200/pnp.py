@@ -99,7 +99,8 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
                   layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, istd_thres=0.6,
                   inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
                   adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False, peers=None, row_offset=0,
-                  decision_bands=None, ransac_thres=None):
+                  decision_bands=None, ransac_thres=None, peer_flags=None, flag_slot=0, flag_value=0, acks=None,
+                  ack_value=0):
     """Batched uncertainty-PnP on device tensors -- direct wrapper of ``mrpnp_solve``.
 
     layout 'planar':      coords_3d [N,3,*], coords_2d [N,2,*], weights [N,2|3,*]   (head level)
@@ -161,6 +162,13 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
         p.n_peers, p.row_offset = len(peers), int(row_offset)
         for r, ptr in enumerate(peers):
             p.peer_results[r] = _native.ffi.cast('float*', int(ptr))
+        if peer_flags:   # completion flags raised by the launch's last thread block (dist.FusedGather)
+            assert len(peer_flags) == len(peers)
+            for r, ptr in enumerate(peer_flags):
+                p.peer_flags[r] = _native.ffi.cast('uint32_t*', int(ptr))
+            p.flag_slot, p.flag_value = int(flag_slot), int(flag_value) & 0xffffffff
+            if acks:
+                p.acks, p.ack_value = _native.ffi.cast('const uint32_t*', int(acks)), int(ack_value) & 0xffffffff
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
         _native.check(_native.lib().mrpnp_solve(
@@ -361,6 +369,26 @@ def score_stage(rows, dims, reg_fc_out, w1, b1, w2t, b2, w3, b3, cov_calib_logsc
             _ptr(w2t), _ptr(b2), _ptr(w3), _ptr(b3), h1, h2, _ptr(ds), int(bool(pre_sigmoid)), _ptr(scores), _ptr(bbox),
             _ptr(cal), _ptr(logits), n, _native.ffi.cast('void*', stream)))
     return scores, bbox, cal, logits
+
+
+def gather_wait(device, flags_ptr=None, n=1, value=0, peer_acks=None, ack_slot=0, ack_value=0):
+    """``mrpnp_gather_wait`` on the current stream of ``device``: wait until the ``n`` completion flags at ``flags_ptr``
+    reach ``value`` and / or store ``ack_value`` into slot ``ack_slot`` of every array in ``peer_acks``."""
+    dev = torch.device(device)
+    ctx = get_ctx(dev)
+    arr = _native.ffi.NULL
+    if peer_acks:
+        arr = _native.ffi.new('uint32_t*[]', [_native.ffi.cast('uint32_t*', int(q)) for q in peer_acks])
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().mrpnp_gather_wait(
+            ctx.ptr, _native.ffi.cast('const uint32_t*', int(flags_ptr)) if flags_ptr else _native.ffi.NULL, int(n),
+            int(value) & 0xffffffff, arr, int(ack_slot), int(ack_value) & 0xffffffff, _native.ffi.cast('void*', stream)))
+
+
+def gather_timeouts(device=None):
+    """Flag / ack waits that gave up (``mrpnp_gather_timeouts``; 0 in a healthy run).  Synchronises the device."""
+    return int(_native.lib().mrpnp_gather_timeouts(get_ctx(device).ptr))
 
 
 def nms_bev(bbox_3d, labels=None, group_offsets=None, iou_thr=0.25, max_group=None):

@@ -42,6 +42,33 @@ with torch.no_grad():
     ms_fp32, ref = timed(lambda: dec.forward_all(x, latent, flip=False))
     torch.backends.cudnn.allow_tf32 = True; torch.backends.cuda.matmul.allow_tf32 = True
     ms_tf32, _ = timed(lambda: dec.forward_all(x, latent, flip=False))
+    # cuDNN bf16 channels-last, CONVOLUTIONS ONLY (the bar SURVEY 2b set): the head's seven convolutions with their bias
+    # + ReLU as torch ops on bf16 NHWC tensors -- no latent bias, no CARAFE softmax / reassembly, no fp32 output conversion,
+    # i.e. strictly less work than the native head's 10 launches
+    import torch.nn.functional as F
+    bf = lambda t: t.detach().to(torch.bfloat16)
+    convs = [(bf(m.conv.weight).contiguous(memory_format=torch.channels_last), bf(m.conv.bias)) for m in dec.convs]
+    up = dec.upsample
+    wc, bc = bf(up.channel_compressor.weight).contiguous(memory_format=torch.channels_last), bf(up.channel_compressor.bias)
+    we, be = bf(up.content_encoder.weight).contiguous(memory_format=torch.channels_last), bf(up.content_encoder.bias)
+    xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x28 = torch.randn(n, 256, 28, 28, device='cuda', dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w28 = bf(dec.convs_upsampled[0].conv.weight).contiguous(memory_format=torch.channels_last)
+    b28 = bf(dec.convs_upsampled[0].conv.bias)
+    wf = bf(dec.conv_final.weight).contiguous(memory_format=torch.channels_last)
+    bfin = bf(dec.conv_final.bias)
+
+    def cudnn_convs():
+        h = xb
+        for w_, b_ in convs:
+            h = F.relu(F.conv2d(h, w_, b_, padding=1))
+        c = F.conv2d(h, wc, bc)
+        e = F.conv2d(c, we, be, padding=1)
+        h2 = F.relu(F.conv2d(x28, w28, b28, padding=1))
+        o = F.conv2d(h2, wf, bfin)
+        return e, o
+    torch.backends.cudnn.benchmark = True
+    ms_cudnn, _ = timed(cudnn_convs)
 got = out.view(n, 2, -1, 28, 28)[:, 0]
 rel_rms = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
 peak = None
@@ -55,6 +82,9 @@ line = {'rois': n, 'gflop_per_roi': flops / 1e9,
                    'launches_per_forward': 10, 'dtype': 'bf16 operands, fp32 accumulate (TMEM)'},
         'torch_fp32_cudnn': {'ms': ms_fp32, 'rois_per_s': n / ms_fp32 * 1e3},
         'torch_tf32_cudnn': {'ms': ms_tf32, 'rois_per_s': n / ms_tf32 * 1e3},
+        'cudnn_bf16_channels_last_convs_only': {
+            'ms': ms_cudnn, 'note': 'F.conv2d bf16 NHWC (cudnn.benchmark) + bias + ReLU for the 7 convolutions only: no latent bias, '
+                                    'CARAFE softmax / reassembly or output conversion', 'native_whole_head_over_this': ms_native / ms_cudnn},
         'speedup_vs_fp32': ms_fp32 / ms_native, 'speedup_vs_tf32': ms_tf32 / ms_native,
         'rel_rms_vs_fp32': rel_rms, 'steps': a.steps}
 print(json.dumps(line))
