@@ -117,6 +117,19 @@ typedef struct mrpnp_params {
      * change relative to the cost (two independently rounded fp32 sums); later steps: band_rel |change| +
      * band_mix sqrt(model change * cost).  mrpnp_default_params sets 8e-6, 4e-3, 2e-6; 0 disables a term. */
     float band_first, band_rel, band_mix;
+    /* band_ratio > 0 narrows the later-step band for objects that converge slowly (at least band_ratio_from evaluations):
+     * the deviation of the fp32 trajectory from the oracle's is about 1e-6 of the PREVIOUS step, so its effect on a cost
+     * change, relative to that change, scales with |previous step| / |this step|: the band is multiplied by
+     * clamp(band_ratio * that ratio, band_rel_min, band_rel) / band_rel.  These are the objects that are expensive to
+     * solve twice.  mrpnp_default_params sets 2e-5, 1e-4, 10 (over 24 seeded data sets x 8192 objects: 295 instead of 344
+     * hand-backs, 8 instead of 7 objects with an evaluation count different from the fp64 kernel's, the same 5 outside the
+     * tolerance, mean launch 160 instead of 187 us); band_ratio = 0 switches this off. */
+    float band_ratio, band_rel_min;
+    int32_t band_ratio_from;
+    /* Diagnostic, DEVICE pointer to [N] int32 or NULL: for every object the fp32 path handed to the exact routine,
+     * reason | (evaluations so far << 8); reason 1 = a point near a clip bound, 2 = first-step band, 3 = function-
+     * tolerance band, 4 = accept band.  Entries of other objects are left untouched. */
+    int32_t* hand_back_log;
     /* Reprojection-threshold consensus after the start pose -- the deterministic counterpart of the inlier refinement
      * the reference gets from cv2.solvePnPRansac (pnp_uncert_cpu.py:34-51): with the start pose (on-device linear
      * initialiser or init_pose) as the model, an istd inlier whose reprojection error exceeds the threshold is dropped,

@@ -221,6 +221,8 @@ int solve_device(mrpnp_ctx* ctx, const mrpnp_params* p, const float* c3d, const 
     kp.work_list = nullptr; kp.work_count = nullptr;
     kp.stats = ctx->stats;
     kp.band_first = p->band_first; kp.band_rel = p->band_rel; kp.band_mix = p->band_mix;
+    kp.band_ratio = p->band_ratio; kp.band_rel_min = p->band_rel_min; kp.band_ratio_from = p->band_ratio_from;
+    kp.hand_back_log = p->hand_back_log;
     kp.global_interleaved = (precision == MRPNP_PREC_FAST && p->layout == MRPNP_LAYOUT_INTERLEAVED) ? 1 : 0;
     kp.ransac_thres = (!dense && p->inlier_opt_only) ? p->ransac_thres : nullptr;
     kp.ransac_ratio = (dense && p->inlier_opt_only) ? p->ransac_ratio : 0.f;
@@ -293,6 +295,9 @@ void mrpnp_default_params(mrpnp_params* p, int32_t n_obj, int32_t n_pts) {
     p->band_first = 8e-6f;
     p->band_rel = 4e-3f;
     p->band_mix = 2e-6f;
+    p->band_ratio = 2e-5f;      // slowly converging objects (>= 10 evaluations): band scaled by 2e-5 |previous step| / |step|,
+    p->band_rel_min = 1e-4f;    // not below 1e-4 / band_rel of its width (profiles/r02_band_sweep.txt)
+    p->band_ratio_from = 10;
 }
 
 int mrpnp_create(mrpnp_ctx** out, int device) {

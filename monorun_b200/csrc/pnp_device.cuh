@@ -70,6 +70,9 @@ struct KParams {
     int* redo_list;
     unsigned long long* stats;   // [0] running total of handed-back objects (mrpnp_handed_back_count)
     float band_first, band_rel, band_mix;   // half-widths of the decision bands (mrpnp_params)
+    float band_ratio, band_rel_min;
+    int band_ratio_from;
+    int* hand_back_log;       // [N] or NULL: reason | evaluations << 8 of the objects handed back (diagnostic)
     int global_interleaved;   // the tensors in global memory are [N,P,C] although the slot is planar (staging transposes)
     // reprojection-threshold consensus after the start pose (replaces the inlier refinement of cv2.solvePnPRansac,
     // pnp_uncert_cpu.py:34-51): per-object threshold in pixels, or (fused head entry) ratio * RoI height
@@ -381,9 +384,12 @@ __device__ __forceinline__ Camera<T> load_camera(const KParams& kp, int obj) {
     return c;
 }
 
+// k0 / kstep: the rows (of 32 points) k0, k0 + kstep, ... only -- a team of warps splits an evaluation this way
+// (RedoTeam below); 0 / 1 = every row.
 template <int WMODE, int LAYOUT>
 __device__ __noinline__ void eval_pass_fp64(const KParams& kp, int obj, const float* __restrict__ slot, int n, int lane,
-                                            uint32_t bits, int clipsem, bool use_bits, double* scratch) {
+                                            uint32_t bits, int clipsem, bool use_bits, double* scratch, int k0 = 0,
+                                            int kstep = 1) {
     const int P = kp.n_pts;
     const float* __restrict__ s3 = slot;
     const float* __restrict__ s2 = slot + 3 * P;
@@ -399,7 +405,7 @@ __device__ __noinline__ void eval_pass_fp64(const KParams& kp, int obj, const fl
     for (int i = 0; i < 16; ++i) acc[i] = 0.0;
     bool any = false;
 #pragma unroll 2
-    for (int p = lane, k = 0; p < n; p += 32, ++k) {
+    for (int p = lane + 32 * k0, k = k0; p < n; p += 32 * kstep, k += kstep) {
         if (use_bits && !((bits >> k) & 1u)) continue;
         const double X = (double)s3[sidx<LAYOUT, 3>(p, 0, P)];
         const double Y = (double)s3[sidx<LAYOUT, 3>(p, 1, P)];
@@ -478,6 +484,61 @@ __device__ __noinline__ void eval_pass_fp64(const KParams& kp, int obj, const fl
     warp_allreduce16<double>(acc, scratch + kScrSums, lane);  // leaves the 16 totals in scratch[0..15]
     if (lane == 0) scratch[kScrClip] = any ? 1.0 : 0.0;
     __syncwarp();
+}
+
+// ------------------------------------------------------------------ a CTA's warps evaluating ONE object together
+// Used by the MRPNP_PREC_FAST kernel for the objects it hands back: when all warps of a CTA have run out of fresh objects
+// they solve handed-back objects together -- warp 0 runs solve_object_exact, and each of its fp64 evaluations is split by
+// rows over all warps (warp w takes rows w, w + W, ...; partial totals through shared memory, added in warp order, so
+// the result does not depend on timing).  Two named-barrier rounds per evaluation.
+struct RedoTeam {
+    double part[kMaxWarpsPerCta][18];   // per warp: 16 totals, [16] clip flag
+    double pt[4];
+    float* slot;
+    int cmd, n, clipsem, obj;
+};
+enum { kTeamEval = 0, kTeamDone = 1 };
+__device__ __forceinline__ void team_barrier() {
+    asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory");
+}
+
+// Leader side of one evaluation (same contract as eval_pass_fp64 with use_bits = false).
+template <int WMODE, int LAYOUT>
+__device__ __forceinline__ void team_eval_fp64(const KParams& kp, RedoTeam* team, int obj, float* slot, int n, int lane,
+                                               int clipsem, double* scratch) {
+    const int nw = blockDim.x >> 5;
+    if (lane < 4) team->pt[lane] = scratch[kScrPt + lane];
+    if (lane == 0) { team->cmd = kTeamEval; team->n = n; team->clipsem = clipsem; team->obj = obj; team->slot = slot; }
+    __syncwarp();
+    team_barrier();                                                       // workers start
+    eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, 0u, clipsem, false, scratch, 0, nw);
+    if (lane < 16) team->part[0][lane] = scratch[kScrSums + lane];
+    if (lane == 16) team->part[0][16] = scratch[kScrClip];
+    __syncwarp();
+    team_barrier();                                                       // all partial totals are written
+    if (lane < 17) {
+        double t = team->part[0][lane];
+        for (int w = 1; w < nw; ++w) t += team->part[w][lane];
+        if (lane < 16) scratch[kScrSums + lane] = t; else scratch[kScrClip] = t != 0.0 ? 1.0 : 0.0;
+    }
+    __syncwarp();
+}
+
+// Worker side: warps 1.. of the CTA while warp 0 solves an object; returns when the leader posts kTeamDone.
+template <int WMODE, int LAYOUT>
+__device__ __noinline__ void team_worker(const KParams& kp, RedoTeam* team, double* scratch, int warp, int lane) {
+    const int nw = blockDim.x >> 5;
+    while (true) {
+        team_barrier();
+        if (team->cmd == kTeamDone) break;
+        if (lane < 4) scratch[kScrPt + lane] = team->pt[lane];
+        __syncwarp();
+        eval_pass_fp64<WMODE, LAYOUT>(kp, team->obj, team->slot, team->n, lane, 0u, team->clipsem, false, scratch, warp, nw);
+        if (lane < 16) team->part[warp][lane] = scratch[kScrSums + lane];
+        if (lane == 16) team->part[warp][16] = scratch[kScrClip];
+        __syncwarp();
+        team_barrier();
+    }
 }
 
 // ------------------------------------------------------------------ fused pass, mixed precision (MRPNP_PREC_MIXED)

@@ -261,9 +261,10 @@ __device__ __forceinline__ int mask_and_compact(const KParams& kp, int obj, floa
 // row.  Out of line: it is the whole body of pnp_lm_kernel below AND the routine the MRPNP_PREC_FAST kernel calls
 // (MIXED = false, exact fp64 decisions) for the few objects it hands back (a point near a clip bound, an accept /
 // function-tolerance decision within rounding of its threshold).  `scratch`: 40 doubles of the warp's header.
-template <bool MIXED, int WMODE, int LAYOUT>
+// TEAM: warp 0 of a CTA whose other warps sit in team_worker(): the fp64 evaluations go through team_eval_fp64.
+template <bool MIXED, int WMODE, int LAYOUT, bool TEAM = false>
 __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, float* slot, uint64_t* bar, uint32_t parity,
-                                                    double* scratch, int lane) {
+                                                    double* scratch, int lane, RedoTeam* team = nullptr) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     const int P = kp.n_pts;
     const float* s3 = slot;
@@ -390,7 +391,8 @@ __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, 
                 scratch[kScrPt + lane] = v;
             }
             __syncwarp();
-            eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 0, false, scratch);
+            if (TEAM) team_eval_fp64<WMODE, LAYOUT>(kp, team, obj, slot, n, lane, 0, scratch);
+            else eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 0, false, scratch);
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = scratch[kScrSums + i];
             clip_p = scratch[kScrClip] != 0.0;
@@ -536,7 +538,8 @@ __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, 
                 scratch[kScrPt + lane] = v;
             }
             __syncwarp();
-            eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 1, !compacted, scratch);
+            if (TEAM && compacted) team_eval_fp64<WMODE, LAYOUT>(kp, team, obj, slot, n, lane, 1, scratch);
+            else eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 1, !compacted, scratch);
 #pragma unroll
             for (int i = 0; i < 10; ++i) H[i] = scratch[kScrSums + 5 + i];
             __syncwarp();

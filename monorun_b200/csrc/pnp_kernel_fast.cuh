@@ -56,7 +56,7 @@ constexpr int kFastBufA = 4, kFastBufB = 32, kFastScaleDiag = 56, kFastArgStash 
 constexpr int kFastScratch64 = 128;   // byte offset
 constexpr int kNoPending = -1;
 // work counters of one launch (ints, all zero between launches; the last CTA re-arms them)
-enum { kCntFresh = 0, kCntCtasDone = 1, kCntRedoCount = 2, kCntRedoTaken = 3 };
+enum { kCntFresh = 0, kCntCtasDone = 1, kCntRedoCount = 2, kCntRedoTaken = 3, kCntCtasInRedo = 4 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
@@ -122,19 +122,31 @@ __device__ __forceinline__ void issue_bulk_copies(const KParams& kp, int obj, fl
     }
 }
 
-// Work distribution.  Every warp draws fresh objects from one counter (kCntFresh) and, before each of them, looks at
-// the list of objects some warp handed back (kCntRedoCount / kCntRedoTaken over kp.redo_list; taken first, so that the
-// slow exact solves start early instead of forming the tail of the launch).  A warp that hands an object back looks
-// at the list right afterwards, so it finds its own entry unless another warp took it first: no entry is ever
-// stranded, and a warp that finds neither kind of work may leave.  A fresh index drawn while a handed-back object was
-// taken instead is kept in `pending`.  (Measured and dropped: drawing the ticket one object ahead, prefetching the next
-// object's slabs into L2 and its initial pose into registers -- 5 to 10 % slower, profiles/r02_ab_variants.txt.)
-// Returns the object, -1 (nothing left) or -2 (lost a race for a list entry: look again); is_redo tells which kind.
-// For a fresh object on the TMA path the bulk copies are started.
+// Work distribution.  Every warp draws fresh objects from one counter (kCntFresh).  An object the fp32 path must not
+// decide is appended to a list in global memory (hand_back: kCntRedoCount over kp.redo_list) and the warp goes on with
+// the next fresh object; the list is worked off in the redo phase at the end of the kernel, by whole CTAs (eight warps to
+// one fp64 evaluation), on SMs that would otherwise idle through the launch's tail.  (Measured and dropped: the warp that
+// hands an object back solves it itself right away -- MRPNP_EXP_INLINE_REDO keeps that variant: a second, fp64 solve by
+// one warp that starts when the first ends put +50 us on the launch, profiles/r02_band_sweep.txt; drawing the ticket one
+// object ahead and prefetching the next object's slabs into L2 -- 5 to 10 % slower, profiles/r02_ab_variants.txt.)
+// Returns the object or -1 (nothing left); for a fresh object on the TMA path the bulk copies are started.
 template <int WC>
 __device__ __forceinline__ int fetch_job(const KParams& kp, float* slot, int P, uint64_t* bar, int lane, int& pending,
                                          bool& is_redo) {
     int obj = -1, redo = 0;
+#ifndef MRPNP_EXP_INLINE_REDO
+    // handed-back objects are solved by whole CTAs after the fresh objects (redo phase at the end of the kernel)
+    if (lane == 0) {
+        const int fresh = atomicAdd(kp.counters + kCntFresh, 1);
+        if (fresh < kp.n_obj) {
+            obj = fresh;
+            if (kp.use_tma) issue_bulk_copies<WC>(kp, obj, slot, P, bar);
+        }
+    }
+    obj = __shfl_sync(kFull, obj, 0);
+    is_redo = false;
+    return obj;
+#endif
     if (lane == 0) {
         int* c = kp.counters;
         int fresh = pending;
@@ -632,6 +644,8 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
         int term = kNoConvergence, iteration = 0, cost_evals = 0, num_invalid = 0;
         float radius = (float)kInitialRadius, decrease_factor = 2.f, x_norm = 0.f, model_change = 1.f;
         bool reuse_diagonal = false, step_ok = true, first = true, redo = false;
+        float prev_step_norm2 = 0.f;   // |step|^2 of the last accepted step (adaptive decision band)
+        int redo_why = 0;
         PassArgs pa;
         store_consts(hdr + kFastConsts, make_camn(camf), make_clip_window(camf), lane);
         pa.consts = hdr + kFastConsts;
@@ -654,7 +668,7 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
             jfin = run_pass<WMODE>(slot, P, n_main, n, lane, pa, from_observations, cand, arg_stash, hdr + kFastReduce, flagged);
             if (cost_evals == 0) { ext.xm = cand[16]; ext.ym = cand[17]; ext.zm = cand[18]; }
             TR_MARK(from_observations ? 3 : 4)
-            if (flagged) { redo = true; break; }
+            if (flagged) { redo = true; redo_why = 1; break; }
             ++cost_evals;
             const float c_term = cand[14];  // first two evaluations: sum |r|^2; afterwards: its change
             const bool cfinite = fabsf(c_term) < kFltMax;
@@ -682,13 +696,22 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
                 } else {
                     cost_change = -0.5f * c_term;
                     err = fmaf(kp.band_rel, fabsf(cost_change), kp.band_mix * fast_sqrtf(fabsf(model_change) * cost));
+                    // Objects that converge slowly (many evaluations, consecutive steps of similar size): the deviation
+                    // of this trajectory from the oracle's, ~1e-6 of the previous step, is small against the current
+                    // step, so the band may shrink in proportion to |previous step| / |this step| -- and these are the
+                    // objects that are expensive to solve twice.
+                    if (kp.band_ratio > 0.f && cost_evals >= kp.band_ratio_from) {
+                        const float r = kp.band_ratio * fast_sqrtf(prev_step_norm2 * fast_rcp(fmaxf(step_norm2, 1e-30f)));
+                        err *= fminf(1.f, fmaxf(kp.band_rel_min, r) * fast_rcp(kp.band_rel));
+                    }
                 }
                 const float ftol_cost = (float)kFunctionTol * cost;
                 // a decision within the band of its threshold is not ours to take: the exact routine solves the object.
                 // (The accept test only matters when the function-tolerance test has not ended the solve.)
-                if (fabsf(fabsf(cost_change) - ftol_cost) <= err) { redo = true; break; }
+                if (fabsf(fabsf(cost_change) - ftol_cost) <= err) { redo = true; redo_why = from_observations ? 2 : 3; break; }
                 if (fabsf(cost_change) > ftol_cost && fabsf(cost_change - (float)kMinRelDecrease * model_change) <= err) {
                     redo = true;
+                    redo_why = 4;
                     break;
                 }
                 bool stop_after = false;
@@ -701,6 +724,7 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
                 if (stop_after || rho > (float)kMinRelDecrease) {  // HandleSuccessfulStep
                     if (!jfinite) { term = kFailure; break; }
                     accept = true;
+                    prev_step_norm2 = step_norm2;
                     cost = from_observations ? 0.5f * c_term : cost - cost_change;
                     const float q = 2.f * rho - 1.f;
                     radius = fminf((float)kMaxRadius, radius * fast_rcp(fmaxf(1.f / 3.f, 1.f - q * q * q)));
@@ -823,7 +847,12 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
         // before finishing this one
         __syncwarp();
         const int this_obj = obj;
-        if (redo) hand_back(kp, this_obj, lane);
+        if (redo) {
+            hand_back(kp, this_obj, lane);
+            // diagnostic: why (1 clip proximity, 2 first-step band, 3 function-tolerance band, 4 accept band) and after
+            // how many evaluations
+            if (kp.hand_back_log && lane == 0) kp.hand_back_log[this_obj] = redo_why | (cost_evals << 8);
+        }
         bool next_redo;
         int next_obj;
         do { next_obj = fetch_job<WC>(kp, slot, P, bar, lane, pending, next_redo); } while (next_obj == -2);
@@ -849,6 +878,56 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
         is_redo = next_redo;
     }
 
+#if !defined(MRPNP_EXP_INLINE_REDO) && !defined(MRPNP_NO_EXACT)
+    // ---------------- redo phase: the CTA's warps solve handed-back objects TOGETHER ----------------
+    // Every warp of this CTA is out of fresh objects.  Most CTAs get here long before the launch ends (its tail is a few
+    // long objects on a few SMs), so the handed-back objects -- appended to the list by whichever warp met them -- are
+    // solved here by otherwise idle SMs, eight warps to an fp64 evaluation (RedoTeam, pnp_device.cuh).  A CTA leaves
+    // when the list is empty AND every CTA has entered this phase (nobody can append any more).
+    __shared__ RedoTeam team;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(kp.counters + kCntCtasInRedo, 1);
+    }
+    while (true) {
+        if (threadIdx.x == 0) {
+            int got = -1;
+            const unsigned long long t0 = global_timer_ns();
+            while (true) {
+                const int all_in = ld_acquire(kp.counters + kCntCtasInRedo) == (int)gridDim.x;
+                const int rt = ld_relaxed(kp.counters + kCntRedoTaken), rc = ld_relaxed(kp.counters + kCntRedoCount);
+                if (rt < rc) {
+                    if (atomicCAS(kp.counters + kCntRedoTaken, rt, rt + 1) != rt) continue;
+                    volatile int* e = kp.redo_list + rt;   // entries are object + 1; 0 = reserved but not yet written
+                    int v;
+                    while ((v = *e) == 0) {}
+                    *e = 0;                                // the reader re-arms the entry
+                    got = v - 1;
+                    break;
+                }
+                if (all_in) break;                         // read BEFORE the counts: no append can follow
+                __nanosleep(256);
+                if (global_timer_ns() - t0 > 2000000000ull) break;   // never hang the device
+            }
+            team.obj = got;
+        }
+        __syncthreads();
+        const int robj = team.obj;
+        if (robj < 0) break;
+        if (warp == 0) {
+            parity = solve_object_exact<false, WMODE, MRPNP_LAYOUT_PLANAR, true>(kp, robj, slot, bar, parity, scratch64, lane, &team);
+            __syncwarp();
+            if (lane == 0) team.cmd = kTeamDone;
+            __syncwarp();
+            team_barrier();                                // releases the workers
+        } else {
+            team_worker<WMODE, MRPNP_LAYOUT_PLANAR>(kp, &team, scratch64, warp, lane);
+        }
+        __syncthreads();
+    }
+#endif
+
     // self-resetting work counters: the last CTA to finish rearms them for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -858,7 +937,7 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
         if (done == (int)gridDim.x - 1) {
             if (kp.stats) atomicAdd(kp.stats, (unsigned long long)kp.counters[kCntRedoCount]);   // objects handed back, running total
 #pragma unroll
-            for (int i = 0; i < 4; ++i) kp.counters[i] = 0;
+            for (int i = 0; i < 5; ++i) kp.counters[i] = 0;
             __threadfence();
             raise_peer_flags(kp);
         }

@@ -100,7 +100,7 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
                   inlier_opt_only=True, cov_mode='pipeline', precision='fast', max_iterations=50,
                   adopt_candidate_on_ftol=False, return_inlier_mask=True, return_fp64=False, peers=None, row_offset=0,
                   decision_bands=None, ransac_thres=None, peer_flags=None, flag_slot=0, flag_value=0, acks=None,
-                  ack_value=0):
+                  ack_value=0, hand_back_log=None):
     """Batched uncertainty-PnP on device tensors -- direct wrapper of ``mrpnp_solve``.
 
     layout 'planar':      coords_3d [N,3,*], coords_2d [N,2,*], weights [N,2|3,*]   (head level)
@@ -155,7 +155,13 @@ def solve_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose=N
             raise ValueError('ransac_thres must be a device tensor with one threshold per object')
         p.ransac_thres = _ptr(thr)
     if decision_bands is not None:   # (band_first, band_rel, band_mix) of mrpnp_params; the defaults are the product's
-        p.band_first, p.band_rel, p.band_mix = (float(v) for v in decision_bands)
+        p.band_first, p.band_rel, p.band_mix = (float(v) for v in decision_bands[:3])
+        if len(decision_bands) > 3:   # (…, band_ratio, band_rel_min): the adaptive relative band
+            p.band_ratio, p.band_rel_min = float(decision_bands[3]), float(decision_bands[4])
+            p.band_ratio_from = int(decision_bands[5]) if len(decision_bands) > 5 else 0
+    if hand_back_log is not None:   # int32 [N] device tensor: reason | evaluations << 8 of handed-back objects
+        assert hand_back_log.dtype == torch.int32 and hand_back_log.numel() == n and hand_back_log.device == dev
+        p.hand_back_log = _native.ffi.cast('int32_t*', hand_back_log.data_ptr())
     if peers:
         if len(peers) > C['MRPNP_MAX_PEERS']:
             raise ValueError('at most %d peers' % C['MRPNP_MAX_PEERS'])

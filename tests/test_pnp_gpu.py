@@ -702,3 +702,36 @@ def test_fused_entry_decodes_dimensions_like_the_dim_coder(cuda_lib, precision):
     e = torch.zeros((0, 3), device='cuda')
     out = pnp.solve_dense(maps[0][:0], maps[1][:0], maps[2][:0], e, e, *tail, dim_coder=coder, dim_labels=lab[:0], **kw)
     assert out[2].shape == (0, 3) and out[3].shape == (0, 3)
+
+
+@pytest.mark.parametrize('weights,n', [('full', 300), ('diag', 2500)])
+def test_redo_phase_solves_every_handed_back_object_like_the_fp64_kernel(cuda_lib, weights, n):
+    """The redo phase of the fast kernel (whole CTAs solving handed-back objects together, each fp64 evaluation split
+    over the warps by rows): with a band that catches EVERY later decision all objects take that route, and the rows
+    must be those of the fp64 kernel (same decisions; sums added in a different order: 1e-9).  n = 300 leaves most CTAs
+    with a partly filled team of fresh work, n = 2500 makes every CTA loop over several handed-back objects.  Also the
+    diagnostic log (reason | evaluations << 8)."""
+    from monorun_b200 import pnp
+    cfg = 3 if weights == 'full' else 2
+    b = synth.make_batch(n, config=cfg, weights=weights, mode='S1', classes=(0, 1, 2) if cfg == 3 else (0,))
+    full = weights == 'full'
+    ih, iw = b['img_shape']
+    rng = torch.tensor([[-200., iw + 200., -200., ih + 200.]], device='cuda')
+    args = (dev(b['coords_3d']), dev(b['coords_2d']), dev(b['w_full'] if full else b['logstd']), dev(b['cam_mat'][None]), rng)
+    kw = dict(init_pose=dev(b['init_pose']), layout='planar', weight_mode='full' if full else 'logstd', return_fp64=True)
+    _, m64, ref = pnp.solve_batched(*args, precision='fp64', **kw)
+    log = torch.zeros(n, dtype=torch.int32, device='cuda')
+    hb0 = pnp.handed_back_count()
+    res, m, r = pnp.solve_batched(*args, precision='fast', decision_bands=(0.0, 1e9, 0.0), hand_back_log=log, **kw)
+    handed = pnp.handed_back_count() - hb0
+    log = log.cpu().numpy()
+    assert handed == int((log != 0).sum()) and handed > 0.95 * n      # a few objects end on a tolerance test that needs no decision
+    assert set(np.unique(log & 255)) <= {0, 3, 4} and ((log >> 8)[log != 0] >= 2).all()
+    ref, r = ref.cpu().numpy(), r.cpu().numpy()
+    sel = log != 0
+    assert np.array_equal(r[sel, 6], ref[sel, 6]) and np.array_equal(r[sel, 7], ref[sel, 7])   # evaluations, termination
+    np.testing.assert_allclose(r[sel, :6], ref[sel, :6], rtol=1e-9, atol=1e-12)
+    assert torch.equal(m, m64) and (res[:, 20] == 1).all()
+    # and twice the same launch gives bitwise the same rows (the split of an evaluation over the warps is fixed)
+    res2, _, r2 = pnp.solve_batched(*args, precision='fast', decision_bands=(0.0, 1e9, 0.0), **kw)
+    assert torch.equal(res, res2) and torch.equal(r, r2) if isinstance(r, torch.Tensor) else np.array_equal(r, r2.cpu().numpy())
