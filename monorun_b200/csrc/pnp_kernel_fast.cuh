@@ -57,6 +57,7 @@ constexpr int kFastScratch64 = 128;   // byte offset
 constexpr int kNoPending = -1;
 // work counters of one launch (ints, all zero between launches; the last CTA re-arms them)
 enum { kCntFresh = 0, kCntCtasDone = 1, kCntRedoCount = 2, kCntRedoTaken = 3, kCntCtasInRedo = 4 };
+constexpr int kRedoKeepers = 24;   // CTAs that stay until every CTA has entered the redo phase
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
@@ -884,18 +885,22 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
     // long objects on a few SMs), so the handed-back objects -- appended to the list by whichever warp met them -- are
     // solved here by otherwise idle SMs, eight warps to an fp64 evaluation (RedoTeam, pnp_device.cuh).  A CTA leaves
     // when the list is empty AND every CTA has entered this phase (nobody can append any more).
+    // Only the last kRedoKeepers CTAs to get here wait for that; an earlier one leaves as soon as it finds the list empty
+    // -- later hand-backs are taken by the keepers -- so that its SM is free for the next launch on another stream.
     __shared__ RedoTeam team;
+    __shared__ int keeper;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(kp.counters + kCntCtasInRedo, 1);
+        const int order = atomicAdd(kp.counters + kCntCtasInRedo, 1);
+        keeper = order >= (int)gridDim.x - kRedoKeepers;
     }
     while (true) {
         if (threadIdx.x == 0) {
             int got = -1;
             const unsigned long long t0 = global_timer_ns();
             while (true) {
-                const int all_in = ld_acquire(kp.counters + kCntCtasInRedo) == (int)gridDim.x;
+                const int all_in = !keeper || ld_acquire(kp.counters + kCntCtasInRedo) == (int)gridDim.x;
                 const int rt = ld_relaxed(kp.counters + kCntRedoTaken), rc = ld_relaxed(kp.counters + kCntRedoCount);
                 if (rt < rc) {
                     if (atomicCAS(kp.counters + kCntRedoTaken, rt, rt + 1) != rt) continue;
