@@ -371,7 +371,10 @@ class MLPScoreHead(nn.Module):
         MonoRUnRoIHead.simple_test (monorun_roi_head.py:530-556) with two launches around the GEMMs."""
         from . import pnp
         norm = self.pose_norm if self.use_pose_norm else None
-        if native_mlp and self.num_pose_fcs == 1 and self.num_fused_fcs == 1 and self.fusion_type == 'add':
+        # (streams the fused layer's weights once per 8 objects: the right shape for an image's <= 100 RoIs; from a few
+        # hundred objects on the library GEMMs below are faster -- 1024 objects: 0.16 ms against 0.09 ms)
+        if native_mlp and rows.shape[0] <= self.native_mlp_max_objects and self.num_pose_fcs == 1 \
+                and self.num_fused_fcs == 1 and self.fusion_type == 'add':
             # every reference config: the whole stage is ONE launch (mrpnp_score_stage)
             w = self._native_weights()
             scores, bbox_3d, cov_calib, _ = pnp.score_stage(
@@ -384,6 +387,8 @@ class MLPScoreHead(nn.Module):
         logits = self._mlp(feat, reg_fc_out)
         scores, bbox_3d = pnp.finish_scores(logits, rows, dimensions, det_scores, self.pre_sigmoid)
         return scores, bbox_3d, cov_calib.view(-1, 4, 4)
+
+    native_mlp_max_objects = 384
 
     def _native_weights(self):
         """fp32 contiguous weights in the layout of ``mrpnp_score_stage`` (fused layer transposed); rebuilt when a

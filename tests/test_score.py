@@ -122,7 +122,7 @@ def test_score_head_rows_path_matches_reference_sequence(cuda_lib):
         head.score_head.pose_norm.running_mean.normal_(0, 1.0)
         head.score_head.pose_norm.running_var.uniform_(0.5, 2.0)
         head.score_head.fc_out.weight.normal_(0, 0.05)
-    n = 513
+    n = 353   # 44 tiles of 8 objects + 1; above MLPScoreHead.native_mlp_max_objects the GEMM path is taken
     rows_np, dims_np = _random_rows(n, seed=5)
     rows, dims = torch.from_numpy(rows_np).cuda(), torch.from_numpy(dims_np).cuda()
     reg = torch.randn(n, 1024, device='cuda')

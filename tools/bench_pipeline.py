@@ -76,8 +76,8 @@ for _ in range(a.steps):
 acc /= a.steps
 print(json.dumps({'rois': n, 'images': a.images,
                   'ms': {'dense head (10 launches, random-init weights)': acc[0],
-                         'fused head->PnP solve incl. on-device initialiser (2 launches, synthetic head output)': acc[1],
-                         'score stage (2 launches + 3 library GEMMs)': acc[2], '3-D NMS (1 launch)': acc[3], 'total': acc.sum()},
+                         'fused head->PnP solve incl. on-device initialiser (1 launch, synthetic head output)': acc[1],
+                         'score stage (1024 RoIs: 2 launches + 3 library GEMMs; <= 384 RoIs: 1 launch)': acc[2], '3-D NMS (1 launch)': acc[3], 'total': acc.sum()},
                   'rois_per_s': n / acc.sum() * 1e3, 'valid_poses': float(ret_val.float().mean().item()),
                   'kept_after_nms': int(keep.sum().item())}))
 
