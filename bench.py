@@ -572,7 +572,7 @@ def main():
                     'path': 'mrpnp_solve_host: pinned host tensors -> chunked H2D overlapped with the kernel -> D2H of result rows'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': ncu_traffic(args.workload), 'peak_source': peak_src,
+                         'traffic': (ncu_traffic(args.workload) * n_local / OBJ_PER_GPU) if ncu_traffic(args.workload) else None, 'peak_source': peak_src,
                          'kernel': 'mrpnp::pnp_lm_fast_kernel' if args.precision == 'fast' else 'mrpnp::pnp_lm_kernel',
                          'kernel_ms': kernel_ms,
                          'algorithmic_bytes_per_object': ALG_BYTES[args.workload], 'objects_per_launch': n_local},

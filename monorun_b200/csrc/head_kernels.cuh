@@ -482,77 +482,51 @@ __global__ void __launch_bounds__(256) carafe_kernel(const __nv_bfloat16* __rest
         reinterpret_cast<uint4*>(o + ((size_t)y * wop + x) * C)[lane] = zero;
     }
 
-    // Two horizontally adjacent low-res pixels per warp iteration: their 5 x 5 neighbourhoods overlap in 20 of 25 rows, so
-    // the pair needs 30 row loads instead of 50, and two independent accumulation chains hide the load latency.
-    const int wpairs = (w + 1) >> 1;
-    for (int pp = warp; pp < h * wpairs; pp += nwarps) {
-        const int y = pp / wpairs, x0 = 2 * (pp - y * wpairs);
-        const bool second = x0 + 1 < w;
-        // lane k < 25 holds the weights of tap k for the four sub-pixels of each of the two pixels
-        float wgt[2][SS];
+    for (int pix = warp; pix < h * w; pix += nwarps) {
+        const int y = pix / w, x = pix - y * w;
+        const float* lrow = lg + ((size_t)(y + 1) * wp + (x + 1)) * ld_logits;
+        // lane k < 25 holds the weights of tap k for the four sub-pixels
+        float wgt[SS];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const float* lrow = lg + ((size_t)(y + 1) * wp + (x0 + (q && second ? 1 : 0) + 1)) * ld_logits;
+        for (int s = 0; s < SS; ++s) {
+            const float v = lane < KK ? __ldg(lrow + lane * SS + s) : -INFINITY;
+            float m = v;
 #pragma unroll
-            for (int s = 0; s < SS; ++s) {
-                const float v = lane < KK ? __ldg(lrow + lane * SS + s) : -INFINITY;
-                float m = v;
+            for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+            const float e = lane < KK ? __expf(v - m) : 0.f;
+            float t = e;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-                const float e = lane < KK ? __expf(v - m) : 0.f;
-                float t = e;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-                wgt[q][s] = e / t;
-            }
+            for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            wgt[s] = e / t;
         }
         // packed fp32: one FFMA2 (weight as the broadcast operand) per channel pair and sub-pixel
-        float2 acc[2][SS][4];
+        float2 acc[SS][4];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int s = 0; s < SS; ++s)
 #pragma unroll
-            for (int s = 0; s < SS; ++s)
+            for (int j = 0; j < 4; ++j) acc[s][j] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[q][s][j] = make_float2(0.f, 0.f);
+        for (int k = 0; k < KK; ++k) {
+            const int yy = y + k / K - K / 2, xx = x + k % K - K / 2;
+            float ws[SS];
 #pragma unroll
-        for (int ky = 0; ky < K; ++ky) {
-            const int yy = y + ky - K / 2;
+            for (int s = 0; s < SS; ++s) ws[s] = __shfl_sync(0xffffffffu, wgt[s], k);
+            if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;   // warp-uniform
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(f + ((size_t)(yy + 1) * wp + (xx + 1)) * C) + lane);
+            const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-            for (int cx = 0; cx <= K; ++cx) {            // column x0 - K/2 + cx: tap cx of the first pixel, tap cx - 1 of the second
-                const int xx = x0 + cx - K / 2;
-                float ws[2][SS];
+            for (int j = 0; j < 4; ++j) {
+                const float2 v = make_float2(__uint_as_float(u[j] << 16), __uint_as_float(u[j] & 0xffff0000u));
 #pragma unroll
-                for (int s = 0; s < SS; ++s) {
-                    ws[0][s] = cx < K ? __shfl_sync(0xffffffffu, wgt[0][s], ky * K + (cx < K ? cx : 0)) : 0.f;
-                    ws[1][s] = cx > 0 ? __shfl_sync(0xffffffffu, wgt[1][s], ky * K + (cx > 0 ? cx - 1 : 0)) : 0.f;
-                }
-                if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;   // warp-uniform
-                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(f + ((size_t)(yy + 1) * wp + (xx + 1)) * C) + lane);
-                const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 v = make_float2(__uint_as_float(u[j] << 16), __uint_as_float(u[j] & 0xffff0000u));
-                    if (cx < K) {
-#pragma unroll
-                        for (int s = 0; s < SS; ++s) acc[0][s][j] = __ffma2_rn(make_float2(ws[0][s], ws[0][s]), v, acc[0][s][j]);
-                    }
-                    if (cx > 0) {
-#pragma unroll
-                        for (int s = 0; s < SS; ++s) acc[1][s][j] = __ffma2_rn(make_float2(ws[1][s], ws[1][s]), v, acc[1][s][j]);
-                    }
-                }
+                for (int s = 0; s < SS; ++s) acc[s][j] = __ffma2_rn(make_float2(ws[s], ws[s]), v, acc[s][j]);
             }
         }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (q && !second) break;
-#pragma unroll
-            for (int s = 0; s < SS; ++s) {
-                const int oy = S * y + s / S, ox = S * (x0 + q) + s % S;
-                const uint4 pk = make_uint4(pack_bf16(acc[q][s][0].x, acc[q][s][0].y), pack_bf16(acc[q][s][1].x, acc[q][s][1].y),
-                                            pack_bf16(acc[q][s][2].x, acc[q][s][2].y), pack_bf16(acc[q][s][3].x, acc[q][s][3].y));
-                reinterpret_cast<uint4*>(o + ((size_t)(oy + 1) * wop + (ox + 1)) * C)[lane] = pk;
-            }
+        for (int s = 0; s < SS; ++s) {
+            const int oy = S * y + s / S, ox = S * x + s % S;
+            const uint4 pk = make_uint4(pack_bf16(acc[s][0].x, acc[s][0].y), pack_bf16(acc[s][1].x, acc[s][1].y),
+                                        pack_bf16(acc[s][2].x, acc[s][2].y), pack_bf16(acc[s][3].x, acc[s][3].y));
+            reinterpret_cast<uint4*>(o + ((size_t)(oy + 1) * wop + (ox + 1)) * C)[lane] = pk;
         }
     }
 }

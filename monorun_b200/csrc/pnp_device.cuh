@@ -494,28 +494,34 @@ __device__ __noinline__ void eval_pass_fp64(const KParams& kp, int obj, const fl
 struct RedoTeam {
     double part[kMaxWarpsPerCta][18];   // per warp: 16 totals, [16] clip flag
     double pt[4];
+    uint64_t bar;                       // mbarrier, one arrival per warp
     float* slot;
     int cmd, n, clipsem, obj;
 };
 enum { kTeamEval = 0, kTeamDone = 1 };
-__device__ __forceinline__ void team_barrier() {
-    asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory");
+// All warps of the CTA meet here (leader and workers from different code): an mbarrier with one arrival per warp;
+// `phase` is each thread's own count of the rounds (parity).
+__device__ __forceinline__ void team_barrier(RedoTeam* team, uint32_t& phase, int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(&team->bar)) : "memory");
+    }
+    mbar_wait(&team->bar, phase);
+    phase ^= 1u;
 }
 
 // Leader side of one evaluation (same contract as eval_pass_fp64 with use_bits = false).
 template <int WMODE, int LAYOUT>
-__device__ __forceinline__ void team_eval_fp64(const KParams& kp, RedoTeam* team, int obj, float* slot, int n, int lane,
-                                               int clipsem, double* scratch) {
+__device__ __forceinline__ void team_eval_fp64(const KParams& kp, RedoTeam* team, uint32_t& phase, int obj, float* slot, int n,
+                                               int lane, int clipsem, double* scratch) {
     const int nw = blockDim.x >> 5;
     if (lane < 4) team->pt[lane] = scratch[kScrPt + lane];
     if (lane == 0) { team->cmd = kTeamEval; team->n = n; team->clipsem = clipsem; team->obj = obj; team->slot = slot; }
-    __syncwarp();
-    team_barrier();                                                       // workers start
+    team_barrier(team, phase, lane);                                      // workers start
     eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, 0u, clipsem, false, scratch, 0, nw);
     if (lane < 16) team->part[0][lane] = scratch[kScrSums + lane];
     if (lane == 16) team->part[0][16] = scratch[kScrClip];
-    __syncwarp();
-    team_barrier();                                                       // all partial totals are written
+    team_barrier(team, phase, lane);                                      // all partial totals are written
     if (lane < 17) {
         double t = team->part[0][lane];
         for (int w = 1; w < nw; ++w) t += team->part[w][lane];
@@ -526,19 +532,20 @@ __device__ __forceinline__ void team_eval_fp64(const KParams& kp, RedoTeam* team
 
 // Worker side: warps 1.. of the CTA while warp 0 solves an object; returns when the leader posts kTeamDone.
 template <int WMODE, int LAYOUT>
-__device__ __noinline__ void team_worker(const KParams& kp, RedoTeam* team, double* scratch, int warp, int lane) {
+__device__ __noinline__ uint32_t team_worker(const KParams& kp, RedoTeam* team, uint32_t phase, double* scratch, int warp,
+                                             int lane) {
     const int nw = blockDim.x >> 5;
     while (true) {
-        team_barrier();
+        team_barrier(team, phase, lane);
         if (team->cmd == kTeamDone) break;
         if (lane < 4) scratch[kScrPt + lane] = team->pt[lane];
         __syncwarp();
         eval_pass_fp64<WMODE, LAYOUT>(kp, team->obj, team->slot, team->n, lane, 0u, team->clipsem, false, scratch, warp, nw);
         if (lane < 16) team->part[warp][lane] = scratch[kScrSums + lane];
         if (lane == 16) team->part[warp][16] = scratch[kScrClip];
-        __syncwarp();
-        team_barrier();
+        team_barrier(team, phase, lane);
     }
+    return phase;
 }
 
 // ------------------------------------------------------------------ fused pass, mixed precision (MRPNP_PREC_MIXED)

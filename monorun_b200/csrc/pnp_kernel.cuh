@@ -264,7 +264,8 @@ __device__ __forceinline__ int mask_and_compact(const KParams& kp, int obj, floa
 // TEAM: warp 0 of a CTA whose other warps sit in team_worker(): the fp64 evaluations go through team_eval_fp64.
 template <bool MIXED, int WMODE, int LAYOUT, bool TEAM = false>
 __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, float* slot, uint64_t* bar, uint32_t parity,
-                                                    double* scratch, int lane, RedoTeam* team = nullptr) {
+                                                    double* scratch, int lane, RedoTeam* team = nullptr,
+                                                    uint32_t* team_phase = nullptr) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
     const int P = kp.n_pts;
     const float* s3 = slot;
@@ -274,6 +275,7 @@ __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, 
     const Camera<float> camf = load_camera<float>(kp, obj);
     Camera<double> cam;
     cam.fx = camf.fx; cam.fy = camf.fy; cam.cx = camf.cx; cam.cy = camf.cy;  // only these four are used inline
+    uint32_t tphase = TEAM ? *team_phase : 0u;   // round count of the team barrier, in a register while this routine runs
 
     // ---------------- stage + istd + inlier mask + compaction ----------------
     uint32_t bits = 0u;
@@ -391,7 +393,7 @@ __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, 
                 scratch[kScrPt + lane] = v;
             }
             __syncwarp();
-            if (TEAM) team_eval_fp64<WMODE, LAYOUT>(kp, team, obj, slot, n, lane, 0, scratch);
+            if (TEAM) team_eval_fp64<WMODE, LAYOUT>(kp, team, tphase, obj, slot, n, lane, 0, scratch);
             else eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 0, false, scratch);
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = scratch[kScrSums + i];
@@ -538,7 +540,7 @@ __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, 
                 scratch[kScrPt + lane] = v;
             }
             __syncwarp();
-            if (TEAM && compacted) team_eval_fp64<WMODE, LAYOUT>(kp, team, obj, slot, n, lane, 1, scratch);
+            if (TEAM && compacted) team_eval_fp64<WMODE, LAYOUT>(kp, team, tphase, obj, slot, n, lane, 1, scratch);
             else eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, bits, 1, !compacted, scratch);
 #pragma unroll
             for (int i = 0; i < 10; ++i) H[i] = scratch[kScrSums + 5 + i];
@@ -573,6 +575,11 @@ __device__ __noinline__ uint32_t solve_object_exact(const KParams& kp, int obj, 
             d = (lane == 7) ? (double)term : d;
             if (lane < 8) kp.result64[(size_t)obj * 8 + lane] = d;
         }
+    }
+    if (TEAM) {
+        __syncwarp();
+        if (lane == 0) *team_phase = tphase;
+        __syncwarp();
     }
     return parity;   // mbarrier phase after this object's copies (by value: no local of the caller has its address taken)
 }

@@ -310,9 +310,11 @@ __device__ __forceinline__ int fast_mask_and_compact(const KParams& kp, int obj,
         __syncwarp();  // the reads of these rows (all lanes) happen before any lane's compacted writes
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            float* d = slot + (inl[u] ? dst[u] : base);
+            if (inl[u]) {   // predicated stores
+                float* d = slot + dst[u];
 #pragma unroll
-            for (int c = 0; c < NPL; ++c) d[c * P] = val[u][c];
+                for (int c = 0; c < NPL; ++c) d[c * P] = val[u][c];
+            }
         }
         // (no barrier after the stores: they land at or below this batch's rows, never ahead of the read front)
     }
@@ -889,6 +891,13 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
     // -- later hand-backs are taken by the keepers -- so that its SM is free for the next launch on another stream.
     __shared__ RedoTeam team;
     __shared__ int keeper;
+    __shared__ uint32_t leader_phase;
+    uint32_t team_phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&team.bar, (uint32_t)nwarps);
+        fence_mbar_init();
+        leader_phase = 0;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -921,13 +930,18 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
         const int robj = team.obj;
         if (robj < 0) break;
         if (warp == 0) {
-            parity = solve_object_exact<false, WMODE, MRPNP_LAYOUT_PLANAR, true>(kp, robj, slot, bar, parity, scratch64, lane, &team);
+            // the leader's round count lives in shared memory across the call (a local passed by address to the
+            // out-of-line routine would live in local memory)
+            parity = solve_object_exact<false, WMODE, MRPNP_LAYOUT_PLANAR, true>(kp, robj, slot, bar, parity, scratch64, lane, &team,
+                                                                                 &leader_phase);
             __syncwarp();
+            team_phase = leader_phase;
             if (lane == 0) team.cmd = kTeamDone;
+            team_barrier(&team, team_phase, lane);         // releases the workers
             __syncwarp();
-            team_barrier();                                // releases the workers
+            if (lane == 0) leader_phase = team_phase;
         } else {
-            team_worker<WMODE, MRPNP_LAYOUT_PLANAR>(kp, &team, scratch64, warp, lane);
+            team_phase = team_worker<WMODE, MRPNP_LAYOUT_PLANAR>(kp, &team, team_phase, scratch64, warp, lane);
         }
         __syncthreads();
     }

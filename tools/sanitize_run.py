@@ -31,3 +31,28 @@ res, _, _ = pnp.solve_batched(t(op['coords_3d']), t(op['coords_2d']), t(op['coor
                               layout='interleaved', weight_mode='istd', precision='fast')
 torch.cuda.synchronize()
 print('clip case valid', res[:, 20].mean().item())
+# round 2: the redo phase (whole CTAs solving handed-back objects, evaluations split over the warps): every object handed
+# back, few and many objects per CTA; the consensus prune; the score stage; the flag kernels
+for n_obj in (5, 300):
+    b = synth.make_batch(n_obj, config=3, weights='full', mode='S1')
+    ih, iw = b['img_shape']
+    uvr = torch.tensor([[-200., iw + 200., -200., ih + 200.]], device='cuda')
+    log = torch.zeros(n_obj, dtype=torch.int32, device='cuda')
+    res, _, _ = pnp.solve_batched(t(b['coords_3d']), t(b['coords_2d']), t(b['w_full']), t(b['cam_mat'][None]), uvr, init_pose=t(b['init_pose']),
+                                  layout='planar', weight_mode='full', precision='fast', decision_bands=(0.0, 1e9, 0.0), hand_back_log=log)
+    torch.cuda.synchronize()
+    print('redo phase', n_obj, 'handed', int((log != 0).sum()), 'valid', res[:, 20].mean().item())
+b = synth.make_batch(40, config=2, weights='diag', mode='S1')
+ih, iw = b['img_shape']
+uvr = torch.tensor([[-200., iw + 200., -200., ih + 200.]], device='cuda')
+thr = torch.full((40,), 6.0, device='cuda')
+res, _, _ = pnp.solve_batched(t(b['coords_3d']), t(b['coords_2d']), t(b['logstd']), t(b['cam_mat'][None]), uvr, layout='planar',
+                              weight_mode='logstd', precision='fast', ransac_thres=thr)
+rows = res.clone()
+w1, b1 = torch.randn(1024, 17, device='cuda') * 0.1, torch.randn(1024, device='cuda') * 0.1
+w2t, b2 = torch.randn(1024, 256, device='cuda') * 0.05, torch.randn(256, device='cuda') * 0.1
+w3, b3 = torch.randn(256, device='cuda') * 0.1, torch.zeros(1, device='cuda')
+sc = pnp.score_stage(rows, torch.rand(40, 3, device='cuda') + 1, torch.randn(40, 1024, device='cuda'), w1, b1, w2t, b2, w3, b3,
+                     det_scores=torch.rand(40, device='cuda'))
+torch.cuda.synchronize()
+print('consensus + score stage', res[:, 20].mean().item(), float(sc[0].mean()))
