@@ -499,16 +499,24 @@ struct RedoTeam {
     int cmd, n, clipsem, obj;
 };
 enum { kTeamEval = 0, kTeamDone = 1 };
-// All warps of the CTA meet here (leader and workers from different code): an mbarrier with one arrival per warp;
-// `phase` is each thread's own count of the rounds (parity).
-__device__ __forceinline__ void team_barrier(RedoTeam* team, uint32_t& phase, int lane) {
+// All warps of the CTA meet here, leader and workers from DIFFERENT code: a named barrier in its non-aligned form
+// (`bar.sync` = barrier.sync.aligned promises that every thread executes the same barrier instruction, which synccheck
+// rightly rejects here).  MRPNP_TEAM_MBARRIER builds the equivalent on an mbarrier with one arrival per warp -- `phase` is
+// each thread's own count of the rounds -- which racecheck does not model (it reports the hand-overs as hazards).
+__device__ __forceinline__ void cta_round(int id, uint64_t* mbar, uint32_t& phase, int lane) {
+#ifdef MRPNP_TEAM_MBARRIER
     __syncwarp();
     if (lane == 0) {
-        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(&team->bar)) : "memory");
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)) : "memory");
     }
-    mbar_wait(&team->bar, phase);
+    mbar_wait(mbar, phase);
     phase ^= 1u;
+#else
+    __syncwarp();
+    asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"((int)blockDim.x) : "memory");
+#endif
 }
+__device__ __forceinline__ void team_barrier(RedoTeam* team, uint32_t& phase, int lane) { cta_round(1, &team->bar, phase, lane); }
 
 // Leader side of one evaluation (same contract as eval_pass_fp64 with use_bits = false).
 template <int WMODE, int LAYOUT>
@@ -516,7 +524,7 @@ __device__ __forceinline__ void team_eval_fp64(const KParams& kp, RedoTeam* team
                                                int lane, int clipsem, double* scratch) {
     const int nw = blockDim.x >> 5;
     if (lane < 4) team->pt[lane] = scratch[kScrPt + lane];
-    if (lane == 0) { team->cmd = kTeamEval; team->n = n; team->clipsem = clipsem; team->obj = obj; team->slot = slot; }
+    if (lane == 0) { team->cmd = kTeamEval; team->n = n; team->clipsem = clipsem; team->slot = slot; }   // team->obj: set by the fetch
     team_barrier(team, phase, lane);                                      // workers start
     eval_pass_fp64<WMODE, LAYOUT>(kp, obj, slot, n, lane, 0u, clipsem, false, scratch, 0, nw);
     if (lane < 16) team->part[0][lane] = scratch[kScrSums + lane];

@@ -509,6 +509,51 @@ __device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, 
     return __all_sync(kFull, fabsf(scratch[lane & 15]) < 3.0e38f);
 }
 
+// ------------------------------------------------------------------ delta passes of LONG objects, split four ways
+// EXPERIMENT (MRPNP_EXP_FAST_TEAM, off): built, parity- and sanitizer-clean, and SLOWER -- 184.7 us against 159.7 us on the
+// full workload, 148.4 against 142.1 us on the diagonal one (profiles/r02_ab_variants.txt, call 31).  The fixed
+// association needs four reductions per pass also when nobody helps, which lengthens exactly the long objects that form
+// the tail, and help only comes when ALL other warps of the CTA are idle.
+// From its kTeamFromEval-th evaluation on, an object's delta pass is computed as kTeamParts separate partial passes
+// (part v = the 64-point groups v, v + 4, ...; each with its own reduction) whose totals are added in part order.  That
+// fixed association makes the result independent of WHO computes the parts: the owner alone, one after the other, or --
+// when every other warp of the CTA has run out of work -- four warps at once (FastTeam).  Long objects are what the tail
+// of a launch consists of, and in the tail their CTA has nothing else to do.
+constexpr int kTeamParts = 4;
+constexpr int kTeamFromEval = 8;
+constexpr int kTeamMinPoints = 256;
+enum { kFtPass = 0, kFtExit = 1 };
+struct FastTeam {
+    uint64_t bar;            // mbarrier, one arrival per warp
+    int idle;                // warps that have run out of fresh objects (they sit in the waiting room)
+    int cmd, owner, n_main, P;
+    float* owner_hdr;
+    float* owner_slot;
+};
+__device__ __forceinline__ void ft_barrier(FastTeam* ft, uint32_t& phase, int lane) { cta_round(2, &ft->bar, phase, lane); }
+
+// One part of a split delta pass over the owner's slot; args / consts: the owner's stash; red: the CALLER's reduction tile;
+// out[0..14]: totals (not yet sign-corrected), out[16]: clip flag.
+template <int WMODE>
+__device__ __noinline__ void team_part(const float* args, const float* consts, float* slot, int P, int n_main, int v, float* red,
+                                       float* out, int lane) {
+    const PassArgs u = fetch_args(args, consts);
+    const CamN cam = args_cam(u);
+    const ClipWindow win = args_win(u);
+    float2 a[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) a[i] = make_float2(0.f, 0.f);
+    PassFlags f = {1e30f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int g = v; 64 * g < n_main; g += kTeamParts) pass_point<WMODE, kPassDelta, float2>(slot, P, 64 * g + 2 * lane, true, u, cam, win, a, f);
+    const float tot = warp_reduce15_smem(a, red, lane);
+    __syncwarp();
+    if (lane < 15) out[lane] = tot;
+    const bool fl = __any_sync(kFull, flags_raised(f, win));
+    if (lane == 16) out[16] = fl ? 1.f : 0.f;
+    __syncwarp();
+}
+
 // Roll the speculative residual update of a rejected candidate back (out of line: rare).  args: stash_args().
 template <int WMODE>
 __device__ __noinline__ void undo_pass(float* slot, int P, int n_main, int n, int lane, const float* args, const float* consts) {

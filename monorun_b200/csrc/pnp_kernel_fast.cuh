@@ -51,7 +51,13 @@ constexpr int kFastMaxWarps = MRPNP_FAST_WARPS;
 // A sums buffer: [0..3] J^T r, [4..13] J^T J, [14] cost term, [16..18] extents; [20..23] linear-initialiser result.
 // [128..671] the 15 x 36 tile of the passes' warp reduction (warp_reduce15_smem).
 constexpr int kFastReduce = 128;
+// MRPNP_EXP_FAST_TEAM only: [672..751] four partial-total rows of a split delta pass (team_part, pnp_fast.cuh).
+constexpr int kFastParts = kFastReduce + ((kReduceTileFloats * 4 + 127) / 128) * 32;
+#ifdef MRPNP_EXP_FAST_TEAM
+constexpr int kFastHeaderBytes = 512 + ((kReduceTileFloats * 4 + 127) / 128) * 128 + 384;
+#else
 constexpr int kFastHeaderBytes = 512 + ((kReduceTileFloats * 4 + 127) / 128) * 128;
+#endif
 constexpr int kFastBufA = 4, kFastBufB = 32, kFastScaleDiag = 56, kFastArgStash = 64, kFastConsts = 96;
 constexpr int kFastScratch64 = 128;   // byte offset
 constexpr int kNoPending = -1;
@@ -489,6 +495,42 @@ __device__ __forceinline__ float fast_sqrtf(float a) {
 // ------------------------------------------------------------------ the kernel
 // PCT: points per object known at compile time (784 = 28 x 28, every reference config) or 0 = kp.n_pts (even); with a
 // compile-time P the plane offsets of the slot become immediates of the shared-memory accesses.
+// Owner side of a split delta pass (see FastTeam).  The arguments are in the warp's stash.  Returns jfinite | flagged << 1 |
+// barrier phase << 2.
+template <int WMODE>
+__device__ __noinline__ int team_delta_pass(FastTeam* ft, float* hdr, float* slot, int P, int n_main, int n, int lane, int warp,
+                                            uint32_t phase, float* cand) {
+    const int nw = blockDim.x >> 5;
+    const float* args = hdr + kFastArgStash;
+    const float* consts = hdr + kFastConsts;
+    float* parts = hdr + kFastParts;
+    float* red = hdr + kFastReduce;
+    int idle = 0;
+    if (lane == 0) idle = *reinterpret_cast<volatile int*>(&ft->idle);
+    idle = __shfl_sync(kFull, idle, 0);
+    if (nw >= kTeamParts && idle == nw - 1) {   // every other warp of the CTA sits in the waiting room: four warps, one part each
+        if (lane == 0) {
+            ft->cmd = kFtPass; ft->owner = warp; ft->n_main = n_main; ft->P = P; ft->owner_hdr = hdr; ft->owner_slot = slot;
+        }
+        ft_barrier(ft, phase, lane);
+        team_part<WMODE>(args, consts, slot, P, n_main, 0, red, parts, lane);
+        ft_barrier(ft, phase, lane);
+    } else {
+#pragma unroll 1
+        for (int v = 0; v < kTeamParts; ++v) team_part<WMODE>(args, consts, slot, P, n_main, v, red, parts + 20 * v, lane);
+    }
+    __syncwarp();
+    if (lane < 16) {
+        const float t = (parts[lane] + parts[20 + lane]) + (parts[40 + lane] + parts[60 + lane]);
+        cand[lane] = lane == 15 ? 0.f : (((kNegatedSums >> lane) & 1u) ? -t : t);
+    }
+    bool flagged = (parts[16] + parts[36]) + (parts[56] + parts[76]) != 0.f;
+    __syncwarp();
+    if (n > n_main) flagged = pass_remainder<WMODE>(slot, P, n_main, n, lane, kPassDelta, args, consts, cand) || flagged;
+    const bool jfin = __all_sync(kFull, fabsf(cand[lane & 15]) < 3.0e38f);
+    return (jfin ? 1 : 0) | (flagged ? 2 : 0) | (int)(phase << 2);
+}
+
 template <int WMODE, int PCT>
 __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(const __grid_constant__ KParams kp) {
     constexpr int WC = (WMODE == MRPNP_W_FULL) ? 3 : 2;
@@ -515,6 +557,16 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
     }
     __syncwarp();
     wait_for_acks(kp);
+#ifdef MRPNP_EXP_FAST_TEAM
+    __shared__ FastTeam ft;
+    uint32_t ft_phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&ft.bar, (uint32_t)nwarps);
+        fence_mbar_init();
+        ft.idle = 0;
+    }
+    __syncthreads();
+#endif
     uint32_t parity = 0;
     int pending = kNoPending;
     bool is_redo = false;
@@ -668,6 +720,14 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
             } else {
                 pa.check = !box_inside_window(args_win(pa), ext, pa.step.cp, pa.step.sp, pa.step.txp, pa.step.typ, pa.step.tzp);
             }
+#ifdef MRPNP_EXP_FAST_TEAM
+            if (!from_observations && cost_evals >= kTeamFromEval && n_main >= kTeamMinPoints) {
+                // a long object: the pass in four parts with a fixed association, by four warps when the CTA is otherwise idle
+                stash_args(arg_stash, pa, lane);
+                const int rc = team_delta_pass<WMODE>(&ft, hdr, slot, P, n_main, n, lane, warp, ft_phase, cand);
+                jfin = (rc & 1) != 0; flagged = (rc & 2) != 0; ft_phase = (uint32_t)(rc >> 2) & 1u;
+            } else
+#endif
             jfin = run_pass<WMODE>(slot, P, n_main, n, lane, pa, from_observations, cand, arg_stash, hdr + kFastReduce, flagged);
             if (cost_evals == 0) { ext.xm = cand[16]; ext.ym = cand[17]; ext.zm = cand[18]; }
             TR_MARK(from_observations ? 3 : 4)
@@ -880,6 +940,31 @@ __global__ void __launch_bounds__(kFastMaxWarps * 32, 1) pnp_lm_fast_kernel(cons
         obj = next_obj;
         is_redo = next_redo;
     }
+
+#ifdef MRPNP_EXP_FAST_TEAM
+    // ---------------- waiting room: out of fresh objects ----------------
+    // A warp that still works on a long object may call on the warps waiting here for the parts of its delta passes
+    // (team_delta_pass) once it is the only busy warp of the CTA; the last warp to arrive lets everybody go on.
+    {
+        int order = 0;
+        if (lane == 0) order = atomicAdd(&ft.idle, 1) + 1;
+        order = __shfl_sync(kFull, order, 0);
+        if (order == nwarps) {
+            if (lane == 0) ft.cmd = kFtExit;
+            ft_barrier(&ft, ft_phase, lane);
+        } else {
+            while (true) {
+                ft_barrier(&ft, ft_phase, lane);
+                if (ft.cmd == kFtExit) break;
+                const int r = (warp - ft.owner + nwarps) % nwarps;
+                if (r < kTeamParts)
+                    team_part<WMODE>(ft.owner_hdr + kFastArgStash, ft.owner_hdr + kFastConsts, ft.owner_slot, ft.P, ft.n_main, r,
+                                     hdr + kFastReduce, ft.owner_hdr + kFastParts + 20 * r, lane);
+                ft_barrier(&ft, ft_phase, lane);
+            }
+        }
+    }
+#endif
 
 #if !defined(MRPNP_EXP_INLINE_REDO) && !defined(MRPNP_NO_EXACT)
     // ---------------- redo phase: the CTA's warps solve handed-back objects TOGETHER ----------------
