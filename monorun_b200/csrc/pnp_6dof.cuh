@@ -164,7 +164,8 @@ struct WarpPass {
     const KParams& kp;
     Camera cam;
     const float *c3, *c2, *cw;
-    const uint32_t* mask;
+    const uint16_t* idx;   // shared memory: the indices of the object's inliers, in point order (built once per object), so that
+    int n_idx;             // every pass runs with full lanes instead of skipping ~half of them (round 2: 1.7x)
     int lane;
 
     __device__ __forceinline__ float at(const float* base, int c, int nc, int p) const {
@@ -176,11 +177,9 @@ struct WarpPass {
         Pose6 ps;
         make_pose(x, &ps);
         constexpr int wc = FULLW ? 3 : 2;
-        for (int base = 0; base < kp.n_pts; base += 32) {
-            const int p = base + lane;
-            bool on = p < kp.n_pts;
-            if (mask) on = on && ((__ldg(mask + (base >> 5)) >> lane) & 1u);
-            if (on) {
+        for (int j = lane; j < n_idx; j += 32) {
+            const int p = idx[j];
+            {
                 double w0 = at(cw, 0, wc, p), w1 = at(cw, 1, wc, p);
                 const double w2 = FULLW ? (double)at(cw, 2, wc, p) : 0.0;
                 if (!FULLW && kp.wmode == 0) { w0 = exp(-w0) / kp.std_scale; w1 = exp(-w1) / kp.std_scale; }
@@ -209,6 +208,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MR6_MIN_BLOCKS) pnp_6dof_ke
     const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * kWarpsPerCta;
     constexpr int wc = FULLW ? 3 : 2;
+    __shared__ uint16_t idx_s[kWarpsPerCta][1024];   // MRPNP_MAX_POINTS
+    uint16_t* my_idx = idx_s[threadIdx.x >> 5];
     for (int obj = warp; obj < kp.n_obj; obj += n_warps) {
         const float* K = kp.cam_mats + (size_t)obj * kp.cam_stride;
         const float* rg = kp.uv_range + (size_t)obj * kp.range_stride;
@@ -219,7 +220,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MR6_MIN_BLOCKS) pnp_6dof_ke
         pass.c3 = kp.coords_3d + (size_t)obj * 3 * kp.n_pts;
         pass.c2 = kp.coords_2d + (size_t)obj * 2 * kp.n_pts;
         pass.cw = kp.weights + (size_t)obj * wc * kp.n_pts;
-        pass.mask = kp.inlier ? kp.inlier + (size_t)obj * ((kp.n_pts + 31) >> 5) : nullptr;
+        {   // inlier index list (order-preserving: ballot + prefix popcount per row of 32 points)
+            const uint32_t* mask = kp.inlier ? kp.inlier + (size_t)obj * ((kp.n_pts + 31) >> 5) : nullptr;
+            int count = 0;
+            __syncwarp();
+            for (int base = 0; base < kp.n_pts; base += 32) {
+                const int p = base + lane;
+                bool on = p < kp.n_pts;
+                if (mask) on = on && ((__ldg(mask + (base >> 5)) >> lane) & 1u);
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) my_idx[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+                count += __popc(m);
+            }
+            __syncwarp();
+            pass.idx = my_idx;
+            pass.n_idx = count;
+        }
         pass.lane = lane;
         double x[kNP];
         for (int k = 0; k < kNP; ++k) x[k] = kp.init[(size_t)obj * kNP + k];
