@@ -113,10 +113,12 @@ int conv_launch(mrhead_ctx* ctx, const mrhead_layer* l, const void* in, int n, i
         if (!std::strcmp(e, "reuse256")) return 256;
         return 128;
     }();
-    if (l->taps == 9 && reuse_mode) {
+    // (1x1 layers take the same kernel with one tap and no halo when their channel count allows two accumulator sets:
+    // what they gain is the epilogue under the next tile's loads.)
+    if (reuse_mode && (l->taps == 9 || (reuse_mode == 128 && l->cout_pad % 32 == 0))) {
         const size_t budget = kSmemBudget - kSmemTail;
-        const int bm = (reuse_mode == 128 && l->cout_pad % 64 == 0) ? 128 : 256;
-        const mrhead::ReuseLayout L = mrhead::reuse_layout(bm, wp, l->cout_pad, budget);
+        const int bm = (reuse_mode == 128 && l->cout_pad % 32 == 0) ? 128 : 256;
+        const mrhead::ReuseLayout L = mrhead::reuse_layout(bm, wp, l->cout_pad, budget, l->taps);
         if (L.b_stages >= 3) {
             cp.stages = (int)budget;
             cp.num_tiles = (int)((rows + bm - 1) / bm);

@@ -262,9 +262,9 @@ struct ReuseLayout {
     size_t a_bytes, b_bytes;
 };
 
-__host__ __device__ inline ReuseLayout reuse_layout(int bm, int wp, int cout_pad, size_t budget) {
+__host__ __device__ inline ReuseLayout reuse_layout(int bm, int wp, int cout_pad, size_t budget, int taps = 9) {
     ReuseLayout L;
-    L.a_lead = wp + 1;
+    L.a_lead = taps == 9 ? wp + 1 : 0;   // 1x1: no halo, the tile itself
     L.a_boxes = (bm + 2 * L.a_lead + kHaloBox - 1) / kHaloBox;
     L.a_bytes = (size_t)L.a_boxes * kHaloBox * 128;
     L.b_bytes = (size_t)cout_pad * 128;
@@ -283,7 +283,7 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
     constexpr int kSets = BM == 128 ? 2 : 1;     // accumulator sets
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const ReuseLayout L = reuse_layout(BM, cp.wp, cp.cout_pad, (size_t)cp.stages);   // cp.stages carries the operand budget in bytes
+    const ReuseLayout L = reuse_layout(BM, cp.wp, cp.cout_pad, (size_t)cp.stages, cp.taps);   // cp.stages carries the operand budget in bytes
     uint8_t* a_tiles = smem;
     uint8_t* b_tiles = smem + (size_t)L.a_stages * L.a_bytes;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(b_tiles + (size_t)L.b_stages * L.b_bytes);
@@ -327,7 +327,7 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                     for (int b = 0; b < L.a_boxes; ++b)   // rows before the first / after the last are zero-filled
                         tma_load_2d(at + (size_t)b * kHaloBox * 128, &tmap_act, kc * kBlockK, m0 - L.a_lead + b * kHaloBox, &a_full[as]);
                     if (++as == L.a_stages) { as = 0; aphase ^= 1u; }
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < cp.taps; ++tap) {
                         mbar_wait(&b_empty[bs], bphase ^ 1u);
                         mbar_expect_tx(&b_full[bs], (uint32_t)L.b_bytes);
                         tma_load_2d(b_tiles + (size_t)bs * L.b_bytes, &tmap_wgt, kc * kBlockK, tap * cp.cout_pad, &b_full[bs]);
@@ -350,11 +350,11 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                     mbar_wait(&a_full[as], aphase);
                     tc_fence_after();
                     const uint8_t* at = a_tiles + (size_t)as * L.a_bytes;
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < cp.taps; ++tap) {
                         mbar_wait(&b_full[bs], bphase);
                         tc_fence_after();
                         const uint64_t b0 = umma_desc_k128(b_tiles + (size_t)bs * L.b_bytes);
-                        const int row0 = L.a_lead + (tap / 3 - 1) * cp.wp + (tap % 3 - 1);
+                        const int row0 = cp.taps == 9 ? L.a_lead + (tap / 3 - 1) * cp.wp + (tap % 3 - 1) : 0;
 #pragma unroll
                         for (int half = 0; half < BM / 128; ++half) {
                             const uint64_t a0 = umma_desc_k128(at + (size_t)(row0 + half * 128) * 128);
@@ -366,7 +366,7 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                         umma_commit(&b_empty[bs]);
                         if (++bs == L.b_stages) { bs = 0; bphase ^= 1u; }
                     }
-                    umma_commit(&a_empty[as]);   // all nine taps of this chunk have read the super-tile
+                    umma_commit(&a_empty[as]);   // all taps of this chunk have read the super-tile
                     if (++as == L.a_stages) { as = 0; aphase ^= 1u; }
                 }
                 umma_commit(&tmem_full[set]);
@@ -410,10 +410,11 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
     const float* src = x + (size_t)n * c * hw;
     // one channel per warp iteration (no per-element division), lanes along the contiguous pixels
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    if (np > 0) {
-        for (int ch = warp; ch < c; ch += nwarps) {
+    if (np > 0) {   // a channel PAIR per warp iteration: two coalesced loads, one packed 32-bit store (c is even)
+        for (int ch = 2 * warp; ch < c; ch += 2 * nwarps) {
             const float* sp = src + (size_t)ch * hw + pmin;
-            for (int p = lane; p < np; p += 32) tile[p * ld + ch] = __float2bfloat16_rn(__ldg(sp + p));
+            for (int p = lane; p < np; p += 32)
+                *reinterpret_cast<__nv_bfloat162*>(tile + p * ld + ch) = __floats2bfloat162_rn(__ldg(sp + p), __ldg(sp + hw + p));
         }
     }
     __syncthreads();
@@ -427,10 +428,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
         __nv_bfloat162* drow = reinterpret_cast<__nv_bfloat162*>(dst + (size_t)r * c);
         for (int q = lane; q < pairs; q += 32) {
             __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
-            if (interior) {
-                v.x = t[2 * q];
-                v.y = t[2 * q + 1];
-            }
+            if (interior) v = *reinterpret_cast<const __nv_bfloat162*>(t + 2 * q);
             drow[q] = v;
         }
     }
