@@ -6,9 +6,10 @@ correspondences, % of the HBM roofline, next to the reference-equivalent CPU pat
 
 A "step" is one pass of the hot path over one batch: 8192 objects per GPU (BASELINE.json configs[2]; configs[4]
 shards 65,536 objects over 8 GPUs = the same 8192 per GPU, so scaling is weak), each with 784 correspondences,
-full 2x2 per-pixel covariance and pose-covariance output.  One solver launch per step (precision 'fast': plus the
-follow-up launch of the exact kernel over the -- normally empty -- redo list); for N > 1 the step also contains the
-single NCCL all-gather of the [N_local, 24] result rows.  Prints ONE JSON line on rank 0.
+full 2x2 per-pixel covariance and pose-covariance output.  One solver launch per step (precision 'fast': the objects the
+fp32 path hands back are solved by the exact fp64 routine inside the same launch); for N > 1 the step also contains the
+gather of the [N_local, 24] result rows (peer-to-peer stores from the kernel + completion flags, or one NCCL all-gather).
+Prints ONE JSON line on rank 0.
 """
 import argparse
 import json

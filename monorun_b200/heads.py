@@ -368,7 +368,8 @@ class MLPScoreHead(nn.Module):
     def forward_rows(self, reg_fc_out, rows, dimensions, cov_calib_logscale=None, cov_correction_sd=0.0,
                      distance_z_depth=False, calib_scoring=False, det_scores=None, native_mlp=True):
         """Solver result rows [N,24] -> (scores [N], bbox_3d [N,8], pose_cov_calib [N,4,4]); the test-time tail of
-        MonoRUnRoIHead.simple_test (monorun_roi_head.py:530-556) with two launches around the GEMMs."""
+        MonoRUnRoIHead.simple_test (monorun_roi_head.py:530-556): one launch (mrpnp_score_stage) for image-sized batches of
+        the reference configs' network shape, else two launches around the library GEMMs."""
         from . import pnp
         norm = self.pose_norm if self.use_pose_norm else None
         # (streams the fused layer's weights once per 8 objects: the right shape for an image's <= 100 RoIs; from a few
