@@ -34,7 +34,7 @@ using EncodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, 
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 constexpr size_t kSmemBudget = 227 * 1024;
-constexpr size_t kSmemTail = 1024 /* alignment slack */ + 256 /* barriers + TMEM slot */;
+constexpr size_t kSmemTail = 1024 /* alignment slack */ + 512 /* barriers (up to 2 x 6 + 2 x 9 + 4) + TMEM slot */;
 
 }  // namespace
 

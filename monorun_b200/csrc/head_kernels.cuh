@@ -268,7 +268,7 @@ __host__ __device__ inline ReuseLayout reuse_layout(int bm, int wp, int cout_pad
     L.a_boxes = (bm + 2 * L.a_lead + kHaloBox - 1) / kHaloBox;
     L.a_bytes = (size_t)L.a_boxes * kHaloBox * 128;
     L.b_bytes = (size_t)cout_pad * 128;
-    L.a_stages = 2;
+    L.a_stages = taps == 9 ? 2 : 6;   // 1x1 layers are HBM-bound on the activations: more of them in flight
     long long left = (long long)budget - (long long)(L.a_stages * L.a_bytes);
     L.b_stages = left > 0 ? (int)(left / (long long)L.b_bytes) : 0;
     if (L.b_stages > 9) L.b_stages = 9;
