@@ -21,7 +21,7 @@ HEADER = os.path.join(_ROOT, 'include', 'monorun_pnp.h')
 SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('pnp_capi.cu', 'pnp_kernel.cuh', 'pnp_device.cuh', 'pnp_fast.cuh', 'pnp_kernel_fast.cuh', 'pnp_score.cuh', 'pnp_nms.cuh', 'pnp_noc.cuh', 'pnp_exact_hessian.cuh', 'pnp_6dof.cuh', 'lm_dense.cuh')]
 HEAD_LIB_PATH = os.path.join(_PKG, 'libmonorun_head.so')
 HEAD_HEADER = os.path.join(_ROOT, 'include', 'monorun_head.h')
-HEAD_SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('head_capi.cu', 'head_kernels.cuh', 'head_tc.cuh')]
+HEAD_SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('head_capi.cu', 'head_kernels.cuh', 'head_tc.cuh', 'head_carafe_tc.cuh')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']

@@ -10,6 +10,7 @@
 
 #include "../../include/monorun_head.h"
 #include "head_kernels.cuh"
+#include "head_carafe_tc.cuh"
 
 namespace {
 
@@ -256,6 +257,27 @@ int mrhead_carafe(mrhead_ctx* ctx, const void* feat, const float* logits, int ld
     if (!ctx || !feat || !logits || !out) return fail(MRHEAD_ERR_ARG, "NULL argument");
     if (n <= 0 || h <= 0 || w <= 0 || ld_logits < 100) return fail(MRHEAD_ERR_ARG, "bad shape");
     MH_CUDA(cudaSetDevice(ctx->device));
+    // 14 x 14 maps (every reference config): the reassembly as a banded GEMM on the tensor cores (head_carafe_tc.cuh);
+    // MRHEAD_CARAFE=fma keeps the fp32 kernel (A/B, other map sizes)
+    static const bool use_tc = [] { const char* e = std::getenv("MRHEAD_CARAFE"); return !(e && !std::strcmp(e, "fma")); }();
+    if (use_tc && w == 14 && h <= 16 && h >= 9) {
+        const long long rows = (long long)n * (h + 2) * (w + 2);
+        CUtensorMap tf;
+        int rc = make_tmap(ctx, &tf, feat, (uint64_t)rows, 256, (uint32_t)mrhead::kCtK);
+        if (rc) return rc;
+        mrhead::CarafeTcParams cp;
+        cp.logits = logits; cp.out = static_cast<__nv_bfloat16*>(out);
+        cp.n = n; cp.h = h; cp.w = w; cp.ld_logits = ld_logits; cp.num_tiles = 2 * n;
+        const size_t smem = (size_t)mrhead::kCtABytes + mrhead::kCtBBytes + kSmemTail;
+        static std::atomic<int> configured3{0};
+        if (!configured3.exchange(1))
+            MH_CUDA(cudaFuncSetAttribute(mrhead::carafe_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        const int grid = cp.num_tiles < ctx->sm_count ? cp.num_tiles : ctx->sm_count;
+        mrhead::carafe_tc_kernel<<<grid, mrhead::kCtThreads, smem, static_cast<cudaStream_t>(stream)>>>(tf, cp);
+        MH_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return MRHEAD_OK;
+    }
     mrhead::carafe_kernel<5, 2><<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(feat), logits, static_cast<__nv_bfloat16*>(out), h, w, ld_logits);
     MH_CUDA(cudaGetLastError());

@@ -24,9 +24,9 @@ def _bf(t):
     return t.to(torch.bfloat16).float()
 
 
-def _close(out, ref, what):
+def _close(out, ref, what, abs_frac=1e-3):
     err = (out - ref).abs()
-    bound = ref.abs() * 2.0 ** -8 + 1e-3 * ref.abs().max()
+    bound = ref.abs() * 2.0 ** -8 + abs_frac * ref.abs().max()
     bad = (err > bound)
     assert not bad.any(), f'{what}: {int(bad.sum())} of {bad.numel()} outside tolerance, max err {err.max().item():.4g} ' \
                           f'(ref max {ref.abs().max().item():.4g}) first at {bad.nonzero()[0].tolist()}'
@@ -105,7 +105,8 @@ def test_carafe_matches_torch(dh):
     patches = patches.repeat_interleave(2, dim=4).repeat_interleave(2, dim=5)
     ref = (patches * mask.unsqueeze(2)).sum(dim=3).view(n, 256, 2 * h, 2 * h)
     full = out.view(n, 2 * h + 2, 2 * h + 2, 256).float()
-    _close(full[:, 1:-1, 1:-1].permute(0, 3, 1, 2), ref, 'carafe')
+    # the tensor-core kernel rounds the 25 softmax weights to bf16 (2^-9 relative each): a few 1e-3 of the largest value
+    _close(full[:, 1:-1, 1:-1].permute(0, 3, 1, 2), ref, 'carafe', abs_frac=5e-3)
     halo = full.clone()
     halo[:, 1:-1, 1:-1] = 0
     assert halo.abs().max().item() == 0.0
