@@ -268,7 +268,7 @@ int mrhead_carafe(mrhead_ctx* ctx, const void* feat, const float* logits, int ld
         mrhead::CarafeTcParams cp;
         cp.logits = logits; cp.out = static_cast<__nv_bfloat16*>(out);
         cp.n = n; cp.h = h; cp.w = w; cp.ld_logits = ld_logits; cp.num_tiles = 2 * n;
-        const size_t smem = (size_t)mrhead::kCtABytes + mrhead::kCtBBytes + kSmemTail;
+        const size_t smem = (size_t)mrhead::kCtABytes + mrhead::kCtBBytes + mrhead::kCtStageBytes + kSmemTail;
         static std::atomic<int> configured3{0};
         if (!configured3.exchange(1))
             MH_CUDA(cudaFuncSetAttribute(mrhead::carafe_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));

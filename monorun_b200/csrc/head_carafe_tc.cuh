@@ -17,7 +17,7 @@
 //   * A_s: K-major, 128-byte swizzle, 4 K blocks of 64 (208 used), written by the builder warps (generic proxy ->
 //     fence.proxy.async -> UMMA).  13 tcgen05.mma (M128 N256 K16) per tile and sub-pixel; fp32 accumulation in TMEM, two
 //     accumulator sets, so the epilogue of one sub-pixel runs under the MMAs of the next.
-//   * warps 4..11 build A_s, then drain the previous accumulator: TMEM -> bf16 -> the 512-byte output rows.
+//   * warps 12-15 build A_s (one thread per row), warps 4-11 drain the accumulators: TMEM -> bf16 -> the 512-byte output rows.
 // 10.4 GFLOP of useful work become 112 GFLOP of tensor work -- still 3x faster than the fp32 pipes.  Weights are rounded
 // to bf16 (2^-9 relative), the products accumulate in fp32.
 #pragma once
@@ -30,7 +30,8 @@ constexpr int kCtKSteps = kCtK / 16;            // 13
 constexpr int kCtABytes = 4 * 128 * 128;        // 4 K blocks x 128 rows x 128 B
 constexpr int kCtBBox = kCtK * 128;             // one [208 x 64 ch] box
 constexpr int kCtBBytes = 4 * kCtBBox;
-constexpr int kCtThreads = 384;                 // warp 0: TMA, warp 1: MMA, warp 2: TMEM allocator, warps 4-11: build + epilogue
+constexpr int kCtStageBytes = 8 * 32 * 80;      // epilogue staging (per warp 32 rows x 64 B, pitch 80 B)
+constexpr int kCtThreads = 512;                 // warp 0: TMA, 1: MMA, 2: TMEM allocator, 3: output halo, 4-11: epilogue, 12-15: build A
 
 struct CarafeTcParams {
     const float* logits;       // [n * hp * wp, ld_logits] fp32, channel k * 4 + s
@@ -52,7 +53,8 @@ carafe_tc_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_tile = smem;
     uint8_t* b_tile = smem + kCtABytes;
-    uint64_t* b_full = reinterpret_cast<uint64_t*>(b_tile + kCtBBytes);
+    uint8_t* stage = b_tile + kCtBBytes;                                  // 8 epilogue warps x 32 rows x 80 B
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(stage + kCtStageBytes);
     uint64_t* b_empty = b_full + 1;
     uint64_t* a_full = b_empty + 1;
     uint64_t* a_empty = a_full + 1;
@@ -67,7 +69,7 @@ carafe_tc_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_feat);
     if (warp == 1 && lane == 0) {
         mbar_init(b_full, 1); mbar_init(b_empty, 1);
-        mbar_init(a_full, kEpilogueWarps); mbar_init(a_empty, 1);
+        mbar_init(a_full, 4); mbar_init(a_empty, 1);             // four builder warps
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpilogueWarps); }
         fence_mbar_init();
     }
@@ -90,8 +92,13 @@ carafe_tc_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
                 const int n = tile >> 1, y0 = (tile & 1) * 8;
                 const int start = n * hp * wp + (y0 - 1) * wp - 1;     // may be negative / past the end: zero-filled
                 mbar_wait(b_empty, phase ^ 1u);
+#ifndef CARAFE_DBG_NO_TMA
                 mbar_expect_tx(b_full, (uint32_t)kCtBBytes);
                 for (int cb = 0; cb < 4; ++cb) tma_load_2d(b_tile + (size_t)cb * kCtBBox, &tmap_feat, cb * 64, start, b_full);
+#else
+                (void)start;
+                mbar_arrive(b_full);     // timing experiment: no loads
+#endif
                 phase ^= 1u;
             }
         }
@@ -111,71 +118,65 @@ carafe_tc_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
                 for (int j = 0; j < kCtKSteps; ++j) {
                     const uint64_t adesc = umma_desc_k128(a_tile + (size_t)(j >> 2) * (128 * 128)) + (uint64_t)(2 * (j & 3));
                     const uint64_t bdesc = umma_desc_mn128(b_tile + (size_t)j * (16 * 128), (uint32_t)kCtBBox);
+#ifndef CARAFE_DBG_NO_MMA
                     umma_bf16(tmem_base + set * 256u, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
+#endif
                 }
                 umma_commit(a_empty);              // the A tile may be rebuilt
                 umma_commit(&tmem_full[set]);
                 if (s == 3) umma_commit(b_empty);  // the source rows may be replaced
             }
         }
-    } else if (warp >= 4) {
-        // ===================== build A_s, drain the previous accumulator =====================
-        const int t = threadIdx.x - 128;                 // 0..255
-        const int m = t >> 1, part = t & 1;              // row of the tile, which half of the 25 taps
+    } else if (warp >= 12) {
+        // ===================== builders (warps 12-15): one thread per row of A_s =====================
+        const int m = threadIdx.x - 384;                 // row of the tile, 0..127
         const int yy = m >> 4, x = m & 15;
-        const int k_begin = part ? 13 : 0, k_end = part ? 25 : 13;
-        const int quarter = warp & 3, half = (warp - 4) >> 2;
-
-        auto build = [&](int i) {
-            const int tile = (int)blockIdx.x + (i >> 2) * (int)gridDim.x, s = i & 3;
+        float v[25];     // the logits of the NEXT build: loaded before the wait for the A tile
+        auto prefetch = [&](int i) {
+            const int tile = (int)blockIdx.x + (i >> 2) * (int)gridDim.x, ss = i & 3;
             const int n = tile >> 1, y = (tile & 1) * 8 + yy;
             const bool live = y < cp.h && x < cp.w;
-            float v[13];
-            float mx = -INFINITY;
             const float* lrow = cp.logits + ((size_t)n * hp * wp + (size_t)(y + 1) * wp + (x + 1)) * cp.ld_logits;
 #pragma unroll
-            for (int k = 0; k < 13; ++k) {
-                const int tap = k_begin + k;
-                v[k] = (live && tap < k_end) ? __ldg(lrow + tap * 4 + s) : -INFINITY;
-                mx = fmaxf(mx, v[k]);
-            }
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            for (int k = 0; k < 25; ++k) v[k] = live ? __ldg(lrow + k * 4 + ss) : 0.f;
+        };
+        auto build = [&](int i) {
+            const int tile = (int)blockIdx.x + (i >> 2) * (int)gridDim.x;
+            const int y = (tile & 1) * 8 + yy;
+            const bool live = y < cp.h && x < cp.w;
+            float mx = v[0];
+#pragma unroll
+            for (int k = 1; k < 25; ++k) mx = fmaxf(mx, v[k]);
             float sum = 0.f;
 #pragma unroll
-            for (int k = 0; k < 13; ++k) { v[k] = live ? __expf(v[k] - mx) : 0.f; sum += v[k]; }   // exp(-inf) = 0 for the 13th slot of part 1
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            const float inv = live ? 1.f / sum : 0.f;
+            for (int k = 0; k < 25; ++k) { v[k] = __expf(v[k] - mx); sum += v[k]; }
+            const float inv = live ? 1.f / sum : 0.f;      // rows outside the map carry zero weights (and are not stored)
 #pragma unroll
-            for (int k = 0; k < 13; ++k) {
-                const int tap = k_begin + k;
-                if (tap < k_end) {
-                    const int kk = (yy + tap / 5) * 16 + (x + tap % 5);          // column of A
-                    const uint32_t off = (uint32_t)(kk >> 6) * (128 * 128) + (uint32_t)m * 128 +
-                                         ((((uint32_t)(kk & 63) >> 3) ^ ((uint32_t)m & 7u)) << 4) + ((uint32_t)kk & 7u) * 2;
-                    *reinterpret_cast<__nv_bfloat16*>(a_tile + off) = __float2bfloat16_rn(v[k] * inv);
-                }
+            for (int k = 0; k < 25; ++k) {
+                const int kk = (yy + k / 5) * 16 + (x + k % 5);          // column of A
+                const uint32_t off = (uint32_t)(kk >> 6) * (128 * 128) + (uint32_t)m * 128 +
+                                     ((((uint32_t)(kk & 63) >> 3) ^ ((uint32_t)m & 7u)) << 4) + ((uint32_t)kk & 7u) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(a_tile + off) = __float2bfloat16_rn(v[k] * inv);
             }
             fence_proxy_async_smem();      // these generic-proxy writes are read by the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
         };
-
-        if (n_iters > 0) build(0);
+        if (n_iters > 0) { prefetch(0); build(0); }
+        for (int i = 0; i + 1 < n_iters; ++i) {
+            prefetch(i + 1);
+            mbar_wait(a_empty, (uint32_t)i & 1u);          // the MMAs of iteration i have read the A tile
+            build(i + 1);
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (warps 4-11): TMEM -> bf16 -> the 512-byte output rows, 128 channels per warp =====================
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
         for (int i = 0; i < n_iters; ++i) {
-            if (i + 1 < n_iters) {
-                mbar_wait(a_empty, (uint32_t)i & 1u);      // the MMAs of iteration i have read the A tile
-                build(i + 1);
-            }
             const uint32_t set = (uint32_t)i & 1u, tphase = ((uint32_t)i >> 1) & 1u;
             mbar_wait(&tmem_full[set], tphase);
             tc_fence_after();
             const int tile = (int)blockIdx.x + (i >> 2) * (int)gridDim.x, s = i & 3;
             const int n = tile >> 1;
-            const int row = quarter * 32 + lane;           // TMEM lane = row of the tile
-            const int ry = (tile & 1) * 8 + (row >> 4), rx = row & 15;
-            const bool live = ry < cp.h && rx < cp.w;
-            const int oy = 2 * ry + (s >> 1), ox = 2 * rx + (s & 1);
-            __nv_bfloat16* orow = cp.out + ((size_t)n * hop * wop + (size_t)(oy + 1) * wop + (ox + 1)) * 256;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * 256u + (uint32_t)(half * 128);
 #pragma unroll 1
             for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -183,14 +184,29 @@ carafe_tc_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
                 tmem_ld16(taddr + (uint32_t)c0, u);
                 tmem_ld16(taddr + (uint32_t)(c0 + 16), u + 16);
                 tmem_ld_wait();
-                if (live) {
-                    uint4* dst = reinterpret_cast<uint4*>(orow + half * 128 + c0);
+                // Through a per-warp staging tile (32 rows x 64 B, pitch 80 B) so that one store instruction writes eight
+                // rows x 64 contiguous bytes (whole 32-byte sectors): with a row per lane every instruction wrote 32 half
+                // sectors, and the stores were 140 of this kernel's 270 us (profiles/r02_head_variants.txt).
+                uint8_t* stg = stage + (size_t)(warp - 4) * (32 * 80);
+                __syncwarp();
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        dst[q] = make_uint4(pack_bf16(__uint_as_float(u[8 * q]), __uint_as_float(u[8 * q + 1])),
-                                            pack_bf16(__uint_as_float(u[8 * q + 2]), __uint_as_float(u[8 * q + 3])),
-                                            pack_bf16(__uint_as_float(u[8 * q + 4]), __uint_as_float(u[8 * q + 5])),
-                                            pack_bf16(__uint_as_float(u[8 * q + 6]), __uint_as_float(u[8 * q + 7])));
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(stg + lane * 80 + q * 16) =
+                        make_uint4(pack_bf16(__uint_as_float(u[8 * q]), __uint_as_float(u[8 * q + 1])),
+                                   pack_bf16(__uint_as_float(u[8 * q + 2]), __uint_as_float(u[8 * q + 3])),
+                                   pack_bf16(__uint_as_float(u[8 * q + 4]), __uint_as_float(u[8 * q + 5])),
+                                   pack_bf16(__uint_as_float(u[8 * q + 6]), __uint_as_float(u[8 * q + 7])));
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = (lane >> 2) + 8 * j;              // row of this warp's 32
+                    const int trow = quarter * 32 + rr;
+                    const int ty = (tile & 1) * 8 + (trow >> 4), tx = trow & 15;
+                    if (ty < cp.h && tx < cp.w) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 80 + (lane & 3) * 16);
+                        __nv_bfloat16* dr = cp.out + ((size_t)n * hop * wop + (size_t)(2 * ty + (s >> 1) + 1) * wop + (2 * tx + (s & 1) + 1)) * 256;
+                        *reinterpret_cast<uint4*>(dr + half * 128 + c0 + (lane & 3) * 8) = val;
+                    }
                 }
             }
             tc_fence_before();
