@@ -30,7 +30,7 @@ constexpr int kCtKSteps = kCtK / 16;            // 13
 constexpr int kCtABytes = 4 * 128 * 128;        // 4 K blocks x 128 rows x 128 B
 constexpr int kCtBBox = kCtK * 128;             // one [208 x 64 ch] box
 constexpr int kCtBBytes = 4 * kCtBBox;
-constexpr int kCtStageBytes = 8 * 32 * 80;      // epilogue staging (per warp 32 rows x 64 B, pitch 80 B)
+constexpr int kCtStageBytes = 8 * 32 * 144;     // epilogue staging (per warp 32 rows x 128 B, pitch 144 B)
 constexpr int kCtThreads = 512;                 // warp 0: TMA, 1: MMA, 2: TMEM allocator, 3: output halo, 4-11: epilogue, 12-15: build A
 
 struct CarafeTcParams {
@@ -53,7 +53,7 @@ carafe_tc_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_tile = smem;
     uint8_t* b_tile = smem + kCtABytes;
-    uint8_t* stage = b_tile + kCtBBytes;                                  // 8 epilogue warps x 32 rows x 80 B
+    uint8_t* stage = b_tile + kCtBBytes;                                  // 8 epilogue warps x 32 rows x 144 B
     uint64_t* b_full = reinterpret_cast<uint64_t*>(stage + kCtStageBytes);
     uint64_t* b_empty = b_full + 1;
     uint64_t* a_full = b_empty + 1;
@@ -179,33 +179,33 @@ carafe_tc_kernel(const __grid_constant__ CUtensorMap tmap_feat, const __grid_con
             const int n = tile >> 1;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * 256u + (uint32_t)(half * 128);
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-                uint32_t u[32];
-                tmem_ld16(taddr + (uint32_t)c0, u);
-                tmem_ld16(taddr + (uint32_t)(c0 + 16), u + 16);
+            for (int c0 = 0; c0 < 128; c0 += 64) {
+                uint32_t u[64];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld16(taddr + (uint32_t)(c0 + 16 * q), u + 16 * q);
                 tmem_ld_wait();
-                // Through a per-warp staging tile (32 rows x 64 B, pitch 80 B) so that one store instruction writes eight
-                // rows x 64 contiguous bytes (whole 32-byte sectors): with a row per lane every instruction wrote 32 half
-                // sectors, and the stores were 140 of this kernel's 270 us (profiles/r02_head_variants.txt).
-                uint8_t* stg = stage + (size_t)(warp - 4) * (32 * 80);
+                // Through a per-warp staging tile (32 rows x 128 B, pitch 144 B) so that one store instruction writes four
+                // rows x 128 contiguous bytes: with a row per lane every instruction wrote 32 half sectors, and the stores
+                // were 140 of this kernel's 270 us (profiles/r02_head_variants.txt).
+                uint8_t* stg = stage + (size_t)(warp - 4) * (32 * 144);
                 __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(stg + lane * 80 + q * 16) =
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<uint4*>(stg + lane * 144 + q * 16) =
                         make_uint4(pack_bf16(__uint_as_float(u[8 * q]), __uint_as_float(u[8 * q + 1])),
                                    pack_bf16(__uint_as_float(u[8 * q + 2]), __uint_as_float(u[8 * q + 3])),
                                    pack_bf16(__uint_as_float(u[8 * q + 4]), __uint_as_float(u[8 * q + 5])),
                                    pack_bf16(__uint_as_float(u[8 * q + 6]), __uint_as_float(u[8 * q + 7])));
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rr = (lane >> 2) + 8 * j;              // row of this warp's 32
+                for (int j = 0; j < 8; ++j) {
+                    const int rr = (lane >> 3) + 4 * j;              // row of this warp's 32
                     const int trow = quarter * 32 + rr;
                     const int ty = (tile & 1) * 8 + (trow >> 4), tx = trow & 15;
                     if (ty < cp.h && tx < cp.w) {
-                        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 80 + (lane & 3) * 16);
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 144 + (lane & 7) * 16);
                         __nv_bfloat16* dr = cp.out + ((size_t)n * hop * wop + (size_t)(2 * ty + (s >> 1) + 1) * wop + (2 * tx + (s & 1) + 1)) * 256;
-                        *reinterpret_cast<uint4*>(dr + half * 128 + c0 + (lane & 3) * 8) = val;
+                        *reinterpret_cast<uint4*>(dr + half * 128 + c0 + (lane & 7) * 8) = val;
                     }
                 }
             }
