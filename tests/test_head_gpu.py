@@ -89,9 +89,11 @@ def test_conv_f32_rows_and_planar(dh):
     assert (out - ref).abs().max().item() < 1e-3 * ref.abs().max().item() + 1e-4
 
 
-def test_carafe_matches_torch(dh):
+@pytest.mark.parametrize('n,h', [(3, 14), (1, 14), (80, 14), (2, 10)])
+def test_carafe_matches_torch(dh, n, h):
+    """14 x 14 maps go through the tensor-core kernel (banded GEMM; n = 80: more tiles than SMs, so CTAs loop over
+    tiles and both accumulator sets and barrier phases wrap), other sizes through the fp32 kernel."""
     from monorun_b200 import heads
-    n, h = 3, 14
     g = torch.Generator(device='cuda').manual_seed(11)
     x = _bf(torch.randn(n, 256, h, h, device='cuda', generator=g))
     logits = torch.randn(n, 100, h, h, device='cuda', generator=g) * 2
