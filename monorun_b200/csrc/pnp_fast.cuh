@@ -465,11 +465,15 @@ __device__ __forceinline__ bool run_pass(float* slot, int P, int n_main, int n, 
     const int end = n_main + 2 * lane;
     if (first) {
 #ifndef MRPNP_EXP_MERGED_FIRST   // one loop per kind: 2-3 % faster than one loop with a runtime switch (r02_ab_variants.txt, call 16)
+#ifndef MRPNP_EXP_FIRST_UNROLL
+#define MRPNP_EXP_FIRST_UNROLL 1   // 2 measured 5 % slower on the full-covariance set (r02_ab_variants.txt, call 53)
+#endif
+        constexpr int kFirstUnroll = MRPNP_EXP_FIRST_UNROLL;
         if (u.anchor) {
-#pragma unroll 1
+#pragma unroll kFirstUnroll
             for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassFirst, float2, 1>(slot, P, idx, true, u, cam, win, a, f);
         } else {
-#pragma unroll 1
+#pragma unroll kFirstUnroll
             for (int idx = 2 * lane; idx < end; idx += 64) pass_point<WMODE, kPassFirst, float2, 0>(slot, P, idx, true, u, cam, win, a, f);
         }
 #else
