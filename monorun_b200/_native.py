@@ -18,7 +18,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get('MRPNP_LIB') or os.path.join(_PKG, 'libmonorun_pnp.so')   # MRPNP_LIB: A/B builds of tools/
 HEADER = os.path.join(_ROOT, 'include', 'monorun_pnp.h')
-SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('pnp_capi.cu', 'pnp_kernel.cuh', 'pnp_device.cuh', 'pnp_fast.cuh', 'pnp_kernel_fast.cuh', 'pnp_score.cuh', 'pnp_nms.cuh', 'pnp_noc.cuh', 'pnp_exact_hessian.cuh', 'pnp_6dof.cuh', 'lm_dense.cuh')]
+SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('pnp_capi.cu', 'pnp_kernel.cuh', 'pnp_device.cuh', 'pnp_fast.cuh', 'pnp_kernel_fast.cuh', 'pnp_score.cuh', 'pnp_nms.cuh', 'pnp_noc.cuh', 'pnp_exact_hessian.cuh', 'pnp_6dof.cuh', 'pnp_6dof_fast.cuh', 'lm_dense.cuh')]
 HEAD_LIB_PATH = os.environ.get('MRHEAD_LIB') or os.path.join(_PKG, 'libmonorun_head.so')   # MRHEAD_LIB: A/B builds of tools/
 HEAD_HEADER = os.path.join(_ROOT, 'include', 'monorun_head.h')
 HEAD_SOURCES = [os.path.join(_PKG, 'csrc', f) for f in ('head_capi.cu', 'head_kernels.cuh', 'head_tc.cuh', 'head_carafe_tc.cuh')]

@@ -33,9 +33,9 @@ MRLM_HD int tri(int a, int b) { return a * NP - a * (a - 1) / 2 + (b - a); }  //
 // Cholesky solve of the symmetric NP x NP system A y = b (A full, row-major).  false when A is not
 // numerically positive definite or y is not finite -- the step is then "invalid", like a failed
 // DenseQRSolver::Solve.
+// The two halves, on caller-supplied storage (L: NP x NP, z: NP): factor once, solve for several right-hand sides.
 template <int NP>
-MRLM_HD_NOINLINE bool cholesky_solve(const double* A, const double* b, double* y) {
-    double L[NP * NP];
+MRLM_HD bool cholesky_factor(const double* A, double* L) {
     for (int i = 0; i < NP; ++i)
         for (int j = 0; j <= i; ++j) {
             double s = A[i * NP + j];
@@ -47,7 +47,11 @@ MRLM_HD_NOINLINE bool cholesky_solve(const double* A, const double* b, double* y
                 L[i * NP + j] = s / L[j * NP + j];
             }
         }
-    double z[NP];
+    return true;
+}
+
+template <int NP>
+MRLM_HD bool cholesky_backsolve(const double* L, const double* b, double* y, double* z) {
     for (int i = 0; i < NP; ++i) {
         double s = b[i];
         for (int k = 0; k < i; ++k) s -= L[i * NP + k] * z[k];
@@ -61,6 +65,12 @@ MRLM_HD_NOINLINE bool cholesky_solve(const double* A, const double* b, double* y
     bool ok = true;
     for (int i = 0; i < NP; ++i) ok = ok && isfinite(y[i]);
     return ok;
+}
+
+template <int NP>
+MRLM_HD_NOINLINE bool cholesky_solve(const double* A, const double* b, double* y) {
+    double L[NP * NP], z[NP];
+    return cholesky_factor<NP>(A, L) && cholesky_backsolve<NP>(L, b, y, z);
 }
 
 enum Termination { kConvergence = 0, kNoConvergence = 1, kFailure = 2 };
@@ -99,10 +109,21 @@ MRLM_HD bool all_finite(const double* acc, int n) {
 // strategy, Jacobi scaling, monotonic steps, no bounds, no inner iterations.  `pass(x, jac, acc)`
 // fills acc[0] (jac == false) or acc[0..kNAcc) (jac == true) for the parameter vector x.
 // x_io: initial parameters in, best accepted parameters out (pnp_uncert_cpu.cpp:259 / :302 memcpy + in-place solve).
-template <int NP, class Pass>
-MRLM_HD_NOINLINE LMResult minimize(Pass& pass, double* x_io, const LMOptions& opt) {
-    double x[NP], grad[NP], scale[NP], diag[NP], Hs[NP * NP], bs[NP], A[NP * NP], step[NP],
-        delta[NP], cand[NP], acc[Layout<NP>::kNAcc];
+// The minimiser's arrays.  minimize() keeps them on the stack; a kernel whose L1 is carved out for shared memory hands in
+// one set per warp in shared memory instead (every lane runs the controller on the same numbers, so all lanes store the
+// same value to the same address and read it back) -- minimize_in() with an LMWork.
+template <int NP>
+struct LMWork {
+    double x[NP], grad[NP], scale[NP], diag[NP], Hs[NP * NP], bs[NP], A[NP * NP], step[NP], delta[NP], cand[NP],
+        acc[Layout<NP>::kNAcc], L[NP * NP], z[NP];
+};
+
+struct LMArrays { double *x, *grad, *scale, *diag, *Hs, *bs, *A, *step, *delta, *cand, *acc, *L, *z; };
+
+template <int NP, bool SHARED_WORK, class Pass>
+MRLM_HD LMResult minimize_on(Pass& pass, double* x_io, const LMOptions& opt, const LMArrays& arr) {
+    double *x = arr.x, *grad = arr.grad, *scale = arr.scale, *diag = arr.diag, *Hs = arr.Hs, *bs = arr.bs, *A = arr.A,
+           *step = arr.step, *delta = arr.delta, *cand = arr.cand, *acc = arr.acc;
     for (int k = 0; k < NP; ++k) x[k] = x_io[k];
     for (int i = 0; i < Layout<NP>::kNAcc; ++i) acc[i] = 0.0;
     LMResult out;
@@ -161,7 +182,9 @@ MRLM_HD_NOINLINE LMResult minimize(Pass& pass, double* x_io, const LMOptions& op
                 diag[k] = fmin(fmax(Hs[k * NP + k], opt.min_lm_diagonal), opt.max_lm_diagonal);
         for (int i = 0; i < NP * NP; ++i) A[i] = Hs[i];
         for (int k = 0; k < NP; ++k) A[k * NP + k] += diag[k] / radius;
-        const bool solved = cholesky_solve<NP>(A, bs, step);
+        bool solved;
+        if (SHARED_WORK) solved = cholesky_factor<NP>(A, arr.L) && cholesky_backsolve<NP>(arr.L, bs, step, arr.z);
+        else solved = cholesky_solve<NP>(A, bs, step);
         reuse_diagonal = true;
         bool step_is_valid = false;
         double model_cost_change = 0.0;
@@ -219,6 +242,20 @@ MRLM_HD_NOINLINE LMResult minimize(Pass& pass, double* x_io, const LMOptions& op
     }
     out.final_cost = minimum_cost;
     return out;
+}
+
+template <int NP, class Pass>
+MRLM_HD_NOINLINE LMResult minimize(Pass& pass, double* x_io, const LMOptions& opt) {
+    double x[NP], grad[NP], scale[NP], diag[NP], Hs[NP * NP], bs[NP], A[NP * NP], step[NP],
+        delta[NP], cand[NP], acc[Layout<NP>::kNAcc];
+    const LMArrays arr = {x, grad, scale, diag, Hs, bs, A, step, delta, cand, acc, nullptr, nullptr};
+    return minimize_on<NP, false>(pass, x_io, opt, arr);
+}
+
+template <int NP, class Pass>
+MRLM_HD_NOINLINE LMResult minimize_in(Pass& pass, double* x_io, const LMOptions& opt, LMWork<NP>& wk) {
+    const LMArrays arr = {wk.x, wk.grad, wk.scale, wk.diag, wk.Hs, wk.bs, wk.A, wk.step, wk.delta, wk.cand, wk.acc, wk.L, wk.z};
+    return minimize_on<NP, true>(pass, x_io, opt, arr);
 }
 
 }  // namespace mrlm

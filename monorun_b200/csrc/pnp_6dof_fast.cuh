@@ -1,0 +1,319 @@
+// pnp_6dof_fast.cuh -- the 6-DoF solve (pnp_6dof.cuh) on the MIXED scheme of the 4-DoF solver (MRPNP_PREC_MIXED): the
+// residual / cost chain of every evaluation in fp64, exactly the expressions of mr6::add_point, so that Ceres'
+// trust-region decisions (lm_dense.cuh) are taken on the same numbers as in the fp64 kernel up to summation order; the
+// Jacobian, J^T r and J^T J in fp32 (their rounding moves a step by ~1e-7 of its length and the covariance by ~1e-6).
+//
+// What differs from pnp_6dof_kernel besides the arithmetic:
+//   * one read of the correspondences: the object's inliers are compacted once into the warp's shared-memory slot
+//     (x y z u v as fp32 planes, then the weight planes: the three entries of the symmetric 2x2 matrix or the two
+//     per-axis inverse deviations as floats, log-std weights exponentiated once in fp64 and kept as doubles), every pass
+//     reads that; the pose matrices, the minimiser's arrays (mrlm::LMWork) and the evaluation stash live there as well --
+//     with the L1 carved out for the slots, per-lane stack arrays would be served by L2 (measured: 1.8 ms -> see
+//     profiles/r02_6dof.txt);
+//   * every evaluation computes cost AND normal equations (a candidate is accepted ~85 % of the time) and leaves its
+//     totals in one of two stash entries per warp; the Jacobian evaluation Ceres asks for after accepting a step, and the
+//     covariance evaluation at the returned pose, find them there: 1 + (LM iterations) passes per object instead of
+//     2 + 2 x (LM iterations);
+//   * 27 fp32 sums leave the lanes through a 31-shuffle transposed reduction (lane L ends with total L), the cost through
+//     a 5-step fp64 butterfly;
+//   * objects are handed out by an atomic counter (they differ in LM iterations), 8 warps per CTA, one CTA per SM.
+// Checked against oracle/pnp_6dof_oracle.cpp and the fp64 kernel in tests/test_6dof_gpu.py.
+#pragma once
+#include "pnp_6dof.cuh"
+
+namespace mr6 {
+
+#ifdef __CUDACC__
+
+constexpr int kMixMaxWarps = 8;
+enum { kWLogstd = 0, kWIstd = 1, kWFull = 2 };   // = MRPNP_W_*
+__host__ __device__ inline int mixed_weight_bytes(int wkind) { return wkind == kWFull ? 12 : wkind == kWIstd ? 8 : 16; }
+#ifndef MR6_MIX_UNROLL
+#define MR6_MIX_UNROLL 2
+#endif
+constexpr int kMixUnroll = MR6_MIX_UNROLL;
+
+struct StashEntry {
+    double x[kNP];
+    double cost;
+    int valid, pad;
+    float tot[32];   // [0..5] J^T r, [6..26] upper triangle of J^T J (the order of mrlm::Layout<6> after the cost)
+};
+static_assert(sizeof(StashEntry) == 192, "stash entry layout");
+
+struct WarpArea {   // per warp, in front of the point planes
+    StashEntry stash[2];
+    Pose6 pose;
+    mrlm::LMWork<kNP> work;
+};
+__host__ __device__ inline int mixed_cap(int n_pts) { return (n_pts + 3) & ~3; }
+__host__ __device__ inline int mixed_slot_bytes(int n_pts, int wkind) {
+    return (int)((sizeof(WarpArea) + 15) & ~(size_t)15) + mixed_cap(n_pts) * (20 + mixed_weight_bytes(wkind));
+}
+
+// Transposed reduction of 32 per-lane partial sums: lane L ends with the warp total of value L.  16+8+4+2+1 shuffles.
+__device__ __forceinline__ float warp_reduce32_scatter(float v[32], int lane) {
+#pragma unroll
+    for (int half = 16, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return v[0];
+}
+
+template <int WKIND>
+struct MixedPass {
+    static constexpr bool FULLW = WKIND == kWFull;
+    const KParams& kp;
+    Camera cam;
+    const float* slot;   // shared memory: planes of `cap` entries x y z u v, then the weight planes
+    WarpArea* area;      // shared memory: stash, pose matrices, minimiser arrays
+    int cap, n, lane, cur;
+
+    __device__ __forceinline__ float at(const float* base, int c, int nc, int p) const {
+        return kp.planar ? __ldg(base + (size_t)c * kp.n_pts + p) : __ldg(base + (size_t)p * nc + c);
+    }
+
+    // Compacts the object's inliers into the slot (point order kept); returns their number.
+    __device__ __forceinline__ int stage(int obj, float* slot_w) {
+        constexpr int wc = FULLW ? 3 : 2;
+        const float* c3 = kp.coords_3d + (size_t)obj * 3 * kp.n_pts;
+        const float* c2 = kp.coords_2d + (size_t)obj * 2 * kp.n_pts;
+        const float* cw = kp.weights + (size_t)obj * wc * kp.n_pts;
+        const uint32_t* mask = kp.inlier ? kp.inlier + (size_t)obj * ((kp.n_pts + 31) >> 5) : nullptr;
+        float *sx = slot_w, *sy = slot_w + cap, *sz = slot_w + 2 * cap, *su = slot_w + 3 * cap, *sv = slot_w + 4 * cap;
+        float* swf = slot_w + 5 * cap;
+        double* swd = reinterpret_cast<double*>(slot_w + 5 * cap);
+        int count = 0;
+#pragma unroll 4
+        for (int base = 0; base < kp.n_pts; base += 32) {
+            const int p = base + lane;
+            const bool in = p < kp.n_pts;
+            const int q = in ? p : 0;
+            // the loads do not wait for the mask: four rows of them are in flight
+            const float X = at(c3, 0, 3, q), Y = at(c3, 1, 3, q), Z = at(c3, 2, 3, q), u = at(c2, 0, 2, q), v = at(c2, 1, 2, q);
+            const float w0 = at(cw, 0, wc, q), w1 = at(cw, 1, wc, q), w2 = FULLW ? at(cw, 2, wc, q) : 0.f;
+            bool on = in;
+            if (mask) on = on && ((__ldg(mask + (base >> 5)) >> lane) & 1u);
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) {
+                const int j = count + __popc(m & ((1u << lane) - 1u));
+                sx[j] = X; sy[j] = Y; sz[j] = Z; su[j] = u; sv[j] = v;
+                if (WKIND == kWLogstd) {
+                    swd[j] = exp(-(double)w0) / kp.std_scale;
+                    swd[cap + j] = exp(-(double)w1) / kp.std_scale;
+                } else {
+                    swf[j] = w0;
+                    swf[cap + j] = w1;
+                    if (FULLW) swf[2 * cap + j] = w2;
+                }
+            }
+            count += __popc(m);
+        }
+        __syncwarp();
+        return count;
+    }
+
+    // One evaluation at x: cost (fp64) and normal equations (fp32) of all staged points, totals into stash[e].
+    __device__ __noinline__ void evaluate(const double* x, int e) const {
+        Pose6* ps = &area->pose;
+        __syncwarp();
+        make_pose(x, ps);   // every lane stores the same numbers
+        __syncwarp();
+        const double R0 = ps->R[0], R1 = ps->R[1], R2 = ps->R[2], R3 = ps->R[3], R4 = ps->R[4], R5 = ps->R[5], R6 = ps->R[6],
+                     R7 = ps->R[7], R8 = ps->R[8], t0 = ps->t[0], t1 = ps->t[1], t2 = ps->t[2];
+        float D[27];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) D[k * 9 + i] = (float)ps->dR[k][i];
+        const double fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy, z_min = cam.z_min, u_min = cam.u_min,
+                     u_max = cam.u_max, v_min = cam.v_min, v_max = cam.v_max;
+        const float fxf = (float)fx, fyf = (float)fy;
+        float a[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = 0.f;
+        double cost = 0.0;
+        const int cap_ = cap, n_ = n;
+        const float *sx = slot, *sy = slot + cap_, *sz = slot + 2 * cap_, *su = slot + 3 * cap_, *sv = slot + 4 * cap_;
+        const float* swf = slot + 5 * cap_;
+        const double* swd = reinterpret_cast<const double*>(slot + 5 * cap_);
+#pragma unroll kMixUnroll
+        for (int j = lane; j < n_; j += 32) {
+            const float Xf = sx[j], Yf = sy[j], Zf = sz[j];
+            const double X = Xf, Y = Yf, Z = Zf;
+            // fp64 residual chain: the expressions of add_point
+            const double xc = R0 * X + R1 * Y + R2 * Z + t0;
+            const double yc = R3 * X + R4 * Y + R5 * Z + t1;
+            const double zc = R6 * X + R7 * Y + R8 * Z + t2;
+            const bool z_free = !(zc < z_min);
+            const double z = z_free ? zc : z_min, iz = 1.0 / z;
+            double pu = fx * xc * iz + cx, pv = fy * yc * iz + cy;
+            bool u_free = true, v_free = true;
+            if (pu < u_min) { pu = u_min; u_free = false; } else if (pu > u_max) { pu = u_max; u_free = false; }
+            if (pv < v_min) { pv = v_min; v_free = false; } else if (pv > v_max) { pv = v_max; v_free = false; }
+            const double du = pu - (double)su[j], dv = pv - (double)sv[j];
+            double w00, w01, w11;
+            float f00, f01, f11;
+            if (WKIND == kWLogstd) {
+                w00 = swd[j]; w01 = 0.0; w11 = swd[cap_ + j];
+                f00 = (float)w00; f01 = 0.f; f11 = (float)w11;
+            } else {
+                f00 = swf[j];
+                f01 = FULLW ? swf[cap_ + j] : 0.f;
+                f11 = FULLW ? swf[2 * cap_ + j] : swf[cap_ + j];
+                w00 = f00; w01 = f01; w11 = f11;
+            }
+            const double r0 = w00 * du + w01 * dv, r1 = w01 * du + w11 * dv;
+            cost += 0.5 * (r0 * r0 + r1 * r1);
+            // fp32 Jacobian rows and normal equations
+            const float izf = (float)iz, xcf = (float)xc, ycf = (float)yc, mz = z_free ? 1.f : 0.f;
+            const float au = u_free ? fxf * izf : 0.f, bu = u_free ? -fxf * xcf * izf * izf * mz : 0.f;
+            const float av = v_free ? fyf * izf : 0.f, bv = v_free ? -fyf * ycf * izf * izf * mz : 0.f;
+            float j0[kNP], j1[kNP];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float* Dk = D + k * 9;
+                const float dx = Dk[0] * Xf + Dk[1] * Yf + Dk[2] * Zf, dy = Dk[3] * Xf + Dk[4] * Yf + Dk[5] * Zf,
+                            dz = Dk[6] * Xf + Dk[7] * Yf + Dk[8] * Zf;
+                const float ju = au * dx + bu * dz, jv = av * dy + bv * dz;
+                j0[k] = f00 * ju + f01 * jv;
+                j1[k] = f01 * ju + f11 * jv;
+            }
+            j0[3] = f00 * au;            j1[3] = f01 * au;
+            j0[4] = f01 * av;            j1[4] = f11 * av;
+            j0[5] = f00 * bu + f01 * bv; j1[5] = f01 * bu + f11 * bv;
+            const float r0f = (float)r0, r1f = (float)r1;
+#pragma unroll
+            for (int p = 0; p < kNP; ++p) {
+                a[p] += j0[p] * r0f + j1[p] * r1f;
+#pragma unroll
+                for (int q = p; q < kNP; ++q) a[kNP + mrlm::tri<kNP>(p, q)] += j0[p] * j0[q] + j1[p] * j1[q];
+            }
+        }
+        const float tot = warp_reduce32_scatter(a, lane);
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, m);
+        __syncwarp();
+        StashEntry* s = area->stash + e;
+        s->tot[lane] = tot;
+        if (lane < kNP) s->x[lane] = x[lane];
+        if (lane == 0) { s->cost = cost; s->valid = 1; }
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ bool holds(int e, const double* x) const {
+        const StashEntry* s = area->stash + e;
+        bool same = s->valid != 0;
+#pragma unroll
+        for (int k = 0; k < kNP; ++k) same = same && (s->x[k] == x[k]);
+        return same;
+    }
+
+    // the interface of mrlm::minimize: jac == false fills acc[0], jac == true all 28 numbers
+    __device__ void operator()(const double* x, bool jac, double* acc) {
+        if (!jac) {
+            evaluate(x, cur ^ 1);
+            acc[0] = area->stash[cur ^ 1].cost;
+            return;
+        }
+        if (holds(cur ^ 1, x)) cur ^= 1;               // the candidate just evaluated was accepted
+        else if (!holds(cur, x)) evaluate(x, cur);
+        const StashEntry* s = area->stash + cur;
+        acc[0] = s->cost;
+#pragma unroll
+        for (int i = 0; i < kNAcc - 1; ++i) acc[1 + i] = (double)s->tot[i];
+    }
+};
+
+// (J^T J)^-1 like mr6::covariance, one factorisation for the six columns, on the minimiser's shared-memory arrays
+// (H in work.A, the factor in work.L, the result in work.Hs).  Same operations in the same order: identical numbers.
+__device__ __forceinline__ bool covariance_in(const double* acc, mrlm::LMWork<kNP>& wk) {
+    for (int a = 0; a < kNP; ++a)
+        for (int b = a; b < kNP; ++b) {
+            wk.A[a * kNP + b] = acc[kAccH + mrlm::tri<kNP>(a, b)];
+            wk.A[b * kNP + a] = wk.A[a * kNP + b];
+        }
+    bool ok = mrlm::cholesky_factor<kNP>(wk.A, wk.L);
+    if (!ok) return false;
+    for (int c = 0; c < kNP; ++c) {
+        for (int i = 0; i < kNP; ++i) wk.bs[i] = (i == c) ? 1.0 : 0.0;
+        ok = mrlm::cholesky_backsolve<kNP>(wk.L, wk.bs, wk.step, wk.z) && ok;
+        for (int i = 0; i < kNP; ++i) wk.Hs[i * kNP + c] = wk.step[i];
+    }
+    return ok;
+}
+
+template <int WKIND>
+__global__ void __launch_bounds__(kMixMaxWarps * 32, 1) pnp_6dof_mixed_kernel(const KParams kp, int* counters, int slot_bytes) {
+    extern __shared__ __align__(16) unsigned char mix_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* mine = mix_smem + (size_t)warp * slot_bytes;
+    MixedPass<WKIND> pass{kp};
+    pass.cap = mixed_cap(kp.n_pts);
+    pass.area = reinterpret_cast<WarpArea*>(mine);
+    float* planes = reinterpret_cast<float*>(mine + ((sizeof(WarpArea) + 15) & ~(size_t)15));
+    pass.slot = planes;
+    pass.lane = lane;
+    pass.cam.z_min = kp.z_min;
+    mrlm::LMWork<kNP>& wk = pass.area->work;
+    while (true) {
+        int obj = 0;
+        if (lane == 0) obj = atomicAdd(counters, 1);
+        obj = __shfl_sync(0xffffffffu, obj, 0);
+        if (obj >= kp.n_obj) break;
+        const float* K = kp.cam_mats + (size_t)obj * kp.cam_stride;
+        const float* rg = kp.uv_range + (size_t)obj * kp.range_stride;
+        pass.cam.fx = K[0]; pass.cam.fy = K[4]; pass.cam.cx = K[2]; pass.cam.cy = K[5];
+        pass.cam.u_min = rg[0]; pass.cam.u_max = rg[1]; pass.cam.v_min = rg[2]; pass.cam.v_max = rg[3];
+        __syncwarp();
+        if (lane < 2) pass.area->stash[lane].valid = 0;
+        pass.cur = 0;
+        pass.n = pass.stage(obj, planes);
+        double x[kNP];
+        for (int k = 0; k < kNP; ++k) x[k] = kp.init[(size_t)obj * kNP + k];
+        mrlm::LMOptions opt = mrlm::default_options();
+        if (kp.max_iterations > 0) opt.max_num_iterations = kp.max_iterations;
+        const mrlm::LMResult r = mrlm::minimize_in<kNP>(pass, x, opt, wk);
+        const bool valid = (r.term == mrlm::kConvergence || r.term == mrlm::kNoConvergence);  // IsSolutionUsable
+        pass(x, true, wk.acc);   // normally found in the stash: the returned pose is the last accepted point
+        const bool spd = covariance_in(wk.acc, wk);
+        __syncwarp();
+        {   // rows of 48 doubles, written by the warp
+            double* out = kp.result + (size_t)obj * kResultStride;
+            const bool good = valid && spd;
+            for (int i = lane; i < kResultStride; i += 32) {
+                double v = 0.0;
+                if (i < kNP) v = x[i];
+                else if (i < kNP + kNP * kNP) v = good ? wk.Hs[i - kNP] : (((i - kNP) % (kNP + 1) == 0) ? 1.0 : 0.0);
+                else if (i == 42) v = good ? 1.0 : 0.0;   // Covariance::Compute failing clears result_val (cpp:287)
+                else if (i == 43) v = r.iterations;
+                else if (i == 44) v = r.final_cost;
+                else if (i == 45) v = r.cost_evals;
+                else if (i == 46) v = r.term;
+                out[i] = v;
+            }
+        }
+        __syncwarp();
+    }
+    // self-resetting work counters, as in pnp_kernel.cuh: the last CTA to finish rearms them for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int done = atomicAdd(counters + 1, 1);
+        if (done == (int)gridDim.x - 1) {
+            counters[0] = 0;
+            counters[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace mr6

@@ -14,6 +14,7 @@
 #include "pnp_noc.cuh"
 #include "pnp_exact_hessian.cuh"
 #include "pnp_6dof.cuh"
+#include "pnp_6dof_fast.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -516,11 +517,44 @@ int mrpnp_solve_6dof(mrpnp_ctx* ctx, const mrpnp_params* p,
     kp.n_obj = p->n_obj; kp.n_pts = p->n_pts; kp.planar = p->layout == MRPNP_LAYOUT_PLANAR;
     kp.wmode = p->weight_mode; kp.cam_stride = p->cam_stride; kp.range_stride = p->range_stride;
     kp.max_iterations = p->max_iterations; kp.z_min = p->z_min; kp.std_scale = p->std_scale;
-    // one object per warp, CTAs handed out by the hardware scheduler: objects differ in LM iterations, and a
-    // persistent grid with static striding measured 10 % slower (profiles/r01b_ncu_noc_summary.txt)
     const bool full = p->weight_mode == MRPNP_W_FULL;
-    const int ctas = (p->n_obj + mr6::kWarpsPerCta - 1) / mr6::kWarpsPerCta;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->precision != MRPNP_PREC_FP64) {
+        // MRPNP_PREC_MIXED / _FAST: pnp_6dof_fast.cuh -- inliers staged once in shared memory, fp64 cost chain, fp32 normal
+        // equations, one CTA per SM, objects handed out by a counter (the sets of the 4-DoF launches, same rotation)
+        const int slot = mr6::mixed_slot_bytes(p->n_pts, p->weight_mode);
+        const int warps = std::min(mr6::kMixMaxWarps, (ctx->max_smem_optin - 1024) / slot);
+        if (warps < 1) return fail(MRPNP_ERR_ARG, "n_pts too large for the shared-memory slot%s");
+        const int smem = warps * slot;
+        void (*kernel)(const mr6::KParams, int*, int) =
+            p->weight_mode == MRPNP_W_FULL ? mr6::pnp_6dof_mixed_kernel<mr6::kWFull>
+            : p->weight_mode == MRPNP_W_ISTD ? mr6::pnp_6dof_mixed_kernel<mr6::kWIstd> : mr6::pnp_6dof_mixed_kernel<mr6::kWLogstd>;
+        MR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &capturing);
+        int set = kCounterSets - 1;
+        if (capturing == cudaStreamCaptureStatusNone) {
+            set = ctx->next_counter;
+            ctx->next_counter = (ctx->next_counter + 1) % (kCounterSets - 1);
+            if (ctx->set_used[set] && cudaEventQuery(ctx->set_done[set]) != cudaSuccess)
+                MR_CUDA(cudaStreamWaitEvent(st, ctx->set_done[set], 0));
+            (void)cudaGetLastError();
+        }
+        int* counters = ctx->counters + kCounterInts * set;
+        const int ctas = std::min(ctx->num_sms, (p->n_obj + warps - 1) / warps);
+        kernel<<<ctas, warps * 32, smem, st>>>(kp, counters, slot);
+        MR_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        if (capturing == cudaStreamCaptureStatusNone) {
+            MR_CUDA(cudaEventRecord(ctx->set_done[set], st));
+            ctx->set_used[set] = true;
+        }
+        return MRPNP_OK;
+    }
+    // MRPNP_PREC_FP64: one object per warp, CTAs handed out by the hardware scheduler: objects differ in LM iterations,
+    // and a persistent grid with static striding measured 10 % slower (profiles/r01b_ncu_noc_summary.txt)
+    const int ctas = (p->n_obj + mr6::kWarpsPerCta - 1) / mr6::kWarpsPerCta;
     if (full)
         mr6::pnp_6dof_kernel<true><<<ctas, mr6::kWarpsPerCta * 32, 0, st>>>(kp);
     else

@@ -228,9 +228,12 @@ def solve_noc_batched(coords_3d, coords_2d, weights, logdim, logdim_wgt, cam_mat
 
 
 def solve_6dof_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_pose6, inlier_mask=None, *,
-                       layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, max_iterations=50):
+                       layout='planar', weight_mode='logstd', z_min=0.5, std_scale=10.0, max_iterations=50,
+                       precision='mixed'):
     """6-DoF extension of the solver -- direct wrapper of ``mrpnp_solve_6dof``: unknowns [rvec(3), t(3)] (angle-axis
     as ceres::AngleAxisRotatePoint), everything else as :func:`solve_batched`.  init_pose6 [N,6].
+    precision: 'mixed' (default; 'fast' is accepted as a synonym) -- correspondences staged once in shared memory, fp64
+    cost chain, fp32 normal equations (pnp_6dof_fast.cuh); 'fp64' -- everything in fp64 (pnp_6dof.cuh).
     Returns result [N,48] float64: rvec, t | cov 6x6 | valid, lm_iterations, final_cost, cost_evals, termination, pad."""
     dev = coords_3d.device
     ctx = get_ctx(dev)
@@ -250,7 +253,8 @@ def solve_6dof_batched(coords_3d, coords_2d, weights, cam_mats, uv_range, init_p
     p = make_params(
         n, n_pts, layout=C['MRPNP_LAYOUT_PLANAR'] if planar else C['MRPNP_LAYOUT_INTERLEAVED'], weight_mode=wmode,
         cam_stride=9 if cam.shape[0] == n and n > 1 else 0, range_stride=4 if rng.shape[0] == n and n > 1 else 0,
-        max_iterations=int(max_iterations), z_min=float(z_min), std_scale=float(std_scale))
+        max_iterations=int(max_iterations), z_min=float(z_min), std_scale=float(std_scale),
+        precision=_PREC[precision])
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
         _native.check(_native.lib().mrpnp_solve_6dof(
@@ -675,7 +679,7 @@ class PnPUncert(torch.nn.Module):
                 istd = istd / torch.mean(istd, dim=(1, 2), keepdim=True).clamp(min=self.eps)
             res = solve_6dof_batched(coords_3d, coords_2d, istd, cam_mats, uv_range, init6,
                                      inlier_mask if self.inlier_opt_only else None, layout='interleaved',
-                                     weight_mode='istd', z_min=self.z_min)
+                                     weight_mode='istd', z_min=self.z_min, precision=self.precision)
             ok = ret_val & (res[:, 42] > 0.5)
             return (ok, res[:, 0:3].float(), res[:, 3:6].float(), res[:, 6:42].reshape(n, 6, 6).float(), inlier_mask)
 
