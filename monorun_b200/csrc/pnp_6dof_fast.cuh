@@ -29,9 +29,13 @@ constexpr int kMixMaxWarps = 8;
 enum { kWLogstd = 0, kWIstd = 1, kWFull = 2 };   // = MRPNP_W_*
 __host__ __device__ inline int mixed_weight_bytes(int wkind) { return wkind == kWFull ? 12 : wkind == kWIstd ? 8 : 16; }
 #ifndef MR6_MIX_UNROLL
-#define MR6_MIX_UNROLL 2
+#define MR6_MIX_UNROLL 1   // 2 measured 4 % slower (instruction cache; profiles/r02_6dof.txt)
 #endif
 constexpr int kMixUnroll = MR6_MIX_UNROLL;
+#ifndef MR6_STAGE_UNROLL
+#define MR6_STAGE_UNROLL 4   // rows of loads in flight while compacting; 8 measured no faster
+#endif
+constexpr int kStageUnroll = MR6_STAGE_UNROLL;
 
 struct StashEntry {
     double x[kNP];
@@ -66,6 +70,45 @@ __device__ __forceinline__ float warp_reduce32_scatter(float v[32], int lane) {
     return v[0];
 }
 
+// make_pose with one reciprocal instead of 27 divisions in the rotation derivatives (they only feed the fp32 Jacobian here);
+// R and t are computed by the same expressions as in make_pose, so the cost chain sees identical numbers.
+__device__ __noinline__ void make_pose_fast(const double* x, Pose6* p) {
+    const double w[3] = {x[0], x[1], x[2]};
+    const double theta2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    p->t[0] = x[3]; p->t[1] = x[4]; p->t[2] = x[5];
+    double W[9];
+    skew(w, W);
+    if (theta2 > 2.220446049250313e-16) {
+        const double theta = sqrt(theta2), c = cos(theta), s = sin(theta), inv = 1.0 / theta, inv2 = 1.0 / theta2;
+        const double k[3] = {w[0] * inv, w[1] * inv, w[2] * inv};
+        double Kx[9];
+        skew(k, Kx);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                p->R[i * 3 + j] = (i == j ? c : 0.0) + s * Kx[i * 3 + j] + (1.0 - c) * k[i] * k[j];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double col[3] = {(a == 0 ? 1.0 : 0.0) - p->R[a], (a == 1 ? 1.0 : 0.0) - p->R[3 + a],
+                                   (a == 2 ? 1.0 : 0.0) - p->R[6 + a]};
+            const double u[3] = {w[1] * col[2] - w[2] * col[1], w[2] * col[0] - w[0] * col[2],
+                                 w[0] * col[1] - w[1] * col[0]};
+            double U[9], M[9];
+            skew(u, U);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) M[i] = (w[a] * W[i] + U[i]) * inv2;
+            mat3_mul(M, p->R, p->dR[a]);
+        }
+    } else {
+        for (int i = 0; i < 9; ++i) p->R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + W[i];
+        for (int a = 0; a < 3; ++a) {
+            const double e[3] = {a == 0 ? 1.0 : 0.0, a == 1 ? 1.0 : 0.0, a == 2 ? 1.0 : 0.0};
+            skew(e, p->dR[a]);
+        }
+    }
+}
+
 template <int WKIND>
 struct MixedPass {
     static constexpr bool FULLW = WKIND == kWFull;
@@ -90,7 +133,7 @@ struct MixedPass {
         float* swf = slot_w + 5 * cap;
         double* swd = reinterpret_cast<double*>(slot_w + 5 * cap);
         int count = 0;
-#pragma unroll 4
+#pragma unroll kStageUnroll
         for (int base = 0; base < kp.n_pts; base += 32) {
             const int p = base + lane;
             const bool in = p < kp.n_pts;
@@ -123,7 +166,7 @@ struct MixedPass {
     __device__ __noinline__ void evaluate(const double* x, int e) const {
         Pose6* ps = &area->pose;
         __syncwarp();
-        make_pose(x, ps);   // every lane stores the same numbers
+        make_pose_fast(x, ps);   // every lane stores the same numbers
         __syncwarp();
         const double R0 = ps->R[0], R1 = ps->R[1], R2 = ps->R[2], R3 = ps->R[3], R4 = ps->R[4], R5 = ps->R[5], R6 = ps->R[6],
                      R7 = ps->R[7], R8 = ps->R[8], t0 = ps->t[0], t1 = ps->t[1], t2 = ps->t[2];
@@ -135,9 +178,9 @@ struct MixedPass {
         const double fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy, z_min = cam.z_min, u_min = cam.u_min,
                      u_max = cam.u_max, v_min = cam.v_min, v_max = cam.v_max;
         const float fxf = (float)fx, fyf = (float)fy;
-        float a[32];
+        float2 a2[kNAcc - 1];   // .x: the first residual row's share, .y: the second's
 #pragma unroll
-        for (int i = 0; i < 32; ++i) a[i] = 0.f;
+        for (int i = 0; i < kNAcc - 1; ++i) a2[i] = make_float2(0.f, 0.f);
         double cost = 0.0;
         const int cap_ = cap, n_ = n;
         const float *sx = slot, *sy = slot + cap_, *sz = slot + 2 * cap_, *su = slot + 3 * cap_, *sv = slot + 4 * cap_;
@@ -189,13 +232,20 @@ struct MixedPass {
             j0[4] = f01 * av;            j1[4] = f11 * av;
             j0[5] = f00 * bu + f01 * bv; j1[5] = f01 * bu + f11 * bv;
             const float r0f = (float)r0, r1f = (float)r1;
+            // the two residual rows side by side: one packed FMA per sum (3.5 % faster than 54 scalar FMAs)
+            const float2 rr = make_float2(r0f, r1f);
 #pragma unroll
             for (int p = 0; p < kNP; ++p) {
-                a[p] += j0[p] * r0f + j1[p] * r1f;
+                const float2 jp = make_float2(j0[p], j1[p]);
+                a2[p] = __ffma2_rn(jp, rr, a2[p]);
 #pragma unroll
-                for (int q = p; q < kNP; ++q) a[kNP + mrlm::tri<kNP>(p, q)] += j0[p] * j0[q] + j1[p] * j1[q];
+                for (int q = p; q < kNP; ++q)
+                    a2[kNP + mrlm::tri<kNP>(p, q)] = __ffma2_rn(jp, make_float2(j0[q], j1[q]), a2[kNP + mrlm::tri<kNP>(p, q)]);
             }
         }
+        float a[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = i < kNAcc - 1 ? a2[i].x + a2[i].y : 0.f;
         const float tot = warp_reduce32_scatter(a, lane);
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, m);
@@ -216,7 +266,7 @@ struct MixedPass {
     }
 
     // the interface of mrlm::minimize: jac == false fills acc[0], jac == true all 28 numbers
-    __device__ void operator()(const double* x, bool jac, double* acc) {
+    __device__ void operator()(const double* x, bool jac, double* acc) {   // (as its own function: 4-7 % slower)
         if (!jac) {
             evaluate(x, cur ^ 1);
             acc[0] = area->stash[cur ^ 1].cost;

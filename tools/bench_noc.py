@@ -62,20 +62,24 @@ def main():
         d = {k: torch.from_numpy(np.ascontiguousarray(c[k])).cuda() for k in ('c3', 'c2', 'w', 'cam', 'uv_range', 'init')}
         pl = [d[k].permute(0, 2, 1).contiguous() for k in ('c3', 'c2', 'w')]
 
-        def run6():
+        def run6(precision='fp64'):
             return pnp.solve_6dof_batched(pl[0], pl[1], pl[2], d['cam'], d['uv_range'], d['init'], layout='planar',
-                                          weight_mode='full' if full else 'istd')
-        for _ in range(3):
-            res = run6()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            res = run6()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        res = res.cpu().numpy()
+                                          weight_mode='full' if full else 'istd', precision=precision)
+
+        def time6(precision):
+            for _ in range(3):
+                res = run6(precision)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                res = run6(precision)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / 10, res
+        ms_mixed, res_mixed = time6('mixed')
+        ms, res = time6('fp64')
+        res, rm = res.cpu().numpy(), res_mixed.cpu().numpy()
         m = a.cpu_sample
         cs = {k: (v[:m] if isinstance(v, np.ndarray) and v.shape[0] == a.n else v) for k, v in c.items()}
         t0 = time.perf_counter()
@@ -85,7 +89,10 @@ def main():
         out['6dof_' + ('full' if full else 'diag')] = dict(
             n=a.n, ms=ms, objects_per_s=a.n / ms * 1e3, mean_cost_evals=float(res[:, 45].mean()),
             cpu_objects_per_s=m / cpu_s, cpu_threads=os.cpu_count(), cpu_sample=m, same_lm_paths=float(same.mean()),
-            max_pose_diff_same_paths=float(np.abs(res[:m, :6] - r['pose'])[same].max()), valid=float((res[:, 42] > 0).mean()))
+            max_pose_diff_same_paths=float(np.abs(res[:m, :6] - r['pose'])[same].max()), valid=float((res[:, 42] > 0).mean()),
+            mixed_ms=ms_mixed, mixed_objects_per_s=a.n / ms_mixed * 1e3,
+            mixed_same_evals_as_fp64=float((rm[:, 45] == res[:, 45]).mean()),
+            mixed_max_pose_diff_same_evals=float(np.abs(rm[:, :6] - res[:, :6])[rm[:, 45] == res[:, 45]].max()))
     print({k: v for k, v in out.items() if k.startswith('6dof')})
 
     # second-order covariance pass (mrpnp_exact_hessian): one read of the correspondences at the final pose
