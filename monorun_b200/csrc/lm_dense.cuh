@@ -17,10 +17,6 @@
 #define MRLM_HD_NOINLINE inline
 #endif
 
-#ifndef MRLM_UNROLL_SHARED
-#define MRLM_UNROLL_SHARED true   // minimize_in(): Cholesky fully unrolled (8 % on the 6-DoF mixed kernel)
-#endif
-
 namespace mrlm {
 
 // accumulator layout: [cost | gradient (NP) | upper triangle of J^T J, row-major]
@@ -37,16 +33,46 @@ MRLM_HD int tri(int a, int b) { return a * NP - a * (a - 1) / 2 + (b - a); }  //
 // Cholesky solve of the symmetric NP x NP system A y = b (A full, row-major).  false when A is not
 // numerically positive definite or y is not finite -- the step is then "invalid", like a failed
 // DenseQRSolver::Solve.
-// The two halves, on caller-supplied storage (L: NP x NP, z: NP): factor once, solve for several right-hand sides.
-template <int NP, bool UNROLL = false>
-MRLM_HD bool cholesky_factor(const double* A, double* L) {
-    constexpr int kU = UNROLL ? NP : 1;   // full unrolling: no index arithmetic or loop branches (the operations are the same)
-#pragma unroll kU
+template <int NP>
+MRLM_HD_NOINLINE bool cholesky_solve(const double* A, const double* b, double* y) {
+    double L[NP * NP];
     for (int i = 0; i < NP; ++i)
-#pragma unroll kU
         for (int j = 0; j <= i; ++j) {
             double s = A[i * NP + j];
-#pragma unroll kU
+            for (int k = 0; k < j; ++k) s -= L[i * NP + k] * L[j * NP + k];
+            if (i == j) {
+                if (!(s > 0.0) || !isfinite(s)) return false;
+                L[i * NP + i] = sqrt(s);
+            } else {
+                L[i * NP + j] = s / L[j * NP + j];
+            }
+        }
+    double z[NP];
+    for (int i = 0; i < NP; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= L[i * NP + k] * z[k];
+        z[i] = s / L[i * NP + i];
+    }
+    for (int i = NP - 1; i >= 0; --i) {
+        double s = z[i];
+        for (int k = i + 1; k < NP; ++k) s -= L[k * NP + i] * y[k];
+        y[i] = s / L[i * NP + i];
+    }
+    bool ok = true;
+    for (int i = 0; i < NP; ++i) ok = ok && isfinite(y[i]);
+    return ok;
+}
+
+// The same solve in two halves on caller-supplied storage (L: NP x NP, z: NP), fully unrolled (no index arithmetic or loop
+// branches; the operations and their order are those of cholesky_solve): factor once, solve for several right-hand sides.
+template <int NP>
+MRLM_HD bool cholesky_factor(const double* A, double* L) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double s = A[i * NP + j];
+#pragma unroll
             for (int k = 0; k < j; ++k) s -= L[i * NP + k] * L[j * NP + k];
             if (i == j) {
                 if (!(s > 0.0) || !isfinite(s)) return false;
@@ -58,33 +84,26 @@ MRLM_HD bool cholesky_factor(const double* A, double* L) {
     return true;
 }
 
-template <int NP, bool UNROLL = false>
+template <int NP>
 MRLM_HD bool cholesky_backsolve(const double* L, const double* b, double* y, double* z) {
-    constexpr int kU = UNROLL ? NP : 1;
-#pragma unroll kU
+#pragma unroll
     for (int i = 0; i < NP; ++i) {
         double s = b[i];
-#pragma unroll kU
+#pragma unroll
         for (int k = 0; k < i; ++k) s -= L[i * NP + k] * z[k];
         z[i] = s / L[i * NP + i];
     }
-#pragma unroll kU
+#pragma unroll
     for (int i = NP - 1; i >= 0; --i) {
         double s = z[i];
-#pragma unroll kU
+#pragma unroll
         for (int k = i + 1; k < NP; ++k) s -= L[k * NP + i] * y[k];
         y[i] = s / L[i * NP + i];
     }
     bool ok = true;
-#pragma unroll kU
+#pragma unroll
     for (int i = 0; i < NP; ++i) ok = ok && isfinite(y[i]);
     return ok;
-}
-
-template <int NP>
-MRLM_HD_NOINLINE bool cholesky_solve(const double* A, const double* b, double* y) {
-    double L[NP * NP], z[NP];
-    return cholesky_factor<NP>(A, L) && cholesky_backsolve<NP>(L, b, y, z);
 }
 
 enum Termination { kConvergence = 0, kNoConvergence = 1, kFailure = 2 };
@@ -123,21 +142,10 @@ MRLM_HD bool all_finite(const double* acc, int n) {
 // strategy, Jacobi scaling, monotonic steps, no bounds, no inner iterations.  `pass(x, jac, acc)`
 // fills acc[0] (jac == false) or acc[0..kNAcc) (jac == true) for the parameter vector x.
 // x_io: initial parameters in, best accepted parameters out (pnp_uncert_cpu.cpp:259 / :302 memcpy + in-place solve).
-// The minimiser's arrays.  minimize() keeps them on the stack; a kernel whose L1 is carved out for shared memory hands in
-// one set per warp in shared memory instead (every lane runs the controller on the same numbers, so all lanes store the
-// same value to the same address and read it back) -- minimize_in() with an LMWork.
-template <int NP>
-struct LMWork {
-    double x[NP], grad[NP], scale[NP], diag[NP], Hs[NP * NP], bs[NP], A[NP * NP], step[NP], delta[NP], cand[NP],
-        acc[Layout<NP>::kNAcc], L[NP * NP], z[NP];
-};
-
-struct LMArrays { double *x, *grad, *scale, *diag, *Hs, *bs, *A, *step, *delta, *cand, *acc, *L, *z; };
-
-template <int NP, bool SHARED_WORK, class Pass>
-MRLM_HD LMResult minimize_on(Pass& pass, double* x_io, const LMOptions& opt, const LMArrays& arr) {
-    double *x = arr.x, *grad = arr.grad, *scale = arr.scale, *diag = arr.diag, *Hs = arr.Hs, *bs = arr.bs, *A = arr.A,
-           *step = arr.step, *delta = arr.delta, *cand = arr.cand, *acc = arr.acc;
+template <int NP, class Pass>
+MRLM_HD_NOINLINE LMResult minimize(Pass& pass, double* x_io, const LMOptions& opt) {
+    double x[NP], grad[NP], scale[NP], diag[NP], Hs[NP * NP], bs[NP], A[NP * NP], step[NP],
+        delta[NP], cand[NP], acc[Layout<NP>::kNAcc];
     for (int k = 0; k < NP; ++k) x[k] = x_io[k];
     for (int i = 0; i < Layout<NP>::kNAcc; ++i) acc[i] = 0.0;
     LMResult out;
@@ -196,9 +204,7 @@ MRLM_HD LMResult minimize_on(Pass& pass, double* x_io, const LMOptions& opt, con
                 diag[k] = fmin(fmax(Hs[k * NP + k], opt.min_lm_diagonal), opt.max_lm_diagonal);
         for (int i = 0; i < NP * NP; ++i) A[i] = Hs[i];
         for (int k = 0; k < NP; ++k) A[k * NP + k] += diag[k] / radius;
-        bool solved;
-        if (SHARED_WORK) solved = cholesky_factor<NP, MRLM_UNROLL_SHARED>(A, arr.L) && cholesky_backsolve<NP, MRLM_UNROLL_SHARED>(arr.L, bs, step, arr.z);
-        else solved = cholesky_solve<NP>(A, bs, step);
+        const bool solved = cholesky_solve<NP>(A, bs, step);
         reuse_diagonal = true;
         bool step_is_valid = false;
         double model_cost_change = 0.0;
@@ -256,20 +262,6 @@ MRLM_HD LMResult minimize_on(Pass& pass, double* x_io, const LMOptions& opt, con
     }
     out.final_cost = minimum_cost;
     return out;
-}
-
-template <int NP, class Pass>
-MRLM_HD_NOINLINE LMResult minimize(Pass& pass, double* x_io, const LMOptions& opt) {
-    double x[NP], grad[NP], scale[NP], diag[NP], Hs[NP * NP], bs[NP], A[NP * NP], step[NP],
-        delta[NP], cand[NP], acc[Layout<NP>::kNAcc];
-    const LMArrays arr = {x, grad, scale, diag, Hs, bs, A, step, delta, cand, acc, nullptr, nullptr};
-    return minimize_on<NP, false>(pass, x_io, opt, arr);
-}
-
-template <int NP, class Pass>
-MRLM_HD_NOINLINE LMResult minimize_in(Pass& pass, double* x_io, const LMOptions& opt, LMWork<NP>& wk) {
-    const LMArrays arr = {wk.x, wk.grad, wk.scale, wk.diag, wk.Hs, wk.bs, wk.A, wk.step, wk.delta, wk.cand, wk.acc, wk.L, wk.z};
-    return minimize_on<NP, true>(pass, x_io, opt, arr);
 }
 
 }  // namespace mrlm

@@ -7,17 +7,19 @@
 //   * one read of the correspondences: the object's inliers are compacted once into the warp's shared-memory slot
 //     (x y z u v as fp32 planes, then the weight planes: the three entries of the symmetric 2x2 matrix or the two
 //     per-axis inverse deviations as floats, log-std weights exponentiated once in fp64 and kept as doubles), every pass
-//     reads that; the pose matrices, the minimiser's arrays (mrlm::LMWork) and the evaluation stash live there as well --
-//     with the L1 carved out for the slots, per-lane stack arrays would be served by L2 (measured: 1.8 ms -> see
-//     profiles/r02_6dof.txt);
+//     reads that;
 //   * every evaluation computes cost AND normal equations (a candidate is accepted ~85 % of the time) and leaves its
 //     totals in one of two stash entries per warp; the Jacobian evaluation Ceres asks for after accepting a step, and the
 //     covariance evaluation at the returned pose, find them there: 1 + (LM iterations) passes per object instead of
 //     2 + 2 x (LM iterations);
-//   * 27 fp32 sums leave the lanes through a 31-shuffle transposed reduction (lane L ends with total L), the cost through
-//     a 5-step fp64 butterfly;
+//   * the trust-region controller is mrlm::minimize cut at its cost evaluation (lm_advance: from one evaluation's totals
+//     to the next candidate or the end), run by lane 0 on a per-warp state in shared memory -- with the L1 carved out for
+//     the slots, the per-lane stack arrays of mrlm::minimize would be served by L2 (measured 1.8 ms against 1.05 ms) --
+//     and handed to the warp through __syncwarp; the six columns of the covariance are back-substituted by six lanes;
+//   * 27 fp32 sums (two residual rows side by side in packed FMAs) leave the lanes through a 31-shuffle transposed
+//     reduction (lane L ends with total L), the cost through a 5-step fp64 butterfly;
 //   * objects are handed out by an atomic counter (they differ in LM iterations), 8 warps per CTA, one CTA per SM.
-// Checked against oracle/pnp_6dof_oracle.cpp and the fp64 kernel in tests/test_6dof_gpu.py.
+// Checked against oracle/pnp_6dof_oracle.cpp and the fp64 kernel in tests/test_6dof_gpu.py; profiles/r02_6dof.txt.
 #pragma once
 #include "pnp_6dof.cuh"
 
@@ -40,15 +42,29 @@ constexpr int kStageUnroll = MR6_STAGE_UNROLL;
 struct StashEntry {
     double x[kNP];
     double cost;
-    int valid, pad;
+    int pad[2];
     float tot[32];   // [0..5] J^T r, [6..26] upper triangle of J^T J (the order of mrlm::Layout<6> after the cost)
 };
 static_assert(sizeof(StashEntry) == 192, "stash entry layout");
 
+enum { kCmdEvaluate = 0, kCmdDone = 1 };
+
+// mrlm::minimize's variables for one object (lane 0 reads and writes them; `cmd`, `cur`, `cand`, `best` and the covariance
+// in Hs are what the other lanes read, after a __syncwarp).
+struct LMState {
+    double x[kNP], best[kNP], grad[kNP], scale[kNP], diag[kNP], bs[kNP], step[kNP], delta[kNP], cand[kNP], z[kNP];
+    double Hs[kNP * kNP], A[kNP * kNP], L[kNP * kNP], acc[kNAcc];
+    double radius, decrease_factor, x_cost, x_norm, gradient_max_norm, minimum_cost, step_norm, model_cost_change, final_cost;
+    int iteration, iterations, num_invalid, reuse_diagonal, step_is_successful, term, cost_evals, jac_evals;
+    int cur;   // stash entry of the current point (cur ^ 1: the candidate's)
+    int cmd, spd, need_final;
+    mrlm::LMOptions opt;
+};
+
 struct WarpArea {   // per warp, in front of the point planes
     StashEntry stash[2];
     Pose6 pose;
-    mrlm::LMWork<kNP> work;
+    LMState lm;
 };
 __host__ __device__ inline int mixed_cap(int n_pts) { return (n_pts + 3) & ~3; }
 __host__ __device__ inline int mixed_slot_bytes(int n_pts, int wkind) {
@@ -116,7 +132,7 @@ struct MixedPass {
     Camera cam;
     const float* slot;   // shared memory: planes of `cap` entries x y z u v, then the weight planes
     WarpArea* area;      // shared memory: stash, pose matrices, minimiser arrays
-    int cap, n, lane, cur;
+    int cap, n, lane;
 
     __device__ __forceinline__ float at(const float* base, int c, int nc, int p) const {
         return kp.planar ? __ldg(base + (size_t)c * kp.n_pts + p) : __ldg(base + (size_t)p * nc + c);
@@ -166,7 +182,7 @@ struct MixedPass {
     __device__ __noinline__ void evaluate(const double* x, int e) const {
         Pose6* ps = &area->pose;
         __syncwarp();
-        make_pose_fast(x, ps);   // every lane stores the same numbers
+        if (lane == 0) make_pose_fast(x, ps);
         __syncwarp();
         const double R0 = ps->R[0], R1 = ps->R[1], R2 = ps->R[2], R3 = ps->R[3], R4 = ps->R[4], R5 = ps->R[5], R6 = ps->R[6],
                      R7 = ps->R[7], R8 = ps->R[8], t0 = ps->t[0], t1 = ps->t[1], t2 = ps->t[2];
@@ -253,50 +269,138 @@ struct MixedPass {
         StashEntry* s = area->stash + e;
         s->tot[lane] = tot;
         if (lane < kNP) s->x[lane] = x[lane];
-        if (lane == 0) { s->cost = cost; s->valid = 1; }
+        if (lane == 0) s->cost = cost;
         __syncwarp();
-    }
-
-    __device__ __forceinline__ bool holds(int e, const double* x) const {
-        const StashEntry* s = area->stash + e;
-        bool same = s->valid != 0;
-#pragma unroll
-        for (int k = 0; k < kNP; ++k) same = same && (s->x[k] == x[k]);
-        return same;
-    }
-
-    // the interface of mrlm::minimize: jac == false fills acc[0], jac == true all 28 numbers
-    __device__ void operator()(const double* x, bool jac, double* acc) {   // (as its own function: 4-7 % slower)
-        if (!jac) {
-            evaluate(x, cur ^ 1);
-            acc[0] = area->stash[cur ^ 1].cost;
-            return;
-        }
-        if (holds(cur ^ 1, x)) cur ^= 1;               // the candidate just evaluated was accepted
-        else if (!holds(cur, x)) evaluate(x, cur);
-        const StashEntry* s = area->stash + cur;
-        acc[0] = s->cost;
-#pragma unroll
-        for (int i = 0; i < kNAcc - 1; ++i) acc[1 + i] = (double)s->tot[i];
     }
 };
 
-// (J^T J)^-1 like mr6::covariance, one factorisation for the six columns, on the minimiser's shared-memory arrays
-// (H in work.A, the factor in work.L, the result in work.Hs).  Same operations in the same order: identical numbers.
-__device__ __forceinline__ bool covariance_in(const double* acc, mrlm::LMWork<kNP>& wk) {
-    for (int a = 0; a < kNP; ++a)
-        for (int b = a; b < kNP; ++b) {
-            wk.A[a * kNP + b] = acc[kAccH + mrlm::tri<kNP>(a, b)];
-            wk.A[b * kNP + a] = wk.A[a * kNP + b];
+// mrlm::minimize (lm_dense.cuh) from one cost evaluation to the next: `first` -- the totals of the start point are in
+// stash[cur]; otherwise the candidate S.cand has just been evaluated into stash[cur ^ 1].  Returns kCmdEvaluate with the
+// next candidate in S.cand, or kCmdDone with S.best / S.term / S.iterations / S.final_cost / S.cost_evals set as
+// minimize() returns them.  Same statements in the same order as minimize(); the Jacobian evaluation after an accepted
+// step is the candidate's stash entry.  Lane 0 only.
+__device__ __noinline__ int lm_advance(LMState& S, const StashEntry* stash, bool first) {
+    constexpr int NP = kNP;
+    const mrlm::LMOptions& opt = S.opt;
+    auto fetch = [&](int e) {
+        S.acc[0] = stash[e].cost;
+#pragma unroll
+        for (int i = 0; i < kNAcc - 1; ++i) S.acc[1 + i] = (double)stash[e].tot[i];
+    };
+    auto load_point = [&](bool initial) {
+        S.x_cost = S.acc[0];
+        S.gradient_max_norm = 0.0;
+        for (int k = 0; k < NP; ++k) {
+            S.grad[k] = S.acc[kAccG + k];
+            S.gradient_max_norm = fmax(S.gradient_max_norm, fabs(S.grad[k]));
         }
-    bool ok = mrlm::cholesky_factor<kNP>(wk.A, wk.L);
-    if (!ok) return false;
-    for (int c = 0; c < kNP; ++c) {
-        for (int i = 0; i < kNP; ++i) wk.bs[i] = (i == c) ? 1.0 : 0.0;
-        ok = mrlm::cholesky_backsolve<kNP>(wk.L, wk.bs, wk.step, wk.z) && ok;
-        for (int i = 0; i < kNP; ++i) wk.Hs[i * kNP + c] = wk.step[i];
+        if (initial)
+            for (int k = 0; k < NP; ++k) S.scale[k] = 1.0 / (1.0 + sqrt(S.acc[kAccH + mrlm::tri<NP>(k, k)]));
+        for (int a = 0; a < NP; ++a) {
+            S.bs[a] = S.scale[a] * S.grad[a];
+            for (int b = a; b < NP; ++b) {
+                const double h = S.acc[kAccH + mrlm::tri<NP>(a, b)] * S.scale[a] * S.scale[b];
+                S.Hs[a * NP + b] = h;
+                S.Hs[b * NP + a] = h;
+            }
+        }
+        S.x_norm = 0.0;
+        for (int k = 0; k < NP; ++k) S.x_norm += S.x[k] * S.x[k];
+        S.x_norm = sqrt(S.x_norm);
+    };
+    bool finished = false;
+    if (first) {
+        S.radius = opt.initial_radius; S.decrease_factor = 2.0; S.reuse_diagonal = 0; S.num_invalid = 0;
+        S.minimum_cost = 1.7976931348623157e308;
+        S.term = mrlm::kFailure; S.iterations = 0; S.cost_evals = 1; S.jac_evals = 1; S.final_cost = 0.0;
+        for (int k = 0; k < NP; ++k) S.best[k] = S.x[k];
+        fetch(S.cur);
+        if (!mrlm::all_finite(S.acc, kNAcc)) { S.final_cost = S.acc[0]; return kCmdDone; }
+        load_point(true);
+        S.iteration = 0; S.step_is_successful = 1; S.term = mrlm::kNoConvergence;
+    } else {
+        S.cost_evals++;
+        const double c = stash[S.cur ^ 1].cost;
+        const double cand_cost = isfinite(c) ? c : 1.7976931348623157e308;
+        const double cost_change = S.x_cost - cand_cost;
+        if (S.step_norm <= opt.parameter_tolerance * (S.x_norm + opt.parameter_tolerance)) {
+            S.term = mrlm::kConvergence; finished = true;
+        } else if (fabs(cost_change) <= opt.function_tolerance * S.x_cost) {
+            S.term = mrlm::kConvergence; finished = true;
+        } else {
+            const double relative_decrease = cost_change / S.model_cost_change;
+            if (relative_decrease > opt.min_relative_decrease) {  // HandleSuccessfulStep
+                for (int k = 0; k < NP; ++k) S.x[k] = S.cand[k];
+                S.cur ^= 1;
+                fetch(S.cur);
+                S.jac_evals++;
+                if (!mrlm::all_finite(S.acc, kNAcc)) {
+                    S.term = mrlm::kFailure; finished = true;
+                } else {
+                    load_point(false);
+                    S.step_is_successful = 1;
+                    const double q = 2.0 * relative_decrease - 1.0;  // LevenbergMarquardtStrategy::StepAccepted
+                    S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+                    S.radius = fmin(opt.max_radius, S.radius);
+                    S.decrease_factor = 2.0;
+                    S.reuse_diagonal = 0;
+                }
+            } else {  // StepRejected
+                S.radius /= S.decrease_factor; S.decrease_factor *= 2.0;
+            }
+        }
     }
-    return ok;
+    while (!finished) {
+        if (S.step_is_successful && S.x_cost < S.minimum_cost) {
+            S.minimum_cost = S.x_cost;
+            for (int k = 0; k < NP; ++k) S.best[k] = S.x[k];
+        }
+        S.iterations = S.iteration;
+        if (S.iteration >= opt.max_num_iterations) { S.term = mrlm::kNoConvergence; break; }
+        if (S.step_is_successful && S.gradient_max_norm <= opt.gradient_tolerance) { S.term = mrlm::kConvergence; break; }
+        if (S.radius <= opt.min_radius) { S.term = mrlm::kConvergence; break; }
+        ++S.iteration;
+        S.step_is_successful = 0;
+
+        // LevenbergMarquardtStrategy::ComputeStep
+        if (!S.reuse_diagonal)
+            for (int k = 0; k < NP; ++k)
+                S.diag[k] = fmin(fmax(S.Hs[k * NP + k], opt.min_lm_diagonal), opt.max_lm_diagonal);
+        for (int i = 0; i < NP * NP; ++i) S.A[i] = S.Hs[i];
+        for (int k = 0; k < NP; ++k) S.A[k * NP + k] += S.diag[k] / S.radius;
+        const bool solved = mrlm::cholesky_factor<NP>(S.A, S.L) && mrlm::cholesky_backsolve<NP>(S.L, S.bs, S.step, S.z);
+        S.reuse_diagonal = 1;
+        bool step_is_valid = false;
+        S.model_cost_change = 0.0;
+        if (solved) {
+            double lin = 0.0, quad = 0.0;  // -(J s)^T (r + J s / 2) with s = -y
+            for (int a = 0; a < NP; ++a) S.step[a] = -S.step[a];
+            for (int a = 0; a < NP; ++a) {
+                double hs = 0.0;
+                for (int b = 0; b < NP; ++b) hs += S.Hs[a * NP + b] * S.step[b];
+                lin += S.step[a] * S.bs[a];
+                quad += S.step[a] * hs;
+            }
+            S.model_cost_change = -(lin + 0.5 * quad);
+            step_is_valid = S.model_cost_change > 0.0;
+        }
+        if (!step_is_valid) {  // HandleInvalidStep
+            if (++S.num_invalid >= opt.max_consecutive_invalid) { S.term = mrlm::kFailure; break; }
+            S.radius /= S.decrease_factor; S.decrease_factor *= 2.0;
+            continue;
+        }
+        S.num_invalid = 0;
+        double step_norm = 0.0;
+        for (int k = 0; k < NP; ++k) {
+            S.delta[k] = S.step[k] * S.scale[k];
+            S.cand[k] = S.x[k] + S.delta[k];
+            step_norm += S.delta[k] * S.delta[k];
+        }
+        S.step_norm = sqrt(step_norm);
+        return kCmdEvaluate;
+    }
+    S.final_cost = S.minimum_cost;
+    return kCmdDone;
 }
 
 template <int WKIND>
@@ -311,7 +415,12 @@ __global__ void __launch_bounds__(kMixMaxWarps * 32, 1) pnp_6dof_mixed_kernel(co
     pass.slot = planes;
     pass.lane = lane;
     pass.cam.z_min = kp.z_min;
-    mrlm::LMWork<kNP>& wk = pass.area->work;
+    LMState& S = pass.area->lm;
+    const StashEntry* stash = pass.area->stash;
+    if (lane == 0) {
+        S.opt = mrlm::default_options();
+        if (kp.max_iterations > 0) S.opt.max_num_iterations = kp.max_iterations;
+    }
     while (true) {
         int obj = 0;
         if (lane == 0) obj = atomicAdd(counters, 1);
@@ -322,30 +431,62 @@ __global__ void __launch_bounds__(kMixMaxWarps * 32, 1) pnp_6dof_mixed_kernel(co
         pass.cam.fx = K[0]; pass.cam.fy = K[4]; pass.cam.cx = K[2]; pass.cam.cy = K[5];
         pass.cam.u_min = rg[0]; pass.cam.u_max = rg[1]; pass.cam.v_min = rg[2]; pass.cam.v_max = rg[3];
         __syncwarp();
-        if (lane < 2) pass.area->stash[lane].valid = 0;
-        pass.cur = 0;
-        pass.n = pass.stage(obj, planes);
-        double x[kNP];
-        for (int k = 0; k < kNP; ++k) x[k] = kp.init[(size_t)obj * kNP + k];
-        mrlm::LMOptions opt = mrlm::default_options();
-        if (kp.max_iterations > 0) opt.max_num_iterations = kp.max_iterations;
-        const mrlm::LMResult r = mrlm::minimize_in<kNP>(pass, x, opt, wk);
-        const bool valid = (r.term == mrlm::kConvergence || r.term == mrlm::kNoConvergence);  // IsSolutionUsable
-        pass(x, true, wk.acc);   // normally found in the stash: the returned pose is the last accepted point
-        const bool spd = covariance_in(wk.acc, wk);
+        if (lane < kNP) S.x[lane] = kp.init[(size_t)obj * kNP + lane];
+        if (lane == 0) S.cur = 0;
+        pass.n = pass.stage(obj, planes);   // ends with __syncwarp
+        pass.evaluate(S.x, 0);
+        bool first = true;
+        while (true) {
+            if (lane == 0) S.cmd = lm_advance(S, stash, first);
+            __syncwarp();
+            if (S.cmd == kCmdDone) break;
+            pass.evaluate(S.cand, S.cur ^ 1);
+            first = false;
+        }
+        // covariance at the returned pose: its totals are the current stash entry (the returned pose is the last accepted
+        // point) unless the minimiser failed before accepting anything
+        if (lane == 0) {
+            const StashEntry* e = stash + S.cur;
+            bool same = true;
+            for (int k = 0; k < kNP; ++k) same = same && (e->x[k] == S.best[k]);
+            S.need_final = same ? 0 : 1;
+        }
+        __syncwarp();
+        if (S.need_final) pass.evaluate(S.best, S.cur);
+        if (lane == 0) {   // (J^T J) = L L^T, like mr6::covariance
+            const StashEntry* e = stash + S.cur;
+            for (int a = 0; a < kNP; ++a)
+                for (int b = a; b < kNP; ++b) {
+                    S.A[a * kNP + b] = (double)e->tot[kNP + mrlm::tri<kNP>(a, b)];
+                    S.A[b * kNP + a] = S.A[a * kNP + b];
+                }
+            S.spd = mrlm::cholesky_factor<kNP>(S.A, S.L) ? 1 : 0;
+        }
+        __syncwarp();
+        bool col_ok = true;
+        if (lane < kNP && S.spd) {   // one column of the inverse per lane: the same back-substitutions as covariance()
+            double e[kNP], y[kNP], z[kNP];
+#pragma unroll
+            for (int i = 0; i < kNP; ++i) e[i] = (i == lane) ? 1.0 : 0.0;
+            col_ok = mrlm::cholesky_backsolve<kNP>(S.L, e, y, z);
+#pragma unroll
+            for (int i = 0; i < kNP; ++i) S.Hs[i * kNP + lane] = y[i];
+        }
+        const bool spd = S.spd && __all_sync(0xffffffffu, col_ok);
         __syncwarp();
         {   // rows of 48 doubles, written by the warp
             double* out = kp.result + (size_t)obj * kResultStride;
+            const bool valid = (S.term == mrlm::kConvergence || S.term == mrlm::kNoConvergence);  // IsSolutionUsable
             const bool good = valid && spd;
             for (int i = lane; i < kResultStride; i += 32) {
                 double v = 0.0;
-                if (i < kNP) v = x[i];
-                else if (i < kNP + kNP * kNP) v = good ? wk.Hs[i - kNP] : (((i - kNP) % (kNP + 1) == 0) ? 1.0 : 0.0);
+                if (i < kNP) v = S.best[i];
+                else if (i < kNP + kNP * kNP) v = good ? S.Hs[i - kNP] : (((i - kNP) % (kNP + 1) == 0) ? 1.0 : 0.0);
                 else if (i == 42) v = good ? 1.0 : 0.0;   // Covariance::Compute failing clears result_val (cpp:287)
-                else if (i == 43) v = r.iterations;
-                else if (i == 44) v = r.final_cost;
-                else if (i == 45) v = r.cost_evals;
-                else if (i == 46) v = r.term;
+                else if (i == 43) v = S.iterations;
+                else if (i == 44) v = S.final_cost;
+                else if (i == 45) v = S.cost_evals;
+                else if (i == 46) v = S.term;
                 out[i] = v;
             }
         }
