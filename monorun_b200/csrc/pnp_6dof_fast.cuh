@@ -34,10 +34,10 @@ __host__ __device__ inline int mixed_weight_bytes(int wkind) { return wkind == k
 #define MR6_MIX_UNROLL 1   // 2 measured 4 % slower (instruction cache; profiles/r02_6dof.txt)
 #endif
 constexpr int kMixUnroll = MR6_MIX_UNROLL;
-#ifndef MR6_STAGE_UNROLL
-#define MR6_STAGE_UNROLL 4   // rows of loads in flight while compacting; 8 measured no faster
+#ifndef MR6_STAGE_ROWS
+#define MR6_STAGE_ROWS 5
 #endif
-constexpr int kStageUnroll = MR6_STAGE_UNROLL;
+constexpr int kStageRows = MR6_STAGE_ROWS;
 
 struct StashEntry {
     double x[kNP];
@@ -149,30 +149,42 @@ struct MixedPass {
         float* swf = slot_w + 5 * cap;
         double* swd = reinterpret_cast<double*>(slot_w + 5 * cap);
         int count = 0;
-#pragma unroll kStageUnroll
-        for (int base = 0; base < kp.n_pts; base += 32) {
-            const int p = base + lane;
-            const bool in = p < kp.n_pts;
-            const int q = in ? p : 0;
-            // the loads do not wait for the mask: four rows of them are in flight
-            const float X = at(c3, 0, 3, q), Y = at(c3, 1, 3, q), Z = at(c3, 2, 3, q), u = at(c2, 0, 2, q), v = at(c2, 1, 2, q);
-            const float w0 = at(cw, 0, wc, q), w1 = at(cw, 1, wc, q), w2 = FULLW ? at(cw, 2, wc, q) : 0.f;
-            bool on = in;
-            if (mask) on = on && ((__ldg(mask + (base >> 5)) >> lane) & 1u);
-            const unsigned m = __ballot_sync(0xffffffffu, on);
-            if (on) {
-                const int j = count + __popc(m & ((1u << lane) - 1u));
-                sx[j] = X; sy[j] = Y; sz[j] = Z; su[j] = u; sv[j] = v;
-                if (WKIND == kWLogstd) {
-                    swd[j] = exp(-(double)w0) / kp.std_scale;
-                    swd[cap + j] = exp(-(double)w1) / kp.std_scale;
-                } else {
-                    swf[j] = w0;
-                    swf[cap + j] = w1;
-                    if (FULLW) swf[2 * cap + j] = w2;
-                }
+        // kStageRows rows of 32 points per round: all their loads are issued before the first ballot (the compiler does not
+        // move loads across the warp votes by itself, and one row per round left the compaction waiting on memory 25 times
+        // per object)
+        for (int base0 = 0; base0 < kp.n_pts; base0 += 32 * kStageRows) {
+            float X[kStageRows], Y[kStageRows], Z[kStageRows], u[kStageRows], v[kStageRows], w0[kStageRows], w1[kStageRows],
+                w2[kStageRows];
+            unsigned bits[kStageRows];
+#pragma unroll
+            for (int r = 0; r < kStageRows; ++r) {
+                const int p = base0 + 32 * r + lane;
+                const bool in = p < kp.n_pts;
+                const int q = in ? p : 0;
+                X[r] = at(c3, 0, 3, q); Y[r] = at(c3, 1, 3, q); Z[r] = at(c3, 2, 3, q);
+                u[r] = at(c2, 0, 2, q); v[r] = at(c2, 1, 2, q);
+                w0[r] = at(cw, 0, wc, q); w1[r] = at(cw, 1, wc, q); w2[r] = FULLW ? at(cw, 2, wc, q) : 0.f;
+                const bool row = base0 + 32 * r < kp.n_pts;
+                bits[r] = !row ? 0u : (mask ? __ldg(mask + ((base0 >> 5) + r)) : 0xffffffffu);
             }
-            count += __popc(m);
+#pragma unroll
+            for (int r = 0; r < kStageRows; ++r) {
+                const bool on = (base0 + 32 * r + lane < kp.n_pts) && ((bits[r] >> lane) & 1u);
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                    const int j = count + __popc(m & ((1u << lane) - 1u));
+                    sx[j] = X[r]; sy[j] = Y[r]; sz[j] = Z[r]; su[j] = u[r]; sv[j] = v[r];
+                    if (WKIND == kWLogstd) {
+                        swd[j] = exp(-(double)w0[r]) / kp.std_scale;
+                        swd[cap + j] = exp(-(double)w1[r]) / kp.std_scale;
+                    } else {
+                        swf[j] = w0[r];
+                        swf[cap + j] = w1[r];
+                        if (FULLW) swf[2 * cap + j] = w2[r];
+                    }
+                }
+                count += __popc(m);
+            }
         }
         __syncwarp();
         return count;
@@ -426,6 +438,20 @@ __global__ void __launch_bounds__(kMixMaxWarps * 32, 1) pnp_6dof_mixed_kernel(co
         if (lane == 0) obj = atomicAdd(counters, 1);
         obj = __shfl_sync(0xffffffffu, obj, 0);
         if (obj >= kp.n_obj) break;
+#ifndef MR6_EXP_NO_PREFETCH
+        {   // the object one generation of warps ahead: into L2 now, so that whoever claims it compacts from L2 instead of HBM
+            const int ahead = obj + (int)gridDim.x * (int)(blockDim.x >> 5);
+            if (ahead < kp.n_obj) {
+                constexpr int wc = WKIND == kWFull ? 3 : 2;
+                const char* b3 = reinterpret_cast<const char*>(kp.coords_3d + (size_t)ahead * 3 * kp.n_pts);
+                const char* b2 = reinterpret_cast<const char*>(kp.coords_2d + (size_t)ahead * 2 * kp.n_pts);
+                const char* bw = reinterpret_cast<const char*>(kp.weights + (size_t)ahead * wc * kp.n_pts);
+                for (int off = lane * 128; off < 12 * kp.n_pts; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b3 + off));
+                for (int off = lane * 128; off < 8 * kp.n_pts; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + off));
+                for (int off = lane * 128; off < 4 * wc * kp.n_pts; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(bw + off));
+            }
+        }
+#endif
         const float* K = kp.cam_mats + (size_t)obj * kp.cam_stride;
         const float* rg = kp.uv_range + (size_t)obj * kp.range_stride;
         pass.cam.fx = K[0]; pass.cam.fy = K[4]; pass.cam.cx = K[2]; pass.cam.cy = K[5];
