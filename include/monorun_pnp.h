@@ -317,7 +317,9 @@ int mrpnp_exact_hessian(mrpnp_ctx* ctx, const mrpnp_params* p,
  * (its rotation vector is (0, yaw, 0), pnp_uncert_cpu.cpp:28; `use_6dof` is never read, pnp_uncert.py:11,98,122,142),
  * so this entry has no reference interface to replace: PnPUncert(use_6dof=True).forward_6dof calls it.
  * Uses p->n_obj, n_pts, layout, weight_mode (any MRPNP_W_*), cam_stride, range_stride, z_min, std_scale,
- * max_iterations.  Tensors as mrpnp_solve; init_pose6 [N,6] float (e.g. (0, yaw, 0, t) from mrpnp_solve);
+ * max_iterations, precision: MRPNP_PREC_FP64 -- everything in fp64 (pnp_6dof.cuh); MRPNP_PREC_MIXED or _FAST -- the
+ * correspondences staged once in shared memory, fp64 cost chain, fp32 Jacobian and normal equations, the same Ceres
+ * decisions (pnp_6dof_fast.cuh; 3-4 x faster, pose within ~5e-7 of the fp64 kernel, covariance within ~3e-4).  Tensors as mrpnp_solve; init_pose6 [N,6] float (e.g. (0, yaw, 0, t) from mrpnp_solve);
  * inlier_in packed mask or NULL (all points).
  *   result [N,48] DOUBLE: rvec(3), t(3) | cov 6x6 row-major | valid, lm_iterations, final_cost, cost_evals,
  *   termination, pad. */
