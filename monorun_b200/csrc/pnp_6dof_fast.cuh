@@ -25,20 +25,6 @@
 
 namespace mr6 {
 
-#ifdef __CUDACC__
-
-constexpr int kMixMaxWarps = 8;
-enum { kWLogstd = 0, kWIstd = 1, kWFull = 2 };   // = MRPNP_W_*
-__host__ __device__ inline int mixed_weight_bytes(int wkind) { return wkind == kWFull ? 12 : wkind == kWIstd ? 8 : 16; }
-#ifndef MR6_MIX_UNROLL
-#define MR6_MIX_UNROLL 1   // 2 measured 4 % slower (instruction cache; profiles/r02_6dof.txt)
-#endif
-constexpr int kMixUnroll = MR6_MIX_UNROLL;
-#ifndef MR6_STAGE_ROWS
-#define MR6_STAGE_ROWS 5
-#endif
-constexpr int kStageRows = MR6_STAGE_ROWS;
-
 struct StashEntry {
     double x[kNP];
     double cost;
@@ -60,6 +46,150 @@ struct LMState {
     int cmd, spd, need_final;
     mrlm::LMOptions opt;
 };
+
+// mrlm::minimize (lm_dense.cuh) from one cost evaluation to the next: `first` -- the totals of the start point are in
+// stash[cur]; otherwise the candidate S.cand has just been evaluated into stash[cur ^ 1].  Returns kCmdEvaluate with the
+// next candidate in S.cand, or kCmdDone with S.best / S.term / S.iterations / S.final_cost / S.cost_evals set as
+// minimize() returns them.  Same statements in the same order as minimize(); the Jacobian evaluation after an accepted
+// step is the candidate's stash entry.  Lane 0 only.
+// Host-compilable: tests/harness/sixdof_host_harness.cpp runs it against mrlm::minimize on identical numbers (bit-equal).
+MRLM_HD_NOINLINE int lm_advance(LMState& S, const StashEntry* stash, bool first) {
+    constexpr int NP = kNP;
+    const mrlm::LMOptions& opt = S.opt;
+    auto fetch = [&](int e) {
+        S.acc[0] = stash[e].cost;
+#pragma unroll
+        for (int i = 0; i < kNAcc - 1; ++i) S.acc[1 + i] = (double)stash[e].tot[i];
+    };
+    auto load_point = [&](bool initial) {
+        S.x_cost = S.acc[0];
+        S.gradient_max_norm = 0.0;
+        for (int k = 0; k < NP; ++k) {
+            S.grad[k] = S.acc[kAccG + k];
+            S.gradient_max_norm = fmax(S.gradient_max_norm, fabs(S.grad[k]));
+        }
+        if (initial)
+            for (int k = 0; k < NP; ++k) S.scale[k] = 1.0 / (1.0 + sqrt(S.acc[kAccH + mrlm::tri<NP>(k, k)]));
+        for (int a = 0; a < NP; ++a) {
+            S.bs[a] = S.scale[a] * S.grad[a];
+            for (int b = a; b < NP; ++b) {
+                const double h = S.acc[kAccH + mrlm::tri<NP>(a, b)] * S.scale[a] * S.scale[b];
+                S.Hs[a * NP + b] = h;
+                S.Hs[b * NP + a] = h;
+            }
+        }
+        S.x_norm = 0.0;
+        for (int k = 0; k < NP; ++k) S.x_norm += S.x[k] * S.x[k];
+        S.x_norm = sqrt(S.x_norm);
+    };
+    bool finished = false;
+    if (first) {
+        S.radius = opt.initial_radius; S.decrease_factor = 2.0; S.reuse_diagonal = 0; S.num_invalid = 0;
+        S.minimum_cost = 1.7976931348623157e308;
+        S.term = mrlm::kFailure; S.iterations = 0; S.cost_evals = 1; S.jac_evals = 1; S.final_cost = 0.0;
+        for (int k = 0; k < NP; ++k) S.best[k] = S.x[k];
+        fetch(S.cur);
+        if (!mrlm::all_finite(S.acc, kNAcc)) { S.final_cost = S.acc[0]; return kCmdDone; }
+        load_point(true);
+        S.iteration = 0; S.step_is_successful = 1; S.term = mrlm::kNoConvergence;
+    } else {
+        S.cost_evals++;
+        const double c = stash[S.cur ^ 1].cost;
+        const double cand_cost = isfinite(c) ? c : 1.7976931348623157e308;
+        const double cost_change = S.x_cost - cand_cost;
+        if (S.step_norm <= opt.parameter_tolerance * (S.x_norm + opt.parameter_tolerance)) {
+            S.term = mrlm::kConvergence; finished = true;
+        } else if (fabs(cost_change) <= opt.function_tolerance * S.x_cost) {
+            S.term = mrlm::kConvergence; finished = true;
+        } else {
+            const double relative_decrease = cost_change / S.model_cost_change;
+            if (relative_decrease > opt.min_relative_decrease) {  // HandleSuccessfulStep
+                for (int k = 0; k < NP; ++k) S.x[k] = S.cand[k];
+                S.cur ^= 1;
+                fetch(S.cur);
+                S.jac_evals++;
+                if (!mrlm::all_finite(S.acc, kNAcc)) {
+                    S.term = mrlm::kFailure; finished = true;
+                } else {
+                    load_point(false);
+                    S.step_is_successful = 1;
+                    const double q = 2.0 * relative_decrease - 1.0;  // LevenbergMarquardtStrategy::StepAccepted
+                    S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+                    S.radius = fmin(opt.max_radius, S.radius);
+                    S.decrease_factor = 2.0;
+                    S.reuse_diagonal = 0;
+                }
+            } else {  // StepRejected
+                S.radius /= S.decrease_factor; S.decrease_factor *= 2.0;
+            }
+        }
+    }
+    while (!finished) {
+        if (S.step_is_successful && S.x_cost < S.minimum_cost) {
+            S.minimum_cost = S.x_cost;
+            for (int k = 0; k < NP; ++k) S.best[k] = S.x[k];
+        }
+        S.iterations = S.iteration;
+        if (S.iteration >= opt.max_num_iterations) { S.term = mrlm::kNoConvergence; break; }
+        if (S.step_is_successful && S.gradient_max_norm <= opt.gradient_tolerance) { S.term = mrlm::kConvergence; break; }
+        if (S.radius <= opt.min_radius) { S.term = mrlm::kConvergence; break; }
+        ++S.iteration;
+        S.step_is_successful = 0;
+
+        // LevenbergMarquardtStrategy::ComputeStep
+        if (!S.reuse_diagonal)
+            for (int k = 0; k < NP; ++k)
+                S.diag[k] = fmin(fmax(S.Hs[k * NP + k], opt.min_lm_diagonal), opt.max_lm_diagonal);
+        for (int i = 0; i < NP * NP; ++i) S.A[i] = S.Hs[i];
+        for (int k = 0; k < NP; ++k) S.A[k * NP + k] += S.diag[k] / S.radius;
+        const bool solved = mrlm::cholesky_factor<NP>(S.A, S.L) && mrlm::cholesky_backsolve<NP>(S.L, S.bs, S.step, S.z);
+        S.reuse_diagonal = 1;
+        bool step_is_valid = false;
+        S.model_cost_change = 0.0;
+        if (solved) {
+            double lin = 0.0, quad = 0.0;  // -(J s)^T (r + J s / 2) with s = -y
+            for (int a = 0; a < NP; ++a) S.step[a] = -S.step[a];
+            for (int a = 0; a < NP; ++a) {
+                double hs = 0.0;
+                for (int b = 0; b < NP; ++b) hs += S.Hs[a * NP + b] * S.step[b];
+                lin += S.step[a] * S.bs[a];
+                quad += S.step[a] * hs;
+            }
+            S.model_cost_change = -(lin + 0.5 * quad);
+            step_is_valid = S.model_cost_change > 0.0;
+        }
+        if (!step_is_valid) {  // HandleInvalidStep
+            if (++S.num_invalid >= opt.max_consecutive_invalid) { S.term = mrlm::kFailure; break; }
+            S.radius /= S.decrease_factor; S.decrease_factor *= 2.0;
+            continue;
+        }
+        S.num_invalid = 0;
+        double step_norm = 0.0;
+        for (int k = 0; k < NP; ++k) {
+            S.delta[k] = S.step[k] * S.scale[k];
+            S.cand[k] = S.x[k] + S.delta[k];
+            step_norm += S.delta[k] * S.delta[k];
+        }
+        S.step_norm = sqrt(step_norm);
+        return kCmdEvaluate;
+    }
+    S.final_cost = S.minimum_cost;
+    return kCmdDone;
+}
+
+#ifdef __CUDACC__
+
+constexpr int kMixMaxWarps = 8;
+enum { kWLogstd = 0, kWIstd = 1, kWFull = 2 };   // = MRPNP_W_*
+__host__ __device__ inline int mixed_weight_bytes(int wkind) { return wkind == kWFull ? 12 : wkind == kWIstd ? 8 : 16; }
+#ifndef MR6_MIX_UNROLL
+#define MR6_MIX_UNROLL 1   // 2 measured 4 % slower (instruction cache; profiles/r02_6dof.txt)
+#endif
+constexpr int kMixUnroll = MR6_MIX_UNROLL;
+#ifndef MR6_STAGE_ROWS
+#define MR6_STAGE_ROWS 5
+#endif
+constexpr int kStageRows = MR6_STAGE_ROWS;
 
 struct WarpArea {   // per warp, in front of the point planes
     StashEntry stash[2];
@@ -285,135 +415,6 @@ struct MixedPass {
         __syncwarp();
     }
 };
-
-// mrlm::minimize (lm_dense.cuh) from one cost evaluation to the next: `first` -- the totals of the start point are in
-// stash[cur]; otherwise the candidate S.cand has just been evaluated into stash[cur ^ 1].  Returns kCmdEvaluate with the
-// next candidate in S.cand, or kCmdDone with S.best / S.term / S.iterations / S.final_cost / S.cost_evals set as
-// minimize() returns them.  Same statements in the same order as minimize(); the Jacobian evaluation after an accepted
-// step is the candidate's stash entry.  Lane 0 only.
-__device__ __noinline__ int lm_advance(LMState& S, const StashEntry* stash, bool first) {
-    constexpr int NP = kNP;
-    const mrlm::LMOptions& opt = S.opt;
-    auto fetch = [&](int e) {
-        S.acc[0] = stash[e].cost;
-#pragma unroll
-        for (int i = 0; i < kNAcc - 1; ++i) S.acc[1 + i] = (double)stash[e].tot[i];
-    };
-    auto load_point = [&](bool initial) {
-        S.x_cost = S.acc[0];
-        S.gradient_max_norm = 0.0;
-        for (int k = 0; k < NP; ++k) {
-            S.grad[k] = S.acc[kAccG + k];
-            S.gradient_max_norm = fmax(S.gradient_max_norm, fabs(S.grad[k]));
-        }
-        if (initial)
-            for (int k = 0; k < NP; ++k) S.scale[k] = 1.0 / (1.0 + sqrt(S.acc[kAccH + mrlm::tri<NP>(k, k)]));
-        for (int a = 0; a < NP; ++a) {
-            S.bs[a] = S.scale[a] * S.grad[a];
-            for (int b = a; b < NP; ++b) {
-                const double h = S.acc[kAccH + mrlm::tri<NP>(a, b)] * S.scale[a] * S.scale[b];
-                S.Hs[a * NP + b] = h;
-                S.Hs[b * NP + a] = h;
-            }
-        }
-        S.x_norm = 0.0;
-        for (int k = 0; k < NP; ++k) S.x_norm += S.x[k] * S.x[k];
-        S.x_norm = sqrt(S.x_norm);
-    };
-    bool finished = false;
-    if (first) {
-        S.radius = opt.initial_radius; S.decrease_factor = 2.0; S.reuse_diagonal = 0; S.num_invalid = 0;
-        S.minimum_cost = 1.7976931348623157e308;
-        S.term = mrlm::kFailure; S.iterations = 0; S.cost_evals = 1; S.jac_evals = 1; S.final_cost = 0.0;
-        for (int k = 0; k < NP; ++k) S.best[k] = S.x[k];
-        fetch(S.cur);
-        if (!mrlm::all_finite(S.acc, kNAcc)) { S.final_cost = S.acc[0]; return kCmdDone; }
-        load_point(true);
-        S.iteration = 0; S.step_is_successful = 1; S.term = mrlm::kNoConvergence;
-    } else {
-        S.cost_evals++;
-        const double c = stash[S.cur ^ 1].cost;
-        const double cand_cost = isfinite(c) ? c : 1.7976931348623157e308;
-        const double cost_change = S.x_cost - cand_cost;
-        if (S.step_norm <= opt.parameter_tolerance * (S.x_norm + opt.parameter_tolerance)) {
-            S.term = mrlm::kConvergence; finished = true;
-        } else if (fabs(cost_change) <= opt.function_tolerance * S.x_cost) {
-            S.term = mrlm::kConvergence; finished = true;
-        } else {
-            const double relative_decrease = cost_change / S.model_cost_change;
-            if (relative_decrease > opt.min_relative_decrease) {  // HandleSuccessfulStep
-                for (int k = 0; k < NP; ++k) S.x[k] = S.cand[k];
-                S.cur ^= 1;
-                fetch(S.cur);
-                S.jac_evals++;
-                if (!mrlm::all_finite(S.acc, kNAcc)) {
-                    S.term = mrlm::kFailure; finished = true;
-                } else {
-                    load_point(false);
-                    S.step_is_successful = 1;
-                    const double q = 2.0 * relative_decrease - 1.0;  // LevenbergMarquardtStrategy::StepAccepted
-                    S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
-                    S.radius = fmin(opt.max_radius, S.radius);
-                    S.decrease_factor = 2.0;
-                    S.reuse_diagonal = 0;
-                }
-            } else {  // StepRejected
-                S.radius /= S.decrease_factor; S.decrease_factor *= 2.0;
-            }
-        }
-    }
-    while (!finished) {
-        if (S.step_is_successful && S.x_cost < S.minimum_cost) {
-            S.minimum_cost = S.x_cost;
-            for (int k = 0; k < NP; ++k) S.best[k] = S.x[k];
-        }
-        S.iterations = S.iteration;
-        if (S.iteration >= opt.max_num_iterations) { S.term = mrlm::kNoConvergence; break; }
-        if (S.step_is_successful && S.gradient_max_norm <= opt.gradient_tolerance) { S.term = mrlm::kConvergence; break; }
-        if (S.radius <= opt.min_radius) { S.term = mrlm::kConvergence; break; }
-        ++S.iteration;
-        S.step_is_successful = 0;
-
-        // LevenbergMarquardtStrategy::ComputeStep
-        if (!S.reuse_diagonal)
-            for (int k = 0; k < NP; ++k)
-                S.diag[k] = fmin(fmax(S.Hs[k * NP + k], opt.min_lm_diagonal), opt.max_lm_diagonal);
-        for (int i = 0; i < NP * NP; ++i) S.A[i] = S.Hs[i];
-        for (int k = 0; k < NP; ++k) S.A[k * NP + k] += S.diag[k] / S.radius;
-        const bool solved = mrlm::cholesky_factor<NP>(S.A, S.L) && mrlm::cholesky_backsolve<NP>(S.L, S.bs, S.step, S.z);
-        S.reuse_diagonal = 1;
-        bool step_is_valid = false;
-        S.model_cost_change = 0.0;
-        if (solved) {
-            double lin = 0.0, quad = 0.0;  // -(J s)^T (r + J s / 2) with s = -y
-            for (int a = 0; a < NP; ++a) S.step[a] = -S.step[a];
-            for (int a = 0; a < NP; ++a) {
-                double hs = 0.0;
-                for (int b = 0; b < NP; ++b) hs += S.Hs[a * NP + b] * S.step[b];
-                lin += S.step[a] * S.bs[a];
-                quad += S.step[a] * hs;
-            }
-            S.model_cost_change = -(lin + 0.5 * quad);
-            step_is_valid = S.model_cost_change > 0.0;
-        }
-        if (!step_is_valid) {  // HandleInvalidStep
-            if (++S.num_invalid >= opt.max_consecutive_invalid) { S.term = mrlm::kFailure; break; }
-            S.radius /= S.decrease_factor; S.decrease_factor *= 2.0;
-            continue;
-        }
-        S.num_invalid = 0;
-        double step_norm = 0.0;
-        for (int k = 0; k < NP; ++k) {
-            S.delta[k] = S.step[k] * S.scale[k];
-            S.cand[k] = S.x[k] + S.delta[k];
-            step_norm += S.delta[k] * S.delta[k];
-        }
-        S.step_norm = sqrt(step_norm);
-        return kCmdEvaluate;
-    }
-    S.final_cost = S.minimum_cost;
-    return kCmdDone;
-}
 
 template <int WKIND>
 __global__ void __launch_bounds__(kMixMaxWarps * 32, 1) pnp_6dof_mixed_kernel(const KParams kp, int* counters, int slot_bytes) {

@@ -26,7 +26,7 @@ def sd():
 @pytest.fixture(scope='session')
 def harness6():
     src = os.path.join(HERE, 'harness', 'sixdof_host_harness.cpp')
-    hdrs = [os.path.join(ROOT, 'monorun_b200', 'csrc', f) for f in ('pnp_6dof.cuh', 'lm_dense.cuh')]
+    hdrs = [os.path.join(ROOT, 'monorun_b200', 'csrc', f) for f in ('pnp_6dof.cuh', 'pnp_6dof_fast.cuh', 'lm_dense.cuh')]
     out = os.path.join(HERE, 'harness', 'libsixdof_host_harness.so')
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.check_call(['/usr/bin/g++', '-O2', '-fPIC', '-std=c++17', '-Wno-unknown-pragmas', '-shared',
@@ -140,3 +140,33 @@ def test_kernel_logic_first_order_branch_and_masks(sd, harness6):
     same = h[:, 45] == r['stats'][:, 1]
     assert same.mean() >= 0.9 and r['val'].all()
     np.testing.assert_allclose(h[same, :6], r['pose'][same], rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.parametrize('full', [False, True])
+def test_mixed_kernel_controller_is_minimize_cut_at_the_evaluation(harness6, full):
+    """mr6::lm_advance (the mixed 6-DoF kernel's controller, run by lane 0 between evaluations) against mrlm::minimize on
+    identical numbers -- fp64 cost, the 27 sums rounded to fp32 as the kernel's stash holds them: bit-equal pose, cost,
+    iteration and evaluation counts and termination, near and far starts, masked and not, plus a start that fails
+    (non-finite) and one that converges at once."""
+    for far, masked in ((False, False), (True, False), (True, True)):
+        n = 48
+        c = make_case(n, full=full, far=far, seed=5)
+        p = c['c3'].shape[1]
+        init = np.ascontiguousarray(c['init'], np.float32).copy()
+        init[0, 5] = np.nan                      # first evaluation not finite: FAILURE, pose returned untouched
+        init[1] = c['gt'][1].astype(np.float32)  # (nearly) at the minimum
+        mask = None
+        if masked:
+            rng = np.random.default_rng(3)
+            mask = np.ascontiguousarray(rng.uniform(size=(n, p)) < rng.uniform(0.2, 1.0, (n, 1)), np.uint8)
+        a, b = np.zeros((n, 10)), np.zeros((n, 11))
+        fp = lambda x: x.ctypes.data_as(ctypes.c_void_p) if x is not None else None
+        harness6.sixdof_controller_harness(fp(c['c3']), fp(c['c2']), fp(c['w']), fp(mask),
+                                           fp(np.ascontiguousarray(c['cam'].reshape(-1, 9))), fp(c['uv_range']), fp(init), n, p,
+                                           int(full), ctypes.c_double(0.5), fp(a), fp(b))
+        np.testing.assert_array_equal(a[2:], b[2:, :10])
+        np.testing.assert_array_equal(a[0, 6:], b[0, 6:10])          # NaN pose: compare the rest
+        assert a[0, 9] == 2 and np.isnan(b[0, 5])                    # mrlm::kFailure
+        np.testing.assert_array_equal(a[1], b[1, :10])
+        assert (b[1:, 10] == 1).all()                                # returned pose = current stash entry
+        assert (a[2:, 8] >= 3).all() and (a[2:, 9] == 0).all()       # real solves, all converged
