@@ -242,6 +242,7 @@ def main():
                     help='N > 1: result rows by peer-to-peer stores from the kernel + symmetric-memory barrier, or NCCL all-gather')
     ap.add_argument('--large-batch', type=int, default=4,
                     help='N=1: also time one launch over this many concatenated batches (details.large_batch); 0/1 = skip')
+    ap.add_argument('--no-sixdof', action='store_true', help='N=1: skip the 6-DoF leg (details.six_dof)')
     ap.add_argument('--total-objects', type=int, default=0,
                     help='strong scaling (BASELINE configs[4]: 65536): this many objects in total, split over the GPUs; '
                          'default 0 = 8192 objects per GPU (weak scaling)')
@@ -437,6 +438,33 @@ def main():
                  'hbm_roofline_frac': ALG_BYTES[args.workload] * reps * n_local / (lus * 1e-6) / 1e9 / measured_peak()[0]}
         del cat
 
+    # ---- (1c) the 6-DoF extension (the north star's wording; the reference solves 4 DoF) on the same correspondences,
+    #      started from (0, yaw, 0, t): mixed kernel, every point used (informative, not the headline) ----
+    six = None
+    if world == 1 and not args.total_objects and not args.no_sixdof:
+        try:
+            d = dsets[0]
+            zero = torch.zeros_like(d['init'][:, :1])
+            init6 = torch.cat([zero, d['init'][:, :1], zero, d['init'][:, 1:4]], 1).contiguous()
+            run6 = lambda: pnp.solve_6dof_batched(d['c3'], d['c2'], d['w'], d['cam'], d['rng'], init6, layout='planar',
+                                                  weight_mode='full' if full else 'logstd', precision='mixed')
+            for _ in range(2):
+                r6 = run6()
+            fence()
+            sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+            for a, b in sev:
+                a.record()
+                r6 = run6()
+                b.record()
+            fence()
+            sus = float(np.mean([1e3 * a.elapsed_time(b) for a, b in sev]))
+            six = {'kernel': 'mr6::pnp_6dof_mixed_kernel (fp64 cost chain, fp32 normal equations)', 'objects_per_launch': n_local,
+                   'us_per_launch': sus, 'objects_per_s': n_local / (sus * 1e-6),
+                   'valid_fraction': float((r6[:, 42] > 0).double().mean()), 'mean_cost_evaluations': float(r6[:, 45].mean()),
+                   'hbm_roofline_frac': ALG_BYTES[args.workload] * n_local / (sus * 1e-6) / 1e9 / measured_peak()[0]}
+        except Exception as exc:  # informative leg: never take the headline down with it
+            six = {'error': f'{type(exc).__name__}: {exc}'[:300]}
+
     # ---- (2) device-resident throughput: exactly K steps between fences.  Consecutive steps are independent
     #      batches, so they alternate between `--streams` CUDA streams: the ramp-down of one persistent launch (a
     #      few long Levenberg-Marquardt runs on otherwise idle SMs) overlaps the ramp-up of the next one. ----
@@ -548,6 +576,7 @@ def main():
             'streams': nstreams, 'serialized_ms_per_step': kernel_ms,
             'serialized_us_per_launch': [round(v, 1) for v in kernel_us],
             'large_batch': large,
+            'six_dof': six,
             'parallelism': f'objects sharded contiguously over {world} GPU(s)' + (
                 '' if world == 1 else (', result rows stored peer-to-peer into every rank\'s symmetric buffer by the kernel; completion flags '
                                        f'raised by the kernel, waited for {lag} step(s) later on the same stream (1 one-warp launch per step)'
