@@ -25,6 +25,14 @@
 
 namespace mr6 {
 
+// The per-warp areas live in shared memory; functions that receive them by pointer (not inlined into the kernel) would use
+// generic loads and stores with 64-bit address arithmetic.  MR6_NO_ASSUME_SHARED builds without the hint.
+#if defined(__CUDA_ARCH__) && !defined(MR6_NO_ASSUME_SHARED)
+#define MR6_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define MR6_ASSUME_SHARED(p) ((void)0)
+#endif
+
 struct StashEntry {
     double x[kNP];
     double cost;
@@ -55,6 +63,8 @@ struct LMState {
 // Host-compilable: tests/harness/sixdof_host_harness.cpp runs it against mrlm::minimize on identical numbers (bit-equal).
 MRLM_HD_NOINLINE int lm_advance(LMState& S, const StashEntry* stash, bool first) {
     constexpr int NP = kNP;
+    MR6_ASSUME_SHARED(&S);
+    MR6_ASSUME_SHARED(stash);
     const mrlm::LMOptions& opt = S.opt;
     auto fetch = [&](int e) {
         S.acc[0] = stash[e].cost;
@@ -219,6 +229,8 @@ __device__ __forceinline__ float warp_reduce32_scatter(float v[32], int lane) {
 // make_pose with one reciprocal instead of 27 divisions in the rotation derivatives (they only feed the fp32 Jacobian here);
 // R and t are computed by the same expressions as in make_pose, so the cost chain sees identical numbers.
 __device__ __noinline__ void make_pose_fast(const double* x, Pose6* p) {
+    MR6_ASSUME_SHARED(p);
+    MR6_ASSUME_SHARED(x);
     const double w[3] = {x[0], x[1], x[2]};
     const double theta2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
     p->t[0] = x[3]; p->t[1] = x[4]; p->t[2] = x[5];
@@ -341,6 +353,9 @@ struct MixedPass {
         for (int i = 0; i < kNAcc - 1; ++i) a2[i] = make_float2(0.f, 0.f);
         double cost = 0.0;
         const int cap_ = cap, n_ = n;
+        MR6_ASSUME_SHARED(slot);   // LDS instead of generic loads: 19 of the loop's 209 instructions
+        MR6_ASSUME_SHARED(area);
+        MR6_ASSUME_SHARED(x);
         const float *sx = slot, *sy = slot + cap_, *sz = slot + 2 * cap_, *su = slot + 3 * cap_, *sv = slot + 4 * cap_;
         const float* swf = slot + 5 * cap_;
         const double* swd = reinterpret_cast<const double*>(slot + 5 * cap_);
