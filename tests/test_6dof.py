@@ -170,3 +170,20 @@ def test_mixed_kernel_controller_is_minimize_cut_at_the_evaluation(harness6, ful
         np.testing.assert_array_equal(a[1], b[1, :10])
         assert (b[1:, 10] == 1).all()                                # returned pose = current stash entry
         assert (a[2:, 8] >= 3).all() and (a[2:, 9] == 0).all()       # real solves, all converged
+    # wild starts (rotation off by ~1.5 rad, depth scaled 0.3-3x): rejected and invalid steps, shrinking radii, objects that
+    # end far from the minimum or fail -- whatever mrlm::minimize does, lm_advance does the same
+    n = 64
+    c = make_case(n, full=full, far=True, seed=9)
+    p = c['c3'].shape[1]
+    rng = np.random.default_rng(17)
+    init = np.ascontiguousarray(c['init'], np.float32).copy()
+    init[:, :3] += rng.normal(0, 1.5, (n, 3)).astype(np.float32)
+    init[:, 3:] *= rng.uniform(0.3, 3.0, (n, 1)).astype(np.float32)
+    a, b = np.zeros((n, 10)), np.zeros((n, 11))
+    fp = lambda x: x.ctypes.data_as(ctypes.c_void_p) if x is not None else None
+    harness6.sixdof_controller_harness(fp(c['c3']), fp(c['c2']), fp(c['w']), None,
+                                       fp(np.ascontiguousarray(c['cam'].reshape(-1, 9))), fp(c['uv_range']), fp(init), n, p,
+                                       int(full), ctypes.c_double(0.5), fp(a), fp(b))
+    np.testing.assert_array_equal(a, b[:, :10])
+    assert (a[:, 8] > 8).sum() >= n // 4        # long runs are in the sample
+    assert (a[:, 6] + 1 > a[:, 8]).any() or (a[:, 9] != 0).any() or (a[:, 8] > 15).any()
